@@ -1,0 +1,282 @@
+"""
+Generate the golden fixtures in this directory by running the REFERENCE'S OWN CODE in the build container.
+
+    python tests/golden/make_golden.py            # needs /root/reference (read-only); writes tests/golden/*.npz
+
+The reference (jweyn/DLWP @ 3f32bfab) cannot be imported as a package here: ``DLWP/model/__init__.py`` pulls in keras,
+tensorflow, xarray and netCDF4, none of which are installed or installable offline.  Its hot-path modules are therefore
+loaded file by file with stub ``keras`` / ``tensorflow`` modules in ``sys.modules``:
+
+* ``DLWP/custom.py``            -> the real ``PeriodicPadding2D.call`` (custom.py:191-214) and ``row_conv2d`` (840-896)
+                                   run on numpy arrays through a numpy-backed stub of ``keras.backend``;
+* ``DLWP/model/models.py``      -> the real ``DLWPNeuralNet`` / ``DLWPFunctional`` ``predict`` + ``predict_timeseries``
+                                   (230-301, 404-452) run with a duck-typed ``.model``;
+* ``DLWP/model/models_torch.py``-> the real ``DLWPTorchNN`` (77-376) runs end to end on torch-CPU.
+
+Nothing from the reference is copied: only inputs, weights and the arrays the reference code returned are stored.
+This script is never run on the GPU box (``/root/reference`` does not exist there); the committed ``.npz`` files are
+what the tests read.
+"""
+
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('DLWP_REFERENCE', '/root/reference')
+sys.path.insert(0, REPO)
+
+from oracle import layers as OL  # noqa: E402
+from oracle import ops as OO  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------------------------ #
+# Stub third-party modules the reference imports at module level
+# ------------------------------------------------------------------------------------------------------------------ #
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)  # torch._dynamo probes find_spec('tensorflow')
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _StubZeroPadding2D(object):
+    """Just enough of keras.layers.ZeroPadding2D.__init__ (argument normalisation) for PeriodicPadding2D to subclass."""
+
+    def __init__(self, padding=(1, 1), data_format=None, **kwargs):
+        self.data_format = 'channels_last' if data_format is None else data_format
+        if isinstance(padding, int):
+            self.padding = ((padding, padding), (padding, padding))
+        else:
+            pads = []
+            for p in padding:
+                pads.append((p, p) if isinstance(p, int) else tuple(p))
+            self.padding = tuple(pads)
+
+
+class _Any(object):
+    def __init__(self, *a, **k):
+        pass
+
+
+def _np_conv2d(x, kernel, strides=(1, 1), padding='valid', data_format=None):
+    assert padding == 'valid'
+    return OO.conv2d_valid(x, kernel, None, (1, 1), strides, data_format)
+
+
+def install_stubs():
+    K = _mod('keras.backend',
+             backend=lambda: 'numpy',
+             concatenate=lambda xs, axis=-1: np.concatenate(xs, axis=axis),
+             ones=np.ones, zeros=np.zeros,
+             normalize_data_format=lambda v: 'channels_last' if v is None else v,
+             conv2d=_np_conv2d)
+    _mod('keras', backend=K)
+    _mod('keras.callbacks', Callback=_Any, EarlyStopping=_Any)
+    _mod('keras.layers', Lambda=_Any, Layer=_Any)
+    _mod('keras.layers.convolutional', ZeroPadding2D=_StubZeroPadding2D, ZeroPadding3D=_StubZeroPadding2D)
+    _mod('keras.layers.local', LocallyConnected2D=_Any)
+    _mod('keras.losses', mean_absolute_error=None, mean_squared_error=None)
+    _mod('keras.utils', conv_utils=None, multi_gpu_model=None)
+    _mod('keras.engine')
+    _mod('keras.engine.base_layer', InputSpec=_Any)
+    _mod('keras.models')
+    _mod('tensorflow')
+    sys.modules['keras'].layers = sys.modules['keras.layers']
+    sys.modules['keras'].models = sys.modules['keras.models']
+    # parent packages for the relative imports inside the reference files
+    pkg = _mod('DLWP')
+    pkg.__path__ = []
+    mpkg = _mod('DLWP.model')
+    mpkg.__path__ = []
+    _mod('DLWP.model.generators', DataGenerator=type('DataGenerator', (), {}),
+         SmartDataGenerator=type('SmartDataGenerator', (), {}),
+         SeriesDataGenerator=type('SeriesDataGenerator', (), {}))
+
+
+def load_ref(modname, relpath):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------------------------------ #
+
+def gen_periodic_padding(custom):
+    rng = np.random.RandomState(10)
+    out = {}
+    x_cf = rng.standard_normal((2, 3, 5, 7)).astype(np.float32)
+    x_cl = rng.standard_normal((2, 5, 7, 3)).astype(np.float32)
+    out['x_channels_first'] = x_cf
+    out['x_channels_last'] = x_cl
+    pads = [(0, 2), (1, 1), ((1, 2), (3, 0)), 2, ((0, 0), (2, 2)), (2, 0), ((0, 1), (0, 3))]
+    out['n_cases'] = np.int64(len(pads))
+    for k, p in enumerate(pads):
+        out['pad_%d' % k] = np.asarray(OO.normalize_padding(p), np.int64)
+        for fmt, x in (('channels_first', x_cf), ('channels_last', x_cl)):
+            layer = custom.PeriodicPadding2D(padding=p, data_format=fmt)
+            out['y_%d_%s' % (k, fmt)] = layer.call(x)
+    np.savez_compressed(os.path.join(HERE, 'periodic_padding2d.npz'), **out)
+
+
+def gen_row_conv(custom):
+    rng = np.random.RandomState(11)
+    x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
+    kernel = rng.standard_normal((5, 5, 5, 4, 3)).astype(np.float64) * 0.2  # (H_out, kh, kw, Cin, Cout)
+    y = custom.row_conv2d(x, kernel, (5, 5), (1, 1), (5, 8), 'channels_first')
+    x_cl = np.moveaxis(x, 1, 3)
+    y_cl = custom.row_conv2d(x_cl, kernel, (5, 5), (1, 1), (5, 8), 'channels_last')
+    np.savez_compressed(os.path.join(HERE, 'row_conv2d.npz'), x=x, kernel=kernel, y=y, y_channels_last=y_cl)
+
+
+class _FakeKerasModel(object):
+    """Duck-typed stand-in for the compiled keras model: ``predict`` = oracle forward (float64 -> float32)."""
+
+    def __init__(self, net):
+        self.net = net
+        self.outputs = [None] * net.n_outputs
+
+    def predict(self, x, **kwargs):
+        y = self.net.forward(np.asarray(x, np.float64))
+        if isinstance(y, list):
+            return [v.astype(np.float32) for v in y]
+        return y.astype(np.float32)
+
+
+def _small_seq(time_dim, nvar, H, W, seed):
+    cf = 'channels_first'
+    C = time_dim * nvar
+    net = OL.OSequential((
+        ('PeriodicPadding2D', ((0, 1),), {'data_format': cf, 'input_shape': (C, H, W)}),
+        ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+        ('Conv2D', (8, 3), {'activation': 'tanh', 'data_format': cf}),
+        ('PeriodicPadding2D', ((0, 2),), {'data_format': cf}),
+        ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+        ('Conv2D', (C, 3), {'dilation_rate': 2, 'activation': 'linear', 'data_format': cf}),
+    ))
+    OL.init_weights(net.conv_layers, seed=seed, bias_scale=0.1)
+    return net
+
+
+def gen_rollout_neuralnet(models):
+    out = {}
+    rng = np.random.RandomState(12)
+    cases = []
+    for time_dim in (1, 2, 3):
+        net = _small_seq(time_dim, 2, 6, 8, seed=20 + time_dim)
+        x0 = rng.standard_normal((3, time_dim * 2, 6, 8)).astype(np.float32)
+        out['x0_td%d' % time_dim] = x0
+        for k, w in enumerate(net.get_weights()):
+            out['w_td%d_%d' % (time_dim, k)] = w
+        dlwp = models.DLWPNeuralNet(is_convolutional=True, is_recurrent=False, time_dim=time_dim, scaler_type=None,
+                                    scale_targets=False)
+        dlwp.model = _FakeKerasModel(net)
+        for steps in (1, 5):
+            for ss in (False, True):
+                for ktd in (False, True):
+                    key = 'y_td%d_s%d_ss%d_k%d' % (time_dim, steps, ss, ktd)
+                    out[key] = dlwp.predict_timeseries(x0, steps, step_sequence=ss, keep_time_dim=ktd)
+                    cases.append(key)
+    out['cases'] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, 'rollout_neuralnet.npz'), **out)
+
+
+class _SmallUnrolled(object):
+    """A shared-weight net unrolled n times, like examples/train_functional.py:278-281, on top of an OSequential."""
+
+    def __init__(self, net, n):
+        self.net, self.n_outputs = net, n
+
+    def forward(self, x):
+        outs = [self.net.forward(x)]
+        for _ in range(1, self.n_outputs):
+            outs.append(self.net.forward(outs[-1]))
+        return outs[0] if self.n_outputs == 1 else outs
+
+
+def gen_rollout_functional(models):
+    out = {}
+    rng = np.random.RandomState(13)
+    cases = []
+    for time_dim in (1, 2):
+        net = _small_seq(time_dim, 2, 6, 8, seed=30 + time_dim)
+        x0 = rng.standard_normal((3, time_dim * 2, 6, 8)).astype(np.float32)
+        out['x0_td%d' % time_dim] = x0
+        for k, w in enumerate(net.get_weights()):
+            out['w_td%d_%d' % (time_dim, k)] = w
+        for n_steps in (1, 3):
+            dlwp = models.DLWPFunctional(is_convolutional=True, is_recurrent=False, time_dim=time_dim)
+            dlwp.model = _FakeKerasModel(_SmallUnrolled(net, n_steps))
+            dlwp._n_steps = n_steps
+            for steps in (1, 4, 7):
+                for ktd in (False, True):
+                    key = 'y_td%d_n%d_s%d_k%d' % (time_dim, n_steps, steps, ktd)
+                    out[key] = dlwp.predict_timeseries(x0, steps, keep_time_dim=ktd)
+                    cases.append(key)
+    out['cases'] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, 'rollout_functional.npz'), **out)
+
+
+def gen_torchnn(models_torch):
+    """The reference's torch twin running "Net A" end to end (padding + conv + tanh + feedback loop) on CPU."""
+    import torch
+    models_torch.device = torch.device('cpu')
+    torch.set_num_threads(1)  # deterministic summation order
+    out = {}
+    for tag, (C, H, W), n, steps, sub in (('small', (6, 23, 36), 2, 10, 1), ('full', (6, 91, 180), 1, 10, 6)):
+        rng = np.random.RandomState(14)
+        k1 = OO.glorot_uniform(rng, 3, 3, C, 32)
+        b1 = (0.05 * rng.standard_normal(32)).astype(np.float32)
+        k2 = OO.glorot_uniform(rng, 5, 5, 32, C)
+        b2 = (0.05 * rng.standard_normal(C)).astype(np.float32)
+        x0 = rng.standard_normal((n, C, H, W)).astype(np.float32)
+        dlwp = models_torch.DLWPTorchNN(is_convolutional=True, is_recurrent=False, time_dim=1, scaler_type=None,
+                                        scale_targets=False)
+        layers = (
+            ('CircularPad2d', ((2, 2, 0, 0),), None),
+            ('ZeroPad2d', ((0, 0, 2, 2),), None),
+            ('Conv2d', (C, 32, 3), {'dilation': 2, 'activation': 'tanh'}),
+            ('CircularPad2d', ((2, 2, 0, 0),), None),
+            ('ZeroPad2d', ((0, 0, 2, 2),), None),
+            ('Conv2d', (32, C, 5), None),
+        )
+        dlwp.build_model(layers, 'Adam', 'MSELoss')
+        with torch.no_grad():
+            dlwp.layers[2].weight.copy_(torch.from_numpy(np.transpose(k1, (3, 2, 0, 1)).copy()))
+            dlwp.layers[2].bias.copy_(torch.from_numpy(b1))
+            dlwp.layers[5].weight.copy_(torch.from_numpy(np.transpose(k2, (3, 2, 0, 1)).copy()))
+            dlwp.layers[5].bias.copy_(torch.from_numpy(b2))
+        y = dlwp.predict_timeseries(x0, steps)
+        out.update({'%s_x0' % tag: x0, '%s_k1' % tag: k1, '%s_b1' % tag: b1, '%s_k2' % tag: k2, '%s_b2' % tag: b2,
+                    '%s_y' % tag: y[:, :, :, ::sub, ::sub], '%s_sub' % tag: np.int64(sub),
+                    '%s_steps' % tag: np.int64(steps)})
+    np.savez_compressed(os.path.join(HERE, 'torchnn_net_a.npz'), **out)
+
+
+def main():
+    install_stubs()
+    load_ref('DLWP.util', 'DLWP/util.py')
+    custom = load_ref('DLWP.custom', 'DLWP/custom.py')
+    models = load_ref('DLWP.model.models', 'DLWP/model/models.py')
+    models_torch = load_ref('DLWP.model.models_torch', 'DLWP/model/models_torch.py')
+    gen_periodic_padding(custom)
+    gen_row_conv(custom)
+    gen_rollout_neuralnet(models)
+    gen_rollout_functional(models)
+    gen_torchnn(models_torch)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print('%-28s %8d bytes' % (f, os.path.getsize(os.path.join(HERE, f))))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,168 @@
+"""
+The oracle against the golden vectors produced by the reference's own code (tests/golden/make_golden.py), and the
+oracle's independent formulations against each other.  CPU only.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import layers as OL
+from oracle import ops as OO
+from oracle import rollout as OR
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_periodic_padding_matches_reference_call(golden_dir):
+    g = _load(golden_dir, 'periodic_padding2d.npz')
+    for k in range(int(g['n_cases'])):
+        pad = tuple(tuple(int(v) for v in row) for row in g['pad_%d' % k])
+        for fmt in ('channels_first', 'channels_last'):
+            y = OO.periodic_pad2d(g['x_' + fmt], pad, fmt)
+            assert y.shape == g['y_%d_%s' % (k, fmt)].shape
+            np.testing.assert_array_equal(y, g['y_%d_%s' % (k, fmt)])  # pure data movement: bit exact
+
+
+def test_row_conv2d_matches_reference(golden_dir):
+    g = _load(golden_dir, 'row_conv2d.npz')
+    y = OO.row_conv2d(g['x'], g['kernel'])
+    np.testing.assert_allclose(y, g['y'], rtol=0, atol=1e-12)
+    y_cl = OO.row_conv2d(np.moveaxis(g['x'], 1, 3), g['kernel'], data_format='channels_last')
+    np.testing.assert_allclose(y_cl, g['y_channels_last'], rtol=0, atol=1e-12)
+
+
+def _small_seq(time_dim, ws):
+    cf = 'channels_first'
+    C = time_dim * 2
+    net = OL.OSequential((
+        ('PeriodicPadding2D', ((0, 1),), {'data_format': cf, 'input_shape': (C, 6, 8)}),
+        ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+        ('Conv2D', (8, 3), {'activation': 'tanh', 'data_format': cf}),
+        ('PeriodicPadding2D', ((0, 2),), {'data_format': cf}),
+        ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+        ('Conv2D', (C, 3), {'dilation_rate': 2, 'activation': 'linear', 'data_format': cf}),
+    ))
+    net.set_weights(ws)
+    return net
+
+
+def test_neuralnet_rollout_matches_reference_loop(golden_dir):
+    g = _load(golden_dir, 'rollout_neuralnet.npz')
+    for key in g['cases']:
+        key = str(key)
+        td, steps, ss, ktd = (int(p[len(pre):]) for p, pre in zip(key.split('_')[1:], ('td', 's', 'ss', 'k')))
+        net = _small_seq(td, [g['w_td%d_%d' % (td, k)] for k in range(4)])
+        fn = lambda p: net.forward(np.asarray(p, np.float64)).astype(np.float32)
+        y = OR.neuralnet_predict_timeseries(fn, g['x0_td%d' % td], steps, time_dim=td, step_sequence=bool(ss),
+                                            keep_time_dim=bool(ktd))
+        assert y.shape == g[key].shape, key
+        assert y.dtype == np.float32
+        np.testing.assert_array_equal(y, g[key], err_msg=key)
+
+
+def test_functional_rollout_matches_reference_loop(golden_dir):
+    g = _load(golden_dir, 'rollout_functional.npz')
+    for key in g['cases']:
+        key = str(key)
+        td, n, steps, ktd = (int(p[len(pre):]) for p, pre in zip(key.split('_')[1:], ('td', 'n', 's', 'k')))
+        net = _small_seq(td, [g['w_td%d_%d' % (td, k)] for k in range(4)])
+
+        def fn(p):
+            outs = [net.forward(np.asarray(p, np.float64))]
+            for _ in range(1, n):
+                outs.append(net.forward(outs[-1]))
+            outs = [o.astype(np.float32) for o in outs]
+            return outs[0] if n == 1 else outs
+        y = OR.functional_predict_timeseries(fn, g['x0_td%d' % td], steps, n_steps=n, time_dim=td,
+                                             keep_time_dim=bool(ktd))
+        assert y.shape == g[key].shape, key
+        np.testing.assert_array_equal(y, g[key], err_msg=key)
+
+
+@pytest.mark.parametrize('tag', ['small', 'full'])
+def test_net_a_rollout_matches_reference_torch_twin(golden_dir, tag):
+    """End to end (periodic pad + zero pad + dilated conv + tanh + feedback loop) vs DLWPTorchNN run on CPU."""
+    g = _load(golden_dir, 'torchnn_net_a.npz')
+    x0 = g[tag + '_x0']
+    net = OL.OSequential(OL.net_a_layers(x0.shape[1:]))
+    net.set_weights([g[tag + '_k1'], g[tag + '_b1'], g[tag + '_k2'], g[tag + '_b2']])
+    sub = int(g[tag + '_sub'])
+    steps = int(g[tag + '_steps'])
+    y64 = OR.neuralnet_predict_timeseries(lambda p: net.forward(p), x0.astype(np.float64), steps, dtype=np.float64)
+    ref = g[tag + '_y']
+    got = y64[:, :, :, ::sub, ::sub]
+    assert got.shape == ref.shape
+    rel = np.abs(got - ref).max() / np.abs(got).max()
+    assert rel < 2e-6, rel  # fp32 reference vs fp64 oracle over 10 feedback steps
+
+
+def test_conv_closed_form_equals_pad_then_conv():
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal((2, 5, 9, 12))
+    for (kh, kw, d, ph, pw, mh, mw) in [(3, 3, 2, (2, 2), (2, 2), 'zero', 'periodic'),
+                                        (5, 5, 1, (2, 2), (2, 2), 'zero', 'periodic'),
+                                        (3, 3, 1, (1, 1), (1, 1), 'periodic', 'periodic'),
+                                        (3, 5, 1, (0, 2), (3, 1), 'zero', 'zero'),
+                                        (3, 3, 1, (2, 0), (0, 2), 'periodic', 'zero')]:
+        k = rng.standard_normal((kh, kw, 5, 4))
+        b = rng.standard_normal(4)
+        xp = x
+        xp = OO.periodic_pad2d(xp, ((0, 0), pw)) if mw == 'periodic' else OO.zero_pad2d(xp, ((0, 0), pw))
+        xp = OO.periodic_pad2d(xp, (ph, (0, 0))) if mh == 'periodic' else OO.zero_pad2d(xp, (ph, (0, 0)))
+        y1 = OO.conv2d_valid(xp, k, b, (d, d))
+        y2 = OO.pad_conv2d_closed_form(x, k, b, (d, d), ph, pw, mh, mw)
+        np.testing.assert_allclose(y1, y2, rtol=0, atol=1e-12)
+
+
+def test_conv_matches_torch_conv2d():
+    """Keras Conv2D cannot run offline; its cross-correlation semantics are cross-checked against torch (independent)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.RandomState(1)
+    x = rng.standard_normal((2, 6, 11, 14))
+    for kh, kw, d in [(3, 3, 1), (3, 3, 2), (5, 5, 1), (1, 3, 1)]:
+        k = rng.standard_normal((kh, kw, 6, 7))
+        b = rng.standard_normal(7)
+        y = OO.conv2d_valid(x, k, b, (d, d))
+        yt = F.conv2d(torch.from_numpy(x), torch.from_numpy(np.transpose(k, (3, 2, 0, 1)).copy()),
+                      torch.from_numpy(b), dilation=d).numpy()
+        np.testing.assert_allclose(y, yt, rtol=0, atol=1e-11)
+
+
+def test_torch_tier1_equals_numpy_tier0():
+    import torch
+    net = OL.OFunctionalNet((4, 16, 24), skip_connections=True, integration_steps=2)
+    OL.init_weights(net.conv_layers, seed=3, bias_scale=0.1)
+    x = np.random.RandomState(2).standard_normal((2, 4, 16, 24))
+    y64 = net.forward(x)
+    with torch.no_grad():
+        y32 = net.forward(torch.from_numpy(x.astype(np.float32)))
+    for a, b in zip(y64, y32):
+        assert np.abs(a - b.numpy()).max() / np.abs(a).max() < 1e-5
+    netb = OL.OFunctionalNet((4, 16, 24), skip_connections=False)
+    OL.init_weights(netb.conv_layers, seed=4)
+    yb = netb.forward(x)
+    assert yb.shape == (2, 4, 16, 24)
+
+
+def test_pool_upsample_slice_semantics():
+    x = np.arange(2 * 2 * 5 * 6, dtype=np.float64).reshape(2, 2, 5, 6)
+    p = OO.max_pool2d(x, 2)
+    assert p.shape == (2, 2, 2, 3)          # floor: the odd 5th row is dropped
+    assert p[0, 0, 0, 0] == x[0, 0, :2, :2].max()
+    u = OO.upsample2d(p, 2)
+    assert u.shape == (2, 2, 4, 6) and u[1, 1, 3, 5] == p[1, 1, 1, 2] and u[0, 0, 0, 1] == p[0, 0, 0, 0]
+    assert OO.slice_channels(x, 1, 2).shape == (2, 1, 5, 6)
+    with pytest.raises(ValueError):
+        OO.slice_channels(x, 0, 1, axis=-1)
+
+
+def test_rollout_argument_errors():
+    with pytest.raises(ValueError):
+        OR.neuralnet_predict_timeseries(lambda p: p, np.zeros((1, 2, 3, 4), np.float32), 0)
+    with pytest.raises(ValueError):
+        OR.functional_predict_timeseries(lambda p: p, np.zeros((1, 2, 3, 4), np.float32), -1)
