@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""
+bench.py -- forecast-steps/sec of DLWP's predict_timeseries rollout (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): "Net A" -- PeriodicPadding2D((0,2)) + ZeroPadding2D((2,0)) + Conv2D(32,3,d=2,tanh)
++ PeriodicPadding2D + ZeroPadding2D + Conv2D(6,5,linear) on a (B, 6, 91, 180) fp32 state, K feedback steps; synthetic
+inputs x0 = RandomState(0).randn, weights = Keras glorot_uniform restated with RandomState(1), zero biases (BASELINE.md
+section 3).  One "step" = one rollout step over the whole batch; value = B * K / time in forecast-steps/s.
+
+* `value`      device-resident rollout (x0 and the series in HBM), one CUDA-graph launch of K steps, CUDA events.
+* `e2e`        the reference-facing call DLWPNeuralNet.predict_timeseries(numpy) -> numpy: H2D of x0, rollout, D2H of
+               every step's state, wall clock around the call.
+* `roofline`   the dominant kernel (conv 32->6 5x5) timed alone with CUDA events: SURVEY.md 8(d) algorithmic bytes / time
+               against the measured HBM copy peak (MEASURED_PEAKS.json).
+* `cpu_baseline` / `--impl reference`: the reference's rollout loop restated in oracle/ around a torch-CPU fp32 forward
+               (Keras/TensorFlow are not installable offline), all host threads, on a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+STATE = (6, 91, 180)
+BYTES_PER_SAMPLE_STEP = 5005784      # sum over conv layers of 4*Ho*Wo*(Cin+Cout) + 4*(weights+bias)
+FLOP_PER_SAMPLE_STEP = 213857280
+
+
+def conv_alg_bytes(n, cin, cout, k, ho=91, wo=180):
+    return 4 * n * ho * wo * (cin + cout) + 4 * (k * k * cin * cout + cout)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+def make_inputs(batch):
+    return np.random.RandomState(0).standard_normal((batch,) + STATE).astype(np.float32)
+
+
+def net_a_layers():
+    """First and last conv blocks of examples/train.py:159-169, 211-219 as DLWPNeuralNet.build_model layer tuples."""
+    cf = 'channels_first'
+    return (
+        ('PeriodicPadding2D', ((0, 2),), {'data_format': cf, 'input_shape': STATE}),
+        ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+        ('Conv2D', (32, 3), {'dilation_rate': 2, 'padding': 'valid', 'activation': 'tanh', 'data_format': cf}),
+        ('PeriodicPadding2D', ((0, 2),), {'data_format': cf}),
+        ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+        ('Conv2D', (STATE[0], 5), {'padding': 'valid', 'activation': 'linear', 'data_format': cf}),
+    )
+
+
+def net_a_weights():
+    """Keras default glorot_uniform restated with RandomState(1), (kh,kw,Cin,Cout) order per layer; zero biases."""
+    rng = np.random.RandomState(1)
+    ws = []
+    for kh, kw, cin, cout in ((3, 3, STATE[0], 32), (5, 5, 32, STATE[0])):
+        limit = np.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
+        ws += [rng.uniform(-limit, limit, size=(kh, kw, cin, cout)).astype(np.float32), np.zeros(cout, np.float32)]
+    return ws
+
+
+def oracle_net():
+    """cpu_baseline / --impl reference only: the oracle's Net A with the same weights."""
+    from oracle import layers as OL
+    net = OL.OSequential(net_a_layers())
+    net.set_weights(net_a_weights())
+    return net
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(n_samples, steps, warmup):
+    """The reference's rollout loop (oracle.rollout) around a torch-CPU forward; returns (forecast-steps/s, cores)."""
+    from oracle import rollout as OR
+    from oracle import torch_cpu as OT
+    cores = OT.use_all_cores()
+    model = OT.KerasLikeModel(oracle_net())
+    x0 = make_inputs(n_samples)
+    if warmup > 0:
+        OR.neuralnet_predict_timeseries(model.predict, x0, warmup)
+    t0 = time.perf_counter()
+    OR.neuralnet_predict_timeseries(model.predict, x0, steps)
+    dt = time.perf_counter() - t0
+    return n_samples * steps / dt, cores, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: probe one step on 8 samples, then size the sample so the whole run stays within ~2 minutes
+    v, cores, _ = cpu_reference(8, 1, 1)
+    budget_s = 120.0
+    n = int(max(1, min(32, budget_s * v / max(1, args.steps + args.warmup))))
+    value, cores, dt = cpu_reference(n, args.steps, args.warmup)
+    sample = '%d of %d samples x %d steps (Keras-style batch_size=32 chunks)' % (n, args.batch, args.steps)
+    line = {
+        'impl': 'reference', 'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'net_a_6x91x180_rollout', 'batch_per_gpu': args.batch, 'timed_sample_batch': n,
+                   'note': 'reference rollout loop (DLWP/model/models.py:247-301 restated in oracle/) + torch-CPU fp32 '
+                           'forward; Keras/TensorFlow are not installable offline'},
+        'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def build_model():
+    from dlwp_b200.model import DLWPNeuralNet
+    dlwp = DLWPNeuralNet(is_convolutional=True, is_recurrent=False, time_dim=1, scaler_type=None, scale_targets=False)
+    dlwp.build_model(net_a_layers(), loss='mse', optimizer='adam')
+    dlwp.model.set_weights(net_a_weights())
+    return dlwp
+
+
+def time_single_kernel(torch, nat, batch, cin, cout, k, d, act, iters):
+    """Average duration (ms) of one conv layer launched alone, CUDA events on the launching stream."""
+    import ctypes
+    rng = np.random.RandomState(3)
+    x = torch.from_numpy(rng.standard_normal((batch, cin, 91, 180)).astype(np.float32)).cuda()
+    w = torch.from_numpy((0.05 * rng.standard_normal((k, k, cin, cout))).astype(np.float32)).cuda()
+    b = torch.zeros(cout, device='cuda')
+    y = torch.empty((batch, cout, 91, 180), device='cuda')
+    desc = nat.ConvDesc(N=batch, Cin=cin, H=91, W=180, Cout=cout, kh=k, kw=k, dil_h=d, dil_w=d, pad_t=2, pad_b=2,
+                        pad_l=2, pad_r=2, pad_mode_h=0, pad_mode_w=1, act=act, pre_op=0, rowwise=0, impl=0, reserved=0,
+                        x_stride_n=cin * 91 * 180, x_stride_c=91 * 180, x_stride_h=180, y_stride_n=cout * 91 * 180,
+                        y_stride_c=91 * 180, y_stride_h=180)
+    lib = nat.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    name = lib.dlwp_conv2d_impl_name(ctypes.byref(desc)).decode()
+    for _ in range(3):
+        nat.check(lib.dlwp_conv2d_fwd(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                      stream))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        lib.dlwp_conv2d_fwd(ctypes.byref(desc), x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, name
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dlwp_b200 import _native as nat
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    lib = nat.lib()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    dlwp = build_model()
+    eng = dlwp.model.engine(B)
+    assert eng.max_batch >= B, 'batch does not fit the plan'
+    # every rank rolls its own B samples forward (independent forecasts: no data-path collective)
+    x0 = np.random.RandomState(rank).standard_normal((B,) + STATE).astype(np.float32)
+    xd = torch.from_numpy(x0).cuda()
+    series = torch.empty((K, B) + STATE, dtype=torch.float32, device='cuda')
+    warm = torch.empty((W, B) + STATE, dtype=torch.float32, device='cuda')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.rollout_device(xd, W, use_graph=False, out=warm)          # W untimed warm-up steps
+    eng.rollout_device(xd, K, use_graph=True, out=series)         # graph capture + first replay (untimed)
+    barrier()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        eng.rollout_device(xd, K, use_graph=True, out=series)     # EXACTLY K timed steps
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = nat.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the reference-facing API: numpy in -> numpy out, copies inside the timed region ----------
+    Ke = min(K, args.e2e_steps)
+    x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
+    y = dlwp.predict_timeseries(x0_pinned, min(Ke, 3))            # warm-up (allocators, pinned pool)
+    del y
+    barrier()
+    t0 = time.perf_counter()
+    y = dlwp.predict_timeseries(x0_pinned, Ke)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert y.shape == (Ke, B) + STATE
+    if world > 1:
+        t = torch.tensor([dt], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * B * Ke / dt
+    checksum = float(np.abs(y[-1]).mean())
+    slot_bytes = B * int(np.prod(STATE)) * 4
+    del y
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, timed alone (rank 0) -----------------------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    it = max(10, min(50, K))
+    ms2, name2 = time_single_kernel(torch, nat, B, 32, 6, 5, 1, 0, it)
+    ms1, name1 = time_single_kernel(torch, nat, B, 6, 32, 3, 2, 1, it)
+    alg2 = conv_alg_bytes(B, 32, 6, 5)
+    achieved = alg2 / (ms2 * 1e-3) / 1e9
+    roofline = {
+        'kernel': 'conv_ffma_kernel<5,5,1> 32->6 (%s)' % name2, 'bound': 'hbm', 'achieved': achieved,
+        'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+        'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6650',
+        'algorithmic_bytes_per_launch': alg2, 'ms_per_launch': ms2,
+        'achieved_tflops_fp32': 2.0 * B * 91 * 180 * 6 * 32 * 25 / (ms2 * 1e-3) / 1e12,
+        'other_kernels': [{'kernel': 'conv_ffma_kernel<3,3,2> 6->32 tanh (%s)' % name1, 'ms_per_launch': ms1,
+                           'achieved_gbs': conv_alg_bytes(B, 6, 32, 3) / (ms1 * 1e-3) / 1e9}],
+        'step': {'algorithmic_bytes': BYTES_PER_SAMPLE_STEP * B, 'ms': ms / K,
+                 'achieved_gbs': BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9,
+                 'frac': BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                 'achieved_tflops_fp32': FLOP_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e12},
+    }
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, cores, dtc = cpu_reference(32, 4, 1)
+        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port',
+               'sample': '32 of %d samples x 4 steps (1 warm-up step), torch-CPU fp32 forward inside the reference '
+                         'rollout loop' % B}
+
+    line = {
+        'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'batch_per_gpu': B,
+                   'global_batch': B * world, 'state': list(STATE), 'parallelism': 'independent forecasts per GPU'
+                   if world > 1 else 'single GPU',
+                   'l2': 'per-step working set %.0f MB (state in + 32-ch activation + state out) > 126 MB L2; no flush'
+                         % ((6 + 32 + 6) * 91 * 180 * 4 * B / 1e6),
+                   'timed_region': 'one CUDA-graph replay of %d steps, inputs resident in HBM' % K,
+                   'e2e_steps': Ke, 'checksum_mean_abs_last_state': checksum},
+        'e2e': {'value': e2e_value, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': slot_bytes / Ke,
+                'd2h_bytes_per_step': slot_bytes, 'api': 'DLWPNeuralNet.predict_timeseries(numpy)->numpy',
+                'steps': Ke, 'seconds': dt},
+        'gpu_launches': launches,
+        'clocks': clocks.summary(),
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=256, help='forecasts (samples) per GPU')
+    ap.add_argument('--e2e-steps', type=int, default=40, help='steps of the host-API measurement (<= --steps)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit('launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d '
+                         '--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ...' % (args.gpus, args.gpus))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,104 @@
+"""
+ctypes binding of libdlwp_b200.so (include/dlwp_b200.h).  This is the ONLY compute backend of the package: if the
+library is missing or cannot be loaded the import fails loudly -- there is no CPU / PyTorch fallback path.
+"""
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libdlwp_b200.so')
+
+DLWP_OK = 0
+PAD_ZERO, PAD_PERIODIC = 0, 1
+ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
+IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA = 0, 1, 2, 3
+BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2
+OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY = 0, 1, 2, 3, 4
+ACTIVATIONS = {None: ACT_LINEAR, 'linear': ACT_LINEAR, 'tanh': ACT_TANH, 'relu': ACT_RELU}
+IMPLS = {'auto': IMPL_AUTO, 'direct': IMPL_DIRECT, 'ffma': IMPL_FFMA, 'ffma_tma': IMPL_FFMA_TMA}
+
+i32, i64 = ctypes.c_int32, ctypes.c_int64
+fptr = ctypes.c_void_p
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, i32) for n in ('N', 'Cin', 'H', 'W', 'Cout', 'kh', 'kw', 'dil_h', 'dil_w', 'pad_t', 'pad_b',
+                                   'pad_l', 'pad_r', 'pad_mode_h', 'pad_mode_w', 'act', 'pre_op', 'rowwise', 'impl',
+                                   'reserved')] + \
+               [(n, i64) for n in ('x_stride_n', 'x_stride_c', 'x_stride_h', 'y_stride_n', 'y_stride_c',
+                                   'y_stride_h')]
+
+
+class BufferDesc(ctypes.Structure):
+    _fields_ = [(n, i32) for n in ('kind', 'C', 'H', 'W', 'output_index', 'reserved')]
+
+
+class OpDesc(ctypes.Structure):
+    _fields_ = [(n, i32) for n in ('kind', 'src', 'src_c0', 'src_c', 'dst', 'dst_c0', 'weight_id', 'pad_t', 'pad_b',
+                                   'pad_l', 'pad_r', 'pad_mode_h', 'pad_mode_w', 'Cout', 'kh', 'kw', 'dil_h', 'dil_w',
+                                   'act', 'pre_op', 'rowwise', 'impl')]
+
+
+class NetDesc(ctypes.Structure):
+    _fields_ = [('n_buffers', i32), ('n_ops', i32), ('n_weights', i32), ('max_batch', i32),
+                ('buffers', ctypes.POINTER(BufferDesc)), ('ops', ctypes.POINTER(OpDesc))]
+
+
+# every symbol include/dlwp_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    'dlwp_conv2d_fwd': (ctypes.c_int, [ctypes.POINTER(ConvDesc), fptr, fptr, fptr, fptr, ctypes.c_void_p]),
+    'dlwp_pad2d': (ctypes.c_int, [fptr, fptr] + [i32] * 10 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_maxpool2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_upsample2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_copy4d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_plan_create': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    'dlwp_plan_destroy': (None, [ctypes.c_void_p]),
+    'dlwp_plan_set_weights': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, i64, fptr, i64]),
+    'dlwp_plan_get_weights': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, i64, fptr, i64]),
+    'dlwp_plan_forward': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.c_void_p]),
+    'dlwp_rollout': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32, ctypes.c_void_p]),
+    'dlwp_rollout_host': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32]),
+    'dlwp_last_error_string': (ctypes.c_char_p, []),
+    'dlwp_abi_version': (ctypes.c_int, []),
+    'dlwp_kernel_launch_count': (ctypes.c_int64, []),
+    'dlwp_conv2d_impl_name': (ctypes.c_char_p, [ctypes.POINTER(ConvDesc)]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'libdlwp_b200.so is not built (%s). Run `python -m dlwp_b200.build` (needs nvcc); dlwp_b200 has no '
+                'CPU or PyTorch fallback for its CUDA kernels.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI and the binding drift apart
+            fn.restype = res
+            fn.argtypes = args
+        if handle.dlwp_abi_version() != 1:
+            raise ImportError('libdlwp_b200.so ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().dlwp_last_error_string().decode('utf-8', 'replace')
+        exc = ValueError if rc in (-1, -2) else NativeError
+        raise exc('%s failed (code %d): %s' % (what or 'libdlwp_b200 call', rc, msg))
+
+
+def launch_count():
+    return int(lib().dlwp_kernel_launch_count())

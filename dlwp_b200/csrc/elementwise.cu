@@ -1,0 +1,104 @@
+// Stand-alone data-movement layers of the example nets: PeriodicPadding2D / ZeroPadding2D (DLWP/custom.py:191-214),
+// MaxPooling2D(2), UpSampling2D(2), and a strided channel-block copy (materialised concatenate / slice).
+// HBM-bound byte movers: coalesced along W, grid-stride, one thread per output element.
+#include "internal.h"
+
+#include <algorithm>
+
+namespace dlwp {
+
+struct EwParams {
+    const float* x;
+    float* y;
+    int N, C, H, W;      // source dims
+    int Ho, Wo;          // destination dims
+    int pad_t, pad_l, mode_h, mode_w;
+    long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;
+};
+
+enum { EW_PAD = 0, EW_POOL = 1, EW_UP = 2, EW_COPY = 3 };
+
+template <int OP>
+__global__ void __launch_bounds__(256) elementwise_kernel(const EwParams p) {
+    const long long total = (long long)p.N * p.C * p.Ho * p.Wo;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(idx % p.Wo);
+        long long t = idx / p.Wo;
+        const int yo = (int)(t % p.Ho);
+        t /= p.Ho;
+        const int c = (int)(t % p.C);
+        const int n = (int)(t / p.C);
+        const float* xc = p.x + (long long)n * p.xs_n + (long long)c * p.xs_c;
+        float v;
+        if (OP == EW_PAD) {
+            int gy = yo - p.pad_t, gx = xo - p.pad_l;
+            bool ok = true;
+            if (p.mode_h == DLWP_PAD_PERIODIC) gy = wrap_index(gy, p.H);
+            else ok = ok && gy >= 0 && gy < p.H;
+            if (p.mode_w == DLWP_PAD_PERIODIC) gx = wrap_index(gx, p.W);
+            else ok = ok && gx >= 0 && gx < p.W;
+            v = ok ? xc[(long long)gy * p.xs_h + gx] : 0.f;
+        } else if (OP == EW_POOL) {
+            const float* q = xc + (long long)(2 * yo) * p.xs_h + 2 * xo;
+            v = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[p.xs_h], q[p.xs_h + 1]));
+        } else if (OP == EW_UP) {
+            v = xc[(long long)(yo >> 1) * p.xs_h + (xo >> 1)];
+        } else {
+            v = xc[(long long)yo * p.xs_h + xo];
+        }
+        p.y[(long long)n * p.ys_n + (long long)c * p.ys_c + (long long)yo * p.ys_h + xo] = v;
+    }
+}
+
+template <int OP>
+static int launch(const EwParams& p, cudaStream_t stream, const char* name) {
+    int rc = check_device();
+    if (rc) return rc;
+    DLWP_REQUIRE(p.x && p.y, DLWP_EINVAL, "null tensor pointer");
+    DLWP_REQUIRE(p.N > 0 && p.C > 0 && p.H > 0 && p.W > 0 && p.Ho > 0 && p.Wo > 0, DLWP_ESHAPE,
+                 "%s: non-positive dims", name);
+    const long long total = (long long)p.N * p.C * p.Ho * p.Wo;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    elementwise_kernel<OP><<<blocks, 256, 0, stream>>>(p);
+    return after_launch(name);
+}
+
+}  // namespace dlwp
+
+using namespace dlwp;
+
+extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t,
+                          int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n,
+                          int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream) {
+    DLWP_REQUIRE(pad_t >= 0 && pad_b >= 0 && pad_l >= 0 && pad_r >= 0, DLWP_ESHAPE, "negative padding");
+    DLWP_REQUIRE((mode_h == DLWP_PAD_ZERO || mode_h == DLWP_PAD_PERIODIC) &&
+                     (mode_w == DLWP_PAD_ZERO || mode_w == DLWP_PAD_PERIODIC),
+                 DLWP_EINVAL, "bad pad mode");
+    if (mode_h == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_t <= H && pad_b <= H, DLWP_ESHAPE, "periodic pad > axis");
+    if (mode_w == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_l <= W && pad_r <= W, DLWP_ESHAPE, "periodic pad > axis");
+    EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w,
+               xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    return launch<EW_PAD>(p, (cudaStream_t)stream, "pad2d");
+}
+
+extern "C" int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
+                              int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
+                              dlwp_stream_t stream) {
+    EwParams p{x, y, N, C, H, W, H / 2, W / 2, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    return launch<EW_POOL>(p, (cudaStream_t)stream, "maxpool2d");
+}
+
+extern "C" int dlwp_upsample2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
+                               int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
+                               dlwp_stream_t stream) {
+    EwParams p{x, y, N, C, H, W, H * 2, W * 2, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    return launch<EW_UP>(p, (cudaStream_t)stream, "upsample2d");
+}
+
+extern "C" int dlwp_copy4d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
+                           int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
+                           dlwp_stream_t stream) {
+    EwParams p{x, y, N, C, H, W, H, W, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    return launch<EW_COPY>(p, (cudaStream_t)stream, "copy4d");
+}

@@ -1,0 +1,154 @@
+// Internal declarations shared by the translation units of libdlwp_b200.so.  Not part of the ABI.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/dlwp_b200.h"
+
+namespace dlwp {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define DLWP_CUDA_TRY(expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::dlwp::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                 \
+                              cudaGetErrorString(_e));                                             \
+            return (int)_e;                                                                        \
+        }                                                                                          \
+    } while (0)
+
+#define DLWP_REQUIRE(cond, code, ...)                                                              \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            ::dlwp::set_error(__VA_ARGS__);                                                        \
+            return (code);                                                                         \
+        }                                                                                          \
+    } while (0)
+
+inline int after_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ---- kernel launchers (conv.cu / elementwise.cu) ------------------------------------------------------------------
+int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const float* bias, float* y,
+               cudaStream_t stream);
+const char* conv2d_impl_name(const DlwpConvDesc& d);
+int check_device();
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4]);
+
+}  // namespace dlwp
+
+// ---- device helpers -------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace dlwp {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// tanh accurate to a few 1e-7 relative: odd polynomial below 0.3, (1-e)/(1+e) with e = exp(-2|x|) above.
+// (tanh.approx.f32 is only good to 2^-11 -- not enough for the 1e-4 / 50-step parity gate.)
+__device__ __forceinline__ float tanh_accurate(float x) {
+    const float ax = fabsf(x);
+    const float x2 = ax * ax;
+    float p = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);  // 62/2835, -17/315
+    p = fmaf(x2, p, 0.13333333333333333f);                              // 2/15
+    p = fmaf(x2, p, -0.33333333333333333f);                             // -1/3
+    p = fmaf(x2 * ax, p, ax);
+    const float e = __expf(-2.0f * ax);
+    const float q = __fdividef(1.0f - e, 1.0f + e);
+    return copysignf(ax < 0.3f ? p : q, x);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == DLWP_ACT_TANH) return tanh_accurate(v);
+    if (act == DLWP_ACT_RELU) return fmaxf(v, 0.0f);
+    return v;
+}
+
+// floor-mod for possibly negative a, b > 0
+__device__ __forceinline__ int wrap_index(int a, int b) {
+    int m = a % b;
+    return m < 0 ? m + b : m;
+}
+
+// ---- cp.async (LDGSTS) ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const float* src, bool valid) {
+    const int sz = valid ? 4 : 0;  // src-size 0 => destination is zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const float* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- mbarrier + TMA ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a TMA that never completes (bad descriptor) traps the kernel instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+}  // namespace dlwp
+#endif

@@ -1,0 +1,408 @@
+"""
+Lowering of a (front-end) Keras graph to a libdlwp_b200 plan, and the object that runs it.
+
+This is what stands where `keras.Model.predict` -> `tf.Session.run` stands in the reference
+(DLWP/model/models.py:241, :412): the layer DAG recorded by dlwp_b200.keras is lowered ONCE to a static list of device ops
+over (N, C, H, W) buffers:
+
+* PeriodicPadding2D / ZeroPadding2D (DLWP/custom.py:191-214) become padding *attributes* of the following Conv2D -- no
+  padded tensor exists in memory;
+* `slice_layer` (custom.py:675-692) and `concatenate(axis=1)` become channel windows of shared buffers (a producer writes
+  straight into its slot of the concatenated buffer);
+* the last op of every model output writes directly into caller memory (for a rollout: into its slot of the series).
+
+`CompiledNet` owns the DlwpPlan handle.  All compute goes through the C ABI; torch is used for device memory, pinned
+host memory and the current stream only.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+from .keras import layers as KL
+from .keras.engine import InputLayer
+
+
+class _Val(object):
+    """Symbolic value during lowering: a channel window of a buffer plus not-yet-applied paddings."""
+    __slots__ = ('buf', 'c0', 'C', 'H', 'W', 'pads', 'shape')
+
+    def __init__(self, buf, c0, C, H, W, pads=(), shape=None):
+        self.buf, self.c0, self.C, self.H, self.W = buf, c0, C, H, W
+        self.pads = tuple(pads)
+        self.shape = shape if shape is not None else (C, H, W)  # logical per-sample shape reported to the caller
+
+
+def _unsupported(layer, why):
+    raise NotImplementedError('layer %s (%s) cannot be lowered to the GPU plan: %s' %
+                              (layer.name, layer.__class__.__name__, why))
+
+
+class Lowering(object):
+    def __init__(self, model):
+        self.model = model
+        self.buffers = []   # dicts: kind, C, H, W, output_index
+        self.ops = []       # dicts
+        self.weight_layers = []
+        self.out_vals = []
+        self._lower()
+
+    # -- helpers -------------------------------------------------------------------------------------------------
+    def _new_buffer(self, C, H, W, kind=nat.BUF_INTERNAL, output_index=0):
+        self.buffers.append({'kind': kind, 'C': C, 'H': H, 'W': W, 'output_index': output_index})
+        return len(self.buffers) - 1
+
+    def _weight_id(self, layer):
+        if layer not in self.weight_layers:
+            self.weight_layers.append(layer)
+        return self.weight_layers.index(layer)
+
+    def _op(self, kind, src, dst_buf, dst_c0=0, **kw):
+        op = dict(kind=kind, src=src.buf, src_c0=src.c0, src_c=src.C, dst=dst_buf, dst_c0=dst_c0, weight_id=-1,
+                  pad_t=0, pad_b=0, pad_l=0, pad_r=0, pad_mode_h=0, pad_mode_w=0, Cout=0, kh=0, kw=0, dil_h=1,
+                  dil_w=1, act=0, pre_op=0, rowwise=0, impl=0)
+        op.update(kw)
+        self.ops.append(op)
+        return op
+
+    @staticmethod
+    def _pad_mode(mode, layer):
+        if mode == 'zero':
+            return nat.PAD_ZERO
+        if mode == 'periodic':
+            return nat.PAD_PERIODIC
+        _unsupported(layer, 'padding mode %r has no kernel (only zero / periodic are on the hot path)' % mode)
+
+    def _materialise_one_pad(self, v):
+        """Apply the first pending padding with a stand-alone pad op."""
+        mode, (t, b), (l, r), layer = v.pads[0]
+        m = self._pad_mode(mode, layer)
+        H, W = v.H + t + b, v.W + l + r
+        buf = self._new_buffer(v.C, H, W)
+        self._op(nat.OP_PAD, _Val(v.buf, v.c0, v.C, v.H, v.W), buf, pad_t=t, pad_b=b, pad_l=l, pad_r=r,
+                 pad_mode_h=m, pad_mode_w=m)
+        return _Val(buf, 0, v.C, H, W, v.pads[1:])
+
+    def _materialise(self, v):
+        while v.pads:
+            v = self._materialise_one_pad(v)
+        return v
+
+    def _fusable_pads(self, v):
+        """Reduce pending paddings until at most one layer pads each axis; return (v, (mode_h,t,b), (mode_w,l,r))."""
+        while True:
+            h = [(p[0], p[1], p[3]) for p in v.pads if p[1] != (0, 0)]
+            w = [(p[0], p[2], p[3]) for p in v.pads if p[2] != (0, 0)]
+            if len(h) <= 1 and len(w) <= 1:
+                hm = (self._pad_mode(h[0][0], h[0][2]),) + h[0][1] if h else (nat.PAD_ZERO, 0, 0)
+                wm = (self._pad_mode(w[0][0], w[0][2]),) + w[0][1] if w else (nat.PAD_ZERO, 0, 0)
+                return v, hm, wm
+            v = self._materialise_one_pad(v)
+
+    # -- per-layer emitters --------------------------------------------------------------------------------------
+    def _emit(self, layer, ins):
+        if isinstance(layer, KL.ZeroPadding2D):  # includes PeriodicPadding2D & friends (pad_mode attribute)
+            v = ins[0]
+            if layer.data_format != 'channels_first':
+                _unsupported(layer, "only data_format='channels_first' is lowered (all DLWP examples use it)")
+            (t, b), (l, r) = layer.padding
+            if layer.pad_mode == 'periodic' and (max(t, b) > v.H + sum(p[1][0] + p[1][1] for p in v.pads) or
+                                                 max(l, r) > v.W + sum(p[2][0] + p[2][1] for p in v.pads)):
+                raise ValueError('PeriodicPadding2D %s pads by more than the axis length' % layer.name)
+            pads = v.pads + ((layer.pad_mode, (t, b), (l, r), layer),)
+            return _Val(v.buf, v.c0, v.C, v.H, v.W, pads, (v.C, v.H + sum(p[1][0] + p[1][1] for p in pads),
+                                                           v.W + sum(p[2][0] + p[2][1] for p in pads)))
+        if isinstance(layer, KL.Conv2D):  # includes RowConnected2D
+            return self._emit_conv(layer, ins[0])
+        if isinstance(layer, KL.MaxPooling2D):
+            if layer.pool_size != (2, 2) or layer.strides != (2, 2) or layer.padding != 'valid':
+                _unsupported(layer, 'only MaxPooling2D(2) with default strides / valid padding is implemented')
+            if layer.data_format != 'channels_first':
+                _unsupported(layer, "only data_format='channels_first' is lowered")
+            v = self._materialise(ins[0])
+            buf = self._new_buffer(v.C, v.H // 2, v.W // 2)
+            self._op(nat.OP_MAXPOOL, v, buf)
+            return _Val(buf, 0, v.C, v.H // 2, v.W // 2)
+        if isinstance(layer, KL.UpSampling2D):
+            if layer.size != (2, 2):
+                _unsupported(layer, 'only UpSampling2D(2) is implemented')
+            if layer.data_format != 'channels_first':
+                _unsupported(layer, "only data_format='channels_first' is lowered")
+            v = self._materialise(ins[0])
+            buf = self._new_buffer(v.C, v.H * 2, v.W * 2)
+            self._op(nat.OP_UPSAMPLE, v, buf)
+            return _Val(buf, 0, v.C, v.H * 2, v.W * 2)
+        if isinstance(layer, KL.ChannelSlice):
+            v = ins[0]
+            if layer.axis != 1 or layer.step not in (None, 1):
+                _unsupported(layer, 'only contiguous channel slices (axis=1, step 1) are lowered')
+            a, b, _ = slice(layer.start, layer.end, None).indices(v.C)
+            if b <= a:
+                raise ValueError('slice_layer %s selects no channels' % layer.name)
+            return _Val(v.buf, v.c0 + a, b - a, v.H, v.W, v.pads, (b - a,) + tuple(v.shape[1:]))
+        if isinstance(layer, KL.Concatenate):
+            if layer.axis not in (1, -3):
+                _unsupported(layer, 'only channel concatenation (axis=1) is lowered')
+            vs = [self._materialise(v) for v in ins]
+            C = sum(v.C for v in vs)
+            buf = self._new_buffer(C, vs[0].H, vs[0].W)
+            c0 = 0
+            for v in vs:
+                self._op(nat.OP_COPY, v, buf, dst_c0=c0)
+                c0 += v.C
+            return _Val(buf, 0, C, vs[0].H, vs[0].W)
+        if isinstance(layer, KL.Reshape):
+            v = ins[0]
+            tgt = layer.compute_output_shape((None,) + tuple(v.shape))[1:]
+            if len(tgt) >= 2 and tuple(tgt[-2:]) == tuple(v.shape[-2:]):
+                return _Val(v.buf, v.c0, v.C, v.H, v.W, v.pads, tuple(tgt))  # regroups (T, C) <-> (T*C): a view
+            _unsupported(layer, 'Reshape that changes the spatial axes')
+        if isinstance(layer, KL.Lambda):
+            _unsupported(layer, 'arbitrary Lambda functions run on the host; use DLWP.custom.slice_layer')
+        _unsupported(layer, 'no kernel for this layer type')
+
+    def _emit_conv(self, layer, v):
+        if layer.data_format != 'channels_first':
+            _unsupported(layer, "only data_format='channels_first' is lowered (all DLWP examples use it)")
+        if layer.strides != (1, 1):
+            _unsupported(layer, 'strided convolutions are not on the hot path')
+        act = nat.ACTIVATIONS.get(layer.activation)
+        if act is None and layer.activation is not None:
+            _unsupported(layer, 'activation %r' % (layer.activation,))
+        kh, kw = layer.kernel_size
+        dh, dw = layer.dilation_rate
+        if layer.padding == 'same':
+            th, tw = dh * (kh - 1), dw * (kw - 1)
+            v = _Val(v.buf, v.c0, v.C, v.H, v.W,
+                     v.pads + (('zero', (th // 2, th - th // 2), (tw // 2, tw - tw // 2), layer),))
+        v, (mh, t, b), (mw, l, r) = self._fusable_pads(v)
+        Ho = v.H + t + b - dh * (kh - 1)
+        Wo = v.W + l + r - dw * (kw - 1)
+        if Ho <= 0 or Wo <= 0:
+            raise ValueError('Negative dimension size caused by the convolution of layer %s' % layer.name)
+        rowwise = 1 if layer.__class__.__name__ == 'RowConnected2D' else 0
+        buf = self._new_buffer(layer.filters, Ho, Wo)
+        self._op(nat.OP_CONV, _Val(v.buf, v.c0, v.C, v.H, v.W), buf, weight_id=self._weight_id(layer), pad_t=t,
+                 pad_b=b, pad_l=l, pad_r=r, pad_mode_h=mh, pad_mode_w=mw, Cout=layer.filters, kh=kh, kw=kw, dil_h=dh,
+                 dil_w=dw, act=act or 0, rowwise=rowwise)
+        return _Val(buf, 0, layer.filters, Ho, Wo)
+
+    # -- driver --------------------------------------------------------------------------------------------------
+    def _lower(self):
+        m = self.model
+        in_shape = m.inputs[0].shape[1:]
+        if len(in_shape) != 3 or any(s is None for s in in_shape):
+            raise NotImplementedError('the GPU plan needs a fully defined (C, H, W) input, got %s' % (in_shape,))
+        C, H, W = in_shape
+        in_buf = self._new_buffer(C, H, W, nat.BUF_INPUT)
+        vals = {id(m.inputs[0]): _Val(in_buf, 0, C, H, W)}
+        for node in m._nodes:
+            if isinstance(node.layer, InputLayer):
+                continue
+            vals[id(node.output)] = self._emit(node.layer, [vals[id(t)] for t in node.inputs])
+        # model outputs must be dense caller-bound buffers
+        used = set()
+        for k, t in enumerate(m.outputs):
+            v = self._materialise(vals[id(t)])
+            b = self.buffers[v.buf]
+            full = v.c0 == 0 and v.C == b['C']
+            if full and b['kind'] == nat.BUF_INTERNAL and v.buf not in used:
+                b['kind'], b['output_index'] = nat.BUF_OUTPUT, k
+            else:
+                nb = self._new_buffer(v.C, v.H, v.W, nat.BUF_OUTPUT, k)
+                self._op(nat.OP_COPY, v, nb)
+                v = _Val(nb, 0, v.C, v.H, v.W, (), v.shape)
+            used.add(v.buf)
+            self.out_vals.append(v)
+        self._elide_concat_copies()
+
+    def _elide_concat_copies(self):
+        """
+        A COPY of a whole producer-written INTERNAL buffer into a channel window of another buffer is removed by making
+        the producer (and every other reader) use that window directly: concatenate() costs nothing for such inputs.
+        """
+        changed = True
+        while changed:
+            changed = False
+            for ci, cp in enumerate(self.ops):
+                if cp['kind'] != nat.OP_COPY:
+                    continue
+                sb = self.buffers[cp['src']]
+                if sb['kind'] != nat.BUF_INTERNAL or cp['src_c0'] != 0 or cp['src_c'] != sb['C']:
+                    continue
+                writers = [o for o in self.ops if o['dst'] == cp['src']]
+                if len(writers) != 1 or writers[0]['dst_c0'] != 0:
+                    continue
+                wi = self.ops.index(writers[0])
+                # the window must not be written by anything between the producer and the copy
+                clash = any(o['dst'] == cp['dst'] for o in self.ops[wi + 1:ci])
+                if clash:
+                    continue
+                src, dst, off = cp['src'], cp['dst'], cp['dst_c0']
+                writers[0]['dst'], writers[0]['dst_c0'] = dst, off
+                for o in self.ops:
+                    if o is not cp and o['src'] == src:
+                        o['src'], o['src_c0'] = dst, o['src_c0'] + off
+                del self.ops[ci]
+                changed = True
+                break
+        # drop buffers nobody references any more (keep indices stable by compacting)
+        live = sorted({o['src'] for o in self.ops} | {o['dst'] for o in self.ops} |
+                      {i for i, b in enumerate(self.buffers) if b['kind'] != nat.BUF_INTERNAL})
+        remap = {old: new for new, old in enumerate(live)}
+        self.buffers = [self.buffers[i] for i in live]
+        for o in self.ops:
+            o['src'], o['dst'] = remap[o['src']], remap[o['dst']]
+        for v in self.out_vals:
+            v.buf = remap[v.buf]
+
+    def internal_floats_per_sample(self):
+        return sum(b['C'] * b['H'] * b['W'] for b in self.buffers if b['kind'] == nat.BUF_INTERNAL)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('dlwp_b200 needs a CUDA device (B200, sm_100a); there is no CPU execution path')
+    return torch
+
+
+class CompiledNet(object):
+    """A DlwpPlan plus the host-side glue around it.  Created lazily by keras.Model.engine()."""
+
+    def __init__(self, model, batch, impl=None):
+        self.torch = _torch()
+        self.lib = nat.lib()
+        self.model = model
+        self.low = Lowering(model)
+        self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
+        self.plan = ctypes.c_void_p()
+        self.max_batch = 0
+        self._pushed = {}
+        self.in_shape = tuple(model.inputs[0].shape[1:])
+        self.out_shapes = [tuple(v.shape) for v in self.low.out_vals]
+        self.out_phys = [(v.C, v.H, v.W) for v in self.low.out_vals]
+        self.n_outputs = len(self.out_shapes)
+        self._create(self._chunk_for(batch))
+
+    # -- plan management -----------------------------------------------------------------------------------------
+    def _chunk_for(self, batch):
+        free, _ = self.torch.cuda.mem_get_info()
+        per_sample = 4 * max(1, self.low.internal_floats_per_sample())
+        cap = max(1, int(0.35 * free) // per_sample)
+        return int(max(1, min(batch, cap)))
+
+    def fits(self, batch):
+        return batch <= self.max_batch or self._chunk_for(batch) <= self.max_batch
+
+    def _create(self, max_batch):
+        bufs = (nat.BufferDesc * len(self.low.buffers))()
+        for i, b in enumerate(self.low.buffers):
+            bufs[i] = nat.BufferDesc(b['kind'], b['C'], b['H'], b['W'], b['output_index'], 0)
+        ops = (nat.OpDesc * len(self.low.ops))()
+        names = [f[0] for f in nat.OpDesc._fields_]
+        for i, o in enumerate(self.low.ops):
+            o = dict(o)
+            if o['kind'] == nat.OP_CONV and self.impl:
+                o['impl'] = self.impl
+            ops[i] = nat.OpDesc(*[int(o[n]) for n in names])
+        net = nat.NetDesc(len(bufs), len(ops), len(self.low.weight_layers), int(max_batch), bufs, ops)
+        nat.check(self.lib.dlwp_plan_create(ctypes.byref(net), ctypes.byref(self.plan)), 'dlwp_plan_create')
+        self.max_batch = int(max_batch)
+        self._pushed = {}
+        self.sync_weights()
+
+    def close(self):
+        if self.plan:
+            self.lib.dlwp_plan_destroy(self.plan)
+            self.plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync_weights(self):
+        """Push host-side layer weights (Keras layouts) that changed since the last push."""
+        for wid, layer in enumerate(self.low.weight_layers):
+            if self._pushed.get(wid) == layer._weights_version:
+                continue
+            k = np.ascontiguousarray(layer._weights[0], dtype=np.float32)
+            b = np.ascontiguousarray(layer._weights[1], dtype=np.float32).reshape(-1) if layer.use_bias else None
+            nat.check(self.lib.dlwp_plan_set_weights(
+                self.plan, wid, k.ctypes.data, k.size, b.ctypes.data if b is not None else None,
+                b.size if b is not None else 0), 'dlwp_plan_set_weights')
+            self._pushed[wid] = layer._weights_version
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    # -- one model application -----------------------------------------------------------------------------------
+    def forward_device(self, x):
+        """x: CUDA float32 tensor (N, C, H, W), N <= max_batch.  Returns the list of output tensors (on device)."""
+        torch = self.torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        n = x.shape[0]
+        self.sync_weights()
+        outs = [torch.empty((n,) + p, dtype=torch.float32, device=x.device) for p in self.out_phys]
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        nat.check(self.lib.dlwp_plan_forward(self.plan, n, x.data_ptr(), ptrs, self._stream()), 'dlwp_plan_forward')
+        return outs
+
+    def predict(self, x):
+        """numpy (N, C, H, W) -> list of numpy outputs (logical shapes), processed in chunks of max_batch."""
+        torch = self.torch
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        results = [np.empty((n,) + s, np.float32) for s in self.out_shapes]
+        for s in range(0, n, self.max_batch):
+            xd = torch.from_numpy(x[s:s + self.max_batch]).cuda()
+            outs = self.forward_device(xd)
+            for r, o, shp in zip(results, outs, self.out_shapes):
+                r[s:s + self.max_batch] = o.cpu().numpy().reshape((-1,) + shp)
+        return results
+
+    # -- the rollout ---------------------------------------------------------------------------------------------
+    def can_rollout(self):
+        return all(p == self.in_shape for p in self.out_phys)
+
+    def rollout_device(self, x0, iterations, use_graph=True, out=None):
+        """Device-resident rollout.  x0: CUDA (N,C,H,W).  Returns a CUDA tensor (iterations*n_outputs, N, C, H, W)."""
+        torch = self.torch
+        assert x0.is_cuda and x0.dtype == torch.float32 and x0.is_contiguous()
+        n = x0.shape[0]
+        if n > self.max_batch:
+            raise ValueError('batch %d exceeds the plan capacity %d' % (n, self.max_batch))
+        self.sync_weights()
+        shape = (iterations * self.n_outputs, n) + self.in_shape
+        series = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x0.device)
+        assert tuple(series.shape) == shape and series.is_contiguous()
+        nat.check(self.lib.dlwp_rollout(self.plan, n, x0.data_ptr(), series.data_ptr(), int(iterations),
+                                        1 if use_graph else 0, self._stream()), 'dlwp_rollout')
+        return series
+
+    def rollout_host(self, x0, iterations, d2h_group=0, pinned=True):
+        """
+        numpy in -> numpy out through dlwp_rollout_host: H2D of x0, rollout, D2H of the series pipelined behind the
+        compute.  The result lives in pinned host memory from torch's caching host allocator (a fresh array per call).
+        Batches larger than the plan capacity run as independent sample chunks.
+        """
+        torch = self.torch
+        x0 = np.ascontiguousarray(x0, dtype=np.float32)
+        n = x0.shape[0]
+        self.sync_weights()
+        slots = iterations * self.n_outputs
+        shape = (slots, n) + self.in_shape
+        if n <= self.max_batch:
+            buf = torch.empty(shape, dtype=torch.float32, pin_memory=pinned)
+            series = buf.numpy()
+            nat.check(self.lib.dlwp_rollout_host(self.plan, n, x0.ctypes.data, series.ctypes.data, int(iterations),
+                                                 int(d2h_group)), 'dlwp_rollout_host')
+            return series
+        series = np.empty(shape, np.float32)
+        for s in range(0, n, self.max_batch):
+            part = self.rollout_host(x0[s:s + self.max_batch], iterations, d2h_group, pinned)
+            series[:, s:s + self.max_batch] = part
+        return series

@@ -1,0 +1,179 @@
+/*
+ * dlwp_b200.h -- C ABI of libdlwp_b200.so, the B200-native implementation of DLWP's forecast-rollout hot path.
+ *
+ * The reference (jweyn/DLWP @ 3f32bfab) is pure Python on Keras/TensorFlow and has NO FFI: what "calls" the arithmetic
+ * is `keras.Model.predict` (DLWP/model/models.py:241, :412) inside the Python rollout loops
+ * (DLWP/model/models.py:247-301, :414-452).  This header is the boundary a maintainer would bind from Python
+ * (ctypes) to replace exactly those calls.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no torch / numpy types.  Device pointers are raw `float*` in the CUDA device's address
+ *     space (e.g. torch.Tensor.data_ptr()); `dlwp_stream_t` is a `cudaStream_t` passed as an opaque pointer.
+ *   - all tensors are fp32, channels_first: (N, C, H, W) with explicit element strides for N, C and H (W is
+ *     contiguous), so channel slices (`slice_layer`, DLWP/custom.py:675-692) and channel concatenation
+ *     (`keras.layers.concatenate(axis=1)`) are pointer arithmetic, not copies.
+ *   - every function returns 0 on success, a negative DLWP_E* code for argument errors, or a positive `cudaError_t`;
+ *     nothing throws; `dlwp_last_error_string()` returns a thread-local description of the last failure.
+ *   - all device work is asynchronous on the stream passed in, unless the name ends in `_host`.
+ *   - the caller owns every pointer it passes; a DlwpPlan owns its weights, workspace and CUDA graphs.
+ */
+#ifndef DLWP_B200_H
+#define DLWP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLWP_B200_ABI_VERSION 1
+
+typedef void* dlwp_stream_t; /* cudaStream_t */
+
+enum {
+    DLWP_OK = 0,
+    DLWP_EINVAL = -1,   /* bad argument (null pointer, unknown enum, ...)            */
+    DLWP_ESHAPE = -2,   /* inconsistent or unsupported tensor geometry               */
+    DLWP_EARCH = -3,    /* no sm_100 device / kernel image missing                   */
+    DLWP_ENOMEM = -4,   /* workspace allocation failed                               */
+    DLWP_ESTATE = -5    /* call sequence error (e.g. weights not set before forward) */
+};
+
+/* Padding applied (logically) in front of a convolution.  PERIODIC = PeriodicPadding2D (DLWP/custom.py:191-214),
+ * ZERO = keras ZeroPadding2D.  One mode per axis; the example nets use PERIODIC on W (longitude) and ZERO on H. */
+enum { DLWP_PAD_ZERO = 0, DLWP_PAD_PERIODIC = 1 };
+
+/* Conv2D `activation=` values used by the example nets (examples/train.py:159-219). */
+enum { DLWP_ACT_LINEAR = 0, DLWP_ACT_TANH = 1, DLWP_ACT_RELU = 2 };
+
+/* Kernel selection. AUTO picks the fastest applicable implementation; the others force one (tests, A/B timing). */
+enum {
+    DLWP_IMPL_AUTO = 0,
+    DLWP_IMPL_DIRECT = 1,     /* one thread per output element, any geometry (reference CUDA kernel)              */
+    DLWP_IMPL_FFMA = 2,       /* register-tiled fp32 FFMA kernel, input tiles staged with cp.async                */
+    DLWP_IMPL_FFMA_TMA = 3    /* same math, input tiles staged by TMA (cp.async.bulk.tensor) + in-smem wrap fix-up */
+};
+
+/* Geometry of one fused [periodic/zero pad] -> Conv2D('valid', stride 1, dilation) -> bias -> activation.
+ *   out[n,o,y,x] = act( b[o] + sum_{c,i,j} w[i,j,c,o] * X(n, c, y + dil_h*i - pad_t, x + dil_w*j - pad_l) )
+ * X is the (optionally 2x2-max-pooled or nearest-2x-upsampled) source, wrapped modulo the axis length where the axis
+ * mode is PERIODIC and 0 outside the axis where it is ZERO.  H_out = H_in + pad_t + pad_b - dil_h*(kh-1), likewise W.
+ * Weights use the Keras layout (kh, kw, Cin, Cout); `rowwise` selects RowConnected2D (DLWP/custom.py:695-896): weights
+ * (H_out, kh, kw, Cin, Cout) and bias (H_out, Cout). */
+typedef struct DlwpConvDesc {
+    int32_t N, Cin, H, W;                     /* source dims as stored (before pre_op)                           */
+    int32_t Cout, kh, kw, dil_h, dil_w;
+    int32_t pad_t, pad_b, pad_l, pad_r;
+    int32_t pad_mode_h, pad_mode_w;           /* DLWP_PAD_*                                                      */
+    int32_t act;                              /* DLWP_ACT_*                                                      */
+    int32_t pre_op;                           /* 0 none, 1 MaxPooling2D(2) on load, 2 UpSampling2D(2) on load    */
+    int32_t rowwise;                          /* 1 = RowConnected2D                                              */
+    int32_t impl;                             /* DLWP_IMPL_*                                                     */
+    int32_t reserved;
+    int64_t x_stride_n, x_stride_c, x_stride_h;   /* element strides of the source                              */
+    int64_t y_stride_n, y_stride_c, y_stride_h;   /* element strides of the destination                         */
+} DlwpConvDesc;
+
+/* ---- stand-alone operators (each replaces one Keras/DLWP.custom layer call inside keras.Model.predict) ---------- */
+
+/* PeriodicPadding2D / ZeroPadding2D + Conv2D (+bias +activation): DLWP/custom.py:191-214 + keras Conv2D as built at
+ * DLWP/model/models.py:97-103; RowConnected2D.call (custom.py:823-837) when desc->rowwise. x, w, bias, y: device. */
+int dlwp_conv2d_fwd(const DlwpConvDesc* desc, const float* x, const float* w, const float* bias, float* y,
+                    dlwp_stream_t stream);
+
+/* Stand-alone PeriodicPadding2D.call / ZeroPadding2D.call (custom.py:191-214): y = pad(x). Strides in elements. */
+int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t, int32_t pad_b,
+               int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n, int64_t xs_c, int64_t xs_h,
+               int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
+
+/* keras MaxPooling2D(2) ('valid', floor) and UpSampling2D(2) (nearest), channels_first. */
+int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
+                   int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
+int dlwp_upsample2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
+                    int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
+/* Strided channel-block copy (materialised concatenate / slice when a zero-copy view is not possible). */
+int dlwp_copy4d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
+                int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
+
+/* ---- the network plan: what keras.Model.predict executes for one model application ------------------------------ */
+
+enum { DLWP_BUF_INTERNAL = 0, DLWP_BUF_INPUT = 1, DLWP_BUF_OUTPUT = 2 };
+enum { DLWP_OP_CONV = 0, DLWP_OP_PAD = 1, DLWP_OP_MAXPOOL = 2, DLWP_OP_UPSAMPLE = 3, DLWP_OP_COPY = 4 };
+
+/* A dense (N, C, H, W) activation. INTERNAL buffers are allocated by the plan; the INPUT buffer and the OUTPUT buffers
+ * are bound to caller memory at run time (dense, contiguous). `output_index` orders the model outputs. */
+typedef struct DlwpBufferDesc {
+    int32_t kind;       /* DLWP_BUF_* */
+    int32_t C, H, W;
+    int32_t output_index;
+    int32_t reserved;
+} DlwpBufferDesc;
+
+/* One op: dst[:, dst_c0:dst_c0+Cout'] = f(src[:, src_c0:src_c0+Cin']). Channel windows implement slice_layer and
+ * concatenate(axis=1) without copies. For DLWP_OP_CONV `conv` carries geometry (strides/N/H/W are filled in by the
+ * plan); `weight_id` indexes the plan's weight table so layers shared between unrolled applications
+ * (examples/train_functional.py:278-281) share storage. */
+typedef struct DlwpOpDesc {
+    int32_t kind;              /* DLWP_OP_* */
+    int32_t src, src_c0, src_c;
+    int32_t dst, dst_c0;
+    int32_t weight_id;         /* conv only, else -1 */
+    int32_t pad_t, pad_b, pad_l, pad_r, pad_mode_h, pad_mode_w;   /* conv and pad */
+    int32_t Cout, kh, kw, dil_h, dil_w, act, pre_op, rowwise, impl; /* conv only */
+} DlwpOpDesc;
+
+typedef struct DlwpNetDesc {
+    int32_t n_buffers;
+    int32_t n_ops;
+    int32_t n_weights;
+    int32_t max_batch;               /* INTERNAL buffers are sized for this many samples */
+    const DlwpBufferDesc* buffers;
+    const DlwpOpDesc* ops;
+} DlwpNetDesc;
+
+typedef struct DlwpPlan DlwpPlan;
+
+/* Build the executable form of a Keras graph (replaces graph construction at DLWP/model/models.py:96-112, :349-373). */
+int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** plan);
+void dlwp_plan_destroy(DlwpPlan* plan);
+
+/* keras `layer.set_weights([kernel, bias])` / `get_weights()` (DLWP/custom.py:126,136; DLWP/util.py:180).
+ * HOST pointers, Keras layouts: kernel (kh,kw,Cin,Cout) [rowwise: (H_out,kh,kw,Cin,Cout)], bias (Cout) [rowwise:
+ * (H_out,Cout)], bias may be NULL (use_bias=False). Synchronous. */
+int dlwp_plan_set_weights(DlwpPlan* plan, int32_t weight_id, const float* kernel, int64_t kernel_elems,
+                          const float* bias, int64_t bias_elems);
+int dlwp_plan_get_weights(DlwpPlan* plan, int32_t weight_id, float* kernel, int64_t kernel_elems, float* bias,
+                          int64_t bias_elems);
+
+/* One model application on N <= max_batch samples: keras.Model.predict (DLWP/model/models.py:241, :412).
+ * x: device (N,C,H,W); outputs[k]: device, dense, one per model output. */
+int dlwp_plan_forward(DlwpPlan* plan, int32_t N, const float* x, float* const* outputs, dlwp_stream_t stream);
+
+/* The rollout loop of DLWPNeuralNet.predict_timeseries (models.py:277-293, non-step_sequence branch) and
+ * DLWPFunctional.predict_timeseries (models.py:439-447): `iterations` model applications, each fed the LAST output of
+ * the previous one, every output stored.  series: device (iterations * n_outputs, N, C, H, W); step t reads series
+ * slot t*n_outputs-1 directly (no state copy).  Requires every output shape == input shape.
+ * use_graph != 0 captures the whole rollout into one CUDA graph (cached per (N, iterations, x0, series)). */
+int dlwp_rollout(DlwpPlan* plan, int32_t N, const float* x0, float* series, int32_t iterations, int32_t use_graph,
+                 dlwp_stream_t stream);
+
+/* Same with HOST buffers (numpy in / numpy out, like the reference's API): H2D of x0, rollout, D2H of the series
+ * pipelined behind the compute in groups of `d2h_group` iterations. Pinned host memory gives full PCIe speed. Blocking.
+ * The plan keeps the device buffers for reuse. */
+int dlwp_rollout_host(DlwpPlan* plan, int32_t N, const float* x0_host, float* series_host, int32_t iterations,
+                      int32_t d2h_group);
+
+/* ---- introspection --------------------------------------------------------------------------------------------- */
+
+const char* dlwp_last_error_string(void);
+int dlwp_abi_version(void);
+/* Number of kernels this library launched since load (all streams); bench.py reports the delta as gpu_launches. */
+int64_t dlwp_kernel_launch_count(void);
+/* Name of the implementation AUTO would choose for this descriptor ("direct", "ffma", "ffma_tma"). */
+const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLWP_B200_H */

@@ -1,0 +1,203 @@
+"""
+CPU-only tests of the boundary: the C-ABI library loads and exports every declared symbol, the front end builds the
+example nets unchanged and infers Keras shapes, the graph lowers to the expected fused ops, and argument errors match the
+reference's exception types.  No kernel is launched here.
+"""
+
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from oracle import layers as OL
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def nat():
+    from dlwp_b200 import build
+    build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
+    from dlwp_b200 import _native
+    return _native
+
+
+def test_library_exports_every_declared_symbol(nat):
+    header = open(os.path.join(REPO, 'include', 'dlwp_b200.h')).read()
+    declared = set(re.findall(r'\b(dlwp_[a-z0-9_]+)\s*\(', header))
+    declared -= {'dlwp_stream_t'}
+    assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dlwp_abi_version() == 1
+    assert lib.dlwp_kernel_launch_count() == 0
+
+
+def test_struct_layouts_match_header(nat):
+    assert ctypes.sizeof(nat.ConvDesc) == 20 * 4 + 6 * 8
+    assert ctypes.sizeof(nat.BufferDesc) == 6 * 4
+    assert ctypes.sizeof(nat.OpDesc) == 22 * 4
+    assert ctypes.sizeof(nat.NetDesc) == 4 * 4 + 2 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_library_has_tma_and_no_torch_dependency(nat):
+    import subprocess
+    out = subprocess.run(['ldd', nat.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'torch' not in out and 'libcuda.so' not in out
+
+
+def test_build_model_validation_errors():
+    from dlwp_b200.model import DLWPFunctional, DLWPNeuralNet
+    m = DLWPNeuralNet(scaler_type=None, scale_targets=False)
+    with pytest.raises(TypeError):
+        m.build_model(layers='Conv2D')
+    with pytest.raises(TypeError):
+        m.build_model(layers=(('Conv2D', (1, 1), {}),), gpus=1.0)
+    with pytest.raises(TypeError):
+        m.build_model(layers=('Conv2D',))
+    with pytest.raises(ValueError):
+        m.build_model(layers=(('Conv2D', (1, 1)),))
+    with pytest.raises(TypeError):
+        m.build_model(layers=(('Conv2D', [1, 1], {}),))
+    with pytest.raises(TypeError):
+        m.build_model(layers=(('Conv2D', (1, 1), []),))
+    with pytest.raises(AttributeError):
+        m.build_model(layers=(('NoSuchLayer', None, None),))
+    with pytest.raises(ValueError):
+        DLWPNeuralNet(time_dim=0)
+    with pytest.raises(ValueError):
+        DLWPFunctional(time_dim=0)
+    with pytest.raises(TypeError):
+        DLWPFunctional().build_model(None, gpus='1')
+
+
+def test_net_a_builds_from_reference_layer_tuples_and_lowers_to_two_fused_convs(nat):
+    from dlwp_b200.engine import Lowering
+    from tests.helpers import build_product_sequential
+    dlwp = build_product_sequential(OL.net_a_layers())
+    model = dlwp.model
+    assert [l.__class__.__name__ for l in model.layers] == ['PeriodicPadding2D', 'ZeroPadding2D', 'Conv2D'] * 2
+    assert model.layers[0].output_shape == (None, 6, 91, 184)
+    assert model.layers[1].output_shape == (None, 6, 95, 184)
+    assert model.layers[2].output_shape == (None, 32, 91, 180)
+    assert model.output_shape == (None, 6, 91, 180)
+    assert model.count_params() == 6566
+    assert [w.shape for w in model.get_weights()] == [(3, 3, 6, 32), (32,), (5, 5, 32, 6), (6,)]
+    low = Lowering(model)
+    assert [o['kind'] for o in low.ops] == [nat.OP_CONV, nat.OP_CONV]       # no pad op, no copy
+    for o in low.ops:
+        assert (o['pad_t'], o['pad_b'], o['pad_l'], o['pad_r']) == (2, 2, 2, 2)
+        assert (o['pad_mode_h'], o['pad_mode_w']) == (nat.PAD_ZERO, nat.PAD_PERIODIC)
+    assert [b['kind'] for b in low.buffers] == [nat.BUF_INPUT, nat.BUF_INTERNAL, nat.BUF_OUTPUT]
+
+
+def test_keras_shapes_follow_oracle_for_example_stack():
+    """The full convolutional stack of examples/train.py:159-221 (non-recurrent part)."""
+    from tests.helpers import build_product_sequential
+    cf = 'channels_first'
+    cs = (8, 36, 72)
+    conv = lambda f, k, d, a: ('Conv2D', (f, k), {'dilation_rate': d, 'padding': 'valid', 'activation': a,
+                                                  'data_format': cf})
+    pp = lambda p: ('PeriodicPadding2D', ((0, p),), {'data_format': cf})
+    zp = lambda p: ('ZeroPadding2D', ((p, 0),), {'data_format': cf})
+    layers = (('PeriodicPadding2D', ((0, 2),), {'data_format': cf, 'input_shape': cs}), zp(2), conv(32, 3, 2, 'tanh'),
+              ('MaxPooling2D', (2,), {'data_format': cf}), pp(1), zp(1), conv(64, 3, 1, 'tanh'),
+              ('MaxPooling2D', (2,), {'data_format': cf}), pp(1), zp(1), conv(128, 3, 1, 'tanh'),
+              ('UpSampling2D', (2,), {'data_format': cf}), pp(1), zp(1), conv(64, 3, 1, 'tanh'),
+              ('UpSampling2D', (2,), {'data_format': cf}), pp(2), zp(2), conv(32, 3, 2, 'tanh'),
+              pp(2), zp(2), conv(8, 5, 1, 'linear'), ('Reshape', (cs,), None))
+    dlwp = build_product_sequential(layers)
+    onet = OL.OSequential(layers)
+    s = cs
+    for kl, ol in zip(dlwp.model.layers, onet.layers):
+        s = ol.output_shape(s)
+        assert kl.output_shape == (None,) + tuple(s), kl.name
+    assert dlwp.model.output_shape == (None,) + cs
+
+
+def test_skip_model_lowering_has_no_pad_ops_and_elides_producer_copies(nat):
+    from dlwp_b200.engine import Lowering
+    from tests.helpers import build_functional_pair
+    dlwp, _ = build_functional_pair((12, 16, 24), skip=True, integration_steps=2)
+    assert dlwp._n_steps == 2
+    low = Lowering(dlwp.model)
+    kinds = [o['kind'] for o in low.ops]
+    assert nat.OP_PAD not in kinds
+    assert kinds.count(nat.OP_CONV) == 12 and kinds.count(nat.OP_COPY) == 4   # only the slice->concat skips copy
+    assert sorted(o['weight_id'] for o in low.ops if o['kind'] == nat.OP_CONV) == sorted(list(range(6)) * 2)
+    outs = [b for b in low.buffers if b['kind'] == nat.BUF_OUTPUT]
+    assert sorted(b['output_index'] for b in outs) == [0, 1]
+
+
+def test_padding_argument_normalisation_and_errors():
+    from dlwp_b200.custom import PeriodicPadding2D, slice_layer
+    assert PeriodicPadding2D(2).padding == ((2, 2), (2, 2))
+    assert PeriodicPadding2D((0, 2)).padding == ((0, 0), (2, 2))
+    assert PeriodicPadding2D(((1, 2), (3, 0))).padding == ((1, 2), (3, 0))
+    with pytest.raises(ValueError):
+        PeriodicPadding2D((1, 2, 3))
+    with pytest.raises(ValueError):
+        slice_layer(0, 4, axis=-1)
+    with pytest.raises(ValueError):
+        PeriodicPadding2D((1, 1), data_format='bogus')
+
+
+def test_registry_lookup_order_matches_reference():
+    from dlwp_b200 import util
+    assert util.get_from_class('keras.layers', 'Conv2D').__name__ == 'Conv2D'
+    with pytest.raises(AttributeError):
+        util.get_from_class('keras.layers', 'PeriodicPadding2D')     # not a keras layer ...
+    assert util.get_from_class('DLWP.custom', 'PeriodicPadding2D').pad_mode == 'periodic'  # ... but a DLWP.custom one
+    names = util.get_classes('DLWP.custom')
+    for n in ('PeriodicPadding2D', 'PeriodicPadding3D', 'FillPadding2D', 'TFPadding2D', 'RowConnected2D',
+              'EarlyStoppingMin', 'RNNResetStates'):
+        assert n in names
+    for n in ('slice_layer', 'latitude_weighted_loss', 'anomaly_correlation_loss', 'lat_loss', 'acc_loss'):
+        assert n in util.get_methods('DLWP.custom')
+
+
+def test_wrapper_pickles_without_model_and_model_pickles_without_plan(tmp_path):
+    from dlwp_b200 import util
+    from tests.helpers import build_product_sequential
+    dlwp = build_product_sequential(OL.net_a_layers((6, 12, 16)))
+    w = dlwp.model.get_weights()
+    base = str(tmp_path / 'm')
+    util.save_model(dlwp, base)
+    assert os.path.exists(base + '.keras') and os.path.exists(base + '.pkl')
+    with open(base + '.pkl', 'rb') as f:
+        bare = pickle.load(f)
+    assert bare.model is None and bare.base_model is None
+    back = util.load_model(base)
+    assert back.time_dim == 1 and back.model is back.base_model
+    for a, b in zip(back.model.get_weights(), w):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_compat_aliases_install():
+    import subprocess
+    import sys
+    code = ("import dlwp_b200.compat as c; c.install();"
+            "from DLWP.model import DLWPNeuralNet, DLWPFunctional;"
+            "from DLWP.custom import PeriodicPadding2D, RowConnected2D, slice_layer, RNNResetStates, EarlyStoppingMin,"
+            " latitude_weighted_loss, anomaly_correlation_loss;"
+            "from keras.layers import Input, ZeroPadding2D, ZeroPadding3D, Conv2D, ConvLSTM2D, MaxPooling2D,"
+            " UpSampling2D, Reshape, concatenate;"
+            "from keras.models import Model; from keras.callbacks import History, TensorBoard;"
+            "from keras.regularizers import l2; from keras.losses import mean_squared_error;"
+            "from DLWP.util import save_model, load_model, train_test_split_ind; print('ok')")
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=REPO)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
+
+
+def test_latitude_weights_follow_reference_formula():
+    from dlwp_b200.custom import latitude_weighted_loss
+    from dlwp_b200.keras.losses import mean_squared_error
+    lats = np.linspace(-90, 90, 7)
+    f = latitude_weighted_loss(mean_squared_error, lats, (3, 7, 10), axis=-2, weighting='midlatitude')
+    ref = np.cos(lats * np.pi / 180) + 0.5 * np.sin(lats * 2 * np.pi / 180) ** 2     # custom.py:976-978
+    assert f.weights.shape == (7, 10)
+    np.testing.assert_allclose(f.weights[:, 3], ref, rtol=1e-6, atol=1e-7)
