@@ -63,6 +63,7 @@ SYMBOLS = {
     'dlwp_last_error_string': (ctypes.c_char_p, []),
     'dlwp_abi_version': (ctypes.c_int, []),
     'dlwp_kernel_launch_count': (ctypes.c_int64, []),
+    'dlwp_debug_flags': (ctypes.c_int, []),
     'dlwp_conv2d_impl_name': (ctypes.c_char_p, [ctypes.POINTER(ConvDesc)]),
 }
 

@@ -15,6 +15,11 @@
 //                          STAGE_TMA      one cp.async.bulk.tensor box per chunk; rows beyond the poles arrive as TMA
 //                                         out-of-bounds zeros, the longitude wrap is patched into the halo columns in
 //                                         shared memory from values prefetched while the TMA is in flight.
+#define DLWP_CONV_TU
+#include <cuda_runtime.h>
+namespace dlwp {
+__device__ int g_device_flags = 0;  // bit 0: an mbarrier wait timed out (TMA never completed)
+}
 #include "internal.h"
 
 #include <algorithm>
@@ -109,42 +114,71 @@ constexpr int STAGE_CPASYNC = 0;
 constexpr int STAGE_TMA = 1;
 constexpr int MAX_FIX_PER_THREAD = 8;
 
-template <int KH, int KW, int D, int ROWS, int COUT_T>
+// ---- packed fp32 math (sm_100: FFMA2) -----------------------------------------------------------------------------------
+// fma.rn.f32x2 does two IEEE fp32 FMAs (same rounding as two FFMAs) on 64-bit register pairs.  It halves the FMA
+// instruction count and the register-file reads per flop, which is what lets a register-tiled loop approach the fp32
+// pipe's peak: with scalar FFMA the same loop is limited by operand-bank conflicts (measured ~30-50% of peak).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// LEAD: unused columns in front of the halo (STAGE_TMA only): the TMA box must start on a 16-byte boundary in global
+// memory, so a tile whose halo is pad_l columns wide starts (4 - pad_l % 4) % 4 columns earlier.
+//
+// acc[r][px][cp] holds filters (2cp, 2cp+1) of output pixel (row r, column px) as one packed pair: the weight pairs come
+// straight out of shared memory (16-byte loads of 4 consecutive filters), the input value is duplicated into both lanes.
+template <int KH, int KW, int D, int ROWS, int COUT_T, int LEAD>
 __device__ __forceinline__ void ffma_chunk(const float* __restrict__ in_s, const float* __restrict__ w_s,
-                                           float (&acc)[ROWS][4][COUT_T], const int cc, const int plane,
+                                           f32x2 (&acc)[ROWS][4][COUT_T / 2], const int cc, const int plane,
                                            const int pitch, const int w_plane, const int cout_bp) {
+    static_assert(COUT_T % 2 == 0, "filters are processed in packed pairs");
     constexpr int COUT_LD = (COUT_T + 3) / 4 * 4;
-    static_assert((KW - 1) * D + 4 <= 8, "a thread reads 8 consecutive input floats per row");
+    constexpr int NV = (LEAD + (KW - 1) * D + 4 + 3) / 4 * 4;  // input floats a thread reads per row
 #pragma unroll 1
     for (int c = 0; c < cc; ++c) {
         const float* in_c = in_s + c * plane;
         const float* w_c = w_s + c * w_plane;
 #pragma unroll
         for (int i = 0; i < KH; ++i) {
-            float v[ROWS][8];
+            float v[ROWS][NV];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 const float4* q = reinterpret_cast<const float4*>(in_c + (r + i * D) * pitch);
-                const float4 a = q[0], b = q[1];
-                v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
-                v[r][4] = b.x; v[r][5] = b.y; v[r][6] = b.z; v[r][7] = b.w;
+#pragma unroll
+                for (int q4 = 0; q4 < NV / 4; ++q4) {
+                    const float4 a = q[q4];
+                    v[r][4 * q4 + 0] = a.x; v[r][4 * q4 + 1] = a.y; v[r][4 * q4 + 2] = a.z; v[r][4 * q4 + 3] = a.w;
+                }
             }
 #pragma unroll
             for (int j = 0; j < KW; ++j) {
-                float wv[COUT_LD];
-                const float4* wq = reinterpret_cast<const float4*>(w_c + (i * KW + j) * cout_bp);
+                f32x2 wv[COUT_LD / 2];
+                const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(w_c + (i * KW + j) * cout_bp);
 #pragma unroll
                 for (int q4 = 0; q4 < COUT_LD / 4; ++q4) {
-                    const float4 t = wq[q4];
-                    wv[4 * q4 + 0] = t.x; wv[4 * q4 + 1] = t.y; wv[4 * q4 + 2] = t.z; wv[4 * q4 + 3] = t.w;
+                    const ulonglong2 t = wq[q4];
+                    wv[2 * q4 + 0] = t.x; wv[2 * q4 + 1] = t.y;
                 }
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-                    for (int px = 0; px < 4; ++px)
+                    for (int px = 0; px < 4; ++px) {
+                        const float x = v[r][LEAD + px + j * D];
+                        const f32x2 xx = pack2(x, x);
 #pragma unroll
-                        for (int co = 0; co < COUT_T; ++co)
-                            acc[r][px][co] = fmaf(v[r][px + j * D], wv[co], acc[r][px][co]);
+                        for (int cp = 0; cp < COUT_T / 2; ++cp) acc[r][px][cp] = ffma2(xx, wv[cp], acc[r][px][cp]);
+                    }
             }
         }
     }
@@ -153,6 +187,8 @@ __device__ __forceinline__ void ffma_chunk(const float* __restrict__ in_s, const
 template <int KH, int KW, int D, int ROWS, int COUT_T, int STAGE>
 __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int COUT_LD = (COUT_T + 3) / 4 * 4;
+    constexpr int NAT_PAD = D * (KW - 1) / 2;                                  // the 'same'-style halo of this kernel
+    constexpr int LEAD = (STAGE == STAGE_TMA) ? (4 - NAT_PAD % 4) % 4 : 0;     // host guarantees pad_l == NAT_PAD
     extern __shared__ __align__(128) float smem[];
     auto in_stage = [&](int s) { return smem + s * p.in_stage_floats; };
     auto w_stage = [&](int s) { return smem + 2 * p.in_stage_floats + s * p.w_stage_floats; };
@@ -222,17 +258,19 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
     const int fix_cols = fix_l + fix_r;
     const int nfix = fix_cols * p.CC * p.RIN;
     float hv[MAX_FIX_PER_THREAD];
+    const bool fix_prefetched = nfix <= MAX_FIX_PER_THREAD * nthreads;
     auto fix_decode = [&](int e, int& c, int& r, int& k) {
         const int fc = fix_cols > 0 ? fix_cols : 1;
         const int q = e % fc;
         const int row = e / fc;
         c = row / p.RIN;
         r = row % p.RIN;
-        // left patch columns are k = 0..fix_l-1; right patch columns end at the last column with a valid output tap
-        k = (q < fix_l) ? q : (p.W + p.pad_l - x0) + (q - fix_l);
+        // left patch columns are k = LEAD .. LEAD+fix_l-1; right patch columns start where the source x reaches W
+        k = LEAD + ((q < fix_l) ? q : (p.W + p.pad_l - x0) + (q - fix_l));
     };
     auto prefetch_fix = [&](int chunk) {
         if constexpr (STAGE == STAGE_TMA) {
+        if (!fix_prefetched) return;
         const int c0 = chunk * p.CC;
 #pragma unroll
         for (int u = 0; u < MAX_FIX_PER_THREAD; ++u) {
@@ -242,30 +280,44 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
                 int c, r, k;
                 fix_decode(e, c, r, k);
                 const int gy = y0 + r - p.pad_t;
-                const int gx = wrap_index(x0 + k - p.pad_l, p.W);
+                const int gx = wrap_index(x0 + k - LEAD - p.pad_l, p.W);
                 if (gy >= 0 && gy < p.H && c0 + c < p.Cin)
                     hv[u] = __ldg(xn + (long long)(c0 + c) * p.xs_c + (long long)gy * p.xs_h + gx);
             }
         }
         }
     };
-    auto apply_fix = [&](float* dst) {
+    auto apply_fix = [&](float* dst, int chunk) {
         if constexpr (STAGE == STAGE_TMA) {
+            if (fix_prefetched) {
 #pragma unroll
-        for (int u = 0; u < MAX_FIX_PER_THREAD; ++u) {
-            const int e = tid + u * nthreads;
-            if (e < nfix) {
-                int c, r, k;
-                fix_decode(e, c, r, k);
-                dst[(c * p.RIN + r) * p.PITCH + k] = hv[u];
+                for (int u = 0; u < MAX_FIX_PER_THREAD; ++u) {
+                    const int e = tid + u * nthreads;
+                    if (e < nfix) {
+                        int c, r, k;
+                        fix_decode(e, c, r, k);
+                        dst[(c * p.RIN + r) * p.PITCH + k] = hv[u];
+                    }
+                }
+            } else {  // tiny CTAs (few threads, many halo elements): patch straight from global after the TMA landed
+                const int c0 = chunk * p.CC;
+                for (int e = tid; e < nfix; e += nthreads) {
+                    int c, r, k;
+                    fix_decode(e, c, r, k);
+                    const int gy = y0 + r - p.pad_t;
+                    const int gx = wrap_index(x0 + k - LEAD - p.pad_l, p.W);
+                    float val = 0.f;
+                    if (gy >= 0 && gy < p.H && c0 + c < p.Cin)
+                        val = __ldg(xn + (long long)(c0 + c) * p.xs_c + (long long)gy * p.xs_h + gx);
+                    dst[(c * p.RIN + r) * p.PITCH + k] = val;
+                }
             }
-        }
         }
     };
     auto issue_tma = [&](int chunk, int s) {
         if (STAGE == STAGE_TMA && tid == 0) {
             mbar_expect_tx(&mbar[s], (uint32_t)(p.CC * plane * sizeof(float)));
-            tma_load_4d(in_stage(s), &tmap, &mbar[s], x0 - p.pad_l, y0 - p.pad_t, chunk * p.CC, n);
+            tma_load_4d(in_stage(s), &tmap, &mbar[s], x0 - p.pad_l - LEAD, y0 - p.pad_t, chunk * p.CC, n);
         }
     };
 
@@ -279,13 +331,13 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
         __syncthreads();
     }
 
-    float acc[ROWS][4][COUT_T];
+    f32x2 acc[ROWS][4][COUT_T / 2];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
         for (int px = 0; px < 4; ++px)
 #pragma unroll
-            for (int co = 0; co < COUT_T; ++co) acc[r][px][co] = 0.f;
+            for (int cp = 0; cp < COUT_T / 2; ++cp) acc[r][px][cp] = 0ull;
 
     // ---- pipeline: chunk k+1 is in flight while chunk k is consumed ------------------------------------------------
     if (STAGE == STAGE_TMA) issue_tma(0, 0);
@@ -304,7 +356,7 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
         if (STAGE == STAGE_TMA) {
             prefetch_fix(k);
             mbar_wait(&mbar[s], (k >> 1) & 1);
-            apply_fix(in_stage(s));
+            apply_fix(in_stage(s), k);
         }
         if (k + 1 < p.nchunks) cp_async_wait<1>();
         else cp_async_wait<0>();
@@ -312,7 +364,7 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
 
         if (active) {
             const int cc = min(p.CC, p.Cin - k * p.CC);
-            ffma_chunk<KH, KW, D, ROWS, COUT_T>(in_stage(s) + (rg * ROWS) * p.PITCH + 4 * xg,
+            ffma_chunk<KH, KW, D, ROWS, COUT_T, LEAD>(in_stage(s) + (rg * ROWS) * p.PITCH + 4 * xg,
                                                 w_stage(s) + cg * COUT_LD, acc, cc, plane, p.PITCH, w_plane,
                                                 p.COUT_BP);
         }
@@ -336,11 +388,18 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
             if (o >= p.Cout) continue;
             const float b = p.bias ? __ldg(p.bias + o) : 0.f;
             float* dst = p.y + (long long)n * p.ys_n + (long long)o * p.ys_c + (long long)yo * p.ys_h + xo;
+            float a4[4];
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                float lo, hi;
+                unpack2(acc[r][px][co / 2], lo, hi);
+                a4[px] = (co & 1) ? hi : lo;
+            }
             float4 v;
-            v.x = apply_act(acc[r][0][co] + b, p.act);
-            v.y = apply_act(acc[r][1][co] + b, p.act);
-            v.z = apply_act(acc[r][2][co] + b, p.act);
-            v.w = apply_act(acc[r][3][co] + b, p.act);
+            v.x = apply_act(a4[0] + b, p.act);
+            v.y = apply_act(a4[1] + b, p.act);
+            v.z = apply_act(a4[2] + b, p.act);
+            v.w = apply_act(a4[3] + b, p.act);
             if (vec_ok) {
                 *reinterpret_cast<float4*>(dst) = v;
             } else {
@@ -453,7 +512,7 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
+static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     TileChoice tc;
     memset(&tc.p, 0, sizeof(tc.p));
     if (d.rowwise || d.pre_op != 0 || d.dil_h != d.dil_w) return tc;
@@ -468,14 +527,21 @@ static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
     const int Wo = d.W + d.pad_l + d.pad_r - d.dil_w * (d.kw - 1);
     if (Ho <= 0 || Wo <= 0) return tc;
     const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
+    // STAGE_TMA: the box must start on a 16-byte boundary, the kernel is instantiated for the natural halo only
+    const int nat_pad = halo_w / 2;
+    if (use_tma && (d.pad_l != nat_pad || d.pad_mode_h != DLWP_PAD_ZERO || (d.x_stride_h % 4) || (d.x_stride_c % 4) ||
+                    (d.x_stride_n % 4)))
+        return tc;
+    const int lead = use_tma ? (4 - nat_pad % 4) % 4 : 0;
+    const int nv = round_up(lead + halo_w + 4, 4);  // floats a thread reads per input row
 
     TileParams& p = tc.p;
     // --- width: full rows when they fit a TMA box (<= 256 elements) ---
-    p.tiles_x = ceil_div(Wo + halo_w, 256 - 4);
+    p.tiles_x = ceil_div(Wo + nv - 4, 256 - 4);
     p.TW = round_up(ceil_div(Wo, p.tiles_x), 4);
     p.tiles_x = ceil_div(Wo, p.TW);
     p.NXG = p.TW / 4;
-    p.PITCH = round_up(p.TW + halo_w, 4);
+    p.PITCH = p.TW + nv - 4;
 
     // --- filters per CTA ---
     const int groups = ceil_div(d.Cout, cout_t);
@@ -486,8 +552,7 @@ static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
     int th = 2 * std::max(1, std::min(8, 384 / (p.NXG * ncg)));
     while (th > 2 && p.NXG * (th / 2) * ncg > 384) th -= 2;
     th = std::min(th, round_up(Ho, 2));
-    // prefer a TH that divides Ho evenly (91 = 13 x 7 is not available with even TH: minimise the padded rows)
-    {
+    {   // prefer a nearby TH that wastes fewer padded rows (91 rows: 16 -> 96, 14 -> 98, 12 -> 96)
         int best = th, best_waste = round_up(Ho, th) - Ho;
         for (int t = th; t >= std::max(2, th - 4); t -= 2) {
             const int waste = round_up(Ho, t) - Ho;
@@ -507,7 +572,7 @@ static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
     p.COUT_BP = ncg * cout_ld;
 
     // --- channel chunk: two stages of (input tile + weights) should leave room for 2 CTAs per SM ---
-    const int budget = 100 * 1024;
+    const int budget = env_int("DLWP_TILE_SMEM_KB", 100) * 1024;
     int cc = std::min(d.Cin, 16);
     auto stage_bytes = [&](int c) {
         return (size_t)(round_up(c * p.RIN * p.PITCH, 32) + round_up(c * d.kh * d.kw * p.COUT_BP, 32)) * 4;
@@ -526,31 +591,31 @@ static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
     p.pad_t = d.pad_t; p.pad_l = d.pad_l; p.mode_h = d.pad_mode_h; p.mode_w = d.pad_mode_w; p.act = d.act;
     p.xs_n = d.x_stride_n; p.xs_c = d.x_stride_c; p.xs_h = d.x_stride_h;
     p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
-    // halo columns to patch under TMA staging: left edge tile columns [0, pad_l); right edge tile: columns whose
-    // source x >= W, i.e. k in [W + pad_l - x0_last, needed)
+    // halo columns patched under TMA staging: the pad_l columns left of x = 0 (first tile) and the columns whose
+    // source x >= W that a valid output can touch (last tile)
     p.fix_l = d.pad_l;
     {
         const int x0_last = (p.tiles_x - 1) * p.TW;
-        const int needed = std::min(p.PITCH, Wo - x0_last + halo_w);  // columns any valid output can touch
+        const int needed = Wo - x0_last + halo_w;  // halo-relative columns any valid output of the last tile touches
         p.fix_r = std::max(0, needed - (d.W + d.pad_l - x0_last));
     }
     tc.threads = round_up(p.NXG * p.NRG * p.NCG, 32);
     tc.grid = dim3(p.tiles_x * p.tiles_y, ceil_div(groups, ncg), d.N);
     tc.cout_t = cout_t;
+    if (use_tma) {
+        const bool fix_ok = d.pad_mode_w == DLWP_PAD_ZERO || (p.fix_l <= d.W && p.fix_r <= d.W);
+        if (!fix_ok || p.PITCH > 256 || p.RIN > 256 || cc > 256) return tc;
+    }
+    tc.impl = use_tma ? DLWP_IMPL_FFMA_TMA : DLWP_IMPL_FFMA;
+    tc.ok = true;
+    return tc;
+}
 
-    // --- staging variant ---
-    bool tma_ok = d.pad_mode_h == DLWP_PAD_ZERO && (d.x_stride_h % 4 == 0) && (d.x_stride_c % 4 == 0) &&
-                  (d.x_stride_n % 4 == 0) && p.PITCH <= 256 && p.RIN <= 256 && cc <= 256 &&
-                  (d.pad_mode_w == DLWP_PAD_ZERO ||
-                   ((p.fix_l + p.fix_r) * cc * p.RIN <= MAX_FIX_PER_THREAD * tc.threads && p.fix_l <= d.W &&
-                    p.fix_r <= d.W)) &&
-                  (p.tiles_x == 1 || p.fix_l + p.fix_r <= p.PITCH);
-    // with more than one tile along W, a single tile must not need both patches unless it is also the only tile
-    if (want_impl == DLWP_IMPL_FFMA) tc.impl = DLWP_IMPL_FFMA;
-    else if (want_impl == DLWP_IMPL_FFMA_TMA) tc.impl = tma_ok ? DLWP_IMPL_FFMA_TMA : DLWP_IMPL_DIRECT;
-    else tc.impl = tma_ok ? DLWP_IMPL_FFMA_TMA : DLWP_IMPL_FFMA;
-    if (want_impl == DLWP_IMPL_AUTO && env_int("DLWP_NO_TMA", 0)) tc.impl = DLWP_IMPL_FFMA;
-    tc.ok = tc.impl != DLWP_IMPL_DIRECT;
+static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
+    TileChoice tc;
+    const bool try_tma = want_impl == DLWP_IMPL_FFMA_TMA || (want_impl == DLWP_IMPL_AUTO && !env_int("DLWP_NO_TMA", 0));
+    if (try_tma) tc = build_tiling(d, true);
+    if (!tc.ok && want_impl != DLWP_IMPL_FFMA_TMA) tc = build_tiling(d, false);
     return tc;
 }
 
@@ -639,3 +704,11 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
 }
 
 }  // namespace dlwp
+
+// Read-and-clear the device-side diagnostic flags (bit 0: a TMA mbarrier wait timed out). Synchronises the device.
+extern "C" int dlwp_debug_flags(void) {
+    int v = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&v, dlwp::g_device_flags, sizeof(int)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(dlwp::g_device_flags, &zero, sizeof(int));
+    return v;
+}

@@ -65,18 +65,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// tanh accurate to a few 1e-7 relative: odd polynomial below 0.3, (1-e)/(1+e) with e = exp(-2|x|) above.
-// (tanh.approx.f32 is only good to 2^-11 -- not enough for the 1e-4 / 50-step parity gate.)
+// tanh(x) = 1 - 2 / (1 + exp(2x)) with ex2.approx / rcp.approx: 5 instructions, absolute error ~2e-7 everywhere
+// (ex2.approx is good to 2 ulp, rcp.approx to 1 ulp; saturates correctly to +-1).  tanh.approx.f32 (2^-11 relative)
+// would not pass the 1e-4 / 50-step parity gate.
 __device__ __forceinline__ float tanh_accurate(float x) {
-    const float ax = fabsf(x);
-    const float x2 = ax * ax;
-    float p = fmaf(x2, 0.021869488536155203f, -0.053968253968253971f);  // 62/2835, -17/315
-    p = fmaf(x2, p, 0.13333333333333333f);                              // 2/15
-    p = fmaf(x2, p, -0.33333333333333333f);                             // -1/3
-    p = fmaf(x2 * ax, p, ax);
-    const float e = __expf(-2.0f * ax);
-    const float q = __fdividef(1.0f - e, 1.0f + e);
-    return copysignf(ax < 0.3f ? p : q, x);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));  // exp(2x) = 2^(2x log2 e)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -106,7 +103,8 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// ---- mbarrier + TMA ---------------------------------------------------------------------------------------------
+// ---- mbarrier + TMA (conv.cu only: g_device_flags lives there) ----------------------------------------------------
+#ifdef DLWP_CONV_TU
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -131,11 +129,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a TMA that never completes (bad descriptor) traps the kernel instead of hanging the GPU.
+// Bounded wait: a TMA that never completes (bad descriptor) raises a flag the host can read (dlwp_debug_flags) and
+// lets the kernel finish with garbage instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (1u << 22)) {
+            atomicOr(&g_device_flags, 1);
+            break;
+        }
     }
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -149,6 +151,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+#endif  // DLWP_CONV_TU
 
 }  // namespace dlwp
 #endif

@@ -170,6 +170,8 @@ const char* dlwp_last_error_string(void);
 int dlwp_abi_version(void);
 /* Number of kernels this library launched since load (all streams); bench.py reports the delta as gpu_launches. */
 int64_t dlwp_kernel_launch_count(void);
+/* Read-and-clear device-side diagnostic flags; bit 0 = a TMA completion wait timed out. Synchronises the device. */
+int dlwp_debug_flags(void);
 /* Name of the implementation AUTO would choose for this descriptor ("direct", "ffma", "ffma_tma"). */
 const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
 
