@@ -208,7 +208,7 @@ def time_single_kernel(torch, nat, batch, cin, cout, k, d, act, iters):
     b = torch.zeros(cout, device='cuda')
     y = torch.empty((batch, cout, 91, 180), device='cuda')
     desc = nat.ConvDesc(N=batch, Cin=cin, H=91, W=180, Cout=cout, kh=k, kw=k, dil_h=d, dil_w=d, pad_t=2, pad_b=2,
-                        pad_l=2, pad_r=2, pad_mode_h=0, pad_mode_w=1, act=act, pre_op=0, rowwise=0, impl=0, reserved=0,
+                        pad_l=2, pad_r=2, pad_mode_h=0, pad_mode_w=1, act=act, pre_op=0, rowwise=0, impl=0, reserved=0, row_begin=0, row_end=0,
                         x_stride_n=cin * 91 * 180, x_stride_c=91 * 180, x_stride_h=180, y_stride_n=cout * 91 * 180,
                         y_stride_c=91 * 180, y_stride_h=180)
     lib = nat.lib()
@@ -347,6 +347,81 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_latband(args, rank, world, local_rank):
+    """
+    N > 1: the north-star partition -- every GPU owns a latitude band of ALL B forecasts and exchanges a 4-row halo of the
+    state with its neighbours once per step (one grouped NCCL SendRecv).  Strong scaling: the global batch stays B.
+    """
+    import torch
+    import torch.distributed as dist
+    from dlwp_b200 import _native as nat
+    from dlwp_b200.parallel import LatBandEngine, halo_summary
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    dlwp = build_model()
+    eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist)
+    x0 = make_inputs(B)                                    # the same global state on every rank
+    xd = torch.from_numpy(x0).cuda()
+    series = torch.empty((K, B) + STATE, dtype=torch.float32, device='cuda')
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.rollout_device(xd, W, out=series[:W])              # W untimed warm-up steps (also warms NCCL P2P channels)
+    barrier()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        eng.rollout_device(xd, K, out=series)              # EXACTLY K timed steps, K-1 halo exchanges
+        e1.record()
+        barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = nat.launch_count() - launches0
+    value = B * K / (ms * 1e-3)
+
+    # end to end: H2D of x0, rollout, D2H of this rank's band of every state (host concatenation along H is free)
+    Ke = min(K, args.e2e_steps)
+    x0_pinned = torch.from_numpy(x0).pin_memory()
+    eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))   # warm the pinned pool
+    barrier()
+    t0 = time.perf_counter()
+    band = eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    rows = eng.me.band[1] - eng.me.band[0]
+    if rank == 0:
+        halo = halo_summary(eng.planners[min(1, world - 1)], B, STATE[0], STATE[2])
+        per_dir = halo['bytes_per_row'] * 4
+        line = {
+            'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'global_batch': B,
+                       'state': list(STATE), 'parallelism': 'latband%d (91 latitude rows split over %d GPUs, halo 4 rows)'
+                       % (world, world), 'bands': [list(p.band) for p in eng.planners],
+                       'halo': {'rows_per_side': 4, 'bytes_per_neighbour_per_direction_per_step': per_dir,
+                                'collective': 'one grouped NCCL SendRecv per step',
+                                'link_time_us_at_770GBs': per_dir / 770e9 * 1e6,
+                                'fraction_of_step_time': per_dir / 770e9 / (ms / K * 1e-3)},
+                       'l2': 'per-step working set >> L2 at this batch; no flush', 'e2e_steps': Ke},
+            'e2e': {'value': B * Ke / dt, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': B * int(np.prod(STATE)) * 4 / Ke,
+                    'd2h_bytes_per_step': B * STATE[0] * rows * STATE[2] * 4,
+                    'api': 'LatBandEngine.rollout_device + band_to_host (per-rank band)', 'steps': Ke, 'seconds': dt},
+            'gpu_launches': launches, 'clocks': clocks.summary(),
+            'roofline': None, 'cpu_baseline': None,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -356,6 +431,8 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=40, help='steps of the host-API measurement (<= --steps)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--parallel', default='latband', choices=['latband', 'batch'],
+                    help='N>1: latitude bands + halo exchange (north star, strong scaling) or independent forecasts per GPU')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -366,7 +443,10 @@ def main():
     if world == 1 and args.gpus > 1:
         raise SystemExit('launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d '
                          '--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ...' % (args.gpus, args.gpus))
-    run_ours(args, rank, world, local_rank)
+    if world > 1 and args.parallel == 'latband':
+        run_latband(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == '__main__':

@@ -25,7 +25,7 @@ fptr = ctypes.c_void_p
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, i32) for n in ('N', 'Cin', 'H', 'W', 'Cout', 'kh', 'kw', 'dil_h', 'dil_w', 'pad_t', 'pad_b',
                                    'pad_l', 'pad_r', 'pad_mode_h', 'pad_mode_w', 'act', 'pre_op', 'rowwise', 'impl',
-                                   'reserved')] + \
+                                   'reserved', 'row_begin', 'row_end')] + \
                [(n, i64) for n in ('x_stride_n', 'x_stride_c', 'x_stride_h', 'y_stride_n', 'y_stride_c',
                                    'y_stride_h')]
 
@@ -37,7 +37,7 @@ class BufferDesc(ctypes.Structure):
 class OpDesc(ctypes.Structure):
     _fields_ = [(n, i32) for n in ('kind', 'src', 'src_c0', 'src_c', 'dst', 'dst_c0', 'weight_id', 'pad_t', 'pad_b',
                                    'pad_l', 'pad_r', 'pad_mode_h', 'pad_mode_w', 'Cout', 'kh', 'kw', 'dil_h', 'dil_w',
-                                   'act', 'pre_op', 'rowwise', 'impl')]
+                                   'act', 'pre_op', 'rowwise', 'impl', 'row_begin', 'row_end')]
 
 
 class NetDesc(ctypes.Structure):
@@ -52,6 +52,7 @@ SYMBOLS = {
     'dlwp_maxpool2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_upsample2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_copy4d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_rows_op': (ctypes.c_int, [i32, fptr, fptr] + [i32] * 10 + [i64] * 6 + [i32, i32, ctypes.c_void_p]),
     'dlwp_plan_create': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(ctypes.c_void_p)]),
     'dlwp_plan_destroy': (None, [ctypes.c_void_p]),
     'dlwp_plan_set_weights': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, i64, fptr, i64]),

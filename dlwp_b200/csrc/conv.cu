@@ -40,6 +40,7 @@ struct DirectParams {
     int N, Cin, Hs, Ws;  // source dims as stored
     int H, W;            // logical input dims after pre_op
     int Cout, Ho, Wo, kh, kw, dh, dw, pad_t, pad_l, mode_h, mode_w, act, pre_op, rowwise;
+    int row0, rows;      // output row window
     long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;
 };
 
@@ -54,13 +55,13 @@ __device__ __forceinline__ float load_logical(const DirectParams& p, const float
 }
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) {
-    const long long total = (long long)p.N * p.Cout * p.Ho * p.Wo;
+    const long long total = (long long)p.N * p.Cout * p.rows * p.Wo;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int xo = (int)(idx % p.Wo);
         long long t = idx / p.Wo;
-        const int yo = (int)(t % p.Ho);
-        t /= p.Ho;
+        const int yo = p.row0 + (int)(t % p.rows);
+        t /= p.rows;
         const int o = (int)(t % p.Cout);
         const int n = (int)(t / p.Cout);
         const float* w = p.w;
@@ -98,6 +99,7 @@ struct TileParams {
     const float* bias;
     float* y;
     int N, Cin, H, W, Cout, Ho, Wo;
+    int row0, row1;    // output rows [row0, row1) computed by this launch (latitude band)
     int pad_t, pad_l, mode_h, mode_w, act;
     long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;
     int TH, TW;        // output tile (TW multiple of 4, TH multiple of ROWS)
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
     const int nthreads = blockDim.x;
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    const int x0 = tx * p.TW, y0 = p.row0 + ty * p.TH;
     const int cout0 = blockIdx.y * (p.NCG * COUT_T);
     const int n = blockIdx.z;
 
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(384) conv_ffma_kernel(const TileParams p, cons
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int yo = y0 + rg * ROWS + r;
-        if (yo >= p.Ho) continue;
+        if (yo >= p.row1) continue;
 #pragma unroll
         for (int co = 0; co < COUT_T; ++co) {
             const int o = cout0 + cg * COUT_T + co;
@@ -523,9 +525,13 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     else cout_t = (d.Cout > 6) ? 8 : 6;
     if (!find_kernel(d.kh, d.kw, d.dil_h, cout_t, STAGE_CPASYNC)) return tc;
 
-    const int Ho = d.H + d.pad_t + d.pad_b - d.dil_h * (d.kh - 1);
+    const int Ho_full = d.H + d.pad_t + d.pad_b - d.dil_h * (d.kh - 1);
     const int Wo = d.W + d.pad_l + d.pad_r - d.dil_w * (d.kw - 1);
-    if (Ho <= 0 || Wo <= 0) return tc;
+    if (Ho_full <= 0 || Wo <= 0) return tc;
+    const int row0 = (d.row_begin == 0 && d.row_end == 0) ? 0 : d.row_begin;
+    const int row1 = (d.row_begin == 0 && d.row_end == 0) ? Ho_full : d.row_end;
+    const int Ho = row1 - row0;  // rows this launch computes (a latitude band, or everything)
+    if (Ho <= 0) return tc;
     const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
     // STAGE_TMA: the box must start on a 16-byte boundary, the kernel is instantiated for the natural halo only
     const int nat_pad = halo_w / 2;
@@ -587,7 +593,8 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     tc.smem = (size_t)(2 * p.in_stage_floats + 2 * p.w_stage_floats) * 4 + 64;
     if (tc.smem > (size_t)g_smem_optin) return tc;
 
-    p.N = d.N; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Cout = d.Cout; p.Ho = Ho; p.Wo = Wo;
+    p.N = d.N; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Cout = d.Cout; p.Ho = Ho_full; p.Wo = Wo;
+    p.row0 = row0; p.row1 = row1;
     p.pad_t = d.pad_t; p.pad_l = d.pad_l; p.mode_h = d.pad_mode_h; p.mode_w = d.pad_mode_w; p.act = d.act;
     p.xs_n = d.x_stride_n; p.xs_c = d.x_stride_c; p.xs_h = d.x_stride_h;
     p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
@@ -662,6 +669,9 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
     const int Ho = H + d.pad_t + d.pad_b - d.dil_h * (d.kh - 1);
     const int Wo = W + d.pad_l + d.pad_r - d.dil_w * (d.kw - 1);
     DLWP_REQUIRE(Ho > 0 && Wo > 0, DLWP_ESHAPE, "convolution output would be empty (%d x %d)", Ho, Wo);
+    const bool all_rows = d.row_begin == 0 && d.row_end == 0;
+    DLWP_REQUIRE(all_rows || (d.row_begin >= 0 && d.row_end <= Ho && d.row_begin < d.row_end), DLWP_ESHAPE,
+                 "row window [%d,%d) outside the %d output rows", d.row_begin, d.row_end, Ho);
 
     TileChoice tc;
     if (d.impl != DLWP_IMPL_DIRECT) tc = choose_tiling(d, d.impl);
@@ -697,7 +707,9 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
     p.pre_op = d.pre_op; p.rowwise = d.rowwise;
     p.xs_n = d.x_stride_n; p.xs_c = d.x_stride_c; p.xs_h = d.x_stride_h;
     p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
-    const long long total = (long long)d.N * d.Cout * Ho * Wo;
+    p.row0 = all_rows ? 0 : d.row_begin;
+    p.rows = all_rows ? Ho : d.row_end - d.row_begin;
+    const long long total = (long long)d.N * d.Cout * p.rows * Wo;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)g_num_sms * 32);
     conv_direct_kernel<<<blocks, 256, 0, stream>>>(p);
     return after_launch("conv_direct_kernel");

@@ -13,6 +13,7 @@ struct EwParams {
     int N, C, H, W;      // source dims
     int Ho, Wo;          // destination dims
     int pad_t, pad_l, mode_h, mode_w;
+    int row0, rows;      // destination row window: rows [row0, row0 + rows)
     long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;
 };
 
@@ -20,13 +21,13 @@ enum { EW_PAD = 0, EW_POOL = 1, EW_UP = 2, EW_COPY = 3 };
 
 template <int OP>
 __global__ void __launch_bounds__(256) elementwise_kernel(const EwParams p) {
-    const long long total = (long long)p.N * p.C * p.Ho * p.Wo;
+    const long long total = (long long)p.N * p.C * p.rows * p.Wo;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int xo = (int)(idx % p.Wo);
         long long t = idx / p.Wo;
-        const int yo = (int)(t % p.Ho);
-        t /= p.Ho;
+        const int yo = p.row0 + (int)(t % p.rows);
+        t /= p.rows;
         const int c = (int)(t % p.C);
         const int n = (int)(t / p.C);
         const float* xc = p.x + (long long)n * p.xs_n + (long long)c * p.xs_c;
@@ -52,13 +53,18 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwParams p) {
 }
 
 template <int OP>
-static int launch(const EwParams& p, cudaStream_t stream, const char* name) {
+static int launch(EwParams p, cudaStream_t stream, const char* name, int row_begin = 0, int row_end = 0) {
     int rc = check_device();
     if (rc) return rc;
     DLWP_REQUIRE(p.x && p.y, DLWP_EINVAL, "null tensor pointer");
     DLWP_REQUIRE(p.N > 0 && p.C > 0 && p.H > 0 && p.W > 0 && p.Ho > 0 && p.Wo > 0, DLWP_ESHAPE,
                  "%s: non-positive dims", name);
-    const long long total = (long long)p.N * p.C * p.Ho * p.Wo;
+    if (row_begin == 0 && row_end == 0) row_end = p.Ho;
+    DLWP_REQUIRE(row_begin >= 0 && row_end <= p.Ho && row_begin < row_end, DLWP_ESHAPE, "%s: bad row window [%d,%d)",
+                 name, row_begin, row_end);
+    p.row0 = row_begin;
+    p.rows = row_end - row_begin;
+    const long long total = (long long)p.N * p.C * p.rows * p.Wo;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     elementwise_kernel<OP><<<blocks, 256, 0, stream>>>(p);
     return after_launch(name);
@@ -77,7 +83,7 @@ extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_
                  DLWP_EINVAL, "bad pad mode");
     if (mode_h == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_t <= H && pad_b <= H, DLWP_ESHAPE, "periodic pad > axis");
     if (mode_w == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_l <= W && pad_r <= W, DLWP_ESHAPE, "periodic pad > axis");
-    EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w,
+    EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
                xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_PAD>(p, (cudaStream_t)stream, "pad2d");
 }
@@ -85,20 +91,48 @@ extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_
 extern "C" int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
                               int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
                               dlwp_stream_t stream) {
-    EwParams p{x, y, N, C, H, W, H / 2, W / 2, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    EwParams p{x, y, N, C, H, W, H / 2, W / 2, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_POOL>(p, (cudaStream_t)stream, "maxpool2d");
 }
 
 extern "C" int dlwp_upsample2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
                                int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
                                dlwp_stream_t stream) {
-    EwParams p{x, y, N, C, H, W, H * 2, W * 2, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    EwParams p{x, y, N, C, H, W, H * 2, W * 2, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_UP>(p, (cudaStream_t)stream, "upsample2d");
 }
 
 extern "C" int dlwp_copy4d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,
                            int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
                            dlwp_stream_t stream) {
-    EwParams p{x, y, N, C, H, W, H, W, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+    EwParams p{x, y, N, C, H, W, H, W, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_COPY>(p, (cudaStream_t)stream, "copy4d");
+}
+
+extern "C" int dlwp_rows_op(int32_t op, const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                            int32_t pad_t, int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w,
+                            int64_t xs_n, int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h,
+                            int32_t row_begin, int32_t row_end, dlwp_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (op) {
+        case DLWP_OP_PAD: {
+            DLWP_REQUIRE(pad_t >= 0 && pad_b >= 0 && pad_l >= 0 && pad_r >= 0, DLWP_ESHAPE, "negative padding");
+            EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
+                       xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+            return launch<EW_PAD>(p, st, "pad2d", row_begin, row_end);
+        }
+        case DLWP_OP_MAXPOOL: {
+            EwParams p{x, y, N, C, H, W, H / 2, W / 2, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+            return launch<EW_POOL>(p, st, "maxpool2d", row_begin, row_end);
+        }
+        case DLWP_OP_UPSAMPLE: {
+            EwParams p{x, y, N, C, H, W, H * 2, W * 2, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+            return launch<EW_UP>(p, st, "upsample2d", row_begin, row_end);
+        }
+        case DLWP_OP_COPY: {
+            EwParams p{x, y, N, C, H, W, H, W, 0, 0, 0, 0, 0, 0, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
+            return launch<EW_COPY>(p, st, "copy4d", row_begin, row_end);
+        }
+        default: DLWP_REQUIRE(false, DLWP_EINVAL, "dlwp_rows_op: unknown op %d", op);
+    }
 }

@@ -116,23 +116,19 @@ static int run_ops(DlwpPlan* pl, int N, cudaStream_t stream) {
                 d.pad_t = op.pad_t; d.pad_b = op.pad_b; d.pad_l = op.pad_l; d.pad_r = op.pad_r;
                 d.pad_mode_h = op.pad_mode_h; d.pad_mode_w = op.pad_mode_w;
                 d.act = op.act; d.pre_op = op.pre_op; d.rowwise = op.rowwise; d.impl = op.impl;
+                d.row_begin = op.row_begin; d.row_end = op.row_end;
                 d.x_stride_n = xs_n; d.x_stride_c = xs_c; d.x_stride_h = xs_h;
                 d.y_stride_n = ys_n; d.y_stride_c = ys_c; d.y_stride_h = ys_h;
                 rc = conv2d_fwd(d, x, w.k, w.has_bias ? w.b : nullptr, y, stream);
                 break;
             }
             case DLWP_OP_PAD:
-                rc = dlwp_pad2d(x, y, N, op.src_c, s.d.H, s.d.W, op.pad_t, op.pad_b, op.pad_l, op.pad_r,
-                                op.pad_mode_h, op.pad_mode_w, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, stream);
-                break;
             case DLWP_OP_MAXPOOL:
-                rc = dlwp_maxpool2d(x, y, N, op.src_c, s.d.H, s.d.W, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, stream);
-                break;
             case DLWP_OP_UPSAMPLE:
-                rc = dlwp_upsample2d(x, y, N, op.src_c, s.d.H, s.d.W, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, stream);
-                break;
             case DLWP_OP_COPY:
-                rc = dlwp_copy4d(x, y, N, op.src_c, s.d.H, s.d.W, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, stream);
+                rc = dlwp_rows_op(op.kind, x, y, N, op.src_c, s.d.H, s.d.W, op.pad_t, op.pad_b, op.pad_l, op.pad_r,
+                                  op.pad_mode_h, op.pad_mode_w, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, op.row_begin,
+                                  op.row_end, stream);
                 break;
             default: DLWP_REQUIRE(false, DLWP_EINVAL, "op %zu: unknown kind %d", i, op.kind);
         }

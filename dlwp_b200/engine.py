@@ -61,7 +61,7 @@ class Lowering(object):
     def _op(self, kind, src, dst_buf, dst_c0=0, **kw):
         op = dict(kind=kind, src=src.buf, src_c0=src.c0, src_c=src.C, dst=dst_buf, dst_c0=dst_c0, weight_id=-1,
                   pad_t=0, pad_b=0, pad_l=0, pad_r=0, pad_mode_h=0, pad_mode_w=0, Cout=0, kh=0, kw=0, dil_h=1,
-                  dil_w=1, act=0, pre_op=0, rowwise=0, impl=0)
+                  dil_w=1, act=0, pre_op=0, rowwise=0, impl=0, row_begin=0, row_end=0)
         op.update(kw)
         self.ops.append(op)
         return op
@@ -271,11 +271,14 @@ def _torch():
 class CompiledNet(object):
     """A DlwpPlan plus the host-side glue around it.  Created lazily by keras.Model.engine()."""
 
-    def __init__(self, model, batch, impl=None):
+    def __init__(self, model, batch, impl=None, row_windows=None):
+        """row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
+        (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op."""
         self.torch = _torch()
         self.lib = nat.lib()
         self.model = model
         self.low = Lowering(model)
+        self.row_windows = row_windows
         self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
         self.plan = ctypes.c_void_p()
         self.max_batch = 0
@@ -300,12 +303,19 @@ class CompiledNet(object):
         bufs = (nat.BufferDesc * len(self.low.buffers))()
         for i, b in enumerate(self.low.buffers):
             bufs[i] = nat.BufferDesc(b['kind'], b['C'], b['H'], b['W'], b['output_index'], 0)
-        ops = (nat.OpDesc * len(self.low.ops))()
-        names = [f[0] for f in nat.OpDesc._fields_]
+        live = []
         for i, o in enumerate(self.low.ops):
             o = dict(o)
             if o['kind'] == nat.OP_CONV and self.impl:
                 o['impl'] = self.impl
+            if self.row_windows is not None:
+                if self.row_windows[i] is None:
+                    continue
+                o['row_begin'], o['row_end'] = self.row_windows[i]
+            live.append(o)
+        ops = (nat.OpDesc * len(live))()
+        names = [f[0] for f in nat.OpDesc._fields_]
+        for i, o in enumerate(live):
             ops[i] = nat.OpDesc(*[int(o[n]) for n in names])
         net = nat.NetDesc(len(bufs), len(ops), len(self.low.weight_layers), int(max_batch), bufs, ops)
         nat.check(self.lib.dlwp_plan_create(ctypes.byref(net), ctypes.byref(self.plan)), 'dlwp_plan_create')
@@ -350,6 +360,13 @@ class CompiledNet(object):
         ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
         nat.check(self.lib.dlwp_plan_forward(self.plan, n, x.data_ptr(), ptrs, self._stream()), 'dlwp_plan_forward')
         return outs
+
+    def forward_into(self, x, outs):
+        """Like forward_device but into caller-provided dense output tensors (used by the latitude-band driver)."""
+        self.sync_weights()
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        nat.check(self.lib.dlwp_plan_forward(self.plan, x.shape[0], x.data_ptr(), ptrs, self._stream()),
+                  'dlwp_plan_forward')
 
     def predict(self, x):
         """numpy (N, C, H, W) -> list of numpy outputs (logical shapes), processed in chunks of max_batch."""

@@ -71,6 +71,7 @@ typedef struct DlwpConvDesc {
     int32_t rowwise;                          /* 1 = RowConnected2D                                              */
     int32_t impl;                             /* DLWP_IMPL_*                                                     */
     int32_t reserved;
+    int32_t row_begin, row_end;               /* compute only output rows [row_begin, row_end); 0,0 = all rows   */
     int64_t x_stride_n, x_stride_c, x_stride_h;   /* element strides of the source                              */
     int64_t y_stride_n, y_stride_c, y_stride_h;   /* element strides of the destination                         */
 } DlwpConvDesc;
@@ -86,6 +87,12 @@ int dlwp_conv2d_fwd(const DlwpConvDesc* desc, const float* x, const float* w, co
 int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t, int32_t pad_b,
                int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n, int64_t xs_c, int64_t xs_h,
                int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
+/* Row-windowed variants of the data movers (op = DLWP_OP_PAD/MAXPOOL/UPSAMPLE/COPY): only destination rows
+ * [row_begin, row_end) are written. Used by latitude-band plans. */
+int dlwp_rows_op(int32_t op, const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t,
+                 int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n, int64_t xs_c,
+                 int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, int32_t row_begin, int32_t row_end,
+                 dlwp_stream_t stream);
 
 /* keras MaxPooling2D(2) ('valid', floor) and UpSampling2D(2) (nearest), channels_first. */
 int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
@@ -121,6 +128,7 @@ typedef struct DlwpOpDesc {
     int32_t weight_id;         /* conv only, else -1 */
     int32_t pad_t, pad_b, pad_l, pad_r, pad_mode_h, pad_mode_w;   /* conv and pad */
     int32_t Cout, kh, kw, dil_h, dil_w, act, pre_op, rowwise, impl; /* conv only */
+    int32_t row_begin, row_end;    /* destination rows this plan computes ([0,0) = all): latitude-band partitioning */
 } DlwpOpDesc;
 
 typedef struct DlwpNetDesc {

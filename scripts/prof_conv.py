@@ -33,7 +33,7 @@ for lid, (cin, cout, k, d, act) in LAYERS.items():
     y = torch.empty((B, cout, 91, 180), device='cuda')
     desc = nat.ConvDesc(N=B, Cin=cin, H=91, W=180, Cout=cout, kh=k, kw=k, dil_h=d, dil_w=d, pad_t=2, pad_b=2, pad_l=2,
                         pad_r=2, pad_mode_h=0, pad_mode_w=1, act=act, pre_op=0, rowwise=0, impl=nat.IMPLS[args.impl],
-                        reserved=0, x_stride_n=cin * 91 * 180, x_stride_c=91 * 180, x_stride_h=180,
+                        reserved=0, row_begin=0, row_end=0, x_stride_n=cin * 91 * 180, x_stride_c=91 * 180, x_stride_h=180,
                         y_stride_n=cout * 91 * 180, y_stride_c=91 * 180, y_stride_h=180)
     name = lib.dlwp_conv2d_impl_name(ctypes.byref(desc)).decode()
     for _ in range(2):

@@ -104,7 +104,7 @@ def conv_desc(nat, N, Cin, H, W, Cout, kh, kw, d, pads, mode_h, mode_w, act, imp
     Wo = Wl + pl + pr - d * (kw - 1)
     desc = nat.ConvDesc(N=N, Cin=Cin, H=H, W=W, Cout=Cout, kh=kh, kw=kw, dil_h=d, dil_w=d, pad_t=pt, pad_b=pb,
                         pad_l=pl, pad_r=pr, pad_mode_h=mode_h, pad_mode_w=mode_w, act=act, pre_op=pre_op,
-                        rowwise=rowwise, impl=impl, reserved=0, x_stride_n=Cin * H * W, x_stride_c=H * W, x_stride_h=W,
+                        rowwise=rowwise, impl=impl, reserved=0, row_begin=0, row_end=0, x_stride_n=Cin * H * W, x_stride_c=H * W, x_stride_h=W,
                         y_stride_n=Cout * Ho * Wo, y_stride_c=Ho * Wo, y_stride_h=Wo)
     return desc, Ho, Wo
 

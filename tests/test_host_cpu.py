@@ -38,9 +38,9 @@ def test_library_exports_every_declared_symbol(nat):
 
 
 def test_struct_layouts_match_header(nat):
-    assert ctypes.sizeof(nat.ConvDesc) == 20 * 4 + 6 * 8
+    assert ctypes.sizeof(nat.ConvDesc) == 22 * 4 + 6 * 8
     assert ctypes.sizeof(nat.BufferDesc) == 6 * 4
-    assert ctypes.sizeof(nat.OpDesc) == 22 * 4
+    assert ctypes.sizeof(nat.OpDesc) == 24 * 4
     assert ctypes.sizeof(nat.NetDesc) == 4 * 4 + 2 * ctypes.sizeof(ctypes.c_void_p)
 
 
