@@ -294,25 +294,30 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, timed alone (rank 0) -----------------------------------------------------------
+    # ---- roofline of the dominant kernel: each layer of the plan launched alone, CUDA events (rank 0) ----------------------
     peaks, peak_kind = measured_peaks()
     it = max(10, min(50, K))
-    ms2, name2 = time_single_kernel(torch, nat, B, 32, 6, 5, 1, 0, it)
-    ms1, name1 = time_single_kernel(torch, nat, B, 6, 32, 3, 2, 1, it)
-    alg2 = conv_alg_bytes(B, 32, 6, 5)
-    achieved = alg2 / (ms2 * 1e-3) / 1e9
+    tc = eng.uses_tensor_cores()
+    layers = [('conv1 6->32 3x3 d2 tanh', 6, 32, 3), ('conv2 32->6 5x5 linear', 32, 6, 5)]
+    timed = []
+    for i, (name, cin, cout, k) in enumerate(layers):
+        ms_i = eng.profile_op(B, i, it)
+        alg = conv_alg_bytes(B, cin, cout, k)
+        timed.append({'kernel': ('conv_tc_kernel ' if tc else 'conv_ffma_kernel ') + name, 'ms_per_launch': ms_i,
+                      'algorithmic_bytes_per_launch': alg, 'achieved_gbs': alg / (ms_i * 1e-3) / 1e9,
+                      'useful_tflops': 2.0 * B * 91 * 180 * cin * cout * k * k / (ms_i * 1e-3) / 1e12})
+    dom = max(timed, key=lambda r: r['ms_per_launch'])
+    step_gbs = BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9
     roofline = {
-        'kernel': 'conv_ffma_kernel<5,5,1> 32->6 (%s)' % name2, 'bound': 'hbm', 'achieved': achieved,
-        'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
-        'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback 6650',
-        'algorithmic_bytes_per_launch': alg2, 'ms_per_launch': ms2,
-        'achieved_tflops_fp32': 2.0 * B * 91 * 180 * 6 * 32 * 25 / (ms2 * 1e-3) / 1e12,
-        'other_kernels': [{'kernel': 'conv_ffma_kernel<3,3,2> 6->32 tanh (%s)' % name1, 'ms_per_launch': ms1,
-                           'achieved_gbs': conv_alg_bytes(B, 6, 32, 3) / (ms1 * 1e-3) / 1e9}],
-        'step': {'algorithmic_bytes': BYTES_PER_SAMPLE_STEP * B, 'ms': ms / K,
-                 'achieved_gbs': BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9,
-                 'frac': BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                 'achieved_tflops_fp32': FLOP_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e12},
+        'kernel': dom['kernel'], 'bound': 'hbm', 'achieved': dom['achieved_gbs'], 'peak': peaks['hbm_gbs'],
+        'unit': 'GB/s', 'frac': dom['achieved_gbs'] / peaks['hbm_gbs'], 'traffic': None,
+        'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peak_kind == 'measured' else 'fallback 6650 GB/s',
+        'algorithmic_bytes_per_launch': dom['algorithmic_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
+        'math': 'tcgen05 f16 hi/lo split x3 -> fp32 TMEM accumulators' if tc else 'fp32 FFMA2',
+        'layers': timed,
+        'step': {'algorithmic_bytes': BYTES_PER_SAMPLE_STEP * B, 'ms': ms / K, 'achieved_gbs': step_gbs,
+                 'frac': step_gbs / peaks['hbm_gbs'],
+                 'useful_tflops': FLOP_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e12},
     }
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----------------------------------------------------------------
@@ -328,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
         'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'batch_per_gpu': B,
-                   'global_batch': B * world, 'state': list(STATE), 'parallelism': 'independent forecasts per GPU'
+                   'global_batch': B * world, 'state': list(STATE), 'math': args.math, 'parallelism': 'independent forecasts per GPU'
                    if world > 1 else 'single GPU',
                    'l2': 'per-step working set %.0f MB (state in + 32-ch activation + state out) > 126 MB L2; no flush'
                          % ((6 + 32 + 6) * 91 * 180 * 4 * B / 1e6),
@@ -431,9 +436,12 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=40, help='steps of the host-API measurement (<= --steps)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--math', default=os.environ.get('DLWP_MATH', 'tc'), choices=['tc', 'ffma'],
+                    help='tc: tcgen05 tensor cores, fp16 hi/lo split x3 (fp32-level accuracy); ffma: fp32 FFMA2 kernels')
     ap.add_argument('--parallel', default='latband', choices=['latband', 'batch'],
                     help='N>1: latitude bands + halo exchange (north star, strong scaling) or independent forecasts per GPU')
     args = ap.parse_args()
+    os.environ['DLWP_MATH'] = args.math
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

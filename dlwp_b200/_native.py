@@ -12,11 +12,11 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libdlwp_b200.so')
 DLWP_OK = 0
 PAD_ZERO, PAD_PERIODIC = 0, 1
 ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
-IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA = 0, 1, 2, 3
+IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
 BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2
 OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY = 0, 1, 2, 3, 4
 ACTIVATIONS = {None: ACT_LINEAR, 'linear': ACT_LINEAR, 'tanh': ACT_TANH, 'relu': ACT_RELU}
-IMPLS = {'auto': IMPL_AUTO, 'direct': IMPL_DIRECT, 'ffma': IMPL_FFMA, 'ffma_tma': IMPL_FFMA_TMA}
+IMPLS = {'auto': IMPL_AUTO, 'direct': IMPL_DIRECT, 'ffma': IMPL_FFMA, 'ffma_tma': IMPL_FFMA_TMA, 'tc': IMPL_TC}
 
 i32, i64 = ctypes.c_int32, ctypes.c_int64
 fptr = ctypes.c_void_p
@@ -61,6 +61,9 @@ SYMBOLS = {
                                          ctypes.c_void_p]),
     'dlwp_rollout': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32, ctypes.c_void_p]),
     'dlwp_rollout_host': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32]),
+    'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
+                                            ctypes.c_void_p]),
+    'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),
     'dlwp_last_error_string': (ctypes.c_char_p, []),
     'dlwp_abi_version': (ctypes.c_int, []),
     'dlwp_kernel_launch_count': (ctypes.c_int64, []),

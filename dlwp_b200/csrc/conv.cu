@@ -21,6 +21,7 @@ namespace dlwp {
 __device__ int g_device_flags = 0;  // bit 0: an mbarrier wait timed out (TMA never completed)
 }
 #include "internal.h"
+#include "conv_tc.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -634,7 +635,7 @@ static int validate(const DlwpConvDesc& d) {
     DLWP_REQUIRE(d.pad_mode_w == DLWP_PAD_ZERO || d.pad_mode_w == DLWP_PAD_PERIODIC, DLWP_EINVAL, "bad pad_mode_w");
     DLWP_REQUIRE(d.act >= DLWP_ACT_LINEAR && d.act <= DLWP_ACT_RELU, DLWP_EINVAL, "bad activation %d", d.act);
     DLWP_REQUIRE(d.pre_op >= 0 && d.pre_op <= 2, DLWP_EINVAL, "bad pre_op %d", d.pre_op);
-    DLWP_REQUIRE(d.impl >= DLWP_IMPL_AUTO && d.impl <= DLWP_IMPL_FFMA_TMA, DLWP_EINVAL, "bad impl %d", d.impl);
+    DLWP_REQUIRE(d.impl >= DLWP_IMPL_AUTO && d.impl <= DLWP_IMPL_TC, DLWP_EINVAL, "bad impl %d", d.impl);
     return 0;
 }
 
@@ -673,6 +674,10 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
     DLWP_REQUIRE(all_rows || (d.row_begin >= 0 && d.row_end <= Ho && d.row_begin < d.row_end), DLWP_ESHAPE,
                  "row window [%d,%d) outside the %d output rows", d.row_begin, d.row_end, Ho);
 
+    if (d.impl == DLWP_IMPL_TC) {
+        DLWP_REQUIRE(all_rows, DLWP_ESHAPE, "the tensor-core path does not take row windows yet");
+        return conv2d_fwd_tc(d, x, w, bias, y, stream);
+    }
     TileChoice tc;
     if (d.impl != DLWP_IMPL_DIRECT) tc = choose_tiling(d, d.impl);
     if (d.impl == DLWP_IMPL_FFMA || d.impl == DLWP_IMPL_FFMA_TMA)
@@ -722,5 +727,6 @@ extern "C" int dlwp_debug_flags(void) {
     int v = 0, zero = 0;
     if (cudaMemcpyFromSymbol(&v, dlwp::g_device_flags, sizeof(int)) != cudaSuccess) return -1;
     cudaMemcpyToSymbol(dlwp::g_device_flags, &zero, sizeof(int));
-    return v;
+    const int t = dlwp::tc_debug_flags();
+    return v | (t > 0 ? (t << 1) : 0);
 }

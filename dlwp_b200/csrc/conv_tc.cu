@@ -1,0 +1,575 @@
+// Tensor-core (tcgen05 / TMEM / TMA) implementation of the fused periodic-pad + Conv2D layer.
+//
+// Why a different formulation than a textbook implicit GEMM.  With pixels as the M dimension a 'valid' conv is
+//   D[m, co] = sum_{i,j,c} A[m + shift(i,j), c] * W[i,j,c,co]
+// and the example nets have tiny N (6..32 filters): every K=16 step would re-read a 4 KB A tile from shared memory for
+// 8..16 clocks of tensor work -- shared-memory bound at ~10 % tensor utilisation.  Instead
+//   * vertical taps i are folded into K:   K = (i, c)   (a tap is just a +i*dil*Wp*16-byte offset of the A view), and
+//   * horizontal taps j are folded into N: N = (j, co)  (5x fewer A reads for a 5x5 kernel),
+//   D[m, (j,co)] = sum_{i,c} A[m + i*dil*Wp, c] * W[i,j,c,co],        out[p, co] = sum_j D[p + j*dil, (j,co)],
+// and the horizontal shifted sum runs in the epilogue on the TMEM rows (warp shuffles; 4 boundary lanes via smem).
+//
+// Precision: operands are fp16 hi/lo splits of fp32 values (x = hi + lo, 22 significant bits); three MMAs per K step
+// (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -> ~1e-6 relative error, inside the 1e-4 / 50-step gate.  Activations
+// live in HBM already split and channel-blocked ("P layout"): [n][plane = 2*c8 + {hi,lo}][H][Wp][8] fp16 with the periodic
+// longitude halo (wpad columns each side) materialised by the PRODUCER's epilogue, so a consumer tile is ONE TMA box and
+// the zero rows beyond the poles are TMA out-of-bounds fill.  A-operand views are K-major, no-swizzle UMMA descriptors into
+// that image (8 pixels x 16 B core matrices; validated by scripts/umma_probe.cu on B200).
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):  warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
+// warps 2-5 epilogue (TMEM quadrant = warp & 3).  Pipelines: smem stages full/empty (TMA <-> MMA), TMEM accumulator sets
+// full/empty (MMA <-> epilogue, double buffered).
+#define DLWP_CONV_TU  // mbarrier helpers
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+namespace dlwp {
+__device__ int g_tc_flags = 0;  // bit 0: mbarrier wait timed out
+}
+#define g_device_flags g_tc_flags
+#include "internal.h"
+#undef g_device_flags
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "conv_tc.h"
+
+namespace dlwp {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_KSTEPS = 32;
+
+struct TcParams {
+    int N, H, W, Wp;          // source image; Wp = W + 2*wpad_in
+    int R_out, Rin, MT, S;    // rows per tile, staged rows, M-tiles per tile, M-tile stride (128 - (KW-1)*D)
+    int KW, D, pad_t;
+    int Cout, NCOLS, CBLK, CSTRIDE;  // filters, MMA N, 8-filter blocks, TMEM columns per horizontal tap of a block
+    int G, KS, NS;            // channel groups per tile, K steps per group, smem stages
+    int planes_per_group;
+    int tiles_per_sample, total_tiles;
+    uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;  // b_bytes: one (hi or lo) weight image
+    int XL;                   // lanes a pixel reaches to its right: (KW-1)*D
+    uint32_t idesc;
+    int act;
+    const float* bias;
+    const __half* bimg;       // [hi image | lo image], each [G*KS*2 units][NCOLS][8]
+    float* y32; long long ys_n, ys_c, ys_h;
+    __half* yp; int Wp_out, wpad_out, planes_out;
+    TcKStep kst[TC_MAX_KSTEPS];  // [G][KS]
+};
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // sm_100 descriptor version; layout_type 0 = no swizzle
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct alignas(16) Half8 {
+    __half2 a, b, c, d;
+};
+
+// ===================================================================================================================
+template <int KW>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;
+    unsigned char* b_hi = stages + (size_t)p.NS * p.stage_stride;
+    unsigned char* b_lo = b_hi + p.b_bytes;
+    float* xch = reinterpret_cast<float*>(b_lo + p.b_bytes);                 // [2][4 quadrants][XL lanes][KW*8]
+    const int XQ = p.XL * KW * 8;                                            // floats one quadrant publishes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * XQ);
+    uint64_t* full = bars;             // [NS]
+    uint64_t* empty = bars + 8;        // [NS]
+    uint64_t* acc_full = bars + 16;    // [2]
+    uint64_t* acc_empty = bars + 18;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ACC_COLS = p.MT * p.NCOLS;  // columns of one accumulator set (<= 256)
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------------
+    for (uint32_t i = tid; i < 2 * p.b_bytes / 16; i += TC_THREADS)  // weight images -> smem (hi then lo, contiguous)
+        reinterpret_cast<uint4*>(b_hi)[i] = reinterpret_cast<const uint4*>(p.bimg)[i];
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    if (tid == 0) {
+        prefetch_tensormap(&tmap);
+        for (int s = 0; s < p.NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int idx = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n = tile / p.tiles_per_sample;
+                const int y0 = (tile % p.tiles_per_sample) * p.R_out;
+                for (int g = 0; g < p.G; ++g, ++idx) {
+                    const int s = idx % p.NS;
+                    mbar_wait(&empty[s], ((idx / p.NS) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], p.stage_bytes);
+                    tma_load_5d(stages + (size_t)s * p.stage_stride, &tmap, &full[s], 0, 0, y0 - p.pad_t,
+                                g * p.planes_per_group, n);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            int idx = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc_base = tmem + ab * ACC_COLS;
+                for (int g = 0; g < p.G; ++g, ++idx) {
+                    const int s = idx % p.NS;
+                    mbar_wait(&full[s], (idx / p.NS) & 1);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(stages + (size_t)s * p.stage_stride);
+                    for (int t = 0; t < p.MT; ++t) {
+                        const uint32_t row_off = (uint32_t)(t * p.S) * 16u;
+                        for (int ks = 0; ks < p.KS; ++ks) {
+                            const TcKStep k = p.kst[g * p.KS + ks];
+                            const uint32_t a_hi = sbase + k.a_off + row_off;
+                            const uint32_t boff = (uint32_t)((g * p.KS + ks) * 2 * p.NCOLS) * 16u;
+                            const uint64_t bd_hi = umma_desc(smem_u32(b_hi) + boff, p.NCOLS * 16u, 128u);
+                            const uint64_t bd_lo = umma_desc(smem_u32(b_lo) + boff, p.NCOLS * 16u, 128u);
+                            const uint64_t ad_hi = umma_desc(a_hi, k.a_lbo, 128u);
+                            const uint64_t ad_lo = umma_desc(a_hi + p.plane_bytes, k.a_lbo, 128u);
+                            const uint32_t d = acc_base + t * p.NCOLS;
+                            umma_f16(d, ad_hi, bd_hi, p.idesc, (g | ks) != 0);
+                            umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+                            umma_f16(d, ad_lo, bd_hi, p.idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);  // stage s may be refilled once these MMAs have read it
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else {
+        // =============================== epilogue (4 warps) ===============================
+        const int q = warp & 3;
+        const int XL = p.XL;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int n = tile / p.tiles_per_sample;
+            const int y0 = (tile % p.tiles_per_sample) * p.R_out;
+            mbar_wait(&acc_full[ab], (it >> 1) & 1);
+            tc_fence_after();
+            for (int t = 0; t < p.MT; ++t) {
+                const int ml = q * 32 + lane;           // row of the M tile
+                const int pos = t * p.S + ml;           // flattened (row, padded column) position in the tile
+                const int r = pos / p.Wp, xq = pos - r * p.Wp;
+                const int y = y0 + r;
+                const bool valid = (ml < p.S) && (r < p.R_out) && (y < p.H) && (xq < p.W);
+                for (int cb = 0; cb < p.CBLK; ++cb) {
+                    float d[KW][8];
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j]);
+                    tmem_ld_wait();
+                    // lanes 0..XL-1 of every quadrant publish their taps for the quadrant before them
+                    float* xb = xch + ((size_t)((t * p.CBLK + cb) & 1) * 4 + q) * XQ;
+                    if (lane < XL) {
+#pragma unroll
+                        for (int j = 1; j < KW; ++j)
+#pragma unroll
+                            for (int ci = 0; ci < 8; ++ci) xb[(lane * KW + j) * 8 + ci] = d[j][ci];
+                    }
+                    named_bar_sync(1, 128);
+                    const float* xn = xch + ((size_t)((t * p.CBLK + cb) & 1) * 4 + ((q + 1) & 3)) * XQ;
+                    float o[8];
+#pragma unroll
+                    for (int ci = 0; ci < 8; ++ci) o[ci] = d[0][ci];
+#pragma unroll
+                    for (int j = 1; j < KW; ++j) {
+                        const int sh = j * p.D;
+                        const int src = lane + sh;
+#pragma unroll
+                        for (int ci = 0; ci < 8; ++ci) {
+                            const float v = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
+                            o[ci] += (src < 32) ? v : xn[(min(src - 32, XL - 1) * KW + j) * 8 + ci];
+                        }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int ci = 0; ci < 8; ++ci) {
+                            const int co = cb * 8 + ci;
+                            const float b = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+                            o[ci] = co < p.Cout ? apply_act(o[ci] + b, p.act) : 0.f;  // padded channels stay exactly 0
+                        }
+                        if (p.y32 != nullptr) {
+#pragma unroll
+                            for (int ci = 0; ci < 8; ++ci) {
+                                const int co = cb * 8 + ci;
+                                if (co < p.Cout)
+                                    p.y32[(long long)n * p.ys_n + (long long)co * p.ys_c + (long long)y * p.ys_h + xq] = o[ci];
+                            }
+                        }
+                        if (p.yp != nullptr) {
+                            __half h[8], l[8];
+#pragma unroll
+                            for (int ci = 0; ci < 8; ++ci) {
+                                h[ci] = __float2half_rn(o[ci]);
+                                l[ci] = __float2half_rn(o[ci] - __half2float(h[ci]));
+                            }
+                            Half8 vh, vl;
+                            vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
+                            vh.c = __halves2half2(h[4], h[5]); vh.d = __halves2half2(h[6], h[7]);
+                            vl.a = __halves2half2(l[0], l[1]); vl.b = __halves2half2(l[2], l[3]);
+                            vl.c = __halves2half2(l[4], l[5]); vl.d = __halves2half2(l[6], l[7]);
+                            const long long row_hi = (((long long)n * p.planes_out + cb * 2) * p.H + y) * p.Wp_out;
+                            const long long row_lo = (((long long)n * p.planes_out + cb * 2 + 1) * p.H + y) * p.Wp_out;
+                            Half8* yp = reinterpret_cast<Half8*>(p.yp);
+                            const int xo = xq + p.wpad_out;
+                            yp[row_hi + xo] = vh;
+                            yp[row_lo + xo] = vl;
+                            if (xq < p.wpad_out) {            // periodic longitude halo of the NEXT layer, right side
+                                yp[row_hi + xo + p.W] = vh;
+                                yp[row_lo + xo + p.W] = vl;
+                            }
+                            if (xq >= p.W - p.wpad_out) {     // ... and left side
+                                yp[row_hi + xo - p.W] = vh;
+                                yp[row_lo + xo - p.W] = vl;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// fp32 (N,C,H,W) -> P layout with the periodic halo; one thread per (n, c8, y, padded x)
+__global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict__ x, __half* __restrict__ yp, int N, int C,
+                                                         int H, int W, int wpad, long long xs_n, long long xs_c,
+                                                         long long xs_h) {
+    const int Wp = W + 2 * wpad, C8 = (C + 7) / 8;
+    const long long total = (long long)N * C8 * H * Wp;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int xq = (int)(idx % Wp);
+        long long t = idx / Wp;
+        const int y = (int)(t % H);
+        t /= H;
+        const int c8 = (int)(t % C8);
+        const int n = (int)(t / C8);
+        const int gx = wrap_index(xq - wpad, W);
+        __half h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            const float v = c < C ? x[(long long)n * xs_n + (long long)c * xs_c + (long long)y * xs_h + gx] : 0.f;
+            h[e] = __float2half_rn(v);
+            l[e] = __float2half_rn(v - __half2float(h[e]));
+        }
+        Half8 vh, vl;
+        vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
+        vh.c = __halves2half2(h[4], h[5]); vh.d = __halves2half2(h[6], h[7]);
+        vl.a = __halves2half2(l[0], l[1]); vl.b = __halves2half2(l[2], l[3]);
+        vl.c = __halves2half2(l[4], l[5]); vl.d = __halves2half2(l[6], l[7]);
+        Half8* out = reinterpret_cast<Half8*>(yp);
+        out[(((long long)n * 2 * C8 + 2 * c8) * H + y) * Wp + xq] = vh;
+        out[(((long long)n * 2 * C8 + 2 * c8 + 1) * H + y) * Wp + xq] = vl;
+    }
+}
+
+// ===================================================================================================================
+// Host side
+// ===================================================================================================================
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_p_map(CUtensorMap* map, const __half* base, int N, int planes, int H, int Wp, int Rin, int ppg) {
+    static encode_tiled_t fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_t>(ptr);
+    });
+    DLWP_REQUIRE(fn != nullptr, DLWP_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[5] = {8, (cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)N};
+    cuuint64_t str[4] = {16, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16, (cuuint64_t)planes * H * Wp * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)Wp, (cuuint32_t)Rin, (cuuint32_t)ppg, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DLWP_REQUIRE(r == CUDA_SUCCESS, DLWP_ESHAPE, "cuTensorMapEncodeTiled (P layout) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+bool tc_geometry_ok(const DlwpConvDesc& d) {
+    if (d.rowwise || d.pre_op || d.dil_h != d.dil_w) return false;
+    if (d.pad_mode_h != DLWP_PAD_ZERO || d.pad_mode_w != DLWP_PAD_PERIODIC) return false;
+    if (d.kw != 3 && d.kw != 5) return false;
+    const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
+    if (d.pad_l != halo_w / 2 || d.pad_r != halo_w / 2 || (halo_w & 1)) return false;  // 'same' width
+    if (d.pad_t + d.pad_b != halo_h) return false;                                      // 'same' height
+    if (d.W + halo_w > 256 || d.W < halo_w) return false;                               // one TMA box per row
+    if ((d.kw - 1) * d.dil_w > 8) return false;
+    TcLayer L;
+    return tc_plan_layer(d, &L) == 0;
+}
+
+int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
+    memset(L, 0, sizeof(*L));
+    const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
+    L->wpad = halo_w / 2;
+    L->Wp = d.W + halo_w;
+    L->C8 = cdiv(d.Cin, 8);
+    L->planes = 2 * L->C8;
+    L->CBLK = cdiv(d.Cout, 8);
+    L->CSTRIDE = d.Cout < 8 ? d.Cout : 8;  // a single partial block packs its taps tightly (5 taps x 6 filters -> 32 cols)
+    L->NCOLS = cdiv(L->CBLK * d.kw * L->CSTRIDE + (8 - L->CSTRIDE), 16) * 16;  // x8 loads of the last tap stay inside
+    if (L->NCOLS > 256) return -1;
+    L->S = 128 - halo_w;
+    // units = (chunk, tap) in order; groups of chunks so that a group has an even number of units when possible
+    const int smem_budget = 224 * 1024;
+    const size_t fixed = (size_t)2 * 4 * halo_w * d.kw * 8 * 4 + 512;  // lane exchange + barriers
+    int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0;
+    for (int r_out = 8; r_out >= 1; --r_out) {
+        const int rin = r_out + halo_h;
+        const int mt = cdiv(r_out * L->Wp, L->S);
+        if (mt * L->NCOLS > 256) continue;  // two accumulator sets in 512 TMEM columns
+        for (int cpg = std::min(L->C8, 4); cpg >= 1; --cpg) {
+            const int G = cdiv(L->C8, cpg);
+            const int units = cpg * d.kh;
+            const int KS = cdiv(units, 2);
+            if (G * KS > TC_MAX_KSTEPS) continue;
+            const size_t stage = (size_t)2 * cpg * rin * L->Wp * 16;
+            const size_t bimg = (size_t)G * KS * 2 * L->NCOLS * 16;
+            const size_t stride = (stage + 127) / 128 * 128;
+            const int ns = G >= 2 ? 2 : (stride * 3 + 2 * bimg + fixed <= (size_t)smem_budget ? 3 : 2);
+            if (stride * ns + 2 * bimg + fixed > (size_t)smem_budget) continue;
+            if (stage > (1u << 20)) continue;
+            best_r = r_out; best_cpg = cpg; best_ns = ns; best_mt = mt;
+            break;
+        }
+        if (best_r) break;
+    }
+    if (!best_r) return -1;
+    L->R_out = best_r;
+    L->Rin = best_r + halo_h;
+    L->MT = best_mt;
+    L->cpg = best_cpg;
+    L->G = cdiv(L->C8, best_cpg);
+    L->KS = cdiv(best_cpg * d.kh, 2);
+    L->NS = best_ns;
+    L->stage_bytes = (uint32_t)(2 * best_cpg * L->Rin * L->Wp * 16);
+    L->stage_stride = (L->stage_bytes + 127) / 128 * 128;
+    L->plane_bytes = (uint32_t)(L->Rin * L->Wp * 16);
+    L->b_bytes = (uint32_t)(L->G * L->KS * 2 * L->NCOLS * 16);
+    L->smem = (size_t)L->NS * L->stage_stride + 2 * (size_t)L->b_bytes + fixed + 1024;
+    return 0;
+}
+
+// Weight image: for every group g and K step ks two units of [NCOLS][8] fp16; a unit = (chunk, vertical tap i) holding
+// w[i][j][c8*8+e][co] at column n = (cb*KW + j)*8 + ci, co = cb*8 + ci.  Odd unit counts pair the last unit with a zero unit
+// that re-reads the previous tap's A rows.
+int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
+                    TcKStep* kst_out) {
+    const size_t per_img = (size_t)L.b_bytes / 2;
+    img->assign(2 * per_img, __float2half(0.f));
+    for (int g = 0; g < L.G; ++g) {
+        struct U { int chunk_in_group, chunk, i; bool zero; };
+        std::vector<U> units;
+        for (int cg = 0; cg < L.cpg; ++cg)
+            for (int i = 0; i < d.kh; ++i) units.push_back({cg, g * L.cpg + cg, i, false});
+        if (units.size() & 1) {  // [.., u(n-2), u(n-1)] -> [.., u(n-2), ZERO(view of u(n-2)), u(n-1)]  (needs >= 2 units)
+            U last = units.back();
+            units.pop_back();
+            U z = units.empty() ? last : units.back();
+            z.zero = true;
+            if (units.empty()) { units.push_back(last); units.push_back(z); }  // single unit: (u, ZERO view of u) lbo = 0 ...
+            else { units.push_back(z); units.push_back(last); }
+        }
+        for (int ks = 0; ks < L.KS; ++ks) {
+            const U& u0 = units[2 * ks];
+            const U& u1 = units[2 * ks + 1];
+            auto aoff = [&](const U& u) {
+                return (long long)(2 * u.chunk_in_group) * L.plane_bytes + (long long)u.i * d.dil_h * L.Wp * 16;
+            };
+            const long long lbo = aoff(u1) - aoff(u0);
+            if (lbo < 0 || (lbo >> 4) > 0x3FFF) return -1;
+            kst_out[g * L.KS + ks].a_off = (uint32_t)aoff(u0);
+            kst_out[g * L.KS + ks].a_lbo = (uint32_t)lbo;
+            for (int half = 0; half < 2; ++half) {
+                const U& u = half ? u1 : u0;
+                if (u.zero) continue;
+                const size_t ubase = ((size_t)(g * L.KS + ks) * 2 + half) * L.NCOLS * 8;
+                for (int cb = 0; cb < L.CBLK; ++cb)
+                    for (int j = 0; j < d.kw; ++j)
+                        for (int ci = 0; ci < 8; ++ci) {
+                            const int co = cb * 8 + ci, ncol = (cb * d.kw + j) * L.CSTRIDE + ci;
+                            if (ci >= L.CSTRIDE) continue;
+                            if (co >= d.Cout) continue;
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = u.chunk * 8 + e;
+                                if (c >= d.Cin) continue;
+                                const float v = w_host[(((size_t)u.i * d.kw + j) * d.Cin + c) * d.Cout + co];
+                                const __half h = __float2half_rn(v);
+                                (*img)[ubase + (size_t)ncol * 8 + e] = h;
+                                (*img)[per_img + ubase + (size_t)ncol * 8 + e] = __float2half_rn(v - __half2float(h));
+                            }
+                        }
+            }
+        }
+    }
+    return 0;
+}
+
+static int g_tc_sms = 0;
+
+int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
+              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaGetDeviceProperties(&prop, dev);
+        g_tc_sms = prop.multiProcessorCount;
+        cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+        cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+    });
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;
+    p.R_out = L.R_out; p.Rin = L.Rin; p.MT = L.MT; p.S = L.S;
+    p.KW = d.kw; p.D = d.dil_w; p.pad_t = d.pad_t;
+    p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (d.kw - 1) * d.dil_w;
+    p.G = L.G; p.KS = L.KS; p.NS = L.NS; p.planes_per_group = 2 * L.cpg;
+    p.tiles_per_sample = cdiv(d.H, L.R_out);
+    p.total_tiles = p.tiles_per_sample * d.N;
+    p.stage_bytes = L.stage_bytes; p.stage_stride = L.stage_stride; p.plane_bytes = L.plane_bytes; p.b_bytes = L.b_bytes;
+    p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
+    p.act = d.act; p.bias = bias; p.bimg = bimg;
+    p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
+    p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
+    for (int i = 0; i < L.G * L.KS; ++i) p.kst[i] = kst[i];
+    CUtensorMap map;
+    int rc = encode_p_map(&map, xp, d.N, L.planes, d.H, L.Wp, L.Rin, 2 * L.cpg);
+    if (rc) return rc;
+    const int grid = std::min(p.total_tiles, g_tc_sms);
+    if (d.kw == 3) conv_tc_kernel<3><<<grid, TC_THREADS, L.smem, stream>>>(p, map);
+    else conv_tc_kernel<5><<<grid, TC_THREADS, L.smem, stream>>>(p, map);
+    return after_launch("conv_tc_kernel");
+}
+
+int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
+                  long long xs_h, cudaStream_t stream) {
+    const long long total = (long long)N * cdiv(C, 8) * H * (W + 2 * wpad);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    pack_state_kernel<<<blocks, 256, 0, stream>>>(x, xp, N, C, H, W, wpad, xs_n, xs_c, xs_h);
+    return after_launch("pack_state_kernel");
+}
+
+int tc_debug_flags() {
+    int v = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&v, g_tc_flags, sizeof(int)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_tc_flags, &zero, sizeof(int));
+    return v;
+}
+
+// Stand-alone layer through the tensor-core path (tests / A-B timing): packs x and the weights into temporaries.
+int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
+                  cudaStream_t stream) {
+    DLWP_REQUIRE(tc_geometry_ok(d), DLWP_ESHAPE, "geometry not supported by the tensor-core conv kernel");
+    TcLayer L;
+    tc_plan_layer(d, &L);
+    const size_t wn = (size_t)d.kh * d.kw * d.Cin * d.Cout;
+    std::vector<float> w_host(wn);
+    DLWP_CUDA_TRY(cudaMemcpyAsync(w_host.data(), w_dev, wn * 4, cudaMemcpyDeviceToHost, stream));
+    DLWP_CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<__half> img;
+    TcKStep kst[TC_MAX_KSTEPS];
+    DLWP_REQUIRE(tc_pack_weights(d, L, w_host.data(), &img, kst) == 0, DLWP_ESHAPE, "weight packing failed");
+    __half *bimg = nullptr, *xp = nullptr;
+    const size_t xp_bytes = (size_t)d.N * L.planes * d.H * L.Wp * 16;
+    DLWP_CUDA_TRY(cudaMalloc(&bimg, img.size() * 2));
+    DLWP_CUDA_TRY(cudaMalloc(&xp, xp_bytes));
+    DLWP_CUDA_TRY(cudaMemcpyAsync(bimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
+    int rc = tc_pack_state(x, xp, d.N, d.Cin, d.H, d.W, L.wpad, d.x_stride_n, d.x_stride_c, d.x_stride_h, stream);
+    if (!rc) rc = tc_launch(d, L, kst, xp, bimg, bias, y, nullptr, 0, 0, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(bimg);
+    cudaFree(xp);
+    return rc;
+}
+
+}  // namespace dlwp

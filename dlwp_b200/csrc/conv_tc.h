@@ -1,0 +1,42 @@
+// Host-side interface of the tensor-core conv path (conv_tc.cu); internal, not part of the C ABI.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/dlwp_b200.h"
+
+namespace dlwp {
+
+struct TcKStep {
+    uint32_t a_off;  // byte offset (inside a stage) of the first 8-channel unit's hi plane, tap row included
+    uint32_t a_lbo;  // byte distance to the second unit of this K=16 step
+};
+
+// Static schedule of one layer: how the P-layout input is tiled, staged and fed to the tensor core.
+struct TcLayer {
+    int wpad, Wp;          // periodic halo columns per side of the INPUT image, padded width
+    int C8, planes;        // 8-channel chunks of the input, planes = 2 * C8 (hi, lo)
+    int CBLK, CSTRIDE, NCOLS;  // 8-filter blocks, TMEM columns per horizontal tap, MMA N
+    int S;                 // M-tile stride in pixels (128 - (kw-1)*dil)
+    int R_out, Rin, MT;    // rows per tile, staged rows, M tiles per tile
+    int cpg, G, KS, NS;    // chunks per group, groups per tile, K=16 steps per group, smem stages
+    uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;
+    size_t smem;
+};
+
+bool tc_geometry_ok(const DlwpConvDesc& d);
+int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L);
+int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
+                    TcKStep* kst_out);
+int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
+              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream);
+int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
+                  long long xs_h, cudaStream_t stream);
+int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
+                  cudaStream_t stream);
+int tc_debug_flags();
+
+}  // namespace dlwp

@@ -7,8 +7,10 @@
 // t*n_out-1 of the output series directly and writes slots t*n_out .. t*n_out+n_out-1 -- and the whole loop can be
 // replayed as one CUDA graph.
 #include "internal.h"
+#include "conv_tc.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cstring>
@@ -34,6 +36,9 @@ struct Buffer {
     DlwpBufferDesc d;
     float* ptr = nullptr;  // INTERNAL: owned; INPUT/OUTPUT: bound per call
     long long sample_elems() const { return (long long)d.C * d.H * d.W; }
+    // tensor-core chain: the same activation in P layout (fp16 hi/lo planes, periodic halo materialised)
+    __half* P = nullptr;
+    int wpad = -1, planes = 0;
 };
 
 struct Weight {
@@ -41,6 +46,8 @@ struct Weight {
     float* b = nullptr;
     long long k_elems = 0, b_elems = 0;
     bool has_bias = false, set = false;
+    __half* bimg = nullptr;        // tensor-core chain: packed hi/lo weight images
+    TcKStep kst[32];
 };
 
 struct GraphKey {
@@ -70,6 +77,11 @@ struct DlwpPlan {
     long long d_x0_cap = 0, d_series_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     std::vector<cudaEvent_t> events;
+    // tensor-core chain mode (every op a tc-capable conv): per-op schedule + which packed buffer each conv writes
+    bool tc = false;
+    std::vector<TcLayer> tc_layers;
+    std::vector<int> tc_pdst;      // buffer whose P image op i writes (-1: none)
+    int tc_feedback_op = -1;       // op that also serves as the packer of the next iteration's input
 };
 
 namespace dlwp {
@@ -94,8 +106,121 @@ static void out_dims(const DlwpPlan* pl, const DlwpOpDesc& op, int& C, int& H, i
     }
 }
 
-static int run_ops(DlwpPlan* pl, int N, cudaStream_t stream) {
+static DlwpConvDesc conv_desc_of(const DlwpPlan* pl, const DlwpOpDesc& op, int N) {
+    const Buffer& s = pl->buffers[op.src];
+    const Buffer& t = pl->buffers[op.dst];
+    DlwpConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.Cin = op.src_c; d.H = s.d.H; d.W = s.d.W;
+    d.Cout = op.Cout; d.kh = op.kh; d.kw = op.kw; d.dil_h = op.dil_h; d.dil_w = op.dil_w;
+    d.pad_t = op.pad_t; d.pad_b = op.pad_b; d.pad_l = op.pad_l; d.pad_r = op.pad_r;
+    d.pad_mode_h = op.pad_mode_h; d.pad_mode_w = op.pad_mode_w;
+    d.act = op.act; d.pre_op = op.pre_op; d.rowwise = op.rowwise; d.impl = op.impl;
+    d.row_begin = op.row_begin; d.row_end = op.row_end;
+    d.x_stride_n = s.sample_elems(); d.x_stride_c = (long long)s.d.H * s.d.W; d.x_stride_h = s.d.W;
+    d.y_stride_n = t.sample_elems(); d.y_stride_c = (long long)t.d.H * t.d.W; d.y_stride_h = t.d.W;
+    return d;
+}
+
+// Decide whether the whole plan can run as a tensor-core chain and size its packed buffers.
+static int tc_setup(DlwpPlan* pl) {
+    const char* env = getenv("DLWP_MATH");
+    bool want = env && !strcmp(env, "tc");
+    bool all_flagged = !pl->ops.empty();
+    for (const DlwpOpDesc& op : pl->ops) all_flagged = all_flagged && op.kind == DLWP_OP_CONV && op.impl == DLWP_IMPL_TC;
+    if (!want && !all_flagged) return 0;
+    const int nops = (int)pl->ops.size();
+    std::vector<TcLayer> layers(nops);
+    std::vector<int> writer(pl->buffers.size(), -1);
+    for (int i = 0; i < nops; ++i) {
+        const DlwpOpDesc& op = pl->ops[i];
+        const Buffer& s = pl->buffers[op.src];
+        const Buffer& t = pl->buffers[op.dst];
+        if (op.kind != DLWP_OP_CONV || op.row_begin || op.row_end) return 0;
+        if (op.src_c0 != 0 || op.src_c != s.d.C || op.dst_c0 != 0 || op.Cout != t.d.C) return 0;
+        DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
+        if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
+        if (op.src != pl->input_buf && writer[op.src] < 0) return 0;  // source must be the input or a conv result
+        if (writer[op.dst] >= 0) return 0;
+        writer[op.dst] = i;
+        Buffer& sb = pl->buffers[op.src];
+        if (sb.wpad >= 0 && sb.wpad != layers[i].wpad) return 0;     // all readers must want the same halo
+        sb.wpad = layers[i].wpad;
+        sb.planes = layers[i].planes;
+    }
+    pl->tc_pdst.assign(nops, -1);
+    for (int i = 0; i < nops; ++i)
+        if (pl->buffers[pl->ops[i].dst].wpad >= 0) pl->tc_pdst[i] = pl->ops[i].dst;
+    // feedback: the producer of the LAST output re-packs the next iteration's input when shapes allow
+    const int last_out = pl->outputs.back();
+    const Buffer& in = pl->buffers[pl->input_buf];
+    const Buffer& lo = pl->buffers[last_out];
+    if (writer[last_out] >= 0 && pl->tc_pdst[writer[last_out]] < 0 && lo.d.C == in.d.C && lo.d.H == in.d.H &&
+        lo.d.W == in.d.W) {
+        pl->tc_feedback_op = writer[last_out];
+        pl->tc_pdst[writer[last_out]] = pl->input_buf;
+    }
+    for (Buffer& b : pl->buffers)
+        if (b.wpad >= 0) {
+            const size_t bytes = (size_t)pl->max_batch * b.planes * b.d.H * (b.d.W + 2 * b.wpad) * 16;
+            if (cudaMalloc(&b.P, bytes) != cudaSuccess) return DLWP_ENOMEM;
+            cudaMemset(b.P, 0, bytes);
+        }
+    pl->tc_layers = layers;
+    pl->tc = true;
+    return 0;
+}
+
+static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel_host) {
     for (size_t i = 0; i < pl->ops.size(); ++i) {
+        const DlwpOpDesc& op = pl->ops[i];
+        if (op.weight_id != weight_id) continue;
+        Weight& w = pl->weights[weight_id];
+        DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
+        std::vector<__half> img;
+        DLWP_REQUIRE(tc_pack_weights(d, pl->tc_layers[i], kernel_host, &img, w.kst) == 0,
+                     DLWP_ESHAPE, "tensor-core weight packing failed for weight %d", weight_id);
+        if (!w.bimg) DLWP_CUDA_TRY(cudaMalloc(&w.bimg, img.size() * sizeof(__half)));
+        DLWP_CUDA_TRY(cudaMemcpy(w.bimg, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        return 0;  // ops sharing a weight id share geometry and therefore the image
+    }
+    return 0;
+}
+
+static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
+    const DlwpOpDesc& op = pl->ops[i];
+    const Weight& w = pl->weights[op.weight_id];
+    DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);
+    const Buffer& s = pl->buffers[op.src];
+    const Buffer& t = pl->buffers[op.dst];
+    DlwpConvDesc d = conv_desc_of(pl, op, N);
+    float* y32 = (t.d.kind == DLWP_BUF_OUTPUT) ? t.ptr : nullptr;
+    __half* yp = nullptr;
+    int wpad_out = 0, planes_out = 0;
+    if (pl->tc_pdst[i] >= 0) {
+        const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
+        yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
+    }
+    return tc_launch(d, pl->tc_layers[i], w.kst, s.P, w.bimg, w.has_bias ? w.b : nullptr, y32, yp, wpad_out,
+                     planes_out, stream);
+}
+
+static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_packed) {
+    Buffer& in = pl->buffers[pl->input_buf];
+    if (!input_is_packed) {
+        int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
+                               (long long)in.d.H * in.d.W, in.d.W, stream);
+        if (rc) return rc;
+    }
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+        int rc = run_one_tc(pl, (int)i, N, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int run_one(DlwpPlan* pl, size_t i, int N, cudaStream_t stream) {
+    {
         const DlwpOpDesc& op = pl->ops[i];
         const Buffer& s = pl->buffers[op.src];
         const Buffer& t = pl->buffers[op.dst];
@@ -132,6 +257,13 @@ static int run_ops(DlwpPlan* pl, int N, cudaStream_t stream) {
                 break;
             default: DLWP_REQUIRE(false, DLWP_EINVAL, "op %zu: unknown kind %d", i, op.kind);
         }
+        return rc;
+    }
+}
+
+static int run_ops(DlwpPlan* pl, int N, cudaStream_t stream) {
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+        int rc = run_one(pl, i, N, stream);
         if (rc) return rc;
     }
     return 0;
@@ -156,7 +288,7 @@ static int rollout_range(DlwpPlan* pl, int N, const float* x0, float* series, in
         pl->buffers[pl->input_buf].ptr =
             const_cast<float*>(t == 0 ? x0 : series + ((long long)t * n_out - 1) * slot);
         for (int k = 0; k < n_out; ++k) pl->buffers[pl->outputs[k]].ptr = series + ((long long)t * n_out + k) * slot;
-        int rc = run_ops(pl, N, stream);
+        int rc = pl->tc ? run_ops_tc(pl, N, stream, t > 0 && pl->tc_feedback_op >= 0) : run_ops(pl, N, stream);
         if (rc) return rc;
     }
     return 0;
@@ -268,6 +400,11 @@ extern "C" int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** out) {
             DLWP_REQUIRE(false, DLWP_ENOMEM, "cudaMalloc of a weight tensor failed");
         }
     }
+    rc = tc_setup(pl);
+    if (rc) {
+        dlwp_plan_destroy(pl);
+        DLWP_REQUIRE(false, rc, "tensor-core chain setup failed");
+    }
     *out = pl;
     return 0;
 }
@@ -277,7 +414,10 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
     for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
+    for (Buffer& b : pl->buffers)
+        if (b.P) cudaFree(b.P);
     for (Weight& w : pl->weights) {
+        if (w.bimg) cudaFree(w.bimg);
         if (w.k) cudaFree(w.k);
         if (w.b) cudaFree(w.b);
     }
@@ -304,6 +444,7 @@ extern "C" int dlwp_plan_set_weights(DlwpPlan* pl, int32_t id, const float* kern
     if (bias) DLWP_CUDA_TRY(cudaMemcpy(w.b, bias, sizeof(float) * w.b_elems, cudaMemcpyHostToDevice));
     w.has_bias = bias != nullptr;
     w.set = true;
+    if (pl->tc) return tc_pack_plan_weights(pl, id, kernel);
     return 0;
 }
 
@@ -329,7 +470,7 @@ extern "C" int dlwp_plan_forward(DlwpPlan* pl, int32_t N, const float* x, float*
         DLWP_REQUIRE(outputs[k] != nullptr, DLWP_EINVAL, "output %zu is null", k);
         pl->buffers[pl->outputs[k]].ptr = outputs[k];
     }
-    return run_ops(pl, N, (cudaStream_t)stream);
+    return pl->tc ? run_ops_tc(pl, N, (cudaStream_t)stream, false) : run_ops(pl, N, (cudaStream_t)stream);
 }
 
 extern "C" int dlwp_rollout(DlwpPlan* pl, int32_t N, const float* x0, float* series, int32_t iterations,
@@ -422,3 +563,32 @@ extern "C" int dlwp_rollout_host(DlwpPlan* pl, int32_t N, const float* x0_host, 
     DLWP_CUDA_TRY(cudaStreamSynchronize(pl->s_compute));
     return 0;
 }
+
+extern "C" int dlwp_plan_profile_op(DlwpPlan* pl, int32_t N, int32_t op_index, int32_t iters, float* ms_per_launch,
+                                    dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && ms_per_launch, DLWP_EINVAL, "null argument");
+    DLWP_REQUIRE(op_index >= 0 && op_index < (int)pl->ops.size() && iters > 0, DLWP_EINVAL, "bad op index / iters");
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch, DLWP_ESHAPE, "batch %d outside (0, %d]", N, pl->max_batch);
+    DLWP_REQUIRE(pl->buffers[pl->input_buf].ptr != nullptr, DLWP_ESTATE, "run a forward / rollout first");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaEvent_t e0, e1;
+    DLWP_CUDA_TRY(cudaEventCreate(&e0));
+    DLWP_CUDA_TRY(cudaEventCreate(&e1));
+    int rc = 0;
+    for (int w = 0; w < 2 && !rc; ++w) rc = pl->tc ? run_one_tc(pl, op_index, N, stream) : run_one(pl, op_index, N, stream);
+    cudaEventRecord(e0, stream);
+    for (int k = 0; k < iters && !rc; ++k)
+        rc = pl->tc ? run_one_tc(pl, op_index, N, stream) : run_one(pl, op_index, N, stream);
+    cudaEventRecord(e1, stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    DLWP_CUDA_TRY(e);
+    *ms_per_launch = ms / iters;
+    return 0;
+}
+
+extern "C" int dlwp_plan_uses_tensor_cores(DlwpPlan* pl) { return pl && pl->tc ? 1 : 0; }

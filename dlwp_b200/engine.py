@@ -368,6 +368,16 @@ class CompiledNet(object):
         nat.check(self.lib.dlwp_plan_forward(self.plan, x.shape[0], x.data_ptr(), ptrs, self._stream()),
                   'dlwp_plan_forward')
 
+    def uses_tensor_cores(self):
+        return bool(self.lib.dlwp_plan_uses_tensor_cores(self.plan))
+
+    def profile_op(self, n, op_index, iters=20):
+        """Average device time (ms) of one op of the plan launched alone (CUDA events); run a forward/rollout first."""
+        ms = ctypes.c_float(0)
+        nat.check(self.lib.dlwp_plan_profile_op(self.plan, int(n), int(op_index), int(iters), ctypes.byref(ms),
+                                                self._stream()), 'dlwp_plan_profile_op')
+        return float(ms.value)
+
     def predict(self, x):
         """numpy (N, C, H, W) -> list of numpy outputs (logical shapes), processed in chunks of max_batch."""
         torch = self.torch

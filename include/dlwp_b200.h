@@ -52,7 +52,8 @@ enum {
     DLWP_IMPL_AUTO = 0,
     DLWP_IMPL_DIRECT = 1,     /* one thread per output element, any geometry (reference CUDA kernel)              */
     DLWP_IMPL_FFMA = 2,       /* register-tiled fp32 FFMA kernel, input tiles staged with cp.async                */
-    DLWP_IMPL_FFMA_TMA = 3    /* same math, input tiles staged by TMA (cp.async.bulk.tensor) + in-smem wrap fix-up */
+    DLWP_IMPL_FFMA_TMA = 3,   /* same math, input tiles staged by TMA (cp.async.bulk.tensor) + in-smem wrap fix-up */
+    DLWP_IMPL_TC = 4          /* tcgen05 tensor cores: fp16 hi/lo split x3 (fp32-level accuracy), TMEM accumulators     */
 };
 
 /* Geometry of one fused [periodic/zero pad] -> Conv2D('valid', stride 1, dilation) -> bias -> activation.
@@ -171,6 +172,13 @@ int dlwp_rollout(DlwpPlan* plan, int32_t N, const float* x0, float* series, int3
  * The plan keeps the device buffers for reuse. */
 int dlwp_rollout_host(DlwpPlan* plan, int32_t N, const float* x0_host, float* series_host, int32_t iterations,
                       int32_t d2h_group);
+
+/* Time one op of the plan alone: `iters` launches bracketed by CUDA events on `stream` (after 2 warm-up launches), using
+ * whatever the plan's buffers hold from the last forward / rollout. Blocking. Used by bench.py for the roofline figure. */
+int dlwp_plan_profile_op(DlwpPlan* plan, int32_t N, int32_t op_index, int32_t iters, float* ms_per_launch,
+                         dlwp_stream_t stream);
+/* 1 if the plan runs as a tcgen05 tensor-core chain (DLWP_MATH=tc or every conv op flagged DLWP_IMPL_TC). */
+int dlwp_plan_uses_tensor_cores(DlwpPlan* plan);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 

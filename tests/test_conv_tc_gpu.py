@@ -1,0 +1,126 @@
+"""
+Tensor-core (tcgen05) conv path vs the float64 oracle, per layer through the C ABI (impl = DLWP_IMPL_TC).
+Operands are fp16 hi/lo splits (3 MMAs per K step, fp32 accumulation in TMEM): the bar stays 2e-5 of max|oracle|.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ops as OO
+from tests.helpers import rel_err, run_conv
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+@pytest.fixture(scope='module')
+def env():
+    import torch
+    from dlwp_b200 import _native as nat
+    nat.lib()
+    return nat, torch
+
+
+def _check(nat, torch, N, cin, H, W, cout, k, d, act, seed):
+    rng = np.random.RandomState(seed)
+    x = rng.standard_normal((N, cin, H, W)).astype(np.float32)
+    w = OO.glorot_uniform(rng, k, k, cin, cout)
+    b = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+    pad = d * (k - 1) // 2
+    pads = ((pad, pad), (pad, pad))
+    y = run_conv(nat, torch, x, w, b, d, pads, nat.PAD_ZERO, nat.PAD_PERIODIC, act, nat.IMPL_TC)
+    assert nat.lib().dlwp_debug_flags() == 0
+    ref = OO.pad_conv2d_closed_form(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), (d, d), pads[0],
+                                    pads[1], 'zero', 'periodic')
+    ref = OO.activation({0: None, 1: 'tanh', 2: 'relu'}[act])(ref)
+    err = rel_err(y, ref)
+    assert err < TOL, err
+    return err
+
+
+def test_net_a_conv2_32_to_6_k5(env):
+    nat, torch = env
+    _check(nat, torch, 2, 32, 91, 180, 6, 5, 1, nat.ACT_LINEAR, 1)
+
+
+def test_net_a_conv1_6_to_32_k3_d2_tanh(env):
+    nat, torch = env
+    _check(nat, torch, 2, 6, 91, 180, 32, 3, 2, nat.ACT_TANH, 2)
+
+
+@pytest.mark.parametrize('case', [(3, 6, 23, 36, 32, 3, 2), (3, 32, 23, 36, 6, 5, 1), (2, 16, 17, 44, 64, 3, 1),
+                                  (2, 64, 12, 60, 16, 3, 2), (2, 12, 14, 40, 12, 5, 1),
+                                  (1, 128, 10, 48, 32, 3, 1), (5, 8, 7, 124, 8, 3, 1)])
+def test_other_geometries(env, case):
+    nat, torch = env
+    N, cin, H, W, cout, k, d = case
+    _check(nat, torch, N, cin, H, W, cout, k, d, nat.ACT_RELU, sum(case))
+
+
+def test_many_tiles_persistent_loop(env):
+    """More tiles than SMs: every CTA loops, TMEM accumulator sets and smem stages wrap their phases several times."""
+    nat, torch = env
+    _check(nat, torch, 24, 32, 91, 180, 6, 5, 1, nat.ACT_LINEAR, 7)
+
+
+def test_net_a_rollout_on_tensor_cores_meets_the_gate(env):
+    """The whole plan as a tensor-core chain: state kept in P layout between layers AND between iterations (the last conv
+    re-packs the next input), fp32 series written every step."""
+    nat, torch = env
+    from dlwp_b200.engine import CompiledNet
+    from oracle import layers as OL
+    from tests.helpers import build_product_sequential, oracle_rollout64, oracle_sequential_like
+    layers = OL.net_a_layers()
+    dlwp = build_product_sequential(layers)
+    net = oracle_sequential_like(dlwp, layers, seed=1, bias_scale=0.02)
+    x0 = np.random.RandomState(0).standard_normal((3, 6, 91, 180)).astype(np.float32)
+    eng = CompiledNet(dlwp.model, 3, impl='tc')
+    assert eng.uses_tensor_cores()
+    xd = torch.from_numpy(x0).cuda()
+    got = eng.rollout_device(xd, 50, use_graph=True).cpu().numpy()
+    assert nat.lib().dlwp_debug_flags() == 0
+    ref = oracle_rollout64(net, x0, 50)
+    per_step = [rel_err(got[t], ref[t]) for t in range(50)]
+    assert max(per_step) <= 1e-4, per_step
+    plain = eng.rollout_device(xd, 50, use_graph=False).cpu().numpy()
+    np.testing.assert_array_equal(plain, got)
+    one = eng.predict(x0)[0]                                  # single application (packs the input itself)
+    np.testing.assert_array_equal(one, got[0])
+    host = eng.rollout_host(x0, 7)
+    np.testing.assert_array_equal(host, got[:7])
+    ffma = dlwp.predict_timeseries(x0, 50)                    # the fp32 FFMA path agrees to ~1e-6
+    assert rel_err(ffma, got.astype(np.float64)) < 2e-5
+    eng.close()
+
+
+def test_unrolled_two_step_model_on_tensor_cores(env):
+    """n_outputs = 2 (shared weights applied twice): the first output is both a model output and a conv input."""
+    nat, torch = env
+    from dlwp_b200 import keras
+    from dlwp_b200.engine import CompiledNet
+    from oracle import layers as OL
+    from oracle import rollout as OR
+    from tests.helpers import build_product_sequential, oracle_sequential_like
+    layers = OL.net_a_layers((6, 30, 64))
+    seq = build_product_sequential(layers)
+    net = oracle_sequential_like(seq, layers, seed=5, bias_scale=0.05)
+    x_in = keras.Input(shape=(6, 30, 64))
+
+    def apply(t):
+        for layer in seq.model.layers:
+            t = layer(t)
+        return t
+    o1 = apply(x_in)
+    model = keras.Model(inputs=x_in, outputs=[o1, apply(o1)])
+    eng = CompiledNet(model, 2, impl='tc')
+    assert eng.uses_tensor_cores()
+    x0 = np.random.RandomState(3).standard_normal((2, 6, 30, 64)).astype(np.float32)
+    got = eng.rollout_host(x0, 3)
+
+    def fn(p):
+        a = net.forward(p)
+        return [a, net.forward(a)]
+    ref = OR.functional_predict_timeseries(fn, x0.astype(np.float64), 6, n_steps=2, dtype=np.float64)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 2e-5
+    eng.close()
