@@ -29,6 +29,8 @@ __device__ int g_tc_flags = 0;  // bit 0: mbarrier wait timed out
 #include "internal.h"
 #undef g_device_flags
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -38,7 +40,8 @@ __device__ int g_tc_flags = 0;  // bit 0: mbarrier wait timed out
 
 namespace dlwp {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two sets of 4 quadrant warps)
+constexpr int TC_HPAD = 12;        // zero rows stored above and below every P-layout plane (>= pad + rows per tile)
 constexpr int TC_MAX_KSTEPS = 32;
 
 struct TcParams {
@@ -55,6 +58,8 @@ struct TcParams {
     int act;
     const float* bias;
     const __half* bimg;       // [hi image | lo image], each [G*KS*2 units][NCOLS][8]
+    const __half* xp;         // source activation, P layout with TC_HPAD zero rows above/below each plane
+    int planes_in;            // real planes of the source (the last channel group may be partial)
     float* y32; long long ys_n, ys_c, ys_h;
     __half* yp; int Wp_out, wpad_out, planes_out;
     TcKStep kst[TC_MAX_KSTEPS];  // [G][KS]
@@ -103,6 +108,12 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -113,14 +124,15 @@ struct alignas(16) Half8 {
 
 // ===================================================================================================================
 template <int KW>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
     unsigned char* b_hi = stages + (size_t)p.NS * p.stage_stride;
     unsigned char* b_lo = b_hi + p.b_bytes;
-    float* xch = reinterpret_cast<float*>(b_lo + p.b_bytes);                 // [2][4 quadrants][XL lanes][KW*8]
+    float* xch = reinterpret_cast<float*>(b_lo + p.b_bytes);                 // [2 sets][2 bufs][4 quadrants][XL][KW*8]
     const int XQ = p.XL * KW * 8;                                            // floats one quadrant publishes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * XQ);
+    float* sbias = xch + 2 * 2 * 4 * XQ;                                     // [CBLK*8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.CBLK * 8);
     uint64_t* full = bars;             // [NS]
     uint64_t* empty = bars + 8;        // [NS]
     uint64_t* acc_full = bars + 16;    // [2]
@@ -133,16 +145,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     for (uint32_t i = tid; i < 2 * p.b_bytes / 16; i += TC_THREADS)  // weight images -> smem (hi then lo, contiguous)
         reinterpret_cast<uint4*>(b_hi)[i] = reinterpret_cast<const uint4*>(p.bimg)[i];
-    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    // stages start as zeros: planes of a partial last channel group are never loaded and meet zero weights (0 * 0, not
+    // 0 * stale NaN)
+    for (uint32_t i = tid; i < (uint32_t)p.NS * p.stage_stride / 16; i += TC_THREADS)
+        reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < p.CBLK * 8; i += TC_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    fence_proxy_async();  // generic-proxy writes -> visible to the async proxy (bulk copies, tensor core)
     if (tid == 0) {
-        prefetch_tensormap(&tmap);
         for (int s = 0; s < p.NS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 128);
+            mbar_init(&acc_empty[b], 256);
         }
         fence_mbar_init();
     }
@@ -155,9 +171,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const int Halloc = p.H + 2 * TC_HPAD;
 
     if (warp == 0) {
-        // =============================== TMA producer ===============================
+        // =============================== producer: one bulk copy per plane ===============================
+        // A tile's Rin rows of one plane are contiguous in the P layout (full-width rows, zero rows stored beyond the
+        // poles), so a stage is planes_per_group copies of plane_bytes each -- large requests, not 16-byte tensor rows.
         if (lane == 0) {
             int idx = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -165,10 +184,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 const int y0 = (tile % p.tiles_per_sample) * p.R_out;
                 for (int g = 0; g < p.G; ++g, ++idx) {
                     const int s = idx % p.NS;
+                    const int plane0 = g * p.planes_per_group;
+                    const int np = min(p.planes_per_group, p.planes_in - plane0);
                     mbar_wait(&empty[s], ((idx / p.NS) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], p.stage_bytes);
-                    tma_load_5d(stages + (size_t)s * p.stage_stride, &tmap, &full[s], 0, 0, y0 - p.pad_t,
-                                g * p.planes_per_group, n);
+                    mbar_expect_tx(&full[s], (uint32_t)np * p.plane_bytes);
+                    unsigned char* dst = stages + (size_t)s * p.stage_stride;
+                    for (int q = 0; q < np; ++q) {
+                        const __half* src = p.xp + ((((size_t)n * p.planes_in + plane0 + q) * Halloc) +
+                                                    (size_t)(y0 - p.pad_t + TC_HPAD)) * p.Wp * 8;
+                        bulk_load(dst + (size_t)q * p.plane_bytes, src, p.plane_bytes, &full[s]);
+                    }
                 }
             }
         }
@@ -176,6 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             int idx = 0, it = 0;
+            const uint32_t bhi = smem_u32(b_hi), blo = smem_u32(b_lo);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
                 mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
@@ -192,8 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                             const TcKStep k = p.kst[g * p.KS + ks];
                             const uint32_t a_hi = sbase + k.a_off + row_off;
                             const uint32_t boff = (uint32_t)((g * p.KS + ks) * 2 * p.NCOLS) * 16u;
-                            const uint64_t bd_hi = umma_desc(smem_u32(b_hi) + boff, p.NCOLS * 16u, 128u);
-                            const uint64_t bd_lo = umma_desc(smem_u32(b_lo) + boff, p.NCOLS * 16u, 128u);
+                            const uint64_t bd_hi = umma_desc(bhi + boff, p.NCOLS * 16u, 128u);
+                            const uint64_t bd_lo = umma_desc(blo + boff, p.NCOLS * 16u, 128u);
                             const uint64_t ad_hi = umma_desc(a_hi, k.a_lbo, 128u);
                             const uint64_t ad_lo = umma_desc(a_hi + p.plane_bytes, k.a_lbo, 128u);
                             const uint32_t d = acc_base + t * p.NCOLS;
@@ -208,9 +234,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
         }
     } else {
-        // =============================== epilogue (4 warps) ===============================
-        const int q = warp & 3;
+        // =============================== epilogue (2 sets x 4 quadrant warps) ===============================
+        // Work items (M tile t, filter block cb) alternate between the two sets; inside a set, warp q owns TMEM lanes
+        // 32q..32q+31.  out[p] = sum_j D[p + j*dil][(j, co)]: taps from the same warp come by shuffle, the XL lanes that
+        // spill into the next quadrant go through a small shared-memory mailbox (one named barrier per item and set).
+        const int e = warp - 2;
+        const int q = e & 3, set = e >> 2;
         const int XL = p.XL;
+        float* xset = xch + (size_t)set * 2 * 4 * XQ;
+        const int nitems = p.MT * p.CBLK;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -218,82 +250,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             const int y0 = (tile % p.tiles_per_sample) * p.R_out;
             mbar_wait(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
-            for (int t = 0; t < p.MT; ++t) {
+            int flip = 0;
+            for (int item = set; item < nitems; item += 2, flip ^= 1) {
+                const int t = item / p.CBLK, cb = item - t * p.CBLK;
                 const int ml = q * 32 + lane;           // row of the M tile
                 const int pos = t * p.S + ml;           // flattened (row, padded column) position in the tile
                 const int r = pos / p.Wp, xq = pos - r * p.Wp;
                 const int y = y0 + r;
                 const bool valid = (ml < p.S) && (r < p.R_out) && (y < p.H) && (xq < p.W);
-                for (int cb = 0; cb < p.CBLK; ++cb) {
-                    float d[KW][8];
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
+                float d[KW][8];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
 #pragma unroll
-                    for (int j = 0; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j]);
-                    tmem_ld_wait();
-                    // lanes 0..XL-1 of every quadrant publish their taps for the quadrant before them
-                    float* xb = xch + ((size_t)((t * p.CBLK + cb) & 1) * 4 + q) * XQ;
-                    if (lane < XL) {
+                for (int j = 0; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j]);
+                tmem_ld_wait();
+                float* xb = xset + ((size_t)flip * 4 + q) * XQ;
+                if (lane < XL) {
 #pragma unroll
-                        for (int j = 1; j < KW; ++j)
+                    for (int j = 1; j < KW; ++j)
 #pragma unroll
-                            for (int ci = 0; ci < 8; ++ci) xb[(lane * KW + j) * 8 + ci] = d[j][ci];
+                        for (int ci = 0; ci < 8; ci += 4)
+                            *reinterpret_cast<float4*>(&xb[(lane * KW + j) * 8 + ci]) =
+                                make_float4(d[j][ci], d[j][ci + 1], d[j][ci + 2], d[j][ci + 3]);
+                }
+                named_bar_sync(1 + set, 128);
+                const float* xn = xset + ((size_t)flip * 4 + ((q + 1) & 3)) * XQ;
+                float o[8];
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) o[ci] = d[0][ci] + sbias[cb * 8 + ci];
+#pragma unroll
+                for (int j = 1; j < KW; ++j) {
+                    const int sh = j * p.D;
+#pragma unroll
+                    for (int ci = 0; ci < 8; ++ci) d[j][ci] = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
+                    if (lane + sh >= 32) {  // the tap lives in the next quadrant's first lanes
+                        const float* m = xn + (min(lane + sh - 32, XL - 1) * KW + j) * 8;
+                        const float4 m0 = *reinterpret_cast<const float4*>(m), m1 = *reinterpret_cast<const float4*>(m + 4);
+                        d[j][0] = m0.x; d[j][1] = m0.y; d[j][2] = m0.z; d[j][3] = m0.w;
+                        d[j][4] = m1.x; d[j][5] = m1.y; d[j][6] = m1.z; d[j][7] = m1.w;
                     }
-                    named_bar_sync(1, 128);
-                    const float* xn = xch + ((size_t)((t * p.CBLK + cb) & 1) * 4 + ((q + 1) & 3)) * XQ;
-                    float o[8];
 #pragma unroll
-                    for (int ci = 0; ci < 8; ++ci) o[ci] = d[0][ci];
+                    for (int ci = 0; ci < 8; ++ci) o[ci] += d[j][ci];
+                }
+                if (valid) {
 #pragma unroll
-                    for (int j = 1; j < KW; ++j) {
-                        const int sh = j * p.D;
-                        const int src = lane + sh;
+                    for (int ci = 0; ci < 8; ++ci) o[ci] = (cb * 8 + ci < p.Cout) ? apply_act(o[ci], p.act) : 0.f;
+                    if (p.y32 != nullptr) {
+                        float* yb = p.y32 + (long long)n * p.ys_n + (long long)(cb * 8) * p.ys_c + (long long)y * p.ys_h + xq;
+#pragma unroll
+                        for (int ci = 0; ci < 8; ++ci)
+                            if (cb * 8 + ci < p.Cout) yb[(long long)ci * p.ys_c] = o[ci];
+                    }
+                    if (p.yp != nullptr) {
+                        __half h[8], l[8];
 #pragma unroll
                         for (int ci = 0; ci < 8; ++ci) {
-                            const float v = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
-                            o[ci] += (src < 32) ? v : xn[(min(src - 32, XL - 1) * KW + j) * 8 + ci];
+                            h[ci] = __float2half_rn(o[ci]);
+                            l[ci] = __float2half_rn(o[ci] - __half2float(h[ci]));
                         }
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int ci = 0; ci < 8; ++ci) {
-                            const int co = cb * 8 + ci;
-                            const float b = (p.bias != nullptr && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
-                            o[ci] = co < p.Cout ? apply_act(o[ci] + b, p.act) : 0.f;  // padded channels stay exactly 0
+                        Half8 vh, vl;
+                        vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
+                        vh.c = __halves2half2(h[4], h[5]); vh.d = __halves2half2(h[6], h[7]);
+                        vl.a = __halves2half2(l[0], l[1]); vl.b = __halves2half2(l[2], l[3]);
+                        vl.c = __halves2half2(l[4], l[5]); vl.d = __halves2half2(l[6], l[7]);
+                        const int Hout = p.H + 2 * TC_HPAD;
+                        Half8* row_hi = reinterpret_cast<Half8*>(p.yp) +
+                                        (((size_t)n * p.planes_out + cb * 2) * Hout + y + TC_HPAD) * p.Wp_out + xq + p.wpad_out;
+                        Half8* row_lo = row_hi + (size_t)Hout * p.Wp_out;
+                        row_hi[0] = vh;
+                        row_lo[0] = vl;
+                        if (xq < p.wpad_out) {            // periodic longitude halo of the NEXT layer, right side
+                            row_hi[p.W] = vh;
+                            row_lo[p.W] = vl;
                         }
-                        if (p.y32 != nullptr) {
-#pragma unroll
-                            for (int ci = 0; ci < 8; ++ci) {
-                                const int co = cb * 8 + ci;
-                                if (co < p.Cout)
-                                    p.y32[(long long)n * p.ys_n + (long long)co * p.ys_c + (long long)y * p.ys_h + xq] = o[ci];
-                            }
-                        }
-                        if (p.yp != nullptr) {
-                            __half h[8], l[8];
-#pragma unroll
-                            for (int ci = 0; ci < 8; ++ci) {
-                                h[ci] = __float2half_rn(o[ci]);
-                                l[ci] = __float2half_rn(o[ci] - __half2float(h[ci]));
-                            }
-                            Half8 vh, vl;
-                            vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
-                            vh.c = __halves2half2(h[4], h[5]); vh.d = __halves2half2(h[6], h[7]);
-                            vl.a = __halves2half2(l[0], l[1]); vl.b = __halves2half2(l[2], l[3]);
-                            vl.c = __halves2half2(l[4], l[5]); vl.d = __halves2half2(l[6], l[7]);
-                            const long long row_hi = (((long long)n * p.planes_out + cb * 2) * p.H + y) * p.Wp_out;
-                            const long long row_lo = (((long long)n * p.planes_out + cb * 2 + 1) * p.H + y) * p.Wp_out;
-                            Half8* yp = reinterpret_cast<Half8*>(p.yp);
-                            const int xo = xq + p.wpad_out;
-                            yp[row_hi + xo] = vh;
-                            yp[row_lo + xo] = vl;
-                            if (xq < p.wpad_out) {            // periodic longitude halo of the NEXT layer, right side
-                                yp[row_hi + xo + p.W] = vh;
-                                yp[row_lo + xo + p.W] = vl;
-                            }
-                            if (xq >= p.W - p.wpad_out) {     // ... and left side
-                                yp[row_hi + xo - p.W] = vh;
-                                yp[row_lo + xo - p.W] = vl;
-                            }
+                        if (xq >= p.W - p.wpad_out) {     // ... and left side
+                            row_hi[-p.W] = vh;
+                            row_lo[-p.W] = vl;
                         }
                     }
                 }
@@ -337,40 +368,15 @@ __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict
         vl.a = __halves2half2(l[0], l[1]); vl.b = __halves2half2(l[2], l[3]);
         vl.c = __halves2half2(l[4], l[5]); vl.d = __halves2half2(l[6], l[7]);
         Half8* out = reinterpret_cast<Half8*>(yp);
-        out[(((long long)n * 2 * C8 + 2 * c8) * H + y) * Wp + xq] = vh;
-        out[(((long long)n * 2 * C8 + 2 * c8 + 1) * H + y) * Wp + xq] = vl;
+        const long long Ha = H + 2 * TC_HPAD;
+        out[(((long long)n * 2 * C8 + 2 * c8) * Ha + y + TC_HPAD) * Wp + xq] = vh;
+        out[(((long long)n * 2 * C8 + 2 * c8 + 1) * Ha + y + TC_HPAD) * Wp + xq] = vl;
     }
 }
 
 // ===================================================================================================================
 // Host side
 // ===================================================================================================================
-typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int encode_p_map(CUtensorMap* map, const __half* base, int N, int planes, int H, int Wp, int Rin, int ppg) {
-    static encode_tiled_t fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<encode_tiled_t>(ptr);
-    });
-    DLWP_REQUIRE(fn != nullptr, DLWP_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
-    cuuint64_t dims[5] = {8, (cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)N};
-    cuuint64_t str[4] = {16, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16, (cuuint64_t)planes * H * Wp * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)Wp, (cuuint32_t)Rin, (cuuint32_t)ppg, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, str, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DLWP_REQUIRE(r == CUDA_SUCCESS, DLWP_ESHAPE, "cuTensorMapEncodeTiled (P layout) failed with CUresult %d", (int)r);
-    return 0;
-}
-
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 bool tc_geometry_ok(const DlwpConvDesc& d) {
@@ -400,9 +406,11 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->S = 128 - halo_w;
     // units = (chunk, tap) in order; groups of chunks so that a group has an even number of units when possible
     const int smem_budget = 224 * 1024;
-    const size_t fixed = (size_t)2 * 4 * halo_w * d.kw * 8 * 4 + 512;  // lane exchange + barriers
+    const size_t fixed = (size_t)2 * 2 * 4 * halo_w * d.kw * 8 * 4 + (size_t)cdiv(d.Cout, 8) * 32 + 512;  // mailboxes, bias, barriers
     int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0;
-    for (int r_out = 8; r_out >= 1; --r_out) {
+    const char* env_r = getenv("DLWP_TC_ROUT");
+    const int r_max = env_r ? atoi(env_r) : 8;
+    for (int r_out = r_max; r_out >= 1; --r_out) {
         const int rin = r_out + halo_h;
         const int mt = cdiv(r_out * L->Wp, L->S);
         if (mt * L->NCOLS > 256) continue;  // two accumulator sets in 512 TMEM columns
@@ -522,12 +530,11 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
     p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
     for (int i = 0; i < L.G * L.KS; ++i) p.kst[i] = kst[i];
-    CUtensorMap map;
-    int rc = encode_p_map(&map, xp, d.N, L.planes, d.H, L.Wp, L.Rin, 2 * L.cpg);
-    if (rc) return rc;
+    p.xp = xp;
+    p.planes_in = L.planes;
     const int grid = std::min(p.total_tiles, g_tc_sms);
-    if (d.kw == 3) conv_tc_kernel<3><<<grid, TC_THREADS, L.smem, stream>>>(p, map);
-    else conv_tc_kernel<5><<<grid, TC_THREADS, L.smem, stream>>>(p, map);
+    if (d.kw == 3) conv_tc_kernel<3><<<grid, TC_THREADS, L.smem, stream>>>(p);
+    else conv_tc_kernel<5><<<grid, TC_THREADS, L.smem, stream>>>(p);
     return after_launch("conv_tc_kernel");
 }
 
@@ -538,6 +545,8 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
     pack_state_kernel<<<blocks, 256, 0, stream>>>(x, xp, N, C, H, W, wpad, xs_n, xs_c, xs_h);
     return after_launch("pack_state_kernel");
 }
+
+size_t tc_p_bytes(int N, int planes, int H, int Wp) { return (size_t)N * planes * (H + 2 * TC_HPAD) * Wp * 16; }
 
 int tc_debug_flags() {
     int v = 0, zero = 0;
@@ -560,9 +569,10 @@ int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, con
     TcKStep kst[TC_MAX_KSTEPS];
     DLWP_REQUIRE(tc_pack_weights(d, L, w_host.data(), &img, kst) == 0, DLWP_ESHAPE, "weight packing failed");
     __half *bimg = nullptr, *xp = nullptr;
-    const size_t xp_bytes = (size_t)d.N * L.planes * d.H * L.Wp * 16;
+    const size_t xp_bytes = tc_p_bytes(d.N, L.planes, d.H, L.Wp);
     DLWP_CUDA_TRY(cudaMalloc(&bimg, img.size() * 2));
     DLWP_CUDA_TRY(cudaMalloc(&xp, xp_bytes));
+    DLWP_CUDA_TRY(cudaMemsetAsync(xp, 0, xp_bytes, stream));
     DLWP_CUDA_TRY(cudaMemcpyAsync(bimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
     int rc = tc_pack_state(x, xp, d.N, d.Cin, d.H, d.W, L.wpad, d.x_stride_n, d.x_stride_c, d.x_stride_h, stream);
     if (!rc) rc = tc_launch(d, L, kst, xp, bimg, bias, y, nullptr, 0, 0, stream);

@@ -38,5 +38,7 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
                   cudaStream_t stream);
 int tc_debug_flags();
+// bytes of a P-layout buffer (planes of (H + zero rows) x Wp pixels x 8 fp16)
+size_t tc_p_bytes(int N, int planes, int H, int Wp);
 
 }  // namespace dlwp

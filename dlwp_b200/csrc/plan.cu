@@ -162,7 +162,7 @@ static int tc_setup(DlwpPlan* pl) {
     }
     for (Buffer& b : pl->buffers)
         if (b.wpad >= 0) {
-            const size_t bytes = (size_t)pl->max_batch * b.planes * b.d.H * (b.d.W + 2 * b.wpad) * 16;
+            const size_t bytes = tc_p_bytes(pl->max_batch, b.planes, b.d.H, b.d.W + 2 * b.wpad);
             if (cudaMalloc(&b.P, bytes) != cudaSuccess) return DLWP_ENOMEM;
             cudaMemset(b.P, 0, bytes);
         }

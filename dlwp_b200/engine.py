@@ -329,6 +329,9 @@ class CompiledNet(object):
             self.plan = ctypes.c_void_p()
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():   # the CUDA context may already be gone at interpreter shutdown
+            return
         try:
             self.close()
         except Exception:

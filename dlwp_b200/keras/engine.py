@@ -377,6 +377,9 @@ class Model(object):
             self.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():
+            return
         try:
             if self._engine is not None:
                 self._engine.close()
