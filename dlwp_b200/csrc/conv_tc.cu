@@ -40,7 +40,8 @@ __device__ int g_tc_flags = 0;  // bit 0: mbarrier wait timed out
 
 namespace dlwp {
 
-constexpr int TC_THREADS = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two sets of 4 quadrant warps)
+constexpr int TC_SETS = 4;          // epilogue warp sets (each = 4 warps, one per TMEM lane quadrant)
+constexpr int TC_THREADS = 64 + TC_SETS * 128;  // warp 0 producer, warp 1 MMA issuer, then the epilogue sets
 constexpr int TC_HPAD = 12;        // zero rows stored above and below every P-layout plane (>= pad + rows per tile)
 constexpr int TC_MAX_KSTEPS = 32;
 
@@ -114,6 +115,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -129,9 +137,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     unsigned char* stages = smem_raw;
     unsigned char* b_hi = stages + (size_t)p.NS * p.stage_stride;
     unsigned char* b_lo = b_hi + p.b_bytes;
-    float* xch = reinterpret_cast<float*>(b_lo + p.b_bytes);                 // [2 sets][2 bufs][4 quadrants][XL][KW*8]
-    const int XQ = p.XL * KW * 8;                                            // floats one quadrant publishes
-    float* sbias = xch + 2 * 2 * 4 * XQ;                                     // [CBLK*8]
+    float* xch = reinterpret_cast<float*>(b_lo + p.b_bytes);  // mailbox [set][item of the set][4 quadrants][XL][(KW-1)*8]
+    const int XQ = p.XL * (KW - 1) * 8;                       // floats one quadrant publishes per item
+    const int items_per_set = (p.MT * p.CBLK + TC_SETS - 1) / TC_SETS;
+    float* sbias = xch + (size_t)TC_SETS * items_per_set * 4 * XQ;  // [CBLK*8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.CBLK * 8);
     uint64_t* full = bars;             // [NS]
     uint64_t* empty = bars + 8;        // [NS]
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 256);
+            mbar_init(&acc_empty[b], TC_SETS * 128);
         }
         fence_mbar_init();
     }
@@ -199,49 +208,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            int idx = 0, it = 0;
-            const uint32_t bhi = smem_u32(b_hi), blo = smem_u32(b_lo);
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int ab = it & 1;
-                mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
+        // The whole warp runs the loop convergently (all values are warp-uniform, so the descriptor arithmetic stays on
+        // the uniform datapath); one elected lane issues the tcgen05 instructions.  The MMAs are small (N = 32..96), so
+        // the issue rate matters: per K step the descriptors cost two integer adds on precomputed 32-bit low words.
+        const bool leader = elect_one();
+        int idx = 0, it = 0;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, sm_100 descriptor version
+        const uint32_t b_lbo_field = ((p.NCOLS * 16u) >> 4) << 16;
+        const uint32_t bhi16 = smem_u32(b_hi) >> 4, blo16 = smem_u32(b_lo) >> 4;
+        const uint32_t plane16 = p.plane_bytes >> 4;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc_base = tmem + ab * ACC_COLS;
+            for (int g = 0; g < p.G; ++g, ++idx) {
+                const int s = idx % p.NS;
+                mbar_wait(&full[s], (idx / p.NS) & 1);
                 tc_fence_after();
-                const uint32_t acc_base = tmem + ab * ACC_COLS;
-                for (int g = 0; g < p.G; ++g, ++idx) {
-                    const int s = idx % p.NS;
-                    mbar_wait(&full[s], (idx / p.NS) & 1);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(stages + (size_t)s * p.stage_stride);
-                    for (int t = 0; t < p.MT; ++t) {
-                        const uint32_t row_off = (uint32_t)(t * p.S) * 16u;
-                        for (int ks = 0; ks < p.KS; ++ks) {
-                            const TcKStep k = p.kst[g * p.KS + ks];
-                            const uint32_t a_hi = sbase + k.a_off + row_off;
-                            const uint32_t boff = (uint32_t)((g * p.KS + ks) * 2 * p.NCOLS) * 16u;
-                            const uint64_t bd_hi = umma_desc(bhi + boff, p.NCOLS * 16u, 128u);
-                            const uint64_t bd_lo = umma_desc(blo + boff, p.NCOLS * 16u, 128u);
-                            const uint64_t ad_hi = umma_desc(a_hi, k.a_lbo, 128u);
-                            const uint64_t ad_lo = umma_desc(a_hi + p.plane_bytes, k.a_lbo, 128u);
-                            const uint32_t d = acc_base + t * p.NCOLS;
+                const uint32_t sbase16 = smem_u32(stages + (size_t)s * p.stage_stride) >> 4;
+                for (int t = 0; t < p.MT; ++t) {
+                    const uint32_t d = acc_base + t * p.NCOLS;
+                    const uint32_t row16 = sbase16 + (uint32_t)(t * p.S);
+                    for (int ks = 0; ks < p.KS; ++ks) {
+                        const TcKStep k = p.kst[g * p.KS + ks];
+                        const uint32_t a_lo = ((k.a_lbo >> 4) << 16) | (row16 + (k.a_off >> 4));
+                        const uint32_t boff16 = (uint32_t)((g * p.KS + ks) * 2 * p.NCOLS);
+                        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo;
+                        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo + plane16);
+                        const uint64_t bd_hi = ((uint64_t)desc_hi << 32) | (b_lbo_field | (bhi16 + boff16));
+                        const uint64_t bd_lo = ((uint64_t)desc_hi << 32) | (b_lbo_field | (blo16 + boff16));
+                        if (leader) {
                             umma_f16(d, ad_hi, bd_hi, p.idesc, (g | ks) != 0);
                             umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
                             umma_f16(d, ad_lo, bd_hi, p.idesc, 1u);
                         }
                     }
-                    umma_commit(&empty[s]);  // stage s may be refilled once these MMAs have read it
                 }
-                umma_commit(&acc_full[ab]);
+                __syncwarp();
+                if (leader) umma_commit(&empty[s]);  // stage s may be refilled once these MMAs have read it
             }
+            if (leader) umma_commit(&acc_full[ab]);
         }
     } else {
-        // =============================== epilogue (2 sets x 4 quadrant warps) ===============================
-        // Work items (M tile t, filter block cb) alternate between the two sets; inside a set, warp q owns TMEM lanes
-        // 32q..32q+31.  out[p] = sum_j D[p + j*dil][(j, co)]: taps from the same warp come by shuffle, the XL lanes that
-        // spill into the next quadrant go through a small shared-memory mailbox (one named barrier per item and set).
-        const int e = warp - 2;
-        const int q = e & 3, set = e >> 2;
+        // =============================== epilogue (TC_SETS sets x 4 quadrant warps) ===============================
+        // Work items (M tile t, filter block cb) are dealt round-robin to the sets; inside a set, the warp with hardware
+        // index w owns TMEM lanes 32*(w%4)..+31.  out[p] = sum_j D[p + j*dil][(j, co)]: taps from the same quadrant come by
+        // warp shuffle, the XL lanes that spill into the next quadrant through a shared-memory mailbox.  Two passes per tile
+        // so that a set synchronises twice per tile instead of once per item: (1) every item's boundary taps -> mailbox,
+        // barrier, (2) the sums, barrier.
+        const int q = warp & 3, set = (warp - 2) >> 2;
         const int XL = p.XL;
-        float* xset = xch + (size_t)set * 2 * 4 * XQ;
+        float* xset = xch + (size_t)set * items_per_set * 4 * XQ;
         const int nitems = p.MT * p.CBLK;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -250,8 +268,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             const int y0 = (tile % p.tiles_per_sample) * p.R_out;
             mbar_wait(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
-            int flip = 0;
-            for (int item = set; item < nitems; item += 2, flip ^= 1) {
+            // ---- pass 1: publish the taps the previous quadrant will need --------------------------------------------
+            int li = 0;
+            for (int item = set; item < nitems; item += TC_SETS, ++li) {
+                const int t = item / p.CBLK, cb = item - t * p.CBLK;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
+                float d[KW - 1][8];
+#pragma unroll
+                for (int j = 1; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j - 1]);
+                tmem_ld_wait();
+                if (lane < XL) {
+                    float* xb = xset + ((size_t)li * 4 + q) * XQ + lane * (KW - 1) * 8;
+#pragma unroll
+                    for (int j = 0; j < KW - 1; ++j) {
+                        *reinterpret_cast<float4*>(xb + j * 8) = make_float4(d[j][0], d[j][1], d[j][2], d[j][3]);
+                        *reinterpret_cast<float4*>(xb + j * 8 + 4) = make_float4(d[j][4], d[j][5], d[j][6], d[j][7]);
+                    }
+                }
+            }
+            named_bar_sync(1 + set, 128);
+            // ---- pass 2: shifted sums, bias, activation, stores ---------------------------------------------------------
+            li = 0;
+            for (int item = set; item < nitems; item += TC_SETS, ++li) {
                 const int t = item / p.CBLK, cb = item - t * p.CBLK;
                 const int ml = q * 32 + lane;           // row of the M tile
                 const int pos = t * p.S + ml;           // flattened (row, padded column) position in the tile
@@ -263,17 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
                 for (int j = 0; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j]);
                 tmem_ld_wait();
-                float* xb = xset + ((size_t)flip * 4 + q) * XQ;
-                if (lane < XL) {
-#pragma unroll
-                    for (int j = 1; j < KW; ++j)
-#pragma unroll
-                        for (int ci = 0; ci < 8; ci += 4)
-                            *reinterpret_cast<float4*>(&xb[(lane * KW + j) * 8 + ci]) =
-                                make_float4(d[j][ci], d[j][ci + 1], d[j][ci + 2], d[j][ci + 3]);
-                }
-                named_bar_sync(1 + set, 128);
-                const float* xn = xset + ((size_t)flip * 4 + ((q + 1) & 3)) * XQ;
+                const float* xn = xset + ((size_t)li * 4 + ((q + 1) & 3)) * XQ;
                 float o[8];
 #pragma unroll
                 for (int ci = 0; ci < 8; ++ci) o[ci] = d[0][ci] + sbias[cb * 8 + ci];
@@ -283,7 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
                     for (int ci = 0; ci < 8; ++ci) d[j][ci] = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
                     if (lane + sh >= 32) {  // the tap lives in the next quadrant's first lanes
-                        const float* m = xn + (min(lane + sh - 32, XL - 1) * KW + j) * 8;
+                        const float* m = xn + (min(lane + sh - 32, XL - 1) * (KW - 1) + (j - 1)) * 8;
                         const float4 m0 = *reinterpret_cast<const float4*>(m), m1 = *reinterpret_cast<const float4*>(m + 4);
                         d[j][0] = m0.x; d[j][1] = m0.y; d[j][2] = m0.z; d[j][3] = m0.w;
                         d[j][4] = m1.x; d[j][5] = m1.y; d[j][6] = m1.z; d[j][7] = m1.w;
@@ -331,6 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
+            named_bar_sync(1 + set, 128);  // the mailbox may be rewritten (next tile's pass 1) only after every reader is done
         }
     }
 
@@ -406,14 +435,16 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->S = 128 - halo_w;
     // units = (chunk, tap) in order; groups of chunks so that a group has an even number of units when possible
     const int smem_budget = 224 * 1024;
-    const size_t fixed = (size_t)2 * 2 * 4 * halo_w * d.kw * 8 * 4 + (size_t)cdiv(d.Cout, 8) * 32 + 512;  // mailboxes, bias, barriers
+    const size_t bias_bars = (size_t)cdiv(d.Cout, 8) * 32 + 512;
     int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0;
     const char* env_r = getenv("DLWP_TC_ROUT");
-    const int r_max = env_r ? atoi(env_r) : 8;
+    // big-K layers (>= 2 channel groups per tile) run best with small tiles: more tiles to balance, shorter TMA latency
+    const int r_max = env_r ? atoi(env_r) : (cdiv(L->C8, std::min(L->C8, 4)) >= 1 && L->C8 > 2 ? 2 : 8);
     for (int r_out = r_max; r_out >= 1; --r_out) {
         const int rin = r_out + halo_h;
         const int mt = cdiv(r_out * L->Wp, L->S);
         if (mt * L->NCOLS > 256) continue;  // two accumulator sets in 512 TMEM columns
+        const size_t fixed = (size_t)TC_SETS * cdiv(mt * L->CBLK, TC_SETS) * 4 * halo_w * (d.kw - 1) * 8 * 4 + bias_bars;
         for (int cpg = std::min(L->C8, 4); cpg >= 1; --cpg) {
             const int G = cdiv(L->C8, cpg);
             const int units = cpg * d.kh;
@@ -442,7 +473,8 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->stage_stride = (L->stage_bytes + 127) / 128 * 128;
     L->plane_bytes = (uint32_t)(L->Rin * L->Wp * 16);
     L->b_bytes = (uint32_t)(L->G * L->KS * 2 * L->NCOLS * 16);
-    L->smem = (size_t)L->NS * L->stage_stride + 2 * (size_t)L->b_bytes + fixed + 1024;
+    L->smem = (size_t)L->NS * L->stage_stride + 2 * (size_t)L->b_bytes +
+              (size_t)TC_SETS * cdiv(L->MT * L->CBLK, TC_SETS) * 4 * halo_w * (d.kw - 1) * 8 * 4 + bias_bars + 1024;
     return 0;
 }
 

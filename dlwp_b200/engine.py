@@ -17,6 +17,8 @@ host memory and the current stream only.
 
 import ctypes
 
+import sys
+
 import numpy as np
 
 from . import _native as nat
@@ -329,7 +331,6 @@ class CompiledNet(object):
             self.plan = ctypes.c_void_p()
 
     def __del__(self):
-        import sys
         if sys is None or sys.is_finalizing():   # the CUDA context may already be gone at interpreter shutdown
             return
         try:

@@ -11,6 +11,8 @@ carry the leading `None` batch axis, weights use Keras layouts -- so the example
 import pickle
 import re
 
+import sys
+
 import numpy as np
 
 _NAME_COUNTS = {}
@@ -377,7 +379,6 @@ class Model(object):
             self.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
 
     def __del__(self):
-        import sys
         if sys is None or sys.is_finalizing():
             return
         try:
