@@ -675,7 +675,6 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
                  "row window [%d,%d) outside the %d output rows", d.row_begin, d.row_end, Ho);
 
     if (d.impl == DLWP_IMPL_TC) {
-        DLWP_REQUIRE(all_rows, DLWP_ESHAPE, "the tensor-core path does not take row windows yet");
         return conv2d_fwd_tc(d, x, w, bias, y, stream);
     }
     TileChoice tc;

@@ -53,6 +53,7 @@ struct TcParams {
     int G, KS, NS;            // channel groups per tile, K steps per group, smem stages
     int planes_per_group;
     int tiles_per_sample, total_tiles;
+    int row0, row1;           // output rows [row0, row1) this launch computes (latitude band); tiles start at row0
     uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;  // b_bytes: one (hi or lo) weight image
     int XL;                   // lanes a pixel reaches to its right: (KW-1)*D
     uint32_t idesc;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             int idx = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int n = tile / p.tiles_per_sample;
-                const int y0 = (tile % p.tiles_per_sample) * p.R_out;
+                const int y0 = p.row0 + (tile % p.tiles_per_sample) * p.R_out;
                 for (int g = 0; g < p.G; ++g, ++idx) {
                     const int s = idx % p.NS;
                     const int plane0 = g * p.planes_per_group;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             const int n = tile / p.tiles_per_sample;
-            const int y0 = (tile % p.tiles_per_sample) * p.R_out;
+            const int y0 = p.row0 + (tile % p.tiles_per_sample) * p.R_out;
             mbar_wait(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
             // ---- pass 1: publish the taps the previous quadrant will need --------------------------------------------
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 const int pos = t * p.S + ml;           // flattened (row, padded column) position in the tile
                 const int r = pos / p.Wp, xq = pos - r * p.Wp;
                 const int y = y0 + r;
-                const bool valid = (ml < p.S) && (r < p.R_out) && (y < p.H) && (xq < p.W);
+                const bool valid = (ml < p.S) && (r < p.R_out) && (y < p.row1) && (xq < p.W);
                 float d[KW][8];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
 #pragma unroll
@@ -335,6 +336,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                             h[ci] = __float2half_rn(o[ci]);
                             l[ci] = __float2half_rn(o[ci] - __half2float(h[ci]));
                         }
+                        float amax = 0.f;
+#pragma unroll
+                        for (int ci = 0; ci < 8; ++ci) amax = fmaxf(amax, fabsf(o[ci]));
+                        if (!(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);  // outside the fp16 split's range (or NaN)
                         Half8 vh, vl;
                         vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
                         vh.c = __halves2half2(h[4], h[5]); vh.d = __halves2half2(h[6], h[7]);
@@ -371,15 +376,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 // fp32 (N,C,H,W) -> P layout with the periodic halo; one thread per (n, c8, y, padded x)
 __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict__ x, __half* __restrict__ yp, int N, int C,
                                                          int H, int W, int wpad, long long xs_n, long long xs_c,
-                                                         long long xs_h) {
+                                                         long long xs_h, int row0, int rows) {
     const int Wp = W + 2 * wpad, C8 = (C + 7) / 8;
-    const long long total = (long long)N * C8 * H * Wp;
+    const long long total = (long long)N * C8 * rows * Wp;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int xq = (int)(idx % Wp);
         long long t = idx / Wp;
-        const int y = (int)(t % H);
-        t /= H;
+        const int y = row0 + (int)(t % rows);
+        t /= rows;
         const int c8 = (int)(t % C8);
         const int n = (int)(t / C8);
         const int gx = wrap_index(xq - wpad, W);
@@ -390,6 +395,7 @@ __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict
             const float v = c < C ? x[(long long)n * xs_n + (long long)c * xs_c + (long long)y * xs_h + gx] : 0.f;
             h[e] = __float2half_rn(v);
             l[e] = __float2half_rn(v - __half2float(h[e]));
+            if (__hisinf(h[e]) || __hisnan(h[e])) atomicOr(&g_tc_flags, 2);  // |x| > 65504: outside the fp16 split's range
         }
         Half8 vh, vl;
         vh.a = __halves2half2(h[0], h[1]); vh.b = __halves2half2(h[2], h[3]);
@@ -554,7 +560,10 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.KW = d.kw; p.D = d.dil_w; p.pad_t = d.pad_t;
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (d.kw - 1) * d.dil_w;
     p.G = L.G; p.KS = L.KS; p.NS = L.NS; p.planes_per_group = 2 * L.cpg;
-    p.tiles_per_sample = cdiv(d.H, L.R_out);
+    const bool all_rows = d.row_begin == 0 && d.row_end == 0;
+    p.row0 = all_rows ? 0 : d.row_begin;
+    p.row1 = all_rows ? d.H : d.row_end;
+    p.tiles_per_sample = cdiv(p.row1 - p.row0, L.R_out);
     p.total_tiles = p.tiles_per_sample * d.N;
     p.stage_bytes = L.stage_bytes; p.stage_stride = L.stage_stride; p.plane_bytes = L.plane_bytes; p.b_bytes = L.b_bytes;
     p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
@@ -571,10 +580,11 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
 }
 
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
-                  long long xs_h, cudaStream_t stream) {
-    const long long total = (long long)N * cdiv(C, 8) * H * (W + 2 * wpad);
+                  long long xs_h, cudaStream_t stream, int row0, int row1) {
+    if (row0 == 0 && row1 == 0) row1 = H;
+    const long long total = (long long)N * cdiv(C, 8) * (row1 - row0) * (W + 2 * wpad);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    pack_state_kernel<<<blocks, 256, 0, stream>>>(x, xp, N, C, H, W, wpad, xs_n, xs_c, xs_h);
+    pack_state_kernel<<<blocks, 256, 0, stream>>>(x, xp, N, C, H, W, wpad, xs_n, xs_c, xs_h, row0, row1 - row0);
     return after_launch("pack_state_kernel");
 }
 

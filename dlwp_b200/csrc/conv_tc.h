@@ -34,7 +34,7 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream);
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
-                  long long xs_h, cudaStream_t stream);
+                  long long xs_h, cudaStream_t stream, int row0 = 0, int row1 = 0);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
                   cudaStream_t stream);
 int tc_debug_flags();

@@ -82,6 +82,7 @@ struct DlwpPlan {
     std::vector<TcLayer> tc_layers;
     std::vector<int> tc_pdst;      // buffer whose P image op i writes (-1: none)
     int tc_feedback_op = -1;       // op that also serves as the packer of the next iteration's input
+    int tc_in_row0 = 0, tc_in_row1 = 0;  // rows of the input the (row-windowed) convs read: only those are packed
 };
 
 namespace dlwp {
@@ -124,19 +125,28 @@ static DlwpConvDesc conv_desc_of(const DlwpPlan* pl, const DlwpOpDesc& op, int N
 
 // Decide whether the whole plan can run as a tensor-core chain and size its packed buffers.
 static int tc_setup(DlwpPlan* pl) {
+    // Default: use the tensor-core chain whenever the whole plan is eligible.  DLWP_MATH=ffma (or any conv op forced to
+    // an FFMA/direct implementation) keeps the fp32 FFMA kernels.
     const char* env = getenv("DLWP_MATH");
-    bool want = env && !strcmp(env, "tc");
-    bool all_flagged = !pl->ops.empty();
-    for (const DlwpOpDesc& op : pl->ops) all_flagged = all_flagged && op.kind == DLWP_OP_CONV && op.impl == DLWP_IMPL_TC;
-    if (!want && !all_flagged) return 0;
+    if (env && !strcmp(env, "ffma")) return 0;
+    for (const DlwpOpDesc& op : pl->ops)
+        if (op.kind == DLWP_OP_CONV && op.impl != DLWP_IMPL_AUTO && op.impl != DLWP_IMPL_TC) return 0;
     const int nops = (int)pl->ops.size();
     std::vector<TcLayer> layers(nops);
     std::vector<int> writer(pl->buffers.size(), -1);
+    bool windowed = false;
     for (int i = 0; i < nops; ++i) {
         const DlwpOpDesc& op = pl->ops[i];
         const Buffer& s = pl->buffers[op.src];
         const Buffer& t = pl->buffers[op.dst];
-        if (op.kind != DLWP_OP_CONV || op.row_begin || op.row_end) return 0;
+        if (op.kind != DLWP_OP_CONV) return 0;
+        if (op.row_begin || op.row_end) windowed = true;
+        if (op.src == pl->input_buf && (op.row_begin || op.row_end)) {
+            const int lo = std::max(0, op.row_begin - op.pad_t);
+            const int hi = std::min(s.d.H, op.row_end - op.pad_t + op.dil_h * (op.kh - 1));
+            if (pl->tc_in_row1 == 0) { pl->tc_in_row0 = lo; pl->tc_in_row1 = hi; }
+            else { pl->tc_in_row0 = std::min(pl->tc_in_row0, lo); pl->tc_in_row1 = std::max(pl->tc_in_row1, hi); }
+        }
         if (op.src_c0 != 0 || op.src_c != s.d.C || op.dst_c0 != 0 || op.Cout != t.d.C) return 0;
         DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
         if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
@@ -155,8 +165,9 @@ static int tc_setup(DlwpPlan* pl) {
     const int last_out = pl->outputs.back();
     const Buffer& in = pl->buffers[pl->input_buf];
     const Buffer& lo = pl->buffers[last_out];
-    if (writer[last_out] >= 0 && pl->tc_pdst[writer[last_out]] < 0 && lo.d.C == in.d.C && lo.d.H == in.d.H &&
-        lo.d.W == in.d.W) {
+    // (not for latitude bands: the halo rows of the next input arrive as fp32 from the neighbours and are re-packed)
+    if (!windowed && writer[last_out] >= 0 && pl->tc_pdst[writer[last_out]] < 0 && lo.d.C == in.d.C &&
+        lo.d.H == in.d.H && lo.d.W == in.d.W) {
         pl->tc_feedback_op = writer[last_out];
         pl->tc_pdst[writer[last_out]] = pl->input_buf;
     }
@@ -209,7 +220,7 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_pa
     Buffer& in = pl->buffers[pl->input_buf];
     if (!input_is_packed) {
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
-                               (long long)in.d.H * in.d.W, in.d.W, stream);
+                               (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1);
         if (rc) return rc;
     }
     for (size_t i = 0; i < pl->ops.size(); ++i) {

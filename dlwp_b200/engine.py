@@ -273,6 +273,8 @@ def _torch():
 class CompiledNet(object):
     """A DlwpPlan plus the host-side glue around it.  Created lazily by keras.Model.engine()."""
 
+    FLAG_TC_RANGE = 4   # dlwp_debug_flags bit: a value left the fp16 hi/lo split's range (|x| > 65504)
+
     def __init__(self, model, batch, impl=None, row_windows=None):
         """row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
         (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op."""
@@ -320,7 +322,18 @@ class CompiledNet(object):
         for i, o in enumerate(live):
             ops[i] = nat.OpDesc(*[int(o[n]) for n in names])
         net = nat.NetDesc(len(bufs), len(ops), len(self.low.weight_layers), int(max_batch), bufs, ops)
-        nat.check(self.lib.dlwp_plan_create(ctypes.byref(net), ctypes.byref(self.plan)), 'dlwp_plan_create')
+        import os
+        saved = os.environ.get('DLWP_MATH')
+        if getattr(self, '_force_ffma', False):
+            os.environ['DLWP_MATH'] = 'ffma'
+        try:
+            nat.check(self.lib.dlwp_plan_create(ctypes.byref(net), ctypes.byref(self.plan)), 'dlwp_plan_create')
+        finally:
+            if getattr(self, '_force_ffma', False):
+                if saved is None:
+                    os.environ.pop('DLWP_MATH', None)
+                else:
+                    os.environ['DLWP_MATH'] = saved
         self.max_batch = int(max_batch)
         self._pushed = {}
         self.sync_weights()
@@ -382,8 +395,34 @@ class CompiledNet(object):
                                                 self._stream()), 'dlwp_plan_profile_op')
         return float(ms.value)
 
+    def _range_fallback(self):
+        """
+        The tensor-core path stores activations as fp16 hi/lo pairs: fine for the standardised fields DLWP feeds its nets,
+        but |x| > 65504 overflows.  The kernels raise a device flag when that happens; the host-level entry points then
+        rebuild the plan on the fp32 FFMA kernels and redo the call (True = caller must rerun).
+        """
+        if not self.uses_tensor_cores():
+            return False
+        if not (int(self.lib.dlwp_debug_flags()) & self.FLAG_TC_RANGE):
+            return False
+        import warnings
+        warnings.warn('dlwp_b200: activations exceed the fp16-split range of the tensor-core path; '
+                      'falling back to the fp32 FFMA kernels for this model')
+        self._force_ffma = True
+        mb = self.max_batch
+        self.close()
+        self._create(mb)
+        return True
+
     def predict(self, x):
         """numpy (N, C, H, W) -> list of numpy outputs (logical shapes), processed in chunks of max_batch."""
+        self.lib.dlwp_debug_flags()          # clear stale device flags
+        out = self._predict(x)
+        if self._range_fallback():
+            out = self._predict(x)
+        return out
+
+    def _predict(self, x):
         torch = self.torch
         x = np.ascontiguousarray(x, dtype=np.float32)
         n = x.shape[0]
@@ -415,6 +454,13 @@ class CompiledNet(object):
         return series
 
     def rollout_host(self, x0, iterations, d2h_group=0, pinned=True):
+        self.lib.dlwp_debug_flags()          # clear stale device flags
+        out = self._rollout_host(x0, iterations, d2h_group, pinned)
+        if self._range_fallback():
+            out = self._rollout_host(x0, iterations, d2h_group, pinned)
+        return out
+
+    def _rollout_host(self, x0, iterations, d2h_group=0, pinned=True):
         """
         numpy in -> numpy out through dlwp_rollout_host: H2D of x0, rollout, D2H of the series pipelined behind the
         compute.  The result lives in pinned host memory from torch's caching host allocator (a fresh array per call).
@@ -434,6 +480,6 @@ class CompiledNet(object):
             return series
         series = np.empty(shape, np.float32)
         for s in range(0, n, self.max_batch):
-            part = self.rollout_host(x0[s:s + self.max_batch], iterations, d2h_group, pinned)
+            part = self._rollout_host(x0[s:s + self.max_batch], iterations, d2h_group, pinned)
             series[:, s:s + self.max_batch] = part
         return series

@@ -124,3 +124,42 @@ def test_unrolled_two_step_model_on_tensor_cores(env):
     assert got.shape == ref.shape
     assert rel_err(got, ref) < 2e-5
     eng.close()
+
+
+def test_out_of_range_inputs_fall_back_to_fp32_kernels(env):
+    """|x| > 65504 cannot be split into fp16 hi/lo: the kernels flag it and the engine reruns on the FFMA path."""
+    nat, torch = env
+    import warnings
+    from dlwp_b200.engine import CompiledNet
+    from oracle import layers as OL
+    from tests.helpers import build_product_sequential, oracle_sequential_like
+    layers = OL.net_a_layers((6, 20, 36))
+    dlwp = build_product_sequential(layers)
+    net = oracle_sequential_like(dlwp, layers, seed=2, bias_scale=0.0)
+    x0 = np.random.RandomState(1).standard_normal((2, 6, 20, 36)).astype(np.float32)
+    x0[0, 0, 3, 5] = 3.0e5
+    eng = CompiledNet(dlwp.model, 2)
+    assert eng.uses_tensor_cores()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        y = eng.predict(x0)[0]
+    assert any('fp16-split range' in str(m.message) for m in w)
+    assert not eng.uses_tensor_cores()
+    assert rel_err(y, net.forward(x0.astype(np.float64))) < 2e-5
+    eng.close()
+
+
+def test_latitude_band_windows_on_tensor_cores(env):
+    """Row-windowed tensor-core plans (one per band) reproduce the single-domain tensor-core rollout bit for bit."""
+    nat, torch = env
+    from oracle import layers as OL
+    from tests.helpers import build_product_sequential, oracle_sequential_like
+    from tests.test_latband_gpu import _run_bands
+    layers = OL.net_a_layers()
+    dlwp = build_product_sequential(layers)
+    oracle_sequential_like(dlwp, layers, seed=1, bias_scale=0.05)
+    x0 = np.random.RandomState(0).standard_normal((2, 6, 91, 180)).astype(np.float32)
+    assert dlwp.model.engine(2).uses_tensor_cores()
+    ref = dlwp.predict_timeseries(x0, 4)
+    got, _ = _run_bands(dlwp.model, 4, x0, 4)
+    np.testing.assert_array_equal(got, ref)
