@@ -271,10 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             tc_fence_after();
             // ---- pass 1: publish the taps the previous quadrant will need --------------------------------------------
             int li = 0;
+            if (KW > 1)
             for (int item = set; item < nitems; item += TC_SETS, ++li) {
                 const int t = item / p.CBLK, cb = item - t * p.CBLK;
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + t * p.NCOLS + cb * KW * p.CSTRIDE;
-                float d[KW - 1][8];
+                float d[KW > 1 ? KW - 1 : 1][8];
 #pragma unroll
                 for (int j = 1; j < KW; ++j) tmem_ld8(taddr + j * p.CSTRIDE, d[j - 1]);
                 tmem_ld_wait();
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                     }
                 }
             }
-            named_bar_sync(1 + set, 128);
+            if (KW > 1) named_bar_sync(1 + set, 128);
             // ---- pass 2: shifted sums, bias, activation, stores ---------------------------------------------------------
             li = 0;
             for (int item = set; item < nitems; item += TC_SETS, ++li) {
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
-            named_bar_sync(1 + set, 128);  // the mailbox may be rewritten (next tile's pass 1) only after every reader is done
+            if (KW > 1) named_bar_sync(1 + set, 128);  // the mailbox may be rewritten (next tile) only after every reader is done
         }
     }
 
@@ -436,24 +437,30 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->planes = 2 * L->C8;
     L->CBLK = cdiv(d.Cout, 8);
     L->CSTRIDE = d.Cout < 8 ? d.Cout : 8;  // a single partial block packs its taps tightly (5 taps x 6 filters -> 32 cols)
-    L->NCOLS = cdiv(L->CBLK * d.kw * L->CSTRIDE + (8 - L->CSTRIDE), 16) * 16;  // x8 loads of the last tap stay inside
+    // Few input channels (K small): fold the horizontal taps into K as well (K = (i, j, c), N = filters only).  The A view
+    // of tap (i, j) is just +(i*dil*Wp + j*dil)*16 bytes, the epilogue needs no shifted sum, and N shrinks by kw.
+    L->taps_in_k = (L->C8 * d.kh * d.kw <= 12) ? 1 : 0;
+    const char* env_m = getenv("DLWP_TC_TAPS_IN_K");
+    if (env_m) L->taps_in_k = atoi(env_m) ? 1 : 0;
+    L->kw_eff = L->taps_in_k ? 1 : d.kw;
+    L->NCOLS = cdiv(L->CBLK * L->kw_eff * L->CSTRIDE + (8 - L->CSTRIDE), 16) * 16;  // x8 loads of the last tap stay inside
     if (L->NCOLS > 256) return -1;
-    L->S = 128 - halo_w;
+    L->S = L->taps_in_k ? 128 : 128 - halo_w;
     // units = (chunk, tap) in order; groups of chunks so that a group has an even number of units when possible
     const int smem_budget = 224 * 1024;
     const size_t bias_bars = (size_t)cdiv(d.Cout, 8) * 32 + 512;
     int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0;
     const char* env_r = getenv("DLWP_TC_ROUT");
     // big-K layers (>= 2 channel groups per tile) run best with small tiles: more tiles to balance, shorter TMA latency
-    const int r_max = env_r ? atoi(env_r) : (cdiv(L->C8, std::min(L->C8, 4)) >= 1 && L->C8 > 2 ? 2 : 8);
+    const int r_max = env_r ? atoi(env_r) : (L->C8 > 2 ? 4 : 8);
     for (int r_out = r_max; r_out >= 1; --r_out) {
         const int rin = r_out + halo_h;
         const int mt = cdiv(r_out * L->Wp, L->S);
         if (mt * L->NCOLS > 256) continue;  // two accumulator sets in 512 TMEM columns
-        const size_t fixed = (size_t)TC_SETS * cdiv(mt * L->CBLK, TC_SETS) * 4 * halo_w * (d.kw - 1) * 8 * 4 + bias_bars;
+        const size_t fixed = (size_t)TC_SETS * cdiv(mt * L->CBLK, TC_SETS) * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 + bias_bars;
         for (int cpg = std::min(L->C8, 4); cpg >= 1; --cpg) {
             const int G = cdiv(L->C8, cpg);
-            const int units = cpg * d.kh;
+            const int units = cpg * d.kh * (L->taps_in_k ? d.kw : 1);
             const int KS = cdiv(units, 2);
             if (G * KS > TC_MAX_KSTEPS) continue;
             const size_t stage = (size_t)2 * cpg * rin * L->Wp * 16;
@@ -473,14 +480,14 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->MT = best_mt;
     L->cpg = best_cpg;
     L->G = cdiv(L->C8, best_cpg);
-    L->KS = cdiv(best_cpg * d.kh, 2);
+    L->KS = cdiv(best_cpg * d.kh * (L->taps_in_k ? d.kw : 1), 2);
     L->NS = best_ns;
     L->stage_bytes = (uint32_t)(2 * best_cpg * L->Rin * L->Wp * 16);
     L->stage_stride = (L->stage_bytes + 127) / 128 * 128;
     L->plane_bytes = (uint32_t)(L->Rin * L->Wp * 16);
     L->b_bytes = (uint32_t)(L->G * L->KS * 2 * L->NCOLS * 16);
     L->smem = (size_t)L->NS * L->stage_stride + 2 * (size_t)L->b_bytes +
-              (size_t)TC_SETS * cdiv(L->MT * L->CBLK, TC_SETS) * 4 * halo_w * (d.kw - 1) * 8 * 4 + bias_bars + 1024;
+              (size_t)TC_SETS * cdiv(L->MT * L->CBLK, TC_SETS) * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 + bias_bars + 1024;
     return 0;
 }
 
@@ -492,10 +499,15 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     const size_t per_img = (size_t)L.b_bytes / 2;
     img->assign(2 * per_img, __float2half(0.f));
     for (int g = 0; g < L.G; ++g) {
-        struct U { int chunk_in_group, chunk, i; bool zero; };
+        struct U { int chunk_in_group, chunk, i, j; bool zero; };  // j = -1: all horizontal taps live in N
         std::vector<U> units;
         for (int cg = 0; cg < L.cpg; ++cg)
-            for (int i = 0; i < d.kh; ++i) units.push_back({cg, g * L.cpg + cg, i, false});
+            for (int i = 0; i < d.kh; ++i) {
+                if (L.taps_in_k)
+                    for (int j = 0; j < d.kw; ++j) units.push_back({cg, g * L.cpg + cg, i, j, false});
+                else
+                    units.push_back({cg, g * L.cpg + cg, i, -1, false});
+            }
         if (units.size() & 1) {  // [.., u(n-2), u(n-1)] -> [.., u(n-2), ZERO(view of u(n-2)), u(n-1)]  (needs >= 2 units)
             U last = units.back();
             units.pop_back();
@@ -508,7 +520,8 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
             const U& u0 = units[2 * ks];
             const U& u1 = units[2 * ks + 1];
             auto aoff = [&](const U& u) {
-                return (long long)(2 * u.chunk_in_group) * L.plane_bytes + (long long)u.i * d.dil_h * L.Wp * 16;
+                return (long long)(2 * u.chunk_in_group) * L.plane_bytes + (long long)u.i * d.dil_h * L.Wp * 16 +
+                       (long long)(u.j > 0 ? u.j : 0) * d.dil_w * 16;
             };
             const long long lbo = aoff(u1) - aoff(u0);
             if (lbo < 0 || (lbo >> 4) > 0x3FFF) return -1;
@@ -519,9 +532,10 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
                 if (u.zero) continue;
                 const size_t ubase = ((size_t)(g * L.KS + ks) * 2 + half) * L.NCOLS * 8;
                 for (int cb = 0; cb < L.CBLK; ++cb)
-                    for (int j = 0; j < d.kw; ++j)
+                    for (int j = (u.j >= 0 ? u.j : 0); j < (u.j >= 0 ? u.j + 1 : d.kw); ++j)
                         for (int ci = 0; ci < 8; ++ci) {
-                            const int co = cb * 8 + ci, ncol = (cb * d.kw + j) * L.CSTRIDE + ci;
+                            const int co = cb * 8 + ci;
+                            const int ncol = (cb * L.kw_eff + (u.j >= 0 ? 0 : j)) * L.CSTRIDE + ci;
                             if (ci >= L.CSTRIDE) continue;
                             if (co >= d.Cout) continue;
                             for (int e = 0; e < 8; ++e) {
@@ -550,6 +564,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
         cudaGetDevice(&dev);
         cudaGetDeviceProperties(&prop, dev);
         g_tc_sms = prop.multiProcessorCount;
+        cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     });
@@ -557,8 +572,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     memset(&p, 0, sizeof(p));
     p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;
     p.R_out = L.R_out; p.Rin = L.Rin; p.MT = L.MT; p.S = L.S;
-    p.KW = d.kw; p.D = d.dil_w; p.pad_t = d.pad_t;
-    p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (d.kw - 1) * d.dil_w;
+    p.KW = L.kw_eff; p.D = d.dil_w; p.pad_t = d.pad_t;
+    p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
     p.G = L.G; p.KS = L.KS; p.NS = L.NS; p.planes_per_group = 2 * L.cpg;
     const bool all_rows = d.row_begin == 0 && d.row_end == 0;
     p.row0 = all_rows ? 0 : d.row_begin;
@@ -574,7 +589,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.xp = xp;
     p.planes_in = L.planes;
     const int grid = std::min(p.total_tiles, g_tc_sms);
-    if (d.kw == 3) conv_tc_kernel<3><<<grid, TC_THREADS, L.smem, stream>>>(p);
+    if (L.kw_eff == 1) conv_tc_kernel<1><<<grid, TC_THREADS, L.smem, stream>>>(p);
+    else if (d.kw == 3) conv_tc_kernel<3><<<grid, TC_THREADS, L.smem, stream>>>(p);
     else conv_tc_kernel<5><<<grid, TC_THREADS, L.smem, stream>>>(p);
     return after_launch("conv_tc_kernel");
 }

@@ -20,7 +20,8 @@ struct TcLayer {
     int wpad, Wp;          // periodic halo columns per side of the INPUT image, padded width
     int C8, planes;        // 8-channel chunks of the input, planes = 2 * C8 (hi, lo)
     int CBLK, CSTRIDE, NCOLS;  // 8-filter blocks, TMEM columns per horizontal tap, MMA N
-    int S;                 // M-tile stride in pixels (128 - (kw-1)*dil)
+    int S;                 // M-tile stride in pixels (128 - (kw-1)*dil, or 128 with taps_in_k)
+    int taps_in_k, kw_eff; // horizontal taps folded into K (small Cin) -> the epilogue sees a 1-tap layer
     int R_out, Rin, MT;    // rows per tile, staged rows, M tiles per tile
     int cpg, G, KS, NS;    // chunks per group, groups per tile, K=16 steps per group, smem stages
     uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;
