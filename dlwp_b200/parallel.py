@@ -226,14 +226,41 @@ class LatBandEngine(object):
                                      lambda src, outs: self.net.forward_into(src, outs), dist=dist)
         self.rank, self.world, self.H = rank, world, H
         self.n_out = self.net.n_outputs
+        self.graphs = {}
+        self.graph_broken = False
 
-    def rollout_device(self, x0, iterations, out=None):
-        """x0: CUDA (N, C, H, W), identical on every rank (or at least valid on band + halo rows).  Returns the full-shape
-        series tensor of this rank; only rows `band` are meaningful."""
+    def rollout_device(self, x0, iterations, out=None, use_graph=True):
+        """
+        x0: CUDA (N, C, H, W), identical on every rank (or at least valid on band + halo rows).  Returns the full-shape
+        series tensor of this rank; only rows `band` are meaningful.  With `use_graph` the whole loop -- band kernels AND
+        the NCCL SendRecv groups -- is captured once into a CUDA graph per (iterations, x0, series) and replayed: the
+        per-iteration host work (a dozen launches and P2P calls) would otherwise cost more than the band's compute.
+        """
         import torch
         shape = (iterations * self.n_out,) + tuple(x0.shape)
         series = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x0.device)
-        return self.driver.rollout(x0, series, iterations, self.n_out)
+        if not use_graph or self.graph_broken:
+            return self.driver.rollout(x0, series, iterations, self.n_out)
+        key = (iterations, x0.data_ptr(), series.data_ptr())
+        g = self.graphs.get(key)
+        if g is None:
+            self.driver.rollout(x0, series, min(iterations, 2), self.n_out)   # warm NCCL channels, allocators, attributes
+            torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.driver.rollout(x0, series, iterations, self.n_out)
+            except Exception as exc:  # pragma: no cover  (capture support depends on the NCCL build)
+                import warnings
+                warnings.warn('dlwp_b200: CUDA-graph capture of the latitude-band rollout failed (%s); running eagerly' % exc)
+                self.graph_broken = True
+                torch.cuda.synchronize()
+                return self.driver.rollout(x0, series, iterations, self.n_out)
+            if len(self.graphs) >= 4:
+                self.graphs.pop(next(iter(self.graphs)))
+            self.graphs[key] = g
+        g.replay()
+        return series
 
     def band_to_host(self, series):
         """This rank's band of the series as a pinned numpy array (steps, N, C, band_rows, W)."""
