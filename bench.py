@@ -414,8 +414,7 @@ def run_latband(args, rank, world, local_rank):
                        'state': list(STATE), 'parallelism': 'latband%d (91 latitude rows split over %d GPUs, halo 4 rows)'
                        % (world, world), 'bands': [list(p.band) for p in eng.planners],
                        'halo': {'rows_per_side': 4, 'bytes_per_neighbour_per_direction_per_step': per_dir,
-                                'collective': 'one grouped NCCL SendRecv per step, captured with the band kernels in one CUDA graph',
-                                'graph': not eng.graph_broken,
+                                'collective': 'one grouped NCCL SendRecv per step (ncclSend/ncclRecv inside the C library), captured with the band kernels in one CUDA graph',
                                 'link_time_us_at_770GBs': per_dir / 770e9 * 1e6,
                                 'fraction_of_step_time': per_dir / 770e9 / (ms / K * 1e-3)},
                        'l2': 'per-step working set >> L2 at this batch; no flush', 'e2e_steps': Ke},

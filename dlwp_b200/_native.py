@@ -40,6 +40,10 @@ class OpDesc(ctypes.Structure):
                                    'act', 'pre_op', 'rowwise', 'impl', 'row_begin', 'row_end')]
 
 
+class BandInfo(ctypes.Structure):
+    _fields_ = [(n, i32) for n in ('rank', 'world', 'band_lo', 'band_hi', 'recv_top', 'recv_bot', 'send_up', 'send_down')]
+
+
 class NetDesc(ctypes.Structure):
     _fields_ = [('n_buffers', i32), ('n_ops', i32), ('n_weights', i32), ('max_batch', i32),
                 ('buffers', ctypes.POINTER(BufferDesc)), ('ops', ctypes.POINTER(OpDesc))]
@@ -61,6 +65,11 @@ SYMBOLS = {
                                          ctypes.c_void_p]),
     'dlwp_rollout': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32, ctypes.c_void_p]),
     'dlwp_rollout_host': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32]),
+    'dlwp_comm_unique_id': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p]),
+    'dlwp_comm_create': (ctypes.c_int, [ctypes.c_char_p, i32, i32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    'dlwp_comm_destroy': (None, [ctypes.c_void_p]),
+    'dlwp_rollout_latband': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i32, fptr, fptr, i32,
+                                            ctypes.POINTER(BandInfo), i32, ctypes.c_void_p]),
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.c_void_p]),
     'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),

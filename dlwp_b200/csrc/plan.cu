@@ -9,6 +9,7 @@
 #include "internal.h"
 #include "conv_tc.h"
 
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -83,6 +84,10 @@ struct DlwpPlan {
     std::vector<int> tc_pdst;      // buffer whose P image op i writes (-1: none)
     int tc_feedback_op = -1;       // op that also serves as the packer of the next iteration's input
     int tc_in_row0 = 0, tc_in_row1 = 0;  // rows of the input the (row-windowed) convs read: only those are packed
+    // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
+    float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
+    long long halo_cap = 0;
+    std::map<GraphKey, cudaGraphExec_t> band_graphs;
 };
 
 namespace dlwp {
@@ -423,6 +428,9 @@ extern "C" int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** out) {
 extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
     if (!pl) return;
     for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : pl->band_graphs) cudaGraphExecDestroy(kv.second);
+    for (float* h : pl->halo_stage)
+        if (h) cudaFree(h);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
     for (Buffer& b : pl->buffers)
@@ -603,3 +611,165 @@ extern "C" int dlwp_plan_profile_op(DlwpPlan* pl, int32_t N, int32_t op_index, i
 }
 
 extern "C" int dlwp_plan_uses_tensor_cores(DlwpPlan* pl) { return pl && pl->tc ? 1 : 0; }
+
+// =================================================================================================================
+// Latitude-band rollout with the halo exchange inside the library (NCCL resolved at run time, no link dependency)
+// =================================================================================================================
+namespace dlwp {
+typedef struct { char internal[128]; } NcclId;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(const char* path) {
+    if (g_nccl.handle) return 0;
+    void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    DLWP_REQUIRE(h != nullptr, DLWP_EARCH, "cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+    g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    DLWP_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Send &&
+                     g_nccl.Recv,
+                 DLWP_EARCH, "NCCL library lacks the point-to-point API");
+    g_nccl.handle = h;
+    return 0;
+}
+
+#define DLWP_NCCL_TRY(expr)                                                                            \
+    do {                                                                                               \
+        int _r = (expr);                                                                               \
+        if (_r != 0) {                                                                                 \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+            return 1000 + _r;                                                                          \
+        }                                                                                              \
+    } while (0)
+
+// one grouped SendRecv of the halo rows of `slot` (N, C, H, W): my top/bottom band rows out, the neighbours' rows in
+static int halo_exchange(DlwpPlan* pl, void* comm, int N, float* slot, const DlwpBandInfo& b, cudaStream_t stream) {
+    const Buffer& in = pl->buffers[pl->input_buf];
+    const int C = in.d.C, H = in.d.H, W = in.d.W;
+    const long long sn = (long long)C * H * W, sc = (long long)H * W;
+    auto pack = [&](int row0, int rows, float* stage) {
+        return dlwp_copy4d(slot + (long long)row0 * W, stage, N, C, rows, W, sn, sc, W, (long long)C * rows * W,
+                           (long long)rows * W, W, stream);
+    };
+    auto unpack = [&](int row0, int rows, const float* stage) {
+        return dlwp_copy4d(stage, slot + (long long)row0 * W, N, C, rows, W, (long long)C * rows * W,
+                           (long long)rows * W, W, sn, sc, W, stream);
+    };
+    int rc = 0;
+    const bool up = b.rank > 0, down = b.rank + 1 < b.world;
+    if (up && b.send_up && (rc = pack(b.band_lo, b.send_up, pl->halo_stage[0]))) return rc;
+    if (down && b.send_down && (rc = pack(b.band_hi - b.send_down, b.send_down, pl->halo_stage[1]))) return rc;
+    const size_t per_row = (size_t)N * C * W;
+    DLWP_NCCL_TRY(g_nccl.GroupStart());
+    if (up && b.send_up) DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[0], per_row * b.send_up, 7, b.rank - 1, comm, stream));
+    if (up && b.recv_top) DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[2], per_row * b.recv_top, 7, b.rank - 1, comm, stream));
+    if (down && b.send_down)
+        DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[1], per_row * b.send_down, 7, b.rank + 1, comm, stream));
+    if (down && b.recv_bot)
+        DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[3], per_row * b.recv_bot, 7, b.rank + 1, comm, stream));
+    DLWP_NCCL_TRY(g_nccl.GroupEnd());
+    if (up && b.recv_top && (rc = unpack(b.band_lo - b.recv_top, b.recv_top, pl->halo_stage[2]))) return rc;
+    if (down && b.recv_bot && (rc = unpack(b.band_hi, b.recv_bot, pl->halo_stage[3]))) return rc;
+    return 0;
+}
+
+static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float* series, int iterations,
+                         const DlwpBandInfo& b, cudaStream_t stream) {
+    const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
+    const int n_out = (int)pl->outputs.size();
+    for (int t = 0; t < iterations; ++t) {
+        int rc = rollout_range(pl, N, x0, series, t, t + 1, stream);
+        if (rc) return rc;
+        if (t + 1 < iterations && b.world > 1) {
+            rc = halo_exchange(pl, comm, N, series + ((long long)t * n_out + n_out - 1) * slot, b, stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+}  // namespace dlwp
+
+extern "C" int dlwp_comm_unique_id(const char* libnccl_path, void* id128) {
+    DLWP_REQUIRE(id128 != nullptr, DLWP_EINVAL, "null argument");
+    int rc = nccl_load(libnccl_path);
+    if (rc) return rc;
+    DLWP_NCCL_TRY(g_nccl.GetUniqueId(reinterpret_cast<NcclId*>(id128)));
+    return 0;
+}
+
+extern "C" int dlwp_comm_create(const char* libnccl_path, int32_t rank, int32_t world, const void* id128, void** comm) {
+    DLWP_REQUIRE(id128 && comm && world > 0 && rank >= 0 && rank < world, DLWP_EINVAL, "bad argument");
+    int rc = nccl_load(libnccl_path);
+    if (rc) return rc;
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    DLWP_NCCL_TRY(g_nccl.CommInitRank(comm, world, id, rank));
+    return 0;
+}
+
+extern "C" void dlwp_comm_destroy(void* comm) {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+}
+
+extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const float* x0, float* series,
+                                    int32_t iterations, const DlwpBandInfo* band, int32_t use_graph,
+                                    dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && x0 && series && band, DLWP_EINVAL, "null argument");
+    DLWP_REQUIRE(band->world == 1 || comm != nullptr, DLWP_EINVAL, "a communicator is required for world > 1");
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch && iterations > 0, DLWP_ESHAPE, "bad batch / iterations");
+    int rc = check_rollout_shapes(pl);
+    if (rc) return rc;
+    const Buffer& in = pl->buffers[pl->input_buf];
+    const int max_rows = std::max(std::max(band->send_up, band->send_down), std::max(band->recv_top, band->recv_bot));
+    const long long need = (long long)pl->max_batch * in.d.C * std::max(1, max_rows) * in.d.W;
+    if (pl->halo_cap < need) {
+        for (float*& h : pl->halo_stage) {
+            if (h) cudaFree(h);
+            h = nullptr;
+            DLWP_CUDA_TRY(cudaMalloc(&h, sizeof(float) * need));
+        }
+        pl->halo_cap = need;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!use_graph) return latband_range(pl, comm, N, x0, series, iterations, *band, stream);
+    GraphKey key{N, iterations, x0, series};
+    auto it = pl->band_graphs.find(key);
+    if (it == pl->band_graphs.end()) {
+        if (!pl->s_compute) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        DLWP_CUDA_TRY(cudaStreamBeginCapture(pl->s_compute, cudaStreamCaptureModeThreadLocal));
+        const long long before = g_launches.load();
+        rc = latband_range(pl, comm, N, x0, series, iterations, *band, pl->s_compute);
+        cudaError_t e = cudaStreamEndCapture(pl->s_compute, &graph);
+        g_launches.store(before);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        DLWP_CUDA_TRY(e);
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        DLWP_CUDA_TRY(e);
+        it = pl->band_graphs.emplace(key, exec).first;
+    }
+    DLWP_CUDA_TRY(cudaGraphLaunch(it->second, stream));
+    g_launches.fetch_add((long long)pl->ops.size() * iterations);
+    return 0;
+}

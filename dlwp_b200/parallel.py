@@ -208,10 +208,29 @@ def halo_summary(planner, N, C, W):
             'recv_bytes_per_iteration': int((top + bottom) * per_row)}
 
 
-class LatBandEngine(object):
-    """GPU implementation: a row-windowed DlwpPlan per rank + the exchange driver above (NCCL via torch.distributed)."""
+def _nccl_library():
+    """torch's bundled NCCL (the same shared object torch.distributed uses), loaded by the C library with dlopen."""
+    import os
+    try:
+        import nvidia.nccl
+        cand = os.path.join(list(nvidia.nccl.__path__)[0], 'lib', 'libnccl.so.2')
+        if os.path.exists(cand):
+            return cand
+    except ImportError:
+        pass
+    return 'libnccl.so.2'
 
-    def __init__(self, model, batch, rank, world, dist=None, impl=None):
+
+class LatBandEngine(object):
+    """
+    GPU implementation: a row-windowed DlwpPlan per rank; the rollout loop INCLUDING the halo exchange runs inside the C
+    library (dlwp_rollout_latband: pack rows -> ncclGroupStart / ncclSend+ncclRecv up and down / ncclGroupEnd -> unpack),
+    captured as one CUDA graph.  torch.distributed is only used once, to broadcast the NCCL unique id.
+    `native=False` keeps the torch.distributed driver above (what the gloo CPU tests exercise).
+    """
+
+    def __init__(self, model, batch, rank, world, dist=None, impl=None, native=True):
+        import ctypes
         from .engine import CompiledNet, Lowering
         low = Lowering(model)
         H = low.buffers[[i for i, b in enumerate(low.buffers) if b['kind'] == nat.BUF_INPUT][0]]['H']
@@ -226,40 +245,45 @@ class LatBandEngine(object):
                                      lambda src, outs: self.net.forward_into(src, outs), dist=dist)
         self.rank, self.world, self.H = rank, world, H
         self.n_out = self.net.n_outputs
-        self.graphs = {}
-        self.graph_broken = False
+        self.native = bool(native)
+        self.comm = ctypes.c_void_p()
+        up = self.planners[rank - 1] if rank > 0 else None
+        down = self.planners[rank + 1] if rank + 1 < world else None
+        self.info = nat.BandInfo(rank, world, self.me.band[0], self.me.band[1], self.me.halo[0], self.me.halo[1],
+                                 up.halo[1] if up else 0, down.halo[0] if down else 0)
+        if self.native and world > 1:
+            import torch
+            lib = nat.lib()
+            path = _nccl_library().encode()
+            ident = (ctypes.c_char * 128)()
+            if rank == 0:
+                nat.check(lib.dlwp_comm_unique_id(path, ident), 'dlwp_comm_unique_id')
+            t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device='cuda')
+            dist.broadcast(t, 0)
+            ident = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+            nat.check(lib.dlwp_comm_create(path, rank, world, ident, ctypes.byref(self.comm)), 'dlwp_comm_create')
+
+    def close(self):
+        if self.comm:
+            nat.lib().dlwp_comm_destroy(self.comm)
+            self.comm = None
+        self.net.close()
 
     def rollout_device(self, x0, iterations, out=None, use_graph=True):
         """
         x0: CUDA (N, C, H, W), identical on every rank (or at least valid on band + halo rows).  Returns the full-shape
-        series tensor of this rank; only rows `band` are meaningful.  With `use_graph` the whole loop -- band kernels AND
-        the NCCL SendRecv groups -- is captured once into a CUDA graph per (iterations, x0, series) and replayed: the
-        per-iteration host work (a dozen launches and P2P calls) would otherwise cost more than the band's compute.
+        series tensor of this rank; only rows `band` are meaningful.
         """
+        import ctypes
         import torch
         shape = (iterations * self.n_out,) + tuple(x0.shape)
         series = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x0.device)
-        if not use_graph or self.graph_broken:
+        if not self.native:
             return self.driver.rollout(x0, series, iterations, self.n_out)
-        key = (iterations, x0.data_ptr(), series.data_ptr())
-        g = self.graphs.get(key)
-        if g is None:
-            self.driver.rollout(x0, series, min(iterations, 2), self.n_out)   # warm NCCL channels, allocators, attributes
-            torch.cuda.synchronize()
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.driver.rollout(x0, series, iterations, self.n_out)
-            except Exception as exc:  # pragma: no cover  (capture support depends on the NCCL build)
-                import warnings
-                warnings.warn('dlwp_b200: CUDA-graph capture of the latitude-band rollout failed (%s); running eagerly' % exc)
-                self.graph_broken = True
-                torch.cuda.synchronize()
-                return self.driver.rollout(x0, series, iterations, self.n_out)
-            if len(self.graphs) >= 4:
-                self.graphs.pop(next(iter(self.graphs)))
-            self.graphs[key] = g
-        g.replay()
+        self.net.sync_weights()
+        nat.check(nat.lib().dlwp_rollout_latband(self.net.plan, self.comm, x0.shape[0], x0.data_ptr(), series.data_ptr(),
+                                                 int(iterations), ctypes.byref(self.info), 1 if use_graph else 0,
+                                                 self.net._stream()), 'dlwp_rollout_latband')
         return series
 
     def band_to_host(self, series):

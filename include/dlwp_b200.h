@@ -173,6 +173,31 @@ int dlwp_rollout(DlwpPlan* plan, int32_t N, const float* x0, float* series, int3
 int dlwp_rollout_host(DlwpPlan* plan, int32_t N, const float* x0_host, float* series_host, int32_t iterations,
                       int32_t d2h_group);
 
+/* ---- latitude-band rollout: one process per GPU, halo rows exchanged with ONE grouped NCCL SendRecv per iteration ----- */
+
+/* This rank's share of the H latitude rows (dlwp_b200.parallel.BandPlanner computes it): it owns output rows
+ * [band_lo, band_hi); before an iteration it needs `recv_top` rows above and `recv_bot` rows below its band from its
+ * neighbours, and serves them `send_up` / `send_down` rows of its own band. The plan's ops must be row-windowed. */
+typedef struct DlwpBandInfo {
+    int32_t rank, world;
+    int32_t band_lo, band_hi;
+    int32_t recv_top, recv_bot, send_up, send_down;
+} DlwpBandInfo;
+
+/* NCCL is resolved at run time from `libnccl_path` (torch's bundled libnccl.so.2); the library has no link dependency on
+ * it. Rank 0 creates the 128-byte id and distributes it (e.g. torch.distributed.broadcast); every rank then creates the
+ * communicator. */
+int dlwp_comm_unique_id(const char* libnccl_path, void* id128);
+int dlwp_comm_create(const char* libnccl_path, int32_t rank, int32_t world, const void* id128, void** comm);
+void dlwp_comm_destroy(void* comm);
+
+/* dlwp_rollout for a latitude band: after every iteration but the last, the band rows of the last output that the
+ * neighbours need are packed, exchanged (ncclGroupStart; ncclSend/ncclRecv up and down; ncclGroupEnd) and unpacked into
+ * the halo rows of the same series slot, all on `stream`. use_graph captures kernels AND the NCCL group into one CUDA
+ * graph. series holds full (N,C,H,W) slots of which the band rows are valid. */
+int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0, float* series, int32_t iterations,
+                         const DlwpBandInfo* band, int32_t use_graph, dlwp_stream_t stream);
+
 /* Time one op of the plan alone: `iters` launches bracketed by CUDA events on `stream` (after 2 warm-up launches), using
  * whatever the plan's buffers hold from the last forward / rollout. Blocking. Used by bench.py for the roofline figure. */
 int dlwp_plan_profile_op(DlwpPlan* plan, int32_t N, int32_t op_index, int32_t iters, float* ms_per_launch,
