@@ -391,6 +391,20 @@ def run_latband(args, rank, world, local_rank):
     launches = nat.launch_count() - launches0
     value = B * K / (ms * 1e-3)
 
+    # self-check of the exchange (local, no extra collective): on a small batch this rank's band of a graph-replayed
+    # lat-band rollout must equal the same rows of the single-domain rollout computed on this GPU, bit for bit
+    vb, vk = 2, 5
+    veng = eng                                            # same plan and communicator, smaller batch
+    vx = xd[:vb].contiguous()
+    vs = torch.full((vk, vb) + STATE, float('nan'), device='cuda')
+    veng.rollout_device(vx, vk, out=vs)
+    vref = dlwp.model.engine(vb).rollout_device(vx, vk, use_graph=False)
+    torch.cuda.synchronize()
+    lo_, hi_ = veng.me.band
+    vflag = torch.tensor([1 if torch.equal(vs[:, :, :, lo_:hi_], vref[:, :, :, lo_:hi_]) else 0], device='cuda')
+    dist.all_reduce(vflag, op=dist.ReduceOp.MIN)
+    verified = bool(int(vflag.item()))
+
     # end to end: H2D of x0, rollout, D2H of this rank's band of every state (host concatenation along H is free)
     Ke = min(K, args.e2e_steps)
     x0_pinned = torch.from_numpy(x0).pin_memory()
@@ -413,6 +427,7 @@ def run_latband(args, rank, world, local_rank):
             'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'global_batch': B,
                        'state': list(STATE), 'parallelism': 'latband%d (91 latitude rows split over %d GPUs, halo 4 rows)'
                        % (world, world), 'bands': [list(p.band) for p in eng.planners],
+                       'bands_equal_single_domain_bitwise': verified,
                        'halo': {'rows_per_side': 4, 'bytes_per_neighbour_per_direction_per_step': per_dir,
                                 'collective': 'one grouped NCCL SendRecv per step (ncclSend/ncclRecv inside the C library), captured with the band kernels in one CUDA graph',
                                 'link_time_us_at_770GBs': per_dir / 770e9 * 1e6,

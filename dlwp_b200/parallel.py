@@ -263,10 +263,12 @@ class LatBandEngine(object):
             ident = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
             nat.check(lib.dlwp_comm_create(path, rank, world, ident, ctypes.byref(self.comm)), 'dlwp_comm_create')
 
-    def close(self):
-        if self.comm:
+    def close(self, destroy_comm=False):
+        """ncclCommDestroy is collective-like (it can block until every rank calls it); by default the communicator is
+        left to process teardown."""
+        if self.comm and destroy_comm:
             nat.lib().dlwp_comm_destroy(self.comm)
-            self.comm = None
+        self.comm = None
         self.net.close()
 
     def rollout_device(self, x0, iterations, out=None, use_graph=True):
