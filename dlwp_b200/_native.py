@@ -70,6 +70,14 @@ SYMBOLS = {
     'dlwp_comm_destroy': (None, [ctypes.c_void_p]),
     'dlwp_rollout_latband': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i32, fptr, fptr, i32,
                                             ctypes.POINTER(BandInfo), i32, ctypes.c_void_p]),
+    'dlwp_train_step': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(ctypes.c_float), i32, i32, ctypes.POINTER(ctypes.c_float),
+                                       ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
+    'dlwp_train_buffers': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64),
+                                          ctypes.POINTER(ctypes.c_void_p)]),
+    'dlwp_train_weight_offsets': (ctypes.c_int, [ctypes.c_void_p, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+    'dlwp_train_adam': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_void_p]),
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.c_void_p]),
     'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),

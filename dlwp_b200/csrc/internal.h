@@ -51,6 +51,21 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
 const char* conv2d_impl_name(const DlwpConvDesc& d);
 int check_device();
 
+// ---- training kernels (train.cu); stride arrays are {n, c, h} element strides -------------------------------------------
+int conv2d_bwd_input(const DlwpConvDesc& d, const float* dy, const float* w, float* dx, cudaStream_t stream);
+int conv2d_bwd_weight(const DlwpConvDesc& d, const float* x, const float* dy, float* dw, float* db, cudaStream_t stream);
+int act_bwd(const float* y, float* g, int act, int N, int C, int H, int W, const long long* ys, const long long* gs,
+            cudaStream_t stream);
+int maxpool_bwd(const float* x, const float* g, float* dx, int N, int C, int Hp, int Wp, const long long* xs,
+                const long long* gs, const long long* dxs, cudaStream_t stream);
+int upsample_bwd(const float* g, float* dx, int N, int C, int Hl, int Wl, const long long* gs, const long long* dxs,
+                 cudaStream_t stream);
+int add_bwd(const float* g, float* dx, int N, int C, int H, int W, const long long* gs, const long long* dxs,
+            cudaStream_t stream);
+int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream);
+int adam_step(float* w, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
+              cudaStream_t stream);
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                          const uint32_t box[4]);

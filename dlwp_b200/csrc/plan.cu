@@ -10,6 +10,7 @@
 #include "conv_tc.h"
 
 #include <dlfcn.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -88,6 +89,13 @@ struct DlwpPlan {
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     long long halo_cap = 0;
     std::map<GraphKey, cudaGraphExec_t> band_graphs;
+    // training state (lazily created by dlwp_train_step)
+    bool train_ready = false;
+    std::vector<float*> gbuf;        // gradient w.r.t. every buffer (max_batch samples)
+    std::vector<float*> out_store;   // plan-owned model outputs during training
+    float *flat_g = nullptr, *flat_m = nullptr, *flat_v = nullptr, *stats = nullptr;
+    long long flat_elems = 0, adam_t = 0;
+    std::vector<long long> gk_off, gb_off;
 };
 
 namespace dlwp {
@@ -431,6 +439,12 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
     for (auto& kv : pl->band_graphs) cudaGraphExecDestroy(kv.second);
     for (float* h : pl->halo_stage)
         if (h) cudaFree(h);
+    for (float* g : pl->gbuf)
+        if (g) cudaFree(g);
+    for (float* g : pl->out_store)
+        if (g) cudaFree(g);
+    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats})
+        if (g) cudaFree(g);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
     for (Buffer& b : pl->buffers)
@@ -771,5 +785,149 @@ extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const f
     }
     DLWP_CUDA_TRY(cudaGraphLaunch(it->second, stream));
     g_launches.fetch_add((long long)pl->ops.size() * iterations);
+    return 0;
+}
+
+// =================================================================================================================
+// Training: forward + sum_k w_k MSE_k + backward, gradient buffer for the data-parallel all-reduce, Adam
+// (keras.Model.fit_generator / train_on_batch as driven by DLWP/model/models.py:216-228, :394-402)
+// =================================================================================================================
+namespace dlwp {
+static int train_setup(DlwpPlan* pl) {
+    if (pl->train_ready) return 0;
+    DLWP_REQUIRE(!pl->tc, DLWP_ESTATE, "training needs the fp32 plan (create it with DLWP_MATH=ffma)");
+    for (const DlwpOpDesc& op : pl->ops) {
+        DLWP_REQUIRE(op.kind != DLWP_OP_PAD, DLWP_ESHAPE, "stand-alone padding layers are not differentiable here yet");
+        DLWP_REQUIRE(!(op.kind == DLWP_OP_CONV && (op.rowwise || op.pre_op)), DLWP_ESHAPE,
+                     "RowConnected2D / fused pre-ops are not differentiable here yet");
+        DLWP_REQUIRE(!op.row_begin && !op.row_end, DLWP_ESHAPE, "row-windowed plans cannot be trained");
+    }
+    pl->gbuf.assign(pl->buffers.size(), nullptr);
+    for (size_t i = 0; i < pl->buffers.size(); ++i)
+        DLWP_CUDA_TRY(cudaMalloc(&pl->gbuf[i], sizeof(float) * pl->buffers[i].sample_elems() * pl->max_batch));
+    pl->out_store.assign(pl->outputs.size(), nullptr);
+    for (size_t k = 0; k < pl->outputs.size(); ++k)
+        DLWP_CUDA_TRY(cudaMalloc(&pl->out_store[k],
+                                 sizeof(float) * pl->buffers[pl->outputs[k]].sample_elems() * pl->max_batch));
+    long long off = 0;
+    pl->gk_off.assign(pl->weights.size(), 0);
+    pl->gb_off.assign(pl->weights.size(), 0);
+    for (size_t w = 0; w < pl->weights.size(); ++w) {
+        pl->gk_off[w] = off; off += pl->weights[w].k_elems;
+        pl->gb_off[w] = off; off += pl->weights[w].b_elems;
+    }
+    pl->flat_elems = off;
+    DLWP_CUDA_TRY(cudaMalloc(&pl->flat_g, sizeof(float) * off));
+    DLWP_CUDA_TRY(cudaMalloc(&pl->flat_m, sizeof(float) * off));
+    DLWP_CUDA_TRY(cudaMalloc(&pl->flat_v, sizeof(float) * off));
+    DLWP_CUDA_TRY(cudaMemset(pl->flat_m, 0, sizeof(float) * off));
+    DLWP_CUDA_TRY(cudaMemset(pl->flat_v, 0, sizeof(float) * off));
+    DLWP_CUDA_TRY(cudaMalloc(&pl->stats, sizeof(float) * 2 * pl->outputs.size()));
+    pl->train_ready = true;
+    return 0;
+}
+}  // namespace dlwp
+
+extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const float* const* targets,
+                               const float* loss_weights, int32_t backward, int32_t input_grad, float* losses,
+                               float* maes, dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && x && targets && losses, DLWP_EINVAL, "null argument");
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch, DLWP_ESHAPE, "batch %d outside (0, %d]", N, pl->max_batch);
+    int rc = train_setup(pl);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n_out = (int)pl->outputs.size();
+    // ---- forward (every intermediate stays in its INTERNAL buffer) ----
+    pl->buffers[pl->input_buf].ptr = const_cast<float*>(x);
+    for (int k = 0; k < n_out; ++k) pl->buffers[pl->outputs[k]].ptr = pl->out_store[k];
+    rc = run_ops(pl, N, stream);
+    if (rc) return rc;
+    // ---- loss and its gradient ----
+    DLWP_CUDA_TRY(cudaMemsetAsync(pl->stats, 0, sizeof(float) * 2 * n_out, stream));
+    if (backward) {
+        for (size_t i = 0; i < pl->buffers.size(); ++i)
+            DLWP_CUDA_TRY(cudaMemsetAsync(pl->gbuf[i], 0, sizeof(float) * pl->buffers[i].sample_elems() * N, stream));
+        DLWP_CUDA_TRY(cudaMemsetAsync(pl->flat_g, 0, sizeof(float) * pl->flat_elems, stream));
+    }
+    for (int k = 0; k < n_out; ++k) {
+        DLWP_REQUIRE(targets[k] != nullptr, DLWP_EINVAL, "target %d is null", k);
+        const long long nk = (long long)N * pl->buffers[pl->outputs[k]].sample_elems();
+        const float lw = loss_weights ? loss_weights[k] : 1.f;
+        rc = mse_grad(pl->out_store[k], targets[k], backward ? pl->gbuf[pl->outputs[k]] : nullptr, nk, lw * 2.f / (float)nk,
+                      pl->stats + 2 * k, stream);
+        if (rc) return rc;
+    }
+    // ---- backward: ops in reverse order; gradients accumulate into channel windows of the per-buffer gradient ----
+    if (backward) {
+        for (int i = (int)pl->ops.size() - 1; i >= 0; --i) {
+            const DlwpOpDesc& op = pl->ops[i];
+            const Buffer& s = pl->buffers[op.src];
+            const Buffer& t = pl->buffers[op.dst];
+            const long long s_hw = (long long)s.d.H * s.d.W, t_hw = (long long)t.d.H * t.d.W;
+            const long long ss[3] = {s.sample_elems(), s_hw, s.d.W}, ts[3] = {t.sample_elems(), t_hw, t.d.W};
+            const float* xs = s.ptr + op.src_c0 * s_hw;
+            float* gs = pl->gbuf[op.src] + op.src_c0 * s_hw;
+            float* gt = pl->gbuf[op.dst] + op.dst_c0 * t_hw;
+            const float* yt = t.ptr + op.dst_c0 * t_hw;
+            switch (op.kind) {
+                case DLWP_OP_CONV: {
+                    Weight& w = pl->weights[op.weight_id];
+                    DlwpConvDesc d = conv_desc_of(pl, op, N);
+                    rc = act_bwd(yt, gt, op.act, N, op.Cout, t.d.H, t.d.W, ts, ts, stream);
+                    if (!rc) rc = conv2d_bwd_weight(d, xs, gt, pl->flat_g + pl->gk_off[op.weight_id],
+                                                    w.has_bias ? pl->flat_g + pl->gb_off[op.weight_id] : nullptr, stream);
+                    if (!rc && (op.src != pl->input_buf || input_grad)) rc = conv2d_bwd_input(d, gt, w.k, gs, stream);
+                    break;
+                }
+                case DLWP_OP_MAXPOOL: rc = maxpool_bwd(xs, gt, gs, N, op.src_c, t.d.H, t.d.W, ss, ts, ss, stream); break;
+                case DLWP_OP_UPSAMPLE: rc = upsample_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); break;
+                case DLWP_OP_COPY: rc = add_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); break;
+                default: DLWP_REQUIRE(false, DLWP_ESHAPE, "op %d has no backward", i);
+            }
+            if (rc) return rc;
+        }
+    }
+    std::vector<float> h(2 * n_out);
+    DLWP_CUDA_TRY(cudaMemcpyAsync(h.data(), pl->stats, sizeof(float) * 2 * n_out, cudaMemcpyDeviceToHost, stream));
+    DLWP_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int k = 0; k < n_out; ++k) {
+        const double nk = (double)N * pl->buffers[pl->outputs[k]].sample_elems();
+        losses[k] = (float)(h[2 * k] / nk);
+        if (maes) maes[k] = (float)(h[2 * k + 1] / nk);
+    }
+    return 0;
+}
+
+extern "C" int dlwp_train_buffers(DlwpPlan* pl, float** flat_grad, int64_t* elems, float** input_grad) {
+    DLWP_REQUIRE(pl && pl->train_ready, DLWP_ESTATE, "run dlwp_train_step first");
+    if (flat_grad) *flat_grad = pl->flat_g;
+    if (elems) *elems = pl->flat_elems;
+    if (input_grad) *input_grad = pl->gbuf[pl->input_buf];
+    return 0;
+}
+
+extern "C" int dlwp_train_weight_offsets(DlwpPlan* pl, int32_t weight_id, int64_t* kernel_off, int64_t* bias_off) {
+    DLWP_REQUIRE(pl && pl->train_ready && weight_id >= 0 && weight_id < (int)pl->weights.size(), DLWP_ESTATE, "bad state");
+    *kernel_off = pl->gk_off[weight_id];
+    *bias_off = pl->gb_off[weight_id];
+    return 0;
+}
+
+extern "C" int dlwp_train_adam(DlwpPlan* pl, float lr, float beta1, float beta2, float eps, dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && pl->train_ready, DLWP_ESTATE, "run dlwp_train_step first");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    pl->adam_t += 1;
+    const double t = (double)pl->adam_t;
+    const float lr_t = (float)(lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+    for (size_t w = 0; w < pl->weights.size(); ++w) {
+        Weight& W = pl->weights[w];
+        if (!W.k_elems) continue;
+        int rc = adam_step(W.k, pl->flat_g + pl->gk_off[w], pl->flat_m + pl->gk_off[w], pl->flat_v + pl->gk_off[w],
+                           W.k_elems, lr_t, beta1, beta2, eps, stream);
+        if (!rc && W.has_bias)
+            rc = adam_step(W.b, pl->flat_g + pl->gb_off[w], pl->flat_m + pl->gb_off[w], pl->flat_v + pl->gb_off[w], W.b_elems,
+                           lr_t, beta1, beta2, eps, stream);
+        if (rc) return rc;
+    }
     return 0;
 }

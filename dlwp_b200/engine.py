@@ -275,14 +275,16 @@ class CompiledNet(object):
 
     FLAG_TC_RANGE = 4   # dlwp_debug_flags bit: a value left the fp16 hi/lo split's range (|x| > 65504)
 
-    def __init__(self, model, batch, impl=None, row_windows=None):
-        """row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
+    def __init__(self, model, batch, impl=None, row_windows=None, force_ffma=False):
+        """force_ffma: build the plan on the fp32 kernels (training needs fp32 intermediates).
+        row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
         (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op."""
         self.torch = _torch()
         self.lib = nat.lib()
         self.model = model
         self.low = Lowering(model)
         self.row_windows = row_windows
+        self._force_ffma = bool(force_ffma)
         self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
         self.plan = ctypes.c_void_p()
         self.max_batch = 0
@@ -384,6 +386,67 @@ class CompiledNet(object):
         ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
         nat.check(self.lib.dlwp_plan_forward(self.plan, x.shape[0], x.data_ptr(), ptrs, self._stream()),
                   'dlwp_plan_forward')
+
+    # -- training -------------------------------------------------------------------------------------------------
+    def train_step(self, x, targets, loss_weights=None, backward=True, input_grad=False):
+        """Forward + MSE losses (+ backward into the flat gradient buffer).  x, targets: CUDA float32 tensors.
+        Returns (per-output mse list, per-output mae list)."""
+        n = x.shape[0]
+        self.sync_weights()
+        k = self.n_outputs
+        tp = (ctypes.c_void_p * k)(*[t.data_ptr() for t in targets])
+        lw = (ctypes.c_float * k)(*([1.0] * k if loss_weights is None else [float(v) for v in loss_weights]))
+        losses, maes = (ctypes.c_float * k)(), (ctypes.c_float * k)()
+        nat.check(self.lib.dlwp_train_step(self.plan, n, x.data_ptr(), tp, lw, 1 if backward else 0,
+                                           1 if input_grad else 0, losses, maes, self._stream()), 'dlwp_train_step')
+        return list(losses), list(maes)
+
+    def _device_view(self, ptr, elems):
+        class _Arr(object):
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {'shape': (int(elems),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+        return self.torch.as_tensor(a, device='cuda')
+
+    def grad_tensor(self):
+        """The flat gradient buffer as a CUDA tensor view (for torch.distributed.all_reduce)."""
+        p, n, gi = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
+        nat.check(self.lib.dlwp_train_buffers(self.plan, ctypes.byref(p), ctypes.byref(n), ctypes.byref(gi)))
+        return self._device_view(p.value, n.value)
+
+    def input_grad_tensor(self, n):
+        p, m, gi = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
+        nat.check(self.lib.dlwp_train_buffers(self.plan, ctypes.byref(p), ctypes.byref(m), ctypes.byref(gi)))
+        return self._device_view(gi.value, n * int(np.prod(self.in_shape))).view((n,) + self.in_shape)
+
+    def weight_grads(self):
+        """Gradients in Keras layouts, ordered like model.get_weights() (host numpy)."""
+        flat = self.grad_tensor().cpu().numpy()
+        out = []
+        for wid, layer in enumerate(self.low.weight_layers):
+            ko, bo = ctypes.c_int64(), ctypes.c_int64()
+            nat.check(self.lib.dlwp_train_weight_offsets(self.plan, wid, ctypes.byref(ko), ctypes.byref(bo)))
+            k = layer._weights[0]
+            out.append(flat[ko.value:ko.value + k.size].reshape(k.shape).copy())
+            if layer.use_bias:
+                b = layer._weights[1]
+                out.append(flat[bo.value:bo.value + b.size].reshape(b.shape).copy())
+        return out
+
+    def adam(self, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        nat.check(self.lib.dlwp_train_adam(self.plan, lr, beta_1, beta_2, epsilon, self._stream()), 'dlwp_train_adam')
+
+    def pull_weights(self):
+        """Device weights -> the front-end layers (after optimizer steps)."""
+        for wid, layer in enumerate(self.low.weight_layers):
+            k = np.empty(layer._weights[0].shape, np.float32)
+            b = np.empty(layer._weights[1].size, np.float32) if layer.use_bias else None
+            nat.check(self.lib.dlwp_plan_get_weights(self.plan, wid, k.ctypes.data, k.size,
+                                                     b.ctypes.data if b is not None else None,
+                                                     b.size if b is not None else 0), 'dlwp_plan_get_weights')
+            layer._weights = [k] + ([b.reshape(layer._weights[1].shape)] if b is not None else [])
+            layer._weights_version += 1
+            self._pushed[wid] = layer._weights_version
 
     def uses_tensor_cores(self):
         return bool(self.lib.dlwp_plan_uses_tensor_cores(self.plan))

@@ -1,9 +1,188 @@
-"""Training entry points of the front-end Model (fit / fit_generator / evaluate).  Filled in by the backward path."""
+"""
+Training entry points of the front-end Model: `fit_generator`, `fit`, `train_on_batch`, `evaluate` with the Keras call
+signatures the reference uses (DLWP/model/models.py:188-228, :384-402, :303-317; examples/train_functional.py:300-316).
+
+Per batch (what keras does inside fit_generator): forward through the (possibly unrolled, shared-weight) net, loss =
+sum_k loss_weights[k] * mse_k, backward, Adam -- all in libdlwp_b200 (dlwp_train_step / dlwp_train_adam).  With
+torch.distributed initialised (one process per GPU) the flat gradient buffer is all-reduced between the two: plain data
+parallelism, the multi-GPU mode of the reference's `multi_gpu_model` (models.py:104-109) without its CPU-hosted weights.
+"""
+
+import numpy as np
+
+from .keras.engine import History
+from .keras.losses import mean_squared_error
 
 
-def _todo(*args, **kwargs):
-    raise NotImplementedError('training (Conv2D backward kernels, BASELINE.json configs[4]) is not built yet; the '
-                              'rollout / predict path is')
+def _loss_is_mse(loss):
+    return loss in ('mse', 'MSE', 'mean_squared_error') or loss is mean_squared_error
 
 
-fit = fit_generator = evaluate = train_on_batch = _todo
+def _engine(model, batch):
+    from .engine import CompiledNet
+    eng = getattr(model, '_train_engine', None)
+    if eng is None or eng.max_batch < batch:
+        if eng is not None:
+            eng.close()
+        eng = CompiledNet(model, batch, force_ffma=True)
+        if eng.max_batch < batch:
+            raise MemoryError('training batch %d does not fit the device' % batch)
+        model._train_engine = eng
+    return eng
+
+
+def _as_list(y, n):
+    ys = list(y) if isinstance(y, (list, tuple)) else [y]
+    if len(ys) != n:
+        raise ValueError('Error when checking model target: expected %d target arrays but got %d' % (n, len(ys)))
+    return ys
+
+
+def _check_compiled(model):
+    if model._compile_kwargs is None:
+        raise RuntimeError('You must compile your model before using it.')
+    loss = model.loss
+    losses = loss if isinstance(loss, (list, tuple)) else [loss]
+    if not all(_loss_is_mse(l) for l in losses):
+        raise NotImplementedError('dlwp_b200 trains with loss="mse" (latitude-weighted / ACC losses: SURVEY.md 8f)')
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def _step(model, x, y, train):
+    import torch
+    _check_compiled(model)
+    x = np.ascontiguousarray(x, np.float32)
+    eng = _engine(model, x.shape[0])
+    ys = _as_list(y, eng.n_outputs)
+    xd = torch.from_numpy(x).cuda()
+    yd = [torch.from_numpy(np.ascontiguousarray(v, np.float32).reshape((x.shape[0],) + p)).cuda()
+          for v, p in zip(ys, eng.out_phys)]
+    lw = model.loss_weights
+    losses, maes = eng.train_step(xd, yd, lw, backward=train)
+    if train:
+        opt = model.optimizer
+        dist = _dist()
+        if dist is not None:
+            g = eng.grad_tensor()
+            dist.all_reduce(g)
+            g.div_(dist.get_world_size())
+        if opt.__class__.__name__ != 'Adam':
+            raise NotImplementedError('dlwp_b200 implements the Adam update (the optimizer of every DLWP example)')
+        lr = opt.lr * (1. / (1. + opt.decay * opt.iterations))
+        eng.adam(lr, opt.beta_1, opt.beta_2, opt.epsilon)
+        opt.iterations += 1
+    w = [1.0] * len(losses) if lw is None else list(lw)
+    logs = {'loss': float(sum(wi * li for wi, li in zip(w, losses)))}
+    if len(losses) > 1:
+        for k, li in enumerate(losses):
+            logs['output_%d_loss' % k] = float(li)
+    if any(m in ('mae', 'mean_absolute_error') for m in (model.metrics or [])):
+        if len(maes) == 1:
+            logs['mean_absolute_error'] = float(maes[0])
+        else:
+            for k, m in enumerate(maes):
+                logs['output_%d_mean_absolute_error' % k] = float(m)
+    return logs
+
+
+def train_on_batch(model, x, y, **kwargs):
+    logs = _step(model, x, y, True)
+    model._train_engine.pull_weights()
+    return logs['loss'] if len(logs) == 1 else [logs[k] for k in logs]
+
+
+def _iter_batches(data, steps=None, batch_size=32):
+    """(x, y) tuple of arrays or a keras Sequence -> batches."""
+    if isinstance(data, (tuple, list)):
+        x, y = data[0], data[1]
+        n = len(x)
+        for s in range(0, n, batch_size):
+            yb = [v[s:s + batch_size] for v in y] if isinstance(y, (list, tuple)) else y[s:s + batch_size]
+            yield x[s:s + batch_size], yb
+        return
+    n = len(data) if steps is None else min(steps, len(data))
+    for i in range(n):
+        b = data[i]
+        yield b[0], b[1]
+
+
+def evaluate(model, x=None, y=None, batch_size=32, verbose=0, steps=None, **kwargs):
+    data = x if y is None else (x, y)
+    totals, count = {}, 0
+    for xb, yb in _iter_batches(data, steps, batch_size):
+        logs = _step(model, xb, yb, False)
+        n = len(xb)
+        for k, v in logs.items():
+            totals[k] = totals.get(k, 0.0) + v * n
+        count += n
+    out = [totals[k] / max(count, 1) for k in totals]
+    return out[0] if len(out) == 1 else out
+
+
+def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
+                  validation_steps=None, class_weight=None, max_queue_size=10, workers=1, use_multiprocessing=False,
+                  shuffle=True, initial_epoch=0, **kwargs):
+    _check_compiled(model)
+    history = History()
+    cbs = [history] + list(callbacks or [])
+    for cb in cbs:
+        if hasattr(cb, 'set_model'):
+            cb.set_model(model)
+        if hasattr(cb, 'set_params'):
+            cb.set_params({'epochs': epochs, 'steps': steps_per_epoch, 'verbose': verbose})
+    model.stop_training = False
+    model.history = history
+    for cb in cbs:
+        cb.on_train_begin()
+    for epoch in range(initial_epoch, epochs):
+        for cb in cbs:
+            cb.on_epoch_begin(epoch)
+        totals, count = {}, 0
+        for bi, (xb, yb) in enumerate(_iter_batches(generator, steps_per_epoch)):
+            for cb in cbs:
+                cb.on_batch_begin(bi)
+            logs = _step(model, xb, yb, True)
+            n = len(xb)
+            for k, v in logs.items():
+                totals[k] = totals.get(k, 0.0) + v * n
+            count += n
+            for cb in cbs:
+                cb.on_batch_end(bi, dict(logs, batch=bi, size=n))
+        epoch_logs = {k: v / max(count, 1) for k, v in totals.items()}
+        model._train_engine.pull_weights()
+        if validation_data is not None:
+            val = evaluate(model, validation_data, steps=validation_steps)
+            vals = val if isinstance(val, list) else [val]
+            for k, v in zip(list(epoch_logs.keys()), vals):
+                epoch_logs['val_' + k] = v
+        if verbose:
+            print('Epoch %d/%d - ' % (epoch + 1, epochs) + ' - '.join('%s: %.6f' % kv for kv in epoch_logs.items()))
+        for cb in cbs:
+            cb.on_epoch_end(epoch, epoch_logs)
+        if hasattr(generator, 'on_epoch_end'):
+            generator.on_epoch_end()
+        if model.stop_training:
+            break
+    for cb in cbs:
+        cb.on_train_end()
+    model._train_engine.pull_weights()
+    return history
+
+
+def fit(model, x=None, y=None, batch_size=32, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True,
+        **kwargs):
+    from .model.generators import ArrayDataGenerator
+    gen = ArrayDataGenerator(x, y, batch_size=batch_size or 32, shuffle=shuffle)
+    val = None
+    if validation_data is not None:
+        val = ArrayDataGenerator(validation_data[0], validation_data[1], batch_size=batch_size or 32)
+    return fit_generator(model, gen, epochs=epochs, verbose=verbose, callbacks=callbacks, validation_data=val)

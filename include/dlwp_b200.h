@@ -198,6 +198,21 @@ void dlwp_comm_destroy(void* comm);
 int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0, float* series, int32_t iterations,
                          const DlwpBandInfo* band, int32_t use_graph, dlwp_stream_t stream);
 
+/* ---- training (BASELINE.json configs[4]): what keras fit_generator / train_on_batch does per batch ------------------- */
+
+/* Forward through the plan, loss = sum_k loss_weights[k] * mean((yhat_k - y_k)^2) (Keras 'mse'), and -- if `backward` --
+ * backprop into one flat gradient buffer (kernel then bias per weight id, Keras layouts; shared layers accumulate).
+ * x, targets[k]: device, dense. losses[k] / maes[k] (host, may be NULL for maes) receive the unweighted per-output MSE / MAE.
+ * Needs a plan built on the fp32 kernels (DLWP_MATH=ffma). Blocking (returns the loss). */
+int dlwp_train_step(DlwpPlan* plan, int32_t N, const float* x, const float* const* targets, const float* loss_weights,
+                    int32_t backward, int32_t input_grad, float* losses, float* maes, dlwp_stream_t stream);
+/* The flat gradient buffer (device) for a data-parallel all-reduce between dlwp_train_step and dlwp_train_adam, and the
+ * gradient w.r.t. the input (valid when input_grad was set). */
+int dlwp_train_buffers(DlwpPlan* plan, float** flat_grad, int64_t* elems, float** input_grad);
+int dlwp_train_weight_offsets(DlwpPlan* plan, int32_t weight_id, int64_t* kernel_off, int64_t* bias_off);
+/* Keras Adam update of every weight from the flat gradient buffer (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps outside sqrt). */
+int dlwp_train_adam(DlwpPlan* plan, float lr, float beta1, float beta2, float eps, dlwp_stream_t stream);
+
 /* Time one op of the plan alone: `iters` launches bracketed by CUDA events on `stream` (after 2 warm-up launches), using
  * whatever the plan's buffers hold from the last forward / rollout. Blocking. Used by bench.py for the roofline figure. */
 int dlwp_plan_profile_op(DlwpPlan* plan, int32_t N, int32_t op_index, int32_t iters, float* ms_per_launch,

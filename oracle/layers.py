@@ -114,6 +114,8 @@ class OConv2D(OLayer):
     def __call__(self, x):
         if _is_torch(x):
             assert self.data_format == 'channels_first'
+            if getattr(self, '_tparam', None) is not None:   # autograd leaves supplied by a gradient test
+                self._tw = self._tparam
             if self._tw is None:
                 w = torch.from_numpy(np.ascontiguousarray(np.transpose(self.kernel, (3, 2, 0, 1)))).to(x.dtype)
                 b = torch.from_numpy(np.ascontiguousarray(self.bias)).to(x.dtype) if self.use_bias else None
