@@ -422,7 +422,7 @@ bool tc_geometry_ok(const DlwpConvDesc& d) {
     const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
     if (d.pad_l != halo_w / 2 || d.pad_r != halo_w / 2 || (halo_w & 1)) return false;  // 'same' width
     if (d.pad_t + d.pad_b != halo_h) return false;                                      // 'same' height
-    if (d.W + halo_w > 256 || d.W < halo_w) return false;                               // one TMA box per row
+    if (d.W < halo_w || d.W + halo_w > 1024) return false;                              // rows are staged whole
     if ((d.kw - 1) * d.dil_w > 8) return false;
     TcLayer L;
     return tc_plan_layer(d, &L) == 0;

@@ -62,7 +62,8 @@ int upsample_bwd(const float* g, float* dx, int N, int C, int Hl, int Wl, const 
                  cudaStream_t stream);
 int add_bwd(const float* g, float* dx, int N, int C, int H, int W, const long long* gs, const long long* dxs,
             cudaStream_t stream);
-int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream);
+int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream,
+             const float* wmap = nullptr, long long hw = 1);
 int adam_step(float* w, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
               cudaStream_t stream);
 

@@ -96,6 +96,7 @@ struct DlwpPlan {
     float *flat_g = nullptr, *flat_m = nullptr, *flat_v = nullptr, *stats = nullptr;
     long long flat_elems = 0, adam_t = 0;
     std::vector<long long> gk_off, gb_off;
+    float* loss_wmap = nullptr;      // optional (H, W) latitude weights of the loss
 };
 
 namespace dlwp {
@@ -443,7 +444,7 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (g) cudaFree(g);
     for (float* g : pl->out_store)
         if (g) cudaFree(g);
-    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats})
+    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats, pl->loss_wmap})
         if (g) cudaFree(g);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
@@ -853,8 +854,9 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
         DLWP_REQUIRE(targets[k] != nullptr, DLWP_EINVAL, "target %d is null", k);
         const long long nk = (long long)N * pl->buffers[pl->outputs[k]].sample_elems();
         const float lw = loss_weights ? loss_weights[k] : 1.f;
+        const Buffer& ob = pl->buffers[pl->outputs[k]];
         rc = mse_grad(pl->out_store[k], targets[k], backward ? pl->gbuf[pl->outputs[k]] : nullptr, nk, lw * 2.f / (float)nk,
-                      pl->stats + 2 * k, stream);
+                      pl->stats + 2 * k, stream, pl->loss_wmap, (long long)ob.d.H * ob.d.W);
         if (rc) return rc;
     }
     // ---- backward: ops in reverse order; gradients accumulate into channel windows of the per-buffer gradient ----
@@ -895,6 +897,19 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
         losses[k] = (float)(h[2 * k] / nk);
         if (maes) maes[k] = (float)(h[2 * k + 1] / nk);
     }
+    return 0;
+}
+
+extern "C" int dlwp_train_loss_weights(DlwpPlan* pl, const float* wmap_host, int64_t elems) {
+    DLWP_REQUIRE(pl != nullptr, DLWP_EINVAL, "null plan");
+    if (pl->loss_wmap) cudaFree(pl->loss_wmap);
+    pl->loss_wmap = nullptr;
+    if (!wmap_host) return 0;
+    const Buffer& ob = pl->buffers[pl->outputs[0]];
+    DLWP_REQUIRE(elems == (int64_t)ob.d.H * ob.d.W, DLWP_ESHAPE, "loss weight map must have H*W = %d elements",
+                 ob.d.H * ob.d.W);
+    DLWP_CUDA_TRY(cudaMalloc(&pl->loss_wmap, sizeof(float) * elems));
+    DLWP_CUDA_TRY(cudaMemcpy(pl->loss_wmap, wmap_host, sizeof(float) * elems, cudaMemcpyHostToDevice));
     return 0;
 }
 

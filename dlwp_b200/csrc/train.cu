@@ -185,13 +185,17 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(const EwBwd p) {
 }
 
 // dL/dyhat = scale * (yhat - y); stats[0] += sum (yhat-y)^2, stats[1] += sum |yhat-y|
+// `wmap` (optional, hw elements): latitude weights of DLWP.custom.latitude_weighted_loss (custom.py:956-991), which scales
+// BOTH tensors before the base loss: loss = mean((w*yhat - w*y)^2), dL/dyhat = scale * w^2 * (yhat - y); MAE stays unweighted.
 __global__ void __launch_bounds__(256) mse_grad_kernel(const float* yhat, const float* y, float* g, long long n,
-                                                       float scale, float* stats) {
+                                                       float scale, float* stats, const float* wmap, long long hw) {
     float s2 = 0.f, s1 = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = yhat[i] - y[i];
-        if (g) g[i] += scale * d;
-        s2 += d * d;
+        const float w = wmap ? wmap[i % hw] : 1.f;
+        const float w2 = w * w;
+        if (g) g[i] += scale * w2 * d;
+        s2 += w2 * d * d;
         s1 += fabsf(d);
     }
     __shared__ float r2[8], r1[8];
@@ -297,8 +301,9 @@ int add_bwd(const float* g, float* dx, int N, int C, int H, int W, const long lo
     ew_bwd_kernel<BW_ADD><<<blocks_for((long long)N * C * H * W), 256, 0, stream>>>(p);
     return after_launch("add_bwd");
 }
-int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream) {
-    mse_grad_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, g, n, scale, stats);
+int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream,
+             const float* wmap, long long hw) {
+    mse_grad_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, g, n, scale, stats, wmap, hw);
     return after_launch("mse_grad_kernel");
 }
 int adam_step(float* w, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,

@@ -15,7 +15,23 @@ from .keras.losses import mean_squared_error
 
 
 def _loss_is_mse(loss):
-    return loss in ('mse', 'MSE', 'mean_squared_error') or loss is mean_squared_error
+    if loss in ('mse', 'MSE', 'mean_squared_error') or loss is mean_squared_error:
+        return True
+    # DLWP.custom.latitude_weighted_loss(mean_squared_error, lats, output_shape, ...): an MSE on latitude-scaled tensors
+    return getattr(loss, 'base_loss', None) is mean_squared_error and hasattr(loss, 'weights')
+
+
+def _loss_weight_map(model, eng):
+    """(H, W) weight map of a latitude-weighted loss, or None."""
+    loss = model.loss[0] if isinstance(model.loss, (list, tuple)) else model.loss
+    w = getattr(loss, 'weights', None)
+    if w is None or not hasattr(loss, 'base_loss'):
+        return None
+    H, W = eng.out_phys[0][1], eng.out_phys[0][2]
+    w = np.asarray(w, np.float32)
+    if w.size == 1:
+        return None
+    return np.ascontiguousarray(np.broadcast_to(w.reshape(w.shape[-2:]) if w.ndim >= 2 else w.reshape(H, 1), (H, W)))
 
 
 def _engine(model, batch):
@@ -27,6 +43,10 @@ def _engine(model, batch):
         eng = CompiledNet(model, batch, force_ffma=True)
         if eng.max_batch < batch:
             raise MemoryError('training batch %d does not fit the device' % batch)
+        wmap = _loss_weight_map(model, eng)
+        if wmap is not None:
+            from . import _native as nat
+            nat.check(nat.lib().dlwp_train_loss_weights(eng.plan, wmap.ctypes.data, wmap.size), 'dlwp_train_loss_weights')
         model._train_engine = eng
     return eng
 

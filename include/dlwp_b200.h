@@ -206,6 +206,9 @@ int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0,
  * Needs a plan built on the fp32 kernels (DLWP_MATH=ffma). Blocking (returns the loss). */
 int dlwp_train_step(DlwpPlan* plan, int32_t N, const float* x, const float* const* targets, const float* loss_weights,
                     int32_t backward, int32_t input_grad, float* losses, float* maes, dlwp_stream_t stream);
+/* Optional (H, W) weight map of DLWP.custom.latitude_weighted_loss (custom.py:956-991): both tensors are multiplied by it
+ * before the MSE. HOST pointer; NULL removes it. */
+int dlwp_train_loss_weights(DlwpPlan* plan, const float* wmap_host, int64_t elems);
 /* The flat gradient buffer (device) for a data-parallel all-reduce between dlwp_train_step and dlwp_train_adam, and the
  * gradient w.r.t. the input (valid when input_grad was set). */
 int dlwp_train_buffers(DlwpPlan* plan, float** flat_grad, int64_t* elems, float** input_grad);

@@ -163,3 +163,10 @@ def test_latitude_band_windows_on_tensor_cores(env):
     ref = dlwp.predict_timeseries(x0, 4)
     got, _ = _run_bands(dlwp.model, 4, x0, 4)
     np.testing.assert_array_equal(got, ref)
+
+
+def test_one_degree_grid_rows_wider_than_a_tma_box(env):
+    """W = 360 (the 1-degree grid): rows are staged whole by bulk copies, no 256-element box limit."""
+    nat, torch = env
+    _check(nat, torch, 1, 12, 22, 360, 32, 3, 2, nat.ACT_TANH, 11)
+    _check(nat, torch, 1, 32, 16, 360, 12, 5, 1, nat.ACT_LINEAR, 12)

@@ -129,3 +129,44 @@ def test_adam_steps_match_torch_adam_and_fit_generator_learns():
     net.set_weights(dlwp.model.get_weights())
     y_pred = dlwp.predict(X[:2])
     assert _rel(y_pred, net.forward(X[:2].astype(np.float64))) < 2e-5
+
+
+def test_latitude_weighted_mse_matches_reference_definition():
+    """DLWP.custom.latitude_weighted_loss(mean_squared_error, lats, shape, weighting='midlatitude') as the training loss."""
+    import torch
+    from dlwp_b200.custom import latitude_weighted_loss
+    from dlwp_b200.keras.losses import mean_squared_error
+    from dlwp_b200.model import DLWPNeuralNet
+    cs = (6, 20, 36)
+    layers = OL.net_a_layers(cs)
+    lats = np.linspace(-85, 85, cs[1])
+    dlwp = DLWPNeuralNet(is_convolutional=True, time_dim=1, scaler_type=None, scale_targets=False)
+    dlwp.build_model(layers, loss=latitude_weighted_loss(mean_squared_error, lats, cs, axis=-2, weighting='midlatitude'),
+                     optimizer='adam')
+    net = oracle_sequential_like(dlwp, layers, seed=6, bias_scale=0.05)
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal((4,) + cs).astype(np.float32)
+    y = rng.standard_normal((4,) + cs).astype(np.float32)
+    got = dlwp.model.evaluate(x, y, batch_size=4)
+    w = np.cos(lats * np.pi / 180) + 0.5 * np.sin(lats * 2 * np.pi / 180) ** 2          # custom.py:976-978
+    ref = float(np.mean((w[None, None, :, None] * (net.forward(x.astype(np.float64)) - y)) ** 2))
+    assert abs(got - ref) / ref < 1e-5
+    # gradient of the weighted loss vs autograd
+    eng = dlwp.model._train_engine
+    eng.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(y).cuda()], None, True, False)
+    params = []
+    for layer in net.conv_layers:
+        wt = torch.tensor(np.transpose(layer.kernel, (3, 2, 0, 1)).astype(np.float64), requires_grad=True)
+        bt = torch.tensor(layer.bias.astype(np.float64), requires_grad=True)
+        layer._tparam, layer._tw = (wt, bt), None
+        params += [wt, bt]
+    wt_map = torch.tensor(w)[None, None, :, None]
+    loss = ((wt_map * (net.forward(torch.tensor(x.astype(np.float64))) - torch.tensor(y.astype(np.float64)))) ** 2).mean()
+    loss.backward()
+    want = []
+    for layer in net.conv_layers:
+        wt, bt = layer._tparam
+        want += [np.transpose(wt.grad.numpy(), (2, 3, 1, 0)), bt.grad.numpy()]
+        layer._tparam, layer._tw = None, None
+    for g, r in zip(eng.weight_grads(), want):
+        assert _rel(g, r) < TOL
