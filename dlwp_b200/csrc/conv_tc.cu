@@ -51,6 +51,7 @@ struct TcParams {
     int KW, D, pad_t;
     int Cout, NCOLS, CBLK, CSTRIDE;  // filters, MMA N, 8-filter blocks, TMEM columns per horizontal tap of a block
     int G, KS, NS;            // channel groups per tile, K steps per group, smem stages
+    int NACC;                 // TMEM accumulator sets: 2 (MMA of tile t+1 overlaps the epilogue of tile t) or 1
     int planes_per_group;
     int tiles_per_sample, total_tiles;
     int row0, row1;           // output rows [row0, row1) this launch computes (latitude band); tiles start at row0
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ACC_COLS = p.MT * p.NCOLS;  // columns of one accumulator set (<= 256)
+    const int ACC_COLS = p.MT * p.NCOLS;  // columns of one accumulator set (NACC * ACC_COLS <= 512)
 
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     for (uint32_t i = tid; i < 2 * p.b_bytes / 16; i += TC_THREADS)  // weight images -> smem (hi then lo, contiguous)
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const uint32_t bhi16 = smem_u32(b_hi) >> 4, blo16 = smem_u32(b_lo) >> 4;
         const uint32_t plane16 = p.plane_bytes >> 4;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int ab = it & 1;
-            mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
+            const int ab = it % p.NACC;
+            mbar_wait(&acc_empty[ab], ((it / p.NACC) & 1) ^ 1);
             tc_fence_after();
             const uint32_t acc_base = tmem + ab * ACC_COLS;
             for (int g = 0; g < p.G; ++g, ++idx) {
@@ -264,10 +265,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const int nitems = p.MT * p.CBLK;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int ab = it & 1;
+            const int ab = it % p.NACC;
             const int n = tile / p.tiles_per_sample;
             const int y0 = p.row0 + (tile % p.tiles_per_sample) * p.R_out;
-            mbar_wait(&acc_full[ab], (it >> 1) & 1);
+            mbar_wait(&acc_full[ab], (it / p.NACC) & 1);
             tc_fence_after();
             // ---- pass 1: publish the taps the previous quadrant will need --------------------------------------------
             int li = 0;
@@ -449,14 +450,16 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     // units = (chunk, tap) in order; groups of chunks so that a group has an even number of units when possible
     const int smem_budget = 224 * 1024;
     const size_t bias_bars = (size_t)cdiv(d.Cout, 8) * 32 + 512;
-    int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0;
+    int best_r = 0, best_cpg = 0, best_ns = 0, best_mt = 0, best_nacc = 2;
     const char* env_r = getenv("DLWP_TC_ROUT");
     // big-K layers (>= 2 channel groups per tile) run best with small tiles: more tiles to balance, shorter TMA latency
     const int r_max = env_r ? atoi(env_r) : (L->C8 > 2 ? 4 : 8);
+    // prefer two accumulator sets (the MMAs of tile t+1 overlap the epilogue of tile t); wide rows may only fit one
+    for (int nacc = 2; nacc >= 1 && !best_r; --nacc)
     for (int r_out = r_max; r_out >= 1; --r_out) {
         const int rin = r_out + halo_h;
         const int mt = cdiv(r_out * L->Wp, L->S);
-        if (mt * L->NCOLS > 256) continue;  // two accumulator sets in 512 TMEM columns
+        if (mt * L->NCOLS * nacc > 512) continue;  // the accumulator sets must fit the 512 TMEM columns
         const size_t fixed = (size_t)TC_SETS * cdiv(mt * L->CBLK, TC_SETS) * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 + bias_bars;
         for (int cpg = std::min(L->C8, 4); cpg >= 1; --cpg) {
             const int G = cdiv(L->C8, cpg);
@@ -469,7 +472,7 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
             const int ns = G >= 2 ? 2 : (stride * 3 + 2 * bimg + fixed <= (size_t)smem_budget ? 3 : 2);
             if (stride * ns + 2 * bimg + fixed > (size_t)smem_budget) continue;
             if (stage > (1u << 20)) continue;
-            best_r = r_out; best_cpg = cpg; best_ns = ns; best_mt = mt;
+            best_r = r_out; best_cpg = cpg; best_ns = ns; best_mt = mt; best_nacc = nacc;
             break;
         }
         if (best_r) break;
@@ -482,6 +485,7 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->G = cdiv(L->C8, best_cpg);
     L->KS = cdiv(best_cpg * d.kh * (L->taps_in_k ? d.kw : 1), 2);
     L->NS = best_ns;
+    L->NACC = best_nacc;
     L->stage_bytes = (uint32_t)(2 * best_cpg * L->Rin * L->Wp * 16);
     L->stage_stride = (L->stage_bytes + 127) / 128 * 128;
     L->plane_bytes = (uint32_t)(L->Rin * L->Wp * 16);
@@ -574,7 +578,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.R_out = L.R_out; p.Rin = L.Rin; p.MT = L.MT; p.S = L.S;
     p.KW = L.kw_eff; p.D = d.dil_w; p.pad_t = d.pad_t;
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
-    p.G = L.G; p.KS = L.KS; p.NS = L.NS; p.planes_per_group = 2 * L.cpg;
+    p.G = L.G; p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC; p.planes_per_group = 2 * L.cpg;
     const bool all_rows = d.row_begin == 0 && d.row_end == 0;
     p.row0 = all_rows ? 0 : d.row_begin;
     p.row1 = all_rows ? d.H : d.row_end;

@@ -24,6 +24,7 @@ struct TcLayer {
     int taps_in_k, kw_eff; // horizontal taps folded into K (small Cin) -> the epilogue sees a 1-tap layer
     int R_out, Rin, MT;    // rows per tile, staged rows, M tiles per tile
     int cpg, G, KS, NS;    // chunks per group, groups per tile, K=16 steps per group, smem stages
+    int NACC;              // TMEM accumulator sets (2 = double buffered)
     uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;
     size_t smem;
 };
