@@ -412,9 +412,438 @@ __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict
 }
 
 // ===================================================================================================================
+// Sliding-window kernel (mode 1).
+//
+// Measured on B200 (scripts/mma_rate_probe.cu, profiles/r01_mma_rate_probe.txt): a 128 x N x 16 f16 MMA with both operands
+// in shared memory takes max(N/2, 32 + N/4) clocks -- for the N = 32..96 of these layers it is bound by the 4 KB A read,
+// not by the tensor pipe.  With .collector::a::fill/use/lastuse consecutive MMAs that share their A operand run at
+// ~19 clk (N = 32; tensor floor 16).  So the tile is laid out to make A sharing the common case:
+//   * an M tile is 128 consecutive pixels of ONE padded row ("strip"; lane = x - x0).  The remainder strips of two
+//     samples share a tile (lanes 0-63 / 64-127) when they fit, so W = 180 costs 1.5 tiles per row, not 2;
+//   * a CTA walks a strip top to bottom.  Each padded input row is staged once (one bulk copy per plane and segment
+//     into a ring of row stages) and feeds ALL vertical taps: row rp updates the accumulators of output rows
+//     rp - i*dil, i = 0..KH-1, with the same A view and different weight blocks -> per K step the hi view is read once
+//     for 2*KH MMAs (hi*hi, hi*lo) and the lo view once for KH MMAs;
+//   * TMEM holds a ring of NACC accumulators (one output row x 128 lanes x NCOLS columns each); a row is committed to
+//     the epilogue when its last tap has been issued.  Four epilogue warp sets take rows round robin.
+// Horizontal taps live in N (few filters: the epilogue's shifted sum, as in the flattened kernel) or in K (A views
+// shifted by j*dil pixels inside the staged row; N = filters).
+// ===================================================================================================================
+constexpr int SW_MAX_STAGES = 12;
+constexpr int SW_MAX_ACC = 16;
+
+struct SwParams {
+    int N, H, W, Wp;
+    int D, pad_t;
+    int S, nfull, rem, pair;          // strips: valid outputs per full strip, full strips per row, remainder, pairing
+    int units_per_group, nbands, RB, total_units;
+    int row0, row1;
+    int Cout, NCOLS, CBLK, CSTRIDE, XL;
+    int KS, NS, NACC;
+    int planes_in;
+    uint32_t rowpitch, stage_stride, b_unit16, b_bytes;  // b_unit16: one (k step, tap, hi|lo) weight block in 16-byte units
+    uint32_t idesc;
+    int act;
+    const float* bias;
+    const __half* bimg;
+    const __half* xp;
+    float* y32; long long ys_n, ys_c, ys_h;
+    __half* yp; int Wp_out, wpad_out, planes_out;
+    TcKStep kst[TC_MAX_KSTEPS];
+};
+
+struct SwUnit {
+    int n0, n1;      // samples of the two segments (n1 = -1: none)
+    int x0;          // first padded column of the strip (both segments of a paired tile start at the same column)
+    int nva, nvb;    // valid output lanes per segment
+    int ya, yb;      // output rows [ya, yb)
+    int paired;      // lanes 64.. belong to segment b
+};
+
+__device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwUnit& U) {
+    const int band = u % p.nbands, su = u / p.nbands;
+    const int g = su / p.units_per_group, k = su - g * p.units_per_group;
+    U.ya = p.row0 + band * p.RB;
+    U.yb = min(p.row1, U.ya + p.RB);
+    U.n1 = -1; U.nvb = 0; U.paired = 0;
+    if (!p.pair) {
+        U.n0 = g; U.x0 = k * p.S; U.nva = k < p.nfull ? p.S : p.rem;
+    } else if (k < 2 * p.nfull) {
+        const int which = k / p.nfull;
+        U.n0 = 2 * g + which; U.x0 = (k - which * p.nfull) * p.S; U.nva = p.S;
+    } else {
+        U.paired = 1;
+        U.n0 = 2 * g; U.x0 = p.nfull * p.S; U.nva = p.rem;
+        if (2 * g + 1 < p.N) { U.n1 = 2 * g + 1; U.nvb = p.rem; }
+    }
+    return U.n0 < p.N && U.ya < U.yb;
+}
+
+template <int COLL>  // 0: no collector hint, 1: fill, 2: use, 3: lastuse
+__device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (COLL == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else if constexpr (COLL == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else if constexpr (COLL == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// KH: kernel height (vertical taps), KW: horizontal taps summed by the epilogue (1 = folded into K), NC: filters per
+// 8-filter block that exist (6: the single packed block of a 6-filter layer, else 8)
+template <int KH, int KW, int NC>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;
+    unsigned char* bsm = stages + (size_t)p.NS * p.stage_stride;
+    float* xch = reinterpret_cast<float*>(bsm + p.b_bytes);  // mailbox [set][parity][block][quadrant][XL][(KW-1)*8]
+    const int XQ = p.XL * (KW - 1) * 8;
+    float* sbias = xch + (size_t)TC_SETS * 2 * p.CBLK * 4 * XQ;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.CBLK * 8);
+    uint64_t* full = bars;                                  // [NS]       bulk copies of a row landed
+    uint64_t* empty = bars + SW_MAX_STAGES;                 // [NS]       the row's MMAs have read the stage
+    uint64_t* acc_full = bars + 2 * SW_MAX_STAGES;          // [NACC]     output row complete in TMEM
+    uint64_t* acc_empty = acc_full + SW_MAX_ACC;            // [NACC]     epilogue done with the accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SW_MAX_ACC);
+
+    // Warp roles: warps 0-15 epilogue (set = warp / 4, TMEM lane quadrant = warp % 4), warp 16 producer, warp 17 MMA
+    // issuer.  The two single-warp roles sit on the highest warp ids: the issuer's serial instruction stream is the
+    // critical path (ncu: with it on warp 1 the epilogue warps waited on acc_full 36 % of the time while the issuer never
+    // waited on a barrier), and the scheduler favours higher warp ids among eligible warps.
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int W_PROD = TC_SETS * 4, W_MMA = TC_SETS * 4 + 1;
+    const int SPAN = (KH - 1) * p.D;
+
+    for (uint32_t i = tid; i < p.b_bytes / 16; i += TC_THREADS)
+        reinterpret_cast<uint4*>(bsm)[i] = reinterpret_cast<const uint4*>(p.bimg)[i];
+    for (uint32_t i = tid; i < (uint32_t)p.NS * p.stage_stride / 16; i += TC_THREADS)  // lanes past a row's end stay finite
+        reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < p.CBLK * 8; i += TC_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < p.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < p.NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        fence_mbar_init();
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int Halloc = p.H + 2 * TC_HPAD;
+
+    if (warp == W_PROD) {
+        // =============================== producer: one bulk copy per (plane, segment) and input row =======================
+        int s = 0;
+        uint32_t ph = 0;  // parity of the stage ring's current lap
+        SwUnit U;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            if (!sw_decode(p, u, U)) continue;
+            const int nseg = U.n1 >= 0 ? 2 : 1;
+            const int avail = p.Wp - U.x0;                                   // pixels left in the padded row
+            const uint32_t lenA = (uint32_t)min(U.paired ? 64 : (int)(p.rowpitch >> 4), avail) * 16u;
+            const uint32_t lenB = (uint32_t)min((int)(p.rowpitch >> 4) - 64, avail) * 16u;
+            const uint32_t row_bytes = (uint32_t)p.planes_in * (lenA + (nseg == 2 ? lenB : 0u));
+            const int ncp = p.planes_in * nseg;
+            // this lane's copies: c = lane and c = lane + 32 (planes_in <= 32, two segments)
+            const __half* src[2];
+            uint32_t dsto[2], len[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = lane + 32 * k;
+                const int seg = c >= p.planes_in ? 1 : 0;
+                const int q = c - seg * p.planes_in;
+                const int n = seg ? U.n1 : U.n0;
+                src[k] = p.xp + ((((size_t)max(n, 0) * p.planes_in + q) * Halloc + (size_t)(U.ya - p.pad_t + TC_HPAD)) * p.Wp + U.x0) * 8;
+                dsto[k] = (uint32_t)q * p.rowpitch + (uint32_t)seg * 1024u;
+                len[k] = seg ? lenB : lenA;
+            }
+            const size_t row_halfs = (size_t)p.Wp * 8;
+            const int nrows = U.yb - U.ya + SPAN;
+            for (int r = 0; r < nrows; ++r) {
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], row_bytes);
+                }
+                __syncwarp();
+                unsigned char* dst0 = stages + (size_t)s * p.stage_stride;
+                if (lane < ncp) bulk_load(dst0 + dsto[0], src[0], len[0], &full[s]);
+                if (lane + 32 < ncp) bulk_load(dst0 + dsto[1], src[1], len[1], &full[s]);
+                src[0] += row_halfs;
+                src[1] += row_halfs;
+                if (++s == p.NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // =============================== MMA issuer (warp-convergent, one elected lane issues) ===========================
+        const bool leader = elect_one();
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, sm_100 descriptor version
+        const uint32_t b_lbo_field = ((p.NCOLS * 16u) >> 4) << 16;
+        const uint32_t b16 = smem_u32(bsm) >> 4;
+        const uint32_t pitch16 = p.rowpitch >> 4;
+        const uint32_t stages16 = smem_u32(stages) >> 4, stride16 = p.stage_stride >> 4;
+        const uint32_t unit16 = p.b_unit16;
+        int s = 0;
+        uint32_t ph = 0;
+        int sl0 = 0;        // accumulator slot of the output row that starts at the current input row
+        uint32_t aph = 0;   // parity of the accumulator ring's current lap
+        SwUnit U;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            if (!sw_decode(p, u, U)) continue;
+            const int nout = U.yb - U.ya;
+            const int nrows = nout + SPAN;
+            int sl = sl0;           // slot of (virtual) output row r; rows r >= nout are never started
+            uint32_t ap = aph;
+            for (int r = 0; r < nrows; ++r) {
+                if (r < nout) mbar_wait(&acc_empty[sl], ap ^ 1);  // output row r starts accumulating: slot must be drained
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sbase16 = stages16 + (uint32_t)s * stride16;
+                uint32_t dcol[KH];
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    int si = sl - i * p.D;
+                    if (si < 0) si += p.NACC;
+                    dcol[i] = tmem + (uint32_t)(si * p.NCOLS);
+                }
+                const bool interior = (r >= SPAN) && (r < nout);
+                if (interior) {
+                    for (int ks = 0; ks < p.KS; ++ks) {
+                        const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
+                        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
+                        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
+                        const uint32_t bks = b_lbo_field | (b16 + (uint32_t)(ks * KH) * 2u * unit16);
+#pragma unroll
+                        for (int i = 0; i < KH; ++i) {
+                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
+                            const uint64_t bl = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i + 1) * unit16);
+                            if (leader) {
+                                if (i == 0) umma_f16_c<1>(dcol[i], ad_hi, bh, p.idesc, ks != 0);
+                                else umma_f16_c<2>(dcol[i], ad_hi, bh, p.idesc, 1u);
+                                if (i == KH - 1) umma_f16_c<3>(dcol[i], ad_hi, bl, p.idesc, 1u);
+                                else umma_f16_c<2>(dcol[i], ad_hi, bl, p.idesc, 1u);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < KH; ++i) {
+                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
+                            if (leader) {
+                                if (i == 0) umma_f16_c<1>(dcol[i], ad_lo, bh, p.idesc, 1u);
+                                else if (i == KH - 1) umma_f16_c<3>(dcol[i], ad_lo, bh, p.idesc, 1u);
+                                else umma_f16_c<2>(dcol[i], ad_lo, bh, p.idesc, 1u);
+                            }
+                        }
+                    }
+                } else {
+                    for (int ks = 0; ks < p.KS; ++ks) {
+                        const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;
+                        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
+                        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
+                        const uint32_t bks = b_lbo_field | (b16 + (uint32_t)(ks * KH) * 2u * unit16);
+#pragma unroll
+                        for (int i = 0; i < KH; ++i) {
+                            const int yo = r - i * p.D;  // output row (relative to the unit) this tap contributes to
+                            if (yo < 0 || yo >= nout) continue;
+                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
+                            const uint64_t bl = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i + 1) * unit16);
+                            if (leader) {
+                                umma_f16(dcol[i], ad_hi, bh, p.idesc, (i | ks) != 0);
+                                umma_f16(dcol[i], ad_hi, bl, p.idesc, 1u);
+                                umma_f16(dcol[i], ad_lo, bh, p.idesc, 1u);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (leader) {
+                    umma_commit(&empty[s]);
+                    if (r >= SPAN) {  // the last tap of output row r - SPAN has been issued
+                        int sd = sl - SPAN;
+                        if (sd < 0) sd += p.NACC;
+                        umma_commit(&acc_full[sd]);
+                    }
+                }
+                if (++s == p.NS) { s = 0; ph ^= 1; }
+                if (++sl == p.NACC) { sl = 0; ap ^= 1; }
+            }
+            // the next unit's first output row follows this unit's last one in the accumulator ring
+            sl0 += nout;
+            while (sl0 >= p.NACC) { sl0 -= p.NACC; aph ^= 1; }
+        }
+    } else {
+        // =============================== epilogue: 4 sets x 4 quadrant warps, rows dealt round robin ===================
+        // Output rows are numbered G = 0, 1, 2, ... across the units of this CTA; set s takes G = s, s + 4, ... so its
+        // accumulator slot advances by 4 (mod NACC) per row, whatever the unit boundaries are.
+        const int q = warp & 3, set = warp >> 2;
+        const int XL = p.XL;
+        float* xset = xch + (size_t)set * 2 * p.CBLK * 4 * XQ;
+        const int Hout = p.H + 2 * TC_HPAD;
+        const size_t plane_stride = (size_t)Hout * p.Wp_out;  // uint4 units
+        int slot = set;
+        uint32_t aph = 0;
+        while (slot >= p.NACC) { slot -= p.NACC; aph ^= 1; }
+        int g = 0, lrow = 0;
+        SwUnit U;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            if (!sw_decode(p, u, U)) continue;
+            const int ml = q * 32 + lane;
+            const int seg = (U.paired && ml >= 64) ? 1 : 0;
+            const int l = ml - seg * 64;
+            const int n = seg ? U.n1 : U.n0;
+            const int x = U.x0 + l;
+            const bool lane_ok = (n >= 0) && (l < (seg ? U.nvb : U.nva)) && (x < p.W);
+            const bool halo_r = x < p.wpad_out, halo_l = x >= p.W - p.wpad_out;
+            float* y32n = p.y32 != nullptr ? p.y32 + (long long)max(n, 0) * p.ys_n + x : nullptr;
+            uint4* ypn = p.yp != nullptr
+                             ? reinterpret_cast<uint4*>(p.yp) + ((size_t)max(n, 0) * p.planes_out * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
+                             : nullptr;
+            for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
+                mbar_wait(&acc_full[slot], aph);
+                tc_fence_after();
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.NCOLS);
+                float* mb = xset + (size_t)(lrow & 1) * p.CBLK * 4 * XQ;
+                if (KW > 1) {
+                    // ---- pass 1: the taps that the previous quadrant's last lanes need -> mailbox ----------------------
+                    for (int cb = 0; cb < p.CBLK; ++cb) {
+                        float d[KW > 1 ? KW - 1 : 1][8];
+#pragma unroll
+                        for (int j = 1; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * p.CSTRIDE, d[j - 1]);
+                        tmem_ld_wait();
+                        if (lane < XL) {
+                            float* xb = mb + ((size_t)cb * 4 + q) * XQ + lane * (KW - 1) * 8;
+#pragma unroll
+                            for (int j = 0; j < KW - 1; ++j) {
+                                *reinterpret_cast<float4*>(xb + j * 8) = make_float4(d[j][0], d[j][1], d[j][2], d[j][3]);
+                                *reinterpret_cast<float4*>(xb + j * 8 + 4) = make_float4(d[j][4], d[j][5], d[j][6], d[j][7]);
+                            }
+                        }
+                    }
+                    named_bar_sync(1 + set, 128);
+                }
+                // ---- pass 2: shifted sums, bias, activation, stores ---------------------------------------------------
+                float* y32c = y32n != nullptr ? y32n + (long long)y * p.ys_h : nullptr;
+                uint4* row_hi = ypn != nullptr ? ypn + (size_t)y * p.Wp_out : nullptr;
+                for (int cb = 0; cb < p.CBLK; ++cb) {
+                    float d[KW][8];
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * p.CSTRIDE, d[j]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + cb * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + cb * 8 + 4);
+                    tmem_ld_wait();
+                    float o[8];
+                    o[0] = d[0][0] + b0.x; o[1] = d[0][1] + b0.y; o[2] = d[0][2] + b0.z; o[3] = d[0][3] + b0.w;
+                    o[4] = d[0][4] + b1.x; o[5] = d[0][5] + b1.y;
+                    o[6] = NC > 6 ? d[0][6] + b1.z : 0.f; o[7] = NC > 6 ? d[0][7] + b1.w : 0.f;
+                    if (KW > 1) {
+                        const float* xn = mb + ((size_t)cb * 4 + ((q + 1) & 3)) * XQ;
+#pragma unroll
+                        for (int j = 1; j < KW; ++j) {
+                            const int sh = j * p.D;
+                            float v[8];
+#pragma unroll
+                            for (int ci = 0; ci < NC; ++ci) v[ci] = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
+                            if (lane + sh >= 32) {  // the tap lives in the next quadrant's first lanes
+                                const float* m = xn + ((lane + sh - 32) * (KW - 1) + (j - 1)) * 8;
+                                const float4 m0 = *reinterpret_cast<const float4*>(m);
+                                const float4 m1 = *reinterpret_cast<const float4*>(m + 4);
+                                v[0] = m0.x; v[1] = m0.y; v[2] = m0.z; v[3] = m0.w; v[4] = m1.x; v[5] = m1.y;
+                                v[6] = m1.z; v[7] = m1.w;
+                            }
+#pragma unroll
+                            for (int ci = 0; ci < NC; ++ci) o[ci] += v[ci];
+                        }
+                    }
+                    if (lane_ok) {
+                        if (p.act == DLWP_ACT_TANH) {
+#pragma unroll
+                            for (int ci = 0; ci < NC; ++ci) o[ci] = tanh_accurate(o[ci]);
+                        } else if (p.act == DLWP_ACT_RELU) {
+#pragma unroll
+                            for (int ci = 0; ci < NC; ++ci) o[ci] = fmaxf(o[ci], 0.f);
+                        }
+                        const int nreal = p.Cout - cb * 8;  // filters of this block that exist (>= NC: all of them)
+                        if (nreal < NC) {
+#pragma unroll
+                            for (int ci = 0; ci < NC; ++ci)
+                                if (ci >= nreal) o[ci] = 0.f;
+                        }
+                        if (y32c != nullptr) {
+                            float* yb = y32c + (long long)(cb * 8) * p.ys_c;
+                            if (nreal >= NC) {
+#pragma unroll
+                                for (int ci = 0; ci < NC; ++ci) yb[(long long)ci * p.ys_c] = o[ci];
+                            } else {
+#pragma unroll
+                                for (int ci = 0; ci < NC; ++ci)
+                                    if (ci < nreal) yb[(long long)ci * p.ys_c] = o[ci];
+                            }
+                        }
+                        if (row_hi != nullptr) {
+                            float amax = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[4]), fabsf(o[5])), fmaxf(fabsf(o[6]), fabsf(o[7]))));
+                            if (!(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);  // outside the fp16 split's range (or NaN)
+                            uint4 vh, vl;
+                            {
+                                const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+                                const __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
+                                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2),
+                                             f3 = __half22float2(h3);
+                                vh.x = *reinterpret_cast<const uint32_t*>(&h0); vh.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                vh.z = *reinterpret_cast<const uint32_t*>(&h2); vh.w = *reinterpret_cast<const uint32_t*>(&h3);
+                                vl.x = pack_half2(o[0] - f0.x, o[1] - f0.y); vl.y = pack_half2(o[2] - f1.x, o[3] - f1.y);
+                                vl.z = pack_half2(o[4] - f2.x, o[5] - f2.y); vl.w = pack_half2(o[6] - f3.x, o[7] - f3.y);
+                            }
+                            uint4* row_lo = row_hi + plane_stride;
+                            row_hi[0] = vh;
+                            row_lo[0] = vl;
+                            if (halo_r) {            // periodic longitude halo of the NEXT layer, right side
+                                row_hi[p.W] = vh;
+                                row_lo[p.W] = vl;
+                            }
+                            if (halo_l) {            // ... and left side
+                                row_hi[-p.W] = vh;
+                                row_lo[-p.W] = vl;
+                            }
+                        }
+                    }
+                    if (row_hi != nullptr) row_hi += 2 * plane_stride;
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[slot]);
+                slot += TC_SETS;
+                if (slot >= p.NACC) { slot -= p.NACC; aph ^= 1; }
+            }
+            g += U.yb - U.ya;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ===================================================================================================================
 // Host side
 // ===================================================================================================================
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static int g_tc_sms = 0;
 
 bool tc_geometry_ok(const DlwpConvDesc& d) {
     if (d.rowwise || d.pre_op || d.dil_h != d.dil_w) return false;
@@ -429,7 +858,54 @@ bool tc_geometry_ok(const DlwpConvDesc& d) {
     return tc_plan_layer(d, &L) == 0;
 }
 
+// Sliding-window schedule of one layer (mode 1); -1 if the geometry does not fit (TMEM columns, shared memory, K steps).
+static int sw_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
+    memset(L, 0, sizeof(*L));
+    if (d.kh != d.kw || (d.kh != 3 && d.kh != 5)) return -1;
+    const int halo_w = d.dil_w * (d.kw - 1), span = d.dil_h * (d.kh - 1);
+    L->mode = 1;
+    L->wpad = halo_w / 2;
+    L->Wp = d.W + halo_w;
+    L->C8 = cdiv(d.Cin, 8);
+    L->planes = 2 * L->C8;
+    if (L->planes > 32) return -1;  // the producer issues at most two copies per lane and row
+    L->CBLK = cdiv(d.Cout, 8);
+    // Many filters: N = filters is wide enough, fold the horizontal taps into K (shifted A views, no shifted sum in the
+    // epilogue).  Few filters: fold them into N so that the MMA N reaches 32..96.
+    L->taps_in_k = d.Cout > 16 ? 1 : 0;
+    const char* env_m = getenv("DLWP_TC_TAPS_IN_K");
+    if (env_m) L->taps_in_k = atoi(env_m) ? 1 : 0;
+    L->kw_eff = L->taps_in_k ? 1 : d.kw;
+    L->CSTRIDE = (!L->taps_in_k && d.Cout == 6) ? 6 : 8;  // 5 taps x 6 filters pack into 32 columns
+    L->NCOLS = cdiv(L->CBLK * L->kw_eff * L->CSTRIDE + (8 - L->CSTRIDE), 16) * 16;
+    if (L->NCOLS > 256) return -1;
+    L->NACC = std::min(SW_MAX_ACC, 512 / L->NCOLS);
+    if (L->NACC < span + 2) return -1;  // rows in flight (span + 1) plus one being drained by the epilogue
+    L->XLK = L->taps_in_k ? halo_w : 0;
+    L->S = L->taps_in_k ? 128 : 128 - halo_w;
+    L->nfull = d.W / L->S;
+    L->rem = d.W - L->nfull * L->S;
+    L->pair = (L->rem > 0 && L->rem + halo_w <= 64) ? 1 : 0;
+    const int units = L->C8 * (L->taps_in_k ? d.kw : 1);
+    L->KS = cdiv(units, 2);
+    if (L->KS > TC_MAX_KSTEPS) return -1;
+    L->G = 1; L->cpg = L->C8; L->MT = 1; L->R_out = 1; L->Rin = 1 + span;
+    L->rowpitch = (uint32_t)(((128 + L->XLK) * 16 + 127) / 128 * 128);
+    L->plane_bytes = L->rowpitch;
+    L->stage_bytes = L->stage_stride = (uint32_t)L->planes * L->rowpitch;
+    L->b_bytes = (uint32_t)(L->KS * d.kh * 2) * (uint32_t)(2 * L->NCOLS * 16);
+    const size_t mailbox = L->kw_eff > 1 ? (size_t)TC_SETS * 2 * L->CBLK * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 : 0;
+    const size_t fixed = (size_t)L->b_bytes + mailbox + (size_t)L->CBLK * 32 + (2 * SW_MAX_STAGES + 2 * SW_MAX_ACC) * 8 + 64 + 1024;
+    const size_t budget = 227 * 1024;
+    if (fixed + L->stage_stride > budget) return -1;
+    L->NS = (int)std::min<size_t>(SW_MAX_STAGES, (budget - fixed) / L->stage_stride);
+    L->smem = (size_t)L->NS * L->stage_stride + fixed;
+    return 0;
+}
+
 int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
+    const char* env_k = getenv("DLWP_TC_KERNEL");  // "flat": the flattened-tile kernel only; default: sliding window first
+    if (!(env_k && !strcmp(env_k, "flat")) && sw_plan_layer(d, L) == 0) return 0;
     memset(L, 0, sizeof(*L));
     const int halo_w = d.dil_w * (d.kw - 1), halo_h = d.dil_h * (d.kh - 1);
     L->wpad = halo_w / 2;
@@ -498,8 +974,61 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
 // Weight image: for every group g and K step ks two units of [NCOLS][8] fp16; a unit = (chunk, vertical tap i) holding
 // w[i][j][c8*8+e][co] at column n = (cb*KW + j)*8 + ci, co = cb*8 + ci.  Odd unit counts pair the last unit with a zero unit
 // that re-reads the previous tap's A rows.
+// Sliding-window weight image: for every K step ks and vertical tap i a hi block then a lo block, each
+// [2 units][NCOLS][8] fp16 (K-major, LBO = NCOLS*16 B between the two 8-channel units).  A unit is (8-channel chunk c8)
+// with all horizontal taps in N, column n = (cb*KW + j)*CSTRIDE + ci, or (c8, horizontal tap j) with N = filters.
+static int sw_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
+                           TcKStep* kst_out) {
+    struct U { int c8, j; bool zero; };
+    std::vector<U> units;
+    for (int c8 = 0; c8 < L.C8; ++c8) {
+        if (L.taps_in_k) for (int j = 0; j < d.kw; ++j) units.push_back({c8, j, false});
+        else units.push_back({c8, -1, false});
+    }
+    if (units.size() & 1) units.push_back({units.back().c8, units.back().j, true});
+    auto aoff = [&](const U& u) {
+        // the zero unit (zero weights) views the lo plane of the last real unit: finite data, positive LBO
+        return (long long)(2 * u.c8 + (u.zero ? 1 : 0)) * L.rowpitch + (long long)(u.j > 0 ? u.j : 0) * d.dil_w * 16;
+    };
+    const size_t block = (size_t)2 * L.NCOLS * 8;  // fp16 elements of one (ks, i, hi|lo) block
+    img->assign((size_t)L.KS * d.kh * 2 * block, __float2half(0.f));
+    for (int ks = 0; ks < L.KS; ++ks) {
+        const U& u0 = units[2 * ks];
+        const U& u1 = units[2 * ks + 1];
+        const long long lbo = aoff(u1) - aoff(u0);
+        if (lbo <= 0 || (lbo >> 4) > 0x3FFF) return -1;
+        // the issuer adds the stage base (in 16-byte units) to this: low word of the A descriptor, LBO field included
+        kst_out[ks].a_off = (uint32_t)((((uint32_t)lbo >> 4) << 16) | ((uint32_t)aoff(u0) >> 4));
+        kst_out[ks].a_lbo = (uint32_t)lbo;
+        for (int i = 0; i < d.kh; ++i)
+            for (int half = 0; half < 2; ++half) {
+                const U& u = half ? u1 : u0;
+                if (u.zero) continue;
+                const size_t bh = ((size_t)(ks * d.kh + i) * 2 + 0) * block + (size_t)half * L.NCOLS * 8;
+                const size_t bl = ((size_t)(ks * d.kh + i) * 2 + 1) * block + (size_t)half * L.NCOLS * 8;
+                for (int cb = 0; cb < L.CBLK; ++cb)
+                    for (int j = (u.j >= 0 ? u.j : 0); j < (u.j >= 0 ? u.j + 1 : d.kw); ++j)
+                        for (int ci = 0; ci < L.CSTRIDE; ++ci) {
+                            const int co = cb * 8 + ci;
+                            if (co >= d.Cout) continue;
+                            const int ncol = (cb * L.kw_eff + (u.j >= 0 ? 0 : j)) * L.CSTRIDE + ci;
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = u.c8 * 8 + e;
+                                if (c >= d.Cin) continue;
+                                const float v = w_host[(((size_t)i * d.kw + j) * d.Cin + c) * d.Cout + co];
+                                const __half h = __float2half_rn(v);
+                                (*img)[bh + (size_t)ncol * 8 + e] = h;
+                                (*img)[bl + (size_t)ncol * 8 + e] = __float2half_rn(v - __half2float(h));
+                            }
+                        }
+            }
+    }
+    return 0;
+}
+
 int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
                     TcKStep* kst_out) {
+    if (L.mode == 1) return sw_pack_weights(d, L, w_host, img, kst_out);
     const size_t per_img = (size_t)L.b_bytes / 2;
     img->assign(2 * per_img, __float2half(0.f));
     for (int g = 0; g < L.G; ++g) {
@@ -557,7 +1086,75 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     return 0;
 }
 
-static int g_tc_sms = 0;
+template <int KH, int KW, int NC>
+static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t stream) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    conv_sw_kernel<KH, KW, NC><<<grid, TC_THREADS, smem, stream>>>(p);
+}
+
+static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
+                     const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream) {
+    if (g_tc_sms == 0) {
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaGetDeviceProperties(&prop, dev);
+        g_tc_sms = prop.multiProcessorCount;
+    }
+    SwParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;
+    p.D = d.dil_w; p.pad_t = d.pad_t;
+    p.S = L.S; p.nfull = L.nfull; p.rem = L.rem; p.pair = L.pair;
+    const bool all_rows = d.row_begin == 0 && d.row_end == 0;
+    p.row0 = all_rows ? 0 : d.row_begin;
+    p.row1 = all_rows ? d.H : d.row_end;
+    const int rows = p.row1 - p.row0, span = d.dil_h * (d.kh - 1);
+    const int groups = L.pair ? cdiv(d.N, 2) : d.N;
+    p.units_per_group = L.pair ? 2 * L.nfull + 1 : L.nfull + (L.rem > 0 ? 1 : 0);
+    // latitude bands per strip: enough units to balance the SMs, few enough that the (KH-1)*dil halo rows re-read at
+    // every band edge stay a small fraction
+    int best_nb = 1;
+    double best_score = -1.0;
+    const char* env_nb = getenv("DLWP_TC_BANDS");
+    for (int nb = 1; nb <= 16 && nb <= rows; ++nb) {
+        const int rb = cdiv(rows, nb);
+        if (cdiv(rows, rb) != nb) continue;
+        const long long total = (long long)groups * p.units_per_group * nb;
+        const double balance = (double)total / (double)(cdiv((int)total, g_tc_sms) * (long long)g_tc_sms);
+        const double reread = (double)rows / (double)(rows + span * nb);
+        const double score = balance * (0.5 + 0.5 * reread);
+        if (score > best_score + 1e-9) { best_score = score; best_nb = nb; }
+    }
+    if (env_nb && atoi(env_nb) > 0) best_nb = std::min(atoi(env_nb), rows);
+    p.RB = cdiv(rows, best_nb);
+    p.nbands = cdiv(rows, p.RB);
+    p.total_units = groups * p.units_per_group * p.nbands;
+    p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
+    p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC;
+    p.planes_in = L.planes;
+    p.rowpitch = L.rowpitch; p.stage_stride = L.stage_stride; p.b_unit16 = (uint32_t)(2 * L.NCOLS); p.b_bytes = L.b_bytes;
+    p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
+    p.act = d.act; p.bias = bias; p.bimg = bimg; p.xp = xp;
+    p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
+    p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
+    for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
+    const int grid = std::min(p.total_units, g_tc_sms);
+    const int nc = L.CSTRIDE == 6 ? 6 : 8;
+    if (getenv("DLWP_TC_DEBUG"))
+        fprintf(stderr, "sw_launch %d->%d k%d: units %d (groups %d x %d strips x %d bands of %d rows) grid %d NS %d NACC %d KS %d smem %zu\n",
+                d.Cin, d.Cout, d.kh, p.total_units, groups, p.units_per_group, p.nbands, p.RB, grid, p.NS, p.NACC, p.KS, L.smem);
+    if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8>(p, grid, L.smem, stream);
+    else if (d.kh == 5 && L.kw_eff == 1) sw_launch_one<5, 1, 8>(p, grid, L.smem, stream);
+    else if (d.kh == 3 && nc == 8) sw_launch_one<3, 3, 8>(p, grid, L.smem, stream);
+    else if (d.kh == 3) sw_launch_one<3, 3, 6>(p, grid, L.smem, stream);
+    else if (d.kh == 5 && nc == 8) sw_launch_one<5, 5, 8>(p, grid, L.smem, stream);
+    else sw_launch_one<5, 5, 6>(p, grid, L.smem, stream);
+    return after_launch("conv_sw_kernel");
+}
 
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream) {
@@ -572,6 +1169,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
         cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     });
+    if (L.mode == 1) return sw_launch(d, L, kst, xp, bimg, bias, y32, yp, wpad_out, planes_out, stream);
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;

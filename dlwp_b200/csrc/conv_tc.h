@@ -27,6 +27,12 @@ struct TcLayer {
     int NACC;              // TMEM accumulator sets (2 = double buffered)
     uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;
     size_t smem;
+    // sliding-window kernel (mode 1, conv_sw_kernel): M tile = 128 consecutive pixels of ONE row; every staged input row
+    // feeds all vertical taps (same A operand -> collector reuse), one TMEM accumulator per output row in flight
+    int mode;              // 0 = flattened-tile kernel (conv_tc_kernel), 1 = sliding window
+    int XLK;               // pixels an A view reaches to the right of its lane (horizontal taps folded into K)
+    int nfull, rem, pair;  // full strips per row, valid outputs of the remainder strip, remainder strips of 2 samples share a tile
+    uint32_t rowpitch;     // bytes of one staged plane row
 };
 
 bool tc_geometry_ok(const DlwpConvDesc& d);
