@@ -504,15 +504,36 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // KH: kernel height (vertical taps), KW: horizontal taps summed by the epilogue (1 = folded into K), NC: filters per
 // 8-filter block that exist (6: the single packed block of a 6-filter layer, else 8)
-template <int KH, int KW, int NC>
+//
+// ST: compile-time copy of the per-layer constants (0 / -1 = take the value from SwParams at run time).  The generic
+// instance serves any layer; the benchmark nets' layers get instances with everything folded, which matters because the
+// single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's critical path.
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_>
+struct SwStatic {
+    static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
+};
+using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
+
+template <int KH, int KW, int NC, class ST>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p) {
+    const int NCOLS = ST::NCOLS ? ST::NCOLS : p.NCOLS;
+    const int KS = ST::KS ? ST::KS : p.KS;
+    const int D = ST::D ? ST::D : p.D;
+    const int CBLK = ST::CBLK ? ST::CBLK : p.CBLK;
+    const int NACC = ST::NCOLS ? (512 / (ST::NCOLS ? ST::NCOLS : 1) > SW_MAX_ACC ? SW_MAX_ACC : 512 / (ST::NCOLS ? ST::NCOLS : 1)) : p.NACC;
+    const int act = ST::ACT >= 0 ? ST::ACT : p.act;
+    const bool has_yp = ST::OUT ? (ST::OUT & 1) != 0 : p.yp != nullptr;
+    const bool has_y32 = ST::OUT ? (ST::OUT & 2) != 0 : p.y32 != nullptr;
+    constexpr int CSTRIDE = NC;  // 6: the single packed block of a 6-filter layer, else 8
+    const uint32_t unit16 = (uint32_t)(2 * NCOLS);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
     unsigned char* bsm = stages + (size_t)p.NS * p.stage_stride;
     float* xch = reinterpret_cast<float*>(bsm + p.b_bytes);  // mailbox [set][parity][block][quadrant][XL][(KW-1)*8]
-    const int XQ = p.XL * (KW - 1) * 8;
-    float* sbias = xch + (size_t)TC_SETS * 2 * p.CBLK * 4 * XQ;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.CBLK * 8);
+    const int XLc = (KW - 1) * D;
+    const int XQ = XLc * (KW - 1) * 8;
+    float* sbias = xch + (size_t)TC_SETS * 2 * CBLK * 4 * XQ;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + CBLK * 8);
     uint64_t* full = bars;                                  // [NS]       bulk copies of a row landed
     uint64_t* empty = bars + SW_MAX_STAGES;                 // [NS]       the row's MMAs have read the stage
     uint64_t* acc_full = bars + 2 * SW_MAX_STAGES;          // [NACC]     output row complete in TMEM
@@ -525,17 +546,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     // waited on a barrier), and the scheduler favours higher warp ids among eligible warps.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int W_PROD = TC_SETS * 4, W_MMA = TC_SETS * 4 + 1;
-    const int SPAN = (KH - 1) * p.D;
+    const int SPAN = (KH - 1) * D;
 
     for (uint32_t i = tid; i < p.b_bytes / 16; i += TC_THREADS)
         reinterpret_cast<uint4*>(bsm)[i] = reinterpret_cast<const uint4*>(p.bimg)[i];
     for (uint32_t i = tid; i < (uint32_t)p.NS * p.stage_stride / 16; i += TC_THREADS)  // lanes past a row's end stay finite
         reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < p.CBLK * 8; i += TC_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    for (int i = tid; i < CBLK * 8; i += TC_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
     fence_proxy_async();
     if (tid == 0) {
         for (int s = 0; s < p.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < p.NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
         fence_mbar_init();
     }
     if (warp == W_MMA) {
@@ -595,12 +616,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
         // =============================== MMA issuer (warp-convergent, one elected lane issues) ===========================
         const bool leader = elect_one();
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, sm_100 descriptor version
-        const uint32_t b_lbo_field = ((p.NCOLS * 16u) >> 4) << 16;
+        const uint32_t b_lbo_field = ((NCOLS * 16u) >> 4) << 16;
         const uint32_t b16 = smem_u32(bsm) >> 4;
         const uint32_t pitch16 = p.rowpitch >> 4;
         const uint32_t stages16 = smem_u32(stages) >> 4, stride16 = p.stage_stride >> 4;
-        const uint32_t unit16 = p.b_unit16;
-        int s = 0;
+                int s = 0;
         uint32_t ph = 0;
         int sl0 = 0;        // accumulator slot of the output row that starts at the current input row
         uint32_t aph = 0;   // parity of the accumulator ring's current lap
@@ -619,13 +639,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                 uint32_t dcol[KH];
 #pragma unroll
                 for (int i = 0; i < KH; ++i) {
-                    int si = sl - i * p.D;
-                    if (si < 0) si += p.NACC;
-                    dcol[i] = tmem + (uint32_t)(si * p.NCOLS);
+                    int si = sl - i * D;
+                    if (si < 0) si += NACC;
+                    dcol[i] = tmem + (uint32_t)(si * NCOLS);
                 }
                 const bool interior = (r >= SPAN) && (r < nout);
                 if (interior) {
-                    for (int ks = 0; ks < p.KS; ++ks) {
+                    for (int ks = 0; ks < KS; ++ks) {
                         const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
                         const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
                         const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
@@ -652,14 +672,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                         }
                     }
                 } else {
-                    for (int ks = 0; ks < p.KS; ++ks) {
+                    for (int ks = 0; ks < KS; ++ks) {
                         const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;
                         const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
                         const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
                         const uint32_t bks = b_lbo_field | (b16 + (uint32_t)(ks * KH) * 2u * unit16);
 #pragma unroll
                         for (int i = 0; i < KH; ++i) {
-                            const int yo = r - i * p.D;  // output row (relative to the unit) this tap contributes to
+                            const int yo = r - i * D;  // output row (relative to the unit) this tap contributes to
                             if (yo < 0 || yo >= nout) continue;
                             const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
                             const uint64_t bl = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i + 1) * unit16);
@@ -676,29 +696,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                     umma_commit(&empty[s]);
                     if (r >= SPAN) {  // the last tap of output row r - SPAN has been issued
                         int sd = sl - SPAN;
-                        if (sd < 0) sd += p.NACC;
+                        if (sd < 0) sd += NACC;
                         umma_commit(&acc_full[sd]);
                     }
                 }
                 if (++s == p.NS) { s = 0; ph ^= 1; }
-                if (++sl == p.NACC) { sl = 0; ap ^= 1; }
+                if (++sl == NACC) { sl = 0; ap ^= 1; }
             }
             // the next unit's first output row follows this unit's last one in the accumulator ring
             sl0 += nout;
-            while (sl0 >= p.NACC) { sl0 -= p.NACC; aph ^= 1; }
+            while (sl0 >= NACC) { sl0 -= NACC; aph ^= 1; }
         }
     } else {
         // =============================== epilogue: 4 sets x 4 quadrant warps, rows dealt round robin ===================
         // Output rows are numbered G = 0, 1, 2, ... across the units of this CTA; set s takes G = s, s + 4, ... so its
         // accumulator slot advances by 4 (mod NACC) per row, whatever the unit boundaries are.
         const int q = warp & 3, set = warp >> 2;
-        const int XL = p.XL;
-        float* xset = xch + (size_t)set * 2 * p.CBLK * 4 * XQ;
+        const int XL = XLc;
+        float* xset = xch + (size_t)set * 2 * CBLK * 4 * XQ;
         const int Hout = p.H + 2 * TC_HPAD;
         const size_t plane_stride = (size_t)Hout * p.Wp_out;  // uint4 units
         int slot = set;
         uint32_t aph = 0;
-        while (slot >= p.NACC) { slot -= p.NACC; aph ^= 1; }
+        while (slot >= NACC) { slot -= NACC; aph ^= 1; }
         int g = 0, lrow = 0;
         SwUnit U;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -710,21 +730,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
             const int x = U.x0 + l;
             const bool lane_ok = (n >= 0) && (l < (seg ? U.nvb : U.nva)) && (x < p.W);
             const bool halo_r = x < p.wpad_out, halo_l = x >= p.W - p.wpad_out;
-            float* y32n = p.y32 != nullptr ? p.y32 + (long long)max(n, 0) * p.ys_n + x : nullptr;
-            uint4* ypn = p.yp != nullptr
+            float* y32n = has_y32 ? p.y32 + (long long)max(n, 0) * p.ys_n + x : nullptr;
+            uint4* ypn = has_yp
                              ? reinterpret_cast<uint4*>(p.yp) + ((size_t)max(n, 0) * p.planes_out * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
                              : nullptr;
             for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
                 mbar_wait(&acc_full[slot], aph);
                 tc_fence_after();
-                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.NCOLS);
-                float* mb = xset + (size_t)(lrow & 1) * p.CBLK * 4 * XQ;
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOLS);
+                float* mb = xset + (size_t)(lrow & 1) * CBLK * 4 * XQ;
                 if (KW > 1) {
                     // ---- pass 1: the taps that the previous quadrant's last lanes need -> mailbox ----------------------
-                    for (int cb = 0; cb < p.CBLK; ++cb) {
+                    for (int cb = 0; cb < CBLK; ++cb) {
                         float d[KW > 1 ? KW - 1 : 1][8];
 #pragma unroll
-                        for (int j = 1; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * p.CSTRIDE, d[j - 1]);
+                        for (int j = 1; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * CSTRIDE, d[j - 1]);
                         tmem_ld_wait();
                         if (lane < XL) {
                             float* xb = mb + ((size_t)cb * 4 + q) * XQ + lane * (KW - 1) * 8;
@@ -738,12 +758,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                     named_bar_sync(1 + set, 128);
                 }
                 // ---- pass 2: shifted sums, bias, activation, stores ---------------------------------------------------
-                float* y32c = y32n != nullptr ? y32n + (long long)y * p.ys_h : nullptr;
-                uint4* row_hi = ypn != nullptr ? ypn + (size_t)y * p.Wp_out : nullptr;
-                for (int cb = 0; cb < p.CBLK; ++cb) {
+                float* y32c = has_y32 ? y32n + (long long)y * p.ys_h : nullptr;
+                uint4* row_hi = has_yp ? ypn + (size_t)y * p.Wp_out : nullptr;
+                for (int cb = 0; cb < CBLK; ++cb) {
                     float d[KW][8];
 #pragma unroll
-                    for (int j = 0; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * p.CSTRIDE, d[j]);
+                    for (int j = 0; j < KW; ++j) tmem_ld8(tbase + (cb * KW + j) * CSTRIDE, d[j]);
                     const float4 b0 = *reinterpret_cast<const float4*>(sbias + cb * 8);
                     const float4 b1 = *reinterpret_cast<const float4*>(sbias + cb * 8 + 4);
                     tmem_ld_wait();
@@ -755,7 +775,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                         const float* xn = mb + ((size_t)cb * 4 + ((q + 1) & 3)) * XQ;
 #pragma unroll
                         for (int j = 1; j < KW; ++j) {
-                            const int sh = j * p.D;
+                            const int sh = j * D;
                             float v[8];
 #pragma unroll
                             for (int ci = 0; ci < NC; ++ci) v[ci] = __shfl_down_sync(0xffffffffu, d[j][ci], sh);
@@ -771,10 +791,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                         }
                     }
                     if (lane_ok) {
-                        if (p.act == DLWP_ACT_TANH) {
+                        if (act == DLWP_ACT_TANH) {
 #pragma unroll
                             for (int ci = 0; ci < NC; ++ci) o[ci] = tanh_accurate(o[ci]);
-                        } else if (p.act == DLWP_ACT_RELU) {
+                        } else if (act == DLWP_ACT_RELU) {
 #pragma unroll
                             for (int ci = 0; ci < NC; ++ci) o[ci] = fmaxf(o[ci], 0.f);
                         }
@@ -784,7 +804,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                             for (int ci = 0; ci < NC; ++ci)
                                 if (ci >= nreal) o[ci] = 0.f;
                         }
-                        if (y32c != nullptr) {
+                        if (has_y32) {
                             float* yb = y32c + (long long)(cb * 8) * p.ys_c;
                             if (nreal >= NC) {
 #pragma unroll
@@ -795,7 +815,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                                     if (ci < nreal) yb[(long long)ci * p.ys_c] = o[ci];
                             }
                         }
-                        if (row_hi != nullptr) {
+                        if (has_yp) {
                             float amax = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
                             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[4]), fabsf(o[5])), fmaxf(fabsf(o[6]), fabsf(o[7]))));
                             if (!(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);  // outside the fp16 split's range (or NaN)
@@ -823,12 +843,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                             }
                         }
                     }
-                    if (row_hi != nullptr) row_hi += 2 * plane_stride;
+                    if (has_yp) row_hi += 2 * plane_stride;
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[slot]);
                 slot += TC_SETS;
-                if (slot >= p.NACC) { slot -= p.NACC; aph ^= 1; }
+                if (slot >= NACC) { slot -= NACC; aph ^= 1; }
             }
             g += U.yb - U.ya;
         }
@@ -1086,13 +1106,13 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     return 0;
 }
 
-template <int KH, int KW, int NC>
+template <int KH, int KW, int NC, class ST = SwGeneric>
 static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t stream) {
     static std::once_flag once;
     std::call_once(once, [] {
-        cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
-    conv_sw_kernel<KH, KW, NC><<<grid, TC_THREADS, smem, stream>>>(p);
+    conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p);
 }
 
 static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
@@ -1147,7 +1167,16 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     if (getenv("DLWP_TC_DEBUG"))
         fprintf(stderr, "sw_launch %d->%d k%d: units %d (groups %d x %d strips x %d bands of %d rows) grid %d NS %d NACC %d KS %d smem %zu\n",
                 d.Cin, d.Cout, d.kh, p.total_units, groups, p.units_per_group, p.nbands, p.RB, grid, p.NS, p.NACC, p.KS, L.smem);
-    if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8>(p, grid, L.smem, stream);
+    // fully folded instances for the benchmark nets' layers (SwStatic<NCOLS, KS, D, CBLK, ACT, OUT>)
+    const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
+    const bool generic_only = getenv("DLWP_TC_GENERIC") != nullptr;
+    if (!generic_only && d.kh == 3 && L.kw_eff == 1 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 2 && L.CBLK == 4 &&
+        d.act == DLWP_ACT_TANH && out_mode == 1)            // Net A conv1: 6 -> 32, 3x3 dilation 2, tanh, P-layout output
+        sw_launch_one<3, 1, 8, SwStatic<32, 2, 2, 4, DLWP_ACT_TANH, 1>>(p, grid, L.smem, stream);
+    else if (!generic_only && d.kh == 5 && L.kw_eff == 5 && nc == 6 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 1 &&
+             L.CBLK == 1 && d.act == DLWP_ACT_LINEAR && out_mode == 3)  // Net A conv2: 32 -> 6, 5x5, fp32 series + feedback
+        sw_launch_one<5, 5, 6, SwStatic<32, 2, 1, 1, DLWP_ACT_LINEAR, 3>>(p, grid, L.smem, stream);
+    else if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 5 && L.kw_eff == 1) sw_launch_one<5, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 3 && nc == 8) sw_launch_one<3, 3, 8>(p, grid, L.smem, stream);
     else if (d.kh == 3) sw_launch_one<3, 3, 6>(p, grid, L.smem, stream);
