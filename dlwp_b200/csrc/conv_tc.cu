@@ -508,9 +508,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // ST: compile-time copy of the per-layer constants (0 / -1 = take the value from SwParams at run time).  The generic
 // instance serves any layer; the benchmark nets' layers get instances with everything folded, which matters because the
 // single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's critical path.
-template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_>
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0>
 struct SwStatic {
     static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
+    static constexpr int FULL = FULL_;  // 1: Cout == CBLK * NC, no partial filter block
 };
 using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
 
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
             const int nrows = U.yb - U.ya + SPAN;
             for (int r = 0; r < nrows; ++r) {
                 if (lane == 0) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait_relaxed(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], row_bytes);
                 }
                 __syncwarp();
@@ -631,17 +632,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
             const int nrows = nout + SPAN;
             int sl = sl0;           // slot of (virtual) output row r; rows r >= nout are never started
             uint32_t ap = aph;
+            uint32_t dh[(KH - 1) * (ST::D ? ST::D : 1) + 1];  // dh[k]: accumulator columns of output row r - k
+#pragma unroll
+            for (int k = 0; k <= (KH - 1) * (ST::D ? ST::D : 1); ++k) dh[k] = tmem;
+            uint32_t dcur = tmem + (uint32_t)(sl0 * NCOLS);
             for (int r = 0; r < nrows; ++r) {
                 if (r < nout) mbar_wait(&acc_empty[sl], ap ^ 1);  // output row r starts accumulating: slot must be drained
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sbase16 = stages16 + (uint32_t)s * stride16;
                 uint32_t dcol[KH];
+                if constexpr (ST::D != 0) {  // rolling register file of the live rows' accumulator columns: no index math
 #pragma unroll
-                for (int i = 0; i < KH; ++i) {
-                    int si = sl - i * D;
-                    if (si < 0) si += NACC;
-                    dcol[i] = tmem + (uint32_t)(si * NCOLS);
+                    for (int k = (KH - 1) * (ST::D ? ST::D : 1); k > 0; --k) dh[k] = dh[k - 1];
+                    dh[0] = dcur;
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) dcol[i] = dh[i * (ST::D ? ST::D : 1)];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) {
+                        int si = sl - i * D;
+                        if (si < 0) si += NACC;
+                        dcol[i] = tmem + (uint32_t)(si * NCOLS);
+                    }
                 }
                 const bool interior = (r >= SPAN) && (r < nout);
                 if (interior) {
@@ -701,7 +714,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                     }
                 }
                 if (++s == p.NS) { s = 0; ph ^= 1; }
-                if (++sl == NACC) { sl = 0; ap ^= 1; }
+                dcur += (uint32_t)NCOLS;
+                if (++sl == NACC) { sl = 0; ap ^= 1; dcur = tmem; }
             }
             // the next unit's first output row follows this unit's last one in the accumulator ring
             sl0 += nout;
@@ -735,7 +749,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                              ? reinterpret_cast<uint4*>(p.yp) + ((size_t)max(n, 0) * p.planes_out * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
                              : nullptr;
             for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
-                mbar_wait(&acc_full[slot], aph);
+                mbar_wait_relaxed(&acc_full[slot], aph);
                 tc_fence_after();
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOLS);
                 float* mb = xset + (size_t)(lrow & 1) * CBLK * 4 * XQ;
@@ -760,6 +774,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                 // ---- pass 2: shifted sums, bias, activation, stores ---------------------------------------------------
                 float* y32c = has_y32 ? y32n + (long long)y * p.ys_h : nullptr;
                 uint4* row_hi = has_yp ? ypn + (size_t)y * p.Wp_out : nullptr;
+#pragma unroll(ST::CBLK ? ST::CBLK : 1)
                 for (int cb = 0; cb < CBLK; ++cb) {
                     float d[KW][8];
 #pragma unroll
@@ -798,7 +813,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
 #pragma unroll
                             for (int ci = 0; ci < NC; ++ci) o[ci] = fmaxf(o[ci], 0.f);
                         }
-                        const int nreal = p.Cout - cb * 8;  // filters of this block that exist (>= NC: all of them)
+                        const int nreal = ST::FULL ? NC : p.Cout - cb * 8;  // filters of this block that exist (>= NC: all)
                         if (nreal < NC) {
 #pragma unroll
                             for (int ci = 0; ci < NC; ++ci)
@@ -816,9 +831,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                             }
                         }
                         if (has_yp) {
-                            float amax = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
-                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[4]), fabsf(o[5])), fmaxf(fabsf(o[6]), fabsf(o[7]))));
-                            if (!(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);  // outside the fp16 split's range (or NaN)
+                            float amax = 0.f;
+                            if (act != DLWP_ACT_TANH) {
+                                amax = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
+                                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[4]), fabsf(o[5])), fmaxf(fabsf(o[6]), fabsf(o[7]))));
+                            }
+                            // outside the fp16 split's range (or NaN); tanh output cannot be (a NaN input was flagged upstream)
+                            if (act != DLWP_ACT_TANH && !(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);
                             uint4 vh, vl;
                             {
                                 const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
@@ -1171,11 +1190,11 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
     const bool generic_only = getenv("DLWP_TC_GENERIC") != nullptr;
     if (!generic_only && d.kh == 3 && L.kw_eff == 1 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 2 && L.CBLK == 4 &&
-        d.act == DLWP_ACT_TANH && out_mode == 1)            // Net A conv1: 6 -> 32, 3x3 dilation 2, tanh, P-layout output
-        sw_launch_one<3, 1, 8, SwStatic<32, 2, 2, 4, DLWP_ACT_TANH, 1>>(p, grid, L.smem, stream);
+        d.Cout == 32 && d.act == DLWP_ACT_TANH && out_mode == 1)            // Net A conv1: 6 -> 32, 3x3 dilation 2, tanh, P-layout output
+        sw_launch_one<3, 1, 8, SwStatic<32, 2, 2, 4, DLWP_ACT_TANH, 1, 1>>(p, grid, L.smem, stream);
     else if (!generic_only && d.kh == 5 && L.kw_eff == 5 && nc == 6 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 1 &&
              L.CBLK == 1 && d.act == DLWP_ACT_LINEAR && out_mode == 3)  // Net A conv2: 32 -> 6, 5x5, fp32 series + feedback
-        sw_launch_one<5, 5, 6, SwStatic<32, 2, 1, 1, DLWP_ACT_LINEAR, 3>>(p, grid, L.smem, stream);
+        sw_launch_one<5, 5, 6, SwStatic<32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1>>(p, grid, L.smem, stream);
     else if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 5 && L.kw_eff == 1) sw_launch_one<5, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 3 && nc == 8) sw_launch_one<3, 3, 8>(p, grid, L.smem, stream);

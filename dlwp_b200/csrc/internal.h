@@ -147,6 +147,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a TMA that never completes (bad descriptor) raises a flag the host can read (dlwp_debug_flags) and
 // lets the kernel finish with garbage instead of hanging the GPU.
+// try_wait with a suspend-time hint: the warp may sleep up to ~hint ns per attempt instead of re-polling (idle epilogue /
+// producer warps otherwise burn issue slots and power in the poll loop while the MMA issuer is the critical path).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (1u << 20)) {
+            atomicOr(&g_device_flags, 1);
+            break;
+        }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {

@@ -174,6 +174,31 @@ __global__ void __launch_bounds__(128) probe(int mode, int iters, int N, long lo
                         if (leader) mma_ss(dv[t], term == 2 ? ac[6 + (t & 1)] : ac[t], bv[term == 1 ? 8 : 0], idesc);
             }
         }
+        if (mode >= 100) {
+#define GROUPS(NG)                                                                                          \
+    for (int i = 0; i < iters; i += 30) {                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 30; ++u) {                                                    \
+            if (leader) {                                                                                   \
+                constexpr int n = NG;                                                                       \
+                const int g = u / n, j = u % n;                                                             \
+                if (n == 1) mma_ss(dv[u % 5], av[g & 7], bv[u % 10], idesc);                                \
+                else if (j == 0) mma_ss_fill(dv[u % 5], av[g & 7], bv[u % 10], idesc);                      \
+                else if (j == n - 1) mma_ss_last(dv[u % 5], av[g & 7], bv[u % 10], idesc);                  \
+                else mma_ss_use(dv[u % 5], av[g & 7], bv[u % 10], idesc);                                   \
+            }                                                                                               \
+        }                                                                                                   \
+    }
+            switch (mode - 100) {
+                case 1: { GROUPS(1) } break;
+                case 2: { GROUPS(2) } break;
+                case 3: { GROUPS(3) } break;
+                case 5: { GROUPS(5) } break;
+                case 6: { GROUPS(6) } break;
+                case 10: { GROUPS(10) } break;
+                case 15: { GROUPS(15) } break;
+                case 30: { GROUPS(30) } break;
+            }
+        }
         __syncwarp();
         if (leader) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s32(bar)) : "memory");
@@ -215,6 +240,9 @@ int main(int argc, char** argv) {
         {1, 96, "SS N=96 chain"}, {1, 128, "SS N=128 chain"}, {1, 256, "SS N=256 chain"},
         {7, 64, "TS N=64 6 rot"}, {6, 128, "TS N=128 chain"}, {6, 256, "TS N=256 chain"},
         {5, 64, "SS N=64 collector x10"}, {4, 64, "SS N=64 same A x10 no hint"},
+        {101, 32, "group 1 (no reuse)"}, {102, 32, "collector groups of 2"}, {103, 32, "collector groups of 3"}, {105, 32, "collector groups of 5"},
+        {106, 32, "collector groups of 6"}, {110, 32, "collector groups of 10"}, {115, 32, "collector groups of 15"}, {130, 32, "collector groups of 30"},
+        {102, 64, "N=64 groups of 2"}, {105, 64, "N=64 groups of 5"}, {110, 64, "N=64 groups of 10"}, {105, 96, "N=96 groups of 5"}, {103, 96, "N=96 groups of 3"},
     };
     long long* d_cycles; int* d_flag;
     cudaMalloc(&d_cycles, 148 * 8); cudaMalloc(&d_flag, 4);
