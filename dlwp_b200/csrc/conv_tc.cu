@@ -447,6 +447,7 @@ struct SwParams {
     const float* bias;
     const __half* bimg;
     const __half* xp;
+    int in_plane0, in_planes_total, out_plane0;  // channel windows of the source / destination P images
     float* y32; long long ys_n, ys_c, ys_h;
     __half* yp; int Wp_out, wpad_out, planes_out;
     TcKStep kst[TC_MAX_KSTEPS];
@@ -593,7 +594,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                 const int seg = c >= p.planes_in ? 1 : 0;
                 const int q = c - seg * p.planes_in;
                 const int n = seg ? U.n1 : U.n0;
-                src[k] = p.xp + ((((size_t)max(n, 0) * p.planes_in + q) * Halloc + (size_t)(U.ya - p.pad_t + TC_HPAD)) * p.Wp + U.x0) * 8;
+                src[k] = p.xp + ((((size_t)max(n, 0) * p.in_planes_total + p.in_plane0 + q) * Halloc +
+                                  (size_t)(U.ya - p.pad_t + TC_HPAD)) * p.Wp + U.x0) * 8;
                 dsto[k] = (uint32_t)q * p.rowpitch + (uint32_t)seg * 1024u;
                 len[k] = seg ? lenB : lenA;
             }
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
             const bool halo_r = x < p.wpad_out, halo_l = x >= p.W - p.wpad_out;
             float* y32n = has_y32 ? p.y32 + (long long)max(n, 0) * p.ys_n + x : nullptr;
             uint4* ypn = has_yp
-                             ? reinterpret_cast<uint4*>(p.yp) + ((size_t)max(n, 0) * p.planes_out * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
+                             ? reinterpret_cast<uint4*>(p.yp) + (((size_t)max(n, 0) * p.planes_out + p.out_plane0) * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
                              : nullptr;
             for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
                 mbar_wait_relaxed(&acc_full[slot], aph);
@@ -876,6 +878,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ===================================================================================================================
+// Data movers on P images: MaxPooling2D(2) / UpSampling2D(2) / channel-window copy (skip connections of the U-Net).
+// One thread per destination pixel and 8-channel chunk (a hi and a lo 16-byte vector); the destination's periodic halo
+// columns are written with the interior.  HBM-bound byte movers: 32 B read (128 B for the pooling) + 32 B written per
+// thread, coalesced along x.
+// ===================================================================================================================
+__device__ __forceinline__ void p_unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
+    const __half2* hh = reinterpret_cast<const __half2*>(&h);
+    const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(hh[k]), b = __half22float2(ll[k]);
+        v[2 * k] = a.x + b.x;      // exact: hi and lo are an exact split of an fp32 value
+        v[2 * k + 1] = a.y + b.y;
+    }
+}
+__device__ __forceinline__ void p_pack8(const float (&v)[8], uint4& h, uint4& l) {
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 hh = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        const float2 f = __half22float2(hh);
+        hp[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        lp[k] = pack_half2(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+    }
+}
+
+template <int KIND>  // 0 copy, 1 maxpool 2x2 stride 2 (floor), 2 nearest upsample x2
+__global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int C8, int Hs,
+                                                  int Ws, int wpad_s, int src_plane0, int src_planes_total, int Hd, int Wd,
+                                                  int wpad_d, int dst_plane0, int dst_planes_total) {
+    const int Wps = Ws + 2 * wpad_s, Wpd = Wd + 2 * wpad_d;
+    const long long Has = Hs + 2 * TC_HPAD, Had = Hd + 2 * TC_HPAD;
+    const long long total = (long long)N * C8 * Hd * Wd;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % Wd);
+        long long t = idx / Wd;
+        const int y = (int)(t % Hd);
+        t /= Hd;
+        const int c8 = (int)(t % C8);
+        const int n = (int)(t / C8);
+        const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + 2 * c8) * Has + TC_HPAD) * Wps + wpad_s;
+        const uint4* sl = sh + Has * Wps;
+        uint4 vh, vl;
+        if (KIND == 0) {
+            vh = sh[(long long)y * Wps + x];
+            vl = sl[(long long)y * Wps + x];
+        } else if (KIND == 2) {
+            vh = sh[(long long)(y >> 1) * Wps + (x >> 1)];
+            vl = sl[(long long)(y >> 1) * Wps + (x >> 1)];
+        } else {
+            float m[8];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const long long o = (long long)(2 * y + dy) * Wps + 2 * x + dx;
+                    float v[8];
+                    p_unpack8(sh[o], sl[o], v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) m[e] = (dy | dx) ? fmaxf(m[e], v[e]) : v[e];
+                }
+            p_pack8(m, vh, vl);
+        }
+        uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + 2 * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + x;
+        uint4* dl = dh + Had * Wpd;
+        dh[0] = vh;
+        dl[0] = vl;
+        if (x < wpad_d) { dh[Wd] = vh; dl[Wd] = vl; }
+        if (x >= Wd - wpad_d) { dh[-Wd] = vh; dl[-Wd] = vl; }
+    }
+}
+
+int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
+                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream) {
+    const int C8 = planes / 2;
+    int Hd = Hs, Wd = Ws;
+    if (kind == DLWP_OP_MAXPOOL) { Hd = Hs / 2; Wd = Ws / 2; }
+    if (kind == DLWP_OP_UPSAMPLE) { Hd = Hs * 2; Wd = Ws * 2; }
+    const long long total = (long long)N * C8 * Hd * Wd;
+    if (total == 0) return 0;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    if (kind == DLWP_OP_MAXPOOL)
+        p_ew_kernel<1><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+    else if (kind == DLWP_OP_UPSAMPLE)
+        p_ew_kernel<2><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+    else
+        p_ew_kernel<0><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+    return after_launch("p_ew_kernel");
 }
 
 // ===================================================================================================================
@@ -1135,7 +1231,8 @@ static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t
 }
 
 static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
-                     const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream) {
+                     const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
+                     const TcWindow& win) {
     if (g_tc_sms == 0) {
         cudaDeviceProp prop;
         int dev = 0;
@@ -1178,6 +1275,8 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     p.rowpitch = L.rowpitch; p.stage_stride = L.stage_stride; p.b_unit16 = (uint32_t)(2 * L.NCOLS); p.b_bytes = L.b_bytes;
     p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
     p.act = d.act; p.bias = bias; p.bimg = bimg; p.xp = xp;
+    p.in_plane0 = win.in_plane0; p.in_planes_total = win.in_planes_total ? win.in_planes_total : L.planes;
+    p.out_plane0 = win.out_plane0;
     p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
     p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
     for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
@@ -1205,7 +1304,8 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
 }
 
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
-              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream) {
+              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
+              const TcWindow& win) {
     static std::once_flag once;
     std::call_once(once, [] {
         cudaDeviceProp prop;
@@ -1217,7 +1317,10 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
         cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
         cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
     });
-    if (L.mode == 1) return sw_launch(d, L, kst, xp, bimg, bias, y32, yp, wpad_out, planes_out, stream);
+    if (L.mode == 1) return sw_launch(d, L, kst, xp, bimg, bias, y32, yp, wpad_out, planes_out, stream, win);
+    DLWP_REQUIRE(win.in_plane0 == 0 && win.out_plane0 == 0 && (win.in_planes_total == 0 || win.in_planes_total == L.planes) &&
+                     (yp == nullptr || planes_out == 2 * cdiv(d.Cout, 8)),
+                 DLWP_ESHAPE, "the flattened-tile tensor-core kernel does not take channel windows");
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;

@@ -39,8 +39,21 @@ bool tc_geometry_ok(const DlwpConvDesc& d);
 int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L);
 int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
                     TcKStep* kst_out);
+// Channel windows of P images (slice_layer / concatenate without copies): the conv reads planes
+// [in_plane0, in_plane0 + L.planes) of a source image that has in_planes_total planes per sample (0 = L.planes) and writes
+// planes [out_plane0, ...) of a destination image with planes_out planes per sample.
+struct TcWindow {
+    int in_plane0 = 0, in_planes_total = 0, out_plane0 = 0;
+};
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
-              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream);
+              const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
+              const TcWindow& win = TcWindow());
+// Data movers on P images (the U-Net's MaxPooling2D(2), UpSampling2D(2) and skip-connection copies): `planes` planes
+// starting at src_plane0 of the source -> planes starting at dst_plane0 of the destination; the destination's periodic
+// halo (wpad_d columns per side) is written with the interior.  kind: DLWP_OP_COPY / DLWP_OP_MAXPOOL / DLWP_OP_UPSAMPLE.
+// (Hs, Ws): source image size.
+int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
+                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream);
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0 = 0, int row1 = 0);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,

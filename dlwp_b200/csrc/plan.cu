@@ -138,6 +138,11 @@ static DlwpConvDesc conv_desc_of(const DlwpPlan* pl, const DlwpOpDesc& op, int N
 }
 
 // Decide whether the whole plan can run as a tensor-core chain and size its packed buffers.
+//
+// Chain = every activation lives in P layout (fp16 hi/lo planes, 8 channels per plane pair).  Convs run on the tcgen05
+// kernels; MaxPooling2D(2), UpSampling2D(2) and the skip-connection copies of the U-Net run as data movers on P images;
+// slice_layer / concatenate are plane windows (channel offsets must be multiples of 8).  Anything else (stand-alone
+// padding, RowConnected2D, pool/upsample fused into a conv, ...) keeps the whole plan on the fp32 kernels.
 static int tc_setup(DlwpPlan* pl) {
     // Default: use the tensor-core chain whenever the whole plan is eligible.  DLWP_MATH=ffma (or any conv op forced to
     // an FFMA/direct implementation) keeps the fp32 FFMA kernels.
@@ -147,31 +152,49 @@ static int tc_setup(DlwpPlan* pl) {
         if (op.kind == DLWP_OP_CONV && op.impl != DLWP_IMPL_AUTO && op.impl != DLWP_IMPL_TC) return 0;
     const int nops = (int)pl->ops.size();
     std::vector<TcLayer> layers(nops);
-    std::vector<int> writer(pl->buffers.size(), -1);
-    bool windowed = false;
+    std::vector<int> wpad(pl->buffers.size(), -1);
+    std::vector<char> is_src(pl->buffers.size(), 0), written(pl->buffers.size(), 0);
+    bool windowed = false, movers = false, windows = false;
+    auto chunk_window_ok = [](int c0, int c, int C) { return c0 % 8 == 0 && (c % 8 == 0 || c0 + c == C); };
+    written[pl->input_buf] = 1;
     for (int i = 0; i < nops; ++i) {
         const DlwpOpDesc& op = pl->ops[i];
         const Buffer& s = pl->buffers[op.src];
         const Buffer& t = pl->buffers[op.dst];
-        if (op.kind != DLWP_OP_CONV) return 0;
         if (op.row_begin || op.row_end) windowed = true;
-        if (op.src == pl->input_buf && (op.row_begin || op.row_end)) {
-            const int lo = std::max(0, op.row_begin - op.pad_t);
-            const int hi = std::min(s.d.H, op.row_end - op.pad_t + op.dil_h * (op.kh - 1));
-            if (pl->tc_in_row1 == 0) { pl->tc_in_row0 = lo; pl->tc_in_row1 = hi; }
-            else { pl->tc_in_row0 = std::min(pl->tc_in_row0, lo); pl->tc_in_row1 = std::max(pl->tc_in_row1, hi); }
+        if (!written[op.src]) return 0;  // source must be the input or the result of an earlier op
+        is_src[op.src] = 1;
+        written[op.dst] = 1;
+        if (op.kind == DLWP_OP_CONV) {
+            if (op.src == pl->input_buf && (op.row_begin || op.row_end)) {
+                const int lo = std::max(0, op.row_begin - op.pad_t);
+                const int hi = std::min(s.d.H, op.row_end - op.pad_t + op.dil_h * (op.kh - 1));
+                if (pl->tc_in_row1 == 0) { pl->tc_in_row0 = lo; pl->tc_in_row1 = hi; }
+                else { pl->tc_in_row0 = std::min(pl->tc_in_row0, lo); pl->tc_in_row1 = std::max(pl->tc_in_row1, hi); }
+            }
+            if (!chunk_window_ok(op.src_c0, op.src_c, s.d.C) || !chunk_window_ok(op.dst_c0, op.Cout, t.d.C)) return 0;
+            const bool win = op.src_c0 != 0 || op.src_c != s.d.C || op.dst_c0 != 0 || op.Cout != t.d.C;
+            DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
+            if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
+            if (win && layers[i].mode != 1) return 0;  // only the sliding-window kernel takes channel windows
+            windows = windows || win;
+            if (wpad[op.src] >= 0 && wpad[op.src] != layers[i].wpad) return 0;  // all conv readers must want the same halo
+            wpad[op.src] = layers[i].wpad;
+        } else if (op.kind == DLWP_OP_MAXPOOL || op.kind == DLWP_OP_UPSAMPLE || op.kind == DLWP_OP_COPY) {
+            if (op.src_c0 % 8 || op.src_c % 8 || op.dst_c0 % 8) return 0;
+            if (op.kind == DLWP_OP_MAXPOOL && ((s.d.H | s.d.W) & 1)) return 0;
+            movers = true;
+        } else {
+            return 0;
         }
-        if (op.src_c0 != 0 || op.src_c != s.d.C || op.dst_c0 != 0 || op.Cout != t.d.C) return 0;
-        DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
-        if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
-        if (op.src != pl->input_buf && writer[op.src] < 0) return 0;  // source must be the input or a conv result
-        if (writer[op.dst] >= 0) return 0;
-        writer[op.dst] = i;
-        Buffer& sb = pl->buffers[op.src];
-        if (sb.wpad >= 0 && sb.wpad != layers[i].wpad) return 0;     // all readers must want the same halo
-        sb.wpad = layers[i].wpad;
-        sb.planes = layers[i].planes;
     }
+    if (windowed && (movers || windows)) return 0;  // latitude-band plans: plain conv stacks only (for now)
+    for (size_t b = 0; b < pl->buffers.size(); ++b)
+        if (is_src[b]) {
+            Buffer& B = pl->buffers[b];
+            B.wpad = wpad[b] >= 0 ? wpad[b] : 0;  // read only by data movers: no halo needed
+            B.planes = 2 * ((B.d.C + 7) / 8);
+        }
     pl->tc_pdst.assign(nops, -1);
     for (int i = 0; i < nops; ++i)
         if (pl->buffers[pl->ops[i].dst].wpad >= 0) pl->tc_pdst[i] = pl->ops[i].dst;
@@ -179,11 +202,15 @@ static int tc_setup(DlwpPlan* pl) {
     const int last_out = pl->outputs.back();
     const Buffer& in = pl->buffers[pl->input_buf];
     const Buffer& lo = pl->buffers[last_out];
+    int last_writer = -1, n_writers = 0;
+    for (int i = 0; i < nops; ++i)
+        if (pl->ops[i].dst == last_out) { last_writer = i; ++n_writers; }
     // (not for latitude bands: the halo rows of the next input arrive as fp32 from the neighbours and are re-packed)
-    if (!windowed && writer[last_out] >= 0 && pl->tc_pdst[writer[last_out]] < 0 && lo.d.C == in.d.C &&
-        lo.d.H == in.d.H && lo.d.W == in.d.W) {
-        pl->tc_feedback_op = writer[last_out];
-        pl->tc_pdst[writer[last_out]] = pl->input_buf;
+    if (!windowed && n_writers == 1 && pl->ops[last_writer].kind == DLWP_OP_CONV && pl->tc_pdst[last_writer] < 0 &&
+        pl->ops[last_writer].dst_c0 == 0 && pl->ops[last_writer].Cout == lo.d.C && lo.d.C == in.d.C && lo.d.H == in.d.H &&
+        lo.d.W == in.d.W && in.wpad >= 0) {
+        pl->tc_feedback_op = last_writer;
+        pl->tc_pdst[last_writer] = pl->input_buf;
     }
     for (Buffer& b : pl->buffers)
         if (b.wpad >= 0) {
@@ -214,20 +241,30 @@ static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel
 
 static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
     const DlwpOpDesc& op = pl->ops[i];
-    const Weight& w = pl->weights[op.weight_id];
-    DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);
     const Buffer& s = pl->buffers[op.src];
     const Buffer& t = pl->buffers[op.dst];
+    if (op.kind != DLWP_OP_CONV) {  // data mover on P images
+        if (pl->tc_pdst[i] < 0) return 0;  // nobody reads the result in P layout
+        const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
+        return tc_ew_launch(op.kind, s.P, pb.P, N, 2 * (op.src_c / 8), s.d.H, s.d.W, s.wpad, 2 * (op.src_c0 / 8), s.planes,
+                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream);
+    }
+    const Weight& w = pl->weights[op.weight_id];
+    DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);
     DlwpConvDesc d = conv_desc_of(pl, op, N);
-    float* y32 = (t.d.kind == DLWP_BUF_OUTPUT) ? t.ptr : nullptr;
+    float* y32 = (t.d.kind == DLWP_BUF_OUTPUT) ? t.ptr + (long long)op.dst_c0 * t.d.H * t.d.W : nullptr;
     __half* yp = nullptr;
     int wpad_out = 0, planes_out = 0;
+    TcWindow win;
+    win.in_plane0 = 2 * (op.src_c0 / 8);
+    win.in_planes_total = s.planes;
     if (pl->tc_pdst[i] >= 0) {
         const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
+        win.out_plane0 = pl->tc_pdst[i] == op.dst ? 2 * (op.dst_c0 / 8) : 0;
     }
     return tc_launch(d, pl->tc_layers[i], w.kst, s.P, w.bimg, w.has_bias ? w.b : nullptr, y32, yp, wpad_out,
-                     planes_out, stream);
+                     planes_out, stream, win);
 }
 
 static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_packed) {

@@ -170,3 +170,54 @@ def test_one_degree_grid_rows_wider_than_a_tma_box(env):
     nat, torch = env
     _check(nat, torch, 1, 12, 22, 360, 32, 3, 2, nat.ACT_TANH, 11)
     _check(nat, torch, 1, 32, 16, 360, 12, 5, 1, nat.ACT_LINEAR, 12)
+
+
+@pytest.mark.parametrize('cs,N', [((12, 24, 48), 3), ((12, 36, 104), 2)])
+def test_unet_skip_model_runs_as_a_tensor_core_chain(env, cs, N):
+    """Net B (examples/train_functional.py:248-275): convs on tcgen05, MaxPooling2D / UpSampling2D / skip-connection
+    copies as data movers on P images, slice_layer / concatenate as plane windows.  fp16 hi/lo split keeps fp32-level
+    accuracy: same 5e-5 bar as the fp32 path; a 6-step rollout (feedback re-packed by the last conv) stays under 1e-4."""
+    nat, torch = env
+    from dlwp_b200.engine import CompiledNet
+    from oracle import rollout as OR
+    from tests.helpers import build_functional_pair
+    dlwp, onet = build_functional_pair(cs, skip=True, integration_steps=1, seed=3)
+    x0 = np.random.RandomState(4).standard_normal((N,) + cs).astype(np.float32)
+    eng = CompiledNet(dlwp.model, N, impl='tc')
+    assert eng.uses_tensor_cores()
+    y = eng.predict(x0)[0]
+    assert nat.lib().dlwp_debug_flags() == 0
+    ref = onet.forward(x0.astype(np.float64))
+    assert rel_err(y, ref) < 5e-5
+    got = eng.rollout_host(x0, 6)
+    refs = OR.functional_predict_timeseries(lambda p: onet.forward(p), x0.astype(np.float64), 6, n_steps=1, dtype=np.float64)
+    assert got.shape == refs.shape
+    assert rel_err(got, refs) < 1e-4
+    xd = torch.from_numpy(x0).cuda()
+    g1 = eng.rollout_device(xd, 4, use_graph=True).cpu().numpy()
+    g0 = eng.rollout_device(xd, 4, use_graph=False).cpu().numpy()
+    np.testing.assert_array_equal(g0, g1)
+    np.testing.assert_array_equal(g1, got[:4])
+    eng.close()
+    ffma = CompiledNet(dlwp.model, N, force_ffma=True)
+    assert not ffma.uses_tensor_cores()
+    assert rel_err(ffma.predict(x0)[0], y.astype(np.float64)) < 5e-5
+    ffma.close()
+
+
+def test_unet_full_grid_on_tensor_cores(env):
+    """BASELINE.json configs[2] shape (12, 180, 360): one application vs the torch-CPU tier-1 oracle."""
+    nat, torch = env
+    from dlwp_b200.engine import CompiledNet
+    from tests.helpers import build_functional_pair
+    cs = (12, 180, 360)
+    dlwp, onet = build_functional_pair(cs, skip=True, integration_steps=1, seed=5)
+    x0 = np.random.RandomState(6).standard_normal((2,) + cs).astype(np.float32)
+    eng = CompiledNet(dlwp.model, 2, impl='tc')
+    assert eng.uses_tensor_cores()
+    y = eng.predict(x0)[0]
+    assert nat.lib().dlwp_debug_flags() == 0
+    with torch.no_grad():
+        ref = onet.forward(torch.from_numpy(x0)).numpy()
+    assert rel_err(y, ref.astype(np.float64)) < 5e-5
+    eng.close()
