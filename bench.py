@@ -48,6 +48,21 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
 
 
+def ncu_traffic(kernel, batch):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r01_ncu_traffic.json, taken at the bench batch); None if there is no capture for
+    this kernel / batch."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
+    try:
+        table = json.load(open(path))
+    except (IOError, OSError, ValueError):
+        return None
+    for row in table:
+        if row.get('batch') == batch and kernel.startswith(row.get('kernel_prefix', '\0')) and row.get('layer', '') in kernel:
+            return row.get('dram_bytes_per_launch')
+    return None
+
+
 def make_inputs(batch):
     return np.random.RandomState(0).standard_normal((batch,) + STATE).astype(np.float32)
 
@@ -303,14 +318,15 @@ def run_ours(args, rank, world, local_rank):
     for i, (name, cin, cout, k) in enumerate(layers):
         ms_i = eng.profile_op(B, i, it)
         alg = conv_alg_bytes(B, cin, cout, k)
-        timed.append({'kernel': ('conv_tc_kernel ' if tc else 'conv_ffma_kernel ') + name, 'ms_per_launch': ms_i,
+        tc_name = 'conv_tc_kernel ' if os.environ.get('DLWP_TC_KERNEL') == 'flat' else 'conv_sw_kernel '
+        timed.append({'kernel': (tc_name if tc else 'conv_ffma_kernel ') + name, 'ms_per_launch': ms_i,
                       'algorithmic_bytes_per_launch': alg, 'achieved_gbs': alg / (ms_i * 1e-3) / 1e9,
                       'useful_tflops': 2.0 * B * 91 * 180 * cin * cout * k * k / (ms_i * 1e-3) / 1e12})
     dom = max(timed, key=lambda r: r['ms_per_launch'])
     step_gbs = BYTES_PER_SAMPLE_STEP * B / (ms / K * 1e-3) / 1e9
     roofline = {
         'kernel': dom['kernel'], 'bound': 'hbm', 'achieved': dom['achieved_gbs'], 'peak': peaks['hbm_gbs'],
-        'unit': 'GB/s', 'frac': dom['achieved_gbs'] / peaks['hbm_gbs'], 'traffic': None,
+        'unit': 'GB/s', 'frac': dom['achieved_gbs'] / peaks['hbm_gbs'], 'traffic': ncu_traffic(dom['kernel'], B),
         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peak_kind == 'measured' else 'fallback 6650 GB/s',
         'algorithmic_bytes_per_launch': dom['algorithmic_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
         'math': 'tcgen05 f16 hi/lo split x3 -> fp32 TMEM accumulators' if tc else 'fp32 FFMA2',

@@ -448,6 +448,7 @@ struct SwParams {
     const __half* bimg;
     const __half* xp;
     int in_plane0, in_planes_total, out_plane0;  // channel windows of the source / destination P images
+    int debug;  // DLWP_SW_DEBUG: 1 = epilogue only waits/arrives, 2 = issuer only commits (bottleneck triage; wrong results)
     float* y32; long long ys_n, ys_c, ys_h;
     __half* yp; int Wp_out, wpad_out, planes_out;
     TcKStep kst[TC_MAX_KSTEPS];
@@ -659,7 +660,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
                     }
                 }
                 const bool interior = (r >= SPAN) && (r < nout);
-                if (interior) {
+                if (p.debug & 2) {
+                } else if (interior) {
                     for (int ks = 0; ks < KS; ++ks) {
                         const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
                         const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
@@ -753,6 +755,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
             for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
                 mbar_wait_relaxed(&acc_full[slot], aph);
                 tc_fence_after();
+                if (p.debug & 1) {
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[slot]);
+                    slot += TC_SETS;
+                    if (slot >= NACC) { slot -= NACC; aph ^= 1; }
+                    continue;
+                }
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOLS);
                 float* mb = xset + (size_t)(lrow & 1) * CBLK * 4 * XQ;
                 if (KW > 1) {
@@ -1275,6 +1284,10 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     p.rowpitch = L.rowpitch; p.stage_stride = L.stage_stride; p.b_unit16 = (uint32_t)(2 * L.NCOLS); p.b_bytes = L.b_bytes;
     p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
     p.act = d.act; p.bias = bias; p.bimg = bimg; p.xp = xp;
+    {
+        const char* env_dbg = getenv("DLWP_SW_DEBUG");
+        p.debug = env_dbg ? atoi(env_dbg) : 0;
+    }
     p.in_plane0 = win.in_plane0; p.in_planes_total = win.in_planes_total ? win.in_planes_total : L.planes;
     p.out_plane0 = win.out_plane0;
     p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
