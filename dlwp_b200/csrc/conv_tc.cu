@@ -1307,6 +1307,9 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     else if (!generic_only && d.kh == 5 && L.kw_eff == 5 && nc == 6 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 1 &&
              L.CBLK == 1 && d.act == DLWP_ACT_LINEAR && out_mode == 3)  // Net A conv2: 32 -> 6, 5x5, fp32 series + feedback
         sw_launch_one<5, 5, 6, SwStatic<32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1>>(p, grid, L.smem, stream);
+    else if (!generic_only && d.kh == 5 && L.kw_eff == 5 && nc == 6 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 1 &&
+             L.CBLK == 1 && d.act == DLWP_ACT_LINEAR && out_mode == 2)  // ... the same layer in a latitude band (fp32 only)
+        sw_launch_one<5, 5, 6, SwStatic<32, 2, 1, 1, DLWP_ACT_LINEAR, 2, 1>>(p, grid, L.smem, stream);
     else if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 5 && L.kw_eff == 1) sw_launch_one<5, 1, 8>(p, grid, L.smem, stream);
     else if (d.kh == 3 && nc == 8) sw_launch_one<3, 3, 8>(p, grid, L.smem, stream);

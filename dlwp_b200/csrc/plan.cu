@@ -85,6 +85,9 @@ struct DlwpPlan {
     std::vector<int> tc_pdst;      // buffer whose P image op i writes (-1: none)
     int tc_feedback_op = -1;       // op that also serves as the packer of the next iteration's input
     int tc_in_row0 = 0, tc_in_row1 = 0;  // rows of the input the (row-windowed) convs read: only those are packed
+    // latitude band: rows [tc_band_row0, tc_band_row1) of the next input are re-packed by the feedback conv itself; only the
+    // halo rows that arrive as fp32 from the neighbours ([tc_in_row0, band_row0) and [band_row1, tc_in_row1)) are packed
+    int tc_band_row0 = 0, tc_band_row1 = 0;
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     long long halo_cap = 0;
@@ -205,12 +208,15 @@ static int tc_setup(DlwpPlan* pl) {
     int last_writer = -1, n_writers = 0;
     for (int i = 0; i < nops; ++i)
         if (pl->ops[i].dst == last_out) { last_writer = i; ++n_writers; }
-    // (not for latitude bands: the halo rows of the next input arrive as fp32 from the neighbours and are re-packed)
-    if (!windowed && n_writers == 1 && pl->ops[last_writer].kind == DLWP_OP_CONV && pl->tc_pdst[last_writer] < 0 &&
+    // (latitude bands: the conv re-packs its own band rows; the halo rows arrive as fp32 from the neighbours and are
+    // packed after the exchange, see run_ops_tc)
+    if (n_writers == 1 && pl->ops[last_writer].kind == DLWP_OP_CONV && pl->tc_pdst[last_writer] < 0 &&
         pl->ops[last_writer].dst_c0 == 0 && pl->ops[last_writer].Cout == lo.d.C && lo.d.C == in.d.C && lo.d.H == in.d.H &&
         lo.d.W == in.d.W && in.wpad >= 0) {
         pl->tc_feedback_op = last_writer;
         pl->tc_pdst[last_writer] = pl->input_buf;
+        pl->tc_band_row0 = pl->ops[last_writer].row_begin;
+        pl->tc_band_row1 = pl->ops[last_writer].row_end;
     }
     for (Buffer& b : pl->buffers)
         if (b.wpad >= 0) {
@@ -273,6 +279,14 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_pa
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
                                (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1);
         if (rc) return rc;
+    } else if (pl->tc_band_row1 > 0) {  // latitude band: pack the halo rows received from the neighbours
+        const int lo[2] = {pl->tc_in_row0, pl->tc_band_row1}, hi[2] = {pl->tc_band_row0, pl->tc_in_row1};
+        for (int k = 0; k < 2; ++k)
+            if (hi[k] > lo[k]) {
+                int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
+                                       (long long)in.d.H * in.d.W, in.d.W, stream, lo[k], hi[k]);
+                if (rc) return rc;
+            }
     }
     for (size_t i = 0; i < pl->ops.size(); ++i) {
         int rc = run_one_tc(pl, (int)i, N, stream);
