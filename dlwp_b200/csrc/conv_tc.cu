@@ -1017,6 +1017,9 @@ static int sw_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     // Many filters: N = filters is wide enough, fold the horizontal taps into K (shifted A views, no shifted sum in the
     // epilogue).  Few filters: fold them into N so that the MMA N reaches 32..96.
     L->taps_in_k = d.Cout > 16 ? 1 : 0;
+    // ... unless there are many input channels and still few enough filters for the accumulator ring: with taps in K the
+    // K loop is kw times longer (kw * C8 / 2 steps of N = Cout MMAs), and the single issuing warp is the bottleneck
+    if (L->taps_in_k && L->C8 >= 8 && 512 / (cdiv(cdiv(d.Cout, 8) * d.kw * 8, 16) * 16) >= span + 2) L->taps_in_k = 0;
     const char* env_m = getenv("DLWP_TC_TAPS_IN_K");
     if (env_m) L->taps_in_k = atoi(env_m) ? 1 : 0;
     L->kw_eff = L->taps_in_k ? 1 : d.kw;
