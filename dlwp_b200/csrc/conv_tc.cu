@@ -1413,3 +1413,35 @@ int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, con
 }
 
 }  // namespace dlwp
+
+// ---- host-only test hooks (include/dlwp_b200.h) -------------------------------------------------------------------------
+extern "C" int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out) {
+    using namespace dlwp;
+    DLWP_REQUIRE(desc && out && n_out >= 16, DLWP_EINVAL, "bad argument");
+    TcLayer L;
+    DLWP_REQUIRE(tc_geometry_ok(*desc) && tc_plan_layer(*desc, &L) == 0, DLWP_ESHAPE,
+                 "geometry not supported by the tensor-core conv kernels");
+    const int32_t v[16] = {L.mode, L.taps_in_k, L.NCOLS, L.NACC, L.KS, L.NS, L.S, L.nfull, L.rem, L.pair, (int32_t)L.smem,
+                           (int32_t)L.b_bytes, L.CBLK, L.CSTRIDE, L.planes, (int32_t)L.rowpitch};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return 0;
+}
+
+extern "C" int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16_t* image, int64_t image_cap,
+                                      uint32_t* kstep_words, int32_t kstep_cap) {
+    using namespace dlwp;
+    if (!desc || !kernel || !image || !kstep_words) return DLWP_EINVAL;
+    TcLayer L;
+    if (!tc_geometry_ok(*desc) || tc_plan_layer(*desc, &L) != 0) return DLWP_ESHAPE;
+    std::vector<__half> img;
+    TcKStep kst[TC_MAX_KSTEPS];
+    if (tc_pack_weights(*desc, L, kernel, &img, kst) != 0) return DLWP_ESHAPE;
+    const int nks = L.mode == 1 ? L.KS : L.G * L.KS;
+    if ((int64_t)img.size() > image_cap || 2 * nks > kstep_cap) return DLWP_EINVAL;
+    memcpy(image, img.data(), img.size() * sizeof(__half));
+    for (int i = 0; i < nks; ++i) {
+        kstep_words[2 * i] = kst[i].a_off;
+        kstep_words[2 * i + 1] = kst[i].a_lbo;
+    }
+    return (int64_t)img.size();
+}

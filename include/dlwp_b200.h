@@ -233,6 +233,15 @@ int64_t dlwp_kernel_launch_count(void);
 int dlwp_debug_flags(void);
 /* Name of the implementation AUTO would choose for this descriptor ("direct", "ffma", "ffma_tma"). */
 const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
+/* Host-only test hooks of the tensor-core path (no GPU needed).
+ * dlwp_debug_tc_plan: the schedule the planner picks for one layer. out[0..15] = mode (0 flattened tiles, 1 sliding window),
+ *   taps_in_k, NCOLS, NACC, KS, NS, S, nfull, rem, pair, shared-memory bytes, weight-image bytes, CBLK, CSTRIDE, planes,
+ *   row pitch.  Returns 0, or DLWP_ESHAPE when the layer cannot run on the tensor-core kernels.
+ * dlwp_debug_tc_pack: the packed fp16 hi/lo weight image of that schedule (kernel in Keras layout (kh,kw,Cin,Cout), HOST
+ *   pointer) and the low words of its A-operand descriptors per K step; returns the number of fp16 elements written. */
+int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out);
+int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16_t* image, int64_t image_cap,
+                           uint32_t* kstep_words, int32_t kstep_cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,117 @@
+"""
+Host-side logic of the tensor-core path, no GPU: the sliding-window planner's invariants (TMEM accumulator ring, shared
+memory, strip pairing) over the benchmark nets' layers, and the packed hi/lo weight image decoded back to the Keras kernel
+through the documented layout (conv_tc.cu `sw_pack_weights`).
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.helpers import conv_desc
+
+LAYERS = [  # (Cin, H, W, Cout, k, dil)  Net A, Net B (skip U-Net), test geometries
+    (6, 91, 180, 32, 3, 2), (32, 91, 180, 6, 5, 1),
+    (12, 180, 360, 32, 3, 2), (16, 90, 180, 64, 3, 1), (32, 45, 90, 128, 3, 1), (128, 90, 180, 32, 3, 1),
+    (64, 180, 360, 16, 3, 2), (32, 180, 360, 12, 5, 1),
+    (8, 7, 124, 8, 3, 1), (12, 14, 40, 12, 5, 1), (16, 17, 44, 64, 3, 1),
+]
+
+
+@pytest.fixture(scope='module')
+def nat():
+    from dlwp_b200 import _native
+    _native.lib()
+    return _native
+
+
+def _desc(nat, cin, H, W, cout, k, d, N=4):
+    pad = d * (k - 1) // 2
+    desc, _, _ = conv_desc(nat, N, cin, H, W, cout, k, k, d, ((pad, pad), (pad, pad)), nat.PAD_ZERO, nat.PAD_PERIODIC,
+                           nat.ACT_LINEAR, nat.IMPL_TC)
+    return desc
+
+
+def _plan(nat, desc):
+    out = (ctypes.c_int32 * 16)()
+    rc = nat.lib().dlwp_debug_tc_plan(ctypes.byref(desc), out, 16)
+    keys = ('mode', 'taps_in_k', 'NCOLS', 'NACC', 'KS', 'NS', 'S', 'nfull', 'rem', 'pair', 'smem', 'b_bytes', 'CBLK', 'CSTRIDE',
+            'planes', 'rowpitch')
+    return rc, dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize('layer', LAYERS)
+def test_sliding_window_plan_invariants(nat, layer):
+    cin, H, W, cout, k, d = layer
+    rc, L = _plan(nat, _desc(nat, cin, H, W, cout, k, d))
+    assert rc == 0
+    assert L['mode'] == 1                                   # every benchmark layer runs on the sliding-window kernel
+    span, halo_w = d * (k - 1), d * (k - 1)
+    assert L['NCOLS'] % 16 == 0 and L['NCOLS'] <= 256       # tcgen05 N granularity for M = 128
+    assert L['NACC'] * L['NCOLS'] <= 512                     # accumulator ring fits the 512 TMEM columns
+    assert L['NACC'] >= span + 2                             # rows in flight + one being drained
+    assert L['smem'] <= 227 * 1024 and L['NS'] >= 1
+    assert L['planes'] == 2 * ((cin + 7) // 8) <= 32
+    kw_eff = 1 if L['taps_in_k'] else k
+    assert L['NCOLS'] >= L['CBLK'] * kw_eff * L['CSTRIDE']
+    assert L['S'] == (128 if L['taps_in_k'] else 128 - halo_w)
+    assert L['nfull'] * L['S'] + L['rem'] == W
+    assert L['pair'] == int(0 < L['rem'] and L['rem'] + halo_w <= 64)
+    assert L['rowpitch'] % 128 == 0 and L['rowpitch'] >= (128 + (halo_w if L['taps_in_k'] else 0)) * 16
+    units = ((cin + 7) // 8) * (k if L['taps_in_k'] else 1)
+    assert L['KS'] == (units + 1) // 2
+    assert L['b_bytes'] == L['KS'] * k * 2 * (2 * L['NCOLS'] * 16)
+
+
+def test_unsupported_geometries_are_refused(nat):
+    rc, _ = _plan(nat, _desc(nat, 6, 20, 36, 8, 7, 1))       # 7x7 kernel
+    assert rc == nat.ESHAPE if hasattr(nat, 'ESHAPE') else rc != 0
+
+
+@pytest.mark.parametrize('layer', [(6, 91, 180, 32, 3, 2), (32, 91, 180, 6, 5, 1), (12, 14, 40, 12, 5, 1), (24, 9, 60, 40, 3, 1)])
+def test_weight_image_decodes_to_the_keras_kernel(nat, layer):
+    cin, H, W, cout, k, d = layer
+    desc = _desc(nat, cin, H, W, cout, k, d)
+    rc, L = _plan(nat, desc)
+    assert rc == 0 and L['mode'] == 1
+    rng = np.random.RandomState(sum(layer))
+    w = rng.standard_normal((k, k, cin, cout)).astype(np.float32)
+    cap = L['b_bytes'] // 2
+    img = np.zeros(cap, np.uint16)
+    kst = np.zeros(2 * L['KS'], np.uint32)
+    n = nat.lib().dlwp_debug_tc_pack(ctypes.byref(desc), w.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                     img.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), cap,
+                                     kst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 2 * L['KS'])
+    assert n == cap
+    img = img.view(np.float16).astype(np.float64).reshape(L['KS'], k, 2, 2, L['NCOLS'], 8)   # [ks][tap i][hi|lo][unit][col][e]
+    C8 = (cin + 7) // 8
+    units = [(c8, j) for c8 in range(C8) for j in (range(k) if L['taps_in_k'] else [-1])]
+    rebuilt = np.zeros((k, k, C8 * 8, cout))
+    seen = np.zeros((k, k, C8 * 8, cout), int)
+    for ks in range(L['KS']):
+        for half in range(2):
+            u = 2 * ks + half
+            if u >= len(units):                              # the zero unit that pads an odd unit count
+                assert not img[ks, :, :, half].any()
+                continue
+            c8, j = units[u]
+            for i in range(k):
+                for co in range(cout):
+                    cb, ci = divmod(co, 8)
+                    for jj in ([j] if j >= 0 else range(k)):
+                        col = (cb * (1 if j >= 0 else k) + (0 if j >= 0 else jj)) * L['CSTRIDE'] + ci
+                        val = img[ks, i, 0, half, col] + img[ks, i, 1, half, col]     # hi + lo, 8 channels
+                        rebuilt[i, jj, c8 * 8:c8 * 8 + 8, co] += val
+                        seen[i, jj, c8 * 8:c8 * 8 + 8, co] += 1
+    assert (seen == 1).all()                                 # every (tap, channel, filter) has exactly one home
+    np.testing.assert_allclose(rebuilt[:, :, :cin], w, rtol=0, atol=2.0 ** -21 * np.abs(w).max())   # fp16 hi + lo: 22 bits
+    assert not rebuilt[:, :, cin:].any()                     # padded channels carry zero weights
+    # total image mass: nothing else is stored anywhere
+    np.testing.assert_allclose(img.sum(), w.astype(np.float64).sum(), atol=1e-3)
+    # A-operand descriptor words: (LBO >> 4) << 16 | offset >> 4, LBO = distance between the two units of the K step
+    for ks in range(L['KS']):
+        word, lbo = int(kst[2 * ks]), int(kst[2 * ks + 1])
+        assert word >> 16 == lbo >> 4 and lbo > 0 and lbo % 16 == 0
+        c8, j = units[2 * ks]
+        assert (word & 0xFFFF) * 16 == 2 * c8 * L['rowpitch'] + max(j, 0) * d * 16
