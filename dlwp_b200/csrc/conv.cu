@@ -496,6 +496,32 @@ int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dim
     return 0;
 }
 
+// Generic tiled tensor map over 8-byte elements (the tensor-core path views a P image as 16-byte pixel chunks = 2 elements):
+// rank <= 5, dims fastest first, strides_bytes[i] = stride of dimension i + 1.  Returns nonzero (and sets the error string)
+// when the driver refuses the descriptor, so callers can fall back to plain bulk copies.
+int encode_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
+    static encode_tiled_t fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_t>(ptr);
+    });
+    DLWP_REQUIRE(fn != nullptr, DLWP_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdims[5] = {1, 1, 1, 1, 1}, gstr[4] = {0, 0, 0, 0};
+    cuuint32_t gbox[5] = {1, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DLWP_REQUIRE(r == CUDA_SUCCESS, DLWP_ESHAPE, "cuTensorMapEncodeTiled (u64, rank %d) failed with CUresult %d", rank, (int)r);
+    return 0;
+}
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -448,6 +448,7 @@ struct SwParams {
     const __half* bimg;
     const __half* xp;
     int in_plane0, in_planes_total, out_plane0;  // channel windows of the source / destination P images
+    int use_tma;  // 1: the producer stages rows with tensor-map loads (one per row and unit) instead of per-plane bulk copies
     int debug;  // DLWP_SW_DEBUG: 1 = epilogue only waits/arrives, 2 = issuer only commits (bottleneck triage; wrong results)
     float* y32; long long ys_n, ys_c, ys_h;
     __half* yp; int Wp_out, wpad_out, planes_out;
@@ -518,7 +519,8 @@ struct SwStatic {
 using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
 
 template <int KH, int KW, int NC, class ST>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full,
+                                                                const __grid_constant__ CUtensorMap map_pair) {
     const int NCOLS = ST::NCOLS ? ST::NCOLS : p.NCOLS;
     const int KS = ST::KS ? ST::KS : p.KS;
     const int D = ST::D ? ST::D : p.D;
@@ -573,7 +575,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     const uint32_t tmem = *tmem_slot;
     const int Halloc = p.H + 2 * TC_HPAD;
 
-    if (warp == W_PROD) {
+    if (warp == W_PROD && p.use_tma) {
+        // =============================== producer, tensor-map flavour ===================================================
+        // One tiled load per input row and unit brings all planes of the strip: box (128 px, 1 row, planes) for a full
+        // strip, (64 px, 1 row, 2 samples, planes) for a paired remainder strip -- the box order makes the stage layout
+        // [plane][segment][pixel][8 ch] either way.  Columns past the padded row end and the absent partner sample of an odd
+        // batch are out of bounds: zero filled (and counted by complete_tx).  ~15 instructions per row instead of ~10 per
+        // plane: with per-plane bulk copies the producer's own instruction stream capped the load path at 4 TB/s.
+        if (lane == 0) {
+            prefetch_tensormap(&map_full);
+            prefetch_tensormap(&map_pair);
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t row_bytes = (uint32_t)p.planes_in * p.rowpitch;
+            SwUnit U;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                if (!sw_decode(p, u, U)) continue;
+                const int nrows = U.yb - U.ya + SPAN;
+                int row = U.ya - p.pad_t + TC_HPAD;
+                const int plane = U.n0 * p.in_planes_total + p.in_plane0;
+                for (int r = 0; r < nrows; ++r, ++row) {
+                    mbar_wait_relaxed(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], row_bytes);
+                    unsigned char* dst = stages + (size_t)s * p.stage_stride;
+                    if (!U.paired) tma_load_3d(dst, &map_full, &full[s], U.x0 * 2, row, plane);
+                    else tma_load_4d(dst, &map_pair, &full[s], U.x0 * 2, row, U.n0, p.in_plane0);
+                    if (++s == p.NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == W_PROD) {
         // =============================== producer: one bulk copy per (plane, segment) and input row =======================
         int s = 0;
         uint32_t ph = 0;  // parity of the stage ring's current lap
@@ -1233,13 +1264,15 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     return 0;
 }
 
+static CUtensorMap g_sw_map_full, g_sw_map_pair;  // the maps of the launch being issued (copied into the kernel parameters)
+
 template <int KH, int KW, int NC, class ST = SwGeneric>
 static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t stream) {
     static std::once_flag once;
     std::call_once(once, [] {
         cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
-    conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p);
+    conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p, g_sw_map_full, g_sw_map_pair);
 }
 
 static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
@@ -1298,9 +1331,25 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
     const int grid = std::min(p.total_units, g_tc_sms);
     const int nc = L.CSTRIDE == 6 ? 6 : 8;
+    // Tensor-map producer for layers whose staged row is exactly 128 pixels per plane (taps in N) and has several planes.
+    p.use_tma = 0;
+    if (L.XLK == 0 && L.rowpitch == 2048 && L.planes >= 4 && !getenv("DLWP_SW_NO_TMA")) {
+        const uint64_t Halloc = (uint64_t)d.H + 2 * TC_HPAD, row_b = (uint64_t)L.Wp * 16, plane_b = Halloc * row_b;
+        const uint64_t dims3[3] = {(uint64_t)L.Wp * 2, Halloc, (uint64_t)d.N * p.in_planes_total};
+        const uint64_t str3[2] = {row_b, plane_b};
+        const uint32_t box3[3] = {256, 1, (uint32_t)L.planes};
+        const uint64_t dims4[4] = {(uint64_t)L.Wp * 2, Halloc, (uint64_t)d.N, (uint64_t)p.in_planes_total};
+        const uint64_t str4[3] = {row_b, plane_b * p.in_planes_total, plane_b};
+        const uint32_t box4[4] = {128, 1, 2, (uint32_t)L.planes};
+        if (encode_tensor_map_u64(&g_sw_map_full, xp, 3, dims3, str3, box3) == 0 &&
+            (!L.pair || encode_tensor_map_u64(&g_sw_map_pair, xp, 4, dims4, str4, box4) == 0)) {
+            if (!L.pair) g_sw_map_pair = g_sw_map_full;
+            p.use_tma = 1;
+        }
+    }
     if (getenv("DLWP_TC_DEBUG"))
-        fprintf(stderr, "sw_launch %d->%d k%d: units %d (groups %d x %d strips x %d bands of %d rows) grid %d NS %d NACC %d KS %d smem %zu\n",
-                d.Cin, d.Cout, d.kh, p.total_units, groups, p.units_per_group, p.nbands, p.RB, grid, p.NS, p.NACC, p.KS, L.smem);
+        fprintf(stderr, "sw_launch %d->%d k%d: units %d (groups %d x %d strips x %d bands of %d rows) grid %d NS %d NACC %d KS %d smem %zu tma %d\n",
+                d.Cin, d.Cout, d.kh, p.total_units, groups, p.units_per_group, p.nbands, p.RB, grid, p.NS, p.NACC, p.KS, L.smem, p.use_tma);
     // fully folded instances for the benchmark nets' layers (SwStatic<NCOLS, KS, D, CBLK, ACT, OUT>)
     const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
     const bool generic_only = getenv("DLWP_TC_GENERIC") != nullptr;

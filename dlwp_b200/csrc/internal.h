@@ -70,6 +70,8 @@ int adam_step(float* w, const float* g, float* m, float* v, long long n, float l
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                          const uint32_t box[4]);
+int encode_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
 
 }  // namespace dlwp
 
@@ -163,7 +165,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (++spins > (1u << 20)) {
+        if (++spins > (1u << 17)) {  // bounded (<~ 3 s): a broken pipeline raises the flag instead of hanging the GPU
             atomicOr(&g_device_flags, 1);
             break;
         }
@@ -184,6 +186,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
         "[%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
