@@ -88,6 +88,8 @@ SYMBOLS = {
     'dlwp_debug_flags': (ctypes.c_int, []),
     'dlwp_conv2d_impl_name': (ctypes.c_char_p, [ctypes.POINTER(ConvDesc)]),
     'dlwp_debug_tc_plan': (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(i32), i32]),
+    'dlwp_debug_sw_cover': (ctypes.c_int, [ctypes.POINTER(ConvDesc), i32, ctypes.POINTER(i32), ctypes.c_int64,
+                                           ctypes.POINTER(i32), i32]),
     'dlwp_debug_tc_pack': (ctypes.c_int64, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_uint16), ctypes.c_int64,
                                             ctypes.POINTER(ctypes.c_uint32), i32]),

@@ -1,24 +1,25 @@
-// Tensor-core (tcgen05 / TMEM / TMA) implementation of the fused periodic-pad + Conv2D layer.
+// Tensor-core (tcgen05 / TMEM / TMA) implementations of the fused periodic-pad + Conv2D layer, and the data movers that let
+// a whole U-Net run on them.
 //
-// Why a different formulation than a textbook implicit GEMM.  With pixels as the M dimension a 'valid' conv is
+// Common ground.  With pixels as the M dimension a 'valid' conv is
 //   D[m, co] = sum_{i,j,c} A[m + shift(i,j), c] * W[i,j,c,co]
-// and the example nets have tiny N (6..32 filters): every K=16 step would re-read a 4 KB A tile from shared memory for
-// 8..16 clocks of tensor work -- shared-memory bound at ~10 % tensor utilisation.  Instead
-//   * vertical taps i are folded into K:   K = (i, c)   (a tap is just a +i*dil*Wp*16-byte offset of the A view), and
-//   * horizontal taps j are folded into N: N = (j, co)  (5x fewer A reads for a 5x5 kernel),
-//   D[m, (j,co)] = sum_{i,c} A[m + i*dil*Wp, c] * W[i,j,c,co],        out[p, co] = sum_j D[p + j*dil, (j,co)],
-// and the horizontal shifted sum runs in the epilogue on the TMEM rows (warp shuffles; 4 boundary lanes via smem).
+// and the example nets have tiny N (6..32 filters).  Precision: operands are fp16 hi/lo splits of fp32 values
+// (x = hi + lo, 22 significant bits); three MMAs per K step (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -> ~1e-6
+// relative error, inside the 1e-4 / 50-step gate.  Activations live in HBM already split and channel-blocked ("P layout"):
+// [n][plane = 2*c8 + {hi,lo}][H + zero rows][Wp][8] fp16 with the periodic longitude halo (wpad columns each side)
+// materialised by the PRODUCER's epilogue and zero rows stored beyond the poles, so a consumer stages rows with plain bulk /
+// tensor-map copies and needs no wrap arithmetic.  A-operand views are K-major, no-swizzle UMMA descriptors into that
+// image (8 pixels x 16 B core matrices; validated by scripts/umma_probe.cu on B200).
 //
-// Precision: operands are fp16 hi/lo splits of fp32 values (x = hi + lo, 22 significant bits); three MMAs per K step
-// (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -> ~1e-6 relative error, inside the 1e-4 / 50-step gate.  Activations
-// live in HBM already split and channel-blocked ("P layout"): [n][plane = 2*c8 + {hi,lo}][H][Wp][8] fp16 with the periodic
-// longitude halo (wpad columns each side) materialised by the PRODUCER's epilogue, so a consumer tile is ONE TMA box and
-// the zero rows beyond the poles are TMA out-of-bounds fill.  A-operand views are K-major, no-swizzle UMMA descriptors into
-// that image (8 pixels x 16 B core matrices; validated by scripts/umma_probe.cu on B200).
-//
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):  warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
-// warps 2-5 epilogue (TMEM quadrant = warp & 3).  Pipelines: smem stages full/empty (TMA <-> MMA), TMEM accumulator sets
-// full/empty (MMA <-> epilogue, double buffered).
+// Two kernels:
+//  * conv_sw_kernel  (mode 1, default): sliding window over row strips -- one staged input row feeds all vertical taps
+//    with the same A operand (collector reuse), one TMEM accumulator per output row in flight.  See the block comment
+//    above the kernel; DESIGN.md 4.1 has the measurements that led to it.
+//  * conv_tc_kernel  (mode 0, DLWP_TC_KERNEL=flat or geometries the sliding window rejects): flattened (row, column)
+//    tiles, vertical taps folded into K (a tap is a +i*dil*Wp*16-byte offset of the A view), horizontal taps folded into N
+//    (N = (j, co), shifted sum in the epilogue) or K; 192+ threads: warp 0 bulk-copy producer, warp 1 MMA issuer, 16
+//    epilogue warps; smem stages full/empty, double-buffered TMEM accumulator sets.
+//  * p_ew_kernel: MaxPooling2D(2) / UpSampling2D(2) / channel-window copies on P images.
 #define DLWP_CONV_TU  // mbarrier helpers
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -102,14 +103,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
-        : "memory");
 }
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -463,11 +456,11 @@ struct SwUnit {
     int paired;      // lanes 64.. belong to segment b
 };
 
-__device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwUnit& U) {
+__host__ __device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwUnit& U) {
     const int band = u % p.nbands, su = u / p.nbands;
     const int g = su / p.units_per_group, k = su - g * p.units_per_group;
     U.ya = p.row0 + band * p.RB;
-    U.yb = min(p.row1, U.ya + p.RB);
+    U.yb = p.row1 < U.ya + p.RB ? p.row1 : U.ya + p.RB;
     U.n1 = -1; U.nvb = 0; U.paired = 0;
     if (!p.pair) {
         U.n0 = g; U.x0 = k * p.S; U.nva = k < p.nfull ? p.S : p.rem;
@@ -1275,18 +1268,10 @@ static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t
     conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p, g_sw_map_full, g_sw_map_pair);
 }
 
-static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
-                     const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
-                     const TcWindow& win) {
-    if (g_tc_sms == 0) {
-        cudaDeviceProp prop;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaGetDeviceProperties(&prop, dev);
-        g_tc_sms = prop.multiProcessorCount;
-    }
-    SwParams p;
-    memset(&p, 0, sizeof(p));
+// The scheduling units of one launch: (strip or paired remainder strips) x (latitude band), see sw_decode.  Host-only
+// arithmetic (also driven by the CPU tests through dlwp_debug_sw_cover); returns the number of sample groups.
+static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, SwParams* pp) {
+    SwParams& p = *pp;
     p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;
     p.D = d.dil_w; p.pad_t = d.pad_t;
     p.S = L.S; p.nfull = L.nfull; p.rem = L.rem; p.pair = L.pair;
@@ -1301,11 +1286,12 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     int best_nb = 1;
     double best_score = -1.0;
     const char* env_nb = getenv("DLWP_TC_BANDS");
+    if (sms < 1) sms = 148;
     for (int nb = 1; nb <= 16 && nb <= rows; ++nb) {
         const int rb = cdiv(rows, nb);
         if (cdiv(rows, rb) != nb) continue;
         const long long total = (long long)groups * p.units_per_group * nb;
-        const double balance = (double)total / (double)(cdiv((int)total, g_tc_sms) * (long long)g_tc_sms);
+        const double balance = (double)total / (double)(cdiv((int)total, sms) * (long long)sms);
         const double reread = (double)rows / (double)(rows + span * nb);
         const double score = balance * (0.5 + 0.5 * reread);
         if (score > best_score + 1e-9) { best_score = score; best_nb = nb; }
@@ -1314,6 +1300,22 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     p.RB = cdiv(rows, best_nb);
     p.nbands = cdiv(rows, p.RB);
     p.total_units = groups * p.units_per_group * p.nbands;
+    return groups;
+}
+
+static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
+                     const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
+                     const TcWindow& win) {
+    if (g_tc_sms == 0) {
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaGetDeviceProperties(&prop, dev);
+        g_tc_sms = prop.multiProcessorCount;
+    }
+    SwParams p;
+    memset(&p, 0, sizeof(p));
+    const int groups = sw_unit_geometry(d, L, g_tc_sms, &p);
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
     p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC;
     p.planes_in = L.planes;
@@ -1493,4 +1495,35 @@ extern "C" int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* ker
         kstep_words[2 * i + 1] = kst[i].a_lbo;
     }
     return (int64_t)img.size();
+}
+
+extern "C" int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_t* cover, int64_t cover_elems,
+                                   int32_t* info, int32_t n_info) {
+    using namespace dlwp;
+    DLWP_REQUIRE(desc && cover && info && n_info >= 4, DLWP_EINVAL, "bad argument");
+    DLWP_REQUIRE(cover_elems == (int64_t)desc->N * desc->H * desc->W, DLWP_EINVAL, "cover must hold N*H*W counters");
+    TcLayer L;
+    DLWP_REQUIRE(tc_geometry_ok(*desc) && tc_plan_layer(*desc, &L) == 0 && L.mode == 1, DLWP_ESHAPE,
+                 "not a sliding-window layer");
+    SwParams p;
+    memset(&p, 0, sizeof(p));
+    sw_unit_geometry(*desc, L, sms, &p);
+    long long staged_rows = 0;
+    int live_units = 0;
+    SwUnit U;
+    for (int u = 0; u < p.total_units; ++u) {
+        if (!sw_decode(p, u, U)) continue;
+        ++live_units;
+        staged_rows += U.yb - U.ya + desc->dil_h * (desc->kh - 1);
+        for (int ml = 0; ml < 128; ++ml) {  // the epilogue's lane -> (sample, column) map
+            const int seg = (U.paired && ml >= 64) ? 1 : 0;
+            const int l = ml - seg * 64;
+            const int n = seg ? U.n1 : U.n0;
+            const int x = U.x0 + l;
+            if (n < 0 || l >= (seg ? U.nvb : U.nva) || x >= p.W) continue;
+            for (int y = U.ya; y < U.yb; ++y) ++cover[((int64_t)n * desc->H + y) * desc->W + x];
+        }
+    }
+    info[0] = p.total_units; info[1] = live_units; info[2] = p.nbands; info[3] = (int32_t)staged_rows;
+    return 0;
 }

@@ -240,6 +240,11 @@ const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
  * dlwp_debug_tc_pack: the packed fp16 hi/lo weight image of that schedule (kernel in Keras layout (kh,kw,Cin,Cout), HOST
  *   pointer) and the low words of its A-operand descriptors per K step; returns the number of fp16 elements written. */
 int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out);
+/* dlwp_debug_sw_cover: walks the sliding-window kernel's scheduling units for this layer on `sms` SMs exactly as the
+ *   device roles do and counts, per output pixel (N,H,W), how many units write it (must be 1 inside [row_begin,row_end),
+ *   0 outside).  info[0..3] = units, non-empty units, latitude bands per strip, staged input rows over all units. */
+int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_t* cover, int64_t cover_elems, int32_t* info,
+                        int32_t n_info);
 int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16_t* image, int64_t image_cap,
                            uint32_t* kstep_words, int32_t kstep_cap);
 

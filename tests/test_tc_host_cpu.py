@@ -115,3 +115,35 @@ def test_weight_image_decodes_to_the_keras_kernel(nat, layer):
         assert word >> 16 == lbo >> 4 and lbo > 0 and lbo % 16 == 0
         c8, j = units[2 * ks]
         assert (word & 0xFFFF) * 16 == 2 * c8 * L['rowpitch'] + max(j, 0) * d * 16
+
+
+@pytest.mark.parametrize('case', [
+    # (N, Cin, H, W, Cout, k, dil, row_begin, row_end, sms)
+    (256, 32, 91, 180, 6, 5, 1, 0, 0, 148),     # Net A conv2 at the bench batch: paired remainder strips
+    (255, 6, 91, 180, 32, 3, 2, 0, 0, 148),     # odd batch: the last paired tile has one segment
+    (3, 32, 91, 180, 6, 5, 1, 23, 46, 148),     # a latitude band of a 4-GPU run
+    (2, 12, 180, 360, 32, 3, 2, 0, 0, 148),     # 1-degree grid: two full strips + an unpaired remainder
+    (5, 8, 7, 124, 8, 3, 1, 0, 0, 148),         # one partial strip, fewer rows than bands
+    (1, 16, 17, 44, 64, 3, 1, 0, 0, 4),         # tiny batch on a tiny device
+])
+def test_sliding_window_units_cover_every_output_pixel_once(nat, case):
+    """The unit decoding shared by the producer, issuer and epilogue roles (sw_decode): every output pixel of the row window
+    is written by exactly one (strip, band) unit, nothing outside it; staged rows = output rows + (k-1)*dil per unit."""
+    N, cin, H, W, cout, k, d, r0, r1, sms = case
+    desc = _desc(nat, cin, H, W, cout, k, d, N=N)
+    desc.row_begin, desc.row_end = r0, r1
+    cover = np.zeros((N, H, W), np.int32)
+    info = (ctypes.c_int32 * 4)()
+    rc = nat.lib().dlwp_debug_sw_cover(ctypes.byref(desc), sms, cover.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                       cover.size, info, 4)
+    assert rc == 0
+    lo, hi = (0, H) if (r0, r1) == (0, 0) else (r0, r1)
+    assert (cover[:, lo:hi] == 1).all()
+    assert not cover[:, :lo].any() and not cover[:, hi:].any()
+    units, live, nbands, staged = list(info)
+    assert 1 <= nbands <= 16 and live <= units
+    _, L = _plan(nat, desc)
+    strips = L['nfull'] + (1 if L['rem'] else 0)
+    strip_units = (N // 2 + N % 2) * (2 * L['nfull'] + 1) if L['pair'] else N * strips
+    assert units == strip_units * nbands
+    assert staged == live // nbands * (hi - lo) + live * d * (k - 1)
