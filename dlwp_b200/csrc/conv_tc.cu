@@ -944,15 +944,15 @@ __device__ __forceinline__ void p_pack8(const float (&v)[8], uint4& h, uint4& l)
 template <int KIND>  // 0 copy, 1 maxpool 2x2 stride 2 (floor), 2 nearest upsample x2
 __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int C8, int Hs,
                                                   int Ws, int wpad_s, int src_plane0, int src_planes_total, int Hd, int Wd,
-                                                  int wpad_d, int dst_plane0, int dst_planes_total) {
+                                                  int wpad_d, int dst_plane0, int dst_planes_total, int row0, int rows) {
     const int Wps = Ws + 2 * wpad_s, Wpd = Wd + 2 * wpad_d;
     const long long Has = Hs + 2 * TC_HPAD, Had = Hd + 2 * TC_HPAD;
-    const long long total = (long long)N * C8 * Hd * Wd;
+    const long long total = (long long)N * C8 * rows * Wd;  // destination rows [row0, row0 + rows): latitude-band window
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(idx % Wd);
         long long t = idx / Wd;
-        const int y = (int)(t % Hd);
-        t /= Hd;
+        const int y = row0 + (int)(t % rows);
+        t /= rows;
         const int c8 = (int)(t % C8);
         const int n = (int)(t / C8);
         const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + 2 * c8) * Has + TC_HPAD) * Wps + wpad_s;
@@ -988,22 +988,25 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
 }
 
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
-                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream) {
+                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream, int row_begin,
+                 int row_end) {
     const int C8 = planes / 2;
     int Hd = Hs, Wd = Ws;
     if (kind == DLWP_OP_MAXPOOL) { Hd = Hs / 2; Wd = Ws / 2; }
     if (kind == DLWP_OP_UPSAMPLE) { Hd = Hs * 2; Wd = Ws * 2; }
-    const long long total = (long long)N * C8 * Hd * Wd;
+    const int row0 = (row_begin == 0 && row_end == 0) ? 0 : row_begin;
+    const int rows = ((row_begin == 0 && row_end == 0) ? Hd : row_end) - row0;
+    const long long total = (long long)N * C8 * rows * Wd;
     if (total == 0) return 0;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
     if (kind == DLWP_OP_MAXPOOL)
-        p_ew_kernel<1><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+        p_ew_kernel<1><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows);
     else if (kind == DLWP_OP_UPSAMPLE)
-        p_ew_kernel<2><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+        p_ew_kernel<2><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows);
     else
-        p_ew_kernel<0><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total);
+        p_ew_kernel<0><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows);
     return after_launch("p_ew_kernel");
 }
 

@@ -53,7 +53,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
 // halo (wpad_d columns per side) is written with the interior.  kind: DLWP_OP_COPY / DLWP_OP_MAXPOOL / DLWP_OP_UPSAMPLE.
 // (Hs, Ws): source image size.
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
-                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream);
+                 int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream,
+                 int row_begin = 0, int row_end = 0);  // destination rows [row_begin, row_end); 0,0 = all
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0 = 0, int row1 = 0);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,

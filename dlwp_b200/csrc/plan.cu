@@ -191,7 +191,7 @@ static int tc_setup(DlwpPlan* pl) {
             return 0;
         }
     }
-    if (windowed && (movers || windows)) return 0;  // latitude-band plans: plain conv stacks only (for now)
+    (void)movers;
     for (size_t b = 0; b < pl->buffers.size(); ++b)
         if (is_src[b]) {
             Buffer& B = pl->buffers[b];
@@ -253,7 +253,7 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
         if (pl->tc_pdst[i] < 0) return 0;  // nobody reads the result in P layout
         const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
         return tc_ew_launch(op.kind, s.P, pb.P, N, 2 * (op.src_c / 8), s.d.H, s.d.W, s.wpad, 2 * (op.src_c0 / 8), s.planes,
-                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream);
+                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream, op.row_begin, op.row_end);
     }
     const Weight& w = pl->weights[op.weight_id];
     DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);

@@ -68,15 +68,16 @@ def test_unet_bands_equal_single_domain():
     cs = (12, 48, 64)
     dlwp, _ = build_functional_pair(cs, skip=True, integration_steps=2, seed=3)
     x0 = np.random.RandomState(4).standard_normal((2,) + cs).astype(np.float32)
-    # Row-windowed U-Net plans run on the fp32 kernels (the tensor-core chain takes row windows for plain conv stacks
-    # only), so the bit-for-bit reference is the single-domain fp32 plan; the single-domain tensor-core chain (the default
-    # engine) agrees with both to fp32 round-off.
+    # Row-windowed U-Net plans run as tensor-core chains too (row windows in the convs and in the P-image data movers);
+    # every pixel sums its taps in the same order whatever the band, so the bands reproduce the single-domain chain bit
+    # for bit, and both agree with the fp32 plan to round-off.
     from dlwp_b200.engine import CompiledNet
-    eng = CompiledNet(dlwp.model, 2, force_ffma=True)
-    ref = eng.rollout_host(x0, 2)
-    eng.close()
+    assert dlwp.model.engine(2).uses_tensor_cores()
+    ref = dlwp.predict_timeseries(x0, 4)
     got, planners = _run_bands(dlwp.model, 2, x0, 2)
     np.testing.assert_array_equal(got, ref)
-    tc = dlwp.predict_timeseries(x0, 4)
-    assert tc.shape == ref.shape
-    assert np.abs(tc - ref).max() <= 5e-5 * np.abs(ref).max()
+    eng = CompiledNet(dlwp.model, 2, force_ffma=True)
+    fp32 = eng.rollout_host(x0, 2)
+    eng.close()
+    assert fp32.shape == ref.shape
+    assert np.abs(fp32 - ref).max() <= 5e-5 * np.abs(ref).max()
