@@ -157,7 +157,7 @@ static int tc_setup(DlwpPlan* pl) {
     std::vector<TcLayer> layers(nops);
     std::vector<int> wpad(pl->buffers.size(), -1);
     std::vector<char> is_src(pl->buffers.size(), 0), written(pl->buffers.size(), 0);
-    bool windowed = false, movers = false, windows = false;
+    bool windowed = false;
     auto chunk_window_ok = [](int c0, int c, int C) { return c0 % 8 == 0 && (c % 8 == 0 || c0 + c == C); };
     written[pl->input_buf] = 1;
     for (int i = 0; i < nops; ++i) {
@@ -180,18 +180,15 @@ static int tc_setup(DlwpPlan* pl) {
             DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
             if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
             if (win && layers[i].mode != 1) return 0;  // only the sliding-window kernel takes channel windows
-            windows = windows || win;
             if (wpad[op.src] >= 0 && wpad[op.src] != layers[i].wpad) return 0;  // all conv readers must want the same halo
             wpad[op.src] = layers[i].wpad;
         } else if (op.kind == DLWP_OP_MAXPOOL || op.kind == DLWP_OP_UPSAMPLE || op.kind == DLWP_OP_COPY) {
             if (op.src_c0 % 8 || op.src_c % 8 || op.dst_c0 % 8) return 0;
             if (op.kind == DLWP_OP_MAXPOOL && ((s.d.H | s.d.W) & 1)) return 0;
-            movers = true;
         } else {
             return 0;
         }
     }
-    (void)movers;
     for (size_t b = 0; b < pl->buffers.size(); ++b)
         if (is_src[b]) {
             Buffer& B = pl->buffers[b];
