@@ -1055,8 +1055,11 @@ static int sw_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     if (L->NCOLS > 256) return -1;
     L->NACC = std::min(SW_MAX_ACC, 512 / L->NCOLS);
     if (L->NACC < span + 2) return -1;  // rows in flight (span + 1) plus one being drained by the epilogue
-    L->XLK = L->taps_in_k ? halo_w : 0;
-    L->S = L->taps_in_k ? 128 : 128 - halo_w;
+    // Either way a strip yields 128 - halo_w outputs: with the taps in N the last halo_w lanes only feed the shifted sum,
+    // with the taps in K the shifted A views of the last valid lane end at pixel 127 -- so the staged row is exactly 128
+    // pixels per plane and one tensor-map box (<= 256 eight-byte elements) can bring it.
+    L->XLK = 0;
+    L->S = 128 - halo_w;
     L->nfull = d.W / L->S;
     L->rem = d.W - L->nfull * L->S;
     L->pair = (L->rem > 0 && L->rem + halo_w <= 64) ? 1 : 0;
@@ -1338,7 +1341,7 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     const int nc = L.CSTRIDE == 6 ? 6 : 8;
     // Tensor-map producer for layers whose staged row is exactly 128 pixels per plane (taps in N) and has several planes.
     p.use_tma = 0;
-    if (L.XLK == 0 && L.rowpitch == 2048 && L.planes >= 4 && !getenv("DLWP_SW_NO_TMA")) {
+    if (L.XLK == 0 && L.rowpitch == 2048 && !getenv("DLWP_SW_NO_TMA")) {
         const uint64_t Halloc = (uint64_t)d.H + 2 * TC_HPAD, row_b = (uint64_t)L.Wp * 16, plane_b = Halloc * row_b;
         const uint64_t dims3[3] = {(uint64_t)L.Wp * 2, Halloc, (uint64_t)d.N * p.in_planes_total};
         const uint64_t str3[2] = {row_b, plane_b};

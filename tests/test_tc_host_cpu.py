@@ -55,10 +55,10 @@ def test_sliding_window_plan_invariants(nat, layer):
     assert L['planes'] == 2 * ((cin + 7) // 8) <= 32
     kw_eff = 1 if L['taps_in_k'] else k
     assert L['NCOLS'] >= L['CBLK'] * kw_eff * L['CSTRIDE']
-    assert L['S'] == (128 if L['taps_in_k'] else 128 - halo_w)
+    assert L['S'] == 128 - halo_w                            # the staged row is exactly 128 pixels in both modes
     assert L['nfull'] * L['S'] + L['rem'] == W
     assert L['pair'] == int(0 < L['rem'] and L['rem'] + halo_w <= 64)
-    assert L['rowpitch'] % 128 == 0 and L['rowpitch'] >= (128 + (halo_w if L['taps_in_k'] else 0)) * 16
+    assert L['rowpitch'] == 128 * 16                         # one tensor-map box per row and unit
     units = ((cin + 7) // 8) * (k if L['taps_in_k'] else 1)
     assert L['KS'] == (units + 1) // 2
     assert L['b_bytes'] == L['KS'] * k * 2 * (2 * L['NCOLS'] * 16)
