@@ -147,3 +147,84 @@ def test_sliding_window_units_cover_every_output_pixel_once(nat, case):
     strip_units = (N // 2 + N % 2) * (2 * L['nfull'] + 1) if L['pair'] else N * strips
     assert units == strip_units * nbands
     assert staged == live // nbands * (hi - lo) + live * d * (k - 1)
+
+
+def _split16(x):
+    """fp32 -> (hi, lo) fp16 pair with x ~= hi + lo (what pack_state_kernel and the epilogues store)."""
+    hi = x.astype(np.float16)
+    lo = (x - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+@pytest.mark.parametrize('layer', [(6, 11, 40, 32, 3, 2), (32, 9, 36, 6, 5, 1), (12, 8, 44, 12, 5, 1), (24, 7, 30, 40, 3, 1)])
+def test_software_model_of_the_tensor_core_formulation_matches_the_oracle(nat, layer):
+    """
+    CPU model of what conv_sw_kernel computes, built from the library's OWN packed weight image and K-step table: the
+    P-layout input (8-channel chunks, fp16 hi/lo planes, periodic halo columns, zero rows beyond the poles), per K step a
+    128-lane A view at `stage + offset` with the second 8-channel unit LBO bytes further, three products per step
+    (hi*hi + hi*lo + lo*hi) accumulated in fp32 per output row, horizontal taps either folded into K or summed from shifted
+    lanes of the N = (j, co) columns.  Compared with the float64 oracle at the tensor-core gate (2e-5).
+    """
+    from oracle import ops as OO
+    cin, H, W, cout, k, d = layer
+    desc = _desc(nat, cin, H, W, cout, k, d, N=1)
+    rc, L = _plan(nat, desc)
+    assert rc == 0 and L['mode'] == 1
+    rng = np.random.RandomState(7 + sum(layer))
+    x = rng.standard_normal((cin, H, W)).astype(np.float32)
+    w = OO.glorot_uniform(rng, k, k, cin, cout)
+    b = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+    cap = L['b_bytes'] // 2
+    img = np.zeros(cap, np.uint16)
+    kst = np.zeros(2 * L['KS'], np.uint32)
+    n = nat.lib().dlwp_debug_tc_pack(ctypes.byref(desc), w.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                     img.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), cap,
+                                     kst.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 2 * L['KS'])
+    assert n == cap
+    B = img.view(np.float16).astype(np.float32).reshape(L['KS'], k, 2, 2, L['NCOLS'], 8)    # [ks][tap i][hi|lo][unit][col][e]
+    pad = d * (k - 1) // 2
+    C8, Wp = (cin + 7) // 8, W + 2 * pad
+    # P layout of the input: [plane = 2*c8 + hi|lo][padded row][padded col][8], zero rows beyond the poles
+    xp = np.zeros((C8 * 8, H + 2 * pad, Wp), np.float32)
+    xp[:cin, pad:pad + H, pad:pad + W] = x
+    xp[:cin, pad:pad + H, :pad] = x[:, :, W - pad:]
+    xp[:cin, pad:pad + H, pad + W:] = x[:, :, :pad]
+    hi, lo = _split16(xp)
+    P = np.zeros((2 * C8, H + 2 * pad, Wp + 128, 8), np.float32)         # + slack: views of the last strip run past the row
+    for c8 in range(C8):
+        P[2 * c8, :, :Wp] = np.moveaxis(hi[c8 * 8:c8 * 8 + 8].astype(np.float32), 0, -1)
+        P[2 * c8 + 1, :, :Wp] = np.moveaxis(lo[c8 * 8:c8 * 8 + 8].astype(np.float32), 0, -1)
+    rowpitch = L['rowpitch']
+    assert rowpitch == 128 * 16
+    kw_eff = 1 if L['taps_in_k'] else k
+    out = np.zeros((cout, H, W), np.float32)
+    S = L['S']
+    for x0 in range(0, W, S):                                             # strips of one padded row
+        for y in range(H):
+            D = np.zeros((128, L['NCOLS']), np.float32)                   # the row's TMEM accumulator
+            for i in range(k):                                            # vertical tap i reads padded row y + i*dil
+                stage = P[:, y + i * d, x0:x0 + 128 + 8]                  # [plane][pixel][8]: one staged row (+ view slack)
+                for ks in range(L['KS']):
+                    word, lbo = int(kst[2 * ks]), int(kst[2 * ks + 1])
+                    off = (word & 0xFFFF) * 16
+                    for half in range(2):                                 # the two 8-channel units of a K = 16 step
+                        byte = off + half * lbo
+                        plane, px = byte // rowpitch, (byte % rowpitch) // 16
+                        if not (B[ks, i, 0, half].any() or B[ks, i, 1, half].any()):
+                            continue                                      # the zero-weight unit padding an odd unit count
+                        a_hi = stage[plane, px:px + 128]                  # A view: 128 lanes x 8 channels
+                        a_lo = stage[plane + 1, px:px + 128]
+                        b_hi, b_lo = B[ks, i, 0, half], B[ks, i, 1, half]  # [col][8]
+                        D += a_hi @ b_hi.T + a_hi @ b_lo.T + a_lo @ b_hi.T
+            for co in range(cout):
+                cb, ci = divmod(co, 8)
+                acc = np.zeros(128, np.float32)
+                for j in range(kw_eff):                                   # shifted sum over the horizontal taps living in N
+                    col = (cb * kw_eff + j) * L['CSTRIDE'] + ci
+                    acc[:128 - j * d] += D[j * d:, col]
+                nv = min(S, W - x0)
+                out[co, y, x0:x0 + nv] = acc[:nv] + b[co]
+    ref = OO.pad_conv2d_closed_form(x[None].astype(np.float64), w.astype(np.float64), b.astype(np.float64), (d, d),
+                                    (pad, pad), (pad, pad), 'zero', 'periodic')[0]
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, err
