@@ -499,8 +499,14 @@ int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dim
 // Generic tiled tensor map over 8-byte elements (the tensor-core path views a P image as 16-byte pixel chunks = 2 elements):
 // rank <= 5, dims fastest first, strides_bytes[i] = stride of dimension i + 1.  Returns nonzero (and sets the error string)
 // when the driver refuses the descriptor, so callers can fall back to plain bulk copies.
+int encode_tensor_map_any(CUtensorMap* map, const void* base, int is_f32, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);
 int encode_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box) {
+    return encode_tensor_map_any(map, base, 0, rank, dims, strides_bytes, box);
+}
+int encode_tensor_map_any(CUtensorMap* map, const void* base, int is_f32, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
     static encode_tiled_t fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -515,10 +521,11 @@ int encode_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const ui
     cuuint32_t gbox[5] = {1, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+    CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank,
+                    const_cast<void*>(base), gdims, gstr, gbox, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DLWP_REQUIRE(r == CUDA_SUCCESS, DLWP_ESHAPE, "cuTensorMapEncodeTiled (u64, rank %d) failed with CUresult %d", rank, (int)r);
+    DLWP_REQUIRE(r == CUDA_SUCCESS, DLWP_ESHAPE, "cuTensorMapEncodeTiled (%s, rank %d) failed with CUresult %d", is_f32 ? "f32" : "u64", rank, (int)r);
     return 0;
 }
 

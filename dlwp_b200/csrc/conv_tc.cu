@@ -441,6 +441,7 @@ struct SwParams {
     const __half* bimg;
     const __half* xp;
     int in_plane0, in_planes_total, out_plane0;  // channel windows of the source / destination P images
+    int f32_C, f32_rawpitch, f32_segstride;  // F32IN: source channels, bytes of a raw channel row (W * 4), of a sample's rows
     int use_tma;  // 1: the producer stages rows with tensor-map loads (one per row and unit) instead of per-plane bulk copies
     int debug;  // DLWP_SW_DEBUG: 1 = epilogue only waits/arrives, 2 = issuer only commits (bottleneck triage; wrong results)
     float* y32; long long ys_n, ys_c, ys_h;
@@ -498,22 +499,52 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void p_unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
+    const __half2* hh = reinterpret_cast<const __half2*>(&h);
+    const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(hh[k]), b = __half22float2(ll[k]);
+        v[2 * k] = a.x + b.x;      // exact: hi and lo are an exact split of an fp32 value
+        v[2 * k + 1] = a.y + b.y;
+    }
+}
+__device__ __forceinline__ void p_pack8(const float (&v)[8], uint4& h, uint4& l) {
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 hh = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        const float2 f = __half22float2(hh);
+        hp[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        lp[k] = pack_half2(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+    }
+}
+
+
 // KH: kernel height (vertical taps), KW: horizontal taps summed by the epilogue (1 = folded into K), NC: filters per
 // 8-filter block that exist (6: the single packed block of a 6-filter layer, else 8)
 //
 // ST: compile-time copy of the per-layer constants (0 / -1 = take the value from SwParams at run time).  The generic
 // instance serves any layer; the benchmark nets' layers get instances with everything folded, which matters because the
 // single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's critical path.
-template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0>
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int F32IN_ = 0>
 struct SwStatic {
     static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
     static constexpr int FULL = FULL_;  // 1: Cout == CBLK * NC, no partial filter block
+    // 1: the source is the fp32 (N,C,H,W) state itself (first layer of a rollout): the producer stages raw fp32 rows and
+    // two converter warps build the hi/lo A layout (periodic wrap and pole rows included) -- no P image of the state, no
+    // pack kernel, no feedback copy written by the last layer
+    static constexpr int F32IN = F32IN_;
 };
+constexpr int SW_CONV_WARPS = 2;   // converter warps of the F32IN variant
+constexpr int SW_RAW_STAGES = 4;   // raw fp32 row stages
 using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
 
 template <int KH, int KW, int NC, class ST>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full,
-                                                                const __grid_constant__ CUtensorMap map_pair) {
+__global__ void __launch_bounds__(TC_THREADS + (ST::F32IN ? SW_CONV_WARPS * 32 : 0), 1)
+conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_pair) {
+    constexpr int NTHREADS = TC_THREADS + (ST::F32IN ? SW_CONV_WARPS * 32 : 0);
     const int NCOLS = ST::NCOLS ? ST::NCOLS : p.NCOLS;
     const int KS = ST::KS ? ST::KS : p.KS;
     const int D = ST::D ? ST::D : p.D;
@@ -536,7 +567,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     uint64_t* empty = bars + SW_MAX_STAGES;                 // [NS]       the row's MMAs have read the stage
     uint64_t* acc_full = bars + 2 * SW_MAX_STAGES;          // [NACC]     output row complete in TMEM
     uint64_t* acc_empty = acc_full + SW_MAX_ACC;            // [NACC]     epilogue done with the accumulator
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SW_MAX_ACC);
+    uint64_t* raw_full = acc_empty + SW_MAX_ACC;            // [SW_RAW_STAGES]  F32IN: raw fp32 row landed
+    uint64_t* raw_empty = raw_full + SW_RAW_STAGES;         // [SW_RAW_STAGES]  F32IN: converters done with the raw row
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + SW_RAW_STAGES);
+    unsigned char* raw = reinterpret_cast<unsigned char*>(tmem_slot + 4);  // F32IN: [stage][segment][channel][W] fp32
+    raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~(uintptr_t)127);
 
     // Warp roles: warps 0-15 epilogue (set = warp / 4, TMEM lane quadrant = warp % 4), warp 16 producer, warp 17 MMA
     // issuer.  The two single-warp roles sit on the highest warp ids: the issuer's serial instruction stream is the
@@ -546,15 +581,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     constexpr int W_PROD = TC_SETS * 4, W_MMA = TC_SETS * 4 + 1;
     const int SPAN = (KH - 1) * D;
 
-    for (uint32_t i = tid; i < p.b_bytes / 16; i += TC_THREADS)
+    for (uint32_t i = tid; i < p.b_bytes / 16; i += NTHREADS)
         reinterpret_cast<uint4*>(bsm)[i] = reinterpret_cast<const uint4*>(p.bimg)[i];
-    for (uint32_t i = tid; i < (uint32_t)p.NS * p.stage_stride / 16; i += TC_THREADS)  // lanes past a row's end stay finite
+    for (uint32_t i = tid; i < (uint32_t)p.NS * p.stage_stride / 16; i += NTHREADS)  // lanes past a row's end stay finite
         reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < CBLK * 8; i += TC_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
+    for (int i = tid; i < CBLK * 8; i += NTHREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
     fence_proxy_async();
     if (tid == 0) {
-        for (int s = 0; s < p.NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // F32IN: a stage is filled by the converter threads (generic stores), not by a bulk copy
+        for (int s = 0; s < p.NS; ++s) { mbar_init(&full[s], ST::F32IN ? SW_CONV_WARPS * 32 : 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        if (ST::F32IN)
+            for (int s = 0; s < SW_RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], SW_CONV_WARPS * 32); }
         fence_mbar_init();
     }
     if (warp == W_MMA) {
@@ -568,7 +606,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
     const uint32_t tmem = *tmem_slot;
     const int Halloc = p.H + 2 * TC_HPAD;
 
-    if (warp == W_PROD && p.use_tma) {
+    if (ST::F32IN && warp == W_PROD) {
+        // =============================== producer, fp32-state flavour ===================================================
+        // One tiled load per input row and sample: box (W floats, 1 row, C channels) of the (N*C, H, W) fp32 state; rows
+        // beyond the poles are out of bounds -> zero filled (ZeroPadding2D).  map_full is the fp32 map here.
+        if (lane == 0) {
+            prefetch_tensormap(&map_full);
+            int rs = 0;
+            uint32_t rph = 0;
+            const uint32_t seg_bytes = (uint32_t)p.f32_C * (uint32_t)p.f32_rawpitch, seg_stride = (uint32_t)p.f32_segstride;
+            SwUnit U;
+            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+                if (!sw_decode(p, u, U)) continue;
+                const int nrows = U.yb - U.ya + SPAN;
+                const int nseg = U.n1 >= 0 ? 2 : 1;
+                int row = U.ya - p.pad_t;  // unpadded source row, may lie beyond the poles
+                for (int r = 0; r < nrows; ++r, ++row) {
+                    mbar_wait_relaxed(&raw_empty[rs], rph ^ 1);
+                    mbar_expect_tx(&raw_full[rs], seg_bytes * nseg);
+                    unsigned char* dst = raw + (size_t)rs * 2 * seg_stride;
+                    tma_load_3d(dst, &map_full, &raw_full[rs], 0, row, U.n0 * p.f32_C);
+                    if (nseg == 2) tma_load_3d(dst + seg_stride, &map_full, &raw_full[rs], 0, row, U.n1 * p.f32_C);
+                    if (++rs == SW_RAW_STAGES) { rs = 0; rph ^= 1; }
+                }
+            }
+        }
+    } else if (ST::F32IN && warp >= W_MMA + 1) {
+        // =============================== converters (F32IN): raw fp32 row -> hi/lo A layout ===============================
+        // Thread t owns lanes t and t + 64 of the 128-lane tile (in a paired tile: the same column of the two samples).
+        // Lane l is padded column x0 + l = source column (x0 + l - wpad) mod W: the periodic wrap is index arithmetic here.
+        const int t = tid - (W_MMA + 1) * 32;
+        const int wpad = (p.Wp - p.W) / 2;
+        const uint32_t seg_stride = (uint32_t)p.f32_segstride;
+        int s = 0, rs = 0;
+        uint32_t ph = 0, rph = 0;
+        SwUnit U;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            if (!sw_decode(p, u, U)) continue;
+            const int nrows = U.yb - U.ya + SPAN;
+            int col[2], seg[2];
+            bool live[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int ml = t + 64 * k;
+                seg[k] = (U.paired && ml >= 64) ? 1 : 0;
+                const int l = ml - 64 * seg[k];
+                const int xpad = U.x0 + l;
+                live[k] = xpad < p.Wp && (seg[k] ? U.n1 : U.n0) >= 0;
+                int c = xpad - wpad;
+                if (c < 0) c += p.W;
+                if (c >= p.W) c -= p.W;
+                col[k] = live[k] ? c : 0;
+            }
+            for (int r = 0; r < nrows; ++r) {
+                mbar_wait_relaxed(&raw_full[rs], rph);
+                mbar_wait_relaxed(&empty[s], ph ^ 1);
+                const unsigned char* rbase = raw + (size_t)rs * 2 * seg_stride;
+                unsigned char* sbase = stages + (size_t)s * p.stage_stride;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float* src = reinterpret_cast<const float*>(rbase + (size_t)seg[k] * seg_stride) + col[k];
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        v[c] = (live[k] && c < p.f32_C) ? src[(size_t)c * (p.f32_rawpitch >> 2)] : 0.f;
+                    float amax = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fabsf(v[c]));
+                    if (!(amax <= 65504.f)) atomicOr(&g_tc_flags, 2);  // outside the fp16 split's range (or NaN)
+                    uint4 vh, vl;
+                    p_pack8(v, vh, vl);
+                    uint4* dst = reinterpret_cast<uint4*>(sbase) + (t + 64 * k);   // plane 0 (hi), lane
+                    dst[0] = vh;
+                    dst[p.rowpitch >> 4] = vl;                                      // plane 1 (lo)
+                }
+                fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&full[s]);
+                mbar_arrive(&raw_empty[rs]);
+                if (++s == p.NS) { s = 0; ph ^= 1; }
+                if (++rs == SW_RAW_STAGES) { rs = 0; rph ^= 1; }
+            }
+        }
+    } else if (warp == W_PROD && p.use_tma) {
         // =============================== producer, tensor-map flavour ===================================================
         // One tiled load per input row and unit brings all planes of the strip: box (128 px, 1 row, planes) for a full
         // strip, (64 px, 1 row, 2 samples, planes) for a paired remainder strip -- the box order makes the stage layout
@@ -919,28 +1038,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_sw_kernel(const SwParams p
 // columns are written with the interior.  HBM-bound byte movers: 32 B read (128 B for the pooling) + 32 B written per
 // thread, coalesced along x.
 // ===================================================================================================================
-__device__ __forceinline__ void p_unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
-    const __half2* hh = reinterpret_cast<const __half2*>(&h);
-    const __half2* ll = reinterpret_cast<const __half2*>(&l);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 a = __half22float2(hh[k]), b = __half22float2(ll[k]);
-        v[2 * k] = a.x + b.x;      // exact: hi and lo are an exact split of an fp32 value
-        v[2 * k + 1] = a.y + b.y;
-    }
-}
-__device__ __forceinline__ void p_pack8(const float (&v)[8], uint4& h, uint4& l) {
-    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
-    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const __half2 hh = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-        const float2 f = __half22float2(hh);
-        hp[k] = *reinterpret_cast<const uint32_t*>(&hh);
-        lp[k] = pack_half2(v[2 * k] - f.x, v[2 * k + 1] - f.y);
-    }
-}
-
 template <int KIND>  // 0 copy, 1 maxpool 2x2 stride 2 (floor), 2 nearest upsample x2
 __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int C8, int Hs,
                                                   int Ws, int wpad_s, int src_plane0, int src_planes_total, int Hd, int Wd,
@@ -1072,7 +1169,7 @@ static int sw_plan_layer(const DlwpConvDesc& d, TcLayer* L) {
     L->stage_bytes = L->stage_stride = (uint32_t)L->planes * L->rowpitch;
     L->b_bytes = (uint32_t)(L->KS * d.kh * 2) * (uint32_t)(2 * L->NCOLS * 16);
     const size_t mailbox = L->kw_eff > 1 ? (size_t)TC_SETS * 2 * L->CBLK * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 : 0;
-    const size_t fixed = (size_t)L->b_bytes + mailbox + (size_t)L->CBLK * 32 + (2 * SW_MAX_STAGES + 2 * SW_MAX_ACC) * 8 + 64 + 1024;
+    const size_t fixed = (size_t)L->b_bytes + mailbox + (size_t)L->CBLK * 32 + (2 * SW_MAX_STAGES + 2 * SW_MAX_ACC + 2 * SW_RAW_STAGES) * 8 + 128 + 1024;
     const size_t budget = 227 * 1024;
     if (fixed + L->stage_stride > budget) return -1;
     L->NS = (int)std::min<size_t>(SW_MAX_STAGES, (budget - fixed) / L->stage_stride);
@@ -1271,7 +1368,14 @@ static void sw_launch_one(const SwParams& p, int grid, size_t smem, cudaStream_t
     std::call_once(once, [] {
         cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
-    conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p, g_sw_map_full, g_sw_map_pair);
+    constexpr int threads = TC_THREADS + (ST::F32IN ? SW_CONV_WARPS * 32 : 0);
+    conv_sw_kernel<KH, KW, NC, ST><<<grid, threads, smem, stream>>>(p, g_sw_map_full, g_sw_map_pair);
+}
+
+bool tc_f32in_ok(const DlwpConvDesc& d, const TcLayer& L) {
+    return L.mode == 1 && d.kh == 3 && L.kw_eff == 1 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 2 && L.CBLK == 4 &&
+           d.Cout == 32 && d.act == DLWP_ACT_TANH && d.Cin <= 8 && d.W <= 256 && d.W % 4 == 0 && d.x_stride_h == d.W &&
+           d.x_stride_c == (long long)d.H * d.W && d.x_stride_n == (long long)d.Cin * d.H * d.W;
 }
 
 // The scheduling units of one launch: (strip or paired remainder strips) x (latitude band), see sw_decode.  Host-only
@@ -1339,9 +1443,25 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
     const int grid = std::min(p.total_units, g_tc_sms);
     const int nc = L.CSTRIDE == 6 ? 6 : 8;
+    size_t smem = L.smem;
+    const bool f32in = win.x32 != nullptr;
+    if (f32in) {  // fp32 state as the source: raw-row ring behind the regular carve-up, fp32 tensor map in map_full
+        DLWP_REQUIRE(tc_f32in_ok(d, L) && yp != nullptr && y32 == nullptr, DLWP_ESHAPE, "layer cannot read the fp32 state directly");
+        p.f32_C = d.Cin;
+        p.f32_rawpitch = d.W * 4;
+        p.f32_segstride = (d.Cin * d.W * 4 + 127) / 128 * 128;
+        smem += (size_t)SW_RAW_STAGES * 2 * p.f32_segstride + 256;
+        DLWP_REQUIRE(smem <= 227 * 1024, DLWP_ESHAPE, "no shared memory left for the raw fp32 row stages");
+        const uint64_t dims[3] = {(uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.N * d.Cin};
+        const uint64_t str[2] = {(uint64_t)d.W * 4, (uint64_t)d.H * d.W * 4};
+        const uint32_t box[3] = {(uint32_t)d.W, 1, (uint32_t)d.Cin};
+        int rc = encode_tensor_map_any(&g_sw_map_full, win.x32, 1, 3, dims, str, box);
+        if (rc) return rc;
+        g_sw_map_pair = g_sw_map_full;
+    }
     // Tensor-map producer for layers whose staged row is exactly 128 pixels per plane (taps in N) and has several planes.
     p.use_tma = 0;
-    if (L.XLK == 0 && L.rowpitch == 2048 && !getenv("DLWP_SW_NO_TMA")) {
+    if (!f32in && L.XLK == 0 && L.rowpitch == 2048 && !getenv("DLWP_SW_NO_TMA")) {
         const uint64_t Halloc = (uint64_t)d.H + 2 * TC_HPAD, row_b = (uint64_t)L.Wp * 16, plane_b = Halloc * row_b;
         const uint64_t dims3[3] = {(uint64_t)L.Wp * 2, Halloc, (uint64_t)d.N * p.in_planes_total};
         const uint64_t str3[2] = {row_b, plane_b};
@@ -1361,7 +1481,9 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
     // fully folded instances for the benchmark nets' layers (SwStatic<NCOLS, KS, D, CBLK, ACT, OUT>)
     const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
     const bool generic_only = getenv("DLWP_TC_GENERIC") != nullptr;
-    if (!generic_only && d.kh == 3 && L.kw_eff == 1 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 2 && L.CBLK == 4 &&
+    if (f32in)                                                                // Net A conv1 reading the fp32 state itself
+        sw_launch_one<3, 1, 8, SwStatic<32, 2, 2, 4, DLWP_ACT_TANH, 1, 1, 1>>(p, grid, smem, stream);
+    else if (!generic_only && d.kh == 3 && L.kw_eff == 1 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 2 && L.CBLK == 4 &&
         d.Cout == 32 && d.act == DLWP_ACT_TANH && out_mode == 1)            // Net A conv1: 6 -> 32, 3x3 dilation 2, tanh, P-layout output
         sw_launch_one<3, 1, 8, SwStatic<32, 2, 2, 4, DLWP_ACT_TANH, 1, 1>>(p, grid, L.smem, stream);
     else if (!generic_only && d.kh == 5 && L.kw_eff == 5 && nc == 6 && L.NCOLS == 32 && L.KS == 2 && d.dil_w == 1 &&

@@ -44,7 +44,12 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
 // planes [out_plane0, ...) of a destination image with planes_out planes per sample.
 struct TcWindow {
     int in_plane0 = 0, in_planes_total = 0, out_plane0 = 0;
+    // first layer of a rollout reading the fp32 (N,C,H,W) state directly (no P image of the state): dense source, see
+    // tc_f32in_ok; xp is ignored when x32 is set
+    const float* x32 = nullptr;
 };
+// The layer can take its input as fp32 (N,C,H,W) instead of a P image (the folded Net A first-layer instance only, for now).
+bool tc_f32in_ok(const DlwpConvDesc& d, const TcLayer& L);
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
               const TcWindow& win = TcWindow());

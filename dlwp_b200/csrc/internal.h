@@ -72,6 +72,8 @@ int encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dim
                          const uint32_t box[4]);
 int encode_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box);
+int encode_tensor_map_any(CUtensorMap* map, const void* base, int is_f32, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace dlwp
 

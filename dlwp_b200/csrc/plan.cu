@@ -88,6 +88,9 @@ struct DlwpPlan {
     // latitude band: rows [tc_band_row0, tc_band_row1) of the next input are re-packed by the feedback conv itself; only the
     // halo rows that arrive as fp32 from the neighbours ([tc_in_row0, band_row0) and [band_row1, tc_in_row1)) are packed
     int tc_band_row0 = 0, tc_band_row1 = 0;
+    // DLWP_SW_F32IN: every conv that reads the input buffer takes the fp32 state itself (no P image of the state, no pack
+    // kernel, no feedback copy written by the last layer)
+    bool tc_f32in = false;
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     long long halo_cap = 0;
@@ -189,8 +192,24 @@ static int tc_setup(DlwpPlan* pl) {
             return 0;
         }
     }
+    {
+        const char* env_f = getenv("DLWP_SW_F32IN");
+        bool f32in = env_f && atoi(env_f) != 0;
+        int readers = 0;
+        for (int i = 0; i < nops && f32in; ++i) {
+            const DlwpOpDesc& op = pl->ops[i];
+            if (op.src != pl->input_buf) continue;
+            ++readers;
+            const Buffer& s = pl->buffers[op.src];
+            DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
+            f32in = op.kind == DLWP_OP_CONV && op.src_c0 == 0 && op.src_c == s.d.C && op.dst_c0 == 0 &&
+                    pl->buffers[op.dst].d.kind == DLWP_BUF_INTERNAL && tc_f32in_ok(d, layers[i]);
+        }
+        pl->tc_f32in = f32in && readers > 0;
+    }
     for (size_t b = 0; b < pl->buffers.size(); ++b)
         if (is_src[b]) {
+            if (pl->tc_f32in && (int)b == pl->input_buf) continue;  // read as fp32: no P image
             Buffer& B = pl->buffers[b];
             B.wpad = wpad[b] >= 0 ? wpad[b] : 0;  // read only by data movers: no halo needed
             B.planes = 2 * ((B.d.C + 7) / 8);
@@ -261,6 +280,7 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
     TcWindow win;
     win.in_plane0 = 2 * (op.src_c0 / 8);
     win.in_planes_total = s.planes;
+    if (pl->tc_f32in && op.src == pl->input_buf) win.x32 = s.ptr;
     if (pl->tc_pdst[i] >= 0) {
         const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
@@ -272,7 +292,9 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
 
 static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_packed) {
     Buffer& in = pl->buffers[pl->input_buf];
-    if (!input_is_packed) {
+    if (pl->tc_f32in) {
+        // the first layer reads the fp32 state (and, in a latitude band, the halo rows the exchange wrote into it) directly
+    } else if (!input_is_packed) {
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
                                (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1);
         if (rc) return rc;

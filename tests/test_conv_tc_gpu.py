@@ -221,3 +221,31 @@ def test_unet_full_grid_on_tensor_cores(env):
         ref = onet.forward(torch.from_numpy(x0)).numpy()
     assert rel_err(y, ref.astype(np.float64)) < 5e-5
     eng.close()
+
+
+@pytest.mark.parametrize('shape,N', [((6, 91, 180), 3), ((6, 20, 36), 2)])
+def test_fp32_state_first_layer_matches_the_p_layout_path_bit_for_bit(env, monkeypatch, shape, N):
+    """DLWP_SW_F32IN=1: the first layer stages raw fp32 rows of the state and converter warps build the hi/lo A layout
+    (periodic wrap and pole rows included); no P image of the state, no pack kernel, no feedback copy.  The split of a value
+    is the same either way, so the rollout is bit-identical to the default tensor-core chain."""
+    nat, torch = env
+    from dlwp_b200.engine import CompiledNet
+    from oracle import layers as OL
+    from tests.helpers import build_product_sequential, oracle_sequential_like
+    layers = OL.net_a_layers(shape)
+    dlwp = build_product_sequential(layers)
+    oracle_sequential_like(dlwp, layers, seed=1, bias_scale=0.02)
+    x0 = np.random.RandomState(0).standard_normal((N,) + shape).astype(np.float32)
+    xd = torch.from_numpy(x0).cuda()
+    eng = CompiledNet(dlwp.model, N, impl='tc')
+    ref = eng.rollout_device(xd, 6, use_graph=True).cpu().numpy()
+    eng.close()
+    monkeypatch.setenv('DLWP_SW_F32IN', '1')
+    eng2 = CompiledNet(dlwp.model, N, impl='tc')
+    assert eng2.uses_tensor_cores()
+    got = eng2.rollout_device(xd, 6, use_graph=False).cpu().numpy()
+    assert nat.lib().dlwp_debug_flags() == 0
+    np.testing.assert_array_equal(got, ref)
+    got_g = eng2.rollout_device(xd, 6, use_graph=True).cpu().numpy()
+    np.testing.assert_array_equal(got_g, ref)
+    eng2.close()
