@@ -1094,7 +1094,7 @@ int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, in
     const int row0 = (row_begin == 0 && row_end == 0) ? 0 : row_begin;
     const int rows = ((row_begin == 0 && row_end == 0) ? Hd : row_end) - row0;
     const long long total = (long long)N * C8 * rows * Wd;
-    if (total == 0) return 0;
+    if (total <= 0) return 0;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -1423,6 +1423,7 @@ static int sw_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst
         cudaGetDeviceProperties(&prop, dev);
         g_tc_sms = prop.multiProcessorCount;
     }
+    if (!(d.row_begin == 0 && d.row_end == 0) && d.row_end <= d.row_begin) return 0;  // empty latitude window: nothing to do
     SwParams p;
     memset(&p, 0, sizeof(p));
     const int groups = sw_unit_geometry(d, L, g_tc_sms, &p);
