@@ -1391,6 +1391,10 @@ static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, Sw
     const int rows = p.row1 - p.row0, span = d.dil_h * (d.kh - 1);
     const int groups = L.pair ? cdiv(d.N, 2) : d.N;
     p.units_per_group = L.pair ? 2 * L.nfull + 1 : L.nfull + (L.rem > 0 ? 1 : 0);
+    if (rows <= 0) {  // empty latitude window
+        p.RB = 1; p.nbands = 1; p.total_units = 0;
+        return groups;
+    }
     // latitude bands per strip: enough units to balance the SMs, few enough that the (KH-1)*dil halo rows re-read at
     // every band edge stay a small fraction
     int best_nb = 1;
