@@ -977,11 +977,11 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                             float* yb = y32c + (long long)(cb * 8) * p.ys_c;
                             if (nreal >= NC) {
 #pragma unroll
-                                for (int ci = 0; ci < NC; ++ci) yb[(long long)ci * p.ys_c] = o[ci];
+                                for (int ci = 0; ci < NC; ++ci) __stcs(yb + (long long)ci * p.ys_c, o[ci]);
                             } else {
 #pragma unroll
                                 for (int ci = 0; ci < NC; ++ci)
-                                    if (ci < nreal) yb[(long long)ci * p.ys_c] = o[ci];
+                                    if (ci < nreal) __stcs(yb + (long long)ci * p.ys_c, o[ci]);
                             }
                         }
                         if (has_yp) {
@@ -1004,15 +1004,15 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                                 vl.z = pack_half2(o[4] - f2.x, o[5] - f2.y); vl.w = pack_half2(o[6] - f3.x, o[7] - f3.y);
                             }
                             uint4* row_lo = row_hi + plane_stride;
-                            row_hi[0] = vh;
-                            row_lo[0] = vl;
+                            __stcs(row_hi, vh);
+                            __stcs(row_lo, vl);
                             if (halo_r) {            // periodic longitude halo of the NEXT layer, right side
-                                row_hi[p.W] = vh;
-                                row_lo[p.W] = vl;
+                                __stcs(row_hi + p.W, vh);
+                                __stcs(row_lo + p.W, vl);
                             }
                             if (halo_l) {            // ... and left side
-                                row_hi[-p.W] = vh;
-                                row_lo[-p.W] = vl;
+                                __stcs(row_hi - p.W, vh);
+                                __stcs(row_lo - p.W, vl);
                             }
                         }
                     }
