@@ -318,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
     for i, (name, cin, cout, k) in enumerate(layers):
         ms_i = eng.profile_op(B, i, it)
         alg = conv_alg_bytes(B, cin, cout, k)
-        tc_name = 'conv_tc_kernel ' if os.environ.get('DLWP_TC_KERNEL') == 'flat' else 'conv_sw_kernel '
+        tc_name = 'conv_sw_kernel '
         timed.append({'kernel': (tc_name if tc else 'conv_ffma_kernel ') + name, 'ms_per_launch': ms_i,
                       'algorithmic_bytes_per_launch': alg, 'achieved_gbs': alg / (ms_i * 1e-3) / 1e9,
                       'useful_tflops': 2.0 * B * 91 * 180 * cin * cout * k * k / (ms_i * 1e-3) / 1e12})

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libdlwp_b200.so')
 
 DLWP_OK = 0
+ABI_VERSION = 2
 PAD_ZERO, PAD_PERIODIC = 0, 1
 ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
 IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
@@ -44,6 +45,24 @@ class BandInfo(ctypes.Structure):
     _fields_ = [(n, i32) for n in ('rank', 'world', 'band_lo', 'band_hi', 'recv_top', 'recv_bot', 'send_up', 'send_down')]
 
 
+class PlanOptions(ctypes.Structure):
+    """DlwpPlanOptions (include/dlwp_b200.h): all zeros = defaults; tc_taps_in_k = -1 leaves the choice to the planner."""
+    _fields_ = [(n, i32) for n in ('math', 'fuse', 'tc_generic', 'tc_bands', 'tc_no_tma', 'tc_taps_in_k', 'tc_debug')] + \
+               [('reserved', i32 * 9)]
+
+    def __init__(self, **kw):
+        super(PlanOptions, self).__init__()
+        self.tc_taps_in_k = -1
+        for k, v in kw.items():
+            if k not in [f[0] for f in self._fields_]:
+                raise TypeError('unknown plan option %r' % k)
+            setattr(self, k, int(v))
+
+
+MATH_AUTO, MATH_FFMA = 0, 1
+FLAG_FFMA_TIMEOUT, FLAG_TC_TIMEOUT, FLAG_TC_RANGE, FLAG_TC_UNDERFLOW = 1, 2, 4, 8
+
+
 class NetDesc(ctypes.Structure):
     _fields_ = [('n_buffers', i32), ('n_ops', i32), ('n_weights', i32), ('max_batch', i32),
                 ('buffers', ctypes.POINTER(BufferDesc)), ('ops', ctypes.POINTER(OpDesc))]
@@ -58,6 +77,8 @@ SYMBOLS = {
     'dlwp_copy4d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_rows_op': (ctypes.c_int, [i32, fptr, fptr] + [i32] * 10 + [i64] * 6 + [i32, i32, ctypes.c_void_p]),
     'dlwp_plan_create': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    'dlwp_plan_create_opts': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(PlanOptions),
+                                              ctypes.POINTER(ctypes.c_void_p)]),
     'dlwp_plan_destroy': (None, [ctypes.c_void_p]),
     'dlwp_plan_set_weights': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, i64, fptr, i64]),
     'dlwp_plan_get_weights': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, i64, fptr, i64]),
@@ -77,6 +98,9 @@ SYMBOLS = {
     'dlwp_train_buffers': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64),
                                           ctypes.POINTER(ctypes.c_void_p)]),
     'dlwp_train_weight_offsets': (ctypes.c_int, [ctypes.c_void_p, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
+    'dlwp_train_regularize': (ctypes.c_int, [ctypes.c_void_p, i32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
+    'dlwp_train_adam_state': (ctypes.c_int, [ctypes.c_void_p, fptr, fptr, i64, ctypes.POINTER(i64), i32]),
     'dlwp_train_adam': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_void_p]),
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
@@ -92,7 +116,10 @@ SYMBOLS = {
                                            ctypes.POINTER(i32), i32]),
     'dlwp_debug_tc_pack': (ctypes.c_int64, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_uint16), ctypes.c_int64,
-                                            ctypes.POINTER(ctypes.c_uint32), i32]),
+                                            ctypes.POINTER(ctypes.c_uint32), i32, ctypes.POINTER(i32),
+                                            ctypes.POINTER(ctypes.c_float)]),
+    'dlwp_debug_tc_folded': (ctypes.c_char_p, [ctypes.POINTER(ConvDesc), i32]),
+    'dlwp_debug_exp_for_bound': (ctypes.c_int, [ctypes.c_float]),
 }
 
 
@@ -116,7 +143,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the ABI and the binding drift apart
             fn.restype = res
             fn.argtypes = args
-        if handle.dlwp_abi_version() != 1:
+        if handle.dlwp_abi_version() != ABI_VERSION:
             raise ImportError('libdlwp_b200.so ABI version mismatch')
         _lib = handle
     return _lib

@@ -542,12 +542,6 @@ struct TileChoice {
     dim3 grid;
 };
 
-// Environment overrides for on-GPU tuning runs: DLWP_TILE_TH, DLWP_TILE_CC, DLWP_TILE_NCG.
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     TileChoice tc;
     memset(&tc.p, 0, sizeof(tc.p));
@@ -586,7 +580,6 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     // --- filters per CTA ---
     const int groups = ceil_div(d.Cout, cout_t);
     int ncg = std::min(groups, 4);
-    ncg = env_int("DLWP_TILE_NCG", ncg);
     ncg = std::max(1, std::min(ncg, groups));
     // --- rows: aim for ~256-384 threads per CTA ---
     int th = 2 * std::max(1, std::min(8, 384 / (p.NXG * ncg)));
@@ -600,7 +593,6 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
         }
         th = best;
     }
-    th = env_int("DLWP_TILE_TH", th);
     th = std::max(2, round_up(th, 2));
     if (p.NXG * (th / 2) * ncg > 384) return tc;
     p.TH = th;
@@ -612,13 +604,12 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
     p.COUT_BP = ncg * cout_ld;
 
     // --- channel chunk: two stages of (input tile + weights) should leave room for 2 CTAs per SM ---
-    const int budget = env_int("DLWP_TILE_SMEM_KB", 100) * 1024;
+    const int budget = 100 * 1024;
     int cc = std::min(d.Cin, 16);
     auto stage_bytes = [&](int c) {
         return (size_t)(round_up(c * p.RIN * p.PITCH, 32) + round_up(c * d.kh * d.kw * p.COUT_BP, 32)) * 4;
     };
     while (cc > 1 && 2 * stage_bytes(cc) > (size_t)budget) cc = (cc > 4) ? cc - 2 : cc - 1;
-    cc = env_int("DLWP_TILE_CC", cc);
     cc = std::max(1, std::min(cc, d.Cin));
     p.CC = cc;
     p.nchunks = ceil_div(d.Cin, cc);
@@ -654,7 +645,7 @@ static TileChoice build_tiling(const DlwpConvDesc& d, bool use_tma) {
 
 static TileChoice choose_tiling(const DlwpConvDesc& d, int want_impl) {
     TileChoice tc;
-    const bool try_tma = want_impl == DLWP_IMPL_FFMA_TMA || (want_impl == DLWP_IMPL_AUTO && !env_int("DLWP_NO_TMA", 0));
+    const bool try_tma = want_impl == DLWP_IMPL_FFMA_TMA || want_impl == DLWP_IMPL_AUTO;
     if (try_tma) tc = build_tiling(d, true);
     if (!tc.ok && want_impl != DLWP_IMPL_FFMA_TMA) tc = build_tiling(d, false);
     return tc;

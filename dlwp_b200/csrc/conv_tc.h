@@ -1,7 +1,8 @@
-// Host-side interface of the tensor-core conv path (conv_tc.cu); internal, not part of the C ABI.
+// Host-side interface of the tensor-core conv path (conv_tc.cu, conv_fused.cu); internal, not part of the C ABI.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include <vector>
@@ -10,58 +11,112 @@
 
 namespace dlwp {
 
+constexpr int TC_HPAD = 12;  // zero rows stored above and below every P-layout plane (>= pad + rows per tile)
+constexpr int TC_MAX_KSTEPS = 32;
+
+// ---- power-of-two scaling of the fp16 hi/lo split -------------------------------------------------------------------
+// A P image stores x * 2^e as (hi, lo) fp16 pairs.  fp16 keeps 11 significant bits down to 2^-14 and a fixed 2^-24 step
+// below, so the pair carries 22 bits of a value v = x * 2^e as long as |v| >= 2^-3, and an absolute error of 2^-25
+// otherwise.  With max|v| placed in [2^13, 2^14) every element within 2^-16 of the image's maximum keeps 22 bits and the
+// rest are off by < 2^-38 of that maximum: fp32-level accuracy at any input / weight magnitude.  The exponents are exact
+// (powers of two), weights get theirs on the host when they are packed, activations on the device from a rigorous bound
+// |out| <= l1max(W) * amax(in) + max|b| evaluated with the MEASURED amax of the layer's input (tanh outputs: |y| <= 1,
+// static exponent TC_EXP_STATIC).  The consumer's epilogue multiplies the accumulator by 2^-(e_in + e_w).
+constexpr int TC_EXP_STATIC = 14;
+constexpr int TC_EXP_LIMIT = 60;
+
+// exponent e with B * 2^e in [2^13, 2^14) for a bound B on |values|; host and device
+__host__ __device__ inline int tc_exp_for_bound(float B) {
+    if (!(B > 1e-30f)) return TC_EXP_LIMIT;   // all zeros: any exponent works
+    if (!(B < 1e30f)) return -TC_EXP_LIMIT;   // inf / NaN: the caller raises the range flag
+    int ex;
+    (void)frexpf(B, &ex);                      // B = m * 2^ex, m in [0.5, 1)  ->  B < 2^ex
+    const int e = TC_EXP_STATIC - ex;
+    return e > TC_EXP_LIMIT ? TC_EXP_LIMIT : (e < -TC_EXP_LIMIT ? -TC_EXP_LIMIT : e);
+}
+
+// Scale bookkeeping of one launch.  Device words live in the plan (one exponent and two amax slots per P buffer).
+struct TcScale {
+    const int* e_in = nullptr;       // exponent of the source image (device word); null: e_in_const
+    int e_in_const = 0;
+    const float* amax_in = nullptr;  // measured max|x| of the source in true units (device word); null: 1
+    int* e_out = nullptr;            // exponent of the destination image, decided by this launch (device word); null: static
+    int e_out_const = TC_EXP_STATIC;
+    float* amax_out = nullptr;       // max|y| of this launch's outputs is atomically max-ed into this word (may be null)
+    float* amax_zero = nullptr;      // word to reset for the next production of the destination (may be null)
+    int e_w = 0;                     // exponent the weight image was packed with
+    float l1max = 0.f, bmax = 0.f;   // max over filters of sum|w|, max|bias| (true units): the output bound's coefficients
+};
+
+struct TcWeightScale {
+    int e_w = 0;
+    float l1max = 0.f;
+};
+
+// Tuning / triage switches, fixed when a plan is created (DlwpPlanOptions); never read from the environment here.
+struct TcOptions {
+    int generic = 0;     // 1: only the generic kernel instances (A/B against the folded ones)
+    int bands = 0;       // latitude bands per strip (0: chosen per launch)
+    int no_tma = 0;      // 1: per-plane bulk copies instead of tensor-map row loads
+    int taps_in_k = -1;  // -1: planner's choice
+    int debug = 0;       // 1: epilogue only waits/arrives, 2: issuer only commits (bottleneck triage; wrong results)
+};
+
 struct TcKStep {
     uint32_t a_off;  // byte offset (inside a stage) of the first 8-channel unit's hi plane, tap row included
     uint32_t a_lbo;  // byte distance to the second unit of this K=16 step
 };
 
-// Static schedule of one layer: how the P-layout input is tiled, staged and fed to the tensor core.
+// Static schedule of one layer: how the P-layout input is tiled, staged and fed to the tensor core (conv_sw_kernel:
+// M tile = 128 consecutive pixels of ONE row; every staged input row feeds all vertical taps with the same A operand,
+// one TMEM accumulator per output row in flight).
 struct TcLayer {
     int wpad, Wp;          // periodic halo columns per side of the INPUT image, padded width
     int C8, planes;        // 8-channel chunks of the input, planes = 2 * C8 (hi, lo)
     int CBLK, CSTRIDE, NCOLS;  // 8-filter blocks, TMEM columns per horizontal tap, MMA N
-    int S;                 // M-tile stride in pixels (128 - (kw-1)*dil, or 128 with taps_in_k)
-    int taps_in_k, kw_eff; // horizontal taps folded into K (small Cin) -> the epilogue sees a 1-tap layer
-    int R_out, Rin, MT;    // rows per tile, staged rows, M tiles per tile
-    int cpg, G, KS, NS;    // chunks per group, groups per tile, K=16 steps per group, smem stages
-    int NACC;              // TMEM accumulator sets (2 = double buffered)
-    uint32_t stage_bytes, stage_stride, plane_bytes, b_bytes;
+    int S;                 // valid outputs per strip: 128 - (kw-1)*dil
+    int taps_in_k, kw_eff; // horizontal taps folded into K (shifted A views) -> the epilogue sees a 1-tap layer
+    int KS, NS;            // K=16 steps per input row, shared-memory row stages
+    int NACC;              // TMEM accumulator ring (output rows in flight)
+    uint32_t stage_stride, b_bytes;
     size_t smem;
-    // sliding-window kernel (mode 1, conv_sw_kernel): M tile = 128 consecutive pixels of ONE row; every staged input row
-    // feeds all vertical taps (same A operand -> collector reuse), one TMEM accumulator per output row in flight
-    int mode;              // 0 = flattened-tile kernel (conv_tc_kernel), 1 = sliding window
-    int XLK;               // pixels an A view reaches to the right of its lane (horizontal taps folded into K)
     int nfull, rem, pair;  // full strips per row, valid outputs of the remainder strip, remainder strips of 2 samples share a tile
     uint32_t rowpitch;     // bytes of one staged plane row
 };
 
-bool tc_geometry_ok(const DlwpConvDesc& d);
-int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L);
+bool tc_geometry_ok(const DlwpConvDesc& d, const TcOptions& opt = TcOptions());
+int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L, const TcOptions& opt = TcOptions());
 int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
-                    TcKStep* kst_out);
+                    TcKStep* kst_out, TcWeightScale* ws);
 // Channel windows of P images (slice_layer / concatenate without copies): the conv reads planes
 // [in_plane0, in_plane0 + L.planes) of a source image that has in_planes_total planes per sample (0 = L.planes) and writes
 // planes [out_plane0, ...) of a destination image with planes_out planes per sample.
 struct TcWindow {
     int in_plane0 = 0, in_planes_total = 0, out_plane0 = 0;
-    // first layer of a rollout reading the fp32 (N,C,H,W) state directly (no P image of the state): dense source, see
-    // tc_f32in_ok; xp is ignored when x32 is set
-    const float* x32 = nullptr;
 };
-// The layer can take its input as fp32 (N,C,H,W) instead of a P image (the folded Net A first-layer instance only, for now).
-bool tc_f32in_ok(const DlwpConvDesc& d, const TcLayer& L);
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
-              const TcWindow& win = TcWindow());
+              const TcWindow& win, const TcScale& sc, const TcOptions& opt);
 // Data movers on P images (the U-Net's MaxPooling2D(2), UpSampling2D(2) and skip-connection copies): `planes` planes
 // starting at src_plane0 of the source -> planes starting at dst_plane0 of the destination; the destination's periodic
 // halo (wpad_d columns per side) is written with the interior.  kind: DLWP_OP_COPY / DLWP_OP_MAXPOOL / DLWP_OP_UPSAMPLE.
-// (Hs, Ws): source image size.
+// (Hs, Ws): source image size.  The values are moved bit for bit, so the destination inherits the source's exponent:
+// sc.e_in -> sc.e_out and sc.amax_in -> sc.amax_out are forwarded by the kernel (null pointers: nothing to forward).
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
                  int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream,
-                 int row_begin = 0, int row_end = 0);  // destination rows [row_begin, row_end); 0,0 = all
+                 int row_begin, int row_end, const TcScale& sc);  // destination rows [row_begin, row_end); 0,0 = all
+// fp32 (N,C,H,W) -> P image, rows [row0, row1) (0,0 = all).  fresh: measure max|x| over the WHOLE (N,C,H,W) tensor into
+// *amax (which must be zero), derive the image's exponent from it and publish it in *e; otherwise the image keeps the
+// exponent in *e (rows that join an image another kernel produced, e.g. halo rows received from a neighbour) and the
+// packed rows' max|x| is max-ed into *amax.
+struct TcPackScale {
+    int* e = nullptr;
+    float* amax = nullptr;
+    float* amax_zero = nullptr;
+    int fresh = 1;
+};
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
-                  long long xs_h, cudaStream_t stream, int row0 = 0, int row1 = 0);
+                  long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
                   cudaStream_t stream);
 int tc_debug_flags();

@@ -41,6 +41,9 @@ struct Buffer {
     // tensor-core chain: the same activation in P layout (fp16 hi/lo planes, periodic halo materialised)
     __half* P = nullptr;
     int wpad = -1, planes = 0;
+    // power-of-two exponent of the P image (conv_tc.h): static = TC_EXP_STATIC (every producer is a tanh conv or moves data
+    // from such an image), else decided per production on the device and kept in DlwpPlan::d_exp[buffer]
+    bool e_static = true;
 };
 
 struct Weight {
@@ -50,6 +53,8 @@ struct Weight {
     bool has_bias = false, set = false;
     __half* bimg = nullptr;        // tensor-core chain: packed hi/lo weight images
     TcKStep kst[32];
+    TcWeightScale ws;              // exponent the image was packed with, max_co sum|w| (the output bound's coefficient)
+    float bmax = 0.f;              // max|bias|
 };
 
 struct GraphKey {
@@ -88,9 +93,12 @@ struct DlwpPlan {
     // latitude band: rows [tc_band_row0, tc_band_row1) of the next input are re-packed by the feedback conv itself; only the
     // halo rows that arrive as fp32 from the neighbours ([tc_in_row0, band_row0) and [band_row1, tc_in_row1)) are packed
     int tc_band_row0 = 0, tc_band_row1 = 0;
-    // DLWP_SW_F32IN: every conv that reads the input buffer takes the fp32 state itself (no P image of the state, no pack
-    // kernel, no feedback copy written by the last layer)
-    bool tc_f32in = false;
+    DlwpPlanOptions opt;           // as given to dlwp_plan_create_opts (zeros = defaults)
+    TcOptions tc_opt;
+    // scale words of the P images (conv_tc.h): one exponent and two amax slots (production parity) per buffer
+    int* d_exp = nullptr;
+    float* d_amax = nullptr;
+    int tc_last_t = 0;             // iteration index of the last application (dlwp_plan_profile_op reuses its parity)
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     long long halo_cap = 0;
@@ -148,26 +156,25 @@ static DlwpConvDesc conv_desc_of(const DlwpPlan* pl, const DlwpOpDesc& op, int N
 // Chain = every activation lives in P layout (fp16 hi/lo planes, 8 channels per plane pair).  Convs run on the tcgen05
 // kernels; MaxPooling2D(2), UpSampling2D(2) and the skip-connection copies of the U-Net run as data movers on P images;
 // slice_layer / concatenate are plane windows (channel offsets must be multiples of 8).  Anything else (stand-alone
-// padding, RowConnected2D, pool/upsample fused into a conv, ...) keeps the whole plan on the fp32 kernels.
+// padding, RowConnected2D, pool/upsample fused into a conv, a data mover that produces a model output, ...) keeps the
+// whole plan on the fp32 kernels.
 static int tc_setup(DlwpPlan* pl) {
-    // Default: use the tensor-core chain whenever the whole plan is eligible.  DLWP_MATH=ffma (or any conv op forced to
-    // an FFMA/direct implementation) keeps the fp32 FFMA kernels.
-    const char* env = getenv("DLWP_MATH");
-    if (env && !strcmp(env, "ffma")) return 0;
+    // Default: use the tensor-core chain whenever the whole plan is eligible.  math = 1 (or any conv op forced to an
+    // FFMA/direct implementation) keeps the fp32 FFMA kernels.
+    if (pl->opt.math == 1) return 0;
     for (const DlwpOpDesc& op : pl->ops)
         if (op.kind == DLWP_OP_CONV && op.impl != DLWP_IMPL_AUTO && op.impl != DLWP_IMPL_TC) return 0;
     const int nops = (int)pl->ops.size();
+    const int nbuf = (int)pl->buffers.size();
     std::vector<TcLayer> layers(nops);
-    std::vector<int> wpad(pl->buffers.size(), -1);
-    std::vector<char> is_src(pl->buffers.size(), 0), written(pl->buffers.size(), 0);
-    bool windowed = false;
+    std::vector<int> wpad(nbuf, -1);
+    std::vector<char> is_src(nbuf, 0), written(nbuf, 0);
     auto chunk_window_ok = [](int c0, int c, int C) { return c0 % 8 == 0 && (c % 8 == 0 || c0 + c == C); };
     written[pl->input_buf] = 1;
     for (int i = 0; i < nops; ++i) {
         const DlwpOpDesc& op = pl->ops[i];
         const Buffer& s = pl->buffers[op.src];
         const Buffer& t = pl->buffers[op.dst];
-        if (op.row_begin || op.row_end) windowed = true;
         if (!written[op.src]) return 0;  // source must be the input or the result of an earlier op
         is_src[op.src] = 1;
         written[op.dst] = 1;
@@ -179,37 +186,21 @@ static int tc_setup(DlwpPlan* pl) {
                 else { pl->tc_in_row0 = std::min(pl->tc_in_row0, lo); pl->tc_in_row1 = std::max(pl->tc_in_row1, hi); }
             }
             if (!chunk_window_ok(op.src_c0, op.src_c, s.d.C) || !chunk_window_ok(op.dst_c0, op.Cout, t.d.C)) return 0;
-            const bool win = op.src_c0 != 0 || op.src_c != s.d.C || op.dst_c0 != 0 || op.Cout != t.d.C;
             DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
-            if (!tc_geometry_ok(d) || tc_plan_layer(d, &layers[i]) != 0) return 0;
-            if (win && layers[i].mode != 1) return 0;  // only the sliding-window kernel takes channel windows
+            if (!tc_geometry_ok(d, pl->tc_opt) || tc_plan_layer(d, &layers[i], pl->tc_opt) != 0) return 0;
             if (wpad[op.src] >= 0 && wpad[op.src] != layers[i].wpad) return 0;  // all conv readers must want the same halo
             wpad[op.src] = layers[i].wpad;
         } else if (op.kind == DLWP_OP_MAXPOOL || op.kind == DLWP_OP_UPSAMPLE || op.kind == DLWP_OP_COPY) {
             if (op.src_c0 % 8 || op.src_c % 8 || op.dst_c0 % 8) return 0;
             if (op.kind == DLWP_OP_MAXPOOL && ((s.d.H | s.d.W) & 1)) return 0;
+            // the data movers only write P images: a model output produced by one would never reach caller memory
+            if (t.d.kind == DLWP_BUF_OUTPUT) return 0;
         } else {
             return 0;
         }
     }
-    {
-        const char* env_f = getenv("DLWP_SW_F32IN");
-        bool f32in = env_f && atoi(env_f) != 0;
-        int readers = 0;
-        for (int i = 0; i < nops && f32in; ++i) {
-            const DlwpOpDesc& op = pl->ops[i];
-            if (op.src != pl->input_buf) continue;
-            ++readers;
-            const Buffer& s = pl->buffers[op.src];
-            DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
-            f32in = op.kind == DLWP_OP_CONV && op.src_c0 == 0 && op.src_c == s.d.C && op.dst_c0 == 0 &&
-                    pl->buffers[op.dst].d.kind == DLWP_BUF_INTERNAL && tc_f32in_ok(d, layers[i]);
-        }
-        pl->tc_f32in = f32in && readers > 0;
-    }
-    for (size_t b = 0; b < pl->buffers.size(); ++b)
+    for (int b = 0; b < nbuf; ++b)
         if (is_src[b]) {
-            if (pl->tc_f32in && (int)b == pl->input_buf) continue;  // read as fp32: no P image
             Buffer& B = pl->buffers[b];
             B.wpad = wpad[b] >= 0 ? wpad[b] : 0;  // read only by data movers: no halo needed
             B.planes = 2 * ((B.d.C + 7) / 8);
@@ -217,16 +208,21 @@ static int tc_setup(DlwpPlan* pl) {
     pl->tc_pdst.assign(nops, -1);
     for (int i = 0; i < nops; ++i)
         if (pl->buffers[pl->ops[i].dst].wpad >= 0) pl->tc_pdst[i] = pl->ops[i].dst;
-    // feedback: the producer of the LAST output re-packs the next iteration's input when shapes allow
+    // feedback: the producer of the LAST output re-packs the next iteration's input when shapes allow -- and when nothing
+    // from that op on still reads the input image (a single conv with Cin == Cout would overwrite rows and halo columns
+    // that other CTAs of the same launch are reading)
     const int last_out = pl->outputs.back();
     const Buffer& in = pl->buffers[pl->input_buf];
     const Buffer& lo = pl->buffers[last_out];
     int last_writer = -1, n_writers = 0;
     for (int i = 0; i < nops; ++i)
         if (pl->ops[i].dst == last_out) { last_writer = i; ++n_writers; }
+    bool input_read_late = false;
+    for (int i = std::max(0, last_writer); i < nops; ++i)
+        if (pl->ops[i].src == pl->input_buf) input_read_late = true;
     // (latitude bands: the conv re-packs its own band rows; the halo rows arrive as fp32 from the neighbours and are
     // packed after the exchange, see run_ops_tc)
-    if (n_writers == 1 && pl->ops[last_writer].kind == DLWP_OP_CONV && pl->tc_pdst[last_writer] < 0 &&
+    if (n_writers == 1 && !input_read_late && pl->ops[last_writer].kind == DLWP_OP_CONV && pl->tc_pdst[last_writer] < 0 &&
         pl->ops[last_writer].dst_c0 == 0 && pl->ops[last_writer].Cout == lo.d.C && lo.d.C == in.d.C && lo.d.H == in.d.H &&
         lo.d.W == in.d.W && in.wpad >= 0) {
         pl->tc_feedback_op = last_writer;
@@ -234,26 +230,53 @@ static int tc_setup(DlwpPlan* pl) {
         pl->tc_band_row0 = pl->ops[last_writer].row_begin;
         pl->tc_band_row1 = pl->ops[last_writer].row_end;
     }
+    // exponents: the input image and everything a linear / relu conv produces are dynamic (decided per production from
+    // the measured amax of the producer's source); tanh outputs and data moved from them are static.  A dynamic image has
+    // ONE exponent word, so it must have one producer.
+    for (Buffer& b : pl->buffers) b.e_static = true;
+    pl->buffers[pl->input_buf].e_static = false;
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int i = 0; i < nops; ++i) {
+            if (pl->tc_pdst[i] < 0 || pl->tc_pdst[i] == pl->input_buf) continue;
+            const DlwpOpDesc& op = pl->ops[i];
+            Buffer& t = pl->buffers[pl->tc_pdst[i]];
+            const bool dyn = op.kind == DLWP_OP_CONV ? op.act != DLWP_ACT_TANH : !pl->buffers[op.src].e_static;
+            if (dyn && t.e_static) { t.e_static = false; changed = true; }
+        }
+    }
+    std::vector<int> producers(nbuf, 0);
+    for (int i = 0; i < nops; ++i)
+        if (pl->tc_pdst[i] >= 0 && pl->tc_pdst[i] != pl->input_buf) ++producers[pl->tc_pdst[i]];
+    for (int b = 0; b < nbuf; ++b)
+        if (!pl->buffers[b].e_static && producers[b] > 1) return 0;
     for (Buffer& b : pl->buffers)
         if (b.wpad >= 0) {
             const size_t bytes = tc_p_bytes(pl->max_batch, b.planes, b.d.H, b.d.W + 2 * b.wpad);
             if (cudaMalloc(&b.P, bytes) != cudaSuccess) return DLWP_ENOMEM;
             cudaMemset(b.P, 0, bytes);
         }
+    if (cudaMalloc(&pl->d_exp, sizeof(int) * nbuf) != cudaSuccess) return DLWP_ENOMEM;
+    if (cudaMalloc(&pl->d_amax, sizeof(float) * 2 * nbuf) != cudaSuccess) return DLWP_ENOMEM;
+    cudaMemset(pl->d_exp, 0, sizeof(int) * nbuf);
+    cudaMemset(pl->d_amax, 0, sizeof(float) * 2 * nbuf);
     pl->tc_layers = layers;
     pl->tc = true;
     return 0;
 }
 
-static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel_host) {
+static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel_host, const float* bias_host) {
     for (size_t i = 0; i < pl->ops.size(); ++i) {
         const DlwpOpDesc& op = pl->ops[i];
         if (op.weight_id != weight_id) continue;
         Weight& w = pl->weights[weight_id];
         DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
         std::vector<__half> img;
-        DLWP_REQUIRE(tc_pack_weights(d, pl->tc_layers[i], kernel_host, &img, w.kst) == 0,
-                     DLWP_ESHAPE, "tensor-core weight packing failed for weight %d", weight_id);
+        DLWP_REQUIRE(tc_pack_weights(d, pl->tc_layers[i], kernel_host, &img, w.kst, &w.ws) == 0,
+                     DLWP_ESHAPE, "tensor-core weight packing failed for weight %d (non-finite weights?)", weight_id);
+        w.bmax = 0.f;
+        if (bias_host)
+            for (long long k = 0; k < w.b_elems; ++k) w.bmax = std::max(w.bmax, fabsf(bias_host[k]));
         if (!w.bimg) DLWP_CUDA_TRY(cudaMalloc(&w.bimg, img.size() * sizeof(__half)));
         DLWP_CUDA_TRY(cudaMemcpy(w.bimg, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
         return 0;  // ops sharing a weight id share geometry and therefore the image
@@ -261,54 +284,87 @@ static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel
     return 0;
 }
 
-static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream) {
+// Scale words of one op at iteration t (conv_tc.h).  An image produced at iteration t is read at iteration t, except
+// the input image: the feedback conv of iteration t produces the input of iteration t + 1 (production index t + 1).
+static TcScale scale_of(const DlwpPlan* pl, int i, int t) {
+    const DlwpOpDesc& op = pl->ops[i];
+    TcScale sc;
+    const Buffer& s = pl->buffers[op.src];
+    if (!s.e_static) sc.e_in = pl->d_exp + op.src;
+    sc.e_in_const = TC_EXP_STATIC;
+    sc.amax_in = pl->d_amax + 2 * op.src + (t & 1);
+    const int pd = pl->tc_pdst[i];
+    if (pd >= 0) {
+        const int prod = pd == pl->input_buf ? t + 1 : t;
+        if (!pl->buffers[pd].e_static) sc.e_out = pl->d_exp + pd;
+        sc.amax_out = pl->d_amax + 2 * pd + (prod & 1);
+        sc.amax_zero = pl->d_amax + 2 * pd + ((prod + 1) & 1);
+    }
+    if (op.kind == DLWP_OP_CONV) {
+        const Weight& w = pl->weights[op.weight_id];
+        sc.e_w = w.ws.e_w; sc.l1max = w.ws.l1max; sc.bmax = w.has_bias ? w.bmax : 0.f;
+    }
+    return sc;
+}
+
+static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bool feedback_write) {
     const DlwpOpDesc& op = pl->ops[i];
     const Buffer& s = pl->buffers[op.src];
-    const Buffer& t = pl->buffers[op.dst];
+    const Buffer& b = pl->buffers[op.dst];
+    int pd = pl->tc_pdst[i];
+    if (pd == pl->input_buf && i == pl->tc_feedback_op && !feedback_write) pd = -1;  // plain forward: nobody reads it
+    TcScale sc = scale_of(pl, i, t);
+    if (pd < 0) { sc.e_out = nullptr; sc.amax_out = nullptr; sc.amax_zero = nullptr; }
     if (op.kind != DLWP_OP_CONV) {  // data mover on P images
-        if (pl->tc_pdst[i] < 0) return 0;  // nobody reads the result in P layout
-        const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
+        if (pd < 0) return 0;  // nobody reads the result in P layout
+        const Buffer& pb = pl->buffers[pd];
         return tc_ew_launch(op.kind, s.P, pb.P, N, 2 * (op.src_c / 8), s.d.H, s.d.W, s.wpad, 2 * (op.src_c0 / 8), s.planes,
-                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream, op.row_begin, op.row_end);
+                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream, op.row_begin, op.row_end, sc);
     }
     const Weight& w = pl->weights[op.weight_id];
     DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);
     DlwpConvDesc d = conv_desc_of(pl, op, N);
-    float* y32 = (t.d.kind == DLWP_BUF_OUTPUT) ? t.ptr + (long long)op.dst_c0 * t.d.H * t.d.W : nullptr;
+    float* y32 = (b.d.kind == DLWP_BUF_OUTPUT) ? b.ptr + (long long)op.dst_c0 * b.d.H * b.d.W : nullptr;
     __half* yp = nullptr;
     int wpad_out = 0, planes_out = 0;
     TcWindow win;
     win.in_plane0 = 2 * (op.src_c0 / 8);
     win.in_planes_total = s.planes;
-    if (pl->tc_f32in && op.src == pl->input_buf) win.x32 = s.ptr;
-    if (pl->tc_pdst[i] >= 0) {
-        const Buffer& pb = pl->buffers[pl->tc_pdst[i]];
+    if (pd >= 0) {
+        const Buffer& pb = pl->buffers[pd];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
-        win.out_plane0 = pl->tc_pdst[i] == op.dst ? 2 * (op.dst_c0 / 8) : 0;
+        win.out_plane0 = pd == op.dst ? 2 * (op.dst_c0 / 8) : 0;
     }
     return tc_launch(d, pl->tc_layers[i], w.kst, s.P, w.bimg, w.has_bias ? w.b : nullptr, y32, yp, wpad_out,
-                     planes_out, stream, win);
+                     planes_out, stream, win, sc, pl->tc_opt);
 }
 
-static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, bool input_is_packed) {
+// One application of the chain at iteration t.  input_is_packed: the feedback conv of iteration t - 1 already wrote the
+// input image (rollout).  feedback_write: let the feedback conv write the next input image (off for a plain forward).
+static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool input_is_packed, bool feedback_write) {
     Buffer& in = pl->buffers[pl->input_buf];
-    if (pl->tc_f32in) {
-        // the first layer reads the fp32 state (and, in a latitude band, the halo rows the exchange wrote into it) directly
-    } else if (!input_is_packed) {
+    pl->tc_last_t = t;
+    TcPackScale ps;
+    ps.e = pl->d_exp + pl->input_buf;
+    ps.amax = pl->d_amax + 2 * pl->input_buf + (t & 1);
+    if (!input_is_packed) {
+        ps.fresh = 1;
+        ps.amax_zero = pl->d_amax + 2 * pl->input_buf + ((t + 1) & 1);
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
-                               (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1);
+                               (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1, ps);
         if (rc) return rc;
     } else if (pl->tc_band_row1 > 0) {  // latitude band: pack the halo rows received from the neighbours
+        ps.fresh = 0;
         const int lo[2] = {pl->tc_in_row0, pl->tc_band_row1}, hi[2] = {pl->tc_band_row0, pl->tc_in_row1};
         for (int k = 0; k < 2; ++k)
             if (hi[k] > lo[k]) {
                 int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
-                                       (long long)in.d.H * in.d.W, in.d.W, stream, lo[k], hi[k]);
+                                       (long long)in.d.H * in.d.W, in.d.W, stream, lo[k], hi[k], ps);
                 if (rc) return rc;
             }
     }
     for (size_t i = 0; i < pl->ops.size(); ++i) {
-        int rc = run_one_tc(pl, (int)i, N, stream);
+        int rc = run_one_tc(pl, (int)i, N, stream, t, feedback_write);
         if (rc) return rc;
     }
     return 0;
@@ -379,11 +435,13 @@ static int check_rollout_shapes(const DlwpPlan* pl) {
 static int rollout_range(DlwpPlan* pl, int N, const float* x0, float* series, int t0, int t1, cudaStream_t stream) {
     const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
     const int n_out = (int)pl->outputs.size();
+    if (pl->tc && t0 == 0)  // a new rollout: every image's amax slots start from zero
+        DLWP_CUDA_TRY(cudaMemsetAsync(pl->d_amax, 0, sizeof(float) * 2 * pl->buffers.size(), stream));
     for (int t = t0; t < t1; ++t) {
         pl->buffers[pl->input_buf].ptr =
             const_cast<float*>(t == 0 ? x0 : series + ((long long)t * n_out - 1) * slot);
         for (int k = 0; k < n_out; ++k) pl->buffers[pl->outputs[k]].ptr = series + ((long long)t * n_out + k) * slot;
-        int rc = pl->tc ? run_ops_tc(pl, N, stream, t > 0 && pl->tc_feedback_op >= 0) : run_ops(pl, N, stream);
+        int rc = pl->tc ? run_ops_tc(pl, N, stream, t, t > 0 && pl->tc_feedback_op >= 0, true) : run_ops(pl, N, stream);
         if (rc) return rc;
     }
     return 0;
@@ -410,6 +468,10 @@ extern "C" int dlwp_conv2d_fwd(const DlwpConvDesc* desc, const float* x, const f
 }
 
 extern "C" int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** out) {
+    return dlwp_plan_create_opts(net, nullptr, out);
+}
+
+extern "C" int dlwp_plan_create_opts(const DlwpNetDesc* net, const DlwpPlanOptions* opts, DlwpPlan** out) {
     DLWP_REQUIRE(net && out, DLWP_EINVAL, "null argument");
     *out = nullptr;
     DLWP_REQUIRE(net->n_buffers > 0 && net->n_ops > 0 && net->max_batch > 0 && net->buffers && net->ops,
@@ -417,6 +479,14 @@ extern "C" int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** out) {
     int rc = check_device();
     if (rc) return rc;
     DlwpPlan* pl = new DlwpPlan();
+    memset(&pl->opt, 0, sizeof(pl->opt));
+    pl->opt.tc_taps_in_k = -1;
+    if (opts) pl->opt = *opts;
+    pl->tc_opt.generic = pl->opt.tc_generic;
+    pl->tc_opt.bands = pl->opt.tc_bands;
+    pl->tc_opt.no_tma = pl->opt.tc_no_tma;
+    pl->tc_opt.taps_in_k = pl->opt.tc_taps_in_k;
+    pl->tc_opt.debug = pl->opt.tc_debug;
     pl->max_batch = net->max_batch;
     pl->buffers.resize(net->n_buffers);
     int n_outputs = 0;
@@ -520,6 +590,8 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
     for (Buffer& b : pl->buffers)
         if (b.P) cudaFree(b.P);
+    if (pl->d_exp) cudaFree(pl->d_exp);
+    if (pl->d_amax) cudaFree(pl->d_amax);
     for (Weight& w : pl->weights) {
         if (w.bimg) cudaFree(w.bimg);
         if (w.k) cudaFree(w.k);
@@ -548,7 +620,7 @@ extern "C" int dlwp_plan_set_weights(DlwpPlan* pl, int32_t id, const float* kern
     if (bias) DLWP_CUDA_TRY(cudaMemcpy(w.b, bias, sizeof(float) * w.b_elems, cudaMemcpyHostToDevice));
     w.has_bias = bias != nullptr;
     w.set = true;
-    if (pl->tc) return tc_pack_plan_weights(pl, id, kernel);
+    if (pl->tc) return tc_pack_plan_weights(pl, id, kernel, bias);
     return 0;
 }
 
@@ -574,7 +646,9 @@ extern "C" int dlwp_plan_forward(DlwpPlan* pl, int32_t N, const float* x, float*
         DLWP_REQUIRE(outputs[k] != nullptr, DLWP_EINVAL, "output %zu is null", k);
         pl->buffers[pl->outputs[k]].ptr = outputs[k];
     }
-    return pl->tc ? run_ops_tc(pl, N, (cudaStream_t)stream, false) : run_ops(pl, N, (cudaStream_t)stream);
+    if (!pl->tc) return run_ops(pl, N, (cudaStream_t)stream);
+    DLWP_CUDA_TRY(cudaMemsetAsync(pl->d_amax, 0, sizeof(float) * 2 * pl->buffers.size(), (cudaStream_t)stream));
+    return run_ops_tc(pl, N, (cudaStream_t)stream, 0, false, false);
 }
 
 extern "C" int dlwp_rollout(DlwpPlan* pl, int32_t N, const float* x0, float* series, int32_t iterations,
@@ -679,10 +753,11 @@ extern "C" int dlwp_plan_profile_op(DlwpPlan* pl, int32_t N, int32_t op_index, i
     DLWP_CUDA_TRY(cudaEventCreate(&e0));
     DLWP_CUDA_TRY(cudaEventCreate(&e1));
     int rc = 0;
-    for (int w = 0; w < 2 && !rc; ++w) rc = pl->tc ? run_one_tc(pl, op_index, N, stream) : run_one(pl, op_index, N, stream);
+    const int pt = pl->tc_last_t;
+    for (int w = 0; w < 2 && !rc; ++w) rc = pl->tc ? run_one_tc(pl, op_index, N, stream, pt, true) : run_one(pl, op_index, N, stream);
     cudaEventRecord(e0, stream);
     for (int k = 0; k < iters && !rc; ++k)
-        rc = pl->tc ? run_one_tc(pl, op_index, N, stream) : run_one(pl, op_index, N, stream);
+        rc = pl->tc ? run_one_tc(pl, op_index, N, stream, pt, true) : run_one(pl, op_index, N, stream);
     cudaEventRecord(e1, stream);
     cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -866,7 +941,7 @@ extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const f
 namespace dlwp {
 static int train_setup(DlwpPlan* pl) {
     if (pl->train_ready) return 0;
-    DLWP_REQUIRE(!pl->tc, DLWP_ESTATE, "training needs the fp32 plan (create it with DLWP_MATH=ffma)");
+    DLWP_REQUIRE(!pl->tc, DLWP_ESTATE, "training needs the fp32 plan (create it with DlwpPlanOptions.math = 1)");
     for (const DlwpOpDesc& op : pl->ops) {
         DLWP_REQUIRE(op.kind != DLWP_OP_PAD, DLWP_ESHAPE, "stand-alone padding layers are not differentiable here yet");
         DLWP_REQUIRE(!(op.kind == DLWP_OP_CONV && (op.rowwise || op.pre_op)), DLWP_ESHAPE,
@@ -995,6 +1070,45 @@ extern "C" int dlwp_train_weight_offsets(DlwpPlan* pl, int32_t weight_id, int64_
     DLWP_REQUIRE(pl && pl->train_ready && weight_id >= 0 && weight_id < (int)pl->weights.size(), DLWP_ESTATE, "bad state");
     *kernel_off = pl->gk_off[weight_id];
     *bias_off = pl->gb_off[weight_id];
+    return 0;
+}
+
+extern "C" int dlwp_train_regularize(DlwpPlan* pl, int32_t weight_id, float kernel_l1, float kernel_l2, float bias_l1,
+                                     float bias_l2, float* penalty, dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && pl->train_ready && penalty, DLWP_ESTATE, "run dlwp_train_step first");
+    DLWP_REQUIRE(weight_id >= 0 && weight_id < (int)pl->weights.size(), DLWP_EINVAL, "weight id %d out of range", weight_id);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Weight& W = pl->weights[weight_id];
+    DLWP_CUDA_TRY(cudaMemsetAsync(pl->stats, 0, sizeof(float), stream));
+    int rc = 0;
+    if (kernel_l1 != 0.f || kernel_l2 != 0.f)
+        rc = regularize_grad(W.k, pl->flat_g + pl->gk_off[weight_id], W.k_elems, kernel_l1, kernel_l2, pl->stats, stream);
+    if (!rc && W.has_bias && (bias_l1 != 0.f || bias_l2 != 0.f))
+        rc = regularize_grad(W.b, pl->flat_g + pl->gb_off[weight_id], W.b_elems, bias_l1, bias_l2, pl->stats, stream);
+    if (rc) return rc;
+    DLWP_CUDA_TRY(cudaMemcpyAsync(penalty, pl->stats, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    DLWP_CUDA_TRY(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+extern "C" int dlwp_train_adam_state(DlwpPlan* pl, float* m_host, float* v_host, int64_t elems, int64_t* step,
+                                     int32_t set) {
+    DLWP_REQUIRE(pl && m_host && v_host && step, DLWP_EINVAL, "null argument");
+    if (set) {
+        int rc = train_setup(pl);
+        if (rc) return rc;
+    }
+    DLWP_REQUIRE(pl->train_ready, DLWP_ESTATE, "the plan has no optimizer state yet");
+    DLWP_REQUIRE(elems == pl->flat_elems, DLWP_ESHAPE, "optimizer state has %lld elements, expected %lld",
+                 (long long)elems, pl->flat_elems);
+    DLWP_CUDA_TRY(cudaDeviceSynchronize());
+    const cudaMemcpyKind kind = set ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    DLWP_CUDA_TRY(cudaMemcpy(set ? (void*)pl->flat_m : (void*)m_host, set ? (void*)m_host : (void*)pl->flat_m,
+                             sizeof(float) * elems, kind));
+    DLWP_CUDA_TRY(cudaMemcpy(set ? (void*)pl->flat_v : (void*)v_host, set ? (void*)v_host : (void*)pl->flat_v,
+                             sizeof(float) * elems, kind));
+    if (set) pl->adam_t = *step;
+    else *step = pl->adam_t;
     return 0;
 }
 

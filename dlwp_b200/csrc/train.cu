@@ -306,6 +306,22 @@ int mse_grad(const float* yhat, const float* y, float* g, long long n, float sca
     mse_grad_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, g, n, scale, stats, wmap, hw);
     return after_launch("mse_grad_kernel");
 }
+// keras regularizers.L1L2 on one weight tensor: g += l1 * sign(w) + 2 * l2 * w; penalty = sum(l1 |w| + l2 w^2) -> *stat
+__global__ void __launch_bounds__(256) regularize_kernel(const float* __restrict__ w, float* __restrict__ g, long long n,
+                                                         float l1, float l2, float* stat) {
+    float pen = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = w[i];
+        g[i] += l1 * (v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f)) + 2.f * l2 * v;
+        pen += l1 * fabsf(v) + l2 * v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) pen += __shfl_down_sync(0xffffffffu, pen, o);
+    if ((threadIdx.x & 31) == 0 && pen != 0.f) atomicAdd(stat, pen);
+}
+int regularize_grad(const float* w, float* g, long long n, float l1, float l2, float* stat, cudaStream_t stream) {
+    regularize_kernel<<<blocks_for(n), 256, 0, stream>>>(w, g, n, l1, l2, stat);
+    return after_launch("regularize_kernel");
+}
 int adam_step(float* w, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
               cudaStream_t stream) {
     adam_kernel<<<blocks_for(n), 256, 0, stream>>>(w, g, m, v, n, lr_t, b1, b2, eps);

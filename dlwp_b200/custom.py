@@ -112,6 +112,19 @@ class RowConnected2D(Conv2D):
 # Losses (host-side definitions; the training path maps the names to device code)
 # ==================================================================================================================== #
 
+class _LatLoss(object):
+    """The `lat_loss` closure of DLWP/custom.py:986-990 as a picklable callable (util.save_model pickles the compile
+    arguments; a nested function cannot be pickled)."""
+    __name__ = 'lat_loss'
+
+    def __init__(self, base_loss, weights):
+        self.base_loss = base_loss
+        self.weights = np.asarray(weights, np.float32)
+
+    def __call__(self, y_true, y_pred):
+        return self.base_loss(y_true * self.weights, y_pred * self.weights)
+
+
 def latitude_weighted_loss(loss_function=mean_squared_error, lats=None, output_shape=(), axis=-2, weighting='cosine'):
     """
     DLWP/custom.py:956-991: multiply y_true and y_pred by a function of latitude before `loss_function`.
@@ -129,13 +142,7 @@ def latitude_weighted_loss(loss_function=mean_squared_error, lats=None, output_s
             weights = np.repeat(np.expand_dims(weights, axis=-1), d, axis=-1)
     else:
         weights = np.ones(tuple(output_shape), np.float32)
-
-    def lat_loss(y_true, y_pred):
-        return loss_function(y_true * weights, y_pred * weights)
-
-    lat_loss.weights = np.asarray(weights, np.float32)
-    lat_loss.base_loss = loss_function
-    return lat_loss
+    return _LatLoss(loss_function, weights)
 
 
 def anomaly_correlation(y_true, y_pred, mean=0., regularize_mean='mse', reverse=True):
@@ -158,6 +165,20 @@ def anomaly_correlation(y_true, y_pred, mean=0., regularize_mean='mse', reverse=
     return a - m if regularize_mean else a
 
 
+class _AccLoss(object):
+    """The `acc_loss` closure of DLWP/custom.py:1080-1086 as a picklable callable."""
+    __name__ = 'acc_loss'
+
+    def __init__(self, mean, regularize_mean, reverse):
+        self.mean, self.regularize_mean, self.reverse = mean, regularize_mean, reverse
+
+    def __call__(self, y_true, y_pred):
+        if self.mean is not None:
+            return anomaly_correlation(y_true - self.mean, y_pred - self.mean, regularize_mean=self.regularize_mean,
+                                       reverse=self.reverse)
+        return anomaly_correlation(y_true, y_pred, regularize_mean=self.regularize_mean, reverse=self.reverse)
+
+
 def anomaly_correlation_loss(mean=None, regularize_mean='mse', reverse=True):
     """DLWP/custom.py:1036-1088."""
     if mean is not None:
@@ -166,13 +187,7 @@ def anomaly_correlation_loss(mean=None, regularize_mean='mse', reverse=True):
     if regularize_mean is not None:
         assert regularize_mean in ['global', 'spatial', 'mse', 'mae']
         reverse = True
-
-    def acc_loss(y_true, y_pred):
-        if mean is not None:
-            return anomaly_correlation(y_true - mean, y_pred - mean, regularize_mean=regularize_mean, reverse=reverse)
-        return anomaly_correlation(y_true, y_pred, regularize_mean=regularize_mean, reverse=reverse)
-
-    return acc_loss
+    return _AccLoss(mean, regularize_mean, reverse)
 
 
 # Defined at import time so that models saved with these losses can be re-loaded by name (custom.py:1092-1093)

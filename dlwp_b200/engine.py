@@ -273,18 +273,24 @@ def _torch():
 class CompiledNet(object):
     """A DlwpPlan plus the host-side glue around it.  Created lazily by keras.Model.engine()."""
 
-    FLAG_TC_RANGE = 4   # dlwp_debug_flags bit: a value left the fp16 hi/lo split's range (|x| > 65504)
+    # dlwp_debug_flags bits that void a tensor-core result: NaN / inf data, or a statically scaled tanh image whose amax
+    # fell below 2^-6 in scaled units (precision underflow)
+    FLAG_TC_FALLBACK = nat.FLAG_TC_RANGE | nat.FLAG_TC_UNDERFLOW
 
-    def __init__(self, model, batch, impl=None, row_windows=None, force_ffma=False):
+    def __init__(self, model, batch, impl=None, row_windows=None, force_ffma=False, options=None):
         """force_ffma: build the plan on the fp32 kernels (training needs fp32 intermediates).
         row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
-        (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op."""
+        (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op.
+        options: dict of DlwpPlanOptions fields (math, fuse, tc_generic, tc_bands, tc_no_tma, tc_taps_in_k, tc_debug).
+        The environment variable DLWP_MATH=ffma is honoured HERE (scripts / bench.py --math), never inside the library."""
         self.torch = _torch()
         self.lib = nat.lib()
         self.model = model
         self.low = Lowering(model)
         self.row_windows = row_windows
-        self._force_ffma = bool(force_ffma)
+        self.options = dict(options or {})
+        import os
+        self._force_ffma = bool(force_ffma) or (os.environ.get('DLWP_MATH') == 'ffma' and 'math' not in self.options)
         self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
         self.plan = ctypes.c_void_p()
         self.max_batch = 0
@@ -324,18 +330,12 @@ class CompiledNet(object):
         for i, o in enumerate(live):
             ops[i] = nat.OpDesc(*[int(o[n]) for n in names])
         net = nat.NetDesc(len(bufs), len(ops), len(self.low.weight_layers), int(max_batch), bufs, ops)
-        import os
-        saved = os.environ.get('DLWP_MATH')
-        if getattr(self, '_force_ffma', False):
-            os.environ['DLWP_MATH'] = 'ffma'
-        try:
-            nat.check(self.lib.dlwp_plan_create(ctypes.byref(net), ctypes.byref(self.plan)), 'dlwp_plan_create')
-        finally:
-            if getattr(self, '_force_ffma', False):
-                if saved is None:
-                    os.environ.pop('DLWP_MATH', None)
-                else:
-                    os.environ['DLWP_MATH'] = saved
+        opts = dict(self.options)
+        if self._force_ffma:
+            opts['math'] = nat.MATH_FFMA
+        po = nat.PlanOptions(**opts)
+        nat.check(self.lib.dlwp_plan_create_opts(ctypes.byref(net), ctypes.byref(po), ctypes.byref(self.plan)),
+                  'dlwp_plan_create_opts')
         self.max_batch = int(max_batch)
         self._pushed = {}
         self.sync_weights()
@@ -436,6 +436,59 @@ class CompiledNet(object):
     def adam(self, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
         nat.check(self.lib.dlwp_train_adam(self.plan, lr, beta_1, beta_2, epsilon, self._stream()), 'dlwp_train_adam')
 
+    def _regularizers(self):
+        """(weight id, kernel l1, kernel l2, bias l1, bias l2) of every layer that carries a keras regularizer."""
+        out = []
+        for wid, layer in enumerate(self.low.weight_layers):
+            kr, br = getattr(layer, 'kernel_regularizer', None), getattr(layer, 'bias_regularizer', None)
+            vals = [float(getattr(kr, 'l1', 0.) or 0.), float(getattr(kr, 'l2', 0.) or 0.),
+                    float(getattr(br, 'l1', 0.) or 0.), float(getattr(br, 'l2', 0.) or 0.)]
+            for r in (kr, br):
+                if r is not None and not (hasattr(r, 'l1') and hasattr(r, 'l2')):
+                    raise NotImplementedError('only keras.regularizers.l1 / l2 / L1L2 are implemented, got %r' % (r,))
+            if any(vals):
+                out.append((wid,) + tuple(vals))
+        return out
+
+    def regularize(self):
+        """Add every layer's L1/L2 term to the flat gradient buffer (call between train_step and adam); returns the
+        penalty Keras adds to the loss."""
+        total = 0.0
+        for wid, kl1, kl2, bl1, bl2 in self._regularizers():
+            pen = ctypes.c_float(0)
+            nat.check(self.lib.dlwp_train_regularize(self.plan, wid, kl1, kl2, bl1, bl2, ctypes.byref(pen),
+                                                     self._stream()), 'dlwp_train_regularize')
+            total += float(pen.value)
+        return total
+
+    def regularization_penalty(self):
+        """The same penalty from the host copy of the weights (evaluation: no gradient to touch)."""
+        total = 0.0
+        for wid, kl1, kl2, bl1, bl2 in self._regularizers():
+            layer = self.low.weight_layers[wid]
+            k = np.asarray(layer._weights[0], np.float64)
+            total += kl1 * np.abs(k).sum() + kl2 * np.square(k).sum()
+            if layer.use_bias:
+                b = np.asarray(layer._weights[1], np.float64)
+                total += bl1 * np.abs(b).sum() + bl2 * np.square(b).sum()
+        return float(total)
+
+    def adam_state(self):
+        """(m, v, step) of the optimizer, host copies; None before the first training step."""
+        g = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        if self.lib.dlwp_train_buffers(self.plan, ctypes.byref(g), ctypes.byref(n), None) != 0:
+            return None
+        m, v, t = np.empty(n.value, np.float32), np.empty(n.value, np.float32), ctypes.c_int64(0)
+        nat.check(self.lib.dlwp_train_adam_state(self.plan, m.ctypes.data, v.ctypes.data, n.value, ctypes.byref(t), 0),
+                  'dlwp_train_adam_state')
+        return m, v, int(t.value)
+
+    def set_adam_state(self, m, v, step):
+        t = ctypes.c_int64(int(step))
+        nat.check(self.lib.dlwp_train_adam_state(self.plan, m.ctypes.data, v.ctypes.data, m.size, ctypes.byref(t), 1),
+                  'dlwp_train_adam_state')
+
     def pull_weights(self):
         """Device weights -> the front-end layers (after optimizer steps)."""
         for wid, layer in enumerate(self.low.weight_layers):
@@ -458,19 +511,24 @@ class CompiledNet(object):
                                                 self._stream()), 'dlwp_plan_profile_op')
         return float(ms.value)
 
+    def check_flags(self):
+        """Read-and-clear the device flags (synchronises).  True = the last tensor-core results must not be trusted: the
+        data held NaN / inf, or a tanh image underflowed its static scale.  The device-resident entry points
+        (rollout_device, forward_device, forward_into) are asynchronous and do NOT check; call this after them."""
+        return bool(int(self.lib.dlwp_debug_flags()) & self.FLAG_TC_FALLBACK) and self.uses_tensor_cores()
+
     def _range_fallback(self):
         """
-        The tensor-core path stores activations as fp16 hi/lo pairs: fine for the standardised fields DLWP feeds its nets,
-        but |x| > 65504 overflows.  The kernels raise a device flag when that happens; the host-level entry points then
-        rebuild the plan on the fp32 FFMA kernels and redo the call (True = caller must rerun).
+        The tensor-core path stores activations as power-of-two scaled fp16 hi/lo pairs whose exponents follow the data
+        (csrc/conv_tc.h), so any finite fp32 magnitude is fine.  What it cannot represent is NaN / inf, and a tanh layer
+        whose outputs are ALL below ~1e-6 underflows its static scale: the kernels raise a device flag, the host-level
+        entry points then rebuild the plan on the fp32 FFMA kernels and redo the call (True = caller must rerun).
         """
-        if not self.uses_tensor_cores():
-            return False
-        if not (int(self.lib.dlwp_debug_flags()) & self.FLAG_TC_RANGE):
+        if not self.check_flags():
             return False
         import warnings
-        warnings.warn('dlwp_b200: activations exceed the fp16-split range of the tensor-core path; '
-                      'falling back to the fp32 FFMA kernels for this model')
+        warnings.warn('dlwp_b200: non-finite activations or a precision underflow on the tensor-core path (fp16-split '
+                      'range); falling back to the fp32 FFMA kernels for this model')
         self._force_ffma = True
         mb = self.max_batch
         self.close()
@@ -502,7 +560,9 @@ class CompiledNet(object):
         return all(p == self.in_shape for p in self.out_phys)
 
     def rollout_device(self, x0, iterations, use_graph=True, out=None):
-        """Device-resident rollout.  x0: CUDA (N,C,H,W).  Returns a CUDA tensor (iterations*n_outputs, N, C, H, W)."""
+        """Device-resident rollout.  x0: CUDA (N,C,H,W).  Returns a CUDA tensor (iterations*n_outputs, N, C, H, W).
+        Asynchronous: no range check happens here (NaN / inf inputs give garbage on the tensor-core path); call
+        check_flags() afterwards, or use rollout_host / predict, which check and fall back."""
         torch = self.torch
         assert x0.is_cuda and x0.dtype == torch.float32 and x0.is_contiguous()
         n = x0.shape[0]

@@ -361,9 +361,11 @@ class Model(object):
 
     # -- persistence ---------------------------------------------------------------------------------------------
     def __getstate__(self):
+        # runtime handles (ctypes plan pointers, torch modules, the History callback's model back-reference) never travel
         d = self.__dict__.copy()
-        d['_engine'] = None
-        d['_engine_key'] = None
+        for k in ('_engine', '_engine_key', '_train_engine', '_train_key', 'history'):
+            if k in d:
+                d[k] = None
         return d
 
     def save(self, filepath, overwrite=True, include_optimizer=True):

@@ -38,11 +38,15 @@ def _engine(model, batch):
     from .engine import CompiledNet
     eng = getattr(model, '_train_engine', None)
     if eng is None or eng.max_batch < batch:
+        state = None
         if eng is not None:
+            state = eng.adam_state()          # a larger batch arrived: the Adam moments and step count move to the new plan
             eng.close()
         eng = CompiledNet(model, batch, force_ffma=True)
         if eng.max_batch < batch:
             raise MemoryError('training batch %d does not fit the device' % batch)
+        if state is not None:
+            eng.set_adam_state(*state)
         wmap = _loss_weight_map(model, eng)
         if wmap is not None:
             from . import _native as nat
@@ -97,11 +101,16 @@ def _step(model, x, y, train):
             g.div_(dist.get_world_size())
         if opt.__class__.__name__ != 'Adam':
             raise NotImplementedError('dlwp_b200 implements the Adam update (the optimizer of every DLWP example)')
+        if getattr(opt, 'amsgrad', False):
+            raise NotImplementedError('Adam(amsgrad=True) is not implemented')
+        penalty = eng.regularize()            # kernel_regularizer / bias_regularizer: gradient term + loss penalty
         lr = opt.lr * (1. / (1. + opt.decay * opt.iterations))
         eng.adam(lr, opt.beta_1, opt.beta_2, opt.epsilon)
         opt.iterations += 1
+    else:
+        penalty = eng.regularization_penalty()
     w = [1.0] * len(losses) if lw is None else list(lw)
-    logs = {'loss': float(sum(wi * li for wi, li in zip(w, losses)))}
+    logs = {'loss': float(sum(wi * li for wi, li in zip(w, losses))) + penalty}
     if len(losses) > 1:
         for k, li in enumerate(losses):
             logs['output_%d_loss' % k] = float(li)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DLWP_B200_ABI_VERSION 1
+#define DLWP_B200_ABI_VERSION 2
 
 typedef void* dlwp_stream_t; /* cudaStream_t */
 
@@ -53,7 +53,7 @@ enum {
     DLWP_IMPL_DIRECT = 1,     /* one thread per output element, any geometry (reference CUDA kernel)              */
     DLWP_IMPL_FFMA = 2,       /* register-tiled fp32 FFMA kernel, input tiles staged with cp.async                */
     DLWP_IMPL_FFMA_TMA = 3,   /* same math, input tiles staged by TMA (cp.async.bulk.tensor) + in-smem wrap fix-up */
-    DLWP_IMPL_TC = 4          /* tcgen05 tensor cores: fp16 hi/lo split x3 (fp32-level accuracy), TMEM accumulators     */
+    DLWP_IMPL_TC = 4          /* tcgen05 tensor cores: scaled fp16 hi/lo split x3 (fp32-level accuracy), TMEM accumulators */
 };
 
 /* Geometry of one fused [periodic/zero pad] -> Conv2D('valid', stride 1, dilation) -> bias -> activation.
@@ -143,8 +143,24 @@ typedef struct DlwpNetDesc {
 
 typedef struct DlwpPlan DlwpPlan;
 
-/* Build the executable form of a Keras graph (replaces graph construction at DLWP/model/models.py:96-112, :349-373). */
+/* How a plan is built; fixed at creation (the library never reads the environment).  All zeros = defaults. */
+typedef struct DlwpPlanOptions {
+    int32_t math;          /* 0: tensor-core chain when the whole plan is eligible, else fp32 kernels; 1: fp32 FFMA kernels
+                              (training needs them: fp32 intermediates)                                                  */
+    int32_t fuse;          /* 0: fuse eligible conv -> conv pairs into one kernel (the intermediate never leaves the SM);
+                              1: one kernel per layer                                                                    */
+    int32_t tc_generic;    /* 1: only the generic tensor-core kernel instances (A/B against the folded ones)             */
+    int32_t tc_bands;      /* latitude bands per strip of the sliding-window kernel; 0 = chosen per launch               */
+    int32_t tc_no_tma;     /* 1: per-plane bulk copies instead of tensor-map row loads                                   */
+    int32_t tc_taps_in_k;  /* -1: planner's choice; 0 / 1: horizontal taps in the MMA N / K dimension                     */
+    int32_t tc_debug;      /* bottleneck triage (WRONG RESULTS): 1 = epilogue only waits/arrives, 2 = issuer only commits */
+    int32_t reserved[9];
+} DlwpPlanOptions;
+
+/* Build the executable form of a Keras graph (replaces graph construction at DLWP/model/models.py:96-112, :349-373).
+ * dlwp_plan_create = dlwp_plan_create_opts with options NULL (defaults). */
 int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** plan);
+int dlwp_plan_create_opts(const DlwpNetDesc* net, const DlwpPlanOptions* options, DlwpPlan** plan);
 void dlwp_plan_destroy(DlwpPlan* plan);
 
 /* keras `layer.set_weights([kernel, bias])` / `get_weights()` (DLWP/custom.py:126,136; DLWP/util.py:180).
@@ -203,7 +219,7 @@ int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0,
 /* Forward through the plan, loss = sum_k loss_weights[k] * mean((yhat_k - y_k)^2) (Keras 'mse'), and -- if `backward` --
  * backprop into one flat gradient buffer (kernel then bias per weight id, Keras layouts; shared layers accumulate).
  * x, targets[k]: device, dense. losses[k] / maes[k] (host, may be NULL for maes) receive the unweighted per-output MSE / MAE.
- * Needs a plan built on the fp32 kernels (DLWP_MATH=ffma). Blocking (returns the loss). */
+ * Needs a plan built on the fp32 kernels (DlwpPlanOptions.math = 1). Blocking (returns the loss). */
 int dlwp_train_step(DlwpPlan* plan, int32_t N, const float* x, const float* const* targets, const float* loss_weights,
                     int32_t backward, int32_t input_grad, float* losses, float* maes, dlwp_stream_t stream);
 /* Optional (H, W) weight map of DLWP.custom.latitude_weighted_loss (custom.py:956-991): both tensors are multiplied by it
@@ -213,6 +229,14 @@ int dlwp_train_loss_weights(DlwpPlan* plan, const float* wmap_host, int64_t elem
  * gradient w.r.t. the input (valid when input_grad was set). */
 int dlwp_train_buffers(DlwpPlan* plan, float** flat_grad, int64_t* elems, float** input_grad);
 int dlwp_train_weight_offsets(DlwpPlan* plan, int32_t weight_id, int64_t* kernel_off, int64_t* bias_off);
+/* keras.regularizers.L1L2 (kernel_regularizer= / bias_regularizer=, examples/train.py:155): adds l1 * sign(w) + 2 * l2 * w
+ * to the weight's slots of the flat gradient buffer (after dlwp_train_step and the all-reduce, before dlwp_train_adam) and
+ * returns the penalty sum(l1 |w| + l2 w^2) that Keras adds to the reported loss. Blocking. */
+int dlwp_train_regularize(DlwpPlan* plan, int32_t weight_id, float kernel_l1, float kernel_l2, float bias_l1,
+                          float bias_l2, float* penalty, dlwp_stream_t stream);
+/* Read (set = 0) or write (set = 1) the Adam moments and step count: HOST arrays of `elems` = flat gradient elements.
+ * Lets the optimizer state survive a plan rebuild (larger batch). */
+int dlwp_train_adam_state(DlwpPlan* plan, float* m_host, float* v_host, int64_t elems, int64_t* step, int32_t set);
 /* Keras Adam update of every weight from the flat gradient buffer (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps outside sqrt). */
 int dlwp_train_adam(DlwpPlan* plan, float lr, float beta1, float beta2, float eps, dlwp_stream_t stream);
 
@@ -220,7 +244,7 @@ int dlwp_train_adam(DlwpPlan* plan, float lr, float beta1, float beta2, float ep
  * whatever the plan's buffers hold from the last forward / rollout. Blocking. Used by bench.py for the roofline figure. */
 int dlwp_plan_profile_op(DlwpPlan* plan, int32_t N, int32_t op_index, int32_t iters, float* ms_per_launch,
                          dlwp_stream_t stream);
-/* 1 if the plan runs as a tcgen05 tensor-core chain (DLWP_MATH=tc or every conv op flagged DLWP_IMPL_TC). */
+/* 1 if the plan runs as a tcgen05 tensor-core chain (DlwpPlanOptions.math = 0 and every op eligible). */
 int dlwp_plan_uses_tensor_cores(DlwpPlan* plan);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
@@ -229,7 +253,10 @@ const char* dlwp_last_error_string(void);
 int dlwp_abi_version(void);
 /* Number of kernels this library launched since load (all streams); bench.py reports the delta as gpu_launches. */
 int64_t dlwp_kernel_launch_count(void);
-/* Read-and-clear device-side diagnostic flags; bit 0 = a TMA completion wait timed out. Synchronises the device. */
+/* Read-and-clear device-side diagnostic flags. Synchronises the device.
+ *   1: an fp32-kernel TMA wait timed out   2: a tensor-core kernel's mbarrier wait timed out
+ *   4: a value left the fp16 hi/lo split's range (NaN / inf data)   8: an image's amax fell below 2^-6 in scaled units
+ *   (precision underflow of a statically scaled tanh image).  dlwp_b200.engine reruns on the fp32 kernels on 4 / 8. */
 int dlwp_debug_flags(void);
 /* Name of the implementation AUTO would choose for this descriptor ("direct", "ffma", "ffma_tma"). */
 const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
@@ -238,7 +265,8 @@ const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
  *   taps_in_k, NCOLS, NACC, KS, NS, S, nfull, rem, pair, shared-memory bytes, weight-image bytes, CBLK, CSTRIDE, planes,
  *   row pitch.  Returns 0, or DLWP_ESHAPE when the layer cannot run on the tensor-core kernels.
  * dlwp_debug_tc_pack: the packed fp16 hi/lo weight image of that schedule (kernel in Keras layout (kh,kw,Cin,Cout), HOST
- *   pointer) and the low words of its A-operand descriptors per K step; returns the number of fp16 elements written. */
+ *   pointer; the image holds w * 2^weight_exponent) and the low words of its A-operand descriptors per K step; returns
+ *   the number of fp16 elements written.  l1max = max over filters of sum|w| (the output bound's coefficient). */
 int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out);
 /* dlwp_debug_sw_cover: walks the sliding-window kernel's scheduling units for this layer on `sms` SMs exactly as the
  *   device roles do and counts, per output pixel (N,H,W), how many units write it (must be 1 inside [row_begin,row_end),
@@ -246,7 +274,13 @@ int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out);
 int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_t* cover, int64_t cover_elems, int32_t* info,
                         int32_t n_info);
 int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16_t* image, int64_t image_cap,
-                           uint32_t* kstep_words, int32_t kstep_cap);
+                           uint32_t* kstep_words, int32_t kstep_cap, int32_t* weight_exponent, float* l1max);
+/* Description of the fully folded tensor-core kernel instance this layer launches when it writes a P image (out_mode 1),
+ * fp32 (2) or both (3); NULL = generic instance (profiles/r02_folded_vs_generic.txt compares the two). */
+const char* dlwp_debug_tc_folded(const DlwpConvDesc* desc, int32_t out_mode);
+/* The power-of-two exponent e the tensor-core path gives an image whose values are bounded by `bound`:
+ * bound * 2^e in [2^13, 2^14) (conv_tc.h). */
+int dlwp_debug_exp_for_bound(float bound);
 
 #ifdef __cplusplus
 }

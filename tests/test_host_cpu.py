@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(nat):
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dlwp_abi_version() == 1
+    assert lib.dlwp_abi_version() == nat.ABI_VERSION == 2
     assert lib.dlwp_kernel_launch_count() == 0
 
 
@@ -42,6 +42,8 @@ def test_struct_layouts_match_header(nat):
     assert ctypes.sizeof(nat.BufferDesc) == 6 * 4
     assert ctypes.sizeof(nat.OpDesc) == 24 * 4
     assert ctypes.sizeof(nat.NetDesc) == 4 * 4 + 2 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(nat.PlanOptions) == 16 * 4
+    assert nat.PlanOptions().tc_taps_in_k == -1 and nat.PlanOptions(math=1).math == 1
 
 
 def test_library_has_tma_and_no_torch_dependency(nat):
@@ -201,3 +203,39 @@ def test_latitude_weights_follow_reference_formula():
     ref = np.cos(lats * np.pi / 180) + 0.5 * np.sin(lats * 2 * np.pi / 180) ** 2     # custom.py:976-978
     assert f.weights.shape == (7, 10)
     np.testing.assert_allclose(f.weights[:, 3], ref, rtol=1e-6, atol=1e-7)
+
+
+def test_model_pickles_after_training_state_was_attached_and_with_latitude_loss(tmp_path):
+    """Model.__getstate__ must drop every runtime handle (the training engine holds ctypes plan pointers)
+    and latitude_weighted_loss / anomaly_correlation_loss must be picklable, or util.save_model fails after fit()."""
+    import pickle
+    from dlwp_b200 import util
+    from dlwp_b200.custom import anomaly_correlation_loss, latitude_weighted_loss
+    from dlwp_b200.keras.losses import mean_squared_error
+    from dlwp_b200.model import DLWPNeuralNet
+    layers = OL.net_a_layers((6, 10, 16))
+    lats = np.linspace(-80, 80, 10)
+    loss = latitude_weighted_loss(mean_squared_error, lats, (6, 10, 16), axis=-2, weighting='midlatitude')
+    dlwp = DLWPNeuralNet(is_convolutional=True, time_dim=1, scaler_type=None, scale_targets=False)
+    dlwp.build_model(layers, loss=loss, optimizer='adam')
+
+    class FakeEngine(object):                   # what training._engine attaches: ctypes pointers cannot be pickled
+        def __init__(self):
+            self.plan = ctypes.pointer(ctypes.c_int(3))
+
+        def close(self):
+            pass
+    dlwp.model._train_engine = FakeEngine()
+    dlwp.model.history = FakeEngine()
+    w0 = dlwp.model.get_weights()
+    util.save_model(dlwp, str(tmp_path / 'm'))
+    back = util.load_model(str(tmp_path / 'm'))
+    for a, b in zip(w0, back.model.get_weights()):
+        np.testing.assert_array_equal(a, b)
+    l2 = back.model.loss
+    y, yh = np.ones((2, 6, 10, 16), np.float32), np.zeros((2, 6, 10, 16), np.float32)
+    assert abs(float(np.mean(l2(y, yh))) - float(np.mean(loss(y, yh)))) < 1e-7 and l2.__name__ == 'lat_loss'
+    acc = pickle.loads(pickle.dumps(anomaly_correlation_loss(regularize_mean='mse')))
+    rng = np.random.RandomState(0)
+    a, b = rng.standard_normal((2, 3, 4, 5)), rng.standard_normal((2, 3, 4, 5))
+    assert np.isfinite(acc(a, b)).all() and acc.__name__ == 'acc_loss'

@@ -170,3 +170,49 @@ def test_latitude_weighted_mse_matches_reference_definition():
         layer._tparam, layer._tw = None, None
     for g, r in zip(eng.weight_grads(), want):
         assert _rel(g, r) < TOL
+
+
+def test_l2_regularizer_enters_gradient_and_loss_and_trained_model_saves(tmp_path):
+    """kernel_regularizer=l2(lambda) (examples/train.py:155) was stored and ignored; Keras adds lambda*sum(w^2)
+    to the loss and 2*lambda*w to the gradient.  Also: after fit, util.save_model / load_model round-trips (the training
+    engine's ctypes handles must not be pickled), and a larger batch keeps the Adam state (step count)."""
+    from dlwp_b200 import util
+    from dlwp_b200.keras.regularizers import l2
+    lam = 1e-2
+    cf = 'channels_first'
+    shape = (6, 16, 24)
+    layers = (('PeriodicPadding2D', ((0, 2),), {'data_format': cf, 'input_shape': shape}),
+              ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+              ('Conv2D', (32, 3), {'dilation_rate': 2, 'padding': 'valid', 'activation': 'tanh', 'data_format': cf,
+                                   'kernel_regularizer': l2(lam)}),
+              ('PeriodicPadding2D', ((0, 2),), {'data_format': cf}),
+              ('ZeroPadding2D', ((2, 0),), {'data_format': cf}),
+              ('Conv2D', (6, 5), {'padding': 'valid', 'activation': 'linear', 'data_format': cf}))
+    dlwp = build_product_sequential(layers)
+    net = oracle_sequential_like(dlwp, OL.net_a_layers(shape), seed=7, bias_scale=0.05)
+    rng = np.random.RandomState(4)
+    X = rng.standard_normal((8, 6, 16, 24)).astype(np.float32)
+    Y = rng.standard_normal((8, 6, 16, 24)).astype(np.float32)
+    k1 = net.conv_layers[0].kernel.astype(np.float64)
+    ref_l, grads, _ = _autograd(net, net.conv_layers, X[:4], [Y[:4]], [1.0])
+    # evaluate() reports mse + penalty
+    got_eval = dlwp.model.evaluate(X[:4], Y[:4], batch_size=4)
+    assert abs(got_eval - (ref_l[0] + lam * np.square(k1).sum())) < 1e-5 * (1 + ref_l[0])
+    # one Adam step from zero moments moves every weight by lr * sign(g): check the sign of the regularised gradient where
+    # the data gradient and the L2 term disagree (|2 lam w| > |g_data|)
+    w_before = dlwp.model.get_weights()[0].astype(np.float64)
+    loss = dlwp.model.train_on_batch(X[:4], Y[:4])
+    assert abs(loss - (ref_l[0] + lam * np.square(k1).sum())) < 1e-5 * (1 + ref_l[0])
+    g_total = grads[0] + 2 * lam * k1
+    moved = dlwp.model.get_weights()[0].astype(np.float64) - w_before
+    sel = (np.sign(grads[0]) != np.sign(g_total)) & (np.abs(g_total) > 1e-6)
+    assert sel.sum() > 10
+    assert (np.sign(moved[sel]) == -np.sign(g_total[sel])).all()
+    # a larger batch rebuilds the training plan: the step count (bias correction) must carry over
+    dlwp.model.train_on_batch(X, Y)
+    assert dlwp.model._train_engine.adam_state()[2] == 2
+    util.save_model(dlwp, str(tmp_path / 'trained'))
+    back = util.load_model(str(tmp_path / 'trained'))
+    for a, b in zip(dlwp.model.get_weights(), back.model.get_weights()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(back.predict(X[:2]), dlwp.predict(X[:2]))
