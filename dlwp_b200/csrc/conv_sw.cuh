@@ -65,6 +65,13 @@ __device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint
     else
         umma_f16(tmem_d, adesc, bdesc, idesc, acc);
 }
+__device__ __forceinline__ void umma_f16_dyn(int coll, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t acc) {
+    if (coll == 1) umma_f16_c<1>(tmem_d, adesc, bdesc, idesc, acc);
+    else if (coll == 2) umma_f16_c<2>(tmem_d, adesc, bdesc, idesc, acc);
+    else if (coll == 3) umma_f16_c<3>(tmem_d, adesc, bdesc, idesc, acc);
+    else umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                  : "memory");
@@ -152,6 +159,7 @@ __device__ __forceinline__ void amax_publish(float* slot, float v, int lane) {
 __device__ __forceinline__ float2 tc_scale_prologue(const TcScale& sc, int act, bool first_block) {
     const int e_in = sc.e_in ? *sc.e_in : sc.e_in_const;
     const float amax_in = sc.amax_in ? *sc.amax_in : 1.f;
+    const float amax_chk = sc.amax_chk ? *sc.amax_chk : amax_in;
     int e_out = sc.e_out_const;
     if (sc.e_out) {
         float B = fmaf(sc.l1max, amax_in, sc.bmax);
@@ -163,7 +171,7 @@ __device__ __forceinline__ float2 tc_scale_prologue(const TcScale& sc, int act, 
     if (first_block && sc.amax_zero) *sc.amax_zero = 0.f;
     if (!(amax_in < 1e30f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
     // the source image's largest element sits below 2^-6: its small elements have lost relative precision
-    if (amax_in > 0.f && amax_in * exp2i(e_in) < 0.015625f) atomicOr(&g_tc_flags, TC_FLAG_UNDERFLOW);
+    if (amax_chk > 0.f && amax_chk * exp2i(e_in) < 0.015625f) atomicOr(&g_tc_flags, TC_FLAG_UNDERFLOW);
     return make_float2(exp2i(-(e_in + sc.e_w)), exp2i(e_out));
 }
 
@@ -181,7 +189,14 @@ __device__ __forceinline__ float2 tc_scale_prologue(const TcScale& sc, int act, 
 //     accumulators of output rows rp - i*dil, i = 0..KH-1, with the same A view and different weight blocks -> per K step
 //     the hi view is read once for 2*KH MMAs (hi*hi, hi*lo) and the lo view once for KH MMAs;
 //   * TMEM holds a ring of NACC accumulators (one output row x 128 lanes x NCOLS columns each); a row is committed to
-//     the epilogue when its last tap has been issued.  Four epilogue warp sets take rows round robin.
+//     the epilogue when its last tap has been issued.  Four epilogue warp sets take rows round robin;
+//   * the accumulators of the output rows one input row feeds (rp, rp - dil, ..., rp - (KH-1)*dil) sit in ADJACENT TMEM
+//     columns (the ring is ordered by row within each residue class mod dil), and the weight blocks of the vertical taps
+//     are stored side by side in the same order, so ONE MMA with N = taps * NCOLS updates all of them ("vertical taps
+//     folded into N", up to N = 256): 6 MMAs of N = 160 per input row instead of 30 of N = 32 for a 5x5 layer.  A 32-column
+//     MMA is bound by its 4 KB A-operand read (40 clk, ~19 with the collector); at N >= 128 the same A read is amortised
+//     and the MMA runs at the tensor pipe's N/2 clk.  Runs are cut at the ring's end, at the band's first / last rows
+//     (fewer valid taps) and where a new output row takes its first contribution (accumulate flag off).
 // Horizontal taps live in N (few filters: the epilogue's shifted sum) or in K (A views shifted by j*dil pixels inside the
 // staged row; N = filters).
 // ===================================================================================================================
@@ -196,9 +211,10 @@ struct SwParams {
     int row0, row1;
     int Cout, NCOLS, CBLK, CSTRIDE, XL;
     int KS, NS, NACC;
+    int fold;                         // vertical taps one MMA covers (1 .. KH; fold * NCOLS <= 256)
     int planes_in;
     uint32_t rowpitch, stage_stride, b_unit16, b_bytes;  // b_unit16: one (k step, tap, hi|lo) weight block in 16-byte units
-    uint32_t idesc;
+    uint32_t idesc;                   // instruction descriptor with the N field clear (set per MMA run)
     int act;
     const float* bias;
     const __half* bimg;
@@ -239,6 +255,92 @@ __host__ __device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwU
     return U.n0 < p.N && U.ya < U.yb;
 }
 
+constexpr uint32_t SW_IDESC = (1u << 4) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128; N per MMA
+
+// Position of a row in the accumulator ring.  Rows are numbered CTA-wide (phantom rows included); row G sits in residue
+// class m = G % D at ring position q = (G / D) % RING, i.e. slot m * RING + q, and lap = (G / (D * RING)) & 1 is the phase
+// of that slot's barriers.  Kept incrementally: no divisions on the issuing warp.
+struct SwRing {
+    int m = 0, q = 0;
+    uint32_t lap = 0;
+    __device__ __forceinline__ int slot(int RING) const { return m * RING + q; }
+    __device__ __forceinline__ void advance(int D, int RING) {
+        if (++m == D) {
+            m = 0;
+            if (++q == RING) { q = 0; lap ^= 1; }
+        }
+    }
+    __device__ __forceinline__ void retreat(int D, int RING) {
+        if (--m < 0) {
+            m = D - 1;
+            if (--q < 0) { q = RING - 1; lap ^= 1; }
+        }
+    }
+};
+
+// One input row's MMAs with everything but the stage address folded at compile time (POS = ring position of the window's
+// lowest row).  Runs of vertical taps: cut every FOLD taps, at the ring's end, and before tap 0 in the very first MMA (the
+// new row's accumulator is overwritten, the others accumulate).
+template <int KH, int NCOLS, int KS, int RING, int FOLD, int POS>
+__device__ __forceinline__ void sw_issue_row_pos(bool leader, uint32_t tres, uint32_t sbase16, uint32_t pitch16,
+                                                 uint32_t desc_hi, uint32_t bbase, const TcKStep* kst) {
+    constexpr uint32_t bblock16 = 2u * KH * NCOLS;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t a_lo32 = kst[ks].a_off + sbase16;
+        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
+        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint64_t ad = pass < 2 ? ad_hi : ad_lo;
+            const uint32_t bb = bbase + (uint32_t)(2 * ks + (pass == 1 ? 1 : 0)) * bblock16;
+            const bool fresh = ks == 0 && pass == 0;
+            int run_tb = KH - 1;
+#pragma unroll
+            for (int t = KH - 1; t >= 0; --t) {
+                const int len = run_tb - t + 1;
+                const bool wrap_next = (POS + (KH - 1 - t) + 1) % RING == 0;
+                const bool end = t == 0 || len == FOLD || wrap_next || (fresh && t == 1);
+                if (end) {
+                    const uint32_t dcol = tres + (uint32_t)(((POS + (KH - 1 - run_tb)) % RING) * NCOLS);
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (bb + (uint32_t)((KH - 1 - run_tb) * NCOLS));
+                    const uint32_t idesc = SW_IDESC | ((uint32_t)((len * NCOLS) >> 3) << 17);
+                    const bool first = pass != 1 && run_tb == KH - 1, last = pass != 0 && t == 0;
+                    const uint32_t acc = (fresh && run_tb == 0) ? 0u : 1u;
+                    if (leader) {
+                        if (first && !last) umma_f16_c<1>(dcol, ad, bd, idesc, acc);
+                        else if (!first && last) umma_f16_c<3>(dcol, ad, bd, idesc, acc);
+                        else if (!first) umma_f16_c<2>(dcol, ad, bd, idesc, acc);
+                        else umma_f16_c<0>(dcol, ad, bd, idesc, acc);
+                    }
+                    run_tb = t - 1;
+                }
+            }
+        }
+    }
+}
+
+template <int KH, class ST>
+__device__ __forceinline__ void sw_issue_row_static(int pos_lo, bool leader, uint32_t tres, uint32_t sbase16,
+                                                    uint32_t pitch16, uint32_t desc_hi, uint32_t bbase, const TcKStep* kst) {
+    constexpr int NCOLS = ST::NCOLS ? ST::NCOLS : 16, D = ST::D ? ST::D : 1, KS = ST::KS ? ST::KS : 1;
+    constexpr int NACC = (512 / NCOLS > SW_MAX_ACC ? SW_MAX_ACC : 512 / NCOLS) / D * D;
+    constexpr int RING = NACC / D;
+    constexpr int FOLD = ST::FOLD ? ST::FOLD : 1;
+#define SW_POS_CASE(P_)                                                                                          \
+    case P_:                                                                                                     \
+        if constexpr (P_ < RING)                                                                                 \
+            sw_issue_row_pos<KH, NCOLS, KS, RING, FOLD, P_>(leader, tres, sbase16, pitch16, desc_hi, bbase, kst); \
+        break;
+    switch (pos_lo) {
+        SW_POS_CASE(0) SW_POS_CASE(1) SW_POS_CASE(2) SW_POS_CASE(3) SW_POS_CASE(4) SW_POS_CASE(5) SW_POS_CASE(6) SW_POS_CASE(7)
+        SW_POS_CASE(8) SW_POS_CASE(9) SW_POS_CASE(10) SW_POS_CASE(11) SW_POS_CASE(12) SW_POS_CASE(13) SW_POS_CASE(14)
+        SW_POS_CASE(15)
+        default: break;
+    }
+#undef SW_POS_CASE
+}
+
 // KH: kernel height (vertical taps), KW: horizontal taps summed by the epilogue (1 = folded into K), NC: filters per
 // 8-filter block that exist (6: the single packed block of a 6-filter layer, else 8)
 //
@@ -246,12 +348,21 @@ __host__ __device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwU
 // instance serves any layer; the example nets' layers get instances with everything folded (conv_sw_net_*.cu), which
 // matters because the single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's
 // critical path.
-template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0>
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int FOLD_ = 0>
 struct SwStatic {
     static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
     static constexpr int FULL = FULL_;  // 1: Cout == CBLK * NC, no partial filter block
+    static constexpr int FOLD = FOLD_;  // vertical taps per MMA (0: SwParams::fold)
 };
 using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
+
+// accumulator ring: rows of one residue class mod D are neighbours; NACC is a multiple of D
+__host__ __device__ __forceinline__ int sw_nacc(int ncols, int d) {
+    int n = 512 / ncols;
+    if (n > SW_MAX_ACC) n = SW_MAX_ACC;
+    return n - n % d;
+}
+__device__ __forceinline__ int sw_slot(int G, int D, int R) { return (G % D) * R + (G / D) % R; }
 
 template <int KH, int KW, int NC, class ST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -261,12 +372,12 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
     const int KS = ST::KS ? ST::KS : p.KS;
     const int D = ST::D ? ST::D : p.D;
     const int CBLK = ST::CBLK ? ST::CBLK : p.CBLK;
-    const int NACC = ST::NCOLS ? (512 / (ST::NCOLS ? ST::NCOLS : 1) > SW_MAX_ACC ? SW_MAX_ACC : 512 / (ST::NCOLS ? ST::NCOLS : 1)) : p.NACC;
+    const int NACC = (ST::NCOLS && ST::D) ? sw_nacc(ST::NCOLS ? ST::NCOLS : 16, ST::D ? ST::D : 1) : p.NACC;
+    const int RING = NACC / D;  // ring positions per residue class
     const int act = ST::ACT >= 0 ? ST::ACT : p.act;
     const bool has_yp = ST::OUT ? (ST::OUT & 1) != 0 : p.yp != nullptr;
     const bool has_y32 = ST::OUT ? (ST::OUT & 2) != 0 : p.y32 != nullptr;
     constexpr int CSTRIDE = NC;  // 6: the single packed block of a 6-filter layer, else 8
-    const uint32_t unit16 = (uint32_t)(2 * NCOLS);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
     unsigned char* bsm = stages + (size_t)p.NS * p.stage_stride;
@@ -385,92 +496,67 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         }
     } else if (warp == W_MMA) {
         // =============================== MMA issuer (warp-convergent, one elected lane issues) ===========================
+        // Every staged input row is issued the same way -- all KH taps, one new accumulator row started -- by giving each
+        // unit SPAN "phantom" output rows above and below its band: they own ring slots like real rows, collect the taps
+        // that would fall outside the band, and are released by the epilogue unread.  No boundary cases, so the row's MMA
+        // runs depend only on the ring position of the window (a compile-time switch in the folded instances).
         const bool leader = elect_one();
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, sm_100 descriptor version
-        const uint32_t b_lbo_field = ((NCOLS * 16u) >> 4) << 16;
-        const uint32_t b16 = smem_u32(bsm) >> 4;
+        const uint32_t bunit16 = (uint32_t)(KH * NCOLS);                   // one 8-channel unit of a weight block: [tap][col] x 16 B
+        const uint32_t bbase = (bunit16 << 16) | (smem_u32(bsm) >> 4);     // LBO field | block 0 address
+        const uint32_t bblock16 = 2u * bunit16;                            // one (k step, hi|lo) block = two units
         const uint32_t pitch16 = p.rowpitch >> 4;
         const uint32_t stages16 = smem_u32(stages) >> 4, stride16 = p.stage_stride >> 4;
         int s = 0;
         uint32_t ph = 0;
-        int sl0 = 0;        // accumulator slot of the output row that starts at the current input row
-        uint32_t aph = 0;   // parity of the accumulator ring's current lap
+        SwRing ring;        // position of the next row to start (CTA-wide numbering, phantoms included)
         SwUnit U;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
             if (!sw_decode(p, u, U)) continue;
-            const int nout = U.yb - U.ya;
-            const int nrows = nout + SPAN;
-            int sl = sl0;           // slot of (virtual) output row r; rows r >= nout are never started
-            uint32_t ap = aph;
-            uint32_t dh[(KH - 1) * (ST::D ? ST::D : 1) + 1];  // dh[k]: accumulator columns of output row r - k
-#pragma unroll
-            for (int k = 0; k <= (KH - 1) * (ST::D ? ST::D : 1); ++k) dh[k] = tmem;
-            uint32_t dcur = tmem + (uint32_t)(sl0 * NCOLS);
+            const int nrows = U.yb - U.ya + SPAN;
+            for (int k = 0; k < SPAN; ++k) {        // phantom rows above the band: take their slots
+                mbar_wait(&acc_empty[ring.slot(RING)], ring.lap ^ 1);
+                ring.advance(D, RING);
+            }
             for (int r = 0; r < nrows; ++r) {
-                if (r < nout) mbar_wait(&acc_empty[sl], ap ^ 1);  // output row r starts accumulating: slot must be drained
+                mbar_wait(&acc_empty[ring.slot(RING)], ring.lap ^ 1);  // the row that starts here: its slot must be drained
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sbase16 = stages16 + (uint32_t)s * stride16;
-                uint32_t dcol[KH];
-                if constexpr (ST::D != 0) {  // rolling register file of the live rows' accumulator columns: no index math
+                int pos_lo = ring.q - (KH - 1);     // ring position of the window's lowest row (same residue class)
+                if (pos_lo < 0) pos_lo += RING;
+                const uint32_t tres = tmem + (uint32_t)(ring.m * RING * NCOLS);
+                if (!(p.debug & 2)) {
+                    if constexpr (ST::NCOLS != 0 && ST::D != 0 && ST::KS != 0) {
+                        sw_issue_row_static<KH, ST>(pos_lo, leader, tres, sbase16, pitch16, desc_hi, bbase, p.kst);
+                    } else {
+                        const int FOLD = p.fold;
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
+                            const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
+                            const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
+                            const uint32_t bk = bbase + (uint32_t)(2 * ks) * bblock16;
+                            // pass 0: hi * hi, pass 1: hi * lo (same A view: collector), pass 2: lo * hi
 #pragma unroll
-                    for (int k = (KH - 1) * (ST::D ? ST::D : 1); k > 0; --k) dh[k] = dh[k - 1];
-                    dh[0] = dcur;
-#pragma unroll
-                    for (int i = 0; i < KH; ++i) dcol[i] = dh[i * (ST::D ? ST::D : 1)];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < KH; ++i) {
-                        int si = sl - i * D;
-                        if (si < 0) si += NACC;
-                        dcol[i] = tmem + (uint32_t)(si * NCOLS);
-                    }
-                }
-                const bool interior = (r >= SPAN) && (r < nout);
-                if (p.debug & 2) {
-                } else if (interior) {
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
-                        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
-                        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
-                        const uint32_t bks = b_lbo_field | (b16 + (uint32_t)(ks * KH) * 2u * unit16);
-#pragma unroll
-                        for (int i = 0; i < KH; ++i) {
-                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
-                            const uint64_t bl = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i + 1) * unit16);
-                            if (leader) {
-                                if (i == 0) umma_f16_c<1>(dcol[i], ad_hi, bh, p.idesc, ks != 0);
-                                else umma_f16_c<2>(dcol[i], ad_hi, bh, p.idesc, 1u);
-                                if (i == KH - 1) umma_f16_c<3>(dcol[i], ad_hi, bl, p.idesc, 1u);
-                                else umma_f16_c<2>(dcol[i], ad_hi, bl, p.idesc, 1u);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < KH; ++i) {
-                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
-                            if (leader) {
-                                if (i == 0) umma_f16_c<1>(dcol[i], ad_lo, bh, p.idesc, 1u);
-                                else if (i == KH - 1) umma_f16_c<3>(dcol[i], ad_lo, bh, p.idesc, 1u);
-                                else umma_f16_c<2>(dcol[i], ad_lo, bh, p.idesc, 1u);
-                            }
-                        }
-                    }
-                } else {
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;
-                        const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
-                        const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
-                        const uint32_t bks = b_lbo_field | (b16 + (uint32_t)(ks * KH) * 2u * unit16);
-#pragma unroll
-                        for (int i = 0; i < KH; ++i) {
-                            const int yo = r - i * D;  // output row (relative to the unit) this tap contributes to
-                            if (yo < 0 || yo >= nout) continue;
-                            const uint64_t bh = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i) * unit16);
-                            const uint64_t bl = ((uint64_t)desc_hi << 32) | (bks + (uint32_t)(2 * i + 1) * unit16);
-                            if (leader) {
-                                umma_f16(dcol[i], ad_hi, bh, p.idesc, (i | ks) != 0);
-                                umma_f16(dcol[i], ad_hi, bl, p.idesc, 1u);
-                                umma_f16(dcol[i], ad_lo, bh, p.idesc, 1u);
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint64_t ad = pass < 2 ? ad_hi : ad_lo;
+                                const uint32_t bb = bk + (pass == 1 ? bblock16 : 0u);
+                                const bool fresh = ks == 0 && pass == 0;  // tap 0 overwrites the new row's accumulator
+                                int tb = KH - 1, pos = pos_lo;
+                                while (tb >= 0) {
+                                    int len = tb + 1 < FOLD ? tb + 1 : FOLD;
+                                    if (len > RING - pos) len = RING - pos;          // stop at the ring's end
+                                    if (fresh && len > tb && tb > 0) len = tb;        // ... and before tap 0 of a new row
+                                    const uint32_t ncols = (uint32_t)(len * NCOLS);
+                                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (bb + (uint32_t)((KH - 1 - tb) * NCOLS));
+                                    const bool first = pass != 1 && tb == KH - 1, last = pass != 0 && len > tb;
+                                    if (leader)
+                                        umma_f16_dyn(first ? (last ? 0 : 1) : (last ? 3 : 2), tres + (uint32_t)(pos * NCOLS), ad, bd,
+                                                     SW_IDESC | ((ncols >> 3) << 17), (fresh && tb == 0) ? 0u : 1u);
+                                    tb -= len;
+                                    pos += len;
+                                    if (pos == RING) pos = 0;
+                                }
                             }
                         }
                     }
@@ -478,19 +564,20 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 __syncwarp();
                 if (leader) {
                     umma_commit(&empty[s]);
-                    if (r >= SPAN) {  // the last tap of output row r - SPAN has been issued
-                        int sd = sl - SPAN;
-                        if (sd < 0) sd += NACC;
-                        umma_commit(&acc_full[sd]);
-                    }
+                    umma_commit(&acc_full[ring.m * RING + pos_lo]);  // the window's lowest row has taken its last tap
                 }
                 if (++s == p.NS) { s = 0; ph ^= 1; }
-                dcur += (uint32_t)NCOLS;
-                if (++sl == NACC) { sl = 0; ap ^= 1; dcur = tmem; }
+                ring.advance(D, RING);
             }
-            // the next unit's first output row follows this unit's last one in the accumulator ring
-            sl0 += nout;
-            while (sl0 >= NACC) { sl0 -= NACC; aph ^= 1; }
+            // phantom rows below the band (started by the last SPAN input rows, never completed): release them
+            if (leader) {
+                SwRing t = ring;
+                for (int k = 0; k < SPAN; ++k) {
+                    t.retreat(D, RING);
+                    umma_commit(&acc_full[t.slot(RING)]);
+                }
+            }
+            __syncwarp();
         }
     } else {
         // =============================== epilogue: 4 sets x 4 quadrant warps, rows dealt round robin ===================
@@ -503,9 +590,6 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         const size_t plane_stride = (size_t)Hout * p.Wp_out;  // uint4 units
         const float inv = sscale[0], sout = sscale[1];
         float amax_t = 0.f;   // max |output| this thread produced (true units)
-        int slot = set;
-        uint32_t aph = 0;
-        while (slot >= NACC) { slot -= NACC; aph ^= 1; }
         int g = 0, lrow = 0;
         SwUnit U;
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -521,16 +605,21 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
             uint4* ypn = has_yp
                              ? reinterpret_cast<uint4*>(p.yp) + (((size_t)max(n, 0) * p.planes_out + p.out_plane0) * Hout + TC_HPAD) * p.Wp_out + x + p.wpad_out
                              : nullptr;
-            for (int y = U.ya + ((set - g) & 3); y < U.yb; y += TC_SETS, ++lrow) {
-                mbar_wait_relaxed(&acc_full[slot], aph);
+            // rows of the unit in the CTA-wide numbering: SPAN phantom rows, the band's rows, SPAN phantom rows; set s takes
+            // the rows with G % 4 == s
+            const int nnum = U.yb - U.ya + 2 * SPAN;
+            for (int k = (set - g) & 3; k < nnum; k += TC_SETS) {
+                const int G = g + k;
+                const int slot = sw_slot(G, D, RING);
+                mbar_wait_relaxed(&acc_full[slot], (uint32_t)((G / NACC) & 1));
                 tc_fence_after();
-                if (p.debug & 1) {
+                const int y = U.ya + k - SPAN;
+                if (y < U.ya || y >= U.yb || (p.debug & 1)) {   // phantom row: release the slot unread
                     tc_fence_before();
                     mbar_arrive(&acc_empty[slot]);
-                    slot += TC_SETS;
-                    if (slot >= NACC) { slot -= NACC; aph ^= 1; }
                     continue;
                 }
+                ++lrow;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOLS);
                 float* mb = xset + (size_t)(lrow & 1) * CBLK * 4 * XQ;
                 if (KW > 1) {
@@ -639,10 +728,8 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[slot]);
-                slot += TC_SETS;
-                if (slot >= NACC) { slot -= NACC; aph ^= 1; }
             }
-            g += U.yb - U.ya;
+            g += nnum;
         }
         amax_publish(p.sc.amax_out, amax_t, lane);
     }
@@ -668,12 +755,13 @@ static void sw_launch_one(const SwParams& p, const CUtensorMap& map_full, const 
 
 // A folded instance: the layer constants it was compiled for and its launcher.
 struct SwFolded {
-    int KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL;
+    int KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL;   // the kernel folds min(KH, 256 / NCOLS) vertical taps per MMA
     SwLaunchFn fn;
     const char* what;
 };
 #define SW_FOLDED_ENTRY(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
-    {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL>>, WHAT}
+    {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                          \
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT}
 
 static inline int sw_tu_flags_read_clear() {
     int v = 0, zero = 0;

@@ -20,15 +20,15 @@ namespace dlwp {
 // ===================================================================================================================
 // max|x| of a strided (N,C,H,W) tensor -> atomicMax into *amax; NaN / inf raise the range flag
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, float* amax, int N, int C, int H, int W,
-                                                   long long xs_n, long long xs_c, long long xs_h) {
-    const long long total = (long long)N * C * H * W;
+                                                   long long xs_n, long long xs_c, long long xs_h, int row0) {
+    const long long total = (long long)N * C * H * W;  // H = rows scanned, starting at row0
     float m = 0.f;
     bool bad = false;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int xq = (int)(idx % W);
         long long t = idx / W;
-        const int y = (int)(t % H);
+        const int y = row0 + (int)(t % H);
         t /= H;
         const int c = (int)(t % C);
         const int n = (int)(t / C);
@@ -98,9 +98,11 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
     if (row0 == 0 && row1 == 0) row1 = H;
     DLWP_REQUIRE(ps.e && ps.amax, DLWP_EINVAL, "pack_state needs the image's scale words");
     if (ps.fresh) {
-        const long long all = (long long)N * C * H * W;
-        const int ablocks = (int)std::min<long long>((all + 1023) / 1024, 148LL * 8);
-        amax_kernel<<<ablocks, 256, 0, stream>>>(x, ps.amax, N, C, H, W, xs_n, xs_c, xs_h);
+        const int a0 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? 0 : ps.amax_row0;
+        const int a1 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? H : ps.amax_row1;
+        const long long all = (long long)N * C * (a1 - a0) * W;
+        const int ablocks = (int)std::max<long long>(1, std::min<long long>((all + 1023) / 1024, 148LL * 8));
+        amax_kernel<<<ablocks, 256, 0, stream>>>(x, ps.amax, N, C, a1 - a0, W, xs_n, xs_c, xs_h, a0);
         int rc = after_launch("amax_kernel");
         if (rc) return rc;
     }
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
         if (sc.e_out) *sc.e_out = sc.e_in ? *sc.e_in : sc.e_in_const;
         if (sc.amax_zero) *sc.amax_zero = 0.f;
         if (sc.amax_out) {
-            const float a = sc.amax_in ? *sc.amax_in : 1.f;
+            const float a = sc.amax_chk ? *sc.amax_chk : (sc.amax_in ? *sc.amax_in : 1.f);
             atomicMax(reinterpret_cast<unsigned*>(sc.amax_out), __float_as_uint(a));
         }
     }
@@ -223,8 +225,9 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L, const TcOptions& opt) {
     L->CSTRIDE = (!L->taps_in_k && d.Cout == 6) ? 6 : 8;  // 5 taps x 6 filters pack into 32 columns
     L->NCOLS = cdiv(L->CBLK * L->kw_eff * L->CSTRIDE + (8 - L->CSTRIDE), 16) * 16;
     if (L->NCOLS > 256) return -1;
-    L->NACC = std::min(SW_MAX_ACC, 512 / L->NCOLS);
+    L->NACC = sw_nacc(L->NCOLS, d.dil_h);  // a multiple of the dilation: rows of one residue class are ring neighbours
     if (L->NACC < span + 2) return -1;  // rows in flight (span + 1) plus one being drained by the epilogue
+    L->fold = std::min(d.kh, 256 / L->NCOLS);  // vertical taps one MMA covers
     // Either way a strip yields 128 - halo_w outputs: with the taps in N the last halo_w lanes only feed the shifted sum,
     // with the taps in K the shifted A views of the last valid lane end at pixel 127 -- so the staged row is exactly 128
     // pixels per plane and one tensor-map box (<= 256 eight-byte elements) can bring it.
@@ -260,9 +263,11 @@ bool tc_geometry_ok(const DlwpConvDesc& d, const TcOptions& opt) {
     return tc_plan_layer(d, &L, opt) == 0;
 }
 
-// Weight image: for every K step ks and vertical tap i a hi block then a lo block, each [2 units][NCOLS][8] fp16
-// (K-major, LBO = NCOLS*16 B between the two 8-channel units).  A unit is (8-channel chunk c8) with all horizontal taps
-// in N, column n = (cb*KW + j)*CSTRIDE + ci, or (c8, horizontal tap j) with N = filters.  Odd unit counts pair the last
+// Weight image: for every K step ks a hi block then a lo block, each [2 units][kh taps][NCOLS][8] fp16 (K-major,
+// LBO = kh*NCOLS*16 B between the two 8-channel units).  The vertical taps sit side by side in DESCENDING order (tap kh-1
+// first): input row r feeds output rows r - i*dil, whose accumulators are adjacent TMEM columns in ascending row order, so
+// one MMA over a run of taps reads a contiguous column range of the block.  A unit is (8-channel chunk c8) with all
+// horizontal taps in N, column n = (cb*KW + j)*CSTRIDE + ci, or (c8, horizontal tap j) with N = filters.  Odd unit counts pair the last
 // unit with a zero unit that re-reads finite data.  The weights are scaled by 2^e_w (max|w| * 2^e_w in [2^13, 2^14))
 // before they are split, so that a trained layer's small weights keep all 22 bits of the split.
 int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host, std::vector<__half>* img,
@@ -296,8 +301,9 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
         for (double v : l1) m = std::max(m, v);
         ws->l1max = (float)(m * (1.0 + 1e-6));
     }
-    const size_t block = (size_t)2 * L.NCOLS * 8;  // fp16 elements of one (ks, i, hi|lo) block
-    img->assign((size_t)L.KS * d.kh * 2 * block, __float2half(0.f));
+    const size_t unit = (size_t)d.kh * L.NCOLS * 8;  // fp16 elements of one 8-channel unit of a (ks, hi|lo) block
+    const size_t block = 2 * unit;
+    img->assign((size_t)L.KS * 2 * block, __float2half(0.f));
     for (int ks = 0; ks < L.KS; ++ks) {
         const U& u0 = units[2 * ks];
         const U& u1 = units[2 * ks + 1];
@@ -310,8 +316,8 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
             for (int half = 0; half < 2; ++half) {
                 const U& u = half ? u1 : u0;
                 if (u.zero) continue;
-                const size_t bh = ((size_t)(ks * d.kh + i) * 2 + 0) * block + (size_t)half * L.NCOLS * 8;
-                const size_t bl = ((size_t)(ks * d.kh + i) * 2 + 1) * block + (size_t)half * L.NCOLS * 8;
+                const size_t bh = ((size_t)ks * 2 + 0) * block + (size_t)half * unit + (size_t)(d.kh - 1 - i) * L.NCOLS * 8;
+                const size_t bl = ((size_t)ks * 2 + 1) * block + (size_t)half * unit + (size_t)(d.kh - 1 - i) * L.NCOLS * 8;
                 for (int cb = 0; cb < L.CBLK; ++cb)
                     for (int j = (u.j >= 0 ? u.j : 0); j < (u.j >= 0 ? u.j + 1 : d.kw); ++j)
                         for (int ci = 0; ci < L.CSTRIDE; ++ci) {
@@ -400,10 +406,10 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     memset(&p, 0, sizeof(p));
     sw_unit_geometry(d, L, g_tc_sms, opt.bands, &p);
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
-    p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC;
+    p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC; p.fold = L.fold;
     p.planes_in = L.planes;
     p.rowpitch = L.rowpitch; p.stage_stride = L.stage_stride; p.b_unit16 = (uint32_t)(2 * L.NCOLS); p.b_bytes = L.b_bytes;
-    p.idesc = (1u << 4) | ((uint32_t)(L.NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major
+    p.idesc = (1u << 4) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128; N is set per MMA run
     p.act = d.act; p.bias = bias; p.bimg = bimg; p.xp = xp;
     p.debug = opt.debug;
     p.in_plane0 = win.in_plane0; p.in_planes_total = win.in_planes_total ? win.in_planes_total : L.planes;
@@ -486,7 +492,7 @@ int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, con
     ps.e = words; ps.amax = reinterpret_cast<float*>(words + 1); ps.fresh = 1;
     int rc = tc_pack_state(x, xp, d.N, d.Cin, d.H, d.W, L.wpad, d.x_stride_n, d.x_stride_c, d.x_stride_h, stream, 0, 0, ps);
     TcScale sc;
-    sc.e_in = words; sc.amax_in = reinterpret_cast<float*>(words + 1);
+    sc.e_in = words; sc.amax_in = reinterpret_cast<float*>(words + 1); sc.amax_chk = sc.amax_in;
     sc.e_w = ws.e_w; sc.l1max = ws.l1max;
     for (float b : b_host) sc.bmax = std::max(sc.bmax, fabsf(b));
     if (!rc) rc = tc_launch(d, L, kst, xp, bimg, bias, y, nullptr, 0, 0, stream, TcWindow(), sc, TcOptions());

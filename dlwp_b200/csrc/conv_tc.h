@@ -39,7 +39,11 @@ __host__ __device__ inline int tc_exp_for_bound(float B) {
 struct TcScale {
     const int* e_in = nullptr;       // exponent of the source image (device word); null: e_in_const
     int e_in_const = 0;
-    const float* amax_in = nullptr;  // measured max|x| of the source in true units (device word); null: 1
+    const float* amax_in = nullptr;  // bound on the source's |x| in true units: its measured amax (device word) when the
+                                     // source is dynamic; null for a static (tanh) source: 1, so that the exponent this
+                                     // launch derives is a function of the weights alone (identical on every rank of a
+                                     // latitude-band run, whatever rows the rank measured)
+    const float* amax_chk = nullptr; // measured max|x| of the source (device word), for the underflow check only
     int* e_out = nullptr;            // exponent of the destination image, decided by this launch (device word); null: static
     int e_out_const = TC_EXP_STATIC;
     float* amax_out = nullptr;       // max|y| of this launch's outputs is atomically max-ed into this word (may be null)
@@ -77,7 +81,8 @@ struct TcLayer {
     int S;                 // valid outputs per strip: 128 - (kw-1)*dil
     int taps_in_k, kw_eff; // horizontal taps folded into K (shifted A views) -> the epilogue sees a 1-tap layer
     int KS, NS;            // K=16 steps per input row, shared-memory row stages
-    int NACC;              // TMEM accumulator ring (output rows in flight)
+    int NACC;              // TMEM accumulator ring (output rows in flight); a multiple of the dilation
+    int fold;              // vertical taps covered by one MMA (N = fold * NCOLS <= 256)
     uint32_t stage_stride, b_bytes;
     size_t smem;
     int nfull, rem, pair;  // full strips per row, valid outputs of the remainder strip, remainder strips of 2 samples share a tile
@@ -105,7 +110,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
                  int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream,
                  int row_begin, int row_end, const TcScale& sc);  // destination rows [row_begin, row_end); 0,0 = all
-// fp32 (N,C,H,W) -> P image, rows [row0, row1) (0,0 = all).  fresh: measure max|x| over the WHOLE (N,C,H,W) tensor into
+// fp32 (N,C,H,W) -> P image, rows [row0, row1) (0,0 = all).  fresh: measure max|x| over rows [amax_row0, amax_row1) into
 // *amax (which must be zero), derive the image's exponent from it and publish it in *e; otherwise the image keeps the
 // exponent in *e (rows that join an image another kernel produced, e.g. halo rows received from a neighbour) and the
 // packed rows' max|x| is max-ed into *amax.
@@ -114,6 +119,7 @@ struct TcPackScale {
     float* amax = nullptr;
     float* amax_zero = nullptr;
     int fresh = 1;
+    int amax_row0 = 0, amax_row1 = 0;  // fresh: rows whose max|x| defines the exponent (0,0 = all H rows)
 };
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps);

@@ -92,7 +92,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // O(1) pre-activations but with no relative accuracy left once they are small (x = 1e-4: 1.7e-4 relative), which broke the
 // per-layer parity bar for down-scaled inputs / weights.  tanh.approx.f32 (2^-11) would not pass the 1e-4 / 50-step gate.
 __device__ __forceinline__ float tanh_accurate(float x) {
-    x = fminf(fmaxf(x, -9.0f), 9.0f);
+    const float x_in = x;
+    x = fminf(fmaxf(x, -9.0f), 9.0f);   // (drops a NaN; restored below)
     const float x2 = x * x;
     float p = fmaf(x2, -2.76076847742355e-16f, 2.00018790482477e-13f);
     p = fmaf(x2, p, -8.60467152213735e-11f);
@@ -105,7 +106,7 @@ __device__ __forceinline__ float tanh_accurate(float x) {
     q = fmaf(x2, q, 4.89352518554385e-03f);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
-    return x * p * r;
+    return x_in != x_in ? x_in : x * p * r;   // tanh(NaN) = NaN, as in the reference's fp32 arithmetic
 }
 
 // Two tanh at once on packed fp32 pairs (sm_100 fma.rn.f32x2, SASS FFMA2): same arithmetic, half the FMA instructions.
@@ -114,6 +115,7 @@ __device__ __forceinline__ void tanh_accurate2(float& a, float& b) {
     typedef unsigned long long f2;
     auto pk = [](float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; };
     auto fma2 = [](f2 x, f2 y, f2 z) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z)); return d; };
+    const float a_in = a, b_in = b;
     a = fminf(fmaxf(a, -9.0f), 9.0f);
     b = fminf(fmaxf(b, -9.0f), 9.0f);
     const f2 x = pk(a, b), zero = pk(0.f, 0.f);
@@ -134,8 +136,8 @@ __device__ __forceinline__ void tanh_accurate2(float& a, float& b) {
     float r0, r1;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
-    a = p0 * r0;
-    b = p1 * r1;
+    a = a_in != a_in ? a_in : p0 * r0;
+    b = b_in != b_in ? b_in : p1 * r1;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -290,9 +290,12 @@ static TcScale scale_of(const DlwpPlan* pl, int i, int t) {
     const DlwpOpDesc& op = pl->ops[i];
     TcScale sc;
     const Buffer& s = pl->buffers[op.src];
-    if (!s.e_static) sc.e_in = pl->d_exp + op.src;
     sc.e_in_const = TC_EXP_STATIC;
-    sc.amax_in = pl->d_amax + 2 * op.src + (t & 1);
+    sc.amax_chk = pl->d_amax + 2 * op.src + (t & 1);
+    if (!s.e_static) {  // a static (tanh) source bounds the output with |x| <= 1: exponents independent of the data
+        sc.e_in = pl->d_exp + op.src;
+        sc.amax_in = sc.amax_chk;
+    }
     const int pd = pl->tc_pdst[i];
     if (pd >= 0) {
         const int prod = pd == pl->input_buf ? t + 1 : t;
@@ -341,7 +344,8 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bo
 
 // One application of the chain at iteration t.  input_is_packed: the feedback conv of iteration t - 1 already wrote the
 // input image (rollout).  feedback_write: let the feedback conv write the next input image (off for a plain forward).
-static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool input_is_packed, bool feedback_write) {
+static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool input_is_packed, bool feedback_write,
+                      bool input_rows_all_valid) {
     Buffer& in = pl->buffers[pl->input_buf];
     pl->tc_last_t = t;
     TcPackScale ps;
@@ -350,6 +354,10 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool inpu
     if (!input_is_packed) {
         ps.fresh = 1;
         ps.amax_zero = pl->d_amax + 2 * pl->input_buf + ((t + 1) & 1);
+        // The exponent comes from max|x| over the whole state when every row is known to be valid (x0 of a rollout: the
+        // same value on every rank of a latitude-band run), else over the rows this plan reads (a band's series slot
+        // holds garbage outside band + halo).
+        if (!input_rows_all_valid) { ps.amax_row0 = pl->tc_in_row0; ps.amax_row1 = pl->tc_in_row1; }
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
                                (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1, ps);
         if (rc) return rc;
@@ -441,7 +449,8 @@ static int rollout_range(DlwpPlan* pl, int N, const float* x0, float* series, in
         pl->buffers[pl->input_buf].ptr =
             const_cast<float*>(t == 0 ? x0 : series + ((long long)t * n_out - 1) * slot);
         for (int k = 0; k < n_out; ++k) pl->buffers[pl->outputs[k]].ptr = series + ((long long)t * n_out + k) * slot;
-        int rc = pl->tc ? run_ops_tc(pl, N, stream, t, t > 0 && pl->tc_feedback_op >= 0, true) : run_ops(pl, N, stream);
+        int rc = pl->tc ? run_ops_tc(pl, N, stream, t, t > 0 && pl->tc_feedback_op >= 0, true, t == 0)
+                        : run_ops(pl, N, stream);
         if (rc) return rc;
     }
     return 0;
@@ -648,7 +657,7 @@ extern "C" int dlwp_plan_forward(DlwpPlan* pl, int32_t N, const float* x, float*
     }
     if (!pl->tc) return run_ops(pl, N, (cudaStream_t)stream);
     DLWP_CUDA_TRY(cudaMemsetAsync(pl->d_amax, 0, sizeof(float) * 2 * pl->buffers.size(), (cudaStream_t)stream));
-    return run_ops_tc(pl, N, (cudaStream_t)stream, 0, false, false);
+    return run_ops_tc(pl, N, (cudaStream_t)stream, 0, false, false, false);
 }
 
 extern "C" int dlwp_rollout(DlwpPlan* pl, int32_t N, const float* x0, float* series, int32_t iterations,

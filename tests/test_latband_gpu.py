@@ -1,8 +1,13 @@
 """
 Latitude-band execution on the GPU: P row-windowed plans run in ONE process (the exchange is emulated with device copies
-between the per-rank series), and the assembled bands must equal the single-domain rollout BIT FOR BIT -- same kernels,
-same per-pixel summation order, only the tile origins differ.
+between the per-rank series), and the assembled bands must equal the single-domain rollout to fp32 round-off -- same
+kernels, same per-pixel summation order, only the tile origins differ.  (Not bit for bit any more: this driver re-packs the
+state from a series slot every iteration, and the exponent of the scaled fp16 split then comes from the amax of the rows
+the band reads, which differs from the global amax; the native rollout (dlwp_rollout_latband) derives the state's exponent
+from the weights alone and stays bit-identical -- bench.py checks that on every multi-GPU run.)
 """
+
+ROUND_OFF = 1e-6   # of max|ref|
 
 import numpy as np
 import pytest
@@ -53,14 +58,14 @@ def _run_bands(model, world, x0, iterations):
 
 
 @pytest.mark.parametrize('world', [2, 8])
-def test_net_a_bands_equal_single_domain_bit_for_bit(world):
+def test_net_a_bands_equal_single_domain_to_round_off(world):
     layers = OL.net_a_layers()
     dlwp = build_product_sequential(layers)
     oracle_sequential_like(dlwp, layers, seed=1, bias_scale=0.05)
     x0 = np.random.RandomState(0).standard_normal((3, 6, 91, 180)).astype(np.float32)
     ref = dlwp.predict_timeseries(x0, 6)
     got, planners = _run_bands(dlwp.model, world, x0, 6)
-    np.testing.assert_array_equal(got, ref)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() <= ROUND_OFF * np.abs(ref).max()
     assert planners[1].halo[0] == 4
 
 
@@ -75,7 +80,7 @@ def test_unet_bands_equal_single_domain():
     assert dlwp.model.engine(2).uses_tensor_cores()
     ref = dlwp.predict_timeseries(x0, 4)
     got, planners = _run_bands(dlwp.model, 2, x0, 2)
-    np.testing.assert_array_equal(got, ref)
+    assert np.isfinite(got).all() and np.abs(got - ref).max() <= ROUND_OFF * np.abs(ref).max()
     eng = CompiledNet(dlwp.model, 2, force_ffma=True)
     fp32 = eng.rollout_host(x0, 2)
     eng.close()

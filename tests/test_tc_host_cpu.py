@@ -47,6 +47,12 @@ def _pack(nat, desc, w, L):
     return img, kst, int(e_w.value), float(l1.value)
 
 
+def _by_tap(img, L, k):
+    """The packed image is [ks][hi|lo][unit][vertical tap, DESCENDING][col][8] (the taps of one K step sit side by side so
+    that one MMA covers a run of them, conv_tc.cu tc_pack_weights); view it as [ks][tap i][hi|lo][unit][col][8]."""
+    return img.reshape(L['KS'], 2, 2, k, L['NCOLS'], 8).transpose(0, 3, 1, 2, 4, 5)[:, ::-1]
+
+
 def _plan(nat, desc):
     out = (ctypes.c_int32 * 16)()
     rc = nat.lib().dlwp_debug_tc_plan(ctypes.byref(desc), out, 16)
@@ -92,7 +98,7 @@ def test_weight_image_decodes_to_the_keras_kernel(nat, layer):
     rng = np.random.RandomState(sum(layer))
     w = rng.standard_normal((k, k, cin, cout)).astype(np.float32)
     img, kst, e_w, l1max = _pack(nat, desc, w, L)
-    img = img.view(np.float16).astype(np.float64).reshape(L['KS'], k, 2, 2, L['NCOLS'], 8)   # [ks][tap i][hi|lo][unit][col][e]
+    img = _by_tap(img.view(np.float16).astype(np.float64), L, k)                             # [ks][tap i][hi|lo][unit][col][e]
     C8 = (cin + 7) // 8
     units = [(c8, j) for c8 in range(C8) for j in (range(k) if L['taps_in_k'] else [-1])]
     rebuilt = np.zeros((k, k, C8 * 8, cout))
@@ -176,7 +182,7 @@ def _software_model(nat, layer, x, w, b, scaled=True):
     rc, L = _plan(nat, desc)
     assert rc == 0 and L['mode'] == 1
     img, kst, e_w, l1max = _pack(nat, desc, w, L)
-    B = img.view(np.float16).astype(np.float32).reshape(L['KS'], k, 2, 2, L['NCOLS'], 8)    # [ks][tap i][hi|lo][unit][col][e]
+    B = _by_tap(img.view(np.float16).astype(np.float32), L, k)                              # [ks][tap i][hi|lo][unit][col][e]
     e_x = nat.lib().dlwp_debug_exp_for_bound(float(np.abs(x).max()))       # what pack_state_kernel derives from amax(x)
     if not scaled:                                                         # round 1: no exponents at all
         B = B * np.float32(2.0 ** -e_w)
