@@ -100,34 +100,44 @@ def oracle_net():
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  The sampler
+    is started ahead of the region (nvidia-smi needs a moment to come up); `mark()` brackets the region and only samples
+    taken between the marks -- while the kernels run -- enter the summary."""
+    FIELDS = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         self.rows = []
         self.proc = None
         self.index = index
+        self.period_ms = period_ms
+        self.marks = []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:      # first sample in hand before the region starts
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        self.marks.append(time.time())
 
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(2.5 * self.period_ms / 1000.0)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -137,10 +147,12 @@ class ClockSampler(object):
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        lo, hi = (self.marks[0], self.marks[-1] + self.period_ms / 1000.0) if len(self.marks) >= 2 else (0, float('inf'))
+        inside = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows[-2:]]
+        for r in inside:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(names, r[4:8]):
@@ -149,7 +161,7 @@ class ClockSampler(object):
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'period_ms': self.period_ms}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -272,10 +284,12 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
+        clocks.mark()
         e0.record()
         eng.rollout_device(xd, K, use_graph=True, out=series)     # EXACTLY K timed steps
         e1.record()
         barrier()
+        clocks.mark()
     ms = e0.elapsed_time(e1)
     launches = nat.launch_count() - launches0
     if world > 1:
@@ -397,10 +411,12 @@ def run_latband(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
+        clocks.mark()
         e0.record()
         eng.rollout_device(xd, K, out=series)              # EXACTLY K timed steps, K-1 halo exchanges
         e1.record()
         barrier()
+        clocks.mark()
     t = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())

@@ -10,12 +10,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libdlwp_b200.so')
 
 DLWP_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 PAD_ZERO, PAD_PERIODIC = 0, 1
 ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
 IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
 BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2
-OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY = 0, 1, 2, 3, 4
+OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY, OP_LSTM = 0, 1, 2, 3, 4, 5
+RECURRENT_ACTIVATIONS = {'hard_sigmoid': 0, 'sigmoid': 1}
 ACTIVATIONS = {None: ACT_LINEAR, 'linear': ACT_LINEAR, 'tanh': ACT_TANH, 'relu': ACT_RELU}
 IMPLS = {'auto': IMPL_AUTO, 'direct': IMPL_DIRECT, 'ffma': IMPL_FFMA, 'ffma_tma': IMPL_FFMA_TMA, 'tc': IMPL_TC}
 
@@ -38,7 +39,7 @@ class BufferDesc(ctypes.Structure):
 class OpDesc(ctypes.Structure):
     _fields_ = [(n, i32) for n in ('kind', 'src', 'src_c0', 'src_c', 'dst', 'dst_c0', 'weight_id', 'pad_t', 'pad_b',
                                    'pad_l', 'pad_r', 'pad_mode_h', 'pad_mode_w', 'Cout', 'kh', 'kw', 'dil_h', 'dil_w',
-                                   'act', 'pre_op', 'rowwise', 'impl', 'row_begin', 'row_end')]
+                                   'act', 'pre_op', 'rowwise', 'impl', 'row_begin', 'row_end', 'aux', 'aux_c0', 'act2')]
 
 
 class BandInfo(ctypes.Structure):
@@ -75,6 +76,7 @@ SYMBOLS = {
     'dlwp_maxpool2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_upsample2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_copy4d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_convlstm_gates': (ctypes.c_int, [fptr] * 5 + [i32] * 4 + [i64] * 4 + [i32] * 4 + [ctypes.c_void_p]),
     'dlwp_rows_op': (ctypes.c_int, [i32, fptr, fptr] + [i32] * 10 + [i64] * 6 + [i32, i32, ctypes.c_void_p]),
     'dlwp_plan_create': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(ctypes.c_void_p)]),
     'dlwp_plan_create_opts': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(PlanOptions),
@@ -106,6 +108,7 @@ SYMBOLS = {
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.c_void_p]),
     'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),
+    'dlwp_plan_fused_pair': (ctypes.c_int, [ctypes.c_void_p]),
     'dlwp_last_error_string': (ctypes.c_char_p, []),
     'dlwp_abi_version': (ctypes.c_int, []),
     'dlwp_kernel_launch_count': (ctypes.c_int64, []),
@@ -119,6 +122,7 @@ SYMBOLS = {
                                             ctypes.POINTER(ctypes.c_uint32), i32, ctypes.POINTER(i32),
                                             ctypes.POINTER(ctypes.c_float)]),
     'dlwp_debug_tc_folded': (ctypes.c_char_p, [ctypes.POINTER(ConvDesc), i32]),
+    'dlwp_debug_counters': (ctypes.c_int, [ctypes.POINTER(ctypes.c_int64), i32]),
     'dlwp_debug_exp_for_bound': (ctypes.c_int, [ctypes.c_float]),
 }
 

@@ -23,9 +23,18 @@
 #ifndef DLWP_SW_TU_FLAGS
 #error "define DLWP_SW_TU_FLAGS (name of this translation unit's device flag word) before including conv_sw.cuh"
 #endif
+#define DLWP_SW_CAT2(a, b) a##b
+#define DLWP_SW_CAT(a, b) DLWP_SW_CAT2(a, b)
+#define DLWP_SW_TU_COUNTERS DLWP_SW_CAT(DLWP_SW_TU_FLAGS, _counters)
 namespace dlwp {
 __device__ int DLWP_SW_TU_FLAGS = 0;
+// TcOptions::debug & 4: clock64 totals of the MMA-issuing warp, summed over CTAs:
+// [0] waiting for an accumulator slot, [1] waiting for a staged row, [2] issuing MMAs + commits, [3] rows; [4..7] the same
+// for the second layer of the fused kernel; [8] issuing warp's clocks from kernel entry to its last commit, [9] the same
+// span in globaltimer ns, [10] CTAs counted, [11] clocks from kernel entry to the first staged row's arrival
+__device__ unsigned long long DLWP_SW_TU_COUNTERS[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }
+#define g_tc_counters DLWP_SW_TU_COUNTERS
 #define g_device_flags DLWP_SW_TU_FLAGS
 #define g_tc_flags DLWP_SW_TU_FLAGS
 #include "internal.h"
@@ -207,7 +216,8 @@ struct SwParams {
     int N, H, W, Wp;
     int D, pad_t;
     int S, nfull, rem, pair;          // strips: valid outputs per full strip, full strips per row, remainder, pairing
-    int units_per_group, nbands, RB, total_units;
+    int units_per_group, nbands, RB, total_units;   // (strip x band) units: the fused pair kernel's schedule (sw_decode)
+    int nstrips, total_rows;          // conv_sw_kernel: strips over all samples, nstrips * (row1 - row0) (sw_next)
     int row0, row1;
     int Cout, NCOLS, CBLK, CSTRIDE, XL;
     int KS, NS, NACC;
@@ -236,7 +246,8 @@ struct SwUnit {
     int paired;      // lanes 64.. belong to segment b
 };
 
-__host__ __device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwUnit& U) {
+template <class P>
+__host__ __device__ __forceinline__ bool sw_decode(const P& p, int u, SwUnit& U) {
     const int band = u % p.nbands, su = u / p.nbands;
     const int g = su / p.units_per_group, k = su - g * p.units_per_group;
     U.ya = p.row0 + band * p.RB;
@@ -253,6 +264,45 @@ __host__ __device__ __forceinline__ bool sw_decode(const SwParams& p, int u, SwU
         if (2 * g + 1 < p.N) { U.n1 = 2 * g + 1; U.nvb = p.rem; }
     }
     return U.n0 < p.N && U.ya < U.yb;
+}
+
+// conv_sw_kernel's schedule: the output rows of all strips form one sequence (strip-major, top to bottom) that is cut
+// into gridDim.x contiguous ranges of equal length; a CTA walks its range as segments ("units": one strip, rows [ya, yb)).
+// Every segment costs (KH-1)*dil warm-up input rows, and a range touches at most rows/len + 2 strips, so the CTAs stay
+// balanced to within a few rows -- against (strip x latitude band) units dealt round robin this removed ~9 % of the
+// staged rows of the slowest CTA at batch 256 (profiles/r02_balanced_ranges.txt).  Strips: all full strips first
+// (sample-major), then the (paired) remainder strips.
+struct SwIter {
+    long long g, g1;
+};
+template <class P>
+__host__ __device__ __forceinline__ void sw_range(const P& p, int cta, int nctas, SwIter& it) {
+    it.g = (long long)p.total_rows * cta / nctas;
+    it.g1 = (long long)p.total_rows * (cta + 1) / nctas;
+}
+template <class P>
+__host__ __device__ __forceinline__ bool sw_next(const P& p, SwIter& it, SwUnit& U) {
+    if (it.g >= it.g1) return false;
+    const int rows = p.row1 - p.row0;
+    const int su = (int)(it.g / rows), y = (int)(it.g - (long long)su * rows);
+    int n = rows - y;
+    if ((long long)n > it.g1 - it.g) n = (int)(it.g1 - it.g);
+    it.g += n;
+    U.ya = p.row0 + y;
+    U.yb = U.ya + n;
+    U.n1 = -1; U.nvb = 0; U.paired = 0;
+    const int nfs = p.N * p.nfull;           // full strips
+    if (su < nfs) {
+        U.n0 = su / p.nfull; U.x0 = (su - U.n0 * p.nfull) * p.S; U.nva = p.S;
+    } else if (!p.pair) {
+        U.n0 = su - nfs; U.x0 = p.nfull * p.S; U.nva = p.rem;
+    } else {
+        const int g = su - nfs;
+        U.paired = 1;
+        U.n0 = 2 * g; U.x0 = p.nfull * p.S; U.nva = p.rem;
+        if (2 * g + 1 < p.N) { U.n1 = 2 * g + 1; U.nvb = p.rem; }
+    }
+    return true;
 }
 
 constexpr uint32_t SW_IDESC = (1u << 4) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128; N per MMA
@@ -281,7 +331,7 @@ struct SwRing {
 // One input row's MMAs with everything but the stage address folded at compile time (POS = ring position of the window's
 // lowest row).  Runs of vertical taps: cut every FOLD taps, at the ring's end, and before tap 0 in the very first MMA (the
 // new row's accumulator is overwritten, the others accumulate).
-template <int KH, int NCOLS, int KS, int RING, int FOLD, int POS>
+template <int KH, int NCOLS, int KS, int RING, int FOLD, int POS, bool HINTS = true>
 __device__ __forceinline__ void sw_issue_row_pos(bool leader, uint32_t tres, uint32_t sbase16, uint32_t pitch16,
                                                  uint32_t desc_hi, uint32_t bbase, const TcKStep* kst) {
     constexpr uint32_t bblock16 = 2u * KH * NCOLS;
@@ -308,7 +358,10 @@ __device__ __forceinline__ void sw_issue_row_pos(bool leader, uint32_t tres, uin
                     const bool first = pass != 1 && run_tb == KH - 1, last = pass != 0 && t == 0;
                     const uint32_t acc = (fresh && run_tb == 0) ? 0u : 1u;
                     if (leader) {
-                        if (first && !last) umma_f16_c<1>(dcol, ad, bd, idesc, acc);
+                        // (HINTS off: two warps issue into the same tensor core -- another warp's MMA may sit between a
+                        // fill and its use, so the collector cannot be relied on)
+                        if (!HINTS) umma_f16_c<0>(dcol, ad, bd, idesc, acc);
+                        else if (first && !last) umma_f16_c<1>(dcol, ad, bd, idesc, acc);
                         else if (!first && last) umma_f16_c<3>(dcol, ad, bd, idesc, acc);
                         else if (!first) umma_f16_c<2>(dcol, ad, bd, idesc, acc);
                         else umma_f16_c<0>(dcol, ad, bd, idesc, acc);
@@ -436,8 +489,9 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
             uint32_t ph = 0;
             const uint32_t row_bytes = (uint32_t)p.planes_in * p.rowpitch;
             SwUnit U;
-            for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-                if (!sw_decode(p, u, U)) continue;
+            SwIter it;
+            sw_range(p, blockIdx.x, gridDim.x, it);
+            while (sw_next(p, it, U)) {
                 const int nrows = U.yb - U.ya + SPAN;
                 int row = U.ya - p.pad_t + TC_HPAD;
                 const int plane = U.n0 * p.in_planes_total + p.in_plane0;
@@ -456,8 +510,9 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         int s = 0;
         uint32_t ph = 0;  // parity of the stage ring's current lap
         SwUnit U;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            if (!sw_decode(p, u, U)) continue;
+        SwIter it;
+        sw_range(p, blockIdx.x, gridDim.x, it);
+        while (sw_next(p, it, U)) {
             const int nseg = U.n1 >= 0 ? 2 : 1;
             const int avail = p.Wp - U.x0;                                   // pixels left in the padded row
             const uint32_t lenA = (uint32_t)min(U.paired ? 64 : (int)(p.rowpitch >> 4), avail) * 16u;
@@ -511,17 +566,26 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         uint32_t ph = 0;
         SwRing ring;        // position of the next row to start (CTA-wide numbering, phantoms included)
         SwUnit U;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            if (!sw_decode(p, u, U)) continue;
+        const bool timing = (p.debug & 4) != 0;
+        long long t_acc = 0, t_full = 0, t_issue = 0, n_rows = 0, t_first = 0;
+        const long long k_c0 = timing ? clock64() : 0;
+        unsigned long long k_g0 = 0;
+        if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(k_g0));
+        SwIter it;
+        sw_range(p, blockIdx.x, gridDim.x, it);
+        while (sw_next(p, it, U)) {
             const int nrows = U.yb - U.ya + SPAN;
             for (int k = 0; k < SPAN; ++k) {        // phantom rows above the band: take their slots
                 mbar_wait(&acc_empty[ring.slot(RING)], ring.lap ^ 1);
                 ring.advance(D, RING);
             }
             for (int r = 0; r < nrows; ++r) {
+                const long long c0 = timing ? clock64() : 0;
                 mbar_wait(&acc_empty[ring.slot(RING)], ring.lap ^ 1);  // the row that starts here: its slot must be drained
+                const long long c1 = timing ? clock64() : 0;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
+                const long long c2 = timing ? clock64() : 0;
                 const uint32_t sbase16 = stages16 + (uint32_t)s * stride16;
                 int pos_lo = ring.q - (KH - 1);     // ring position of the window's lowest row (same residue class)
                 if (pos_lo < 0) pos_lo += RING;
@@ -568,6 +632,11 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 }
                 if (++s == p.NS) { s = 0; ph ^= 1; }
                 ring.advance(D, RING);
+                if (timing) {
+                    const long long c3 = clock64();
+                    if (n_rows == 0) t_first = c2 - k_c0;
+                    t_acc += c1 - c0; t_full += c2 - c1; t_issue += c3 - c2; ++n_rows;
+                }
             }
             // phantom rows below the band (started by the last SPAN input rows, never completed): release them
             if (leader) {
@@ -578,6 +647,18 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 }
             }
             __syncwarp();
+        }
+        if (timing && leader) {
+            atomicAdd(&g_tc_counters[0], (unsigned long long)t_acc);
+            atomicAdd(&g_tc_counters[1], (unsigned long long)t_full);
+            atomicAdd(&g_tc_counters[2], (unsigned long long)t_issue);
+            atomicAdd(&g_tc_counters[3], (unsigned long long)n_rows);
+            unsigned long long k_g1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(k_g1));
+            atomicAdd(&g_tc_counters[8], (unsigned long long)(clock64() - k_c0));
+            atomicAdd(&g_tc_counters[9], k_g1 - k_g0);
+            atomicAdd(&g_tc_counters[10], 1ull);
+            atomicAdd(&g_tc_counters[11], (unsigned long long)t_first);
         }
     } else {
         // =============================== epilogue: 4 sets x 4 quadrant warps, rows dealt round robin ===================
@@ -592,8 +673,9 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         float amax_t = 0.f;   // max |output| this thread produced (true units)
         int g = 0, lrow = 0;
         SwUnit U;
-        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-            if (!sw_decode(p, u, U)) continue;
+        SwIter it;
+        sw_range(p, blockIdx.x, gridDim.x, it);
+        while (sw_next(p, it, U)) {
             const int ml = q * 32 + lane;
             const int seg = (U.paired && ml >= 64) ? 1 : 0;
             const int l = ml - seg * 64;
@@ -769,6 +851,16 @@ static inline int sw_tu_flags_read_clear() {
     cudaMemcpyToSymbol(DLWP_SW_TU_FLAGS, &zero, sizeof(int));
     return v;
 }
+static inline void sw_tu_counters_read_clear(unsigned long long* acc12) {
+    unsigned long long v[12], zero[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(v, DLWP_SW_TU_COUNTERS, sizeof(v)) != cudaSuccess) return;
+    cudaMemcpyToSymbol(DLWP_SW_TU_COUNTERS, zero, sizeof(zero));
+    for (int i = 0; i < 12; ++i) acc12[i] += v[i];
+}
+void sw_counters_net_a(unsigned long long* acc8);
+void sw_counters_net_b(unsigned long long* acc8);
+void sw_counters_net_basic(unsigned long long* acc8);
+void sw_counters_fused(unsigned long long* acc8);
 int sw_flags_net_a();
 int sw_flags_net_b();
 int sw_flags_net_basic();

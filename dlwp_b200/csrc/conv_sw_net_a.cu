@@ -15,4 +15,5 @@ const SwFolded* sw_folded_net_a(int* n) {
     return kTable;
 }
 int sw_flags_net_a() { return sw_tu_flags_read_clear(); }
+void sw_counters_net_a(unsigned long long* acc8) { sw_tu_counters_read_clear(acc8); }
 }  // namespace dlwp

@@ -20,4 +20,5 @@ const SwFolded* sw_folded_net_b(int* n) {
     return kTable;
 }
 int sw_flags_net_b() { return sw_tu_flags_read_clear(); }
+void sw_counters_net_b(unsigned long long* acc8) { sw_tu_counters_read_clear(acc8); }
 }  // namespace dlwp

@@ -17,4 +17,5 @@ const SwFolded* sw_folded_net_basic(int* n) {
     return kTable;
 }
 int sw_flags_net_basic() { return sw_tu_flags_read_clear(); }
+void sw_counters_net_basic(unsigned long long* acc8) { sw_tu_counters_read_clear(acc8); }
 }  // namespace dlwp

@@ -338,9 +338,11 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     return 0;
 }
 
-// The scheduling units of one launch: (strip or paired remainder strips) x (latitude band), see sw_decode.  Host-only
-// arithmetic (also driven by the CPU tests through dlwp_debug_sw_cover); returns the number of sample groups.
-static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, int bands_opt, SwParams* pp) {
+// The schedule of one launch (sw_range / sw_next): nstrips strips x rows output rows, cut into `grid` contiguous ranges.
+// min_rows (DlwpPlanOptions.tc_bands; default 8): a CTA is not started for fewer output rows than this -- every range pays
+// (KH-1)*dil warm-up rows per strip it touches.  Host-only arithmetic (also driven by the CPU tests through
+// dlwp_debug_sw_cover); returns the grid size.
+static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, int min_rows, SwParams* pp) {
     SwParams& p = *pp;
     p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = L.Wp;
     p.D = d.dil_w; p.pad_t = d.pad_t;
@@ -348,32 +350,17 @@ static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, in
     const bool all_rows = d.row_begin == 0 && d.row_end == 0;
     p.row0 = all_rows ? 0 : d.row_begin;
     p.row1 = all_rows ? d.H : d.row_end;
-    const int rows = p.row1 - p.row0, span = d.dil_h * (d.kh - 1);
-    const int groups = L.pair ? cdiv(d.N, 2) : d.N;
-    p.units_per_group = L.pair ? 2 * L.nfull + 1 : L.nfull + (L.rem > 0 ? 1 : 0);
+    const int rows = p.row1 - p.row0;
+    p.units_per_group = 0; p.nbands = 1; p.RB = rows > 0 ? rows : 1; p.total_units = 0;
+    p.nstrips = d.N * L.nfull + (L.rem > 0 ? (L.pair ? cdiv(d.N, 2) : d.N) : 0);
     if (rows <= 0) {  // empty latitude window
-        p.RB = 1; p.nbands = 1; p.total_units = 0;
-        return groups;
+        p.total_rows = 0;
+        return 0;
     }
-    // latitude bands per strip: enough units to balance the SMs, few enough that the (KH-1)*dil halo rows re-read at
-    // every band edge stay a small fraction
-    int best_nb = 1;
-    double best_score = -1.0;
+    p.total_rows = p.nstrips * rows;
     if (sms < 1) sms = 148;
-    for (int nb = 1; nb <= 16 && nb <= rows; ++nb) {
-        const int rb = cdiv(rows, nb);
-        if (cdiv(rows, rb) != nb) continue;
-        const long long total = (long long)groups * p.units_per_group * nb;
-        const double balance = (double)total / (double)(cdiv((int)total, sms) * (long long)sms);
-        const double reread = (double)rows / (double)(rows + span * nb);
-        const double score = balance * (0.5 + 0.5 * reread);
-        if (score > best_score + 1e-9) { best_score = score; best_nb = nb; }
-    }
-    if (bands_opt > 0) best_nb = std::min(bands_opt, rows);
-    p.RB = cdiv(rows, best_nb);
-    p.nbands = cdiv(rows, p.RB);
-    p.total_units = groups * p.units_per_group * p.nbands;
-    return groups;
+    if (min_rows < 1) min_rows = 8;
+    return std::max(1, std::min(sms, p.total_rows / min_rows));
 }
 
 static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int nc, int out_mode) {
@@ -404,7 +391,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     if (!(d.row_begin == 0 && d.row_end == 0) && d.row_end <= d.row_begin) return 0;  // empty latitude window: nothing to do
     SwParams p;
     memset(&p, 0, sizeof(p));
-    sw_unit_geometry(d, L, g_tc_sms, opt.bands, &p);
+    const int grid = sw_unit_geometry(d, L, g_tc_sms, opt.bands, &p);
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
     p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC; p.fold = L.fold;
     p.planes_in = L.planes;
@@ -418,7 +405,6 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
     p.sc = sc;
     for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
-    const int grid = std::min(p.total_units, g_tc_sms);
     if (grid <= 0) return 0;
     const int nc = L.CSTRIDE == 6 ? 6 : 8;
     // Tensor-map producer: the staged row is exactly 128 pixels per plane, one box per row and unit.
@@ -548,14 +534,17 @@ extern "C" int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_
     DLWP_REQUIRE(tc_geometry_ok(*desc) && tc_plan_layer(*desc, &L) == 0, DLWP_ESHAPE, "not a sliding-window layer");
     SwParams p;
     memset(&p, 0, sizeof(p));
-    sw_unit_geometry(*desc, L, sms, 0, &p);
-    long long staged_rows = 0;
+    const int grid = sw_unit_geometry(*desc, L, sms, 0, &p);
+    long long staged_rows = 0, worst = 0;
     int live_units = 0;
     SwUnit U;
-    for (int u = 0; u < p.total_units; ++u) {
-        if (!sw_decode(p, u, U)) continue;
+    for (int cta = 0; cta < grid; ++cta) {
+      SwIter it;
+      sw_range(p, cta, grid, it);
+      long long mine = 0;
+      while (sw_next(p, it, U)) {
         ++live_units;
-        staged_rows += U.yb - U.ya + desc->dil_h * (desc->kh - 1);
+        mine += U.yb - U.ya + desc->dil_h * (desc->kh - 1);
         for (int ml = 0; ml < 128; ++ml) {  // the epilogue's lane -> (sample, column) map
             const int seg = (U.paired && ml >= 64) ? 1 : 0;
             const int l = ml - seg * 64;
@@ -564,8 +553,11 @@ extern "C" int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_
             if (n < 0 || l >= (seg ? U.nvb : U.nva) || x >= p.W) continue;
             for (int y = U.ya; y < U.yb; ++y) ++cover[((int64_t)n * desc->H + y) * desc->W + x];
         }
+      }
+      staged_rows += mine;
+      worst = std::max(worst, mine);
     }
-    info[0] = p.total_units; info[1] = live_units; info[2] = p.nbands; info[3] = (int32_t)staged_rows;
+    info[0] = grid; info[1] = live_units; info[2] = (int32_t)worst; info[3] = (int32_t)staged_rows;
     return 0;
 }
 
@@ -580,4 +572,20 @@ extern "C" const char* dlwp_debug_tc_folded(const DlwpConvDesc* desc, int32_t ou
     if (!tc_geometry_ok(*desc) || tc_plan_layer(*desc, &L) != 0) return nullptr;
     const SwFolded* f = find_folded(*desc, L, L.CSTRIDE == 6 ? 6 : 8, out_mode);
     return f ? f->what : nullptr;
+}
+
+// TcOptions::debug & 4 (DlwpPlanOptions.tc_debug): clock64 totals of the MMA-issuing warps since the last call, summed over
+// CTAs and kernels: out[0] waiting for accumulator slots, [1] waiting for staged rows, [2] issuing, [3] rows issued.
+extern "C" int dlwp_debug_counters(int64_t* out, int32_t n) {
+    using namespace dlwp;
+    DLWP_REQUIRE(out && n >= 8, DLWP_EINVAL, "bad argument");
+    unsigned long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaDeviceSynchronize();
+    sw_tu_counters_read_clear(acc);
+    sw_counters_net_a(acc);
+    sw_counters_net_b(acc);
+    sw_counters_net_basic(acc);
+    sw_counters_fused(acc);
+    for (int i = 0; i < 12 && i < n; ++i) out[i] = (int64_t)acc[i];
+    return 0;
 }

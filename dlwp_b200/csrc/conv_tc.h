@@ -123,6 +123,16 @@ struct TcPackScale {
 };
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps);
+// Two consecutive layers in one kernel (conv_fused.cu): layer 1's output never leaves the SM.  tc_pair_ok: the pair matches
+// an instantiated configuration.  The state image (layer 1's source) must carry wpad1 + wpad2 halo columns, and layer 1's
+// weights must be packed with TcLayer::rowpitch = tc_pair_state_pitch (the staged state row is wider than 128 pixels).
+bool tc_pair_ok(const DlwpConvDesc& d1, const TcLayer& L1, const DlwpConvDesc& d2, const TcLayer& L2);
+uint32_t tc_pair_state_pitch(const DlwpConvDesc& d1);
+int tc_pair_launch(const DlwpConvDesc& d1, const TcLayer& L1, const TcKStep* kst1, const __half* bimg1, const float* bias1,
+                   const DlwpConvDesc& d2, const TcLayer& L2, const TcKStep* kst2, const __half* bimg2, const float* bias2,
+                   const __half* xp, int in_planes_total, int in_plane0, float* y32, __half* yp, int wpad_out,
+                   int planes_out, int out_plane0, const TcScale& sc1, const TcScale& sc2, int* done_counter,
+                   cudaStream_t stream, const TcOptions& opt);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
                   cudaStream_t stream);
 int tc_debug_flags();

@@ -70,9 +70,73 @@ static int launch(EwParams p, cudaStream_t stream, const char* name, int row_beg
     return after_launch(name);
 }
 
+// ConvLSTM2D gate step (keras ConvLSTM2DCell.call).  One thread per (n, f, y, x): reads the four (eight) gate
+// pre-activation planes and c_prev, writes c and h -- 10 floats read, 2 written per element, coalesced along W.
+struct LstmParams {
+    const float* z;
+    const float* r;
+    const float* c_prev;
+    float* c_out;
+    float* h_out;
+    int N, F, H, W, row0, rows, act, ract;
+    long long zs_n, rs_n, cs_n, hs_n;
+};
+
+__device__ __forceinline__ float recurrent_act(float v, int ract) {
+    if (ract == DLWP_RACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return fminf(fmaxf(fmaf(0.2f, v, 0.5f), 0.f), 1.f);   // keras hard_sigmoid
+}
+
+__global__ void __launch_bounds__(256) convlstm_gate_kernel(const LstmParams p) {
+    const long long hw = (long long)p.H * p.W;
+    const long long total = (long long)p.N * p.F * p.rows * p.W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % p.W);
+        long long t = idx / p.W;
+        const int y = p.row0 + (int)(t % p.rows);
+        t /= p.rows;
+        const int f = (int)(t % p.F);
+        const int n = (int)(t / p.F);
+        const long long px = (long long)y * p.W + x;
+        const float* z = p.z + (long long)n * p.zs_n + (long long)f * hw + px;
+        const long long g = (long long)p.F * hw;   // distance between gate blocks
+        float zi = z[0], zf = z[g], zc = z[2 * g], zo = z[3 * g];
+        if (p.r != nullptr) {
+            const float* r = p.r + (long long)n * p.rs_n + (long long)f * hw + px;
+            zi += r[0]; zf += r[g]; zc += r[2 * g]; zo += r[3 * g];
+        }
+        const float ig = recurrent_act(zi, p.ract), fg = recurrent_act(zf, p.ract), og = recurrent_act(zo, p.ract);
+        const float cp = p.c_prev != nullptr ? p.c_prev[(long long)n * p.cs_n + (long long)f * hw + px] : 0.f;
+        const float c = fmaf(fg, cp, ig * apply_act(zc, p.act));
+        p.c_out[(long long)n * p.cs_n + (long long)f * hw + px] = c;
+        p.h_out[(long long)n * p.hs_n + (long long)f * hw + px] = og * apply_act(c, p.act);
+    }
+}
+
 }  // namespace dlwp
 
 using namespace dlwp;
+
+extern "C" int dlwp_convlstm_gates(const float* z, const float* r, const float* c_prev, float* c_out, float* h_out,
+                                   int32_t N, int32_t F, int32_t H, int32_t W, int64_t zs_n, int64_t rs_n, int64_t cs_n,
+                                   int64_t hs_n, int32_t act, int32_t ract, int32_t row_begin, int32_t row_end,
+                                   dlwp_stream_t stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    DLWP_REQUIRE(z && c_out && h_out, DLWP_EINVAL, "null tensor pointer");
+    DLWP_REQUIRE(N > 0 && F > 0 && H > 0 && W > 0, DLWP_ESHAPE, "convlstm_gates: non-positive dims");
+    DLWP_REQUIRE(act == DLWP_ACT_LINEAR || act == DLWP_ACT_TANH || act == DLWP_ACT_RELU, DLWP_EINVAL, "bad activation");
+    DLWP_REQUIRE(ract == DLWP_RACT_HARD_SIGMOID || ract == DLWP_RACT_SIGMOID, DLWP_EINVAL, "bad recurrent activation");
+    if (row_begin == 0 && row_end == 0) row_end = H;
+    DLWP_REQUIRE(row_begin >= 0 && row_end <= H && row_begin < row_end, DLWP_ESHAPE, "convlstm_gates: bad row window");
+    LstmParams p{z, r, r ? c_prev : nullptr, c_out, h_out, N, F, H, W, row_begin, row_end - row_begin, act, ract,
+                 zs_n, rs_n, cs_n, hs_n};
+    const long long total = (long long)N * F * p.rows * W;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    convlstm_gate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("convlstm_gates");
+}
 
 extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t,
                           int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n,

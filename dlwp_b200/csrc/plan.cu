@@ -95,10 +95,14 @@ struct DlwpPlan {
     int tc_band_row0 = 0, tc_band_row1 = 0;
     DlwpPlanOptions opt;           // as given to dlwp_plan_create_opts (zeros = defaults)
     TcOptions tc_opt;
-    // scale words of the P images (conv_tc.h): one exponent and two amax slots (production parity) per buffer
+    // scale words of the P images (conv_tc.h): exponent and amax per buffer, each double-buffered by production parity --
+    // the fused kernel reads the state's exponent of iteration t while its first CTA already publishes the one of t + 1
     int* d_exp = nullptr;
     float* d_amax = nullptr;
     int tc_last_t = 0;             // iteration index of the last application (dlwp_plan_profile_op reuses its parity)
+    // ops pair_first and pair_first + 1 run as ONE kernel (conv_fused.cu); -1: no fused pair
+    int pair_first = -1;
+    int* d_counter = nullptr;      // device word for the fused kernel's last-CTA check
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     long long halo_cap = 0;
@@ -131,6 +135,7 @@ static void out_dims(const DlwpPlan* pl, const DlwpOpDesc& op, int& C, int& H, i
         case DLWP_OP_PAD: H += op.pad_t + op.pad_b; W += op.pad_l + op.pad_r; break;
         case DLWP_OP_MAXPOOL: H /= 2; W /= 2; break;
         case DLWP_OP_UPSAMPLE: H *= 2; W *= 2; break;
+        case DLWP_OP_LSTM: C = op.Cout; break;
         default: break;
     }
 }
@@ -199,6 +204,30 @@ static int tc_setup(DlwpPlan* pl) {
             return 0;
         }
     }
+    // conv -> conv fusion: op i's output is an internal buffer that only op i + 1 reads (whole), op i is the only reader
+    // of its own source, and the pair matches an instantiated fused kernel
+    if (pl->opt.fuse == 1)
+        for (int i = 0; i + 1 < nops && pl->pair_first < 0; ++i) {
+            const DlwpOpDesc& a = pl->ops[i];
+            const DlwpOpDesc& b = pl->ops[i + 1];
+            if (a.kind != DLWP_OP_CONV || b.kind != DLWP_OP_CONV || b.src != a.dst) continue;
+            const Buffer& mid = pl->buffers[a.dst];
+            if (mid.d.kind != DLWP_BUF_INTERNAL || a.dst_c0 != 0 || a.Cout != mid.d.C || b.src_c0 != 0 || b.src_c != mid.d.C) continue;
+            if (a.src_c0 != 0 || a.src_c != pl->buffers[a.src].d.C) continue;
+            int mid_readers = 0, src_readers = 0, mid_writers = 0;
+            for (const DlwpOpDesc& o : pl->ops) {
+                mid_readers += o.src == a.dst;
+                src_readers += o.src == a.src;
+                mid_writers += o.dst == a.dst;
+            }
+            if (mid_readers != 1 || src_readers != 1 || mid_writers != 1) continue;
+            DlwpConvDesc d1 = conv_desc_of(pl, a, pl->max_batch), d2 = conv_desc_of(pl, b, pl->max_batch);
+            if (!tc_pair_ok(d1, layers[i], d2, layers[i + 1])) continue;
+            pl->pair_first = i;
+            layers[i].rowpitch = tc_pair_state_pitch(d1);       // the staged state row is 128 + halo1 pixels
+            wpad[a.src] = layers[i].wpad + layers[i + 1].wpad;  // the state image carries both layers' halo columns
+            is_src[a.dst] = 0;                                  // the intermediate never exists in HBM
+        }
     for (int b = 0; b < nbuf; ++b)
         if (is_src[b]) {
             Buffer& B = pl->buffers[b];
@@ -256,9 +285,11 @@ static int tc_setup(DlwpPlan* pl) {
             if (cudaMalloc(&b.P, bytes) != cudaSuccess) return DLWP_ENOMEM;
             cudaMemset(b.P, 0, bytes);
         }
-    if (cudaMalloc(&pl->d_exp, sizeof(int) * nbuf) != cudaSuccess) return DLWP_ENOMEM;
+    if (cudaMalloc(&pl->d_counter, sizeof(int)) != cudaSuccess) return DLWP_ENOMEM;
+    cudaMemset(pl->d_counter, 0, sizeof(int));
+    if (cudaMalloc(&pl->d_exp, sizeof(int) * 2 * nbuf) != cudaSuccess) return DLWP_ENOMEM;
     if (cudaMalloc(&pl->d_amax, sizeof(float) * 2 * nbuf) != cudaSuccess) return DLWP_ENOMEM;
-    cudaMemset(pl->d_exp, 0, sizeof(int) * nbuf);
+    cudaMemset(pl->d_exp, 0, sizeof(int) * 2 * nbuf);
     cudaMemset(pl->d_amax, 0, sizeof(float) * 2 * nbuf);
     pl->tc_layers = layers;
     pl->tc = true;
@@ -293,13 +324,13 @@ static TcScale scale_of(const DlwpPlan* pl, int i, int t) {
     sc.e_in_const = TC_EXP_STATIC;
     sc.amax_chk = pl->d_amax + 2 * op.src + (t & 1);
     if (!s.e_static) {  // a static (tanh) source bounds the output with |x| <= 1: exponents independent of the data
-        sc.e_in = pl->d_exp + op.src;
+        sc.e_in = pl->d_exp + 2 * op.src + (t & 1);
         sc.amax_in = sc.amax_chk;
     }
     const int pd = pl->tc_pdst[i];
     if (pd >= 0) {
         const int prod = pd == pl->input_buf ? t + 1 : t;
-        if (!pl->buffers[pd].e_static) sc.e_out = pl->d_exp + pd;
+        if (!pl->buffers[pd].e_static) sc.e_out = pl->d_exp + 2 * pd + (prod & 1);
         sc.amax_out = pl->d_amax + 2 * pd + (prod & 1);
         sc.amax_zero = pl->d_amax + 2 * pd + ((prod + 1) & 1);
     }
@@ -310,7 +341,43 @@ static TcScale scale_of(const DlwpPlan* pl, int i, int t) {
     return sc;
 }
 
+// ops pair_first, pair_first + 1 as one kernel
+static int run_pair_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool feedback_write) {
+    const int i = pl->pair_first;
+    const DlwpOpDesc& a = pl->ops[i];
+    const DlwpOpDesc& b = pl->ops[i + 1];
+    const Buffer& s = pl->buffers[a.src];
+    const Buffer& out = pl->buffers[b.dst];
+    const Weight& w1 = pl->weights[a.weight_id];
+    const Weight& w2 = pl->weights[b.weight_id];
+    DLWP_REQUIRE(w1.set && w1.bimg && w2.set && w2.bimg, DLWP_ESTATE, "weights of the fused pair were never set");
+    int pd = pl->tc_pdst[i + 1];
+    if (pd == pl->input_buf && i + 1 == pl->tc_feedback_op && !feedback_write) pd = -1;
+    TcScale sc1 = scale_of(pl, i, t), sc2 = scale_of(pl, i + 1, t);
+    sc1.e_out = nullptr;                                   // tanh intermediate: static exponent
+    sc1.amax_out = pl->d_amax + 2 * a.dst + (t & 1);       // measured for the underflow check the last CTA makes
+    sc1.amax_zero = pl->d_amax + 2 * a.dst + ((t + 1) & 1);
+    sc2.amax_chk = nullptr;
+    if (pd < 0) { sc2.e_out = nullptr; sc2.amax_out = nullptr; sc2.amax_zero = nullptr; }
+    DlwpConvDesc d1 = conv_desc_of(pl, a, N), d2 = conv_desc_of(pl, b, N);
+    float* y32 = (out.d.kind == DLWP_BUF_OUTPUT) ? out.ptr + (long long)b.dst_c0 * out.d.H * out.d.W : nullptr;
+    __half* yp = nullptr;
+    int wpad_out = 0, planes_out = 0, out_plane0 = 0;
+    if (pd >= 0) {
+        const Buffer& pb = pl->buffers[pd];
+        yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
+        out_plane0 = pd == b.dst ? 2 * (b.dst_c0 / 8) : 0;
+    }
+    return tc_pair_launch(d1, pl->tc_layers[i], w1.kst, w1.bimg, w1.has_bias ? w1.b : nullptr, d2, pl->tc_layers[i + 1],
+                          w2.kst, w2.bimg, w2.has_bias ? w2.b : nullptr, s.P, s.planes, 2 * (a.src_c0 / 8), y32, yp,
+                          wpad_out, planes_out, out_plane0, sc1, sc2, pl->d_counter, stream, pl->tc_opt);
+}
+
 static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bool feedback_write) {
+    if (pl->pair_first >= 0) {
+        if (i == pl->pair_first) return 0;                 // runs with its partner
+        if (i == pl->pair_first + 1) return run_pair_tc(pl, N, stream, t, feedback_write);
+    }
     const DlwpOpDesc& op = pl->ops[i];
     const Buffer& s = pl->buffers[op.src];
     const Buffer& b = pl->buffers[op.dst];
@@ -349,7 +416,7 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool inpu
     Buffer& in = pl->buffers[pl->input_buf];
     pl->tc_last_t = t;
     TcPackScale ps;
-    ps.e = pl->d_exp + pl->input_buf;
+    ps.e = pl->d_exp + 2 * pl->input_buf + (t & 1);
     ps.amax = pl->d_amax + 2 * pl->input_buf + (t & 1);
     if (!input_is_packed) {
         ps.fresh = 1;
@@ -414,6 +481,15 @@ static int run_one(DlwpPlan* pl, size_t i, int N, cudaStream_t stream) {
                                   op.pad_mode_h, op.pad_mode_w, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, op.row_begin,
                                   op.row_end, stream);
                 break;
+            case DLWP_OP_LSTM: {
+                const Buffer& cbuf = pl->buffers[op.aux];
+                float* c = cbuf.ptr + op.aux_c0 * t_hw;
+                const bool first = op.src_c == 4 * op.Cout;   // h_-1 = 0, c_-1 = 0: no recurrent half
+                rc = dlwp_convlstm_gates(x, first ? nullptr : x + 4LL * op.Cout * s_hw, first ? nullptr : c, c, y, N,
+                                         op.Cout, t.d.H, t.d.W, xs_n, xs_n, cbuf.sample_elems(), ys_n, op.act, op.act2,
+                                         op.row_begin, op.row_end, stream);
+                break;
+            }
             default: DLWP_REQUIRE(false, DLWP_EINVAL, "op %zu: unknown kind %d", i, op.kind);
         }
         return rc;
@@ -541,6 +617,11 @@ extern "C" int dlwp_plan_create_opts(const DlwpNetDesc* net, const DlwpPlanOptio
             ok = H == t.d.H && W == t.d.W && op.dst_c0 + C <= t.d.C;
         }
         if (ok && op.kind == DLWP_OP_CONV) ok = op.weight_id >= 0 && op.weight_id < net->n_weights;
+        if (ok && op.kind == DLWP_OP_LSTM)
+            ok = op.Cout > 0 && (op.src_c == 4 * op.Cout || op.src_c == 8 * op.Cout) && op.aux >= 0 &&
+                 op.aux < net->n_buffers && op.aux_c0 >= 0 && op.aux_c0 + op.Cout <= pl->buffers[op.aux].d.C &&
+                 pl->buffers[op.aux].d.H == H && pl->buffers[op.aux].d.W == W &&
+                 pl->buffers[op.aux].d.kind == DLWP_BUF_INTERNAL;
         if (!ok) {
             delete pl;
             DLWP_REQUIRE(false, DLWP_ESHAPE, "op %d is inconsistent with its buffers (computed out dims %d,%d,%d)", i,
@@ -599,6 +680,7 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
     for (Buffer& b : pl->buffers)
         if (b.P) cudaFree(b.P);
+    if (pl->d_counter) cudaFree(pl->d_counter);
     if (pl->d_exp) cudaFree(pl->d_exp);
     if (pl->d_amax) cudaFree(pl->d_amax);
     for (Weight& w : pl->weights) {
@@ -780,6 +862,7 @@ extern "C" int dlwp_plan_profile_op(DlwpPlan* pl, int32_t N, int32_t op_index, i
 }
 
 extern "C" int dlwp_plan_uses_tensor_cores(DlwpPlan* pl) { return pl && pl->tc ? 1 : 0; }
+extern "C" int dlwp_plan_fused_pair(DlwpPlan* pl) { return pl && pl->tc ? pl->pair_first : -1; }
 
 // =================================================================================================================
 // Latitude-band rollout with the halo exchange inside the library (NCCL resolved at run time, no link dependency)
@@ -953,6 +1036,7 @@ static int train_setup(DlwpPlan* pl) {
     DLWP_REQUIRE(!pl->tc, DLWP_ESTATE, "training needs the fp32 plan (create it with DlwpPlanOptions.math = 1)");
     for (const DlwpOpDesc& op : pl->ops) {
         DLWP_REQUIRE(op.kind != DLWP_OP_PAD, DLWP_ESHAPE, "stand-alone padding layers are not differentiable here yet");
+        DLWP_REQUIRE(op.kind != DLWP_OP_LSTM, DLWP_ESHAPE, "ConvLSTM2D is inference-only here (no backward kernels yet)");
         DLWP_REQUIRE(!(op.kind == DLWP_OP_CONV && (op.rowwise || op.pre_op)), DLWP_ESHAPE,
                      "RowConnected2D / fused pre-ops are not differentiable here yet");
         DLWP_REQUIRE(!op.row_begin && !op.row_end, DLWP_ESHAPE, "row-windowed plans cannot be trained");

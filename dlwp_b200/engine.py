@@ -63,7 +63,7 @@ class Lowering(object):
     def _op(self, kind, src, dst_buf, dst_c0=0, **kw):
         op = dict(kind=kind, src=src.buf, src_c0=src.c0, src_c=src.C, dst=dst_buf, dst_c0=dst_c0, weight_id=-1,
                   pad_t=0, pad_b=0, pad_l=0, pad_r=0, pad_mode_h=0, pad_mode_w=0, Cout=0, kh=0, kw=0, dil_h=1,
-                  dil_w=1, act=0, pre_op=0, rowwise=0, impl=0, row_begin=0, row_end=0)
+                  dil_w=1, act=0, pre_op=0, rowwise=0, impl=0, row_begin=0, row_end=0, aux=-1, aux_c0=0, act2=0)
         op.update(kw)
         self.ops.append(op)
         return op
@@ -503,6 +503,10 @@ class CompiledNet(object):
 
     def uses_tensor_cores(self):
         return bool(self.lib.dlwp_plan_uses_tensor_cores(self.plan))
+
+    def fused_pair(self):
+        """Index of the first op of the conv -> conv pair that runs as one kernel (csrc/conv_fused.cu), or -1."""
+        return int(self.lib.dlwp_plan_fused_pair(self.plan))
 
     def profile_op(self, n, op_index, iters=20):
         """Average device time (ms) of one op of the plan launched alone (CUDA events); run a forward/rollout first."""

@@ -69,7 +69,10 @@ class ZeroPadding2D(Layer):
 
 
 class ZeroPadding3D(Layer):
-    """Name-compatibility only (recurrent front block): importable, not lowerable yet."""
+    """keras ZeroPadding3D on (batch, depth, dim1, dim2, dim3) (channels_first) / (batch, dim1, dim2, dim3, depth).  The
+    recurrent example nets feed it (batch, time, channels, lat, lon) tensors declared channels_first
+    (examples/train.py:144-149), i.e. 'depth' is the time axis and dim1 the channel axis; the engine lowers the case
+    that pads only the two trailing (lat, lon) axes -- a 2-D padding of every (time, channel) plane."""
     pad_mode = 'zero'
 
     def __init__(self, padding=(1, 1, 1), data_format=None, **kwargs):
@@ -88,6 +91,11 @@ class ZeroPadding3D(Layer):
         for a, (p0, p1) in zip(axes, self.padding):
             out[a] = None if s[a] is None else s[a] + p0 + p1
         return tuple(out)
+
+    def get_config(self):
+        c = super(ZeroPadding3D, self).get_config()
+        c.update({'padding': self.padding, 'data_format': self.data_format})
+        return c
 
 
 class Conv2D(Layer):
@@ -300,15 +308,149 @@ def concatenate(inputs, axis=-1, **kwargs):
 
 class _NotOnHotPath(Layer):
     """Importable so that `from keras.layers import ...` lines of the example scripts work
-    (examples/train_functional.py:21-22); building one raises -- recurrent front block is SURVEY.md 8f rank 1."""
+    (examples/train_functional.py:21-22); building one raises -- dense / locally connected nets are not on the hot path."""
 
     def __init__(self, *args, **kwargs):
         raise NotImplementedError('%s is not part of the convolutional rollout hot path implemented by dlwp_b200 '
                                   '(SURVEY.md section 8f)' % self.__class__.__name__)
 
 
-class ConvLSTM2D(_NotOnHotPath):
-    pass
+class _LstmPart(object):
+    """One of ConvLSTM2D's two convolutions as the engine's weight table sees it (a Conv2D-like weight owner)."""
+
+    def __init__(self, layer, recurrent):
+        self.layer, self.recurrent = layer, recurrent
+        self.name = layer.name + ('/recurrent_kernel' if recurrent else '/kernel')
+
+    @property
+    def _weights(self):
+        w = self.layer._weights
+        return [w[1]] if self.recurrent else [w[0]] + ([w[2]] if self.layer.use_bias else [])
+
+    @property
+    def use_bias(self):
+        return self.layer.use_bias and not self.recurrent
+
+    @property
+    def _weights_version(self):
+        return self.layer._weights_version
+
+    @property
+    def kernel_regularizer(self):
+        return self.layer.recurrent_regularizer if self.recurrent else self.layer.kernel_regularizer
+
+    @property
+    def bias_regularizer(self):
+        return None if self.recurrent else self.layer.bias_regularizer
+
+
+class ConvLSTM2D(Layer):
+    """keras.layers.ConvLSTM2D (Keras 2.2 signature) as the recurrent front block of the example nets uses it
+    (examples/train.py:144-157, examples/train_functional.py:155-166): input (batch, time, channels, rows, cols) for
+    channels_first.  Weights in Keras order and layout: kernel (kh, kw, Cin, 4F), recurrent_kernel (kh, kw, F, 4F), bias
+    (4F,), gate blocks i, f, c, o; `unit_forget_bias` initialises the f block of the bias with ones.  The input convolution
+    uses the layer's padding / dilation, the recurrent one is always 'same', undilated (keras ConvLSTM2DCell)."""
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', data_format=None, dilation_rate=(1, 1),
+                 activation='tanh', recurrent_activation='hard_sigmoid', use_bias=True,
+                 kernel_initializer='glorot_uniform', recurrent_initializer='orthogonal', bias_initializer='zeros',
+                 unit_forget_bias=True, kernel_regularizer=None, recurrent_regularizer=None, bias_regularizer=None,
+                 activity_regularizer=None, kernel_constraint=None, recurrent_constraint=None, bias_constraint=None,
+                 return_sequences=False, go_backwards=False, stateful=False, dropout=0., recurrent_dropout=0., **kwargs):
+        super(ConvLSTM2D, self).__init__(**kwargs)
+        self.filters = int(filters)
+        self.kernel_size = _norm_tuple(kernel_size, 2, 'kernel_size')
+        self.strides = _norm_tuple(strides, 2, 'strides')
+        self.padding = str(padding).lower()
+        if self.padding not in ('valid', 'same'):
+            raise ValueError('The `padding` argument must be one of "valid", "same". Received: ' + str(padding))
+        self.data_format = _norm_data_format(data_format)
+        self.dilation_rate = _norm_tuple(dilation_rate, 2, 'dilation_rate')
+        for a in (activation, recurrent_activation):
+            if a is not None and not isinstance(a, str):
+                raise ValueError('dlwp_b200 ConvLSTM2D takes activation names, got %r' % (a,))
+        self.activation = activation
+        self.recurrent_activation = recurrent_activation
+        self.use_bias = bool(use_bias)
+        self.unit_forget_bias = bool(unit_forget_bias)
+        self.kernel_regularizer = kernel_regularizer
+        self.recurrent_regularizer = recurrent_regularizer
+        self.bias_regularizer = bias_regularizer
+        self.return_sequences = bool(return_sequences)
+        self.go_backwards = bool(go_backwards)
+        self.stateful = bool(stateful)
+        self.dropout, self.recurrent_dropout = float(dropout), float(recurrent_dropout)
+        self._parts = (_LstmPart(self, False), _LstmPart(self, True))
+
+    def _axes(self):   # (channel, rows, cols) of the 5-D input
+        return (2, 3, 4) if self.data_format == 'channels_first' else (4, 2, 3)
+
+    def build(self, s):
+        if len(s) != 5:
+            raise ValueError('Input 0 is incompatible with layer %s: expected ndim=5, found ndim=%d' % (self.name, len(s)))
+        cin = s[self._axes()[0]]
+        if cin is None:
+            raise ValueError('The channel dimension of the inputs should be defined. Found `None`.')
+        kh, kw = self.kernel_size
+        F = self.filters
+        rng = np.random.RandomState(np.random.randint(0, 2 ** 31 - 1))
+        kernel = _glorot_uniform(rng, (kh, kw, cin, 4 * F), kh * kw * cin, kh * kw * 4 * F)
+        # keras' default recurrent initializer is 'orthogonal': Q of a QR of a normal (kh*kw*F, 4F) matrix
+        a = rng.standard_normal((kh * kw * F, 4 * F))
+        q, r = np.linalg.qr(a if a.shape[0] >= a.shape[1] else a.T)
+        q = q * np.sign(np.diag(r))
+        rec = (q if a.shape[0] >= a.shape[1] else q.T).reshape(kh, kw, F, 4 * F).astype(np.float32)
+        self._weights = [kernel, rec]
+        if self.use_bias:
+            b = np.zeros((4 * F,), np.float32)
+            if self.unit_forget_bias:
+                b[F:2 * F] = 1.0
+            self._weights.append(b)
+        self.built = True
+
+    def compute_output_shape(self, s):
+        ca, ha, wa = self._axes()
+
+        def out_len(n, k, d, st):
+            if n is None:
+                return None
+            return (n + st - 1) // st if self.padding == 'same' else (n - d * (k - 1) - 1) // st + 1
+        rows = out_len(s[ha], self.kernel_size[0], self.dilation_rate[0], self.strides[0])
+        cols = out_len(s[wa], self.kernel_size[1], self.dilation_rate[1], self.strides[1])
+        for v in (rows, cols):
+            if v is not None and v <= 0:
+                raise ValueError('Negative dimension size caused by the convolution of layer %s: input %s' %
+                                 (self.name, s))
+        if self.data_format == 'channels_first':
+            tail = (self.filters, rows, cols)
+        else:
+            tail = (rows, cols, self.filters)
+        return (s[0], s[1]) + tail if self.return_sequences else (s[0],) + tail
+
+    @property
+    def kernel(self):
+        return self._weights[0]
+
+    @property
+    def recurrent_kernel(self):
+        return self._weights[1]
+
+    @property
+    def bias(self):
+        return self._weights[2] if self.use_bias else None
+
+    def __getstate__(self):
+        return self.__dict__.copy()
+
+    def get_config(self):
+        c = super(ConvLSTM2D, self).get_config()
+        c.update({'filters': self.filters, 'kernel_size': self.kernel_size, 'strides': self.strides,
+                  'padding': self.padding, 'data_format': self.data_format, 'dilation_rate': self.dilation_rate,
+                  'activation': self.activation, 'recurrent_activation': self.recurrent_activation,
+                  'use_bias': self.use_bias, 'unit_forget_bias': self.unit_forget_bias,
+                  'return_sequences': self.return_sequences, 'go_backwards': self.go_backwards,
+                  'stateful': self.stateful, 'dropout': self.dropout, 'recurrent_dropout': self.recurrent_dropout})
+        return c
 
 
 class LocallyConnected2D(_NotOnHotPath):

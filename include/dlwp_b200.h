@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DLWP_B200_ABI_VERSION 2
+#define DLWP_B200_ABI_VERSION 3
 
 typedef void* dlwp_stream_t; /* cudaStream_t */
 
@@ -104,10 +104,22 @@ int dlwp_upsample2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, i
 int dlwp_copy4d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
                 int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);
 
+/* One time step of keras ConvLSTM2D's cell after its two convolutions (keras ConvLSTM2DCell.call; the layer is built at
+ * examples/train.py:144-157):  i = s(zi + ri), f = s(zf + rf), c = f * c_prev + i * act(zc + rc), o = s(zo + ro),
+ * h = o * act(c), with s = hard_sigmoid (clip(0.2 x + 0.5, 0, 1)) or sigmoid.  z: (N, 4F, H, W) input-conv
+ * pre-activations (bias included), gate blocks in keras order i, f, c, o; r: the recurrent conv's, or NULL (first step:
+ * h_-1 = 0 and c_prev is not read, may be NULL).  c_out may alias c_prev.  Strides in elements; rows [row_begin, row_end)
+ * only (0,0 = all). */
+int dlwp_convlstm_gates(const float* z, const float* r, const float* c_prev, float* c_out, float* h_out, int32_t N,
+                        int32_t F, int32_t H, int32_t W, int64_t zs_n, int64_t rs_n, int64_t cs_n, int64_t hs_n,
+                        int32_t act, int32_t ract, int32_t row_begin, int32_t row_end, dlwp_stream_t stream);
+
 /* ---- the network plan: what keras.Model.predict executes for one model application ------------------------------ */
 
 enum { DLWP_BUF_INTERNAL = 0, DLWP_BUF_INPUT = 1, DLWP_BUF_OUTPUT = 2 };
-enum { DLWP_OP_CONV = 0, DLWP_OP_PAD = 1, DLWP_OP_MAXPOOL = 2, DLWP_OP_UPSAMPLE = 3, DLWP_OP_COPY = 4 };
+enum { DLWP_OP_CONV = 0, DLWP_OP_PAD = 1, DLWP_OP_MAXPOOL = 2, DLWP_OP_UPSAMPLE = 3, DLWP_OP_COPY = 4,
+       DLWP_OP_LSTM = 5 /* ConvLSTM2D gate step: see dlwp_convlstm_gates */ };
+enum { DLWP_RACT_HARD_SIGMOID = 0, DLWP_RACT_SIGMOID = 1 };   /* keras recurrent_activation */
 
 /* A dense (N, C, H, W) activation. INTERNAL buffers are allocated by the plan; the INPUT buffer and the OUTPUT buffers
  * are bound to caller memory at run time (dense, contiguous). `output_index` orders the model outputs. */
@@ -130,6 +142,11 @@ typedef struct DlwpOpDesc {
     int32_t pad_t, pad_b, pad_l, pad_r, pad_mode_h, pad_mode_w;   /* conv and pad */
     int32_t Cout, kh, kw, dil_h, dil_w, act, pre_op, rowwise, impl; /* conv only */
     int32_t row_begin, row_end;    /* destination rows this plan computes ([0,0) = all): latitude-band partitioning */
+    /* DLWP_OP_LSTM: src = pre-activations, channels [i | f | c | o] (4*Cout) of the input conv (bias included), followed
+     * by the same four blocks of the recurrent conv when src_c == 8*Cout (absent on the first time step: h_-1 = 0);
+     * aux / aux_c0 = the cell-state buffer (Cout channels, updated in place; ignored as an input when src_c == 4*Cout);
+     * dst / dst_c0 = where h_t goes; act = cell activation, act2 = DLWP_RACT_* */
+    int32_t aux, aux_c0, act2;
 } DlwpOpDesc;
 
 typedef struct DlwpNetDesc {
@@ -147,13 +164,15 @@ typedef struct DlwpPlan DlwpPlan;
 typedef struct DlwpPlanOptions {
     int32_t math;          /* 0: tensor-core chain when the whole plan is eligible, else fp32 kernels; 1: fp32 FFMA kernels
                               (training needs them: fp32 intermediates)                                                  */
-    int32_t fuse;          /* 0: fuse eligible conv -> conv pairs into one kernel (the intermediate never leaves the SM);
-                              1: one kernel per layer                                                                    */
+    int32_t fuse;          /* 0: one kernel per layer; 1: eligible conv -> conv pairs run as one kernel (conv_fused.cu; the
+                              intermediate never leaves the SM).  Opt-in: measured slower than the two-kernel chain      */
     int32_t tc_generic;    /* 1: only the generic tensor-core kernel instances (A/B against the folded ones)             */
-    int32_t tc_bands;      /* latitude bands per strip of the sliding-window kernel; 0 = chosen per launch               */
+    int32_t tc_bands;      /* sliding-window kernel: fewest output rows a CTA is started for (0 = default 8); the fused
+                              pair kernel: latitude bands per strip (0 = chosen per launch)                               */
     int32_t tc_no_tma;     /* 1: per-plane bulk copies instead of tensor-map row loads                                   */
     int32_t tc_taps_in_k;  /* -1: planner's choice; 0 / 1: horizontal taps in the MMA N / K dimension                     */
-    int32_t tc_debug;      /* bottleneck triage (WRONG RESULTS): 1 = epilogue only waits/arrives, 2 = issuer only commits */
+    int32_t tc_debug;      /* bottleneck triage: 1 = epilogue only waits/arrives, 2 = issuer only commits (both: WRONG
+                              RESULTS); 4 = the issuing warp times itself (dlwp_debug_counters)                         */
     int32_t reserved[9];
 } DlwpPlanOptions;
 
@@ -247,6 +266,10 @@ int dlwp_plan_profile_op(DlwpPlan* plan, int32_t N, int32_t op_index, int32_t it
 /* 1 if the plan runs as a tcgen05 tensor-core chain (DlwpPlanOptions.math = 0 and every op eligible). */
 int dlwp_plan_uses_tensor_cores(DlwpPlan* plan);
 
+/* Index of the first op of the conv -> conv pair that runs as one fused kernel (its partner is the next op), or -1.
+ * dlwp_plan_profile_op reports 0 ms for that op and the fused kernel's time for the partner. */
+int dlwp_plan_fused_pair(DlwpPlan* plan);
+
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 
 const char* dlwp_last_error_string(void);
@@ -270,7 +293,8 @@ const char* dlwp_conv2d_impl_name(const DlwpConvDesc* desc);
 int dlwp_debug_tc_plan(const DlwpConvDesc* desc, int32_t* out, int32_t n_out);
 /* dlwp_debug_sw_cover: walks the sliding-window kernel's scheduling units for this layer on `sms` SMs exactly as the
  *   device roles do and counts, per output pixel (N,H,W), how many units write it (must be 1 inside [row_begin,row_end),
- *   0 outside).  info[0..3] = units, non-empty units, latitude bands per strip, staged input rows over all units. */
+ *   0 outside).  info[0..3] = CTAs, segments (strip x row range) over all CTAs, staged input rows of the busiest CTA,
+ *   staged input rows over all CTAs. */
 int dlwp_debug_sw_cover(const DlwpConvDesc* desc, int32_t sms, int32_t* cover, int64_t cover_elems, int32_t* info,
                         int32_t n_info);
 int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16_t* image, int64_t image_cap,
@@ -278,6 +302,12 @@ int64_t dlwp_debug_tc_pack(const DlwpConvDesc* desc, const float* kernel, uint16
 /* Description of the fully folded tensor-core kernel instance this layer launches when it writes a P image (out_mode 1),
  * fp32 (2) or both (3); NULL = generic instance (profiles/r02_folded_vs_generic.txt compares the two). */
 const char* dlwp_debug_tc_folded(const DlwpConvDesc* desc, int32_t out_mode);
+/* Plans created with tc_debug & 4 make the MMA-issuing warp time itself (clock64): totals since the last call, summed over
+ * CTAs and launches: out[0] cycles waiting for accumulator slots, [1] waiting for staged rows, [2] issuing MMAs,
+ * [3] rows issued; out[4..7] the same for the second layer of a fused pair; n >= 12 adds [8] clocks from kernel entry to
+ * the issuing warp's exit, [9] that span in ns (globaltimer), [10] CTAs counted, [11] clocks until the first staged row
+ * arrived.  Synchronises the device. */
+int dlwp_debug_counters(int64_t* out, int32_t n);
 /* The power-of-two exponent e the tensor-core path gives an image whose values are bounded by `bound`:
  * bound * 2^e in [2^13, 2^14) (conv_tc.h). */
 int dlwp_debug_exp_for_bound(float bound);

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/c_pytest.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/c_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/c_pytest.log
-grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/c_pytest.log | tail -15
+grep -E "^(FAILED|ERROR)|passed|failed|exit" gpurun_out/c_pytest.log | tail -15
 timeout 300 python bench.py --steps 50 --warmup 3 --no-cpu > gpurun_out/c_bench50.log 2>&1
 python - <<'PY'
 import json

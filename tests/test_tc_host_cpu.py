@@ -159,13 +159,15 @@ def test_sliding_window_units_cover_every_output_pixel_once(nat, case):
     lo, hi = (0, H) if (r0, r1) == (0, 0) else (r0, r1)
     assert (cover[:, lo:hi] == 1).all()
     assert not cover[:, :lo].any() and not cover[:, hi:].any()
-    units, live, nbands, staged = list(info)
-    assert 1 <= nbands <= 16 and live <= units
+    ctas, segments, worst, staged = list(info)
     _, L = _plan(nat, desc)
-    strips = L['nfull'] + (1 if L['rem'] else 0)
-    strip_units = (N // 2 + N % 2) * (2 * L['nfull'] + 1) if L['pair'] else N * strips
-    assert units == strip_units * nbands
-    assert staged == live // nbands * (hi - lo) + live * d * (k - 1)
+    rem_strips = 0 if not L['rem'] else ((N + 1) // 2 if L['pair'] else N)
+    strips = N * L['nfull'] + rem_strips
+    assert 1 <= ctas <= sms and strips <= segments <= strips + ctas
+    assert staged == strips * (hi - lo) + segments * d * (k - 1)
+    # contiguous ranges of equal length: the busiest CTA stays within a few warm-up segments of the mean
+    per_cta = -(-strips * (hi - lo) // ctas)
+    assert worst <= per_cta + (per_cta // (hi - lo) + 2) * d * (k - 1)
 
 
 def _split16(x):
