@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libdlwp_b200.so')
 
 DLWP_OK = 0
 ABI_VERSION = 3
-PAD_ZERO, PAD_PERIODIC = 0, 1
+PAD_ZERO, PAD_PERIODIC, PAD_EDGE, PAD_REFLECT, PAD_SYMMETRIC = 0, 1, 2, 3, 4
 ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
 IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
 BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2

@@ -30,7 +30,8 @@ namespace dlwp {
 __device__ int DLWP_SW_TU_FLAGS = 0;
 // TcOptions::debug & 4: clock64 totals of the MMA-issuing warp, summed over CTAs:
 // [0] waiting for an accumulator slot, [1] waiting for a staged row, [2] issuing MMAs + commits, [3] rows; [4..7] the same
-// for the second layer of the fused kernel; [8] issuing warp's clocks from kernel entry to its last commit, [9] the same
+// for the second layer of the fused kernel -- in conv_sw_kernel: [4] issuer waiting for the phantom rows' slots at segment
+// starts, [5] issuer between segments, [6] / [7] epilogue warp 0 waiting for / working on rows; [8] issuing warp's clocks from kernel entry to its last commit, [9] the same
 // span in globaltimer ns, [10] CTAs counted, [11] clocks from kernel entry to the first staged row's arrival
 __device__ unsigned long long DLWP_SW_TU_COUNTERS[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }
@@ -573,11 +574,18 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         if (timing) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(k_g0));
         SwIter it;
         sw_range(p, blockIdx.x, gridDim.x, it);
+        long long t_ph = 0, t_unit = 0, c_prev = k_c0;
         while (sw_next(p, it, U)) {
             const int nrows = U.yb - U.ya + SPAN;
+            const long long cu0 = timing ? clock64() : 0;
             for (int k = 0; k < SPAN; ++k) {        // phantom rows above the band: take their slots
                 mbar_wait(&acc_empty[ring.slot(RING)], ring.lap ^ 1);
                 ring.advance(D, RING);
+            }
+            if (timing) {
+                const long long cu1 = clock64();
+                t_ph += cu1 - cu0;
+                t_unit += cu0 - c_prev;
             }
             for (int r = 0; r < nrows; ++r) {
                 const long long c0 = timing ? clock64() : 0;
@@ -647,8 +655,11 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 }
             }
             __syncwarp();
+            if (timing) c_prev = clock64();
         }
         if (timing && leader) {
+            atomicAdd(&g_tc_counters[4], (unsigned long long)t_ph);
+            atomicAdd(&g_tc_counters[5], (unsigned long long)t_unit);
             atomicAdd(&g_tc_counters[0], (unsigned long long)t_acc);
             atomicAdd(&g_tc_counters[1], (unsigned long long)t_full);
             atomicAdd(&g_tc_counters[2], (unsigned long long)t_issue);
@@ -672,6 +683,8 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
         const float inv = sscale[0], sout = sscale[1];
         float amax_t = 0.f;   // max |output| this thread produced (true units)
         int g = 0, lrow = 0;
+        const bool etiming = (p.debug & 4) != 0 && warp == 0;
+        long long e_wait = 0, e_busy = 0;
         SwUnit U;
         SwIter it;
         sw_range(p, blockIdx.x, gridDim.x, it);
@@ -693,8 +706,11 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
             for (int k = (set - g) & 3; k < nnum; k += TC_SETS) {
                 const int G = g + k;
                 const int slot = sw_slot(G, D, RING);
+                const long long ce0 = etiming ? clock64() : 0;
                 mbar_wait_relaxed(&acc_full[slot], (uint32_t)((G / NACC) & 1));
                 tc_fence_after();
+                const long long ce1 = etiming ? clock64() : 0;
+                e_wait += ce1 - ce0;
                 const int y = U.ya + k - SPAN;
                 if (y < U.ya || y >= U.yb || (p.debug & 1)) {   // phantom row: release the slot unread
                     tc_fence_before();
@@ -810,8 +826,13 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[slot]);
+                if (etiming) e_busy += clock64() - ce1;
             }
             g += nnum;
+        }
+        if (etiming && lane == 0) {
+            atomicAdd(&g_tc_counters[6], (unsigned long long)e_wait);
+            atomicAdd(&g_tc_counters[7], (unsigned long long)e_busy);
         }
         amax_publish(p.sc.amax_out, amax_t, lane);
     }

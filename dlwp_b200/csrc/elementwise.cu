@@ -19,6 +19,18 @@ struct EwParams {
 
 enum { EW_PAD = 0, EW_POOL = 1, EW_UP = 2, EW_COPY = 3 };
 
+// Source index of padded coordinate g (already shifted by the leading pad) on an axis of length n; ok = false: a zero.
+__device__ __forceinline__ int pad_source_index(int g, int n, int mode, bool& ok) {
+    if (g >= 0 && g < n) return g;
+    switch (mode) {
+        case DLWP_PAD_PERIODIC: return wrap_index(g, n);
+        case DLWP_PAD_EDGE: return g < 0 ? 0 : n - 1;
+        case DLWP_PAD_REFLECT: return g < 0 ? -g : 2 * (n - 1) - g;        // pad <= n - 1 (checked on the host)
+        case DLWP_PAD_SYMMETRIC: return g < 0 ? -g - 1 : 2 * n - 1 - g;    // pad <= n
+        default: ok = false; return 0;
+    }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(256) elementwise_kernel(const EwParams p) {
     const long long total = (long long)p.N * p.C * p.rows * p.Wo;
@@ -33,12 +45,9 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwParams p) {
         const float* xc = p.x + (long long)n * p.xs_n + (long long)c * p.xs_c;
         float v;
         if (OP == EW_PAD) {
-            int gy = yo - p.pad_t, gx = xo - p.pad_l;
             bool ok = true;
-            if (p.mode_h == DLWP_PAD_PERIODIC) gy = wrap_index(gy, p.H);
-            else ok = ok && gy >= 0 && gy < p.H;
-            if (p.mode_w == DLWP_PAD_PERIODIC) gx = wrap_index(gx, p.W);
-            else ok = ok && gx >= 0 && gx < p.W;
+            const int gy = pad_source_index(yo - p.pad_t, p.H, p.mode_h, ok);
+            const int gx = pad_source_index(xo - p.pad_l, p.W, p.mode_w, ok);
             v = ok ? xc[(long long)gy * p.xs_h + gx] : 0.f;
         } else if (OP == EW_POOL) {
             const float* q = xc + (long long)(2 * yo) * p.xs_h + 2 * xo;
@@ -118,6 +127,18 @@ __global__ void __launch_bounds__(256) convlstm_gate_kernel(const LstmParams p) 
 
 using namespace dlwp;
 
+static int check_pad_args(int H, int W, int pad_t, int pad_b, int pad_l, int pad_r, int mode_h, int mode_w) {
+    DLWP_REQUIRE(pad_t >= 0 && pad_b >= 0 && pad_l >= 0 && pad_r >= 0, DLWP_ESHAPE, "negative padding");
+    DLWP_REQUIRE(mode_h >= DLWP_PAD_ZERO && mode_h <= DLWP_PAD_SYMMETRIC && mode_w >= DLWP_PAD_ZERO &&
+                     mode_w <= DLWP_PAD_SYMMETRIC, DLWP_EINVAL, "bad pad mode");
+    const int lim_h = mode_h == DLWP_PAD_REFLECT ? H - 1 : H, lim_w = mode_w == DLWP_PAD_REFLECT ? W - 1 : W;
+    if (mode_h == DLWP_PAD_PERIODIC || mode_h == DLWP_PAD_REFLECT || mode_h == DLWP_PAD_SYMMETRIC)
+        DLWP_REQUIRE(pad_t <= lim_h && pad_b <= lim_h, DLWP_ESHAPE, "periodic / mirrored pad > axis");
+    if (mode_w == DLWP_PAD_PERIODIC || mode_w == DLWP_PAD_REFLECT || mode_w == DLWP_PAD_SYMMETRIC)
+        DLWP_REQUIRE(pad_l <= lim_w && pad_r <= lim_w, DLWP_ESHAPE, "periodic / mirrored pad > axis");
+    return 0;
+}
+
 extern "C" int dlwp_convlstm_gates(const float* z, const float* r, const float* c_prev, float* c_out, float* h_out,
                                    int32_t N, int32_t F, int32_t H, int32_t W, int64_t zs_n, int64_t rs_n, int64_t cs_n,
                                    int64_t hs_n, int32_t act, int32_t ract, int32_t row_begin, int32_t row_end,
@@ -141,12 +162,8 @@ extern "C" int dlwp_convlstm_gates(const float* z, const float* r, const float* 
 extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t,
                           int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n,
                           int64_t xs_c, int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream) {
-    DLWP_REQUIRE(pad_t >= 0 && pad_b >= 0 && pad_l >= 0 && pad_r >= 0, DLWP_ESHAPE, "negative padding");
-    DLWP_REQUIRE((mode_h == DLWP_PAD_ZERO || mode_h == DLWP_PAD_PERIODIC) &&
-                     (mode_w == DLWP_PAD_ZERO || mode_w == DLWP_PAD_PERIODIC),
-                 DLWP_EINVAL, "bad pad mode");
-    if (mode_h == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_t <= H && pad_b <= H, DLWP_ESHAPE, "periodic pad > axis");
-    if (mode_w == DLWP_PAD_PERIODIC) DLWP_REQUIRE(pad_l <= W && pad_r <= W, DLWP_ESHAPE, "periodic pad > axis");
+    int rc = check_pad_args(H, W, pad_t, pad_b, pad_l, pad_r, mode_h, mode_w);
+    if (rc) return rc;
     EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
                xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_PAD>(p, (cudaStream_t)stream, "pad2d");
@@ -180,7 +197,8 @@ extern "C" int dlwp_rows_op(int32_t op, const float* x, float* y, int32_t N, int
     cudaStream_t st = (cudaStream_t)stream;
     switch (op) {
         case DLWP_OP_PAD: {
-            DLWP_REQUIRE(pad_t >= 0 && pad_b >= 0 && pad_l >= 0 && pad_r >= 0, DLWP_ESHAPE, "negative padding");
+            int rc = check_pad_args(H, W, pad_t, pad_b, pad_l, pad_r, mode_h, mode_w);
+            if (rc) return rc;
             EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
                        xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
             return launch<EW_PAD>(p, st, "pad2d", row_begin, row_end);

@@ -30,7 +30,9 @@ class PeriodicPadding2D(ZeroPadding2D):
 
 
 class PeriodicPadding3D(ZeroPadding3D):
-    """DLWP/custom.py:217-306.  Name compatibility for the recurrent front block."""
+    """DLWP/custom.py:217-306: periodic padding of the three trailing axes of a 5-D input; on the recurrent nets'
+    (batch, time, channels, lat, lon) tensors `padding=(0, 0, p)` wraps longitude (examples/train.py:144-148).  Lowered
+    as a pending 2-D padding of every (time, channel) plane, fused into the ConvLSTM2D input convolution."""
     pad_mode = 'periodic'
 
     def __init__(self, padding=(1, 1, 1), data_format=None, **kwargs):
@@ -38,7 +40,8 @@ class PeriodicPadding3D(ZeroPadding3D):
 
 
 class FillPadding2D(ZeroPadding2D):
-    """DLWP/custom.py:309-402 (edge-replicating padding).  Name compatibility; not used by the example nets."""
+    """DLWP/custom.py:309-402: replicates the border rows, then the border columns of the row-padded tensor (corners =
+    corner value).  Runs as a stand-alone pad op (DLWP_PAD_EDGE); not used by the example nets."""
     pad_mode = 'fill'
 
 
@@ -47,13 +50,22 @@ class FillPadding3D(ZeroPadding3D):
 
 
 class TFPadding2D(ZeroPadding2D):
-    """DLWP/custom.py:527-599 (tf.pad modes).  Name compatibility; CONSTANT mode equals ZeroPadding2D."""
+    """DLWP/custom.py:527-599: tf.pad with mode CONSTANT (0 only: equals ZeroPadding2D), REFLECT or SYMMETRIC; the
+    mirrored modes run as stand-alone pad ops (DLWP_PAD_REFLECT / DLWP_PAD_SYMMETRIC)."""
 
     def __init__(self, padding=(1, 1), data_format=None, mode='CONSTANT', constant_values=0, **kwargs):
         super(TFPadding2D, self).__init__(padding=padding, data_format=data_format, **kwargs)
         self.mode = mode
         self.constant_values = constant_values
-        self.pad_mode = 'zero' if (mode.upper() == 'CONSTANT' and constant_values == 0) else mode.lower()
+        if mode.upper() == 'CONSTANT':
+            self.pad_mode = 'zero' if constant_values == 0 else 'constant(%r)' % (constant_values,)
+        else:
+            self.pad_mode = mode.lower()
+
+    def get_config(self):
+        c = super(TFPadding2D, self).get_config()
+        c.update({'mode': self.mode, 'constant_values': self.constant_values})
+        return c
 
 
 class TFPadding3D(ZeroPadding3D):

@@ -41,6 +41,10 @@ def _unsupported(layer, why):
                               (layer.name, layer.__class__.__name__, why))
 
 
+# FillPadding2D / TFPadding2D(REFLECT | SYMMETRIC) (DLWP/custom.py:309-402, 527-599): stand-alone pad ops, never fused
+_STANDALONE_PAD_MODES = {'fill': nat.PAD_EDGE, 'reflect': nat.PAD_REFLECT, 'symmetric': nat.PAD_SYMMETRIC}
+
+
 class Lowering(object):
     def __init__(self, model):
         self.model = model
@@ -74,7 +78,9 @@ class Lowering(object):
             return nat.PAD_ZERO
         if mode == 'periodic':
             return nat.PAD_PERIODIC
-        _unsupported(layer, 'padding mode %r has no kernel (only zero / periodic are on the hot path)' % mode)
+        if mode in _STANDALONE_PAD_MODES:
+            return _STANDALONE_PAD_MODES[mode]
+        _unsupported(layer, 'padding mode %r has no kernel' % mode)
 
     def _materialise_one_pad(self, v):
         """Apply the first pending padding with a stand-alone pad op."""
@@ -91,6 +97,16 @@ class Lowering(object):
             v = self._materialise_one_pad(v)
         return v
 
+    def _settle_pad(self, v, layer):
+        """Zero / periodic paddings stay pending (the next conv fuses them); the other modes become pad ops now."""
+        if layer.pad_mode in ('zero', 'periodic'):
+            return v
+        self._pad_mode(layer.pad_mode, layer)      # raises for modes without a kernel
+        shape = v.shape
+        v = self._materialise(v)
+        v.shape = shape
+        return v
+
     def _fusable_pads(self, v):
         """Reduce pending paddings until at most one layer pads each axis; return (v, (mode_h,t,b), (mode_w,l,r))."""
         while True:
@@ -104,6 +120,23 @@ class Lowering(object):
 
     # -- per-layer emitters --------------------------------------------------------------------------------------
     def _emit(self, layer, ins):
+        if isinstance(layer, KL.ZeroPadding3D):  # includes PeriodicPadding3D (DLWP/custom.py:217-306)
+            # (batch, time, channels, lat, lon) declared channels_first: padding axes are (channels, lat, lon)
+            # (examples/train.py:144-149).  Padding the two trailing axes is a 2-D padding of every (time, channel) plane.
+            v = ins[0]
+            if layer.data_format != 'channels_first' or len(v.shape) != 4:
+                _unsupported(layer, "only 5-D channels_first inputs (batch, time, channels, lat, lon) are lowered")
+            (c0, c1), (t, b), (l, r) = layer.padding
+            if (c0, c1) != (0, 0):
+                _unsupported(layer, 'padding of the first padded axis (the channel axis of a (time, channels, lat, lon) '
+                                    'input) is not on the hot path')
+            if layer.pad_mode == 'periodic' and (max(t, b) > v.shape[2] or max(l, r) > v.shape[3]):
+                raise ValueError('PeriodicPadding3D %s pads by more than the axis length' % layer.name)
+            pads = v.pads + ((layer.pad_mode, (t, b), (l, r), layer),)
+            out = _Val(v.buf, v.c0, v.C, v.H, v.W, pads, tuple(v.shape[:2]) + (v.shape[2] + t + b, v.shape[3] + l + r))
+            return self._settle_pad(out, layer)
+        if isinstance(layer, KL.ConvLSTM2D):
+            return self._emit_convlstm(layer, ins[0])
         if isinstance(layer, KL.ZeroPadding2D):  # includes PeriodicPadding2D & friends (pad_mode attribute)
             v = ins[0]
             if layer.data_format != 'channels_first':
@@ -113,8 +146,9 @@ class Lowering(object):
                                                  max(l, r) > v.W + sum(p[2][0] + p[2][1] for p in v.pads)):
                 raise ValueError('PeriodicPadding2D %s pads by more than the axis length' % layer.name)
             pads = v.pads + ((layer.pad_mode, (t, b), (l, r), layer),)
-            return _Val(v.buf, v.c0, v.C, v.H, v.W, pads, (v.C, v.H + sum(p[1][0] + p[1][1] for p in pads),
-                                                           v.W + sum(p[2][0] + p[2][1] for p in pads)))
+            out = _Val(v.buf, v.c0, v.C, v.H, v.W, pads, (v.C, v.H + sum(p[1][0] + p[1][1] for p in pads),
+                                                          v.W + sum(p[2][0] + p[2][1] for p in pads)))
+            return self._settle_pad(out, layer)
         if isinstance(layer, KL.Conv2D):  # includes RowConnected2D
             return self._emit_conv(layer, ins[0])
         if isinstance(layer, KL.MaxPooling2D):
@@ -165,6 +199,8 @@ class Lowering(object):
         _unsupported(layer, 'no kernel for this layer type')
 
     def _emit_conv(self, layer, v):
+        if len(v.shape) != 3:
+            _unsupported(layer, 'expects a 4-D (batch, channels, lat, lon) input, got per-sample shape %s' % (v.shape,))
         if layer.data_format != 'channels_first':
             _unsupported(layer, "only data_format='channels_first' is lowered (all DLWP examples use it)")
         if layer.strides != (1, 1):
@@ -190,15 +226,61 @@ class Lowering(object):
                  dil_w=dw, act=act or 0, rowwise=rowwise)
         return _Val(buf, 0, layer.filters, Ho, Wo)
 
+    def _emit_convlstm(self, layer, v):
+        """keras ConvLSTM2D on a (time, channels, lat, lon) value: per time step the input convolution (the layer's
+        padding / dilation, pending periodic / zero paddings fused), the recurrent convolution of h_{t-1} ('same', zero
+        padded, undilated -- keras ConvLSTM2DCell.recurrent_conv) and one gate op (dlwp_convlstm_gates).  h_t is written
+        straight into its slot of the (time * filters) output, which the next step's recurrent convolution reads."""
+        if layer.data_format != 'channels_first' or len(v.shape) != 4:
+            _unsupported(layer, 'only 5-D channels_first inputs (batch, time, channels, lat, lon) are lowered')
+        if layer.strides != (1, 1) or layer.go_backwards or layer.stateful:
+            _unsupported(layer, 'strides / go_backwards / stateful are not on the hot path')
+        act = nat.ACTIVATIONS.get(layer.activation)
+        ract = nat.RECURRENT_ACTIVATIONS.get(layer.recurrent_activation)
+        if act is None or ract is None:
+            _unsupported(layer, 'activation %r / recurrent_activation %r' % (layer.activation, layer.recurrent_activation))
+        T, C = v.shape[0], v.shape[1]
+        F = layer.filters
+        kh, kw = layer.kernel_size
+        dh, dw = layer.dilation_rate
+        if layer.padding == 'same':
+            th, tw = dh * (kh - 1), dw * (kw - 1)
+            v = _Val(v.buf, v.c0, v.C, v.H, v.W,
+                     v.pads + (('zero', (th // 2, th - th // 2), (tw // 2, tw - tw // 2), layer),), v.shape)
+        v, (mh, t, b), (mw, l, r) = self._fusable_pads(v)
+        Ho = v.H + t + b - dh * (kh - 1)
+        Wo = v.W + l + r - dw * (kw - 1)
+        if Ho <= 0 or Wo <= 0:
+            raise ValueError('Negative dimension size caused by the convolution of layer %s' % layer.name)
+        z = self._new_buffer(8 * F, Ho, Wo)       # [i f c o] of the input conv, [i f c o] of the recurrent conv
+        cst = self._new_buffer(F, Ho, Wo)         # cell state, updated in place
+        hseq = self._new_buffer(T * F, Ho, Wo)
+        w_in, w_rec = self._weight_id(layer._parts[0]), self._weight_id(layer._parts[1])
+        for ts in range(T):
+            self._op(nat.OP_CONV, _Val(v.buf, v.c0 + ts * C, C, v.H, v.W), z, dst_c0=0, weight_id=w_in, pad_t=t, pad_b=b,
+                     pad_l=l, pad_r=r, pad_mode_h=mh, pad_mode_w=mw, Cout=4 * F, kh=kh, kw=kw, dil_h=dh, dil_w=dw)
+            if ts > 0:
+                self._op(nat.OP_CONV, _Val(hseq, (ts - 1) * F, F, Ho, Wo), z, dst_c0=4 * F, weight_id=w_rec,
+                         pad_t=(kh - 1) // 2, pad_b=kh - 1 - (kh - 1) // 2, pad_l=(kw - 1) // 2,
+                         pad_r=kw - 1 - (kw - 1) // 2, pad_mode_h=nat.PAD_ZERO, pad_mode_w=nat.PAD_ZERO, Cout=4 * F,
+                         kh=kh, kw=kw)
+            self._op(nat.OP_LSTM, _Val(z, 0, 8 * F if ts > 0 else 4 * F, Ho, Wo), hseq, dst_c0=ts * F, Cout=F, act=act,
+                     act2=ract, aux=cst, aux_c0=0)
+        if layer.return_sequences:
+            return _Val(hseq, 0, T * F, Ho, Wo, (), (T, F, Ho, Wo))
+        return _Val(hseq, (T - 1) * F, F, Ho, Wo, (), (F, Ho, Wo))
+
     # -- driver --------------------------------------------------------------------------------------------------
     def _lower(self):
         m = self.model
-        in_shape = m.inputs[0].shape[1:]
-        if len(in_shape) != 3 or any(s is None for s in in_shape):
-            raise NotImplementedError('the GPU plan needs a fully defined (C, H, W) input, got %s' % (in_shape,))
-        C, H, W = in_shape
+        in_shape = tuple(m.inputs[0].shape[1:])
+        if len(in_shape) not in (3, 4) or any(s is None for s in in_shape):
+            raise NotImplementedError('the GPU plan needs a fully defined (C, H, W) or (T, C, H, W) input, got %s' %
+                                      (in_shape,))
+        # a (time, channels, lat, lon) input (recurrent nets) is the same memory as (time * channels, lat, lon)
+        C, H, W = int(np.prod(in_shape[:-2])), in_shape[-2], in_shape[-1]
         in_buf = self._new_buffer(C, H, W, nat.BUF_INPUT)
-        vals = {id(m.inputs[0]): _Val(in_buf, 0, C, H, W)}
+        vals = {id(m.inputs[0]): _Val(in_buf, 0, C, H, W, (), in_shape)}
         for node in m._nodes:
             if isinstance(node.layer, InputLayer):
                 continue
@@ -251,11 +333,14 @@ class Lowering(object):
                 break
         # drop buffers nobody references any more (keep indices stable by compacting)
         live = sorted({o['src'] for o in self.ops} | {o['dst'] for o in self.ops} |
+                      {o['aux'] for o in self.ops if o['aux'] >= 0} |
                       {i for i, b in enumerate(self.buffers) if b['kind'] != nat.BUF_INTERNAL})
         remap = {old: new for new, old in enumerate(live)}
         self.buffers = [self.buffers[i] for i in live]
         for o in self.ops:
             o['src'], o['dst'] = remap[o['src']], remap[o['dst']]
+            if o['aux'] >= 0:
+                o['aux'] = remap[o['aux']]
         for v in self.out_vals:
             v.buf = remap[v.buf]
 
@@ -295,7 +380,8 @@ class CompiledNet(object):
         self.plan = ctypes.c_void_p()
         self.max_batch = 0
         self._pushed = {}
-        self.in_shape = tuple(model.inputs[0].shape[1:])
+        self.in_shape = tuple(model.inputs[0].shape[1:])   # logical: (C, H, W), or (T, C, H, W) for recurrent nets
+        self.in_phys = (int(np.prod(self.in_shape[:-2])),) + self.in_shape[-2:]
         self.out_shapes = [tuple(v.shape) for v in self.low.out_vals]
         self.out_phys = [(v.C, v.H, v.W) for v in self.low.out_vals]
         self.n_outputs = len(self.out_shapes)
@@ -561,7 +647,7 @@ class CompiledNet(object):
 
     # -- the rollout ---------------------------------------------------------------------------------------------
     def can_rollout(self):
-        return all(p == self.in_shape for p in self.out_phys)
+        return all(p == self.in_phys for p in self.out_phys)
 
     def rollout_device(self, x0, iterations, use_graph=True, out=None):
         """Device-resident rollout.  x0: CUDA (N,C,H,W).  Returns a CUDA tensor (iterations*n_outputs, N, C, H, W).

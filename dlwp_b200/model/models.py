@@ -187,8 +187,8 @@ class DLWPNeuralNet(object):
         return predicted
 
     def _device_rollout_ok(self, predictors, step_sequence):
-        return (not step_sequence and not self.is_recurrent and not self.impute and self.scaler_type is None and
-                hasattr(self.model, 'engine') and predictors.ndim == 4 and
+        return (not step_sequence and not self.impute and self.scaler_type is None and
+                hasattr(self.model, 'engine') and predictors.ndim == (5 if self.is_recurrent else 4) and
                 self.model.engine(predictors.shape[0]).can_rollout())
 
     def predict_timeseries(self, predictors, time_steps, step_sequence=False, keep_time_dim=False, **kwargs):

@@ -89,8 +89,8 @@ class BandPlanner(object):
                 elif op['pre_op'] == 2:
                     slo, shi = slo // 2, -(-shi // 2)
             elif kind == nat.OP_PAD:
-                if op['pad_mode_h'] == nat.PAD_PERIODIC and (op['pad_t'] or op['pad_b']):
-                    raise NotImplementedError('latitude bands need non-periodic latitude padding')
+                if op['pad_mode_h'] != nat.PAD_ZERO and (op['pad_t'] or op['pad_b']):
+                    raise NotImplementedError('latitude bands need zero latitude padding')
                 slo, shi = lo - op['pad_t'], hi - op['pad_t']
             elif kind == nat.OP_MAXPOOL:
                 slo, shi = 2 * lo, 2 * hi

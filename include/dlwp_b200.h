@@ -42,7 +42,11 @@ enum {
 
 /* Padding applied (logically) in front of a convolution.  PERIODIC = PeriodicPadding2D (DLWP/custom.py:191-214),
  * ZERO = keras ZeroPadding2D.  One mode per axis; the example nets use PERIODIC on W (longitude) and ZERO on H. */
-enum { DLWP_PAD_ZERO = 0, DLWP_PAD_PERIODIC = 1 };
+enum { DLWP_PAD_ZERO = 0, DLWP_PAD_PERIODIC = 1,
+       /* stand-alone padding ops only (dlwp_pad2d / DLWP_OP_PAD), never fused into a conv: */
+       DLWP_PAD_EDGE = 2,        /* FillPadding2D (DLWP/custom.py:359-402): replicate the border row / column      */
+       DLWP_PAD_REFLECT = 3,     /* TFPadding2D mode='REFLECT' (custom.py:581-586 -> tf.pad): mirror, border excluded */
+       DLWP_PAD_SYMMETRIC = 4 }; /* TFPadding2D mode='SYMMETRIC': mirror, border included                            */
 
 /* Conv2D `activation=` values used by the example nets (examples/train.py:159-219). */
 enum { DLWP_ACT_LINEAR = 0, DLWP_ACT_TANH = 1, DLWP_ACT_RELU = 2 };

@@ -189,6 +189,85 @@ class OUpSampling2D(OLayer):
         return ops.upsample2d(x, self.size, self.data_format)
 
 
+class OPeriodicPadding3D(OLayer):
+    """DLWP/custom.py:217-306 on per-sample shapes (d, a1, a2, a3) (channels_first: the three trailing axes are padded)."""
+    _pad = staticmethod(ops.periodic_pad3d)
+
+    def __init__(self, padding=(1, 1, 1), data_format=None, **kwargs):
+        self.padding = ops.normalize_padding3d(padding)
+        self.data_format = data_format or 'channels_last'
+
+    def output_shape(self, s):
+        axes = (1, 2, 3) if self.data_format == 'channels_first' else (0, 1, 2)
+        s = list(s)
+        for a, (p0, p1) in zip(axes, self.padding):
+            s[a] += p0 + p1
+        return tuple(s)
+
+    def __call__(self, x):
+        return self._pad(np.asarray(x), self.padding, self.data_format)
+
+
+class OZeroPadding3D(OPeriodicPadding3D):
+    _pad = staticmethod(ops.zero_pad3d)
+
+
+class OConvLSTM2D(OLayer):
+    """keras ConvLSTM2D as built at examples/train.py:150-157 (channels_first, (T, C, H, W) per sample); numpy only."""
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', data_format=None, dilation_rate=(1, 1),
+                 activation='tanh', recurrent_activation='hard_sigmoid', use_bias=True, unit_forget_bias=True,
+                 return_sequences=False, **kwargs):
+        if (data_format or 'channels_last') != 'channels_first' or ops.normalize_pair(strides) != (1, 1):
+            raise ValueError('oracle ConvLSTM2D restates the channels_first, stride-1 layer of the example nets')
+        self.filters = int(filters)
+        self.kernel_size = ops.normalize_pair(kernel_size, 'kernel_size')
+        self.dilation_rate = ops.normalize_pair(dilation_rate, 'dilation_rate')
+        self.padding = padding
+        self.activation, self.recurrent_activation = activation, recurrent_activation
+        self.use_bias, self.unit_forget_bias = use_bias, unit_forget_bias
+        self.return_sequences = return_sequences
+        self.kernel = self.recurrent_kernel = self.bias = None
+
+    def build(self, s):
+        kh, kw = self.kernel_size
+        F = self.filters
+        self.kernel = np.zeros((kh, kw, s[1], 4 * F), np.float32)
+        self.recurrent_kernel = np.zeros((kh, kw, F, 4 * F), np.float32)
+        if self.use_bias:
+            self.bias = np.zeros((4 * F,), np.float32)
+            if self.unit_forget_bias:
+                self.bias[F:2 * F] = 1.0
+
+    def output_shape(self, s):
+        kh, kw = self.kernel_size
+        dh, dw = self.dilation_rate
+        H, W = (s[2], s[3]) if self.padding == 'same' else (s[2] - dh * (kh - 1), s[3] - dw * (kw - 1))
+        return (s[0], self.filters, H, W) if self.return_sequences else (self.filters, H, W)
+
+    @property
+    def weights(self):
+        return [self.kernel, self.recurrent_kernel] + ([self.bias] if self.use_bias else [])
+
+    def set_weights(self, ws):
+        self.kernel, self.recurrent_kernel = np.asarray(ws[0]), np.asarray(ws[1])
+        if self.use_bias:
+            self.bias = np.asarray(ws[2])
+
+    def randomize(self, rng, bias_scale=0.0):
+        kh, kw, cin, f4 = self.kernel.shape
+        self.kernel = ops.glorot_uniform(rng, kh, kw, cin, f4)
+        self.recurrent_kernel = ops.glorot_uniform(rng, kh, kw, self.filters, f4)
+        if self.use_bias and bias_scale:
+            self.bias = (self.bias + bias_scale * rng.standard_normal(self.bias.shape)).astype(np.float32)
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        cast = lambda w: None if w is None else np.asarray(w, x.dtype)
+        return ops.conv_lstm2d(x, cast(self.kernel), cast(self.recurrent_kernel), cast(self.bias), self.dilation_rate,
+                               self.padding, self.activation, self.recurrent_activation, self.return_sequences)
+
+
 class OReshape(OLayer):
     def __init__(self, target_shape, **kwargs):
         self.target_shape = tuple(target_shape)
@@ -232,6 +311,9 @@ LAYER_REGISTRY = {
     'MaxPooling2D': OMaxPooling2D,
     'UpSampling2D': OUpSampling2D,
     'Reshape': OReshape,
+    'PeriodicPadding3D': OPeriodicPadding3D,
+    'ZeroPadding3D': OZeroPadding3D,
+    'ConvLSTM2D': OConvLSTM2D,
 }
 
 
@@ -293,12 +375,16 @@ class OSequential(object):
     def conv_layers(self):
         return [l for l in self.layers if isinstance(l, OConv2D)]
 
+    @property
+    def weight_layers(self):
+        return [l for l in self.layers if isinstance(l, (OConv2D, OConvLSTM2D))]
+
     def get_weights(self):
-        return [w for l in self.conv_layers for w in l.weights]
+        return [w for l in self.weight_layers for w in l.weights]
 
     def set_weights(self, ws):
         ws = list(ws)
-        for l in self.conv_layers:
+        for l in self.weight_layers:
             n = len(l.weights)
             l.set_weights(ws[:n])
             ws = ws[n:]

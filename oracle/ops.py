@@ -71,6 +71,110 @@ def periodic_pad2d(x, padding, data_format='channels_first'):
     return o
 
 
+def fill_pad2d(x, padding, data_format='channels_first'):
+    """DLWP/custom.py:359-402 (FillPadding2D.call): the first / last row is stacked `pad` times above / below, then the
+    first / last column of the row-padded tensor left / right -- np.pad(mode='edge') on H, then on W."""
+    (t, b), (l, r) = normalize_padding(padding)
+    _, ah, aw = _axes(data_format)
+    pads = [(0, 0)] * x.ndim
+    pads[ah] = (t, b)
+    o = np.pad(x, pads, mode='edge')
+    pads = [(0, 0)] * x.ndim
+    pads[aw] = (l, r)
+    return np.pad(o, pads, mode='edge')
+
+
+def tf_pad2d(x, padding, mode='CONSTANT', data_format='channels_first'):
+    """DLWP/custom.py:581-586 (TFPadding2D.call -> tf.pad): CONSTANT zeros, REFLECT (border excluded) or SYMMETRIC
+    (border included) -- numpy's 'constant' / 'reflect' / 'symmetric' (tf.pad's documented semantics; tensorflow is not
+    in /root/reference: unpinned)."""
+    (t, b), (l, r) = normalize_padding(padding)
+    _, ah, aw = _axes(data_format)
+    pads = [(0, 0)] * x.ndim
+    pads[ah] = (t, b)
+    pads[aw] = (l, r)
+    return np.pad(x, pads, mode={'CONSTANT': 'constant', 'REFLECT': 'reflect', 'SYMMETRIC': 'symmetric'}[mode.upper()])
+
+
+def normalize_padding3d(padding):
+    """keras ZeroPadding3D.__init__: int / 3 ints / 3 pairs -> ((a0,a1),(b0,b1),(c0,c1))."""
+    if isinstance(padding, (int, np.integer)):
+        return ((int(padding),) * 2,) * 3
+    if len(padding) != 3:
+        raise ValueError('`padding` should have 3 elements. Found: ' + str(padding))
+    return tuple(normalize_pair(p, 'entry of padding') for p in padding)
+
+
+def periodic_pad3d(x, padding, data_format='channels_first'):
+    """
+    DLWP/custom.py:277-306 on a 5-D array.  channels_first: the padded axes are 2, 3, 4 -- in the recurrent example nets
+    the input is (batch, time, channels, lat, lon), so 'depth' is time and the first padded axis is the channel axis
+    (examples/train.py:144-149).  Order: axis 4 (horizontal), then axis 3 of the result, then axis 2 of that result.
+    """
+    (d0, d1), (t, b), (l, r) = normalize_padding3d(padding)
+    a1, a2, a3 = (2, 3, 4) if data_format in (None, 'channels_first') else (1, 2, 3)
+
+    def take(a, axis, sl):
+        idx = [slice(None)] * a.ndim
+        idx[axis] = sl
+        return a[tuple(idx)]
+
+    n1, n2, n3 = x.shape[a1], x.shape[a2], x.shape[a3]
+    o = np.concatenate([take(x, a3, slice(n3 - l, n3)), x, take(x, a3, slice(0, r))], axis=a3)
+    o = np.concatenate([take(o, a2, slice(n2 - t, n2)), o, take(o, a2, slice(0, b))], axis=a2)
+    o = np.concatenate([take(o, a1, slice(n1 - d0, n1)), o, take(o, a1, slice(0, d1))], axis=a1)
+    return o
+
+
+def zero_pad3d(x, padding, data_format='channels_first'):
+    """Keras ZeroPadding3D: constant zeros on the three padded axes."""
+    pd = normalize_padding3d(padding)
+    axes = (2, 3, 4) if data_format in (None, 'channels_first') else (1, 2, 3)
+    pads = [(0, 0)] * x.ndim
+    for a, p in zip(axes, pd):
+        pads[a] = p
+    return np.pad(x, pads, mode='constant')
+
+
+def hard_sigmoid(v):
+    """keras.backend.hard_sigmoid: clip(0.2 x + 0.5, 0, 1)."""
+    return np.clip(0.2 * v + 0.5, 0.0, 1.0)
+
+
+def conv_lstm2d(x, kernel, recurrent_kernel, bias, dilation=(1, 1), padding='valid', act='tanh',
+                recurrent_act='hard_sigmoid', return_sequences=True):
+    """
+    keras.layers.ConvLSTM2D forward (Keras 2.2 ConvLSTM2DCell.call; Keras itself is not in /root/reference, so this is
+    a restatement of its published cell: PARITY UNPINNED), channels_first: x (N, T, C, H, W); kernel (kh, kw, C, 4F),
+    recurrent_kernel (kh, kw, F, 4F), bias (4F,) or None; gate blocks i, f, c, o.  Initial h and c are zero.
+        x_g = conv(x_t, W_g, padding, dilation) + b_g          (the layer's padding and dilation)
+        h_g = conv(h_{t-1}, U_g, 'same', no dilation)          (recurrent_conv)
+        i = s(x_i + h_i); f = s(x_f + h_f); c = f * c_{t-1} + i * a(x_c + h_c); o = s(x_o + h_o); h = o * a(c)
+    """
+    n, T, C, H, W = x.shape
+    kh, kw, _, F4 = kernel.shape
+    F = F4 // 4
+    dh, dw = normalize_pair(dilation, 'dilation_rate')
+    a = activation(act)
+    s = hard_sigmoid if recurrent_act == 'hard_sigmoid' else (lambda v: 1.0 / (1.0 + np.exp(-v)))
+    if padding == 'same':
+        th, tw = dh * (kh - 1), dw * (kw - 1)
+        x = np.pad(x, [(0, 0), (0, 0), (0, 0), (th // 2, th - th // 2), (tw // 2, tw - tw // 2)], mode='constant')
+    rp = [(0, 0), (0, 0), ((kh - 1) // 2, kh - 1 - (kh - 1) // 2), ((kw - 1) // 2, kw - 1 - (kw - 1) // 2)]
+    h = c = None
+    out = []
+    for t in range(T):
+        z = conv2d_valid(x[:, t], kernel, bias, (dh, dw))
+        if h is not None:
+            z = z + conv2d_valid(np.pad(h, rp, mode='constant'), recurrent_kernel, None, (1, 1))
+        zi, zf, zc, zo = z[:, :F], z[:, F:2 * F], z[:, 2 * F:3 * F], z[:, 3 * F:]
+        i, f, o = s(zi), s(zf), s(zo)
+        c = i * a(zc) if c is None else f * c + i * a(zc)
+        h = o * a(c)
+        out.append(h)
+    return np.stack(out, axis=1) if return_sequences else h
+
+
 def zero_pad2d(x, padding, data_format='channels_first'):
     """Keras ZeroPadding2D: constant-zero rows/cols."""
     (t, b), (l, r) = normalize_padding(padding)

@@ -39,7 +39,10 @@ for i in range(2):
     if cnt[10]:
         per_row.append('op%d per CTA: span %.0f clk = %.1f us (%.3f GHz), first row after %.0f clk, rows/CTA %.1f' % (
             i, cnt[8] / cnt[10], 1e-3 * cnt[9] / cnt[10], cnt[8] / max(cnt[9], 1), cnt[11] / cnt[10], cnt[3] / cnt[10]))
-    if cnt[7]:
+    if cnt[10] and eng.fused_pair() < 0:
+        per_row.append('op%d per CTA: phantom-slot waits %.0f clk, between segments %.0f clk; epilogue warp 0: waiting %.0f clk, '
+                       'working %.0f clk' % (i, cnt[4] / cnt[10], cnt[5] / cnt[10], cnt[6] / cnt[10], cnt[7] / cnt[10]))
+    elif cnt[7]:
         per_row.append('fused conv2 clk/row: wait-acc %.0f wait-intermediate %.0f issue %.0f (rows %d)' % (
             cnt[4] / cnt[7], cnt[5] / cnt[7], cnt[6] / cnt[7], cnt[7]))
 if per_row:

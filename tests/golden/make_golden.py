@@ -61,6 +61,13 @@ class _StubZeroPadding2D(object):
             self.padding = tuple(pads)
 
 
+class _StubZeroPadding3D(_StubZeroPadding2D):
+    """keras.layers.ZeroPadding3D.__init__ argument normalisation (int -> three symmetric pairs)."""
+
+    def __init__(self, padding=(1, 1, 1), data_format=None, **kwargs):
+        super(_StubZeroPadding3D, self).__init__((padding,) * 3 if isinstance(padding, int) else padding, data_format)
+
+
 class _Any(object):
     def __init__(self, *a, **k):
         pass
@@ -75,13 +82,14 @@ def install_stubs():
     K = _mod('keras.backend',
              backend=lambda: 'numpy',
              concatenate=lambda xs, axis=-1: np.concatenate(xs, axis=axis),
+             stack=lambda xs, axis=0: np.stack(xs, axis=axis),
              ones=np.ones, zeros=np.zeros,
              normalize_data_format=lambda v: 'channels_last' if v is None else v,
              conv2d=_np_conv2d)
     _mod('keras', backend=K)
     _mod('keras.callbacks', Callback=_Any, EarlyStopping=_Any)
     _mod('keras.layers', Lambda=_Any, Layer=_Any)
-    _mod('keras.layers.convolutional', ZeroPadding2D=_StubZeroPadding2D, ZeroPadding3D=_StubZeroPadding2D)
+    _mod('keras.layers.convolutional', ZeroPadding2D=_StubZeroPadding2D, ZeroPadding3D=_StubZeroPadding3D)
     _mod('keras.layers.local', LocallyConnected2D=_Any)
     _mod('keras.losses', mean_absolute_error=None, mean_squared_error=None)
     _mod('keras.utils', conv_utils=None, multi_gpu_model=None)
@@ -126,6 +134,79 @@ def gen_periodic_padding(custom):
             layer = custom.PeriodicPadding2D(padding=p, data_format=fmt)
             out['y_%d_%s' % (k, fmt)] = layer.call(x)
     np.savez_compressed(os.path.join(HERE, 'periodic_padding2d.npz'), **out)
+
+
+def gen_padding_3d_and_fill(custom):
+    """The real PeriodicPadding3D.call (custom.py:277-306) and FillPadding2D.call (custom.py:359-402) on numpy arrays."""
+    rng = np.random.RandomState(15)
+    out = {}
+    x5_cf = rng.standard_normal((2, 3, 4, 5, 7)).astype(np.float32)   # (batch, depth, a1, a2, a3)
+    x5_cl = rng.standard_normal((2, 4, 5, 7, 3)).astype(np.float32)
+    out['x5_channels_first'], out['x5_channels_last'] = x5_cf, x5_cl
+    pads3 = [(0, 0, 2), (0, 2, 0), (1, 1, 1), ((0, 1), (2, 0), (1, 3)), 2]
+    out['n3'] = np.int64(len(pads3))
+    for k, p in enumerate(pads3):
+        out['pad3_%d' % k] = np.asarray(OO.normalize_padding3d(p), np.int64)
+        for fmt, x in (('channels_first', x5_cf), ('channels_last', x5_cl)):
+            out['y3_%d_%s' % (k, fmt)] = custom.PeriodicPadding3D(padding=p, data_format=fmt).call(x)
+    x_cf = rng.standard_normal((2, 3, 5, 7)).astype(np.float32)
+    x_cl = rng.standard_normal((2, 5, 7, 3)).astype(np.float32)
+    out['x_channels_first'], out['x_channels_last'] = x_cf, x_cl
+    pads2 = [(0, 2), (1, 1), ((1, 2), (3, 0)), 2, ((0, 0), (2, 2)), ((0, 1), (0, 3))]
+    out['n2'] = np.int64(len(pads2))
+    for k, p in enumerate(pads2):
+        out['pad2_%d' % k] = np.asarray(OO.normalize_padding(p), np.int64)
+        for fmt, x in (('channels_first', x_cf), ('channels_last', x_cl)):
+            out['yfill_%d_%s' % (k, fmt)] = custom.FillPadding2D(padding=p, data_format=fmt).call(x)
+    np.savez_compressed(os.path.join(HERE, 'padding3d_fill2d.npz'), **out)
+
+
+def _small_recurrent(time_dim, nvar, H, W, seed):
+    """The recurrent front block of examples/train.py:144-157 in front of a small conv stack."""
+    cf = 'channels_first'
+    cs = (time_dim, nvar, H, W)
+    net = OL.OSequential((
+        ('PeriodicPadding3D', ((0, 0, 2),), {'data_format': cf, 'input_shape': cs}),
+        ('ZeroPadding3D', ((0, 2, 0),), {'data_format': cf}),
+        ('ConvLSTM2D', (2 * nvar, 3), {'dilation_rate': 2, 'padding': 'valid', 'data_format': cf, 'activation': 'tanh',
+                                       'return_sequences': True}),
+        ('Reshape', ((2 * time_dim * nvar, H, W),), None),
+        ('PeriodicPadding2D', ((0, 1),), {'data_format': cf}),
+        ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+        ('Conv2D', (time_dim * nvar, 3), {'activation': 'linear', 'data_format': cf}),
+        ('Reshape', (cs,), None),
+    ))
+    rng = np.random.RandomState(seed)
+    for layer in net.weight_layers:
+        if isinstance(layer, OL.OConvLSTM2D):
+            layer.randomize(rng, bias_scale=0.1)
+    OL.init_weights(net.conv_layers, seed=seed + 1, bias_scale=0.1)
+    return net
+
+
+def gen_rollout_recurrent(models):
+    """The reference's own DLWPNeuralNet.predict_timeseries with is_recurrent=True (models.py:270-301: 5-D predictors,
+    feature_shape = shape[2:]) around a ConvLSTM2D-fronted net; the net's arithmetic is the oracle's."""
+    out = {}
+    rng = np.random.RandomState(16)
+    cases = []
+    for time_dim in (2, 3):
+        net = _small_recurrent(time_dim, 2, 6, 8, seed=40 + time_dim)
+        x0 = rng.standard_normal((3, time_dim, 2, 6, 8)).astype(np.float32)
+        out['x0_td%d' % time_dim] = x0
+        for k, w in enumerate(net.get_weights()):
+            out['w_td%d_%d' % (time_dim, k)] = w
+        dlwp = models.DLWPNeuralNet(is_convolutional=True, is_recurrent=True, time_dim=time_dim, scaler_type=None,
+                                    scale_targets=False)
+        dlwp.model = _FakeKerasModel(net)
+        for steps in (1, 5):
+            for ss in (False, True):
+                for ktd in (False, True):
+                    key = 'y_td%d_s%d_ss%d_k%d' % (time_dim, steps, ss, ktd)
+                    out[key] = dlwp.predict_timeseries(x0, steps, step_sequence=ss, keep_time_dim=ktd)
+                    cases.append(key)
+    out['cases'] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, 'rollout_recurrent.npz'), **out)
 
 
 def gen_row_conv(custom):
@@ -268,11 +349,14 @@ def main():
     custom = load_ref('DLWP.custom', 'DLWP/custom.py')
     models = load_ref('DLWP.model.models', 'DLWP/model/models.py')
     models_torch = load_ref('DLWP.model.models_torch', 'DLWP/model/models_torch.py')
-    gen_periodic_padding(custom)
-    gen_row_conv(custom)
-    gen_rollout_neuralnet(models)
-    gen_rollout_functional(models)
-    gen_torchnn(models_torch)
+    only = set(sys.argv[1:])     # e.g. `make_golden.py padding3d recurrent`: regenerate just those fixtures
+    gens = [('padding2d', lambda: gen_periodic_padding(custom)), ('row_conv', lambda: gen_row_conv(custom)),
+            ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
+            ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
+            ('recurrent', lambda: gen_rollout_recurrent(models))]
+    for name, fn in gens:
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print('%-28s %8d bytes' % (f, os.path.getsize(os.path.join(HERE, f))))

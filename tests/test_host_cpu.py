@@ -33,14 +33,14 @@ def test_library_exports_every_declared_symbol(nat):
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dlwp_abi_version() == nat.ABI_VERSION == 2
+    assert lib.dlwp_abi_version() == nat.ABI_VERSION == 3
     assert lib.dlwp_kernel_launch_count() == 0
 
 
 def test_struct_layouts_match_header(nat):
     assert ctypes.sizeof(nat.ConvDesc) == 22 * 4 + 6 * 8
     assert ctypes.sizeof(nat.BufferDesc) == 6 * 4
-    assert ctypes.sizeof(nat.OpDesc) == 24 * 4
+    assert ctypes.sizeof(nat.OpDesc) == 27 * 4
     assert ctypes.sizeof(nat.NetDesc) == 4 * 4 + 2 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(nat.PlanOptions) == 16 * 4
     assert nat.PlanOptions().tc_taps_in_k == -1 and nat.PlanOptions(math=1).math == 1
@@ -239,3 +239,55 @@ def test_model_pickles_after_training_state_was_attached_and_with_latitude_loss(
     rng = np.random.RandomState(0)
     a, b = rng.standard_normal((2, 3, 4, 5)), rng.standard_normal((2, 3, 4, 5))
     assert np.isfinite(acc(a, b)).all() and acc.__name__ == 'acc_loss'
+
+
+def test_recurrent_front_block_builds_and_lowers(nat):
+    """examples/train.py:144-157: PeriodicPadding3D + ZeroPadding3D + ConvLSTM2D + Reshape in front of the conv stack.
+    Per time step: input conv (pads fused), recurrent conv ('same', zero padded; absent at t = 0), one gate op."""
+    from dlwp_b200.engine import Lowering
+    from dlwp_b200.model import DLWPNeuralNet
+    from tests.test_oracle_golden import small_recurrent_layers
+    dlwp = DLWPNeuralNet(is_convolutional=True, is_recurrent=True, time_dim=3, scaler_type=None, scale_targets=False)
+    dlwp.build_model(small_recurrent_layers(3), loss='mse', optimizer='adam')
+    m = dlwp.model
+    assert [l.output_shape for l in m.layers[:4]] == [(None, 3, 2, 6, 12), (None, 3, 2, 10, 12), (None, 3, 4, 6, 8),
+                                                      (None, 12, 6, 8)]
+    lstm = m.layers[2]
+    assert [w.shape for w in lstm.get_weights()] == [(3, 3, 2, 16), (3, 3, 4, 16), (16,)]
+    np.testing.assert_array_equal(lstm.get_weights()[2], np.repeat([0., 1., 0., 0.], 4))   # unit_forget_bias
+    low = Lowering(m)
+    kinds = [o['kind'] for o in low.ops]
+    assert kinds == [nat.OP_CONV, nat.OP_LSTM, nat.OP_CONV, nat.OP_CONV, nat.OP_LSTM, nat.OP_CONV, nat.OP_CONV,
+                     nat.OP_LSTM, nat.OP_CONV]
+    first, rec = low.ops[0], low.ops[3]
+    assert (first['pad_mode_w'], first['pad_mode_h'], first['pad_l'], first['pad_t'], first['dil_h']) == (
+        nat.PAD_PERIODIC, nat.PAD_ZERO, 2, 2, 2)
+    assert (rec['pad_mode_w'], rec['pad_l'], rec['pad_t'], rec['dil_h'], rec['dst_c0']) == (nat.PAD_ZERO, 1, 1, 1, 16)
+    assert [o['src_c'] for o in low.ops if o['kind'] == nat.OP_LSTM] == [16, 32, 32]
+    assert low.out_vals[0].shape == (3, 2, 6, 8)
+    assert low.buffers[low.ops[1]['aux']]['C'] == 4        # the cell state survives buffer compaction
+    import pickle
+    m2 = pickle.loads(pickle.dumps(m))
+    assert [w.shape for w in m2.get_weights()] == [w.shape for w in m.get_weights()]
+
+
+def test_fill_and_tf_padding_lower_to_pad_ops(nat):
+    from dlwp_b200.engine import Lowering
+    from dlwp_b200.model import DLWPNeuralNet
+    cf = 'channels_first'
+    layers = (('FillPadding2D', ((1, 2),), {'data_format': cf, 'input_shape': (3, 9, 12)}),
+              ('Conv2D', (5, 3), {'activation': 'tanh', 'data_format': cf}),
+              ('TFPadding2D', ((1, 1),), {'data_format': cf, 'mode': 'SYMMETRIC'}),
+              ('Conv2D', (3, 3), {'activation': 'linear', 'data_format': cf}))
+    dlwp = DLWPNeuralNet(is_convolutional=True, scaler_type=None, scale_targets=False)
+    dlwp.build_model(layers, loss='mse', optimizer='adam')
+    low = Lowering(dlwp.model)
+    assert [(o['kind'], o['pad_mode_h']) for o in low.ops] == [(nat.OP_PAD, nat.PAD_EDGE), (nat.OP_CONV, 0),
+                                                               (nat.OP_PAD, nat.PAD_SYMMETRIC), (nat.OP_CONV, 0)]
+    bad = (('TFPadding2D', ((1, 1),), {'data_format': cf, 'mode': 'CONSTANT', 'constant_values': 2.0,
+                                       'input_shape': (3, 9, 12)}),
+           ('Conv2D', (3, 3), {'data_format': cf}))
+    dlwp = DLWPNeuralNet(is_convolutional=True, scaler_type=None, scale_targets=False)
+    dlwp.build_model(bad, loss='mse', optimizer='adam')
+    with pytest.raises(NotImplementedError):
+        Lowering(dlwp.model)

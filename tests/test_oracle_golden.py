@@ -166,3 +166,67 @@ def test_rollout_argument_errors():
         OR.neuralnet_predict_timeseries(lambda p: p, np.zeros((1, 2, 3, 4), np.float32), 0)
     with pytest.raises(ValueError):
         OR.functional_predict_timeseries(lambda p: p, np.zeros((1, 2, 3, 4), np.float32), -1)
+
+
+def test_periodic_padding3d_and_fill_padding_match_reference_call(golden_dir):
+    """PeriodicPadding3D.call (custom.py:277-306) and FillPadding2D.call (custom.py:359-402), run in place."""
+    g = _load(golden_dir, 'padding3d_fill2d.npz')
+    for k in range(int(g['n3'])):
+        pad = tuple(tuple(int(v) for v in row) for row in g['pad3_%d' % k])
+        for fmt in ('channels_first', 'channels_last'):
+            np.testing.assert_array_equal(OO.periodic_pad3d(g['x5_' + fmt], pad, fmt), g['y3_%d_%s' % (k, fmt)])
+    for k in range(int(g['n2'])):
+        pad = tuple(tuple(int(v) for v in row) for row in g['pad2_%d' % k])
+        for fmt in ('channels_first', 'channels_last'):
+            np.testing.assert_array_equal(OO.fill_pad2d(g['x_' + fmt], pad, fmt), g['yfill_%d_%s' % (k, fmt)])
+
+
+def small_recurrent_layers(time_dim, nvar=2, H=6, W=8):
+    """The net of tests/golden/make_golden.py:_small_recurrent (ConvLSTM2D front block of examples/train.py:144-157)."""
+    cf = 'channels_first'
+    cs = (time_dim, nvar, H, W)
+    return (('PeriodicPadding3D', ((0, 0, 2),), {'data_format': cf, 'input_shape': cs}),
+            ('ZeroPadding3D', ((0, 2, 0),), {'data_format': cf}),
+            ('ConvLSTM2D', (2 * nvar, 3), {'dilation_rate': 2, 'padding': 'valid', 'data_format': cf,
+                                           'activation': 'tanh', 'return_sequences': True}),
+            ('Reshape', ((2 * time_dim * nvar, H, W),), None),
+            ('PeriodicPadding2D', ((0, 1),), {'data_format': cf}),
+            ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+            ('Conv2D', (time_dim * nvar, 3), {'activation': 'linear', 'data_format': cf}),
+            ('Reshape', (cs,), None))
+
+
+def test_recurrent_rollout_matches_reference_loop(golden_dir):
+    """is_recurrent=True branch of models.py:270-301 (5-D predictors) around the ConvLSTM2D-fronted oracle net."""
+    g = _load(golden_dir, 'rollout_recurrent.npz')
+    for key in g['cases']:
+        key = str(key)
+        td, steps, ss, ktd = (int(p[len(pre):]) for p, pre in zip(key.split('_')[1:], ('td', 's', 'ss', 'k')))
+        net = OL.OSequential(small_recurrent_layers(td))
+        net.set_weights([g['w_td%d_%d' % (td, k)] for k in range(5)])
+        fn = lambda p: net.forward(np.asarray(p, np.float64)).astype(np.float32)
+        y = OR.neuralnet_predict_timeseries(fn, g['x0_td%d' % td], steps, time_dim=td, is_recurrent=True,
+                                            step_sequence=bool(ss), keep_time_dim=bool(ktd))
+        assert y.shape == g[key].shape, key
+        np.testing.assert_array_equal(y, g[key], err_msg=key)
+
+
+def test_conv_lstm_first_step_and_gate_algebra():
+    """ConvLSTM2D restatement: with a zero recurrent kernel every step is the stateless first step with the carried cell
+    state; the first step equals the closed form o * tanh(i * tanh(z_c)) of the four gate convolutions."""
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal((2, 3, 2, 7, 9))
+    k = 0.3 * rng.standard_normal((3, 3, 2, 8))
+    u = 0.3 * rng.standard_normal((3, 3, 2, 8))
+    b = 0.1 * rng.standard_normal(8)
+    y = OO.conv_lstm2d(x, k, u, b, padding='same')
+    assert y.shape == (2, 3, 2, 7, 9)
+    z = OO.conv2d_valid(np.pad(x[:, 0], [(0, 0), (0, 0), (1, 1), (1, 1)]), k, b)
+    i, c, o = OO.hard_sigmoid(z[:, :2]), np.tanh(z[:, 4:6]), OO.hard_sigmoid(z[:, 6:])
+    np.testing.assert_allclose(y[:, 0], o * np.tanh(i * c), atol=1e-14)
+    y0 = OO.conv_lstm2d(x, k, 0 * u, b, padding='same', return_sequences=False)
+    z2 = [OO.conv2d_valid(np.pad(x[:, t], [(0, 0), (0, 0), (1, 1), (1, 1)]), k, b) for t in range(3)]
+    cst = 0
+    for zt in z2:
+        cst = OO.hard_sigmoid(zt[:, 2:4]) * cst + OO.hard_sigmoid(zt[:, :2]) * np.tanh(zt[:, 4:6])
+    np.testing.assert_allclose(y0, OO.hard_sigmoid(z2[-1][:, 6:]) * np.tanh(cst), atol=1e-14)
