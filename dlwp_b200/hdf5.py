@@ -602,7 +602,6 @@ class _Image(object):
 
     def dataset(self, ds):
         a = _as_array(ds.data)
-        a = np.ascontiguousarray(a)
         addr = self.alloc(a.tobytes()) if a.size else UNDEF
         msgs = [(0x0001, _dataspace_message(a.shape)), (0x0003, _dtype_message(a.dtype)),
                 (0x0005, struct.pack('<BBBB', 2, 2, 2, 0)),                      # fill value v2: late alloc, none defined

@@ -369,16 +369,33 @@ class Model(object):
         return d
 
     def save(self, filepath, overwrite=True, include_optimizer=True):
-        """Replaces keras' HDF5 container (h5py is unavailable offline) with a pickle of the graph + weights."""
-        with open(filepath, 'wb') as f:
-            pickle.dump({'format': 'dlwp_b200.keras.v1', 'model': self}, f, protocol=pickle.HIGHEST_PROTOCOL)
+        """keras.Model.save: the Keras 2.2 HDF5 model file (model_config + training_config + model_weights group), written
+        by dlwp_b200.hdf5 -- the format DLWP/util.py:139-141 produces and :173 reads (keras/saving.py has the layout)."""
+        from .saving import save_model
+        save_model(self, filepath, include_optimizer=include_optimizer)
 
     def save_weights(self, filepath):
-        np.savez(filepath, *self.get_weights())
+        """keras.Model.save_weights: an HDF5 file whose root is the `model_weights` group of a full model file."""
+        from .. import hdf5
+        from .saving import save_weights_to_group
+        w = hdf5.FileWriter()
+        save_weights_to_group(self, w)
+        w.save(filepath)
 
     def load_weights(self, filepath):
-        with np.load(filepath) as z:
-            self.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
+        from .. import hdf5
+        from .saving import load_weights_from_group
+        f = hdf5.File(filepath)
+        load_weights_from_group(self, f['model_weights'] if 'model_weights' in f.keys() else f)
+
+    def get_config(self):
+        from .saving import model_config
+        return model_config(self)['config']
+
+    def to_json(self):
+        import json
+        from .saving import model_config
+        return json.dumps(model_config(self))
 
     def __del__(self):
         if sys is None or sys.is_finalizing():
@@ -430,9 +447,15 @@ class Sequential(Model):
 
 
 def load_model(filepath, custom_objects=None, compile=True):
+    """keras.models.load_model for Keras 2.2 HDF5 model files (written by the reference or by Model.save above); the
+    pickle container of this package's first release is still read."""
     with open(filepath, 'rb') as f:
-        blob = pickle.load(f)
-    if not isinstance(blob, dict) or blob.get('format') != 'dlwp_b200.keras.v1':
-        raise ValueError('%s is not a dlwp_b200 model file (the reference\'s HDF5 .keras files need h5py, which is '
-                         'not available offline)' % filepath)
-    return blob['model']
+        head = f.read(8)
+    if head[:2] == b'\x80\x04' or head[:2] == b'\x80\x05' or head[:1] == b'\x80':
+        with open(filepath, 'rb') as f:
+            blob = pickle.load(f)
+        if isinstance(blob, dict) and blob.get('format') == 'dlwp_b200.keras.v1':
+            return blob['model']
+        raise ValueError('%s is neither an HDF5 model file nor a dlwp_b200 pickle container' % filepath)
+    from .saving import load_model as _load
+    return _load(filepath, custom_objects=custom_objects, compile=compile)
