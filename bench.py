@@ -197,6 +197,23 @@ def cpu_reference(n_samples, steps, warmup):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.workload == 'net_b':
+        _, onet = build_net_b_oracle_only()
+        v, cores, _ = net_b_cpu_reference(onet, 4, 1, 1)
+        n = int(max(1, min(16, 120.0 * v / max(1, args.steps + args.warmup))))
+        value, cores, dt = net_b_cpu_reference(onet, n, args.steps, args.warmup)
+        sample = '%d of %d samples x %d steps (Keras-style batch_size=32 chunks)' % (n, args.batch, args.steps)
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'net_b_skip_unet_12x180x360_rollout', 'batch_per_gpu': args.batch, 'timed_sample_batch': n,
+                       'note': 'reference rollout loop (DLWP/model/models.py:414-452 restated in oracle/) + torch-CPU fp32 '
+                               'forward; Keras/TensorFlow are not installable offline'},
+            'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}))
+        return
     # bounded sample: probe one step on 8 samples, then size the sample so the whole run stays within ~2 minutes
     v, cores, _ = cpu_reference(8, 1, 1)
     budget_s = 120.0
@@ -361,8 +378,9 @@ def run_ours(args, rank, world, local_rank):
     line = {
         'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': 'bf16' if (args.precision == 'bf16' and tc) else 'f32', 'data': 'synthetic',
         'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'batch_per_gpu': B,
+                   'precision': args.precision,
                    'global_batch': B * world, 'state': list(STATE), 'math': args.math, 'parallelism': 'independent forecasts per GPU'
                    if world > 1 else 'single GPU',
                    'l2': 'per-step working set %.0f MB (state in + 32-ch activation + state out) > 126 MB L2; no flush'
@@ -384,8 +402,10 @@ def run_ours(args, rank, world, local_rank):
 
 def run_latband(args, rank, world, local_rank):
     """
-    N > 1: the north-star partition -- every GPU owns a latitude band of ALL B forecasts and exchanges a 4-row halo of the
-    state with its neighbours once per step (one grouped NCCL SendRecv).  Strong scaling: the global batch stays B.
+    N > 1: the north-star partition -- every GPU owns a latitude band of ALL forecasts in flight and exchanges a 4-row halo
+    of the state with its neighbours once per step (one grouped NCCL SendRecv).  --scaling weak (default): the global batch
+    grows with the GPU count (B per GPU: B * N forecasts, each GPU computes its band of all of them -- per-GPU work fixed up
+    to the halo rows it recomputes); --scaling strong: the global batch stays B.
     """
     import torch
     import torch.distributed as dist
@@ -393,7 +413,12 @@ def run_latband(args, rank, world, local_rank):
     from dlwp_b200.parallel import LatBandEngine, halo_summary
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    K, W = args.steps, max(args.warmup, 3)
+    B = args.batch * world if args.scaling == 'weak' else args.batch
+    free, _ = torch.cuda.mem_get_info()
+    cap = int(0.5 * free / ((K + 2) * int(np.prod(STATE)) * 4))   # every rank holds full-shape series slots
+    capped = B > cap
+    B = max(world, min(B, cap))
     dlwp = build_model()
     eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist)
     x0 = make_inputs(B)                                    # the same global state on every rank
@@ -454,9 +479,10 @@ def run_latband(args, rank, world, local_rank):
         per_dir = halo['bytes_per_row'] * 4
         line = {
             'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
-            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'net_a_6x91x180_rollout (BASELINE.json configs[1])', 'global_batch': B,
+                       'batch_per_gpu': B / world, 'global_batch_capped_by_memory': capped,
                        'state': list(STATE), 'parallelism': 'latband%d (91 latitude rows split over %d GPUs, halo 4 rows)'
                        % (world, world), 'bands': [list(p.band) for p in eng.planners],
                        'bands_equal_single_domain_bitwise': verified,
@@ -475,6 +501,196 @@ def run_latband(args, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Net B: the skip U-Net of examples/train_functional.py:248-275 on the 12-channel 1-degree grid (BASELINE.json configs[2],
+# lat-band over N GPUs: configs[3]).  python bench.py --workload net_b [--precision bf16] [--batch 16]
+# ---------------------------------------------------------------------------------------------------------------------
+NET_B_STATE = (12, 180, 360)
+NET_B_BYTES = {'fp32': 62111600.0, 'bf16': 31266800.0}     # SURVEY.md 8(d), per sample-step
+NET_B_FLOP = 4678041600.0
+
+
+def build_net_b():
+    from tests.helpers import build_functional_pair
+    dlwp, onet = build_functional_pair(NET_B_STATE, skip=True, integration_steps=1, seed=1, bias_scale=0.02)
+    return dlwp, onet
+
+
+def build_net_b_oracle_only():
+    from oracle import layers as OL
+    onet = OL.OFunctionalNet(NET_B_STATE, skip_connections=True, integration_steps=1)
+    OL.init_weights(onet.conv_layers, seed=1, bias_scale=0.02)
+    return None, onet
+
+
+def net_b_cpu_reference(onet, n_samples, steps, warmup):
+    from oracle import rollout as OR
+    from oracle import torch_cpu as OT
+    model = OT.KerasLikeModel(onet)
+    cores = OT.use_all_cores()
+    x0 = np.random.RandomState(0).standard_normal((n_samples,) + NET_B_STATE).astype(np.float32)
+    if warmup:
+        OR.functional_predict_timeseries(model.predict, x0, warmup)
+    t0 = time.perf_counter()
+    OR.functional_predict_timeseries(model.predict, x0, steps)
+    dt = time.perf_counter() - t0
+    return n_samples * steps / dt, cores, dt
+
+
+def run_net_b(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dlwp_b200 import _native as nat
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    prec = args.precision
+    dlwp, onet = build_net_b()
+    latband = world > 1 and args.parallel == 'latband'
+    B = args.batch * world if (latband and args.scaling == 'weak') else args.batch
+    x0 = np.random.RandomState(0 if latband else rank).standard_normal((B,) + NET_B_STATE).astype(np.float32)
+    xd = torch.from_numpy(x0).cuda()
+    series = torch.empty((K, B) + NET_B_STATE, dtype=torch.float32, device='cuda')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if latband:
+        from dlwp_b200.parallel import LatBandEngine, halo_summary
+        eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist)
+        net = eng.net
+        roll = lambda k, out, graph=True: eng.rollout_device(xd, k, out=out, use_graph=graph)
+    else:
+        eng = None
+        net = dlwp.model.engine(B)
+        assert net.max_batch >= B, 'batch does not fit the plan'
+        roll = lambda k, out, graph=True: net.rollout_device(xd, k, use_graph=graph, out=out)
+    roll(W, series[:W], False)
+    roll(K, series)
+    barrier()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        clocks.mark()
+        e0.record()
+        roll(K, series)
+        e1.record()
+        barrier()
+        clocks.mark()
+    ms = e0.elapsed_time(e1)
+    launches = nat.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_forecasts = B if latband else B * world
+    value = n_forecasts * K / (ms * 1e-3)
+    verified = None
+    if latband:
+        vb, vk = 2, 3
+        vx = xd[:vb].contiguous()
+        vs = torch.full((vk, vb) + NET_B_STATE, float('nan'), device='cuda')
+        eng.rollout_device(vx, vk, out=vs)
+        vref = dlwp.model.engine(vb).rollout_device(vx, vk, use_graph=False)
+        torch.cuda.synchronize()
+        lo_, hi_ = eng.me.band
+        vflag = torch.tensor([1 if torch.equal(vs[:, :, :, lo_:hi_], vref[:, :, :, lo_:hi_]) else 0], device='cuda')
+        dist.all_reduce(vflag, op=dist.ReduceOp.MIN)
+        verified = bool(int(vflag.item()))
+    # end to end
+    Ke = min(K, args.e2e_steps)
+    if latband:
+        x0_pinned = torch.from_numpy(x0).pin_memory()
+        eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+        barrier()
+        t0 = time.perf_counter()
+        eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+        dt = time.perf_counter() - t0
+        rows = eng.me.band[1] - eng.me.band[0]
+        d2h = B * NET_B_STATE[0] * rows * NET_B_STATE[2] * 4
+        api = 'LatBandEngine.rollout_device + band_to_host (per-rank band)'
+    else:
+        x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
+        dlwp.predict_timeseries(x0_pinned, Ke)
+        barrier()
+        t0 = time.perf_counter()
+        y = dlwp.predict_timeseries(x0_pinned, Ke)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert y.shape == (Ke, B) + NET_B_STATE and np.isfinite(y[-1]).all()
+        del y
+        d2h = B * int(np.prod(NET_B_STATE)) * 4
+        api = 'DLWPFunctional.predict_timeseries(numpy)->numpy'
+    if world > 1:
+        t = torch.tensor([dt], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = measured_peaks()
+    tc = net.uses_tensor_cores()
+    s_act = 2 if (prec == 'bf16' and tc) else 4
+    timed = []
+    for i, op in enumerate(net.low.ops if not latband else [o for o, w in zip(net.low.ops, net.row_windows) if w is not None]):
+        if op['kind'] != nat.OP_CONV or latband:
+            continue
+        ms_i = net.profile_op(B, i, 5)
+        ob = net.low.buffers[op['dst']]
+        alg = s_act * B * ob['H'] * ob['W'] * (op['src_c'] + op['Cout']) + 4 * (op['kh'] * op['kw'] * op['src_c'] * op['Cout'] + op['Cout'])
+        timed.append({'kernel': 'conv_sw_kernel %d->%d %dx%d @%dx%d' % (op['src_c'], op['Cout'], op['kh'], op['kw'], ob['H'], ob['W']),
+                      'ms_per_launch': ms_i, 'algorithmic_bytes_per_launch': alg, 'achieved_gbs': alg / (ms_i * 1e-3) / 1e9,
+                      'useful_tflops': 2.0 * B * ob['H'] * ob['W'] * op['src_c'] * op['Cout'] * op['kh'] * op['kw'] / (ms_i * 1e-3) / 1e12})
+    step_bytes = NET_B_BYTES['bf16' if s_act == 2 else 'fp32'] * B
+    step_gbs = step_bytes / (ms / K * 1e-3) / 1e9 / (world if latband else 1)
+    roofline = None
+    if timed:
+        dom = max(timed, key=lambda r: r['ms_per_launch'])
+        roofline = {'kernel': dom['kernel'], 'bound': 'hbm', 'achieved': dom['achieved_gbs'], 'peak': peaks['hbm_gbs'],
+                    'unit': 'GB/s', 'frac': dom['achieved_gbs'] / peaks['hbm_gbs'], 'traffic': None,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peak_kind == 'measured' else 'fallback 6650 GB/s',
+                    'algorithmic_bytes_per_launch': dom['algorithmic_bytes_per_launch'], 'ms_per_launch': dom['ms_per_launch'],
+                    'math': ('tcgen05 bf16 x bf16 -> fp32 TMEM accumulators, one pass' if s_act == 2 else
+                             'tcgen05 f16 hi/lo split x3 -> fp32 TMEM accumulators') if tc else 'fp32 FFMA2',
+                    'layers': timed,
+                    'step': {'algorithmic_bytes': step_bytes, 'ms': ms / K, 'achieved_gbs': step_gbs,
+                             'frac': step_gbs / peaks['hbm_gbs'], 'useful_tflops': NET_B_FLOP * B / (ms / K * 1e-3) / 1e12}}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, cores, _ = net_b_cpu_reference(onet, 8, 2, 1)
+        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port',
+               'sample': '8 of %d samples x 2 steps (1 warm-up step), torch-CPU fp32 forward inside the reference rollout loop' % B}
+    config = {'workload': 'net_b_skip_unet_12x180x360_rollout (BASELINE.json configs[%d])' % (3 if latband else 2),
+              'batch_per_gpu': B / world if latband else B, 'global_batch': n_forecasts, 'state': list(NET_B_STATE),
+              'precision': prec, 'tensor_cores': bool(tc),
+              'parallelism': ('latband%d' % world) if latband else ('independent forecasts per GPU' if world > 1 else 'single GPU'),
+              'l2': 'per-step working set >> 126 MB L2 at this batch; no flush',
+              'timed_region': 'one CUDA-graph replay of %d steps, inputs resident in HBM' % K, 'e2e_steps': Ke}
+    if latband:
+        hs = halo_summary(eng.planners[min(1, world - 1)], B, NET_B_STATE[0], NET_B_STATE[2])
+        config.update({'bands': [list(p.band) for p in eng.planners], 'bands_equal_single_domain_bitwise': verified,
+                       'halo': {'rows_top_bottom': [hs['halo_rows_top'], hs['halo_rows_bottom']],
+                                'recv_bytes_per_step': hs['recv_bytes_per_iteration'],
+                                'link_time_us_at_770GBs': hs['recv_bytes_per_iteration'] / 2 / 770e9 * 1e6,
+                                'collective': 'one grouped NCCL SendRecv per step, overlapped with the interior rows of the next step'}})
+    line = {'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True,
+            'scaling': args.scaling if latband else 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if s_act == 2 else 'f32', 'data': 'synthetic', 'config': config,
+            'e2e': {'value': n_forecasts * Ke / dt, 'unit': 'forecast-steps/s',
+                    'h2d_bytes_per_step': B * int(np.prod(NET_B_STATE)) * 4 / Ke, 'd2h_bytes_per_step': d2h, 'api': api,
+                    'steps': Ke, 'seconds': dt},
+            'gpu_launches': launches, 'clocks': clocks.summary(), 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -487,9 +703,20 @@ def main():
     ap.add_argument('--math', default=os.environ.get('DLWP_MATH', 'tc'), choices=['tc', 'ffma'],
                     help='tc: tcgen05 tensor cores, fp16 hi/lo split x3 (fp32-level accuracy); ffma: fp32 FFMA2 kernels')
     ap.add_argument('--parallel', default='latband', choices=['latband', 'batch'],
-                    help='N>1: latitude bands + halo exchange (north star, strong scaling) or independent forecasts per GPU')
+                    help='N>1: latitude bands + halo exchange (north star) or independent forecasts per GPU')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='latitude bands: weak = --batch forecasts per GPU in flight (global batch grows with N), '
+                         'strong = --batch forecasts in total')
+    ap.add_argument('--workload', default='net_a', choices=['net_a', 'net_b'],
+                    help='net_a: BASELINE.json configs[1] (the headline); net_b: the skip U-Net of configs[2-3]')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'],
+                    help='tensor-core chain arithmetic: fp32-equivalent (fp16 hi/lo split x3) or plain bf16 (configs[2])')
     args = ap.parse_args()
     os.environ['DLWP_MATH'] = args.math
+    if args.precision == 'bf16':
+        os.environ['DLWP_PRECISION'] = 'bf16'
+    if args.workload == 'net_b' and args.batch == 256:
+        args.batch = 16
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -499,7 +726,9 @@ def main():
     if world == 1 and args.gpus > 1:
         raise SystemExit('launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d '
                          '--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ...' % (args.gpus, args.gpus))
-    if world > 1 and args.parallel == 'latband':
+    if args.workload == 'net_b':
+        run_net_b(args, rank, world, local_rank)
+    elif world > 1 and args.parallel == 'latband':
         run_latband(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)

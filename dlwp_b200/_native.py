@@ -17,6 +17,7 @@ IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
 BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2
 OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY, OP_LSTM = 0, 1, 2, 3, 4, 5
 RECURRENT_ACTIVATIONS = {'hard_sigmoid': 0, 'sigmoid': 1}
+PRECISION_FP32, PRECISION_BF16 = 0, 1
 ACTIVATIONS = {None: ACT_LINEAR, 'linear': ACT_LINEAR, 'tanh': ACT_TANH, 'relu': ACT_RELU}
 IMPLS = {'auto': IMPL_AUTO, 'direct': IMPL_DIRECT, 'ffma': IMPL_FFMA, 'ffma_tma': IMPL_FFMA_TMA, 'tc': IMPL_TC}
 
@@ -48,8 +49,9 @@ class BandInfo(ctypes.Structure):
 
 class PlanOptions(ctypes.Structure):
     """DlwpPlanOptions (include/dlwp_b200.h): all zeros = defaults; tc_taps_in_k = -1 leaves the choice to the planner."""
-    _fields_ = [(n, i32) for n in ('math', 'fuse', 'tc_generic', 'tc_bands', 'tc_no_tma', 'tc_taps_in_k', 'tc_debug')] + \
-               [('reserved', i32 * 9)]
+    _fields_ = [(n, i32) for n in ('math', 'fuse', 'tc_generic', 'tc_bands', 'tc_no_tma', 'tc_taps_in_k', 'tc_debug',
+                                   'precision', 'latband_spare_sms')] + \
+               [('reserved', i32 * 7)]
 
     def __init__(self, **kw):
         super(PlanOptions, self).__init__()

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libdlwp_b200.so')
-SOURCES = ['conv.cu', 'conv_tc.cu', 'conv_sw_net_a.cu', 'conv_sw_net_b.cu', 'conv_sw_net_basic.cu', 'conv_fused.cu',
+SOURCES = ['conv.cu', 'conv_tc.cu', 'conv_sw_net_a.cu', 'conv_sw_net_b.cu', 'conv_sw_net_basic.cu', 'conv_sw_bf16.cu', 'conv_fused.cu',
            'elementwise.cu', 'plan.cu', 'train.cu']
 HEADERS = ['internal.h', 'conv_tc.h', 'conv_sw.cuh', os.path.join('..', '..', 'include', 'dlwp_b200.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

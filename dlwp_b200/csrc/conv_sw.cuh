@@ -14,6 +14,7 @@
 // image (8 pixels x 16 B core matrices; validated by scripts/umma_probe.cu on B200).
 #pragma once
 #define DLWP_CONV_TU  // mbarrier helpers of internal.h
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 // Device-side diagnostic flags: bit 0 = an mbarrier wait timed out, bit 1 = a value left the fp16 split's range (or is
@@ -153,6 +154,23 @@ __device__ __forceinline__ void p_pack8(const float (&v)[8], uint4& h, uint4& l)
         lp[k] = pack_half2(v[2 * k] - f.x, v[2 * k + 1] - f.y);
     }
 }
+// bf16 mode (DlwpPlanOptions.precision = 1): one plane per 8-channel chunk, round-to-nearest-even bf16
+__device__ __forceinline__ void p_pack8_bf16(const float (&v)[8], uint4& h) {
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        hp[k] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+}
+__device__ __forceinline__ void p_unpack8_bf16(const uint4& h, float (&v)[8]) {
+    const uint32_t* hp = reinterpret_cast<const uint32_t*>(&h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __uint_as_float(hp[k] << 16);
+        v[2 * k + 1] = __uint_as_float(hp[k] & 0xffff0000u);
+    }
+}
 __device__ __forceinline__ float amax8(const float (&o)[8]) {
     return fmaxf(fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))),
                  fmaxf(fmaxf(fabsf(o[4]), fabsf(o[5])), fmaxf(fabsf(o[6]), fabsf(o[7]))));
@@ -231,6 +249,7 @@ struct SwParams {
     const __half* bimg;
     const __half* xp;
     int in_plane0, in_planes_total, out_plane0;  // channel windows of the source / destination P images
+    int bf16;     // 1: plain bf16 operands, one plane per 8-channel chunk, one MMA pass (BASELINE.json configs[2])
     int use_tma;  // 1: the producer stages rows with tensor-map loads (one per row and unit) instead of per-plane bulk copies
     int debug;    // TcOptions::debug
     float* y32; long long ys_n, ys_c, ys_h;
@@ -307,6 +326,7 @@ __host__ __device__ __forceinline__ bool sw_next(const P& p, SwIter& it, SwUnit&
 }
 
 constexpr uint32_t SW_IDESC = (1u << 4) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128; N per MMA
+constexpr uint32_t SW_IDESC_BF16 = SW_IDESC | (1u << 7) | (1u << 10);     // A and B formats = bf16
 
 // Position of a row in the accumulator ring.  Rows are numbered CTA-wide (phantom rows included); row G sits in residue
 // class m = G % D at ring position q = (G / D) % RING, i.e. slot m * RING + q, and lap = (G / (D * RING)) & 1 is the phase
@@ -332,19 +352,20 @@ struct SwRing {
 // One input row's MMAs with everything but the stage address folded at compile time (POS = ring position of the window's
 // lowest row).  Runs of vertical taps: cut every FOLD taps, at the ring's end, and before tap 0 in the very first MMA (the
 // new row's accumulator is overwritten, the others accumulate).
-template <int KH, int NCOLS, int KS, int RING, int FOLD, int POS, bool HINTS = true>
+template <int KH, int NCOLS, int KS, int RING, int FOLD, int POS, bool HINTS = true, int NPASS = 3>
 __device__ __forceinline__ void sw_issue_row_pos(bool leader, uint32_t tres, uint32_t sbase16, uint32_t pitch16,
                                                  uint32_t desc_hi, uint32_t bbase, const TcKStep* kst) {
     constexpr uint32_t bblock16 = 2u * KH * NCOLS;
+    constexpr uint32_t IDESC0 = NPASS == 1 ? SW_IDESC_BF16 : SW_IDESC;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const uint32_t a_lo32 = kst[ks].a_off + sbase16;
         const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
         const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < NPASS; ++pass) {
             const uint64_t ad = pass < 2 ? ad_hi : ad_lo;
-            const uint32_t bb = bbase + (uint32_t)(2 * ks + (pass == 1 ? 1 : 0)) * bblock16;
+            const uint32_t bb = bbase + (NPASS == 1 ? (uint32_t)ks : (uint32_t)(2 * ks + (pass == 1 ? 1 : 0))) * bblock16;
             const bool fresh = ks == 0 && pass == 0;
             int run_tb = KH - 1;
 #pragma unroll
@@ -355,8 +376,8 @@ __device__ __forceinline__ void sw_issue_row_pos(bool leader, uint32_t tres, uin
                 if (end) {
                     const uint32_t dcol = tres + (uint32_t)(((POS + (KH - 1 - run_tb)) % RING) * NCOLS);
                     const uint64_t bd = ((uint64_t)desc_hi << 32) | (bb + (uint32_t)((KH - 1 - run_tb) * NCOLS));
-                    const uint32_t idesc = SW_IDESC | ((uint32_t)((len * NCOLS) >> 3) << 17);
-                    const bool first = pass != 1 && run_tb == KH - 1, last = pass != 0 && t == 0;
+                    const uint32_t idesc = IDESC0 | ((uint32_t)((len * NCOLS) >> 3) << 17);
+                    const bool first = pass != 1 && run_tb == KH - 1, last = (NPASS == 1 || pass != 0) && t == 0;
                     const uint32_t acc = (fresh && run_tb == 0) ? 0u : 1u;
                     if (leader) {
                         // (HINTS off: two warps issue into the same tensor core -- another warp's MMA may sit between a
@@ -384,7 +405,8 @@ __device__ __forceinline__ void sw_issue_row_static(int pos_lo, bool leader, uin
 #define SW_POS_CASE(P_)                                                                                          \
     case P_:                                                                                                     \
         if constexpr (P_ < RING)                                                                                 \
-            sw_issue_row_pos<KH, NCOLS, KS, RING, FOLD, P_>(leader, tres, sbase16, pitch16, desc_hi, bbase, kst); \
+            sw_issue_row_pos<KH, NCOLS, KS, RING, FOLD, P_, true, ST::BF16 ? 1 : 3>(leader, tres, sbase16, pitch16,  \
+                                                                                     desc_hi, bbase, kst);         \
         break;
     switch (pos_lo) {
         SW_POS_CASE(0) SW_POS_CASE(1) SW_POS_CASE(2) SW_POS_CASE(3) SW_POS_CASE(4) SW_POS_CASE(5) SW_POS_CASE(6) SW_POS_CASE(7)
@@ -402,13 +424,15 @@ __device__ __forceinline__ void sw_issue_row_static(int pos_lo, bool leader, uin
 // instance serves any layer; the example nets' layers get instances with everything folded (conv_sw_net_*.cu), which
 // matters because the single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's
 // critical path.
-template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int FOLD_ = 0>
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int FOLD_ = 0, int BF16_ = 0>
 struct SwStatic {
+    static constexpr int BF16 = BF16_;  // 1: bf16 operands / images, one MMA pass
     static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
     static constexpr int FULL = FULL_;  // 1: Cout == CBLK * NC, no partial filter block
     static constexpr int FOLD = FOLD_;  // vertical taps per MMA (0: SwParams::fold)
 };
 using SwGeneric = SwStatic<0, 0, 0, 0, -1, 0>;
+using SwGenericBf16 = SwStatic<0, 0, 0, 0, -1, 0, 0, 0, 1>;
 
 // accumulator ring: rows of one residue class mod D are neighbours; NACC is a multiple of D
 __host__ __device__ __forceinline__ int sw_nacc(int ncols, int d) {
@@ -607,10 +631,10 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                             const uint32_t a_lo32 = p.kst[ks].a_off + sbase16;  // (LBO field | offset) precomputed on the host
                             const uint64_t ad_hi = ((uint64_t)desc_hi << 32) | a_lo32;
                             const uint64_t ad_lo = ((uint64_t)desc_hi << 32) | (a_lo32 + pitch16);
-                            const uint32_t bk = bbase + (uint32_t)(2 * ks) * bblock16;
-                            // pass 0: hi * hi, pass 1: hi * lo (same A view: collector), pass 2: lo * hi
+                            const uint32_t bk = bbase + (uint32_t)(ST::BF16 ? ks : 2 * ks) * bblock16;
+                            // pass 0: hi * hi, pass 1: hi * lo (same A view: collector), pass 2: lo * hi; bf16: one pass
 #pragma unroll
-                            for (int pass = 0; pass < 3; ++pass) {
+                            for (int pass = 0; pass < (ST::BF16 ? 1 : 3); ++pass) {
                                 const uint64_t ad = pass < 2 ? ad_hi : ad_lo;
                                 const uint32_t bb = bk + (pass == 1 ? bblock16 : 0u);
                                 const bool fresh = ks == 0 && pass == 0;  // tap 0 overwrites the new row's accumulator
@@ -621,10 +645,11 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                                     if (fresh && len > tb && tb > 0) len = tb;        // ... and before tap 0 of a new row
                                     const uint32_t ncols = (uint32_t)(len * NCOLS);
                                     const uint64_t bd = ((uint64_t)desc_hi << 32) | (bb + (uint32_t)((KH - 1 - tb) * NCOLS));
-                                    const bool first = pass != 1 && tb == KH - 1, last = pass != 0 && len > tb;
+                                    const bool first = pass != 1 && tb == KH - 1, last = (ST::BF16 || pass != 0) && len > tb;
                                     if (leader)
                                         umma_f16_dyn(first ? (last ? 0 : 1) : (last ? 3 : 2), tres + (uint32_t)(pos * NCOLS), ad, bd,
-                                                     SW_IDESC | ((ncols >> 3) << 17), (fresh && tb == 0) ? 0u : 1u);
+                                                     (ST::BF16 ? SW_IDESC_BF16 : SW_IDESC) | ((ncols >> 3) << 17),
+                                                     (fresh && tb == 0) ? 0u : 1u);
                                     tb -= len;
                                     pos += len;
                                     if (pos == RING) pos = 0;
@@ -801,7 +826,14 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                         }
                         const float am = amax8(o);
                         amax_t = fmaxf(amax_t, am);
-                        if (has_yp) {
+                        if (has_yp && ST::BF16) {
+                            if (!(am <= 3.0e38f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);    // NaN / inf
+                            uint4 vb;
+                            p_pack8_bf16(o, vb);
+                            __stcs(row_hi, vb);
+                            if (halo_r) __stcs(row_hi + p.W, vb);
+                            if (halo_l) __stcs(row_hi - p.W, vb);
+                        } else if (has_yp) {
                             // the bound behind 2^e_out makes this unreachable for finite data; NaN / inf land here
                             if (!(am * sout <= 65504.f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
                             float v[8];
@@ -822,7 +854,7 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                             }
                         }
                     }
-                    if (has_yp) row_hi += 2 * plane_stride;
+                    if (has_yp) row_hi += (ST::BF16 ? 1 : 2) * plane_stride;
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[slot]);
@@ -861,10 +893,15 @@ struct SwFolded {
     int KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL;   // the kernel folds min(KH, 256 / NCOLS) vertical taps per MMA
     SwLaunchFn fn;
     const char* what;
+    int BF16;   // 1: the bf16 flavour of the instance
 };
 #define SW_FOLDED_ENTRY(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
     {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                          \
-     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT}
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT, 0}
+#define SW_FOLDED_ENTRY_BF16(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT)                                      \
+    {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                                                                    \
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH), 1>>, \
+     WHAT, 1}
 
 static inline int sw_tu_flags_read_clear() {
     int v = 0, zero = 0;
@@ -889,5 +926,11 @@ int sw_flags_fused();
 const SwFolded* sw_folded_net_a(int* n);      // conv_sw_net_a.cu: the 2-layer benchmark net (BASELINE.json configs[0-1])
 const SwFolded* sw_folded_net_b(int* n);      // conv_sw_net_b.cu: skip U-Net of examples/train_functional.py:248-275
 const SwFolded* sw_folded_net_basic(int* n);  // conv_sw_net_basic.cu: examples/train.py:159-219 / train_functional.py:222-245
+const SwFolded* sw_folded_bf16(int* n);       // conv_sw_bf16.cu: Net B's layers in plain bf16 (BASELINE.json configs[2])
+int sw_flags_bf16();
+void sw_counters_bf16(unsigned long long* acc12);
+// generic bf16 instances (conv_sw_bf16.cu); false: no instance for this (KH, KW_eff, NC)
+bool sw_launch_generic_bf16(int kh, int kw_eff, int nc, const SwParams& p, const CUtensorMap& map_full,
+                            const CUtensorMap& map_pair, int grid, size_t smem, cudaStream_t stream);
 
 }  // namespace dlwp

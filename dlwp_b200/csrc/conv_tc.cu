@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict
                                                          int H, int W, int wpad, long long xs_n, long long xs_c,
                                                          long long xs_h, int row0, int rows, TcPackScale ps) {
     __shared__ float s_scale;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && ps.bf16) s_scale = 1.f;
+    if (threadIdx.x == 0 && !ps.bf16) {
         int e;
         if (ps.fresh) {
             const float a = *ps.amax;
@@ -80,24 +81,100 @@ __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict
         }
         const float a = amax8(v);
         am = fmaxf(am, a);
+        uint4* out = reinterpret_cast<uint4*>(yp);
+        const long long Ha = H + 2 * TC_HPAD;
+        if (ps.bf16) {
+            if (!(a <= 3.0e38f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
+            uint4 vb;
+            p_pack8_bf16(v, vb);
+            out[(((long long)n * C8 + c8) * Ha + y + TC_HPAD) * Wp + xq] = vb;
+            continue;
+        }
         if (!(a * scale <= 65504.f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);  // rows joining an image with a smaller bound; NaN
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= scale;
         uint4 vh, vl;
         p_pack8(v, vh, vl);
-        uint4* out = reinterpret_cast<uint4*>(yp);
-        const long long Ha = H + 2 * TC_HPAD;
         out[(((long long)n * 2 * C8 + 2 * c8) * Ha + y + TC_HPAD) * Wp + xq] = vh;
         out[(((long long)n * 2 * C8 + 2 * c8 + 1) * Ha + y + TC_HPAD) * Wp + xq] = vl;
     }
-    if (!ps.fresh) amax_publish(ps.amax, am, threadIdx.x & 31);
+    if (!ps.fresh && !ps.bf16) amax_publish(ps.amax, am, threadIdx.x & 31);
+}
+
+// Halo rows received from the latitude-band neighbours (two contiguous (N, C, rows, W) staging buffers) -> rows
+// [row0[k], row0[k] + rows[k]) of a P image another kernel produced: the image keeps its exponent *ps.e, the packed rows'
+// max|x| is max-ed into *ps.amax.  One launch for both neighbours.
+struct HaloPackParams {
+    const float* src[2];
+    int row0[2], rows[2];
+};
+__global__ void __launch_bounds__(256) pack_halo_kernel(HaloPackParams hp, __half* __restrict__ yp, int N, int C, int H, int W,
+                                                        int wpad, TcPackScale ps) {
+    const float scale = ps.bf16 ? 1.f : exp2i(*ps.e);
+    const int Wp = W + 2 * wpad, C8 = (C + 7) / 8;
+    const long long per0 = (long long)N * C8 * hp.rows[0] * Wp;
+    const long long total = per0 + (long long)N * C8 * hp.rows[1] * Wp;
+    float am = 0.f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = idx >= per0 ? 1 : 0;
+        long long t = idx - (k ? per0 : 0);
+        const int xq = (int)(t % Wp);
+        t /= Wp;
+        const int yl = (int)(t % hp.rows[k]);
+        t /= hp.rows[k];
+        const int c8 = (int)(t % C8);
+        const int n = (int)(t / C8);
+        const int gx = wrap_index(xq - wpad, W);
+        const float* s = hp.src[k] + ((long long)n * C * hp.rows[k] + yl) * W + gx;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            v[e] = c < C ? s[(long long)c * hp.rows[k] * W] : 0.f;
+        }
+        const float a = amax8(v);
+        am = fmaxf(am, a);
+        uint4* out = reinterpret_cast<uint4*>(yp);
+        const long long Ha = H + 2 * TC_HPAD;
+        const int y = hp.row0[k] + yl;
+        if (ps.bf16) {
+            uint4 vb;
+            p_pack8_bf16(v, vb);
+            out[(((long long)n * C8 + c8) * Ha + y + TC_HPAD) * Wp + xq] = vb;
+            continue;
+        }
+        if (!(a * scale <= 65504.f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= scale;
+        uint4 vh, vl;
+        p_pack8(v, vh, vl);
+        out[(((long long)n * 2 * C8 + 2 * c8) * Ha + y + TC_HPAD) * Wp + xq] = vh;
+        out[(((long long)n * 2 * C8 + 2 * c8 + 1) * Ha + y + TC_HPAD) * Wp + xq] = vl;
+    }
+    if (!ps.bf16) amax_publish(ps.amax, am, threadIdx.x & 31);
+}
+
+int tc_pack_halo(const float* const src[2], const int row0[2], const int rows[2], __half* xp, int N, int C, int H, int W,
+                 int wpad, cudaStream_t stream, const TcPackScale& ps) {
+    DLWP_REQUIRE(ps.bf16 || (ps.e && ps.amax), DLWP_EINVAL, "pack_halo needs the image's scale words");
+    HaloPackParams hp;
+    long long total = 0;
+    for (int k = 0; k < 2; ++k) {
+        hp.src[k] = src[k]; hp.row0[k] = row0[k]; hp.rows[k] = src[k] ? rows[k] : 0;
+        total += (long long)N * ((C + 7) / 8) * hp.rows[k] * (W + 2 * wpad);
+    }
+    if (total <= 0) return 0;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    pack_halo_kernel<<<blocks, 256, 0, stream>>>(hp, xp, N, C, H, W, wpad, ps);
+    return after_launch("pack_halo_kernel");
 }
 
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps) {
     if (row0 == 0 && row1 == 0) row1 = H;
-    DLWP_REQUIRE(ps.e && ps.amax, DLWP_EINVAL, "pack_state needs the image's scale words");
-    if (ps.fresh) {
+    DLWP_REQUIRE(ps.bf16 || (ps.e && ps.amax), DLWP_EINVAL, "pack_state needs the image's scale words");
+    if (ps.fresh && !ps.bf16) {
         const int a0 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? 0 : ps.amax_row0;
         const int a1 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? H : ps.amax_row1;
         const long long all = (long long)N * C * (a1 - a0) * W;
@@ -119,12 +196,13 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
 // columns are written with the interior.  HBM-bound byte movers: 32 B read (128 B for the pooling) + 32 B written per
 // thread, coalesced along x.  The values keep the source image's exponent (max of exact hi + lo sums is scale invariant).
 // ===================================================================================================================
-template <int KIND>  // 0 copy, 1 maxpool 2x2 stride 2 (floor), 2 nearest upsample x2
+template <int KIND, int BF16>  // KIND: 0 copy, 1 maxpool 2x2 stride 2 (floor), 2 nearest upsample x2; BF16: one plane per chunk
 __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int C8, int Hs,
                                                   int Ws, int wpad_s, int src_plane0, int src_planes_total, int Hd, int Wd,
                                                   int wpad_d, int dst_plane0, int dst_planes_total, int row0, int rows,
                                                   TcScale sc) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // forward the exponent and the measured amax with the data
+    constexpr int PPC = BF16 ? 1 : 2;
+    if (!BF16 && blockIdx.x == 0 && threadIdx.x == 0) {  // forward the exponent and the measured amax with the data
         if (sc.e_out) *sc.e_out = sc.e_in ? *sc.e_in : sc.e_in_const;
         if (sc.amax_zero) *sc.amax_zero = 0.f;
         if (sc.amax_out) {
@@ -142,15 +220,15 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
         t /= rows;
         const int c8 = (int)(t % C8);
         const int n = (int)(t / C8);
-        const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + 2 * c8) * Has + TC_HPAD) * Wps + wpad_s;
-        const uint4* sl = sh + Has * Wps;
-        uint4 vh, vl;
+        const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + PPC * c8) * Has + TC_HPAD) * Wps + wpad_s;
+        const uint4* sl = sh + Has * Wps;   // fp16 split only
+        uint4 vh, vl = make_uint4(0, 0, 0, 0);
         if (KIND == 0) {
             vh = sh[(long long)y * Wps + x];
-            vl = sl[(long long)y * Wps + x];
+            if (!BF16) vl = sl[(long long)y * Wps + x];
         } else if (KIND == 2) {
             vh = sh[(long long)(y >> 1) * Wps + (x >> 1)];
-            vl = sl[(long long)(y >> 1) * Wps + (x >> 1)];
+            if (!BF16) vl = sl[(long long)(y >> 1) * Wps + (x >> 1)];
         } else {
             float m[8];
 #pragma unroll
@@ -159,25 +237,27 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
                 for (int dx = 0; dx < 2; ++dx) {
                     const long long o = (long long)(2 * y + dy) * Wps + 2 * x + dx;
                     float v[8];
-                    p_unpack8(sh[o], sl[o], v);
+                    if (BF16) p_unpack8_bf16(sh[o], v);
+                    else p_unpack8(sh[o], sl[o], v);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) m[e] = (dy | dx) ? fmaxf(m[e], v[e]) : v[e];
                 }
-            p_pack8(m, vh, vl);
+            if (BF16) p_pack8_bf16(m, vh);    // exact: the maximum of bf16 values is one of them
+            else p_pack8(m, vh, vl);
         }
-        uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + 2 * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + x;
+        uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + PPC * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + x;
         uint4* dl = dh + Had * Wpd;
         dh[0] = vh;
-        dl[0] = vl;
-        if (x < wpad_d) { dh[Wd] = vh; dl[Wd] = vl; }
-        if (x >= Wd - wpad_d) { dh[-Wd] = vh; dl[-Wd] = vl; }
+        if (!BF16) dl[0] = vl;
+        if (x < wpad_d) { dh[Wd] = vh; if (!BF16) dl[Wd] = vl; }
+        if (x >= Wd - wpad_d) { dh[-Wd] = vh; if (!BF16) dl[-Wd] = vl; }
     }
 }
 
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
                  int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream, int row_begin,
-                 int row_end, const TcScale& sc) {
-    const int C8 = planes / 2;
+                 int row_end, const TcScale& sc, int bf16) {
+    const int C8 = bf16 ? planes : planes / 2;
     int Hd = Hs, Wd = Ws;
     if (kind == DLWP_OP_MAXPOOL) { Hd = Hs / 2; Wd = Ws / 2; }
     if (kind == DLWP_OP_UPSAMPLE) { Hd = Hs * 2; Wd = Ws * 2; }
@@ -188,12 +268,13 @@ int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, in
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
-    if (kind == DLWP_OP_MAXPOOL)
-        p_ew_kernel<1><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows, sc);
-    else if (kind == DLWP_OP_UPSAMPLE)
-        p_ew_kernel<2><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows, sc);
-    else
-        p_ew_kernel<0><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, wpad_d, dst_plane0, dst_planes_total, row0, rows, sc);
+#define DLWP_EW_LAUNCH(K_, B_)                                                                                              \
+    p_ew_kernel<K_, B_><<<blocks, 256, 0, stream>>>(s4, d4, N, C8, Hs, Ws, wpad_s, src_plane0, src_planes_total, Hd, Wd, \
+                                                    wpad_d, dst_plane0, dst_planes_total, row0, rows, sc)
+    if (kind == DLWP_OP_MAXPOOL) { if (bf16) DLWP_EW_LAUNCH(1, 1); else DLWP_EW_LAUNCH(1, 0); }
+    else if (kind == DLWP_OP_UPSAMPLE) { if (bf16) DLWP_EW_LAUNCH(2, 1); else DLWP_EW_LAUNCH(2, 0); }
+    else { if (bf16) DLWP_EW_LAUNCH(0, 1); else DLWP_EW_LAUNCH(0, 0); }
+#undef DLWP_EW_LAUNCH
     return after_launch("p_ew_kernel");
 }
 
@@ -211,7 +292,8 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L, const TcOptions& opt) {
     L->wpad = halo_w / 2;
     L->Wp = d.W + halo_w;
     L->C8 = cdiv(d.Cin, 8);
-    L->planes = 2 * L->C8;
+    L->ppc = opt.bf16 ? 1 : 2;
+    L->planes = L->ppc * L->C8;
     if (L->planes > 32) return -1;  // the bulk-copy producer issues at most two copies per lane and row
     L->CBLK = cdiv(d.Cout, 8);
     // Many filters: N = filters is wide enough, fold the horizontal taps into K (shifted A views, no shifted sum in the
@@ -240,7 +322,7 @@ int tc_plan_layer(const DlwpConvDesc& d, TcLayer* L, const TcOptions& opt) {
     if (L->KS > TC_MAX_KSTEPS) return -1;
     L->rowpitch = 128 * 16;
     L->stage_stride = (uint32_t)L->planes * L->rowpitch;
-    L->b_bytes = (uint32_t)(L->KS * d.kh * 2) * (uint32_t)(2 * L->NCOLS * 16);
+    L->b_bytes = (uint32_t)(L->KS * d.kh * L->ppc) * (uint32_t)(2 * L->NCOLS * 16);
     const size_t mailbox = L->kw_eff > 1 ? (size_t)TC_SETS * 2 * L->CBLK * 4 * halo_w * (L->kw_eff - 1) * 8 * 4 : 0;
     const size_t fixed = (size_t)L->b_bytes + mailbox + (size_t)L->CBLK * 32 + (2 * SW_MAX_STAGES + 2 * SW_MAX_ACC) * 8 + 128 + 1024;
     const size_t budget = 227 * 1024;
@@ -279,8 +361,11 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
         else units.push_back({c8, -1, false});
     }
     if (units.size() & 1) units.push_back({units.back().c8, units.back().j, true});
+    const bool bf16 = L.ppc == 1;
     auto aoff = [&](const U& u) {
-        // the zero unit (zero weights) views the lo plane of the last real unit: finite data, positive LBO
+        // the zero unit (zero weights) views finite data at a positive LBO: the lo plane of the last real unit, or (bf16:
+        // no lo plane) the same plane one pixel further (stages are zero-initialised past the row's end)
+        if (bf16) return (long long)u.c8 * L.rowpitch + (long long)(u.j > 0 ? u.j : 0) * d.dil_w * 16 + (u.zero ? 16 : 0);
         return (long long)(2 * u.c8 + (u.zero ? 1 : 0)) * L.rowpitch + (long long)(u.j > 0 ? u.j : 0) * d.dil_w * 16;
     };
     // scale: exact power of two from max|w|; the output bound's coefficient max_co sum|w[..., co]| in true units
@@ -293,7 +378,7 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
         wmax = std::max(wmax, a);
         l1[i % d.Cout] += a;
     }
-    const int e_w = tc_exp_for_bound(wmax);
+    const int e_w = bf16 ? 0 : tc_exp_for_bound(wmax);   // bf16 has fp32's range: no scaling
     const float wscale = ldexpf(1.f, e_w);
     if (ws) {
         ws->e_w = e_w;
@@ -303,7 +388,7 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
     }
     const size_t unit = (size_t)d.kh * L.NCOLS * 8;  // fp16 elements of one 8-channel unit of a (ks, hi|lo) block
     const size_t block = 2 * unit;
-    img->assign((size_t)L.KS * 2 * block, __float2half(0.f));
+    img->assign((size_t)L.KS * L.ppc * block, __float2half(0.f));
     for (int ks = 0; ks < L.KS; ++ks) {
         const U& u0 = units[2 * ks];
         const U& u1 = units[2 * ks + 1];
@@ -316,7 +401,7 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
             for (int half = 0; half < 2; ++half) {
                 const U& u = half ? u1 : u0;
                 if (u.zero) continue;
-                const size_t bh = ((size_t)ks * 2 + 0) * block + (size_t)half * unit + (size_t)(d.kh - 1 - i) * L.NCOLS * 8;
+                const size_t bh = ((size_t)ks * L.ppc + 0) * block + (size_t)half * unit + (size_t)(d.kh - 1 - i) * L.NCOLS * 8;
                 const size_t bl = ((size_t)ks * 2 + 1) * block + (size_t)half * unit + (size_t)(d.kh - 1 - i) * L.NCOLS * 8;
                 for (int cb = 0; cb < L.CBLK; ++cb)
                     for (int j = (u.j >= 0 ? u.j : 0); j < (u.j >= 0 ? u.j + 1 : d.kw); ++j)
@@ -328,6 +413,11 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
                                 const int c = u.c8 * 8 + e;
                                 if (c >= d.Cin) continue;
                                 const float v = w_host[(((size_t)i * d.kw + j) * d.Cin + c) * d.Cout + co] * wscale;
+                                if (bf16) {   // the image is a bag of 16-bit words: store the bf16 bit pattern
+                                    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+                                    memcpy(&(*img)[bh + (size_t)ncol * 8 + e], &b, 2);
+                                    continue;
+                                }
                                 const __half h = __float2half_rn(v);
                                 (*img)[bh + (size_t)ncol * 8 + e] = h;
                                 (*img)[bl + (size_t)ncol * 8 + e] = __float2half_rn(v - __half2float(h));
@@ -365,13 +455,14 @@ static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, in
 
 static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int nc, int out_mode) {
     const int full = (d.Cout == L.CBLK * nc) ? 1 : 0;
+    const int bf16 = L.ppc == 1 ? 1 : 0;
     typedef const SwFolded* (*TableFn)(int*);
-    const TableFn tables[] = {sw_folded_net_a, sw_folded_net_b, sw_folded_net_basic};
+    const TableFn tables[] = {sw_folded_net_a, sw_folded_net_b, sw_folded_net_basic, sw_folded_bf16};
     for (TableFn t : tables) {
         int n = 0;
         const SwFolded* f = t(&n);
         for (int i = 0; i < n; ++i)
-            if (f[i].KH == d.kh && f[i].KWE == L.kw_eff && f[i].NC == nc && f[i].NCOLS == L.NCOLS && f[i].KS == L.KS &&
+            if (f[i].BF16 == bf16 && f[i].KH == d.kh && f[i].KWE == L.kw_eff && f[i].NC == nc && f[i].NCOLS == L.NCOLS && f[i].KS == L.KS &&
                 f[i].D == d.dil_w && f[i].CBLK == L.CBLK && f[i].ACT == d.act && f[i].OUT == out_mode && f[i].FULL == full)
                 return &f[i];
     }
@@ -391,7 +482,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     if (!(d.row_begin == 0 && d.row_end == 0) && d.row_end <= d.row_begin) return 0;  // empty latitude window: nothing to do
     SwParams p;
     memset(&p, 0, sizeof(p));
-    const int grid = sw_unit_geometry(d, L, g_tc_sms, opt.bands, &p);
+    const int grid = sw_unit_geometry(d, L, opt.max_ctas > 0 ? std::min(g_tc_sms, opt.max_ctas) : g_tc_sms, opt.bands, &p);
     p.Cout = d.Cout; p.NCOLS = L.NCOLS; p.CBLK = L.CBLK; p.CSTRIDE = L.CSTRIDE; p.XL = (L.kw_eff - 1) * d.dil_w;
     p.KS = L.KS; p.NS = L.NS; p.NACC = L.NACC; p.fold = L.fold;
     p.planes_in = L.planes;
@@ -399,6 +490,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.idesc = (1u << 4) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128; N is set per MMA run
     p.act = d.act; p.bias = bias; p.bimg = bimg; p.xp = xp;
     p.debug = opt.debug;
+    p.bf16 = L.ppc == 1 ? 1 : 0;
     p.in_plane0 = win.in_plane0; p.in_planes_total = win.in_planes_total ? win.in_planes_total : L.planes;
     p.out_plane0 = win.out_plane0;
     p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
@@ -429,7 +521,10 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
     const SwFolded* f = opt.generic ? nullptr : find_folded(d, L, nc, out_mode);
     if (f) f->fn(p, map_full, map_pair, grid, L.smem, stream);
-    else if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
+    else if (p.bf16) {
+        DLWP_REQUIRE(sw_launch_generic_bf16(d.kh, L.kw_eff, nc, p, map_full, map_pair, grid, L.smem, stream), DLWP_ESHAPE,
+                     "no bf16 kernel instance for this layer");
+    } else if (d.kh == 3 && L.kw_eff == 1) sw_launch_one<3, 1, 8, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
     else if (d.kh == 5 && L.kw_eff == 1) sw_launch_one<5, 1, 8, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
     else if (d.kh == 3 && nc == 8) sw_launch_one<3, 3, 8, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
     else if (d.kh == 3) sw_launch_one<3, 3, 6, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
@@ -441,7 +536,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
 size_t tc_p_bytes(int N, int planes, int H, int Wp) { return (size_t)N * planes * (H + 2 * TC_HPAD) * Wp * 16; }
 
 int tc_debug_flags() {
-    const int parts[] = {sw_tu_flags_read_clear(), sw_flags_net_a(), sw_flags_net_b(), sw_flags_net_basic(), sw_flags_fused()};
+    const int parts[] = {sw_tu_flags_read_clear(), sw_flags_net_a(), sw_flags_net_b(), sw_flags_net_basic(), sw_flags_fused(),
+                         sw_flags_bf16()};
     int v = 0;
     for (int p : parts) {
         if (p < 0) return -1;
@@ -586,6 +682,7 @@ extern "C" int dlwp_debug_counters(int64_t* out, int32_t n) {
     sw_counters_net_b(acc);
     sw_counters_net_basic(acc);
     sw_counters_fused(acc);
+    sw_counters_bf16(acc);
     for (int i = 0; i < 12 && i < n; ++i) out[i] = (int64_t)acc[i];
     return 0;
 }

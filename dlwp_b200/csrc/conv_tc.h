@@ -64,6 +64,9 @@ struct TcOptions {
     int no_tma = 0;      // 1: per-plane bulk copies instead of tensor-map row loads
     int taps_in_k = -1;  // -1: planner's choice
     int debug = 0;       // 1: epilogue only waits/arrives, 2: issuer only commits (bottleneck triage; wrong results)
+    int bf16 = 0;        // 1: plain bf16 images / weights, one MMA pass (DlwpPlanOptions.precision = 1)
+    int max_ctas = 0;    // > 0: launch at most this many persistent CTAs (the latitude-band rollout leaves a few SMs to the
+                         // halo exchange that runs beside the interior rows of the next iteration)
 };
 
 struct TcKStep {
@@ -76,7 +79,8 @@ struct TcKStep {
 // one TMEM accumulator per output row in flight).
 struct TcLayer {
     int wpad, Wp;          // periodic halo columns per side of the INPUT image, padded width
-    int C8, planes;        // 8-channel chunks of the input, planes = 2 * C8 (hi, lo)
+    int C8, planes;        // 8-channel chunks of the input, planes = ppc * C8
+    int ppc;               // planes per chunk: 2 (fp16 hi, lo) or 1 (bf16)
     int CBLK, CSTRIDE, NCOLS;  // 8-filter blocks, TMEM columns per horizontal tap, MMA N
     int S;                 // valid outputs per strip: 128 - (kw-1)*dil
     int taps_in_k, kw_eff; // horizontal taps folded into K (shifted A views) -> the epilogue sees a 1-tap layer
@@ -109,7 +113,7 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
 // sc.e_in -> sc.e_out and sc.amax_in -> sc.amax_out are forwarded by the kernel (null pointers: nothing to forward).
 int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, int Hs, int Ws, int wpad_s, int src_plane0,
                  int src_planes_total, int wpad_d, int dst_plane0, int dst_planes_total, cudaStream_t stream,
-                 int row_begin, int row_end, const TcScale& sc);  // destination rows [row_begin, row_end); 0,0 = all
+                 int row_begin, int row_end, const TcScale& sc, int bf16 = 0);  // destination rows [row_begin, row_end); 0,0 = all
 // fp32 (N,C,H,W) -> P image, rows [row0, row1) (0,0 = all).  fresh: measure max|x| over rows [amax_row0, amax_row1) into
 // *amax (which must be zero), derive the image's exponent from it and publish it in *e; otherwise the image keeps the
 // exponent in *e (rows that join an image another kernel produced, e.g. halo rows received from a neighbour) and the
@@ -120,9 +124,14 @@ struct TcPackScale {
     float* amax_zero = nullptr;
     int fresh = 1;
     int amax_row0 = 0, amax_row1 = 0;  // fresh: rows whose max|x| defines the exponent (0,0 = all H rows)
+    int bf16 = 0;                      // 1: one bf16 plane per chunk, no exponent (e / amax unused)
 };
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps);
+// Latitude bands: halo rows received as fp32 (two contiguous (N, C, rows[k], W) staging buffers, null = none) -> rows
+// [row0[k], row0[k] + rows[k]) of an existing P image (its exponent *ps.e is kept).  One launch for both neighbours.
+int tc_pack_halo(const float* const src[2], const int row0[2], const int rows[2], __half* xp, int N, int C, int H, int W,
+                 int wpad, cudaStream_t stream, const TcPackScale& ps);
 // Two consecutive layers in one kernel (conv_fused.cu): layer 1's output never leaves the SM.  tc_pair_ok: the pair matches
 // an instantiated configuration.  The state image (layer 1's source) must carry wpad1 + wpad2 halo columns, and layer 1's
 // weights must be packed with TcLayer::rowpitch = tc_pair_state_pitch (the staged state row is wider than 128 pixels).

@@ -79,6 +79,52 @@ static int launch(EwParams p, cudaStream_t stream, const char* name, int row_beg
     return after_launch(name);
 }
 
+// Halo rows of a latitude-band rollout: up to two row blocks of a (N, C, H, W) tensor <-> two contiguous staging buffers
+// (N, C, rows, W), ONE launch for both neighbours (plan.cu: halo_exchange).
+struct HaloCopyParams {
+    const float* src[2];
+    float* dst[2];
+    int rows[2];
+    long long ss_n[2], ss_c[2], ds_n[2], ds_c[2];   // row stride is W on both sides
+    int N, C, W;
+};
+
+__global__ void __launch_bounds__(256) halo_copy_kernel(const HaloCopyParams p) {
+    const long long per0 = (long long)p.N * p.C * p.rows[0] * p.W;
+    const long long total = per0 + (long long)p.N * p.C * p.rows[1] * p.W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = idx >= per0 ? 1 : 0;
+        long long t = idx - (k ? per0 : 0);
+        const int x = (int)(t % p.W);
+        t /= p.W;
+        const int y = (int)(t % p.rows[k]);
+        t /= p.rows[k];
+        const int c = (int)(t % p.C);
+        const int n = (int)(t / p.C);
+        p.dst[k][(long long)n * p.ds_n[k] + (long long)c * p.ds_c[k] + (long long)y * p.W + x] =
+            p.src[k][(long long)n * p.ss_n[k] + (long long)c * p.ss_c[k] + (long long)y * p.W + x];
+    }
+}
+
+// segment k: rows[k] rows, src[k] / dst[k] point at the block's first row; strides in elements
+int halo_copy(const float* const src[2], float* const dst[2], const int rows[2], const long long ss_n[2],
+              const long long ss_c[2], const long long ds_n[2], const long long ds_c[2], int N, int C, int W,
+              cudaStream_t stream) {
+    HaloCopyParams p;
+    long long total = 0;
+    for (int k = 0; k < 2; ++k) {
+        p.src[k] = src[k]; p.dst[k] = dst[k]; p.rows[k] = (src[k] && dst[k]) ? rows[k] : 0;
+        p.ss_n[k] = ss_n[k]; p.ss_c[k] = ss_c[k]; p.ds_n[k] = ds_n[k]; p.ds_c[k] = ds_c[k];
+        total += (long long)N * C * p.rows[k] * W;
+    }
+    p.N = N; p.C = C; p.W = W;
+    if (total <= 0) return 0;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    halo_copy_kernel<<<blocks, 256, 0, stream>>>(p);
+    return after_launch("halo_copy_kernel");
+}
+
 // ConvLSTM2D gate step (keras ConvLSTM2DCell.call).  One thread per (n, f, y, x): reads the four (eight) gate
 // pre-activation planes and c_prev, writes c and h -- 10 floats read, 2 written per element, coalesced along W.
 struct LstmParams {

@@ -50,6 +50,9 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
                cudaStream_t stream);
 const char* conv2d_impl_name(const DlwpConvDesc& d);
 int check_device();
+int halo_copy(const float* const src[2], float* const dst[2], const int rows[2], const long long ss_n[2],
+              const long long ss_c[2], const long long ds_n[2], const long long ds_c[2], int N, int C, int W,
+              cudaStream_t stream);
 
 // ---- training kernels (train.cu); stride arrays are {n, c, h} element strides -------------------------------------------
 int conv2d_bwd_input(const DlwpConvDesc& d, const float* dy, const float* w, float* dx, cudaStream_t stream);

@@ -105,6 +105,7 @@ struct DlwpPlan {
     int* d_counter = nullptr;      // device word for the fused kernel's last-CTA check
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
+    bool halo_in_p = false;        // the last exchange wrote the received rows into the input's P image (not the fp32 slot)
     long long halo_cap = 0;
     std::map<GraphKey, cudaGraphExec_t> band_graphs;
     // training state (lazily created by dlwp_train_step)
@@ -206,7 +207,7 @@ static int tc_setup(DlwpPlan* pl) {
     }
     // conv -> conv fusion: op i's output is an internal buffer that only op i + 1 reads (whole), op i is the only reader
     // of its own source, and the pair matches an instantiated fused kernel
-    if (pl->opt.fuse == 1)
+    if (pl->opt.fuse == 1 && !pl->tc_opt.bf16)
         for (int i = 0; i + 1 < nops && pl->pair_first < 0; ++i) {
             const DlwpOpDesc& a = pl->ops[i];
             const DlwpOpDesc& b = pl->ops[i + 1];
@@ -232,7 +233,7 @@ static int tc_setup(DlwpPlan* pl) {
         if (is_src[b]) {
             Buffer& B = pl->buffers[b];
             B.wpad = wpad[b] >= 0 ? wpad[b] : 0;  // read only by data movers: no halo needed
-            B.planes = 2 * ((B.d.C + 7) / 8);
+            B.planes = (pl->tc_opt.bf16 ? 1 : 2) * ((B.d.C + 7) / 8);
         }
     pl->tc_pdst.assign(nops, -1);
     for (int i = 0; i < nops; ++i)
@@ -278,7 +279,7 @@ static int tc_setup(DlwpPlan* pl) {
     for (int i = 0; i < nops; ++i)
         if (pl->tc_pdst[i] >= 0 && pl->tc_pdst[i] != pl->input_buf) ++producers[pl->tc_pdst[i]];
     for (int b = 0; b < nbuf; ++b)
-        if (!pl->buffers[b].e_static && producers[b] > 1) return 0;
+        if (!pl->tc_opt.bf16 && !pl->buffers[b].e_static && producers[b] > 1) return 0;   // (bf16 images carry no exponent)
     for (Buffer& b : pl->buffers)
         if (b.wpad >= 0) {
             const size_t bytes = tc_p_bytes(pl->max_batch, b.planes, b.d.H, b.d.W + 2 * b.wpad);
@@ -317,9 +318,16 @@ static int tc_pack_plan_weights(DlwpPlan* pl, int weight_id, const float* kernel
 
 // Scale words of one op at iteration t (conv_tc.h).  An image produced at iteration t is read at iteration t, except
 // the input image: the feedback conv of iteration t produces the input of iteration t + 1 (production index t + 1).
+static inline int PPC(const DlwpPlan* pl) { return pl->tc_opt.bf16 ? 1 : 2; }   // planes per 8-channel chunk
+
 static TcScale scale_of(const DlwpPlan* pl, int i, int t) {
     const DlwpOpDesc& op = pl->ops[i];
     TcScale sc;
+    if (pl->tc_opt.bf16) {   // plain bf16: no exponents, nothing measured
+        sc.e_in_const = 0;
+        sc.e_out_const = 0;
+        return sc;
+    }
     const Buffer& s = pl->buffers[op.src];
     sc.e_in_const = TC_EXP_STATIC;
     sc.amax_chk = pl->d_amax + 2 * op.src + (t & 1);
@@ -366,10 +374,10 @@ static int run_pair_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool fee
     if (pd >= 0) {
         const Buffer& pb = pl->buffers[pd];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
-        out_plane0 = pd == b.dst ? 2 * (b.dst_c0 / 8) : 0;
+        out_plane0 = pd == b.dst ? PPC(pl) * (b.dst_c0 / 8) : 0;
     }
     return tc_pair_launch(d1, pl->tc_layers[i], w1.kst, w1.bimg, w1.has_bias ? w1.b : nullptr, d2, pl->tc_layers[i + 1],
-                          w2.kst, w2.bimg, w2.has_bias ? w2.b : nullptr, s.P, s.planes, 2 * (a.src_c0 / 8), y32, yp,
+                          w2.kst, w2.bimg, w2.has_bias ? w2.b : nullptr, s.P, s.planes, PPC(pl) * (a.src_c0 / 8), y32, yp,
                           wpad_out, planes_out, out_plane0, sc1, sc2, pl->d_counter, stream, pl->tc_opt);
 }
 
@@ -388,8 +396,9 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bo
     if (op.kind != DLWP_OP_CONV) {  // data mover on P images
         if (pd < 0) return 0;  // nobody reads the result in P layout
         const Buffer& pb = pl->buffers[pd];
-        return tc_ew_launch(op.kind, s.P, pb.P, N, 2 * (op.src_c / 8), s.d.H, s.d.W, s.wpad, 2 * (op.src_c0 / 8), s.planes,
-                            pb.wpad, 2 * (op.dst_c0 / 8), pb.planes, stream, op.row_begin, op.row_end, sc);
+        return tc_ew_launch(op.kind, s.P, pb.P, N, PPC(pl) * (op.src_c / 8), s.d.H, s.d.W, s.wpad, PPC(pl) * (op.src_c0 / 8), s.planes,
+                            pb.wpad, PPC(pl) * (op.dst_c0 / 8), pb.planes, stream, op.row_begin, op.row_end, sc,
+                            pl->tc_opt.bf16);
     }
     const Weight& w = pl->weights[op.weight_id];
     DLWP_REQUIRE(w.set && w.bimg, DLWP_ESTATE, "weights %d were never set", op.weight_id);
@@ -398,12 +407,12 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bo
     __half* yp = nullptr;
     int wpad_out = 0, planes_out = 0;
     TcWindow win;
-    win.in_plane0 = 2 * (op.src_c0 / 8);
+    win.in_plane0 = PPC(pl) * (op.src_c0 / 8);
     win.in_planes_total = s.planes;
     if (pd >= 0) {
         const Buffer& pb = pl->buffers[pd];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
-        win.out_plane0 = pd == op.dst ? 2 * (op.dst_c0 / 8) : 0;
+        win.out_plane0 = pd == op.dst ? PPC(pl) * (op.dst_c0 / 8) : 0;
     }
     return tc_launch(d, pl->tc_layers[i], w.kst, s.P, w.bimg, w.has_bias ? w.b : nullptr, y32, yp, wpad_out,
                      planes_out, stream, win, sc, pl->tc_opt);
@@ -418,6 +427,7 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool inpu
     TcPackScale ps;
     ps.e = pl->d_exp + 2 * pl->input_buf + (t & 1);
     ps.amax = pl->d_amax + 2 * pl->input_buf + (t & 1);
+    ps.bf16 = pl->tc_opt.bf16;
     if (!input_is_packed) {
         ps.fresh = 1;
         ps.amax_zero = pl->d_amax + 2 * pl->input_buf + ((t + 1) & 1);
@@ -428,6 +438,8 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool inpu
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
                                (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1, ps);
         if (rc) return rc;
+    } else if (pl->halo_in_p) {
+        pl->halo_in_p = false;          // dlwp_rollout_latband's exchange stored the received halo rows in the image already
     } else if (pl->tc_band_row1 > 0) {  // latitude band: pack the halo rows received from the neighbours
         ps.fresh = 0;
         const int lo[2] = {pl->tc_in_row0, pl->tc_band_row1}, hi[2] = {pl->tc_band_row0, pl->tc_in_row1};
@@ -572,6 +584,7 @@ extern "C" int dlwp_plan_create_opts(const DlwpNetDesc* net, const DlwpPlanOptio
     pl->tc_opt.no_tma = pl->opt.tc_no_tma;
     pl->tc_opt.taps_in_k = pl->opt.tc_taps_in_k;
     pl->tc_opt.debug = pl->opt.tc_debug;
+    pl->tc_opt.bf16 = pl->opt.precision == 1 ? 1 : 0;
     pl->max_batch = net->max_batch;
     pl->buffers.resize(net->n_buffers);
     int n_outputs = 0;
@@ -910,49 +923,150 @@ static int nccl_load(const char* path) {
         }                                                                                              \
     } while (0)
 
-// one grouped SendRecv of the halo rows of `slot` (N, C, H, W): my top/bottom band rows out, the neighbours' rows in
-static int halo_exchange(DlwpPlan* pl, void* comm, int N, float* slot, const DlwpBandInfo& b, cudaStream_t stream) {
+// One grouped SendRecv of the halo rows of `slot` (N, C, H, W): my top/bottom band rows out, the neighbours' rows in.
+// Three launches per iteration: ONE kernel packs the rows for both neighbours, one NCCL group moves them, ONE kernel
+// stores what arrived -- on the tensor-core chain straight into the halo rows of the next input's P image (iteration
+// t + 1's exponent word, which the feedback conv of iteration t has already published), so the fp32 halo rows of the
+// series slot are never written (they belong to the neighbours' output); otherwise into the fp32 slot.
+static int halo_exchange(DlwpPlan* pl, void* comm, int N, float* slot, const DlwpBandInfo& b, cudaStream_t stream, int t) {
     const Buffer& in = pl->buffers[pl->input_buf];
     const int C = in.d.C, H = in.d.H, W = in.d.W;
     const long long sn = (long long)C * H * W, sc = (long long)H * W;
-    auto pack = [&](int row0, int rows, float* stage) {
-        return dlwp_copy4d(slot + (long long)row0 * W, stage, N, C, rows, W, sn, sc, W, (long long)C * rows * W,
-                           (long long)rows * W, W, stream);
-    };
-    auto unpack = [&](int row0, int rows, const float* stage) {
-        return dlwp_copy4d(stage, slot + (long long)row0 * W, N, C, rows, W, (long long)C * rows * W,
-                           (long long)rows * W, W, sn, sc, W, stream);
-    };
-    int rc = 0;
     const bool up = b.rank > 0, down = b.rank + 1 < b.world;
-    if (up && b.send_up && (rc = pack(b.band_lo, b.send_up, pl->halo_stage[0]))) return rc;
-    if (down && b.send_down && (rc = pack(b.band_hi - b.send_down, b.send_down, pl->halo_stage[1]))) return rc;
+    const int s_rows[2] = {up ? b.send_up : 0, down ? b.send_down : 0};
+    const int r_rows[2] = {up ? b.recv_top : 0, down ? b.recv_bot : 0};
+    int rc = 0;
+    {
+        const float* src[2] = {s_rows[0] ? slot + (long long)b.band_lo * W : nullptr,
+                               s_rows[1] ? slot + (long long)(b.band_hi - b.send_down) * W : nullptr};
+        float* dst[2] = {pl->halo_stage[0], pl->halo_stage[1]};
+        const long long ss_n[2] = {sn, sn}, ss_c[2] = {sc, sc};
+        const long long ds_n[2] = {(long long)C * s_rows[0] * W, (long long)C * s_rows[1] * W};
+        const long long ds_c[2] = {(long long)s_rows[0] * W, (long long)s_rows[1] * W};
+        if ((rc = halo_copy(src, dst, s_rows, ss_n, ss_c, ds_n, ds_c, N, C, W, stream))) return rc;
+    }
     const size_t per_row = (size_t)N * C * W;
     DLWP_NCCL_TRY(g_nccl.GroupStart());
-    if (up && b.send_up) DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[0], per_row * b.send_up, 7, b.rank - 1, comm, stream));
-    if (up && b.recv_top) DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[2], per_row * b.recv_top, 7, b.rank - 1, comm, stream));
-    if (down && b.send_down)
-        DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[1], per_row * b.send_down, 7, b.rank + 1, comm, stream));
-    if (down && b.recv_bot)
-        DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[3], per_row * b.recv_bot, 7, b.rank + 1, comm, stream));
+    if (s_rows[0]) DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[0], per_row * s_rows[0], 7, b.rank - 1, comm, stream));
+    if (r_rows[0]) DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[2], per_row * r_rows[0], 7, b.rank - 1, comm, stream));
+    if (s_rows[1]) DLWP_NCCL_TRY(g_nccl.Send(pl->halo_stage[1], per_row * s_rows[1], 7, b.rank + 1, comm, stream));
+    if (r_rows[1]) DLWP_NCCL_TRY(g_nccl.Recv(pl->halo_stage[3], per_row * r_rows[1], 7, b.rank + 1, comm, stream));
     DLWP_NCCL_TRY(g_nccl.GroupEnd());
-    if (up && b.recv_top && (rc = unpack(b.band_lo - b.recv_top, b.recv_top, pl->halo_stage[2]))) return rc;
-    if (down && b.recv_bot && (rc = unpack(b.band_hi, b.recv_bot, pl->halo_stage[3]))) return rc;
-    return 0;
+    const int r_row0[2] = {b.band_lo - b.recv_top, b.band_hi};
+    if (pl->tc && pl->tc_feedback_op >= 0) {
+        TcPackScale ps;
+        ps.e = pl->d_exp + 2 * pl->input_buf + ((t + 1) & 1);
+        ps.amax = pl->d_amax + 2 * pl->input_buf + ((t + 1) & 1);
+        ps.fresh = 0;
+        ps.bf16 = pl->tc_opt.bf16;
+        const float* src[2] = {r_rows[0] ? pl->halo_stage[2] : nullptr, r_rows[1] ? pl->halo_stage[3] : nullptr};
+        pl->halo_in_p = true;
+        return tc_pack_halo(src, r_row0, r_rows, in.P, N, C, H, W, in.wpad, stream, ps);
+    }
+    const float* src[2] = {r_rows[0] ? pl->halo_stage[2] : nullptr, r_rows[1] ? pl->halo_stage[3] : nullptr};
+    float* dst[2] = {slot + (long long)r_row0[0] * W, slot + (long long)r_row0[1] * W};
+    const long long ss_n[2] = {(long long)C * r_rows[0] * W, (long long)C * r_rows[1] * W};
+    const long long ss_c[2] = {(long long)r_rows[0] * W, (long long)r_rows[1] * W};
+    const long long ds_n[2] = {sn, sn}, ds_c[2] = {sc, sc};
+    return halo_copy(src, dst, r_rows, ss_n, ss_c, ds_n, ds_c, N, C, W, stream);
+}
+
+// Can the exchange of iteration t run BEHIND the start of iteration t + 1?  Yes when the plan is a tensor-core chain with a
+// feedback conv (the received rows go straight into the next input's P image), exactly one op -- the first -- reads the
+// input, it is a conv, and its destination image has a static exponent (so the rows it computes before the halo arrives
+// are scaled like the rows it computes after).  Then op 0 of iteration t + 1 is split into the rows that only read this
+// rank's own band (launched right after iteration t) and the edge rows that read halo rows (launched once the exchange,
+// which runs on a second stream, has finished).
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static bool latband_can_overlap(const DlwpPlan* pl, const DlwpBandInfo& b) {
+    if (b.world <= 1 || !pl->tc || pl->tc_feedback_op < 0 || pl->pair_first >= 0 || pl->opt.latband_spare_sms < 0) return false;
+    if (pl->ops.empty() || pl->ops[0].kind != DLWP_OP_CONV || pl->ops[0].src != pl->input_buf) return false;
+    for (size_t i = 1; i < pl->ops.size(); ++i)
+        if (pl->ops[i].src == pl->input_buf) return false;
+    const int pd = pl->tc_pdst[0];
+    if (pd < 0 || (!pl->tc_opt.bf16 && !pl->buffers[pd].e_static)) return false;
+    if (pl->ops[0].row_begin == 0 && pl->ops[0].row_end == 0) return false;
+    return true;
 }
 
 static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float* series, int iterations,
                          const DlwpBandInfo& b, cudaStream_t stream) {
     const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
     const int n_out = (int)pl->outputs.size();
-    for (int t = 0; t < iterations; ++t) {
-        int rc = rollout_range(pl, N, x0, series, t, t + 1, stream);
-        if (rc) return rc;
-        if (t + 1 < iterations && b.world > 1) {
-            rc = halo_exchange(pl, comm, N, series + ((long long)t * n_out + n_out - 1) * slot, b, stream);
-            if (rc) return rc;
+    const bool overlap = latband_can_overlap(pl, b);
+    if (overlap) {
+        if (!pl->s_copy) {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            DLWP_CUDA_TRY(cudaStreamCreateWithPriority(&pl->s_copy, cudaStreamNonBlocking, hi_pri));
+        }
+        while (pl->events.size() < 2) {
+            cudaEvent_t ev;
+            DLWP_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            pl->events.push_back(ev);
         }
     }
+    // rows of op 0 that read only this rank's band rows of the input
+    DlwpOpDesc& op0 = pl->ops[0];
+    const int w0 = op0.row_begin, w1 = op0.row_end, span = op0.dil_h * (op0.kh - 1);
+    const int int_lo = b.rank > 0 ? std::max(w0, b.band_lo + op0.pad_t) : w0;
+    const int int_hi = b.rank + 1 < b.world ? std::min(w1, b.band_hi - span + op0.pad_t) : w1;
+    bool halo_pending = false;
+    for (int t = 0; t < iterations; ++t) {
+        int rc = 0;
+        if (overlap && halo_pending && int_lo < int_hi) {
+            // iteration t with the exchange of iteration t - 1 still in flight on s_copy
+            Buffer& in = pl->buffers[pl->input_buf];
+            in.ptr = series + ((long long)t * n_out - 1) * slot;
+            for (int k = 0; k < n_out; ++k) pl->buffers[pl->outputs[k]].ptr = series + ((long long)t * n_out + k) * slot;
+            pl->tc_last_t = t;
+            op0.row_begin = int_lo; op0.row_end = int_hi;
+            // the exchange's kernels (packing, NCCL, unpacking) need SMs of their own: the conv CTAs are persistent and
+            // fill an SM's shared memory, so nothing else starts on an SM until its CTA exits
+            pl->tc_opt.max_ctas = std::max(1, sm_count() - (pl->opt.latband_spare_sms > 0 ? pl->opt.latband_spare_sms : 8));
+            rc = run_one_tc(pl, 0, N, stream, t, true);
+            pl->tc_opt.max_ctas = 0;
+            if (!rc) rc = cudaStreamWaitEvent(stream, pl->events[1], 0) == cudaSuccess ? 0 : (int)cudaGetLastError();
+            pl->halo_in_p = false;
+            if (!rc && w0 < int_lo) { op0.row_begin = w0; op0.row_end = int_lo; rc = run_one_tc(pl, 0, N, stream, t, true); }
+            if (!rc && int_hi < w1) { op0.row_begin = int_hi; op0.row_end = w1; rc = run_one_tc(pl, 0, N, stream, t, true); }
+            op0.row_begin = w0; op0.row_end = w1;
+            for (size_t i = 1; i < pl->ops.size() && !rc; ++i) rc = run_one_tc(pl, (int)i, N, stream, t, true);
+            halo_pending = false;
+        } else {
+            if (halo_pending) {   // (no interior rows: plain order)
+                DLWP_CUDA_TRY(cudaStreamWaitEvent(stream, pl->events[1], 0));
+                halo_pending = false;
+            }
+            rc = rollout_range(pl, N, x0, series, t, t + 1, stream);
+        }
+        if (rc) return rc;
+        if (t + 1 < iterations && b.world > 1) {
+            float* last = series + ((long long)t * n_out + n_out - 1) * slot;
+            if (overlap) {
+                DLWP_CUDA_TRY(cudaEventRecord(pl->events[0], stream));
+                DLWP_CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, pl->events[0], 0));
+                rc = halo_exchange(pl, comm, N, last, b, pl->s_copy, t);
+                if (rc) return rc;
+                DLWP_CUDA_TRY(cudaEventRecord(pl->events[1], pl->s_copy));
+                halo_pending = true;
+            } else {
+                rc = halo_exchange(pl, comm, N, last, b, stream, t);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (halo_pending) DLWP_CUDA_TRY(cudaStreamWaitEvent(stream, pl->events[1], 0));
     return 0;
 }
 }  // namespace dlwp

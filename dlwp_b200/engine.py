@@ -366,7 +366,8 @@ class CompiledNet(object):
         """force_ffma: build the plan on the fp32 kernels (training needs fp32 intermediates).
         row_windows: optional list (one (lo, hi) or None per lowered op) restricting each op to a latitude band
         (dlwp_b200.parallel.BandPlanner.windows); None entries drop the op.
-        options: dict of DlwpPlanOptions fields (math, fuse, tc_generic, tc_bands, tc_no_tma, tc_taps_in_k, tc_debug).
+        options: dict of DlwpPlanOptions fields (math, fuse, tc_generic, tc_bands, tc_no_tma, tc_taps_in_k, tc_debug,
+        precision: 0 / 'fp32' = fp32-equivalent tensor-core arithmetic, 1 / 'bf16' = plain bf16 images and weights).
         The environment variable DLWP_MATH=ffma is honoured HERE (scripts / bench.py --math), never inside the library."""
         self.torch = _torch()
         self.lib = nat.lib()
@@ -376,6 +377,10 @@ class CompiledNet(object):
         self.options = dict(options or {})
         import os
         self._force_ffma = bool(force_ffma) or (os.environ.get('DLWP_MATH') == 'ffma' and 'math' not in self.options)
+        if 'precision' not in self.options and os.environ.get('DLWP_PRECISION', '').lower() == 'bf16':
+            self.options['precision'] = nat.PRECISION_BF16      # honoured HERE (scripts / bench.py), never in the library
+        if isinstance(self.options.get('precision'), str):
+            self.options['precision'] = {'fp32': 0, 'f32': 0, 'bf16': nat.PRECISION_BF16}[self.options['precision'].lower()]
         self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
         self.plan = ctypes.c_void_p()
         self.max_batch = 0

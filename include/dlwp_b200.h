@@ -177,7 +177,13 @@ typedef struct DlwpPlanOptions {
     int32_t tc_taps_in_k;  /* -1: planner's choice; 0 / 1: horizontal taps in the MMA N / K dimension                     */
     int32_t tc_debug;      /* bottleneck triage: 1 = epilogue only waits/arrives, 2 = issuer only commits (both: WRONG
                               RESULTS); 4 = the issuing warp times itself (dlwp_debug_counters)                         */
-    int32_t reserved[9];
+    int32_t precision;     /* tensor-core chain: 0 = fp32-equivalent (fp16 hi/lo split, three MMA passes; the 1e-4 / 50-step
+                              parity gate), 1 = plain bf16 activations and weights, one MMA pass, fp32 accumulation
+                              (BASELINE.json configs[2]; parity ~1e-2 per application, reported, not gated)              */
+    int32_t latband_spare_sms; /* dlwp_rollout_latband: SMs left to the halo exchange while the interior rows of the next
+                              iteration's first layer compute beside it (0 = default 8; -1 = no overlap: exchange, then
+                              compute, on one stream)                                                                    */
+    int32_t reserved[7];
 } DlwpPlanOptions;
 
 /* Build the executable form of a Keras graph (replaces graph construction at DLWP/model/models.py:96-112, :349-373).

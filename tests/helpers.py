@@ -125,3 +125,10 @@ def run_conv(nat, torch, x, k, b, d, pads, mode_h, mode_w, act, impl, pre_op=0, 
     nat.check(rc, 'dlwp_conv2d_fwd')
     torch.cuda.synchronize()
     return yd.cpu().numpy()
+
+
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16, returned as float64 (what the bf16 mode stores for activations and weights)."""
+    a = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    a = (a + 0x7FFF + ((a >> 16) & 1)) & 0xFFFF0000
+    return a.astype(np.uint32).view(np.float32).astype(np.float64).reshape(np.shape(x))
