@@ -15,7 +15,7 @@ PAD_ZERO, PAD_PERIODIC, PAD_EDGE, PAD_REFLECT, PAD_SYMMETRIC = 0, 1, 2, 3, 4
 ACT_LINEAR, ACT_TANH, ACT_RELU = 0, 1, 2
 IMPL_AUTO, IMPL_DIRECT, IMPL_FFMA, IMPL_FFMA_TMA, IMPL_TC = 0, 1, 2, 3, 4
 BUF_INTERNAL, BUF_INPUT, BUF_OUTPUT = 0, 1, 2
-OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY, OP_LSTM = 0, 1, 2, 3, 4, 5
+OP_CONV, OP_PAD, OP_MAXPOOL, OP_UPSAMPLE, OP_COPY, OP_LSTM, OP_TO_NCHW, OP_TO_NHWC = 0, 1, 2, 3, 4, 5, 6, 7
 RECURRENT_ACTIVATIONS = {'hard_sigmoid': 0, 'sigmoid': 1}
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 ACTIVATIONS = {None: ACT_LINEAR, 'linear': ACT_LINEAR, 'tanh': ACT_TANH, 'relu': ACT_RELU}
@@ -75,9 +75,12 @@ class NetDesc(ctypes.Structure):
 SYMBOLS = {
     'dlwp_conv2d_fwd': (ctypes.c_int, [ctypes.POINTER(ConvDesc), fptr, fptr, fptr, fptr, ctypes.c_void_p]),
     'dlwp_pad2d': (ctypes.c_int, [fptr, fptr] + [i32] * 10 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_layout2d': (ctypes.c_int, [fptr, fptr] + [i32] * 5 + [ctypes.c_void_p]),
     'dlwp_maxpool2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_upsample2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_copy4d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_conv2d_bwd_input': (ctypes.c_int, [ctypes.POINTER(ConvDesc), fptr, fptr, fptr, ctypes.c_void_p]),
+    'dlwp_conv2d_bwd_weight': (ctypes.c_int, [ctypes.POINTER(ConvDesc), fptr, fptr, fptr, fptr, ctypes.c_void_p]),
     'dlwp_convlstm_gates': (ctypes.c_int, [fptr] * 5 + [i32] * 4 + [i64] * 4 + [i32] * 4 + [ctypes.c_void_p]),
     'dlwp_rows_op': (ctypes.c_int, [i32, fptr, fptr] + [i32] * 10 + [i64] * 6 + [i32, i32, ctypes.c_void_p]),
     'dlwp_plan_create': (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(ctypes.c_void_p)]),
@@ -107,6 +110,7 @@ SYMBOLS = {
     'dlwp_train_adam_state': (ctypes.c_int, [ctypes.c_void_p, fptr, fptr, i64, ctypes.POINTER(i64), i32]),
     'dlwp_train_adam': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_void_p]),
+    'dlwp_rollout_step_sequence': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32, ctypes.c_void_p]),
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.c_void_p]),
     'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),

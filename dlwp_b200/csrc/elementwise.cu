@@ -79,6 +79,22 @@ static int launch(EwParams p, cudaStream_t stream, const char* name, int row_beg
     return after_launch(name);
 }
 
+// (N, H, W, C) <-> (N, C, H, W).  One thread per element, indexed in the DESTINATION order (coalesced writes; the reads are
+// strided by C or H*W -- served from L2 for the small C of these nets).
+__global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C, int H,
+                                                    int W, int to_nchw) {
+    const long long total = (long long)N * C * H * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long t = idx;
+        int n, c, h, w;
+        if (to_nchw) { w = (int)(t % W); t /= W; h = (int)(t % H); t /= H; c = (int)(t % C); n = (int)(t / C); }
+        else { c = (int)(t % C); t /= C; w = (int)(t % W); t /= W; h = (int)(t % H); n = (int)(t / H); }
+        const long long nchw = (((long long)n * C + c) * H + h) * W + w, nhwc = (((long long)n * H + h) * W + w) * C + c;
+        y[to_nchw ? nchw : nhwc] = x[to_nchw ? nhwc : nchw];
+    }
+}
+
 // Halo rows of a latitude-band rollout: up to two row blocks of a (N, C, H, W) tensor <-> two contiguous staging buffers
 // (N, C, rows, W), ONE launch for both neighbours (plan.cu: halo_exchange).
 struct HaloCopyParams {
@@ -213,6 +229,18 @@ extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_
     EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
                xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_PAD>(p, (cudaStream_t)stream, "pad2d");
+}
+
+extern "C" int dlwp_layout2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t to_nchw,
+                             dlwp_stream_t stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    DLWP_REQUIRE(x && y && x != y, DLWP_EINVAL, "layout2d needs distinct tensors");
+    DLWP_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, DLWP_ESHAPE, "layout2d: non-positive dims");
+    const long long total = (long long)N * C * H * W;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    layout_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, N, C, H, W, to_nchw ? 1 : 0);
+    return after_launch("layout_kernel");
 }
 
 extern "C" int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n,

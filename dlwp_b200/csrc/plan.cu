@@ -105,7 +105,9 @@ struct DlwpPlan {
     int* d_counter = nullptr;      // device word for the fused kernel's last-CTA check
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
-    bool halo_in_p = false;        // the last exchange wrote the received rows into the input's P image (not the fp32 slot)
+    bool halo_in_p = false;
+    float* seq_state[2] = {nullptr, nullptr};   // dlwp_rollout_step_sequence: ping-pong input states
+    long long seq_cap = 0;        // the last exchange wrote the received rows into the input's P image (not the fp32 slot)
     long long halo_cap = 0;
     std::map<GraphKey, cudaGraphExec_t> band_graphs;
     // training state (lazily created by dlwp_train_step)
@@ -493,6 +495,12 @@ static int run_one(DlwpPlan* pl, size_t i, int N, cudaStream_t stream) {
                                   op.pad_mode_h, op.pad_mode_w, xs_n, xs_c, xs_h, ys_n, ys_c, ys_h, op.row_begin,
                                   op.row_end, stream);
                 break;
+            case DLWP_OP_TO_NCHW:
+            case DLWP_OP_TO_NHWC:
+                DLWP_REQUIRE(op.src_c0 == 0 && op.dst_c0 == 0 && op.src_c == s.d.C && s.d.C == t.d.C, DLWP_ESHAPE,
+                             "layout ops move whole buffers");
+                rc = dlwp_layout2d(x, y, N, s.d.C, s.d.H, s.d.W, op.kind == DLWP_OP_TO_NCHW ? 1 : 0, stream);
+                break;
             case DLWP_OP_LSTM: {
                 const Buffer& cbuf = pl->buffers[op.aux];
                 float* c = cbuf.ptr + op.aux_c0 * t_hw;
@@ -562,6 +570,22 @@ extern "C" int dlwp_conv2d_fwd(const DlwpConvDesc* desc, const float* x, const f
                                dlwp_stream_t stream) {
     DLWP_REQUIRE(desc != nullptr, DLWP_EINVAL, "null descriptor");
     return conv2d_fwd(*desc, x, w, bias, y, (cudaStream_t)stream);
+}
+
+extern "C" int dlwp_conv2d_bwd_input(const DlwpConvDesc* desc, const float* dy, const float* w, float* dx,
+                                     dlwp_stream_t stream) {
+    DLWP_REQUIRE(desc && dy && w && dx, DLWP_EINVAL, "null argument");
+    int rc = check_device();
+    if (rc) return rc;
+    return conv2d_bwd_input(*desc, dy, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" int dlwp_conv2d_bwd_weight(const DlwpConvDesc* desc, const float* x, const float* dy, float* dw, float* db,
+                                      dlwp_stream_t stream) {
+    DLWP_REQUIRE(desc && x && dy && dw, DLWP_EINVAL, "null argument");
+    int rc = check_device();
+    if (rc) return rc;
+    return conv2d_bwd_weight(*desc, x, dy, dw, db, (cudaStream_t)stream);
 }
 
 extern "C" int dlwp_plan_create(const DlwpNetDesc* net, DlwpPlan** out) {
@@ -693,6 +717,8 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
     for (Buffer& b : pl->buffers)
         if (b.P) cudaFree(b.P);
+    for (float* p : pl->seq_state)
+        if (p) cudaFree(p);
     if (pl->d_counter) cudaFree(pl->d_counter);
     if (pl->d_exp) cudaFree(pl->d_exp);
     if (pl->d_amax) cudaFree(pl->d_amax);
@@ -753,6 +779,48 @@ extern "C" int dlwp_plan_forward(DlwpPlan* pl, int32_t N, const float* x, float*
     if (!pl->tc) return run_ops(pl, N, (cudaStream_t)stream);
     DLWP_CUDA_TRY(cudaMemsetAsync(pl->d_amax, 0, sizeof(float) * 2 * pl->buffers.size(), (cudaStream_t)stream));
     return run_ops_tc(pl, N, (cudaStream_t)stream, 0, false, false, false);
+}
+
+// predict_timeseries(step_sequence=True), DLWP/model/models.py:280-290: the model advances ONE time slice per application.
+// The state holds time_dim slices of C / time_dim channels; after application t the next input is the old input without
+// its first slice, followed by the first slice of the prediction; series slot t keeps the whole prediction.
+extern "C" int dlwp_rollout_step_sequence(DlwpPlan* pl, int32_t N, const float* x0, float* series, int32_t iterations,
+                                          int32_t time_dim, dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && x0 && series, DLWP_EINVAL, "null argument");
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch && iterations > 0, DLWP_ESHAPE, "bad batch / iterations");
+    DLWP_REQUIRE(pl->outputs.size() == 1, DLWP_ESHAPE, "step_sequence needs a single-output model");
+    int rc = check_rollout_shapes(pl);
+    if (rc) return rc;
+    Buffer& in = pl->buffers[pl->input_buf];
+    const int C = in.d.C, H = in.d.H, W = in.d.W;
+    DLWP_REQUIRE(time_dim >= 1 && C % time_dim == 0, DLWP_ESHAPE, "channels %d are not time_dim %d slices", C, time_dim);
+    if (time_dim == 1) return dlwp_rollout(pl, N, x0, series, iterations, 0, stream_);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long slot = (long long)N * in.sample_elems(), hw = (long long)H * W, sn = in.sample_elems();
+    if (pl->seq_cap < slot) {
+        for (float*& p : pl->seq_state) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            DLWP_CUDA_TRY(cudaMalloc(&p, sizeof(float) * slot));
+        }
+        pl->seq_cap = slot;
+    }
+    const int Cs = C / time_dim;
+    if (pl->tc) DLWP_CUDA_TRY(cudaMemsetAsync(pl->d_amax, 0, sizeof(float) * 2 * pl->buffers.size(), stream));
+    for (int t = 0; t < iterations; ++t) {
+        const float* cur = t == 0 ? x0 : pl->seq_state[t & 1];
+        float* pred = series + (long long)t * slot;
+        in.ptr = const_cast<float*>(cur);
+        pl->buffers[pl->outputs[0]].ptr = pred;
+        rc = pl->tc ? run_ops_tc(pl, N, stream, t, false, false, true) : run_ops(pl, N, stream);
+        if (rc) return rc;
+        if (t + 1 == iterations) break;
+        float* nxt = pl->seq_state[(t + 1) & 1];
+        rc = dlwp_copy4d(cur + (long long)Cs * hw, nxt, N, C - Cs, H, W, sn, hw, W, sn, hw, W, stream_);
+        if (!rc) rc = dlwp_copy4d(pred, nxt + (long long)(C - Cs) * hw, N, Cs, H, W, sn, hw, W, sn, hw, W, stream_);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int dlwp_rollout(DlwpPlan* pl, int32_t N, const float* x0, float* series, int32_t iterations,
@@ -1151,6 +1219,8 @@ static int train_setup(DlwpPlan* pl) {
     for (const DlwpOpDesc& op : pl->ops) {
         DLWP_REQUIRE(op.kind != DLWP_OP_PAD, DLWP_ESHAPE, "stand-alone padding layers are not differentiable here yet");
         DLWP_REQUIRE(op.kind != DLWP_OP_LSTM, DLWP_ESHAPE, "ConvLSTM2D is inference-only here (no backward kernels yet)");
+        DLWP_REQUIRE(op.kind != DLWP_OP_TO_NCHW && op.kind != DLWP_OP_TO_NHWC, DLWP_ESHAPE,
+                     "channels_last models are inference-only here");
         DLWP_REQUIRE(!(op.kind == DLWP_OP_CONV && (op.rowwise || op.pre_op)), DLWP_ESHAPE,
                      "RowConnected2D / fused pre-ops are not differentiable here yet");
         DLWP_REQUIRE(!op.row_begin && !op.row_end, DLWP_ESHAPE, "row-windowed plans cannot be trained");

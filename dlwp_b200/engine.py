@@ -97,6 +97,12 @@ class Lowering(object):
             v = self._materialise_one_pad(v)
         return v
 
+    def _check_format(self, layer):
+        """Every layer of a model uses the model's data_format (channels_last models compute channels_first between one
+        layout op at each end: DLWP/custom.py:205-213 is the channels_last branch of PeriodicPadding2D)."""
+        if layer.data_format != self.fmt:
+            _unsupported(layer, 'data_format %r in a %s model' % (layer.data_format, self.fmt))
+
     def _settle_pad(self, v, layer):
         """Zero / periodic paddings stay pending (the next conv fuses them); the other modes become pad ops now."""
         if layer.pad_mode in ('zero', 'periodic'):
@@ -139,8 +145,7 @@ class Lowering(object):
             return self._emit_convlstm(layer, ins[0])
         if isinstance(layer, KL.ZeroPadding2D):  # includes PeriodicPadding2D & friends (pad_mode attribute)
             v = ins[0]
-            if layer.data_format != 'channels_first':
-                _unsupported(layer, "only data_format='channels_first' is lowered (all DLWP examples use it)")
+            self._check_format(layer)
             (t, b), (l, r) = layer.padding
             if layer.pad_mode == 'periodic' and (max(t, b) > v.H + sum(p[1][0] + p[1][1] for p in v.pads) or
                                                  max(l, r) > v.W + sum(p[2][0] + p[2][1] for p in v.pads)):
@@ -154,8 +159,7 @@ class Lowering(object):
         if isinstance(layer, KL.MaxPooling2D):
             if layer.pool_size != (2, 2) or layer.strides != (2, 2) or layer.padding != 'valid':
                 _unsupported(layer, 'only MaxPooling2D(2) with default strides / valid padding is implemented')
-            if layer.data_format != 'channels_first':
-                _unsupported(layer, "only data_format='channels_first' is lowered")
+            self._check_format(layer)
             v = self._materialise(ins[0])
             buf = self._new_buffer(v.C, v.H // 2, v.W // 2)
             self._op(nat.OP_MAXPOOL, v, buf)
@@ -163,23 +167,22 @@ class Lowering(object):
         if isinstance(layer, KL.UpSampling2D):
             if layer.size != (2, 2):
                 _unsupported(layer, 'only UpSampling2D(2) is implemented')
-            if layer.data_format != 'channels_first':
-                _unsupported(layer, "only data_format='channels_first' is lowered")
+            self._check_format(layer)
             v = self._materialise(ins[0])
             buf = self._new_buffer(v.C, v.H * 2, v.W * 2)
             self._op(nat.OP_UPSAMPLE, v, buf)
             return _Val(buf, 0, v.C, v.H * 2, v.W * 2)
         if isinstance(layer, KL.ChannelSlice):
             v = ins[0]
-            if layer.axis != 1 or layer.step not in (None, 1):
-                _unsupported(layer, 'only contiguous channel slices (axis=1, step 1) are lowered')
+            if layer.axis != (3 if self.fmt == 'channels_last' else 1) or layer.step not in (None, 1):
+                _unsupported(layer, 'only contiguous channel slices (step 1 along the channel axis) are lowered')
             a, b, _ = slice(layer.start, layer.end, None).indices(v.C)
             if b <= a:
                 raise ValueError('slice_layer %s selects no channels' % layer.name)
             return _Val(v.buf, v.c0 + a, b - a, v.H, v.W, v.pads, (b - a,) + tuple(v.shape[1:]))
         if isinstance(layer, KL.Concatenate):
-            if layer.axis not in (1, -3):
-                _unsupported(layer, 'only channel concatenation (axis=1) is lowered')
+            if layer.axis not in ((3, -1) if self.fmt == 'channels_last' else (1, -3)):
+                _unsupported(layer, 'only concatenation along the channel axis is lowered')
             vs = [self._materialise(v) for v in ins]
             C = sum(v.C for v in vs)
             buf = self._new_buffer(C, vs[0].H, vs[0].W)
@@ -190,6 +193,8 @@ class Lowering(object):
             return _Val(buf, 0, C, vs[0].H, vs[0].W)
         if isinstance(layer, KL.Reshape):
             v = ins[0]
+            if self.fmt == 'channels_last':
+                _unsupported(layer, 'Reshape in a channels_last model')
             tgt = layer.compute_output_shape((None,) + tuple(v.shape))[1:]
             if len(tgt) >= 2 and tuple(tgt[-2:]) == tuple(v.shape[-2:]):
                 return _Val(v.buf, v.c0, v.C, v.H, v.W, v.pads, tuple(tgt))  # regroups (T, C) <-> (T*C): a view
@@ -201,8 +206,7 @@ class Lowering(object):
     def _emit_conv(self, layer, v):
         if len(v.shape) != 3:
             _unsupported(layer, 'expects a 4-D (batch, channels, lat, lon) input, got per-sample shape %s' % (v.shape,))
-        if layer.data_format != 'channels_first':
-            _unsupported(layer, "only data_format='channels_first' is lowered (all DLWP examples use it)")
+        self._check_format(layer)
         if layer.strides != (1, 1):
             _unsupported(layer, 'strided convolutions are not on the hot path')
         act = nat.ACTIVATIONS.get(layer.activation)
@@ -277,10 +281,21 @@ class Lowering(object):
         if len(in_shape) not in (3, 4) or any(s is None for s in in_shape):
             raise NotImplementedError('the GPU plan needs a fully defined (C, H, W) or (T, C, H, W) input, got %s' %
                                       (in_shape,))
-        # a (time, channels, lat, lon) input (recurrent nets) is the same memory as (time * channels, lat, lon)
-        C, H, W = int(np.prod(in_shape[:-2])), in_shape[-2], in_shape[-1]
-        in_buf = self._new_buffer(C, H, W, nat.BUF_INPUT)
-        vals = {id(m.inputs[0]): _Val(in_buf, 0, C, H, W, (), in_shape)}
+        fmts = [l.data_format for l in m.layers if hasattr(l, 'data_format')]
+        self.fmt = fmts[0] if fmts else 'channels_first'
+        if self.fmt == 'channels_last':
+            if len(in_shape) != 3:
+                raise NotImplementedError('channels_last models are lowered for (H, W, C) inputs only')
+            H, W, C = in_shape
+            in_buf = self._new_buffer(C, H, W, nat.BUF_INPUT)             # caller memory: (N, H, W, C)
+            nchw = self._new_buffer(C, H, W)
+            self._op(nat.OP_TO_NCHW, _Val(in_buf, 0, C, H, W), nchw)
+            vals = {id(m.inputs[0]): _Val(nchw, 0, C, H, W)}
+        else:
+            # a (time, channels, lat, lon) input (recurrent nets) is the same memory as (time * channels, lat, lon)
+            C, H, W = int(np.prod(in_shape[:-2])), in_shape[-2], in_shape[-1]
+            in_buf = self._new_buffer(C, H, W, nat.BUF_INPUT)
+            vals = {id(m.inputs[0]): _Val(in_buf, 0, C, H, W, (), in_shape)}
         for node in m._nodes:
             if isinstance(node.layer, InputLayer):
                 continue
@@ -291,7 +306,15 @@ class Lowering(object):
             v = self._materialise(vals[id(t)])
             b = self.buffers[v.buf]
             full = v.c0 == 0 and v.C == b['C']
-            if full and b['kind'] == nat.BUF_INTERNAL and v.buf not in used:
+            if self.fmt == 'channels_last':
+                nb = self._new_buffer(v.C, v.H, v.W, nat.BUF_OUTPUT, k)   # caller memory: (N, H, W, C)
+                if not full:
+                    tmp = self._new_buffer(v.C, v.H, v.W)
+                    self._op(nat.OP_COPY, v, tmp)
+                    v = _Val(tmp, 0, v.C, v.H, v.W)
+                self._op(nat.OP_TO_NHWC, v, nb)
+                v = _Val(nb, 0, v.C, v.H, v.W, (), (v.H, v.W, v.C))
+            elif full and b['kind'] == nat.BUF_INTERNAL and v.buf not in used:
                 b['kind'], b['output_index'] = nat.BUF_OUTPUT, k
             else:
                 nb = self._new_buffer(v.C, v.H, v.W, nat.BUF_OUTPUT, k)
@@ -386,7 +409,8 @@ class CompiledNet(object):
         self.max_batch = 0
         self._pushed = {}
         self.in_shape = tuple(model.inputs[0].shape[1:])   # logical: (C, H, W), or (T, C, H, W) for recurrent nets
-        self.in_phys = (int(np.prod(self.in_shape[:-2])),) + self.in_shape[-2:]
+        ib = [b for b in self.low.buffers if b['kind'] == nat.BUF_INPUT][0]
+        self.in_phys = (ib['C'], ib['H'], ib['W'])
         self.out_shapes = [tuple(v.shape) for v in self.low.out_vals]
         self.out_phys = [(v.C, v.H, v.W) for v in self.low.out_vals]
         self.n_outputs = len(self.out_shapes)
@@ -670,6 +694,27 @@ class CompiledNet(object):
         nat.check(self.lib.dlwp_rollout(self.plan, n, x0.data_ptr(), series.data_ptr(), int(iterations),
                                         1 if use_graph else 0, self._stream()), 'dlwp_rollout')
         return series
+
+    def rollout_step_sequence_host(self, x0, iterations, time_dim):
+        """predict_timeseries(step_sequence=True) as one device-resident loop (dlwp_rollout_step_sequence): numpy in,
+        numpy (iterations, N) + input shape out; batches beyond the plan capacity run as sample chunks."""
+        torch = self.torch
+        x0 = np.ascontiguousarray(x0, dtype=np.float32)
+        n = x0.shape[0]
+        self.sync_weights()
+        out = np.empty((iterations, n) + self.in_shape, np.float32)
+        for s in range(0, n, self.max_batch):
+            for attempt in (0, 1):
+                self.lib.dlwp_debug_flags()
+                xd = torch.from_numpy(x0[s:s + self.max_batch]).cuda()
+                series = torch.empty((iterations, xd.shape[0]) + self.in_shape, dtype=torch.float32, device='cuda')
+                nat.check(self.lib.dlwp_rollout_step_sequence(self.plan, xd.shape[0], xd.data_ptr(), series.data_ptr(),
+                                                              int(iterations), int(time_dim), self._stream()),
+                          'dlwp_rollout_step_sequence')
+                out[:, s:s + self.max_batch] = series.cpu().numpy()
+                if not self._range_fallback():
+                    break
+        return out
 
     def rollout_host(self, x0, iterations, d2h_group=0, pinned=True):
         self.lib.dlwp_debug_flags()          # clear stale device flags

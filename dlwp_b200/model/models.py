@@ -187,8 +187,9 @@ class DLWPNeuralNet(object):
         return predicted
 
     def _device_rollout_ok(self, predictors, step_sequence):
-        return (not step_sequence and not self.impute and self.scaler_type is None and
+        return (not self.impute and self.scaler_type is None and
                 hasattr(self.model, 'engine') and predictors.ndim == (5 if self.is_recurrent else 4) and
+                (not step_sequence or len(self.model.outputs) == 1) and
                 self.model.engine(predictors.shape[0]).can_rollout())
 
     def predict_timeseries(self, predictors, time_steps, step_sequence=False, keep_time_dim=False, **kwargs):
@@ -211,7 +212,11 @@ class DLWPNeuralNet(object):
         feature_shape = predictors.shape[2:] if self.is_recurrent else predictors.shape[1:]
 
         if self._device_rollout_ok(predictors, step_sequence):
-            series = self.model.engine(sample_dim).rollout_host(predictors, time_steps)
+            eng = self.model.engine(sample_dim)
+            if step_sequence:     # models.py:280-290 as one device-resident loop (one time slice per application)
+                series = eng.rollout_step_sequence_host(predictors, time_steps, self.time_dim)
+            else:
+                series = eng.rollout_host(predictors, time_steps)
         else:
             series = np.full((time_steps,) + predictors.shape, np.nan, dtype=np.float32)
             p = predictors.copy()

@@ -88,6 +88,16 @@ typedef struct DlwpConvDesc {
 int dlwp_conv2d_fwd(const DlwpConvDesc* desc, const float* x, const float* w, const float* bias, float* y,
                     dlwp_stream_t stream);
 
+/* Adjoints of dlwp_conv2d_fwd in fp32 (what Keras' backward pass computes inside fit_generator, DLWP/model/models.py:216-228):
+ *   dlwp_conv2d_bwd_input   dx += sum over taps of dy * w, with the padding's adjoint (PeriodicPadding2D: wrap-ADD,
+ *                           ZeroPadding2D: crop); dy is the gradient w.r.t. the pre-activation output, dx is ACCUMULATED
+ *                           into (zero it first for a plain gradient);
+ *   dlwp_conv2d_bwd_weight  dw (kh, kw, Cin, Cout) and db (Cout; may be NULL) are ACCUMULATED into (atomic adds).
+ * Strides of x / dx come from desc->x_stride_*, of dy from desc->y_stride_*.  rowwise / pre_op descriptors are refused. */
+int dlwp_conv2d_bwd_input(const DlwpConvDesc* desc, const float* dy, const float* w, float* dx, dlwp_stream_t stream);
+int dlwp_conv2d_bwd_weight(const DlwpConvDesc* desc, const float* x, const float* dy, float* dw, float* db,
+                           dlwp_stream_t stream);
+
 /* Stand-alone PeriodicPadding2D.call / ZeroPadding2D.call (custom.py:191-214): y = pad(x). Strides in elements. */
 int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t pad_t, int32_t pad_b,
                int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n, int64_t xs_c, int64_t xs_h,
@@ -98,6 +108,10 @@ int dlwp_rows_op(int32_t op, const float* x, float* y, int32_t N, int32_t C, int
                  int32_t pad_b, int32_t pad_l, int32_t pad_r, int32_t mode_h, int32_t mode_w, int64_t xs_n, int64_t xs_c,
                  int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, int32_t row_begin, int32_t row_end,
                  dlwp_stream_t stream);
+
+/* (N, H, W, C) <-> (N, C, H, W), dense tensors: to_nchw != 0 reads NHWC and writes NCHW, else the reverse. */
+int dlwp_layout2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t to_nchw,
+                  dlwp_stream_t stream);
 
 /* keras MaxPooling2D(2) ('valid', floor) and UpSampling2D(2) (nearest), channels_first. */
 int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
@@ -122,7 +136,10 @@ int dlwp_convlstm_gates(const float* z, const float* r, const float* c_prev, flo
 
 enum { DLWP_BUF_INTERNAL = 0, DLWP_BUF_INPUT = 1, DLWP_BUF_OUTPUT = 2 };
 enum { DLWP_OP_CONV = 0, DLWP_OP_PAD = 1, DLWP_OP_MAXPOOL = 2, DLWP_OP_UPSAMPLE = 3, DLWP_OP_COPY = 4,
-       DLWP_OP_LSTM = 5 /* ConvLSTM2D gate step: see dlwp_convlstm_gates */ };
+       DLWP_OP_LSTM = 5 /* ConvLSTM2D gate step: see dlwp_convlstm_gates */,
+       /* data_format='channels_last' models (DLWP/custom.py:205-213; the Keras default): the plan computes channels_first,
+        * the caller-bound input / outputs are (N, H, W, C) memory -- one layout op at each end (whole buffers only) */
+       DLWP_OP_TO_NCHW = 6, DLWP_OP_TO_NHWC = 7 };
 enum { DLWP_RACT_HARD_SIGMOID = 0, DLWP_RACT_SIGMOID = 1 };   /* keras recurrent_activation */
 
 /* A dense (N, C, H, W) activation. INTERNAL buffers are allocated by the plan; the INPUT buffer and the OUTPUT buffers
@@ -211,6 +228,13 @@ int dlwp_plan_forward(DlwpPlan* plan, int32_t N, const float* x, float* const* o
  * use_graph != 0 captures the whole rollout into one CUDA graph (cached per (N, iterations, x0, series)). */
 int dlwp_rollout(DlwpPlan* plan, int32_t N, const float* x0, float* series, int32_t iterations, int32_t use_graph,
                  dlwp_stream_t stream);
+
+/* DLWPNeuralNet.predict_timeseries(step_sequence=True) (DLWP/model/models.py:280-290) on the device: the state holds
+ * time_dim slices of C / time_dim channels ((N, T, C', H, W) recurrent inputs are the same memory); after every application
+ * the next input is the old one without its first slice followed by the first slice of the prediction.  series
+ * (iterations, N, C, H, W) receives every whole prediction.  x0, series: device; the input is never modified. */
+int dlwp_rollout_step_sequence(DlwpPlan* plan, int32_t N, const float* x0, float* series, int32_t iterations,
+                               int32_t time_dim, dlwp_stream_t stream);
 
 /* Same with HOST buffers (numpy in / numpy out, like the reference's API): H2D of x0, rollout, D2H of the series
  * pipelined behind the compute in groups of `d2h_group` iterations. Pinned host memory gives full PCIe speed. Blocking.

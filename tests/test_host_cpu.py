@@ -291,3 +291,22 @@ def test_fill_and_tf_padding_lower_to_pad_ops(nat):
     dlwp.build_model(bad, loss='mse', optimizer='adam')
     with pytest.raises(NotImplementedError):
         Lowering(dlwp.model)
+
+
+def test_channels_last_model_lowers_with_layout_ops(nat):
+    from dlwp_b200.engine import Lowering
+    from dlwp_b200.model import DLWPNeuralNet
+    from tests.test_channels_last_gpu import _layers
+    dlwp = DLWPNeuralNet(is_convolutional=True, scaler_type=None, scale_targets=False)
+    dlwp.build_model(_layers((12, 20, 5)), loss='mse', optimizer='adam')
+    assert dlwp.model.output_shape == (None, 12, 20, 5)
+    low = Lowering(dlwp.model)
+    kinds = [o['kind'] for o in low.ops]
+    assert kinds[0] == nat.OP_TO_NCHW and kinds[-1] == nat.OP_TO_NHWC and kinds.count(nat.OP_CONV) == 2
+    assert low.out_vals[0].shape == (12, 20, 5)
+    mixed = (('PeriodicPadding2D', ((0, 1),), {'data_format': 'channels_last', 'input_shape': (8, 8, 3)}),
+             ('Conv2D', (4, 3), {'data_format': 'channels_first'}))
+    dlwp = DLWPNeuralNet(is_convolutional=True, scaler_type=None, scale_targets=False)
+    dlwp.build_model(mixed, loss='mse', optimizer='adam')
+    with pytest.raises(NotImplementedError):
+        Lowering(dlwp.model)

@@ -216,3 +216,39 @@ def test_l2_regularizer_enters_gradient_and_loss_and_trained_model_saves(tmp_pat
     for a, b in zip(dlwp.model.get_weights(), back.model.get_weights()):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(back.predict(X[:2]), dlwp.predict(X[:2]))
+
+
+def test_conv_backward_c_abi_entry_points():
+    """dlwp_conv2d_bwd_input / dlwp_conv2d_bwd_weight vs torch autograd (float64) on one fused
+    periodic-pad + zero-pad + dilated conv: y = conv(pad(x), w) + b, loss = sum(y * g)."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from dlwp_b200 import _native as nat
+    from tests.helpers import conv_desc
+    rng = np.random.RandomState(11)
+    N, Cin, H, W, Cout, k, d = 2, 5, 9, 12, 7, 3, 2
+    x = rng.standard_normal((N, Cin, H, W)).astype(np.float32)
+    w = (0.3 * rng.standard_normal((k, k, Cin, Cout))).astype(np.float32)
+    g = rng.standard_normal((N, Cout, H, W)).astype(np.float32)
+    xt = torch.tensor(x.astype(np.float64), requires_grad=True)
+    wt = torch.tensor(np.transpose(w, (3, 2, 0, 1)).astype(np.float64), requires_grad=True)
+    bt = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    xp = torch.cat([xt[..., W - 2:], xt, xt[..., :2]], dim=-1)
+    y = F.conv2d(F.pad(xp, (0, 0, 2, 2)), wt, bt, dilation=d)
+    (y * torch.tensor(g.astype(np.float64))).sum().backward()
+    desc, Ho, Wo = conv_desc(nat, N, Cin, H, W, Cout, k, k, d, ((2, 2), (2, 2)), nat.PAD_ZERO, nat.PAD_PERIODIC,
+                             nat.ACT_LINEAR, nat.IMPL_AUTO)
+    assert (Ho, Wo) == (H, W)
+    lib = nat.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xd, wd, gd = (torch.from_numpy(a).cuda() for a in (x, w, g))
+    dx = torch.zeros_like(xd)
+    dw = torch.zeros_like(wd)
+    db = torch.zeros(Cout, device='cuda')
+    nat.check(lib.dlwp_conv2d_bwd_input(ctypes.byref(desc), gd.data_ptr(), wd.data_ptr(), dx.data_ptr(), st))
+    nat.check(lib.dlwp_conv2d_bwd_weight(ctypes.byref(desc), xd.data_ptr(), gd.data_ptr(), dw.data_ptr(), db.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert _rel(dx.cpu().numpy(), xt.grad.numpy()) < TOL
+    assert _rel(dw.cpu().numpy(), np.transpose(wt.grad.numpy(), (2, 3, 1, 0))) < TOL
+    assert _rel(db.cpu().numpy(), bt.grad.numpy()) < TOL
