@@ -402,6 +402,8 @@ class CompiledNet(object):
         self._force_ffma = bool(force_ffma) or (os.environ.get('DLWP_MATH') == 'ffma' and 'math' not in self.options)
         if 'precision' not in self.options and os.environ.get('DLWP_PRECISION', '').lower() == 'bf16':
             self.options['precision'] = nat.PRECISION_BF16      # honoured HERE (scripts / bench.py), never in the library
+        if 'latband_spare_sms' not in self.options and os.environ.get('DLWP_LATBAND_SPARE_SMS'):
+            self.options['latband_spare_sms'] = int(os.environ['DLWP_LATBAND_SPARE_SMS'])   # -1: no exchange overlap
         if isinstance(self.options.get('precision'), str):
             self.options['precision'] = {'fp32': 0, 'f32': 0, 'bf16': nat.PRECISION_BF16}[self.options['precision'].lower()]
         self.impl = nat.IMPLS[impl] if isinstance(impl, str) else (impl or nat.IMPL_AUTO)
