@@ -400,6 +400,14 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+HALO_TEXT = {
+    'p2p': 'no collective on the data path: the last conv\'s epilogue stores the rows the neighbours need straight into '
+           'their input images over NVLink (CUDA IPC peer memory); two one-thread kernels per step count arrivals; all '
+           'captured in one CUDA graph',
+    'nccl': 'one grouped NCCL SendRecv per step (ncclSend/ncclRecv inside the C library) between one packing and one '
+            'unpacking kernel, captured with the band kernels in one CUDA graph'}
+
+
 def run_latband(args, rank, world, local_rank):
     """
     N > 1: the north-star partition -- every GPU owns a latitude band of ALL forecasts in flight and exchanges a 4-row halo
@@ -420,7 +428,7 @@ def run_latband(args, rank, world, local_rank):
     capped = B > cap
     B = max(world, min(B, cap))
     dlwp = build_model()
-    eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist)
+    eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist, halo=args.halo)
     x0 = make_inputs(B)                                    # the same global state on every rank
     xd = torch.from_numpy(x0).cuda()
     series = torch.empty((K, B) + STATE, dtype=torch.float32, device='cuda')
@@ -487,7 +495,8 @@ def run_latband(args, rank, world, local_rank):
                        % (world, world), 'bands': [list(p.band) for p in eng.planners],
                        'bands_equal_single_domain_bitwise': verified,
                        'halo': {'rows_per_side': 4, 'bytes_per_neighbour_per_direction_per_step': per_dir,
-                                'collective': 'one grouped NCCL SendRecv per step (ncclSend/ncclRecv inside the C library), captured with the band kernels in one CUDA graph',
+                                'exchange': eng.halo,
+                                'collective': HALO_TEXT[eng.halo],
                                 'link_time_us_at_770GBs': per_dir / 770e9 * 1e6,
                                 'fraction_of_step_time': per_dir / 770e9 / (ms / K * 1e-3)},
                        'l2': 'per-step working set >> L2 at this batch; no flush', 'e2e_steps': Ke},
@@ -560,7 +569,7 @@ def run_net_b(args, rank, world, local_rank):
 
     if latband:
         from dlwp_b200.parallel import LatBandEngine, halo_summary
-        eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist)
+        eng = LatBandEngine(dlwp.model, B, rank, world, dist=dist, halo=args.halo)
         net = eng.net
         roll = lambda k, out, graph=True: eng.rollout_device(xd, k, out=out, use_graph=graph)
     else:
@@ -677,7 +686,7 @@ def run_net_b(args, rank, world, local_rank):
                        'halo': {'rows_top_bottom': [hs['halo_rows_top'], hs['halo_rows_bottom']],
                                 'recv_bytes_per_step': hs['recv_bytes_per_iteration'],
                                 'link_time_us_at_770GBs': hs['recv_bytes_per_iteration'] / 2 / 770e9 * 1e6,
-                                'collective': 'one grouped NCCL SendRecv per step, overlapped with the interior rows of the next step'}})
+                                'exchange': eng.halo, 'collective': HALO_TEXT[eng.halo]}})
     line = {'metric': 'forecast_steps_per_sec', 'value': value, 'unit': 'forecast-steps/s', 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True,
             'scaling': args.scaling if latband else 'weak', 'vs_baseline': None,
@@ -704,6 +713,9 @@ def main():
                     help='tc: tcgen05 tensor cores, fp16 hi/lo split x3 (fp32-level accuracy); ffma: fp32 FFMA2 kernels')
     ap.add_argument('--parallel', default='latband', choices=['latband', 'batch'],
                     help='N>1: latitude bands + halo exchange (north star) or independent forecasts per GPU')
+    ap.add_argument('--halo', default='auto', choices=['auto', 'p2p', 'nccl'],
+                    help='latitude bands: halo rows over peer memory (the conv epilogue stores them into the neighbours) or '
+                         'one grouped NCCL SendRecv per step; auto = p2p when the plan qualifies')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='latitude bands: weak = --batch forecasts per GPU in flight (global batch grows with N), '
                          'strong = --batch forecasts in total')

@@ -111,6 +111,10 @@ SYMBOLS = {
     'dlwp_train_adam': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_void_p]),
     'dlwp_rollout_step_sequence': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, fptr, i32, i32, ctypes.c_void_p]),
+    'dlwp_plan_halo_enable': (ctypes.c_int, [ctypes.c_void_p]),
+    'dlwp_plan_halo_export': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'dlwp_plan_halo_import': (ctypes.c_int, [ctypes.c_void_p, i32, ctypes.c_void_p]),
+    'dlwp_plan_halo_connect': (ctypes.c_int, [ctypes.c_void_p, i32, ctypes.c_void_p]),
     'dlwp_plan_profile_op': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.c_void_p]),
     'dlwp_plan_uses_tensor_cores': (ctypes.c_int, [ctypes.c_void_p]),

@@ -751,5 +751,5 @@ extern "C" int dlwp_debug_flags(void) {
     if (cudaMemcpyFromSymbol(&v, dlwp::g_device_flags, sizeof(int)) != cudaSuccess) return -1;
     cudaMemcpyToSymbol(dlwp::g_device_flags, &zero, sizeof(int));
     const int t = dlwp::tc_debug_flags();
-    return v | (t > 0 ? (t << 1) : 0);
+    return v | dlwp::plan_flags_read_clear() | (t > 0 ? (t << 1) : 0);
 }

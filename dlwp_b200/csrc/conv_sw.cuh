@@ -254,6 +254,10 @@ struct SwParams {
     int debug;    // TcOptions::debug
     float* y32; long long ys_n, ys_c, ys_h;
     __half* yp; int Wp_out, wpad_out, planes_out;
+    // Latitude-band halo over peer memory (NVLink): output rows y < peer_up_end are ALSO stored into the upper neighbour's
+    // copy of the destination image (same layout, same absolute rows -- they are its bottom halo rows), rows
+    // y >= peer_down_begin into the lower neighbour's.  Null pointers: no neighbour / not a feedback layer.
+    __half* yp_up; __half* yp_down; int peer_up_end, peer_down_begin;
     TcScale sc;
     TcKStep kst[TC_MAX_KSTEPS];
 };
@@ -766,6 +770,12 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 // ---- pass 2: shifted sums, scale, bias, activation, stores --------------------------------------------
                 float* y32c = has_y32 ? y32n + (long long)y * p.ys_h : nullptr;
                 uint4* row_hi = has_yp ? ypn + (size_t)y * p.Wp_out : nullptr;
+                // element distance from this row of the local image to the same row of a neighbour's image (0: none)
+                long long peer_d[2] = {0, 0};
+                if (has_yp && p.yp_up != nullptr && y < p.peer_up_end)
+                    peer_d[0] = reinterpret_cast<uint4*>(p.yp_up) - reinterpret_cast<uint4*>(p.yp);
+                if (has_yp && p.yp_down != nullptr && y >= p.peer_down_begin)
+                    peer_d[1] = reinterpret_cast<uint4*>(p.yp_down) - reinterpret_cast<uint4*>(p.yp);
 #pragma unroll(ST::CBLK ? ST::CBLK : 1)
                 for (int cb = 0; cb < CBLK; ++cb) {
                     float d[KW][8];
@@ -833,6 +843,14 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                             __stcs(row_hi, vb);
                             if (halo_r) __stcs(row_hi + p.W, vb);
                             if (halo_l) __stcs(row_hi - p.W, vb);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
+                                    uint4* pr = row_hi + peer_d[k];
+                                    __stcs(pr, vb);
+                                    if (halo_r) __stcs(pr + p.W, vb);
+                                    if (halo_l) __stcs(pr - p.W, vb);
+                                }
                         } else if (has_yp) {
                             // the bound behind 2^e_out makes this unreachable for finite data; NaN / inf land here
                             if (!(am * sout <= 65504.f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
@@ -852,6 +870,16 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                                 __stcs(row_hi - p.W, vh);
                                 __stcs(row_lo - p.W, vl);
                             }
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
+                                    uint4* ph = row_hi + peer_d[k];
+                                    uint4* plo = row_lo + peer_d[k];
+                                    __stcs(ph, vh);
+                                    __stcs(plo, vl);
+                                    if (halo_r) { __stcs(ph + p.W, vh); __stcs(plo + p.W, vl); }
+                                    if (halo_l) { __stcs(ph - p.W, vh); __stcs(plo - p.W, vl); }
+                                }
                         }
                     }
                     if (has_yp) row_hi += (ST::BF16 ? 1 : 2) * plane_stride;

@@ -471,7 +471,7 @@ static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int 
 
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
-              const TcWindow& win, const TcScale& sc, const TcOptions& opt) {
+              const TcWindow& win, const TcScale& sc, const TcOptions& opt, const TcPeers& peers) {
     if (g_tc_sms == 0) {
         cudaDeviceProp prop;
         int dev = 0;
@@ -495,6 +495,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     p.out_plane0 = win.out_plane0;
     p.y32 = y32; p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
     p.yp = yp; p.wpad_out = wpad_out; p.Wp_out = d.W + 2 * wpad_out; p.planes_out = planes_out;
+    p.yp_up = yp ? peers.up : nullptr; p.yp_down = yp ? peers.down : nullptr;
+    p.peer_up_end = peers.up_end; p.peer_down_begin = peers.down_begin;
     p.sc = sc;
     for (int i = 0; i < L.KS; ++i) p.kst[i] = kst[i];
     if (grid <= 0) return 0;

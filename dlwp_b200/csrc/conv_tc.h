@@ -103,9 +103,16 @@ int tc_pack_weights(const DlwpConvDesc& d, const TcLayer& L, const float* w_host
 struct TcWindow {
     int in_plane0 = 0, in_planes_total = 0, out_plane0 = 0;
 };
+// Latitude-band neighbours' copies of the destination P image (peer memory): output rows below up_end are also stored into
+// `up`, rows from down_begin on into `down` (conv_sw.cuh, SwParams::yp_up).
+struct TcPeers {
+    __half* up = nullptr;
+    __half* down = nullptr;
+    int up_end = 0, down_begin = 0;
+};
 int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const __half* xp, const __half* bimg,
               const float* bias, float* y32, __half* yp, int wpad_out, int planes_out, cudaStream_t stream,
-              const TcWindow& win, const TcScale& sc, const TcOptions& opt);
+              const TcWindow& win, const TcScale& sc, const TcOptions& opt, const TcPeers& peers = TcPeers());
 // Data movers on P images (the U-Net's MaxPooling2D(2), UpSampling2D(2) and skip-connection copies): `planes` planes
 // starting at src_plane0 of the source -> planes starting at dst_plane0 of the destination; the destination's periodic
 // halo (wpad_d columns per side) is written with the interior.  kind: DLWP_OP_COPY / DLWP_OP_MAXPOOL / DLWP_OP_UPSAMPLE.

@@ -50,6 +50,7 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
                cudaStream_t stream);
 const char* conv2d_impl_name(const DlwpConvDesc& d);
 int check_device();
+int plan_flags_read_clear();   // plan.cu: bit 0 = a latitude-band halo wait timed out
 int halo_copy(const float* const src[2], float* const dst[2], const int rows[2], const long long ss_n[2],
               const long long ss_c[2], const long long ds_n[2], const long long ds_c[2], int N, int C, int W,
               cudaStream_t stream);

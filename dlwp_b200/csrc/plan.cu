@@ -22,6 +22,14 @@
 
 namespace dlwp {
 
+__device__ int g_device_flags_plan = 0;   // bit 0: a halo wait timed out (read by dlwp_debug_flags through plan_flags_read_clear)
+int plan_flags_read_clear() {
+    int v = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&v, g_device_flags_plan, sizeof(int)) != cudaSuccess) return 0;
+    if (v) cudaMemcpyToSymbol(g_device_flags_plan, &zero, sizeof(int));
+    return v;
+}
+
 static thread_local std::string t_error;
 std::atomic<long long> g_launches{0};
 
@@ -106,6 +114,20 @@ struct DlwpPlan {
     // latitude-band rollout: contiguous staging for the halo rows sent / received per iteration
     float* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // send_up, send_down, recv_top, recv_bot
     bool halo_in_p = false;
+    // latitude-band halo over peer memory (dlwp_plan_halo_*): the input image is double-buffered by iteration parity, the
+    // feedback conv of iteration t stores its band rows into P_in[(t+1)&1] and the rows the neighbours need into THEIR
+    // P_in[(t+1)&1]; arrivals are counted in `flags` ([0] from the upper, [1] from the lower neighbour, [2] / [3] how many
+    // this rank has consumed)
+    bool p2p = false;
+    __half* P_in[2] = {nullptr, nullptr};
+    __half* peer_P[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [up | down][parity]
+    int* flags = nullptr;
+    int* peer_flags[2] = {nullptr, nullptr};
+    std::vector<void*> ipc_opened;
+    int cur_parity = 0;            // parity of the iteration being launched (selects the feedback conv's destination)
+    bool p2p_active = false;       // inside dlwp_rollout_latband's peer-memory loop
+    bool p2p_send = false;         // this iteration's feedback conv also writes the neighbours' halo rows
+    int p2p_up_end = 0, p2p_down_begin = 0;
     float* seq_state[2] = {nullptr, nullptr};   // dlwp_rollout_step_sequence: ping-pong input states
     long long seq_cap = 0;        // the last exchange wrote the received rows into the input's P image (not the fp32 slot)
     long long halo_cap = 0;
@@ -411,13 +433,24 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bo
     TcWindow win;
     win.in_plane0 = PPC(pl) * (op.src_c0 / 8);
     win.in_planes_total = s.planes;
+    TcPeers peers;
     if (pd >= 0) {
         const Buffer& pb = pl->buffers[pd];
         yp = pb.P; wpad_out = pb.wpad; planes_out = pb.planes;
         win.out_plane0 = pd == op.dst ? PPC(pl) * (op.dst_c0 / 8) : 0;
+        if (pl->p2p_active && pd == pl->input_buf) {   // double-buffered input image + the neighbours' halo rows
+            const int nxt = (pl->cur_parity + 1) & 1;
+            yp = pl->P_in[nxt];
+            if (pl->p2p_send) {
+                peers.up = pl->peer_P[0][nxt];
+                peers.down = pl->peer_P[1][nxt];
+                peers.up_end = pl->p2p_up_end;
+                peers.down_begin = pl->p2p_down_begin;
+            }
+        }
     }
     return tc_launch(d, pl->tc_layers[i], w.kst, s.P, w.bimg, w.has_bias ? w.b : nullptr, y32, yp, wpad_out,
-                     planes_out, stream, win, sc, pl->tc_opt);
+                     planes_out, stream, win, sc, pl->tc_opt, peers);
 }
 
 // One application of the chain at iteration t.  input_is_packed: the feedback conv of iteration t - 1 already wrote the
@@ -719,6 +752,12 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (b.P) cudaFree(b.P);
     for (float* p : pl->seq_state)
         if (p) cudaFree(p);
+    for (void* p : pl->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (pl->p2p) {   // P_in[0] is the input buffer's own image (freed with the buffers)
+        if (pl->P_in[1]) cudaFree(pl->P_in[1]);
+        pl->buffers[pl->input_buf].P = pl->P_in[0];
+    }
+    if (pl->flags) cudaFree(pl->flags);
     if (pl->d_counter) cudaFree(pl->d_counter);
     if (pl->d_exp) cudaFree(pl->d_exp);
     if (pl->d_amax) cudaFree(pl->d_amax);
@@ -1045,6 +1084,33 @@ static int halo_exchange(DlwpPlan* pl, void* comm, int N, float* slot, const Dlw
 // are scaled like the rows it computes after).  Then op 0 of iteration t + 1 is split into the rows that only read this
 // rank's own band (launched right after iteration t) and the edge rows that read halo rows (launched once the exchange,
 // which runs on a second stream, has finished).
+// ---- halo over peer memory: arrival counters ------------------------------------------------------------------------------
+// After its feedback conv (whose epilogue stored the neighbours' halo rows through NVLink) a rank bumps the arrival counter
+// in each neighbour's flag block; before the first layer of the next iteration it waits until its own counters have
+// reached the number of arrivals it has consumed so far plus one.  All counters only grow, so a CUDA-graph replay of the
+// whole rollout needs no reset.
+__global__ void halo_signal_kernel(int* up_flags, int* down_flags) {
+    __threadfence_system();
+    if (up_flags) atomicAdd_system(up_flags + 1, 1);      // I am the upper neighbour's LOWER neighbour
+    if (down_flags) atomicAdd_system(down_flags + 0, 1);
+}
+__global__ void halo_wait_kernel(int* flags, int has_up, int has_down) {
+    for (int k = 0; k < 2; ++k) {
+        if (!(k == 0 ? has_up : has_down)) continue;
+        const int expected = ++flags[2 + k];
+        volatile int* arr = flags + k;
+        unsigned spins = 0;
+        while (*arr < expected) {
+            __nanosleep(200);
+            if (++spins > (1u << 24)) {            // ~ seconds: a neighbour died; raise the timeout flag instead of hanging
+                atomicOr(&g_device_flags_plan, 1);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -1057,7 +1123,7 @@ static int sm_count() {
 }
 
 static bool latband_can_overlap(const DlwpPlan* pl, const DlwpBandInfo& b) {
-    if (b.world <= 1 || !pl->tc || pl->tc_feedback_op < 0 || pl->pair_first >= 0 || pl->opt.latband_spare_sms < 0) return false;
+    if (b.world <= 1 || !pl->tc || pl->tc_feedback_op < 0 || pl->pair_first >= 0 || pl->opt.latband_spare_sms <= 0) return false;
     if (pl->ops.empty() || pl->ops[0].kind != DLWP_OP_CONV || pl->ops[0].src != pl->input_buf) return false;
     for (size_t i = 1; i < pl->ops.size(); ++i)
         if (pl->ops[i].src == pl->input_buf) return false;
@@ -1071,6 +1137,39 @@ static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float
                          const DlwpBandInfo& b, cudaStream_t stream) {
     const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
     const int n_out = (int)pl->outputs.size();
+    if (pl->p2p && b.world > 1) {
+        // Halo over peer memory: no packing, no NCCL -- the feedback conv's epilogue writes the neighbours' halo rows, two
+        // one-thread kernels count arrivals.  A neighbour barrier opens every rollout (nobody may still read the image
+        // parity this rollout's first feedback conv overwrites).
+        Buffer& in = pl->buffers[pl->input_buf];
+        const bool up = b.rank > 0, down = b.rank + 1 < b.world;
+        pl->p2p_up_end = up ? b.band_lo + b.send_up : 0;
+        pl->p2p_down_begin = down ? b.band_hi - b.send_down : 1 << 30;
+        int rc = 0;
+        halo_signal_kernel<<<1, 1, 0, stream>>>(up ? pl->peer_flags[0] : nullptr, down ? pl->peer_flags[1] : nullptr);
+        halo_wait_kernel<<<1, 1, 0, stream>>>(pl->flags, up ? 1 : 0, down ? 1 : 0);
+        if ((rc = after_launch("halo barrier"))) return rc;
+        pl->p2p_active = true;
+        for (int t = 0; t < iterations && !rc; ++t) {
+            pl->cur_parity = t & 1;
+            in.P = pl->P_in[t & 1];
+            pl->p2p_send = t + 1 < iterations;
+            if (t > 0) {
+                halo_wait_kernel<<<1, 1, 0, stream>>>(pl->flags, up ? 1 : 0, down ? 1 : 0);
+                pl->halo_in_p = true;      // the halo rows are in the image already: nothing to pack from the fp32 slot
+            }
+            rc = rollout_range(pl, N, x0, series, t, t + 1, stream);
+            if (!rc && t + 1 < iterations) {
+                halo_signal_kernel<<<1, 1, 0, stream>>>(up ? pl->peer_flags[0] : nullptr, down ? pl->peer_flags[1] : nullptr);
+                rc = after_launch("halo_signal_kernel");
+            }
+        }
+        pl->p2p_active = false;
+        pl->p2p_send = false;
+        pl->cur_parity = 0;
+        in.P = pl->P_in[0];
+        return rc;
+    }
     const bool overlap = latband_can_overlap(pl, b);
     if (overlap) {
         if (!pl->s_copy) {
@@ -1101,7 +1200,7 @@ static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float
             op0.row_begin = int_lo; op0.row_end = int_hi;
             // the exchange's kernels (packing, NCCL, unpacking) need SMs of their own: the conv CTAs are persistent and
             // fill an SM's shared memory, so nothing else starts on an SM until its CTA exits
-            pl->tc_opt.max_ctas = std::max(1, sm_count() - (pl->opt.latband_spare_sms > 0 ? pl->opt.latband_spare_sms : 8));
+            pl->tc_opt.max_ctas = std::max(1, sm_count() - pl->opt.latband_spare_sms);
             rc = run_one_tc(pl, 0, N, stream, t, true);
             pl->tc_opt.max_ctas = 0;
             if (!rc) rc = cudaStreamWaitEvent(stream, pl->events[1], 0) == cudaSuccess ? 0 : (int)cudaGetLastError();
@@ -1161,11 +1260,80 @@ extern "C" void dlwp_comm_destroy(void* comm) {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
 }
 
+// ---- halo over peer memory: set-up ---------------------------------------------------------------------------------------
+extern "C" int dlwp_plan_halo_enable(DlwpPlan* pl) {
+    DLWP_REQUIRE(pl != nullptr, DLWP_EINVAL, "null plan");
+    if (pl->p2p) return 0;
+    // same preconditions as the overlapped NCCL exchange: a tensor-core chain whose last conv re-packs the next input, one
+    // reader of the input (the first op) whose destination image has a data-independent exponent
+    DLWP_REQUIRE(pl->tc && pl->tc_feedback_op >= 0 && pl->pair_first < 0, DLWP_ESTATE,
+                 "the peer-memory halo needs a tensor-core chain with a feedback conv");
+    DLWP_REQUIRE(!pl->ops.empty() && pl->ops[0].kind == DLWP_OP_CONV && pl->ops[0].src == pl->input_buf, DLWP_ESTATE,
+                 "the peer-memory halo needs a conv as the only reader of the input");
+    for (size_t i = 1; i < pl->ops.size(); ++i)
+        DLWP_REQUIRE(pl->ops[i].src != pl->input_buf, DLWP_ESTATE, "the peer-memory halo needs ONE reader of the input");
+    const int pd = pl->tc_pdst[0];
+    DLWP_REQUIRE(pd >= 0 && (pl->tc_opt.bf16 || pl->buffers[pd].e_static), DLWP_ESTATE,
+                 "the first layer's output exponent depends on the data (rank-dependent without an amax exchange)");
+    Buffer& in = pl->buffers[pl->input_buf];
+    const size_t bytes = tc_p_bytes(pl->max_batch, in.planes, in.d.H, in.d.W + 2 * in.wpad);
+    pl->P_in[0] = in.P;
+    DLWP_CUDA_TRY(cudaMalloc(&pl->P_in[1], bytes));
+    DLWP_CUDA_TRY(cudaMemset(pl->P_in[1], 0, bytes));
+    DLWP_CUDA_TRY(cudaMalloc(&pl->flags, 64));
+    DLWP_CUDA_TRY(cudaMemset(pl->flags, 0, 64));
+    DLWP_CUDA_TRY(cudaDeviceSynchronize());
+    pl->p2p = true;
+    return 0;
+}
+
+// handles: 3 x 64 bytes (cudaIpcMemHandle_t of the two input images and of the flag block), to be sent to the neighbours
+extern "C" int dlwp_plan_halo_export(DlwpPlan* pl, void* handles192) {
+    DLWP_REQUIRE(pl && handles192 && pl->p2p, DLWP_EINVAL, "halo not enabled");
+    cudaIpcMemHandle_t h[3];
+    DLWP_CUDA_TRY(cudaIpcGetMemHandle(&h[0], pl->P_in[0]));
+    DLWP_CUDA_TRY(cudaIpcGetMemHandle(&h[1], pl->P_in[1]));
+    DLWP_CUDA_TRY(cudaIpcGetMemHandle(&h[2], pl->flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles192, h, sizeof(h));
+    return 0;
+}
+
+// which: 0 = upper neighbour (rank - 1), 1 = lower neighbour (rank + 1); handles192 as exported by THAT rank
+extern "C" int dlwp_plan_halo_import(DlwpPlan* pl, int32_t which, const void* handles192) {
+    DLWP_REQUIRE(pl && handles192 && pl->p2p && (which == 0 || which == 1), DLWP_EINVAL, "bad argument");
+    cudaIpcMemHandle_t h[3];
+    memcpy(h, handles192, sizeof(h));
+    void* ptr[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; ++k) {
+        DLWP_CUDA_TRY(cudaIpcOpenMemHandle(&ptr[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+        pl->ipc_opened.push_back(ptr[k]);
+    }
+    pl->peer_P[which][0] = (__half*)ptr[0];
+    pl->peer_P[which][1] = (__half*)ptr[1];
+    pl->peer_flags[which] = (int*)ptr[2];
+    return 0;
+}
+
+// Same-process neighbours (tests: several bands on one GPU, one plan each): raw device pointers of the other plan.
+extern "C" int dlwp_plan_halo_connect(DlwpPlan* pl, int32_t which, DlwpPlan* neighbour) {
+    DLWP_REQUIRE(pl && neighbour && pl->p2p && neighbour->p2p && (which == 0 || which == 1), DLWP_EINVAL, "bad argument");
+    pl->peer_P[which][0] = neighbour->P_in[0];
+    pl->peer_P[which][1] = neighbour->P_in[1];
+    pl->peer_flags[which] = neighbour->flags;
+    return 0;
+}
+
 extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const float* x0, float* series,
                                     int32_t iterations, const DlwpBandInfo* band, int32_t use_graph,
                                     dlwp_stream_t stream_) {
     DLWP_REQUIRE(pl && x0 && series && band, DLWP_EINVAL, "null argument");
-    DLWP_REQUIRE(band->world == 1 || comm != nullptr, DLWP_EINVAL, "a communicator is required for world > 1");
+    DLWP_REQUIRE(band->world == 1 || comm != nullptr || pl->p2p, DLWP_EINVAL,
+                 "a communicator (or dlwp_plan_halo_enable + peers) is required for world > 1");
+    if (pl->p2p && band->world > 1) {
+        DLWP_REQUIRE(band->rank == 0 || pl->peer_flags[0], DLWP_ESTATE, "upper neighbour not connected");
+        DLWP_REQUIRE(band->rank + 1 == band->world || pl->peer_flags[1], DLWP_ESTATE, "lower neighbour not connected");
+    }
     DLWP_REQUIRE(N > 0 && N <= pl->max_batch && iterations > 0, DLWP_ESHAPE, "bad batch / iterations");
     int rc = check_rollout_shapes(pl);
     if (rc) return rc;

@@ -317,14 +317,64 @@ class Model(object):
         self._compile_kwargs = dict(optimizer=optimizer, loss=loss, metrics=metrics, loss_weights=loss_weights,
                                     **kwargs)
 
-    def engine(self, batch=None):
-        """The compiled GPU plan (built lazily; rebuilt when a larger batch chunk is needed)."""
+    def engine(self, batch=None, device=None):
+        """The compiled GPU plan (built lazily; rebuilt when a larger batch chunk is needed).  `device`: CUDA device index
+        of a replica of a multi_gpu_model (None: the current device)."""
         from ..engine import CompiledNet
+        if device is not None:
+            import torch
+            reps = self.__dict__.setdefault('_replicas', {})
+            eng = reps.get(device)
+            if eng is None or (batch is not None and not eng.fits(batch)):
+                with torch.cuda.device(device):
+                    if eng is not None:
+                        eng.close()
+                    eng = reps[device] = CompiledNet(self, batch or 1)
+            return eng
         if self._engine is None or (batch is not None and not self._engine.fits(batch)):
             if self._engine is not None:
                 self._engine.close()
             self._engine = CompiledNet(self, batch or 1)
         return self._engine
+
+    # -- keras.utils.multi_gpu_model (DLWP/model/models.py:104-109): single-process batch split over `gpus` devices ------
+    def _split(self, x, call, axis):
+        """Run call(engine, chunk) for the slices of x dealt to the replicas (one host thread per device: the library calls
+        and the copies release the GIL) and concatenate the results along `axis` of every returned array."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        gpus = int(getattr(self, '_gpus', 1) or 1)
+        if gpus > torch.cuda.device_count():
+            raise ValueError('To call `multi_gpu_model` with `gpus=%d`, we expect the following devices to be available: '
+                             '%s. However this machine only has: %d CUDA device(s).' %
+                             (gpus, ['/gpu:%d' % i for i in range(gpus)], torch.cuda.device_count()))
+        n = x.shape[0]
+        bounds = [(n * d) // gpus for d in range(gpus + 1)]
+        parts = [(d, x[bounds[d]:bounds[d + 1]]) for d in range(gpus) if bounds[d + 1] > bounds[d]]
+
+        def work(item):
+            d, chunk = item
+            with torch.cuda.device(d):
+                return call(self.engine(chunk.shape[0], device=d), chunk)
+        with ThreadPoolExecutor(max_workers=len(parts)) as pool:
+            res = list(pool.map(work, parts))
+        if isinstance(res[0], (list, tuple)):
+            return [np.concatenate([r[k] for r in res], axis=axis) for k in range(len(res[0]))]
+        return np.concatenate(res, axis=axis)
+
+    def _multi(self):
+        return int(getattr(self, '_gpus', 1) or 1) > 1
+
+    def rollout_host(self, x, steps):
+        """Device-resident rollout, numpy in / numpy (slots, N, ...) out; a multi_gpu_model splits the batch over devices."""
+        if self._multi():
+            return self._split(np.asarray(x), lambda eng, c: eng.rollout_host(c, steps), axis=1)
+        return self.engine(len(x)).rollout_host(x, steps)
+
+    def rollout_step_sequence_host(self, x, steps, time_dim):
+        if self._multi():
+            return self._split(np.asarray(x), lambda eng, c: eng.rollout_step_sequence_host(c, steps, time_dim), axis=1)
+        return self.engine(len(x)).rollout_step_sequence_host(x, steps, time_dim)
 
     def predict(self, x, batch_size=None, verbose=0, steps=None, **kwargs):
         """keras.Model.predict: numpy in, numpy (or list of numpy) out.  `batch_size` only affects Keras' host-side
@@ -334,7 +384,10 @@ class Model(object):
         if x.shape[1:] != tuple(exp):
             raise ValueError('Error when checking input: expected %s to have shape %s but got array with shape %s' %
                              (self.inputs[0]._node.layer.name, exp, x.shape[1:]))
-        outs = self.engine(x.shape[0]).predict(x)
+        if self._multi():
+            outs = self._split(x, lambda eng, c: eng.predict(c), axis=0)
+        else:
+            outs = self.engine(x.shape[0]).predict(x)
         return outs[0] if self._single_output_list() else outs
 
     def _single_output_list(self):
@@ -366,6 +419,7 @@ class Model(object):
         for k in ('_engine', '_engine_key', '_train_engine', '_train_key', 'history'):
             if k in d:
                 d[k] = None
+        d.pop('_replicas', None)
         return d
 
     def save(self, filepath, overwrite=True, include_optimizer=True):
@@ -403,6 +457,8 @@ class Model(object):
         try:
             if self._engine is not None:
                 self._engine.close()
+            for eng in self.__dict__.get('_replicas', {}).values():
+                eng.close()
         except Exception:
             pass
 

@@ -13,6 +13,15 @@ class Sequence(object):
 
 
 def multi_gpu_model(model, gpus=None, **kwargs):
-    """The reference's only multi-device mechanism (single-process batch split, models.py:104-109).  dlwp_b200 scales
-    with one process per GPU instead (dlwp_b200.parallel); inside one process this is the identity."""
+    """keras.utils.multi_gpu_model as the reference uses it (DLWP/model/models.py:104-109, DLWP/util.py:176-183): a
+    single-process replica per device, every batch split evenly over them, results concatenated on the host.  The replicas
+    share the model's layers (one set of weights, pushed to each device's plan); `predict` / `predict_timeseries` run one
+    host thread per device.  Training through a multi_gpu_model is not provided -- data-parallel training is one process
+    per GPU (dlwp_b200/training.py: gradient all-reduce over NCCL)."""
+    if gpus is None or isinstance(gpus, (list, tuple)):
+        gpus = len(gpus) if gpus is not None else 1
+    if int(gpus) <= 1:
+        raise ValueError('For multi-gpu usage to be effective, call `multi_gpu_model` with `gpus >= 2`. Received: '
+                         '`gpus=%s`' % (gpus,))
+    model._gpus = int(gpus)
     return model

@@ -58,8 +58,8 @@ class DLWPNeuralNet(object):
         """
         Build the Sequential network.  Each element of `layers` is `(layer_name, args_tuple_or_None,
         kwargs_dict_or_None)`; names resolve in `keras.layers` first and `DLWP.custom` second (models.py:97-103).
-        `gpus` > 1 in the reference wraps the model in keras' single-process `multi_gpu_model`; here scaling is one
-        process per GPU (dlwp_b200.parallel), so the value is only recorded.
+        `gpus` > 1 wraps the model in `keras.utils.multi_gpu_model` like models.py:104-109: predict / predict_timeseries
+        split every batch over that many devices of this process.
         """
         if type(gpus) is not int:
             raise TypeError("'gpus' argument must be an int")
@@ -87,7 +87,7 @@ class DLWPNeuralNet(object):
             except (ImportError, AttributeError):
                 layer_class = util.get_from_class('DLWP.custom', name)
             self.base_model.add(layer_class(*args, **kwargs))
-        self.model = self.base_model
+        self.model = keras.utils.multi_gpu_model(self.base_model, gpus=gpus) if gpus > 1 else self.base_model
         self.gpus = gpus
         self.model.compile(**compile_kwargs)
 
@@ -212,11 +212,10 @@ class DLWPNeuralNet(object):
         feature_shape = predictors.shape[2:] if self.is_recurrent else predictors.shape[1:]
 
         if self._device_rollout_ok(predictors, step_sequence):
-            eng = self.model.engine(sample_dim)
             if step_sequence:     # models.py:280-290 as one device-resident loop (one time slice per application)
-                series = eng.rollout_step_sequence_host(predictors, time_steps, self.time_dim)
+                series = self.model.rollout_step_sequence_host(predictors, time_steps, self.time_dim)
             else:
-                series = eng.rollout_host(predictors, time_steps)
+                series = self.model.rollout_host(predictors, time_steps)
         else:
             series = np.full((time_steps,) + predictors.shape, np.nan, dtype=np.float32)
             p = predictors.copy()
@@ -276,7 +275,7 @@ class DLWPFunctional(object):
         util.make_keras_picklable()
         self.base_model = model
         self._n_steps = len(model.outputs)
-        self.model = self.base_model
+        self.model = keras.utils.multi_gpu_model(self.base_model, gpus=gpus) if gpus > 1 else self.base_model
         self.gpus = gpus
         self.model.compile(**compile_kwargs)
 
@@ -309,7 +308,7 @@ class DLWPFunctional(object):
         eng = self.model.engine(sample_dim) if (hasattr(self.model, 'engine') and predictors.ndim == 4 and
                                                 not self.is_recurrent) else None
         if eng is not None and eng.can_rollout():
-            series = eng.rollout_host(predictors, steps)
+            series = self.model.rollout_host(predictors, steps)
         else:
             series = np.full((out_steps,) + predictors.shape, np.nan, dtype=np.float32)
             p = predictors.copy()

@@ -227,9 +227,14 @@ class LatBandEngine(object):
     library (dlwp_rollout_latband: pack rows -> ncclGroupStart / ncclSend+ncclRecv up and down / ncclGroupEnd -> unpack),
     captured as one CUDA graph.  torch.distributed is only used once, to broadcast the NCCL unique id.
     `native=False` keeps the torch.distributed driver above (what the gloo CPU tests exercise).
+
+    halo = 'p2p': the exchange runs over peer memory instead -- the last conv's epilogue stores the neighbours' halo rows
+    straight into their (IPC-mapped) input images over NVLink and two one-thread kernels count arrivals
+    (dlwp_plan_halo_*); 'nccl': the grouped SendRecv; 'auto' (default): p2p when the plan qualifies and the handles can be
+    exchanged, else nccl.  `self.halo` says which one is in use.
     """
 
-    def __init__(self, model, batch, rank, world, dist=None, impl=None, native=True):
+    def __init__(self, model, batch, rank, world, dist=None, impl=None, native=True, halo='auto'):
         import ctypes
         from .engine import CompiledNet, Lowering
         low = Lowering(model)
@@ -251,7 +256,10 @@ class LatBandEngine(object):
         down = self.planners[rank + 1] if rank + 1 < world else None
         self.info = nat.BandInfo(rank, world, self.me.band[0], self.me.band[1], self.me.halo[0], self.me.halo[1],
                                  up.halo[1] if up else 0, down.halo[0] if down else 0)
-        if self.native and world > 1:
+        self.halo = 'nccl'
+        if self.native and world > 1 and halo in ('auto', 'p2p'):
+            self.halo = 'p2p' if self._connect_peers(dist, rank, world, strict=(halo == 'p2p')) else 'nccl'
+        if self.native and world > 1 and self.halo == 'nccl':
             import torch
             lib = nat.lib()
             path = _nccl_library().encode()
@@ -262,6 +270,38 @@ class LatBandEngine(object):
             dist.broadcast(t, 0)
             ident = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
             nat.check(lib.dlwp_comm_create(path, rank, world, ident, ctypes.byref(self.comm)), 'dlwp_comm_create')
+
+    def _connect_peers(self, dist, rank, world, strict=False):
+        """Enable the peer-memory halo on this rank's plan and map the neighbours' images (CUDA IPC handles swapped with one
+        all_gather).  Every rank must reach the same verdict, so the local outcome is agreed on with an all_reduce(MIN)."""
+        import ctypes
+        import torch
+        lib = nat.lib()
+        ok = lib.dlwp_plan_halo_enable(self.net.plan) == 0
+        mine = (ctypes.c_char * 192)()
+        if ok:
+            ok = lib.dlwp_plan_halo_export(self.net.plan, mine) == 0
+        flag = torch.tensor([1 if ok else 0], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            if strict:
+                raise RuntimeError('peer-memory halo unavailable: ' + nat.lib().dlwp_last_error_string().decode())
+            return False
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device='cuda')
+        allh = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        good = 1
+        for which, nb in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= nb < world:
+                buf = (ctypes.c_char * 192).from_buffer_copy(bytes(allh[nb].cpu().tolist()))
+                if lib.dlwp_plan_halo_import(self.net.plan, which, buf) != 0:
+                    good = 0
+        flag = torch.tensor([good], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            raise RuntimeError('peer-memory halo: cudaIpcOpenMemHandle failed on some rank: ' +
+                               nat.lib().dlwp_last_error_string().decode())
+        return True
 
     def close(self, destroy_comm=False):
         """ncclCommDestroy is collective-like (it can block until every rank calls it); by default the communicator is

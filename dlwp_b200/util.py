@@ -73,7 +73,11 @@ def load_model(file_name, history=False, custom_objects=None, gpus=1):
         model = pickle.load(f)
     loaded = _load('%s.keras' % file_name, custom_objects=custom_objects, compile=True)
     model.base_model = loaded
-    model.model = loaded
+    if gpus > 1:          # DLWP/util.py:176-183
+        from .keras.utils import multi_gpu_model
+        model.model = multi_gpu_model(loaded, gpus=gpus)
+    else:
+        model.model = loaded
     model.gpus = gpus
     if history:
         with open('%s.history' % file_name, 'rb') as f:

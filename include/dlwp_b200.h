@@ -197,9 +197,10 @@ typedef struct DlwpPlanOptions {
     int32_t precision;     /* tensor-core chain: 0 = fp32-equivalent (fp16 hi/lo split, three MMA passes; the 1e-4 / 50-step
                               parity gate), 1 = plain bf16 activations and weights, one MMA pass, fp32 accumulation
                               (BASELINE.json configs[2]; parity ~1e-2 per application, reported, not gated)              */
-    int32_t latband_spare_sms; /* dlwp_rollout_latband: SMs left to the halo exchange while the interior rows of the next
-                              iteration's first layer compute beside it (0 = default 8; -1 = no overlap: exchange, then
-                              compute, on one stream)                                                                    */
+    int32_t latband_spare_sms; /* dlwp_rollout_latband, NCCL exchange: > 0 runs the exchange on a second stream beside the
+                              interior rows of the next iteration's first layer, which leaves this many SMs free for it;
+                              0 (default) = exchange, then compute, on one stream (measured faster at 2 GPUs:
+                              profiles/r02_latband_2gpu.txt)                                                             */
     int32_t reserved[7];
 } DlwpPlanOptions;
 
@@ -266,6 +267,20 @@ void dlwp_comm_destroy(void* comm);
  * graph. series holds full (N,C,H,W) slots of which the band rows are valid. */
 int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0, float* series, int32_t iterations,
                          const DlwpBandInfo* band, int32_t use_graph, dlwp_stream_t stream);
+
+/* Halo exchange over peer memory (NVLink) instead of NCCL: after dlwp_plan_halo_enable the input image is double-buffered
+ * and the last conv of iteration t stores the rows its neighbours need straight into THEIR images from its epilogue; two
+ * one-thread kernels per iteration count arrivals (no packing, no copy kernels, no collective).  Set-up, once per plan:
+ * every rank enables, exports 3 x 64 bytes of CUDA IPC handles, the ranks swap them (any side channel), and each imports
+ * its upper (which = 0) and lower (which = 1) neighbour's.  dlwp_rollout_latband then ignores `comm` (may be NULL).
+ * dlwp_plan_halo_enable returns DLWP_ESTATE for plans it cannot serve (fp32 kernels, no feedback conv, a first layer whose
+ * output exponent depends on the data): keep the NCCL path for those.  dlwp_plan_halo_connect links two plans of ONE
+ * process by raw pointers (tests: several bands on one GPU). */
+int dlwp_plan_halo_enable(DlwpPlan* plan);
+int dlwp_plan_halo_export(DlwpPlan* plan, void* handles192);
+int dlwp_plan_halo_import(DlwpPlan* plan, int32_t which, const void* handles192);
+int dlwp_plan_halo_connect(DlwpPlan* plan, int32_t which, DlwpPlan* neighbour);
+
 
 /* ---- training (BASELINE.json configs[4]): what keras fit_generator / train_on_batch does per batch ------------------- */
 

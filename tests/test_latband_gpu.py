@@ -86,3 +86,72 @@ def test_unet_bands_equal_single_domain():
     eng.close()
     assert fp32.shape == ref.shape
     assert np.abs(fp32 - ref).max() <= 5e-5 * np.abs(ref).max()
+
+
+def _run_bands_p2p(model, world, x0, iterations, use_graph, options=None):
+    """The NATIVE latitude-band rollout (dlwp_rollout_latband) with the halo over peer memory, `world` bands in one process:
+    one row-windowed plan per band, linked by raw pointers (dlwp_plan_halo_connect), each launched on its own stream -- the
+    arrival counters synchronise the streams exactly as they synchronise GPUs."""
+    import ctypes
+    import torch
+    from dlwp_b200 import _native as nat
+    from dlwp_b200.engine import CompiledNet, Lowering
+    from dlwp_b200.parallel import make_planners
+    lib = nat.lib()
+    low = Lowering(model)
+    planners = make_planners(low.ops, low.buffers, x0.shape[2], world)
+    nets = [CompiledNet(model, x0.shape[0], row_windows=p.windows, options=options) for p in planners]
+    for n in nets:
+        nat.check(lib.dlwp_plan_halo_enable(n.plan), 'dlwp_plan_halo_enable')
+    for r in range(world):
+        if r > 0:
+            nat.check(lib.dlwp_plan_halo_connect(nets[r].plan, 0, nets[r - 1].plan))
+        if r + 1 < world:
+            nat.check(lib.dlwp_plan_halo_connect(nets[r].plan, 1, nets[r + 1].plan))
+    n_out = nets[0].n_outputs
+    xd = torch.from_numpy(x0).cuda()
+    series = [torch.full((iterations * n_out,) + x0.shape, float('nan'), device='cuda') for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for rep in range(2):                                    # twice: counters and image parities carry over between rollouts
+        for r in range(world):
+            p = planners[r]
+            up = planners[r - 1] if r > 0 else None
+            down = planners[r + 1] if r + 1 < world else None
+            info = nat.BandInfo(r, world, p.band[0], p.band[1], p.halo[0], p.halo[1], up.halo[1] if up else 0,
+                                down.halo[0] if down else 0)
+            nets[r].sync_weights()
+            nat.check(lib.dlwp_rollout_latband(nets[r].plan, None, x0.shape[0], xd.data_ptr(), series[r].data_ptr(),
+                                               iterations, ctypes.byref(info), 1 if use_graph else 0,
+                                               ctypes.c_void_p(streams[r].cuda_stream)), 'dlwp_rollout_latband')
+        torch.cuda.synchronize()
+        assert lib.dlwp_debug_flags() == 0                  # (bit 0 would be a halo wait that timed out)
+    full = torch.cat([series[r][:, :, :, p.band[0]:p.band[1]] for r, p in enumerate(planners)], dim=3)
+    for n in nets:
+        n.close()
+    return full.cpu().numpy()
+
+
+@pytest.mark.parametrize('world,use_graph', [(2, False), (3, True), (4, True)])
+def test_net_a_peer_memory_halo_is_bit_identical_to_single_domain(world, use_graph):
+    layers = OL.net_a_layers()
+    dlwp = build_product_sequential(layers)
+    oracle_sequential_like(dlwp, layers, seed=1, bias_scale=0.05)
+    x0 = np.random.RandomState(0).standard_normal((3, 6, 91, 180)).astype(np.float32)
+    ref = dlwp.predict_timeseries(x0, 7)
+    got = _run_bands_p2p(dlwp.model, world, x0, 7, use_graph)
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_unet_peer_memory_halo_is_bit_identical_to_single_domain(precision):
+    import torch
+    from dlwp_b200.engine import CompiledNet
+    cs = (12, 48, 64)
+    dlwp, _ = build_functional_pair(cs, skip=True, integration_steps=1, seed=3)
+    x0 = np.random.RandomState(4).standard_normal((2,) + cs).astype(np.float32)
+    eng = CompiledNet(dlwp.model, 2, options={'precision': precision})
+    ref = eng.rollout_device(torch.from_numpy(x0).cuda(), 4, use_graph=False).cpu().numpy()
+    eng.close()
+    got = _run_bands_p2p(dlwp.model, 2, x0, 4, True, options={'precision': precision})
+    np.testing.assert_array_equal(got, ref)
