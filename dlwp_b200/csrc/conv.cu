@@ -463,9 +463,11 @@ int check_device() {
         }
         g_num_sms = prop.multiProcessorCount;
         g_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    });
+    static std::atomic<unsigned long long> optin_done{0};
+    if (g_dev_status == 0 && first_use_on_device(optin_done))   // per device: a process may drive several GPUs
         for (const KernelEntry& e : g_kernels)
             cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    });
     return g_dev_status;
 }
 

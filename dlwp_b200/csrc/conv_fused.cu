@@ -562,10 +562,9 @@ uint32_t tc_pair_state_pitch(const DlwpConvDesc& d1) {
 
 template <class C>
 static void pair_launch_one(const PairParams& p, int grid, size_t smem, cudaStream_t stream) {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static std::atomic<unsigned long long> done{0};
+    if (first_use_on_device(done))
         cudaFuncSetAttribute(conv_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
     conv_pair_kernel<C><<<grid, PF_THREADS, smem, stream>>>(p);
 }
 

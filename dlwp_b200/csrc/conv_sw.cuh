@@ -909,10 +909,9 @@ typedef void (*SwLaunchFn)(const SwParams& p, const CUtensorMap& map_full, const
 template <int KH, int KW, int NC, class ST>
 static void sw_launch_one(const SwParams& p, const CUtensorMap& map_full, const CUtensorMap& map_pair, int grid,
                           size_t smem, cudaStream_t stream) {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static std::atomic<unsigned long long> done{0};
+    if (first_use_on_device(done))
         cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
     conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p, map_full, map_pair);
 }
 

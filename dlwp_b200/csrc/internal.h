@@ -50,6 +50,16 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
                cudaStream_t stream);
 const char* conv2d_impl_name(const DlwpConvDesc& d);
 int check_device();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: a process that drives several GPUs
+// (keras multi_gpu_model: one plan per device) has to opt in on each of them.  Returns true the first time it is called for
+// (this mask, current device).
+#include <atomic>
+inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+}
 int plan_flags_read_clear();   // plan.cu: bit 0 = a latitude-band halo wait timed out
 int halo_copy(const float* const src[2], float* const dst[2], const int rows[2], const long long ss_n[2],
               const long long ss_c[2], const long long ds_n[2], const long long ds_c[2], int N, int C, int W,
