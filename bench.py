@@ -210,7 +210,7 @@ def run_reference(args, rank, world):
             'config': {'workload': 'net_b_skip_unet_12x180x360_rollout', 'batch_per_gpu': args.batch, 'timed_sample_batch': n,
                        'note': 'reference rollout loop (DLWP/model/models.py:414-452 restated in oracle/) + torch-CPU fp32 '
                                'forward; Keras/TensorFlow are not installable offline'},
-            'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'host_cores': os.cpu_count(), 'sample': sample},
             'e2e': {'value': value, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}))
         return
@@ -227,7 +227,7 @@ def run_reference(args, rank, world):
         'config': {'workload': 'net_a_6x91x180_rollout', 'batch_per_gpu': args.batch, 'timed_sample_batch': n,
                    'note': 'reference rollout loop (DLWP/model/models.py:247-301 restated in oracle/) + torch-CPU fp32 '
                            'forward; Keras/TensorFlow are not installable offline'},
-        'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'host_cores': os.cpu_count(), 'sample': sample},
         'e2e': {'value': value, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -371,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         v, cores, dtc = cpu_reference(32, 4, 1)
-        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port',
+        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'host_cores': os.cpu_count(),
                'sample': '32 of %d samples x 4 steps (1 warm-up step), torch-CPU fp32 forward inside the reference '
                          'rollout loop' % B}
 
@@ -672,7 +672,7 @@ def run_net_b(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         v, cores, _ = net_b_cpu_reference(onet, 8, 2, 1)
-        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port',
+        cpu = {'value': v, 'unit': 'forecast-steps/s', 'cores': cores, 'kind': 'port', 'host_cores': os.cpu_count(),
                'sample': '8 of %d samples x 2 steps (1 warm-up step), torch-CPU fp32 forward inside the reference rollout loop' % B}
     config = {'workload': 'net_b_skip_unet_12x180x360_rollout (BASELINE.json configs[%d])' % (3 if latband else 2),
               'batch_per_gpu': B / world if latband else B, 'global_batch': n_forecasts, 'state': list(NET_B_STATE),

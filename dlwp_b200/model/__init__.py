@@ -1,12 +1,13 @@
 """Mirror of `DLWP.model` (reference DLWP/model/__init__.py:11-17).  The xarray/netCDF-dependent classes are resolved
 lazily because those packages are unavailable offline and lie outside the rollout hot path."""
 
-from .generators import ArrayDataGenerator, DataGenerator, SeriesDataGenerator, SmartDataGenerator  # noqa: F401
-from .models import DLWPFunctional, DLWPNeuralNet  # noqa: F401
+from .generators import (ArrayDataGenerator, ArraySeriesGenerator, DataGenerator, SeriesDataGenerator,  # noqa: F401
+                         SmartDataGenerator)
+from .extensions import TimeSeriesEstimator  # noqa: F401,E402
+from .models import DLWPFunctional, DLWPNeuralNet  # noqa: F401,E402
 
 _OUT_OF_SCOPE = {
     'Preprocessor': 'DLWP/model/preprocessing.py (offline data preparation, needs netCDF4/xarray)',
-    'TimeSeriesEstimator': 'DLWP/model/extensions.py (xarray-metadata rollout driver; SURVEY.md 8f rank 2)',
     'verify': 'DLWP/model/verify.py (post-processing metrics, needs xarray/pandas)',
     'DLWPTorchNN': 'DLWP/model/models_torch.py (PyTorch twin of DLWPNeuralNet)',
 }

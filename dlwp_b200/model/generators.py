@@ -58,3 +58,49 @@ class ArrayDataGenerator(Sequence):
     def on_epoch_end(self):
         if self.shuffle:
             self._rng.shuffle(self._idx)
+
+
+class ArraySeriesGenerator(object):
+    """
+    In-memory stand-in for the reference's `SeriesDataGenerator` (DLWP/model/generators.py:529-605) as far as
+    `TimeSeriesEstimator` reads it (extensions.py:37-135, 175-188): unscaled predictors for every sample plus the metadata
+    the estimator needs -- sample times, variable/level names of inputs and outputs, time steps, insolation flag.
+
+    data: (n_sample + padding, V, H, W) time series of fields on an evenly spaced time axis `times`; sample i takes
+    `input_time_steps` consecutive fields starting at i (selected `input_varlev`) and targets the `output_time_steps`
+    fields that follow after `interval - 1` skipped steps (selected `output_varlev`).
+    """
+
+    def __init__(self, data, times, lat, lon, varlev, input_varlev=None, output_varlev=None, input_time_steps=1,
+                 output_time_steps=1, interval=1, add_insolation=False):
+        self.data = np.asarray(data, np.float32)
+        self.times = np.asarray(times).astype('datetime64[s]')
+        self.lat, self.lon = np.asarray(lat, np.float64), np.asarray(lon, np.float64)
+        self.varlev = list(varlev)
+        self._input_sel = {'varlev': list(input_varlev if input_varlev is not None else varlev)}
+        self._output_sel = {'varlev': list(output_varlev if output_varlev is not None else varlev)}
+        self._input_time_steps, self._output_time_steps = int(input_time_steps), int(output_time_steps)
+        self._interval = int(interval)
+        self._add_insolation = bool(add_insolation)
+        self._n_sample = self.data.shape[0] - self._input_time_steps - self._output_time_steps - self._interval + 2
+        if self._n_sample < 2:
+            raise ValueError('not enough time steps for two samples')
+        self.sample_times = self.times[:self._n_sample]
+        H, W = self.data.shape[-2:]
+        v_in = len(self._input_sel['varlev']) + (1 if self._add_insolation else 0)
+        self.convolution_shape = (self._input_time_steps * v_in, H, W)
+        self.output_convolution_shape = (self._output_time_steps * len(self._output_sel['varlev']), H, W)
+
+    def generate(self, samples=(), scale_and_impute=False):
+        from ..util import insolation
+        S, ti, to = self._n_sample, self._input_time_steps, self._output_time_steps
+        iin = [self.varlev.index(v) for v in self._input_sel['varlev']]
+        iout = [self.varlev.index(v) for v in self._output_sel['varlev']]
+        dt = self.times[1] - self.times[0]
+        p = np.stack([self.data[n:n + S][:, iin] for n in range(ti)], axis=1)            # (S, ti, V_in, H, W)
+        if self._add_insolation:
+            sol = np.stack([insolation(self.sample_times + n * dt, self.lat, self.lon) for n in range(ti)], axis=1)
+            p = np.concatenate([p, sol[:, :, None]], axis=2)
+        off = ti + self._interval - 1
+        t = np.stack([self.data[off + n:off + n + S][:, iout] for n in range(to)], axis=1)
+        return p.reshape((S,) + self.convolution_shape), t.reshape((S,) + self.output_convolution_shape)

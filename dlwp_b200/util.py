@@ -86,6 +86,45 @@ def load_model(file_name, history=False, custom_objects=None, gpus=1):
     return model
 
 
+def day_of_year(date):
+    """DLWP/util.py:300-302; also takes arrays of numpy datetime64."""
+    d = np.asarray(date, 'datetime64[s]')
+    start = d.astype('datetime64[Y]').astype('datetime64[s]')
+    return (d - start).astype(np.float64) / 3600. / 24.
+
+
+def insolation(dates, lat, lon, S=1.):
+    """
+    DLWP/util.py:305-352: approximate solar insolation for the given dates, (date, lat, lon) float32.  `dates`: anything
+    numpy can read as datetime64 (pandas Timestamps included); `lat` / `lon` both 1-D or both 2-D of equal shape.  Unlike the
+    reference the caller's `lat` array is not converted to radians in place.
+    """
+    lat, lon = np.asarray(lat, np.float64), np.asarray(lon, np.float64)
+    if lat.ndim != lon.ndim:
+        raise ValueError("'lat' and 'lon' must either both be 1d or both be 2d'")
+    if lat.ndim == 2 and lat.shape != lon.shape:
+        raise ValueError("shape mismatch between lat (%s) and lon (%s)" % (lat.shape, lon.shape))
+    if lat.ndim == 1:
+        lon, lat = np.meshgrid(lon, lat)
+    # constants for year 1995 (standard)
+    eps = 23.4441 * np.pi / 180.
+    ecc = 0.016715
+    om = 282.7 * np.pi / 180.
+    beta = np.sqrt(1 - ecc ** 2.)
+    days = day_of_year(dates).reshape(-1)
+    lambda_m0 = ecc * (1. + beta) * np.sin(om)
+    lambda_m = lambda_m0 + 2. * np.pi * (days - 80.5) / 365.
+    lambda_ = lambda_m + 2. * ecc * np.sin(lambda_m - om)
+    dec = np.arcsin(np.sin(eps) * np.sin(lambda_))                       # solar declination
+    h = 2 * np.pi * (days[:, None, None] + lon / 360.)                   # hour angle
+    rho = (1. - ecc ** 2.) / (1. + ecc * np.cos(lambda_ - om))           # distance
+    lat = lat * np.pi / 180.
+    sol = S * (np.sin(lat[None, ...]) * np.sin(dec[:, None, None]) -
+               np.cos(lat[None, ...]) * np.cos(dec[:, None, None]) * np.cos(h)) * rho[:, None, None] ** -2.
+    sol[sol < 0.] = 0.
+    return sol.astype(np.float32)
+
+
 def train_test_split_ind(n_sample, test_size, method='random'):
     """Index lists (train, test) splitting range(n_sample): same contract as DLWP/util.py:271-297."""
     idx = np.arange(n_sample)

@@ -209,6 +209,23 @@ def gen_rollout_recurrent(models):
     np.savez_compressed(os.path.join(HERE, 'rollout_recurrent.npz'), **out)
 
 
+def gen_insolation():
+    """The reference's own `day_of_year` / `insolation` (DLWP/util.py:300-352), executed from its source text (util.py
+    imports keras at module level; these two functions only need numpy and pandas)."""
+    import pandas as pd
+    src = open(os.path.join(REF, 'DLWP', 'util.py')).read()
+    a, b = src.index('def day_of_year'), src.index('return sol.astype(np.float32)') + len('return sol.astype(np.float32)')
+    ns = {'np': np, 'pd': pd}
+    exec(compile(src[a:b], 'DLWP/util.py', 'exec'), ns)
+    dates = pd.date_range('2003-02-27 06:00', periods=11, freq='6h')
+    lat, lon = np.linspace(90., -90., 13), np.arange(0., 360., 30.)
+    sol = ns['insolation'](dates, lat.copy(), lon.copy())
+    lon2, lat2 = np.meshgrid(lon, lat)
+    sol2 = ns['insolation'](dates[:3], lat2.copy(), lon2.copy(), S=2.)
+    np.savez_compressed(os.path.join(HERE, 'insolation.npz'), dates=dates.values.astype('datetime64[s]').astype(np.int64),
+                        lat=lat, lon=lon, sol=sol, sol2=sol2)
+
+
 def gen_row_conv(custom):
     rng = np.random.RandomState(11)
     x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
@@ -353,7 +370,7 @@ def main():
     gens = [('padding2d', lambda: gen_periodic_padding(custom)), ('row_conv', lambda: gen_row_conv(custom)),
             ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
-            ('recurrent', lambda: gen_rollout_recurrent(models))]
+            ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation)]
     for name, fn in gens:
         if not only or name in only:
             fn()

@@ -1,0 +1,87 @@
+"""
+`TimeSeriesEstimator.predict` (DLWP/model/extensions.py:136-303) with the predictor array resident on
+the GPU, against the numpy restatement of the reference's loop (oracle/estimator.py -- unpinned: the reference needs
+xarray) driven by the float64 oracle net.  Configurations: fewer output than input time steps with an input the model does
+not predict and the insolation forcing; more output than input time steps (first / last times preferred); imputing.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import estimator as OE
+from oracle import layers as OL
+from tests.helpers import build_product_sequential
+
+pytestmark = pytest.mark.gpu
+H, W = 12, 16
+
+
+def _setup(t_in, t_out, in_vl, out_vl, sol, seed=0):
+    from dlwp_b200.model import ArraySeriesGenerator
+    rng = np.random.RandomState(seed)
+    varlev = ['z/500', 't/850', 'u/300']
+    nt = 14
+    data = rng.standard_normal((nt, 3, H, W)).astype(np.float32)
+    times = np.datetime64('2003-03-01T00:00') + np.arange(nt) * np.timedelta64(6, 'h')
+    lat, lon = np.linspace(80, -80, H), np.arange(0, 360, 360. / W)
+    gen = ArraySeriesGenerator(data, times, lat, lon, varlev, in_vl, out_vl, t_in, t_out, 1, sol)
+    cf = 'channels_first'
+    cin, cout = gen.convolution_shape[0], gen.output_convolution_shape[0]
+    layers = (('PeriodicPadding2D', ((0, 1),), {'data_format': cf, 'input_shape': gen.convolution_shape}),
+              ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+              ('Conv2D', (8, 3), {'activation': 'tanh', 'data_format': cf}),
+              ('PeriodicPadding2D', ((0, 1),), {'data_format': cf}),
+              ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+              ('Conv2D', (cout, 3), {'activation': 'linear', 'data_format': cf}))
+    dlwp = build_product_sequential(layers, time_dim=t_in)
+    net = OL.OSequential(layers)
+    OL.init_weights(net.conv_layers, seed=seed + 1, bias_scale=0.05)
+    dlwp.model.set_weights(net.get_weights())
+    assert cin == t_in * (len(in_vl) + (1 if sol else 0))
+    return dlwp, net, gen
+
+
+@pytest.mark.parametrize('t_in,t_out,in_vl,out_vl,sol,impute,first', [
+    (2, 1, ['z/500', 't/850', 'u/300'], ['z/500', 't/850'], True, False, True),
+    (2, 2, ['z/500', 't/850'], ['z/500', 't/850'], False, False, True),
+    (1, 2, ['z/500', 't/850'], ['t/850', 'z/500'], False, False, True),
+    (1, 2, ['z/500', 't/850'], ['z/500', 't/850'], True, False, False),
+    (2, 1, ['z/500', 'u/300'], ['z/500'], True, True, True),
+])
+def test_estimator_matches_restated_reference_loop(t_in, t_out, in_vl, out_vl, sol, impute, first):
+    from dlwp_b200.model import TimeSeriesEstimator
+    dlwp, net, gen = _setup(t_in, t_out, in_vl, out_vl, sol)
+    est = TimeSeriesEstimator(dlwp, gen)
+    steps = 5
+    got = est.predict(steps, impute=impute, prefer_first_times=first)
+    p, _ = gen.generate([], scale_and_impute=False)
+    in_names = list(in_vl) + (['SOL'] if sol else [])
+    fn = lambda x: net.forward(np.asarray(x, np.float64)).astype(np.float32)
+    res, es, keep = OE.estimator_predict(fn, p, steps, t_in, t_out, in_names, out_vl, gen.sample_times,
+                                         gen.times[1] - gen.times[0], gen.lat, gen.lon, 1, sol, impute, first)
+    ref = OE.estimator_series(res, steps, es, keep, False, first)
+    vals = np.asarray(got.values)
+    assert tuple(got.dims) == ('f_hour', 'time', 'varlev', 'lat', 'lon')
+    assert vals.shape == ref.shape == (steps, gen._n_sample, len(out_vl), H, W)
+    np.testing.assert_array_equal(np.isnan(vals), np.isnan(ref))          # the same samples run out of data
+    assert np.isfinite(ref[:, 0]).all()
+    ok = np.isfinite(ref)
+    assert np.abs(vals[ok] - ref[ok]).max() <= 3e-5 * np.abs(ref[ok]).max()
+    kt = est.predict(steps, impute=impute, prefer_first_times=first, keep_time_dim=True)
+    assert tuple(kt.dims) == ('f_hour', 'time', 'time_step', 'varlev', 'lat', 'lon')
+    okk = np.isfinite(res)
+    assert np.abs(np.asarray(kt.values)[okk] - res[okk]).max() <= 3e-5 * np.abs(res[okk]).max()
+    # f_hour coordinates (extensions.py:283-285): multiples of the sample spacing
+    fh = np.asarray(got.coords['f_hour']) if isinstance(got.coords, dict) else got.coords['f_hour'].values
+    assert fh[0] == np.timedelta64(6, 'h') and len(fh) == steps
+
+
+def test_estimator_argument_errors():
+    from dlwp_b200.model import TimeSeriesEstimator
+    dlwp, _, gen = _setup(1, 1, ['z/500'], ['z/500'], False)
+    with pytest.raises(TypeError):
+        TimeSeriesEstimator(object(), gen)
+    with pytest.raises(TypeError):
+        TimeSeriesEstimator(dlwp, object())
+    with pytest.raises(ValueError):
+        TimeSeriesEstimator(dlwp, gen).predict(0)

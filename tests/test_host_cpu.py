@@ -310,3 +310,38 @@ def test_channels_last_model_lowers_with_layout_ops(nat):
     dlwp.build_model(mixed, loss='mse', optimizer='adam')
     with pytest.raises(NotImplementedError):
         Lowering(dlwp.model)
+
+
+def test_time_series_estimator_host_loop_and_coordinates():
+    """TimeSeriesEstimator (extensions.py:136-303) on the host loop, the network replaced by the oracle: values equal the
+    numpy restatement (oracle/estimator.py), dimension names and coordinate values follow extensions.py:259-292."""
+    from dlwp_b200.model import ArraySeriesGenerator, DLWPNeuralNet, TimeSeriesEstimator
+    from oracle import estimator as OE
+    rng = np.random.RandomState(0)
+    varlev = ['z/500', 't/850', 'u/300']
+    nt, Hh, Ww = 12, 6, 8
+    data = rng.standard_normal((nt, 3, Hh, Ww)).astype(np.float32)
+    times = np.datetime64('2003-03-01T00:00') + np.arange(nt) * np.timedelta64(6, 'h')
+    lat, lon = np.linspace(80, -80, Hh), np.arange(0, 360, 45.)
+    gen = ArraySeriesGenerator(data, times, lat, lon, varlev, ['z/500', 't/850', 'u/300'], ['z/500', 't/850'], 2, 1, 1, True)
+    assert gen.convolution_shape == (8, Hh, Ww) and gen.output_convolution_shape == (2, Hh, Ww) and gen._n_sample == 10
+    p, t = gen.generate([])
+    assert p.shape == (10, 8, Hh, Ww) and t.shape == (10, 2, Hh, Ww)
+    np.testing.assert_array_equal(t[0].reshape(1, 2, Hh, Ww)[0], data[2, :2])         # target = the step after the inputs
+    w = rng.standard_normal((8, 2)).astype(np.float32)
+    fn = lambda x: np.einsum('nchw,co->nohw', np.asarray(x, np.float32), w)
+    dlwp = DLWPNeuralNet(is_convolutional=True, time_dim=2, scaler_type=None, scale_targets=False)
+    dlwp.predict = lambda x, **kw: fn(x)
+    est = TimeSeriesEstimator(dlwp, gen)
+    est._device_ok = lambda: False
+    out = est.predict(4)
+    res, es, keep = OE.estimator_predict(fn, p, 4, 2, 1, ['z/500', 't/850', 'u/300', 'SOL'], ['z/500', 't/850'],
+                                         gen.sample_times, np.timedelta64(6, 'h'), lat, lon, 1, True, False, True)
+    ref = OE.estimator_series(res, 4, es, keep)
+    np.testing.assert_array_equal(np.asarray(out.values), ref)
+    assert np.isnan(ref[1, -1]).all() and np.isfinite(ref[1, :-1]).all()      # one sample per step runs out of data
+    coords = out.coords if isinstance(out.coords, dict) else {k: v.values for k, v in out.coords.items()}
+    assert tuple(out.dims) == ('f_hour', 'time', 'varlev', 'lat', 'lon')
+    assert list(coords['f_hour']) == [np.timedelta64(6 * k, 'h') for k in (1, 2, 3, 4)]
+    assert coords['time'][0] == times[1]                                       # the last input time of sample 0
+    assert list(coords['varlev']) == ['z/500', 't/850']

@@ -230,3 +230,17 @@ def test_conv_lstm_first_step_and_gate_algebra():
     for zt in z2:
         cst = OO.hard_sigmoid(zt[:, 2:4]) * cst + OO.hard_sigmoid(zt[:, :2]) * np.tanh(zt[:, 4:6])
     np.testing.assert_allclose(y0, OO.hard_sigmoid(z2[-1][:, 6:]) * np.tanh(cst), atol=1e-14)
+
+
+def test_insolation_matches_reference_function(golden_dir):
+    """DLWP/util.py:300-352 run from the reference's source text (tests/golden/make_golden.py:gen_insolation)."""
+    from oracle import estimator as OE
+    from dlwp_b200 import util
+    g = _load(golden_dir, 'insolation.npz')
+    dates = g['dates'].astype('datetime64[s]')
+    for fn in (OE.insolation, util.insolation):
+        np.testing.assert_array_equal(fn(dates, g['lat'], g['lon']), g['sol'])
+        lon2, lat2 = np.meshgrid(g['lon'], g['lat'])
+        np.testing.assert_array_equal(fn(dates[:3], lat2, lon2, S=2.), g['sol2'])
+        with pytest.raises(ValueError):
+            fn(dates, lat2, g['lon'])
