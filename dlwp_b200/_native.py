@@ -75,6 +75,7 @@ class NetDesc(ctypes.Structure):
 SYMBOLS = {
     'dlwp_conv2d_fwd': (ctypes.c_int, [ctypes.POINTER(ConvDesc), fptr, fptr, fptr, fptr, ctypes.c_void_p]),
     'dlwp_pad2d': (ctypes.c_int, [fptr, fptr] + [i32] * 10 + [i64] * 6 + [ctypes.c_void_p]),
+    'dlwp_gather_series': (ctypes.c_int, [fptr] * 4 + [i32] * 9 + [ctypes.c_void_p]),
     'dlwp_layout2d': (ctypes.c_int, [fptr, fptr] + [i32] * 5 + [ctypes.c_void_p]),
     'dlwp_maxpool2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
     'dlwp_upsample2d': (ctypes.c_int, [fptr, fptr] + [i32] * 4 + [i64] * 6 + [ctypes.c_void_p]),
@@ -152,7 +153,8 @@ def lib():
             raise ImportError(
                 'libdlwp_b200.so is not built (%s). Run `python -m dlwp_b200.build` (needs nvcc); dlwp_b200 has no '
                 'CPU or PyTorch fallback for its CUDA kernels.' % LIB_PATH)
-        handle = ctypes.CDLL(LIB_PATH)
+        # DLWP_B200_LIB: an alternative build of the same ABI (A/B experiments: scripts/build_variants.sh)
+        handle = ctypes.CDLL(os.environ.get('DLWP_B200_LIB') or LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if the ABI and the binding drift apart
             fn.restype = res

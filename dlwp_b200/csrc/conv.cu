@@ -92,6 +92,128 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectParams p) 
 }
 
 // =================================================================================================================
+// RowConnected2D (DLWP/custom.py:695-896: a conv whose weights differ per output row) as a tiled kernel.
+// The reference runs H_out separate K.conv2d calls on row slabs (custom.py:879-893).  Here one CTA owns ONE output row of a
+// chunk of samples: that row's whole weight set (kh*kw*Cin*Cout floats: 38 KB for the 5x5, 32 -> 12 layer of
+// examples/train_functional.py:191-196) is staged in shared memory once and every thread computes 4 adjacent pixels x all
+// filters in registers -- per (channel, tap row) 4 + dw*(kw-1) input values feed kw*4*Cout FMAs, weights arrive as
+// broadcast 16-byte shared-memory loads (~10 FMAs per memory instruction; the direct kernel does 1).
+// =================================================================================================================
+struct RowwiseParams {
+    const float* x;
+    const float* w;      // (H_out, kh, kw, Cin, Cout)
+    const float* bias;   // (H_out, Cout) or null
+    float* y;
+    int N, Cin, H, W, Cout, Wo, pad_t, pad_l, dh, mode_h, mode_w, act, row0, xgroups;
+    long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;
+};
+
+template <int KH, int KW, int DW, int COUT_T>
+__global__ void __launch_bounds__(256) conv_rowwise_kernel(const RowwiseParams p) {
+    extern __shared__ __align__(16) float ws[];          // [i][j][c][COUT_T]
+    constexpr int NV = 4 + DW * (KW - 1);
+    const int yo = p.row0 + blockIdx.x;
+    const float* wrow = p.w + (long long)yo * KH * KW * p.Cin * p.Cout;
+    for (int idx = threadIdx.x; idx < KH * KW * p.Cin * COUT_T; idx += blockDim.x) {
+        const int o = idx % COUT_T, r = idx / COUT_T;     // r = (i*KW + j)*Cin + c
+        ws[idx] = o < p.Cout ? wrow[(long long)r * p.Cout + o] : 0.f;
+    }
+    __syncthreads();
+    const long long items = (long long)p.N * p.xgroups;
+    for (long long it = blockIdx.y * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.y * blockDim.x) {
+        const int xg = (int)(it % p.xgroups), n = (int)(it / p.xgroups);
+        const int x0 = 4 * xg;
+        float acc[4][COUT_T];
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int o = 0; o < COUT_T; ++o) acc[px][o] = (p.bias && o < p.Cout) ? p.bias[(long long)yo * p.Cout + o] : 0.f;
+        int gxs[NV];
+        bool okx[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            int gx = x0 + t - p.pad_l;
+            bool ok = true;
+            if (p.mode_w == DLWP_PAD_PERIODIC) gx = wrap_index(gx, p.W);
+            else if (gx < 0 || gx >= p.W) { ok = false; gx = 0; }
+            gxs[t] = gx; okx[t] = ok;
+        }
+        const float* xn = p.x + (long long)n * p.xs_n;
+#pragma unroll 1
+        for (int c = 0; c < p.Cin; ++c) {
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                int gy = yo + p.dh * i - p.pad_t;
+                if (p.mode_h == DLWP_PAD_PERIODIC) gy = wrap_index(gy, p.H);
+                else if (gy < 0 || gy >= p.H) continue;
+                const float* xr = xn + (long long)c * p.xs_c + (long long)gy * p.xs_h;
+                float v[NV];
+#pragma unroll
+                for (int t = 0; t < NV; ++t) v[t] = okx[t] ? __ldg(xr + gxs[t]) : 0.f;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const float4* w4 = reinterpret_cast<const float4*>(ws + ((long long)(i * KW + j) * p.Cin + c) * COUT_T);
+#pragma unroll
+                    for (int o4 = 0; o4 < COUT_T / 4; ++o4) {
+                        const float4 wv = w4[o4];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            const float xv = v[px + DW * j];
+                            acc[px][4 * o4 + 0] = fmaf(xv, wv.x, acc[px][4 * o4 + 0]);
+                            acc[px][4 * o4 + 1] = fmaf(xv, wv.y, acc[px][4 * o4 + 1]);
+                            acc[px][4 * o4 + 2] = fmaf(xv, wv.z, acc[px][4 * o4 + 2]);
+                            acc[px][4 * o4 + 3] = fmaf(xv, wv.w, acc[px][4 * o4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        float* yn = p.y + (long long)n * p.ys_n + (long long)yo * p.ys_h;
+#pragma unroll
+        for (int o = 0; o < COUT_T; ++o)
+            if (o < p.Cout) {
+#pragma unroll
+                for (int px = 0; px < 4; ++px)
+                    if (x0 + px < p.Wo) yn[(long long)o * p.ys_c + x0 + px] = apply_act(acc[px][o], p.act);
+            }
+    }
+}
+
+template <int KH, int KW, int DW, int COUT_T>
+static int launch_rowwise(const RowwiseParams& p, int rows, size_t smem, cudaStream_t stream) {
+    static std::atomic<unsigned long long> done{0};
+    if (first_use_on_device(done))
+        cudaFuncSetAttribute(conv_rowwise_kernel<KH, KW, DW, COUT_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const long long items = (long long)p.N * p.xgroups;
+    const int by = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, 64));
+    conv_rowwise_kernel<KH, KW, DW, COUT_T><<<dim3(rows, by), 256, smem, stream>>>(p);
+    return after_launch("conv_rowwise_kernel");
+}
+
+// 0: launched; -1: no instance for this geometry (the caller falls back to the direct kernel)
+static int conv2d_rowwise(const DlwpConvDesc& d, const float* x, const float* w, const float* bias, float* y, int Wo,
+                          int row0, int rows, cudaStream_t stream, int* rc_out) {
+    if (d.pre_op || d.kh != d.kw || d.Cout > 16) return -1;
+    const int cout_t = d.Cout <= 4 ? 4 : (d.Cout <= 8 ? 8 : (d.Cout <= 12 ? 12 : 16));
+    const size_t smem = (size_t)d.kh * d.kw * d.Cin * cout_t * sizeof(float);
+    if (smem > 200 * 1024) return -1;
+    RowwiseParams p;
+    p.x = x; p.w = w; p.bias = bias; p.y = y;
+    p.N = d.N; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Cout = d.Cout; p.Wo = Wo; p.pad_t = d.pad_t; p.pad_l = d.pad_l;
+    p.dh = d.dil_h; p.mode_h = d.pad_mode_h; p.mode_w = d.pad_mode_w; p.act = d.act; p.row0 = row0;
+    p.xgroups = (Wo + 3) / 4;
+    p.xs_n = d.x_stride_n; p.xs_c = d.x_stride_c; p.xs_h = d.x_stride_h;
+    p.ys_n = d.y_stride_n; p.ys_c = d.y_stride_c; p.ys_h = d.y_stride_h;
+#define DLWP_ROWWISE_CASE(K_, D_, C_) \
+    if (d.kh == K_ && d.dil_w == D_ && cout_t == C_) { *rc_out = launch_rowwise<K_, K_, D_, C_>(p, rows, smem, stream); return 0; }
+    DLWP_ROWWISE_CASE(5, 1, 12) DLWP_ROWWISE_CASE(5, 1, 8) DLWP_ROWWISE_CASE(5, 1, 16) DLWP_ROWWISE_CASE(5, 1, 4)
+    DLWP_ROWWISE_CASE(3, 1, 12) DLWP_ROWWISE_CASE(3, 1, 8) DLWP_ROWWISE_CASE(3, 1, 16) DLWP_ROWWISE_CASE(3, 1, 4)
+    DLWP_ROWWISE_CASE(3, 2, 12) DLWP_ROWWISE_CASE(3, 2, 8) DLWP_ROWWISE_CASE(3, 2, 16) DLWP_ROWWISE_CASE(3, 2, 4)
+#undef DLWP_ROWWISE_CASE
+    return -1;
+}
+
+// =================================================================================================================
 // Register-tiled FFMA kernel
 // =================================================================================================================
 struct TileParams {
@@ -729,6 +851,12 @@ int conv2d_fwd(const DlwpConvDesc& d, const float* x, const float* w, const floa
         return after_launch("conv_ffma_kernel");
     }
 
+    if (d.rowwise && d.impl != DLWP_IMPL_DIRECT) {   // RowConnected2D: the tiled per-row kernel when it has an instance
+        int rc = 0;
+        if (conv2d_rowwise(d, x, w, bias, y, Wo, all_rows ? 0 : d.row_begin, all_rows ? Ho : d.row_end - d.row_begin,
+                           stream, &rc) == 0)
+            return rc;
+    }
     DirectParams p;
     p.x = x; p.w = w; p.bias = bias; p.y = y;
     p.N = d.N; p.Cin = d.Cin; p.Hs = d.H; p.Ws = d.W; p.H = H; p.W = W;

@@ -428,9 +428,14 @@ __device__ __forceinline__ void sw_issue_row_static(int pos_lo, bool leader, uin
 // instance serves any layer; the example nets' layers get instances with everything folded (conv_sw_net_*.cu), which
 // matters because the single MMA-issuing warp (and, for many filters, the epilogue's instruction issue) is the kernel's
 // critical path.
-template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int FOLD_ = 0, int BF16_ = 0>
+template <int NCOLS_, int KS_, int D_, int CBLK_, int ACT_, int OUT_, int FULL_ = 0, int FOLD_ = 0, int BF16_ = 0,
+          int PEERS_ = 0>
 struct SwStatic {
     static constexpr int BF16 = BF16_;  // 1: bf16 operands / images, one MMA pass
+    // 1: the epilogue can also store rows into the latitude-band neighbours' images (SwParams::yp_up / yp_down).  A flavour of
+    // its own because even the untaken branches cost the hottest epilogues 3-7 % (profiles/r02_variants_ab.txt); the
+    // generic instances (NCOLS_ == 0) always carry the code.
+    static constexpr int PEERS = (PEERS_ != 0 || NCOLS_ == 0) ? 1 : 0;
     static constexpr int NCOLS = NCOLS_, KS = KS_, D = D_, CBLK = CBLK_, ACT = ACT_, OUT = OUT_;  // OUT: 1 = P, 2 = fp32, 3 = both
     static constexpr int FULL = FULL_;  // 1: Cout == CBLK * NC, no partial filter block
     static constexpr int FOLD = FOLD_;  // vertical taps per MMA (0: SwParams::fold)
@@ -772,10 +777,12 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                 uint4* row_hi = has_yp ? ypn + (size_t)y * p.Wp_out : nullptr;
                 // element distance from this row of the local image to the same row of a neighbour's image (0: none)
                 long long peer_d[2] = {0, 0};
-                if (has_yp && p.yp_up != nullptr && y < p.peer_up_end)
-                    peer_d[0] = reinterpret_cast<uint4*>(p.yp_up) - reinterpret_cast<uint4*>(p.yp);
-                if (has_yp && p.yp_down != nullptr && y >= p.peer_down_begin)
-                    peer_d[1] = reinterpret_cast<uint4*>(p.yp_down) - reinterpret_cast<uint4*>(p.yp);
+                if constexpr (ST::PEERS != 0) {
+                    if (has_yp && p.yp_up != nullptr && y < p.peer_up_end)
+                        peer_d[0] = reinterpret_cast<uint4*>(p.yp_up) - reinterpret_cast<uint4*>(p.yp);
+                    if (has_yp && p.yp_down != nullptr && y >= p.peer_down_begin)
+                        peer_d[1] = reinterpret_cast<uint4*>(p.yp_down) - reinterpret_cast<uint4*>(p.yp);
+                }
 #pragma unroll(ST::CBLK ? ST::CBLK : 1)
                 for (int cb = 0; cb < CBLK; ++cb) {
                     float d[KW][8];
@@ -843,14 +850,16 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                             __stcs(row_hi, vb);
                             if (halo_r) __stcs(row_hi + p.W, vb);
                             if (halo_l) __stcs(row_hi - p.W, vb);
+                            if constexpr (ST::PEERS != 0) {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
-                                    uint4* pr = row_hi + peer_d[k];
-                                    __stcs(pr, vb);
-                                    if (halo_r) __stcs(pr + p.W, vb);
-                                    if (halo_l) __stcs(pr - p.W, vb);
-                                }
+                                for (int k = 0; k < 2; ++k)
+                                    if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
+                                        uint4* pr = row_hi + peer_d[k];
+                                        __stcs(pr, vb);
+                                        if (halo_r) __stcs(pr + p.W, vb);
+                                        if (halo_l) __stcs(pr - p.W, vb);
+                                    }
+                            }
                         } else if (has_yp) {
                             // the bound behind 2^e_out makes this unreachable for finite data; NaN / inf land here
                             if (!(am * sout <= 65504.f)) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
@@ -870,16 +879,18 @@ conv_sw_kernel(const SwParams p, const __grid_constant__ CUtensorMap map_full, c
                                 __stcs(row_hi - p.W, vh);
                                 __stcs(row_lo - p.W, vl);
                             }
+                            if constexpr (ST::PEERS != 0) {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
-                                    uint4* ph = row_hi + peer_d[k];
-                                    uint4* plo = row_lo + peer_d[k];
-                                    __stcs(ph, vh);
-                                    __stcs(plo, vl);
-                                    if (halo_r) { __stcs(ph + p.W, vh); __stcs(plo + p.W, vl); }
-                                    if (halo_l) { __stcs(ph - p.W, vh); __stcs(plo - p.W, vl); }
-                                }
+                                for (int k = 0; k < 2; ++k)
+                                    if (peer_d[k] != 0) {          // the neighbour's halo rows, over NVLink
+                                        uint4* ph = row_hi + peer_d[k];
+                                        uint4* plo = row_lo + peer_d[k];
+                                        __stcs(ph, vh);
+                                        __stcs(plo, vl);
+                                        if (halo_r) { __stcs(ph + p.W, vh); __stcs(plo + p.W, vl); }
+                                        if (halo_l) { __stcs(ph - p.W, vh); __stcs(plo - p.W, vl); }
+                                    }
+                            }
                         }
                     }
                     if (has_yp) row_hi += (ST::BF16 ? 1 : 2) * plane_stride;
@@ -921,14 +932,18 @@ struct SwFolded {
     SwLaunchFn fn;
     const char* what;
     int BF16;   // 1: the bf16 flavour of the instance
+    int PEERS;  // 1: the flavour whose epilogue also stores into the latitude-band neighbours' images
 };
 #define SW_FOLDED_ENTRY(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
     {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                          \
-     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT, 0}
-#define SW_FOLDED_ENTRY_BF16(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT)                                      \
-    {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                                                                    \
-     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH), 1>>, \
-     WHAT, 1}
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT, 0, 0}
+// BF16 / PEERS flavours: SW_FOLDED_ENTRY_X(..., WHAT, bf16, peers)
+#define SW_FOLDED_ENTRY_X(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT, BF, PE)                                       \
+    {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                                                                          \
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH), BF, PE>>, \
+     WHAT, BF, PE}
+#define SW_FOLDED_ENTRY_BF16(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
+    SW_FOLDED_ENTRY_X(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT, 1, 0)
 
 static inline int sw_tu_flags_read_clear() {
     int v = 0, zero = 0;

@@ -14,6 +14,8 @@ static const SwFolded kTable[] = {
     SW_FOLDED_ENTRY_BF16(3, 3, 8, 96, 8, 1, 4, DLWP_ACT_TANH, 1, 1, "bf16 Net B conv_2d_4: 128->32 3x3 tanh"),
     SW_FOLDED_ENTRY_BF16(3, 3, 8, 48, 4, 2, 2, DLWP_ACT_TANH, 1, 1, "bf16 Net B conv_2d_5: 64->16 3x3 dil 2 tanh"),
     SW_FOLDED_ENTRY_BF16(5, 5, 8, 80, 2, 1, 2, DLWP_ACT_LINEAR, 3, 0, "bf16 Net B conv_2d_6: 32->12 5x5 linear, fp32 series + P feedback"),
+    SW_FOLDED_ENTRY_X(5, 5, 8, 80, 2, 1, 2, DLWP_ACT_LINEAR, 3, 0,
+                      "bf16 Net B conv_2d_6: 32->12 5x5 linear, fp32 series + P feedback + latitude-band neighbours' halo rows", 1, 1),
 };
 const SwFolded* sw_folded_bf16(int* n) {
     *n = (int)(sizeof(kTable) / sizeof(kTable[0]));

@@ -9,6 +9,8 @@ static const SwFolded kTable[] = {
     SW_FOLDED_ENTRY(3, 1, 8, 32, 2, 2, 4, DLWP_ACT_TANH, 1, 1, "Net A conv1: 6->32 3x3 dil 2 tanh"),
     SW_FOLDED_ENTRY(5, 5, 6, 32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1, "Net A conv2: 32->6 5x5 linear, fp32 series + P feedback"),
     SW_FOLDED_ENTRY(5, 5, 6, 32, 2, 1, 1, DLWP_ACT_LINEAR, 2, 1, "Net A conv2: 32->6 5x5 linear, fp32 only"),
+    SW_FOLDED_ENTRY_X(5, 5, 6, 32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1,
+                      "Net A conv2: 32->6 5x5 linear, fp32 series + P feedback + latitude-band neighbours' halo rows", 0, 1),
 };
 const SwFolded* sw_folded_net_a(int* n) {
     *n = (int)(sizeof(kTable) / sizeof(kTable[0]));

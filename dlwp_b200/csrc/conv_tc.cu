@@ -453,7 +453,7 @@ static int sw_unit_geometry(const DlwpConvDesc& d, const TcLayer& L, int sms, in
     return std::max(1, std::min(sms, p.total_rows / min_rows));
 }
 
-static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int nc, int out_mode) {
+static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int nc, int out_mode, int peers = 0) {
     const int full = (d.Cout == L.CBLK * nc) ? 1 : 0;
     const int bf16 = L.ppc == 1 ? 1 : 0;
     typedef const SwFolded* (*TableFn)(int*);
@@ -462,7 +462,7 @@ static const SwFolded* find_folded(const DlwpConvDesc& d, const TcLayer& L, int 
         int n = 0;
         const SwFolded* f = t(&n);
         for (int i = 0; i < n; ++i)
-            if (f[i].BF16 == bf16 && f[i].KH == d.kh && f[i].KWE == L.kw_eff && f[i].NC == nc && f[i].NCOLS == L.NCOLS && f[i].KS == L.KS &&
+            if (f[i].BF16 == bf16 && f[i].PEERS == peers && f[i].KH == d.kh && f[i].KWE == L.kw_eff && f[i].NC == nc && f[i].NCOLS == L.NCOLS && f[i].KS == L.KS &&
                 f[i].D == d.dil_w && f[i].CBLK == L.CBLK && f[i].ACT == d.act && f[i].OUT == out_mode && f[i].FULL == full)
                 return &f[i];
     }
@@ -521,7 +521,8 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
         }
     }
     const int out_mode = (yp ? 1 : 0) | (y32 ? 2 : 0);
-    const SwFolded* f = opt.generic ? nullptr : find_folded(d, L, nc, out_mode);
+    const int want_peers = (p.yp_up || p.yp_down) ? 1 : 0;
+    const SwFolded* f = opt.generic ? nullptr : find_folded(d, L, nc, out_mode, want_peers);
     if (f) f->fn(p, map_full, map_pair, grid, L.smem, stream);
     else if (p.bf16) {
         DLWP_REQUIRE(sw_launch_generic_bf16(d.kh, L.kw_eff, nc, p, map_full, map_pair, grid, L.smem, stream), DLWP_ESHAPE,

@@ -95,6 +95,30 @@ __global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ x
     }
 }
 
+// SeriesDataGenerator batch assembly: a gather of (time, variable) planes.  One thread per 4 consecutive floats of a plane
+// when H*W is a multiple of 4 (16-byte loads / stores), else per float.
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_series_kernel(const float* __restrict__ data, const long long* __restrict__ samples,
+                                                           const int* __restrict__ sel, float* __restrict__ out, int B, int T,
+                                                           int V, int V_total, long long hw, int t_off, int out_c_per_t,
+                                                           int out_c0) {
+    const long long per = hw / VEC;
+    const long long total = (long long)B * T * V * per;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long e = idx % per;
+        long long r = idx / per;
+        const int v = (int)(r % V);
+        r /= V;
+        const int t = (int)(r % T);
+        const int b = (int)(r / T);
+        const float* src = data + ((samples[b] + t_off + t) * V_total + sel[v]) * hw + e * VEC;
+        float* dst = out + (((long long)b * T + t) * out_c_per_t + out_c0 + v) * hw + e * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+        else *dst = __ldg(src);
+    }
+}
+
 // Halo rows of a latitude-band rollout: up to two row blocks of a (N, C, H, W) tensor <-> two contiguous staging buffers
 // (N, C, rows, W), ONE launch for both neighbours (plan.cu: halo_exchange).
 struct HaloCopyParams {
@@ -229,6 +253,24 @@ extern "C" int dlwp_pad2d(const float* x, float* y, int32_t N, int32_t C, int32_
     EwParams p{x, y, N, C, H, W, H + pad_t + pad_b, W + pad_l + pad_r, pad_t, pad_l, mode_h, mode_w, 0, 0,
                xs_n, xs_c, xs_h, ys_n, ys_c, ys_h};
     return launch<EW_PAD>(p, (cudaStream_t)stream, "pad2d");
+}
+
+extern "C" int dlwp_gather_series(const float* data, const int64_t* samples, const int32_t* sel, float* out, int32_t B,
+                                  int32_t T, int32_t V, int32_t V_total, int32_t H, int32_t W, int32_t t_off,
+                                  int32_t out_c_per_t, int32_t out_c0, dlwp_stream_t stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    DLWP_REQUIRE(data && samples && sel && out, DLWP_EINVAL, "null pointer");
+    DLWP_REQUIRE(B > 0 && T > 0 && V > 0 && V_total > 0 && H > 0 && W > 0 && t_off >= 0, DLWP_ESHAPE, "bad dims");
+    DLWP_REQUIRE(out_c0 >= 0 && out_c0 + V <= out_c_per_t, DLWP_ESHAPE, "channel window outside the destination");
+    const long long hw = (long long)H * W;
+    const bool vec = hw % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const long long total = (long long)B * T * V * (vec ? hw / 4 : hw);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    const long long* sm = reinterpret_cast<const long long*>(samples);
+    if (vec) gather_series_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(data, sm, sel, out, B, T, V, V_total, hw, t_off, out_c_per_t, out_c0);
+    else gather_series_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(data, sm, sel, out, B, T, V, V_total, hw, t_off, out_c_per_t, out_c0);
+    return after_launch("gather_series_kernel");
 }
 
 extern "C" int dlwp_layout2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t to_nchw,

@@ -207,6 +207,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): issued a row ahead by the MMA issuer, consumed after that row's MMAs have been
+// issued, so the barrier's round trip overlaps the issue stream instead of heading every row.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a TMA that never completes (bad descriptor) raises a flag the host can read (dlwp_debug_flags) and
 // lets the kernel finish with garbage instead of hanging the GPU.
 // try_wait with a suspend-time hint: the warp may sleep up to ~hint ns per attempt instead of re-polling (idle epilogue /

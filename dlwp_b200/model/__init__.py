@@ -1,8 +1,8 @@
 """Mirror of `DLWP.model` (reference DLWP/model/__init__.py:11-17).  The xarray/netCDF-dependent classes are resolved
 lazily because those packages are unavailable offline and lie outside the rollout hot path."""
 
-from .generators import (ArrayDataGenerator, ArraySeriesGenerator, DataGenerator, SeriesDataGenerator,  # noqa: F401
-                         SmartDataGenerator)
+from .generators import (ArrayDataGenerator, ArraySeriesGenerator, DataGenerator, DeviceSeriesGenerator,  # noqa: F401
+                         SeriesDataGenerator, SmartDataGenerator)
 from .extensions import TimeSeriesEstimator  # noqa: F401,E402
 from .models import DLWPFunctional, DLWPNeuralNet  # noqa: F401,E402
 

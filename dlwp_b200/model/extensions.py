@@ -187,16 +187,32 @@ class TimeSeriesEstimator(object):
         else:
             pairs = [(k, t_out - t_in + k) for k in range(t_in)]
         eng.lib.dlwp_debug_flags()
-        valid = S          # samples whose inputs are all known: the re-indexing runs `shift` samples past the data per step
+        # Which inputs are known (not NaN) is tracked on the host, per (sample, time step, varlev): the re-indexing runs
+        # `shift` samples past the data per step, imputing / insolation / re-inserted outputs fill some of it back in.
+        known = np.isfinite(p.reshape(S, t_in, V_in, -1)).all(axis=3)
         for s in range(effective_steps):
             # Only the valid samples go through the network: a NaN sample would poison the shared power-of-two exponent of
             # the tensor-core images (their amax); the reference's NaN rows come out as NaN here too.
+            ok = known.all(axis=(1, 2))
+            valid = int(np.argmin(ok)) if not ok.all() else S
+            if ok[valid:].any():           # a hole in the sample axis (never produced by this loop): take the host path
+                return self._predict_host(p, effective_steps, S, t_in, t_out, V_in, V_out, H, W, shift, es, keep_inputs,
+                                          prefer_first_times, impute, idx_in, idx_out, in_vl,
+                                          times - s * shift * self._dt, lat, lon, {})
             if valid > 0:
                 eng.forward_into(cur[:valid], [series[s][:valid]])
             if valid < S:
-                series[s][max(valid, 0):].fill_(float('nan'))
-            if not impute:
-                valid -= shift
+                series[s][valid:].fill_(float('nan'))
+            nk = np.zeros_like(known)
+            if shift < S:
+                nk[:S - shift] = known[shift:]
+            if impute:
+                nk[S - es:] = True
+            if self._add_insolation:
+                nk[S - es:, :, in_vl.index('SOL')] = True
+            for ti, to in pairs:
+                nk[:, ti, idx_in] = ok[:, None]
+            known = nk
             times = times + shift * self._dt
             # p_da.reindex(sample=...) (extensions.py:226): sample i takes the predictors of sample i + shift
             nxt.fill_(float('nan'))

@@ -104,3 +104,73 @@ class ArraySeriesGenerator(object):
         off = ti + self._interval - 1
         t = np.stack([self.data[off + n:off + n + S][:, iout] for n in range(to)], axis=1)
         return p.reshape((S,) + self.convolution_shape), t.reshape((S,) + self.output_convolution_shape)
+
+
+class DeviceSeriesGenerator(Sequence):
+    """
+    `SeriesDataGenerator` (DLWP/model/generators.py:425-640) with the data array RESIDENT ON THE GPU: `__getitem__` assembles
+    a batch -- time-shifted predictor slices, the insolation channel, one target array per element of the sequence -- with
+    `dlwp_gather_series` straight out of HBM and returns CUDA tensors, which `fit_generator` feeds to the training step
+    without touching the host (the reference gathers with numpy fancy indexing from an xarray-backed array and Keras copies
+    every batch to the device).  Same metadata as `ArraySeriesGenerator` (which it wraps); `sequence` = number of target
+    arrays (examples/train_functional.py: integration_steps), batches shuffled per epoch like generators.py:146-159.
+    """
+
+    def __init__(self, series, batch_size=32, sequence=None, shuffle=False, seed=0):
+        import ctypes
+        import torch
+        from .. import _native as nat
+        self._nat, self._torch, self._ctypes = nat, torch, ctypes
+        g = self.series = series
+        self.batch_size, self.sequence, self.shuffle = int(batch_size), sequence, bool(shuffle)
+        self._rng = np.random.RandomState(seed)
+        nseq = int(sequence or 1)
+        self._n_sample = g.data.shape[0] - g._input_time_steps - g._output_time_steps * nseq - g._interval + 2
+        if self._n_sample < 1:
+            raise ValueError('not enough time steps for one sample')
+        self.data = torch.from_numpy(np.ascontiguousarray(g.data)).cuda()
+        self._sel_in = torch.tensor([g.varlev.index(v) for v in g._input_sel['varlev']], dtype=torch.int32, device='cuda')
+        self._sel_out = torch.tensor([g.varlev.index(v) for v in g._output_sel['varlev']], dtype=torch.int32, device='cuda')
+        self._zero = torch.zeros(1, dtype=torch.int32, device='cuda')
+        self.sol = None
+        if g._add_insolation:
+            from ..util import insolation
+            self.sol = torch.from_numpy(insolation(g.times, g.lat, g.lon)).cuda()      # (n_times, H, W)
+        self.convolution_shape = g.convolution_shape
+        self.output_convolution_shape = g.output_convolution_shape
+        self._idx = np.arange(self._n_sample)
+        self.on_epoch_end()
+
+    def __len__(self):
+        return int(np.ceil(self._n_sample / self.batch_size))
+
+    def on_epoch_end(self):
+        if self.shuffle:
+            self._rng.shuffle(self._idx)
+
+    def _gather(self, data, samples, sel, out, T, V, V_total, t_off, c_per_t, c0):
+        torch, nat = self._torch, self._nat
+        H, W = data.shape[-2:]
+        nat.check(nat.lib().dlwp_gather_series(data.data_ptr(), samples.data_ptr(), sel.data_ptr(), out.data_ptr(),
+                                               samples.numel(), T, V, V_total, H, W, t_off, c_per_t, c0,
+                                               self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                  'dlwp_gather_series')
+
+    def __getitem__(self, index):
+        torch, g = self._torch, self.series
+        sel = self._idx[index * self.batch_size:(index + 1) * self.batch_size]
+        samples = torch.from_numpy(np.ascontiguousarray(sel, np.int64)).cuda()
+        B, ti, to = len(sel), g._input_time_steps, g._output_time_steps
+        H, W = g.data.shape[-2:]
+        vi, vo, vt = self._sel_in.numel(), self._sel_out.numel(), g.data.shape[1]
+        c_in = vi + (1 if self.sol is not None else 0)
+        X = torch.empty((B, ti * c_in, H, W), dtype=torch.float32, device='cuda')
+        self._gather(self.data, samples, self._sel_in, X, ti, vi, vt, 0, c_in, 0)
+        if self.sol is not None:
+            self._gather(self.sol, samples, self._zero, X, ti, 1, 1, 0, c_in, vi)
+        ys = []
+        for s in range(int(self.sequence or 1)):
+            y = torch.empty((B, to * vo, H, W), dtype=torch.float32, device='cuda')
+            self._gather(self.data, samples, self._sel_out, y, to, vo, vt, ti + g._interval - 1 + to * s, vo, 0)
+            ys.append(y)
+        return X, (ys if self.sequence is not None else ys[0])

@@ -84,12 +84,14 @@ def _dist():
 def _step(model, x, y, train):
     import torch
     _check_compiled(model)
-    x = np.ascontiguousarray(x, np.float32)
-    eng = _engine(model, x.shape[0])
+    def dev(a):          # CUDA tensors (DeviceSeriesGenerator) pass through; numpy batches are copied to the device
+        if isinstance(a, torch.Tensor):
+            return a.to(device='cuda', dtype=torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    xd = dev(x)
+    eng = _engine(model, xd.shape[0])
     ys = _as_list(y, eng.n_outputs)
-    xd = torch.from_numpy(x).cuda()
-    yd = [torch.from_numpy(np.ascontiguousarray(v, np.float32).reshape((x.shape[0],) + p)).cuda()
-          for v, p in zip(ys, eng.out_phys)]
+    yd = [dev(v).reshape((xd.shape[0],) + p) for v, p in zip(ys, eng.out_phys)]
     lw = model.loss_weights
     losses, maes = eng.train_step(xd, yd, lw, backward=train)
     if train:

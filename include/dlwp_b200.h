@@ -113,6 +113,16 @@ int dlwp_rows_op(int32_t op, const float* x, float* y, int32_t N, int32_t C, int
 int dlwp_layout2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t to_nchw,
                   dlwp_stream_t stream);
 
+/* Batch assembly of the reference's SeriesDataGenerator.generate (DLWP/model/generators.py:529-605) on the device:
+ *   out[b, t * out_c_per_t + out_c0 + v, :, :] = data[samples[b] + t_off + t, sel[v], :, :]     b < B, t < T, v < V
+ * data: (n_times, V_total, H, W) dense, resident in HBM; samples (B) int64 and sel (V) int32: device arrays; out: (B, T *
+ * out_c_per_t, H, W) dense.  Predictors: t_off = 0, T = input time steps; targets: t_off = input steps + interval - 1 (+
+ * output steps * s for the s-th element of a sequence); the insolation channel is a second call with V_total = V = 1 and
+ * out_c0 = the number of selected variables. */
+int dlwp_gather_series(const float* data, const int64_t* samples, const int32_t* sel, float* out, int32_t B, int32_t T,
+                       int32_t V, int32_t V_total, int32_t H, int32_t W, int32_t t_off, int32_t out_c_per_t,
+                       int32_t out_c0, dlwp_stream_t stream);
+
 /* keras MaxPooling2D(2) ('valid', floor) and UpSampling2D(2) (nearest), channels_first. */
 int dlwp_maxpool2d(const float* x, float* y, int32_t N, int32_t C, int32_t H, int32_t W, int64_t xs_n, int64_t xs_c,
                    int64_t xs_h, int64_t ys_n, int64_t ys_c, int64_t ys_h, dlwp_stream_t stream);

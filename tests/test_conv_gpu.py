@@ -143,6 +143,29 @@ def test_row_connected_matches_oracle_and_reference_golden(env, golden_dir):
     assert rel_err(yb, ref) < TOL
 
 
+@pytest.mark.parametrize('k,d,cout', [(5, 1, 12), (3, 1, 6), (3, 2, 16), (5, 1, 3)])
+def test_row_connected_tiled_kernel_equals_direct_kernel(env, k, d, cout):
+    """conv_rowwise_kernel (one CTA per output row, the row's weights in shared memory) against conv_direct_kernel and the
+    oracle: periodic longitude + zero latitude padding as in examples/train_functional.py:191-196, ragged width."""
+    nat, torch = env
+    rng = np.random.RandomState(12)
+    N, Cin, H, W = 3, 9, 11, 30
+    pad = d * (k - 1) // 2
+    x = rng.standard_normal((N, Cin, H, W)).astype(np.float32)
+    kern = (0.2 * rng.standard_normal((H, k, k, Cin, cout))).astype(np.float32)
+    bias = (0.1 * rng.standard_normal((H, cout))).astype(np.float32)
+    pads = ((pad, pad), (pad, pad))
+    args = (nat, torch, x, kern, bias, d, pads, nat.PAD_ZERO, nat.PAD_PERIODIC, nat.ACT_TANH)
+    y_tiled = run_conv(*args, nat.IMPL_AUTO, rowwise=1)
+    y_direct = run_conv(*args, nat.IMPL_DIRECT, rowwise=1)
+    assert y_tiled.shape == (N, cout, H, W)
+    assert np.abs(y_tiled - y_direct).max() < 2e-6
+    xp = OO.zero_pad2d(OO.periodic_pad2d(x.astype(np.float64), ((0, 0), (pad, pad))), ((pad, pad), (0, 0)))
+    ref = np.stack([OO.conv2d_valid(xp[:, :, r:r + d * (k - 1) + 1], kern[r].astype(np.float64), None, (d, d))[:, :, 0]
+                    for r in range(H)], axis=2) + bias.astype(np.float64).T[None, :, :, None]
+    assert rel_err(y_tiled, np.tanh(ref)) < TOL
+
+
 def test_elementwise_ops_bit_exact(env, golden_dir):
     import os
     nat, torch = env

@@ -85,3 +85,41 @@ def test_estimator_argument_errors():
         TimeSeriesEstimator(dlwp, object())
     with pytest.raises(ValueError):
         TimeSeriesEstimator(dlwp, gen).predict(0)
+
+
+def test_device_series_generator_matches_host_assembly_and_trains():
+    """SURVEY.md 8f rank 4 (second half): SeriesDataGenerator batch assembly on the GPU (dlwp_gather_series) -- bit identical
+    to the host assembly of ArraySeriesGenerator.generate (generators.py:529-605 restated), insolation channel and target
+    sequence included; fit_generator consumes its CUDA tensors directly."""
+    import torch
+    from dlwp_b200.model import ArraySeriesGenerator, DeviceSeriesGenerator
+    rng = np.random.RandomState(5)
+    varlev = ['z/500', 't/850', 'u/300']
+    nt = 20
+    data = rng.standard_normal((nt, 3, H, W)).astype(np.float32)
+    times = np.datetime64('2003-03-01T00:00') + np.arange(nt) * np.timedelta64(6, 'h')
+    lat, lon = np.linspace(80, -80, H), np.arange(0, 360, 360. / W)
+    series = ArraySeriesGenerator(data, times, lat, lon, varlev, ['u/300', 'z/500'], ['z/500'], 2, 2, 1, True)
+    gen = DeviceSeriesGenerator(series, batch_size=4, sequence=3, shuffle=False)
+    assert gen._n_sample == nt - 2 - 2 * 3 - 1 + 2 and len(gen) == (gen._n_sample + 3) // 4
+    p_all, _ = series.generate([])
+    for b in (0, len(gen) - 1):
+        X, ys = gen[b]
+        assert X.is_cuda and len(ys) == 3
+        idx = np.arange(b * 4, min((b + 1) * 4, gen._n_sample))
+        np.testing.assert_array_equal(X.cpu().numpy(), p_all[idx])
+        for s, y in enumerate(ys):
+            ref = np.stack([data[idx + 2 + 2 * s + n][:, [0]] for n in range(2)], axis=1).reshape(len(idx), 2, H, W)
+            np.testing.assert_array_equal(y.cpu().numpy(), ref)
+    # fit_generator straight from device batches: a 1-output net on sequence=None
+    gen1 = DeviceSeriesGenerator(ArraySeriesGenerator(data, times, lat, lon, varlev, ['z/500', 't/850'], ['z/500', 't/850'],
+                                                      1, 1, 1, False), batch_size=6, shuffle=True)
+    cf = 'channels_first'
+    layers = (('PeriodicPadding2D', ((0, 1),), {'data_format': cf, 'input_shape': gen1.convolution_shape}),
+              ('ZeroPadding2D', ((1, 0),), {'data_format': cf}),
+              ('Conv2D', (2, 3), {'activation': 'linear', 'data_format': cf}))
+    dlwp = build_product_sequential(layers)
+    h = dlwp.model.fit_generator(gen1, epochs=3, verbose=0)
+    loss = h.history['loss']
+    assert len(loss) == 3 and np.isfinite(loss).all() and loss[-1] < loss[0]
+    assert isinstance(gen1[0][0], torch.Tensor)
