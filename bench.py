@@ -50,9 +50,9 @@ def measured_peaks():
 
 def ncu_traffic(kernel, batch):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r01_ncu_traffic.json, taken at the bench batch); None if there is no capture for
+    `ncu --set full` capture (profiles/r02_ncu_traffic.json, taken at the bench batch); None if there is no capture for
     this kernel / batch."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r02_ncu_traffic.json')
     try:
         table = json.load(open(path))
     except (IOError, OSError, ValueError):

@@ -926,6 +926,18 @@ static void sw_launch_one(const SwParams& p, const CUtensorMap& map_full, const 
     conv_sw_kernel<KH, KW, NC, ST><<<grid, TC_THREADS, smem, stream>>>(p, map_full, map_pair);
 }
 
+// Loads the kernel's module and opts in to its shared memory WITHOUT launching (cudaFuncGetAttributes).  With CUDA's lazy
+// module loading the first launch of an instance can synchronise with kernels already running on the device -- fatal when
+// that running kernel is a latitude-band halo wait spinning for a signal this very host thread has yet to enqueue
+// (several bands in one process); dlwp_plan_halo_enable preloads what its rollout will launch.
+template <int KH, int KW, int NC, class ST>
+static void sw_preload_one() {
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, conv_sw_kernel<KH, KW, NC, ST>);
+    cudaFuncSetAttribute(conv_sw_kernel<KH, KW, NC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+typedef void (*SwPreloadFn)();
+
 // A folded instance: the layer constants it was compiled for and its launcher.
 struct SwFolded {
     int KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL;   // the kernel folds min(KH, 256 / NCOLS) vertical taps per MMA
@@ -933,15 +945,18 @@ struct SwFolded {
     const char* what;
     int BF16;   // 1: the bf16 flavour of the instance
     int PEERS;  // 1: the flavour whose epilogue also stores into the latitude-band neighbours' images
+    SwPreloadFn preload;
 };
 #define SW_FOLDED_ENTRY(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
     {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                          \
-     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT, 0, 0}
+     &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>, WHAT, 0, 0, \
+     &sw_preload_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH)>>}
 // BF16 / PEERS flavours: SW_FOLDED_ENTRY_X(..., WHAT, bf16, peers)
 #define SW_FOLDED_ENTRY_X(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT, BF, PE)                                       \
     {KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL,                                                                          \
      &sw_launch_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH), BF, PE>>, \
-     WHAT, BF, PE}
+     WHAT, BF, PE,                                                                                                             \
+     &sw_preload_one<KH, KWE, NC, SwStatic<NCOLS, KS, D, CBLK, ACT, OUT, FULL, (256 / NCOLS < KH ? 256 / NCOLS : KH), BF, PE>>}
 #define SW_FOLDED_ENTRY_BF16(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT) \
     SW_FOLDED_ENTRY_X(KH, KWE, NC, NCOLS, KS, D, CBLK, ACT, OUT, FULL, WHAT, 1, 0)
 
@@ -974,5 +989,6 @@ void sw_counters_bf16(unsigned long long* acc12);
 // generic bf16 instances (conv_sw_bf16.cu); false: no instance for this (KH, KW_eff, NC)
 bool sw_launch_generic_bf16(int kh, int kw_eff, int nc, const SwParams& p, const CUtensorMap& map_full,
                             const CUtensorMap& map_pair, int grid, size_t smem, cudaStream_t stream);
+void sw_preload_generic_bf16();
 
 }  // namespace dlwp

@@ -35,4 +35,8 @@ bool sw_launch_generic_bf16(int kh, int kw_eff, int nc, const SwParams& p, const
     else return false;
     return true;
 }
+void sw_preload_generic_bf16() {
+    sw_preload_one<3, 1, 8, SwGenericBf16>(); sw_preload_one<5, 1, 8, SwGenericBf16>(); sw_preload_one<3, 3, 8, SwGenericBf16>();
+    sw_preload_one<3, 3, 6, SwGenericBf16>(); sw_preload_one<5, 5, 8, SwGenericBf16>(); sw_preload_one<5, 5, 6, SwGenericBf16>();
+}
 }  // namespace dlwp

@@ -40,6 +40,34 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
     amax_publish(amax, m, threadIdx.x & 31);
 }
 
+// dense tensors: a flat sweep with 16-byte loads, four in flight per thread (the strided kernel above reads the bench state at
+// 0.8 TB/s; this one is bound by HBM)
+__global__ void __launch_bounds__(256) amax_flat_kernel(const float4* __restrict__ x, float* amax, long long n4) {
+    float m = 0.f;
+    bool bad = false;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(x + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = fmaxf(fmaxf(fabsf(v[k].x), fabsf(v[k].y)), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+            // fmaxf drops NaNs: test the sum of the four
+            if (!(fabsf(v[k].x) + fabsf(v[k].y) + fabsf(v[k].z) + fabsf(v[k].w) <= 3.0e38f)) bad = true;
+            m = fmaxf(m, a);
+        }
+    }
+    for (; i < n4; i += stride) {
+        const float4 v = __ldg(x + i);
+        if (!(fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w) <= 3.0e38f)) bad = true;
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (bad) atomicOr(&g_tc_flags, TC_FLAG_RANGE);
+    amax_publish(amax, m, threadIdx.x & 31);
+}
+
 // one thread per (n, c8, y, padded x)
 __global__ void __launch_bounds__(256) pack_state_kernel(const float* __restrict__ x, __half* __restrict__ yp, int N, int C,
                                                          int H, int W, int wpad, long long xs_n, long long xs_c,
@@ -178,8 +206,15 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
         const int a0 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? 0 : ps.amax_row0;
         const int a1 = (ps.amax_row0 == 0 && ps.amax_row1 == 0) ? H : ps.amax_row1;
         const long long all = (long long)N * C * (a1 - a0) * W;
-        const int ablocks = (int)std::max<long long>(1, std::min<long long>((all + 1023) / 1024, 148LL * 8));
-        amax_kernel<<<ablocks, 256, 0, stream>>>(x, ps.amax, N, C, a1 - a0, W, xs_n, xs_c, xs_h, a0);
+        const bool dense = a0 == 0 && a1 == H && xs_h == W && xs_c == (long long)H * W && xs_n == (long long)C * H * W &&
+                           all % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+        if (dense) {
+            const int ablocks = (int)std::max<long long>(1, std::min<long long>((all / 4 + 1023) / 1024, 148LL * 8));
+            amax_flat_kernel<<<ablocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), ps.amax, all / 4);
+        } else {
+            const int ablocks = (int)std::max<long long>(1, std::min<long long>((all + 1023) / 1024, 148LL * 8));
+            amax_kernel<<<ablocks, 256, 0, stream>>>(x, ps.amax, N, C, a1 - a0, W, xs_n, xs_c, xs_h, a0);
+        }
         int rc = after_launch("amax_kernel");
         if (rc) return rc;
     }
@@ -212,6 +247,41 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
     }
     const int Wps = Ws + 2 * wpad_s, Wpd = Wd + 2 * wpad_d;
     const long long Has = Hs + 2 * TC_HPAD, Had = Hd + 2 * TC_HPAD;
+    if (KIND == 2) {
+        // UpSampling2D(2): one thread per SOURCE pixel and chunk -- one 16-byte load (two for the split) feeds the four
+        // destination pixels (the per-destination-pixel form re-read every source vector four times and reached 3.2 TB/s
+        // of DRAM traffic: profiles/r02_net_b_bf16_ncu_summary.txt)
+        const int ys0 = row0 >> 1, ys1 = (row0 + rows + 1) >> 1;
+        const long long totals = (long long)N * C8 * (ys1 - ys0) * Ws;
+        for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < totals; idx += (long long)gridDim.x * blockDim.x) {
+            const int xs = (int)(idx % Ws);
+            long long t = idx / Ws;
+            const int ys = ys0 + (int)(t % (ys1 - ys0));
+            t /= (ys1 - ys0);
+            const int c8 = (int)(t % C8);
+            const int n = (int)(t / C8);
+            const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + PPC * c8) * Has + TC_HPAD + ys) * Wps + wpad_s + xs;
+            const uint4 vh = __ldg(sh);
+            uint4 vl = make_uint4(0, 0, 0, 0);
+            if (!BF16) vl = __ldg(sh + Has * Wps);
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * ys + dy;
+                if (y < row0 || y >= row0 + rows) continue;
+                uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + PPC * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + 2 * xs;
+                uint4* dl = dh + Had * Wpd;
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int x = 2 * xs + dx;
+                    dh[dx] = vh;
+                    if (!BF16) dl[dx] = vl;
+                    if (x < wpad_d) { dh[dx + Wd] = vh; if (!BF16) dl[dx + Wd] = vl; }
+                    if (x >= Wd - wpad_d) { dh[dx - Wd] = vh; if (!BF16) dl[dx - Wd] = vl; }
+                }
+            }
+        }
+        return;
+    }
     const long long total = (long long)N * C8 * rows * Wd;  // destination rows [row0, row0 + rows): latitude-band window
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(idx % Wd);
@@ -263,8 +333,9 @@ int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, in
     if (kind == DLWP_OP_UPSAMPLE) { Hd = Hs * 2; Wd = Ws * 2; }
     const int row0 = (row_begin == 0 && row_end == 0) ? 0 : row_begin;
     const int rows = ((row_begin == 0 && row_end == 0) ? Hd : row_end) - row0;
-    const long long total = (long long)N * C8 * rows * Wd;
+    long long total = (long long)N * C8 * rows * Wd;
     if (total <= 0) return 0;
+    if (kind == DLWP_OP_UPSAMPLE) total = (long long)N * C8 * (((row0 + rows + 1) >> 1) - (row0 >> 1)) * Ws;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -534,6 +605,26 @@ int tc_launch(const DlwpConvDesc& d, const TcLayer& L, const TcKStep* kst, const
     else if (d.kh == 5 && nc == 8) sw_launch_one<5, 5, 8, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
     else sw_launch_one<5, 5, 6, SwGeneric>(p, map_full, map_pair, grid, L.smem, stream);
     return after_launch("conv_sw_kernel");
+}
+
+// Load (without launching) the kernel instance tc_launch would pick for this layer: see sw_preload_one.
+void tc_preload(const DlwpConvDesc& d, const TcLayer& L, int out_mode, int peers, const TcOptions& opt) {
+    const int nc = L.CSTRIDE == 6 ? 6 : 8;
+    const SwFolded* f = opt.generic ? nullptr : find_folded(d, L, nc, out_mode, peers);
+    if (f) { f->preload(); return; }
+    if (L.ppc == 1) { sw_preload_generic_bf16(); return; }
+    sw_preload_one<3, 1, 8, SwGeneric>(); sw_preload_one<5, 1, 8, SwGeneric>(); sw_preload_one<3, 3, 8, SwGeneric>();
+    sw_preload_one<3, 3, 6, SwGeneric>(); sw_preload_one<5, 5, 8, SwGeneric>(); sw_preload_one<5, 5, 6, SwGeneric>();
+}
+
+void tc_preload_aux() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, amax_kernel);
+    cudaFuncGetAttributes(&a, amax_flat_kernel);
+    cudaFuncGetAttributes(&a, pack_state_kernel);
+    cudaFuncGetAttributes(&a, pack_halo_kernel);
+    cudaFuncGetAttributes(&a, p_ew_kernel<0, 0>); cudaFuncGetAttributes(&a, p_ew_kernel<1, 0>); cudaFuncGetAttributes(&a, p_ew_kernel<2, 0>);
+    cudaFuncGetAttributes(&a, p_ew_kernel<0, 1>); cudaFuncGetAttributes(&a, p_ew_kernel<1, 1>); cudaFuncGetAttributes(&a, p_ew_kernel<2, 1>);
 }
 
 size_t tc_p_bytes(int N, int planes, int H, int Wp) { return (size_t)N * planes * (H + 2 * TC_HPAD) * Wp * 16; }

@@ -149,6 +149,8 @@ int tc_pair_launch(const DlwpConvDesc& d1, const TcLayer& L1, const TcKStep* kst
                    const __half* xp, int in_planes_total, int in_plane0, float* y32, __half* yp, int wpad_out,
                    int planes_out, int out_plane0, const TcScale& sc1, const TcScale& sc2, int* done_counter,
                    cudaStream_t stream, const TcOptions& opt);
+void tc_preload_aux();   // the small kernels around the conv chain (packing, data movers)
+void tc_preload(const DlwpConvDesc& d, const TcLayer& L, int out_mode, int peers, const TcOptions& opt);
 int conv2d_fwd_tc(const DlwpConvDesc& d, const float* x, const float* w_dev, const float* bias, float* y,
                   cudaStream_t stream);
 int tc_debug_flags();

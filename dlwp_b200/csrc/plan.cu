@@ -1283,6 +1283,21 @@ extern "C" int dlwp_plan_halo_enable(DlwpPlan* pl) {
     DLWP_CUDA_TRY(cudaMalloc(&pl->flags, 64));
     DLWP_CUDA_TRY(cudaMemset(pl->flags, 0, 64));
     DLWP_CUDA_TRY(cudaDeviceSynchronize());
+    // everything the peer-memory rollout launches is loaded now, not at its first launch (sw_preload_one)
+    {
+        const int fb = pl->tc_feedback_op;
+        const DlwpOpDesc& op = pl->ops[fb];
+        DlwpConvDesc d = conv_desc_of(pl, op, pl->max_batch);
+        tc_preload(d, pl->tc_layers[fb], 3, 1, pl->tc_opt);
+        for (size_t i = 0; i < pl->ops.size(); ++i)
+            if (pl->ops[i].kind == DLWP_OP_CONV)
+                for (int mode = 1; mode <= 3; ++mode)
+                    tc_preload(conv_desc_of(pl, pl->ops[i], pl->max_batch), pl->tc_layers[i], mode, 0, pl->tc_opt);
+        tc_preload_aux();
+        cudaFuncAttributes attr;
+        cudaFuncGetAttributes(&attr, halo_signal_kernel);
+        cudaFuncGetAttributes(&attr, halo_wait_kernel);
+    }
     pl->p2p = true;
     return 0;
 }

@@ -159,7 +159,7 @@ def test_row_connected_tiled_kernel_equals_direct_kernel(env, k, d, cout):
     y_tiled = run_conv(*args, nat.IMPL_AUTO, rowwise=1)
     y_direct = run_conv(*args, nat.IMPL_DIRECT, rowwise=1)
     assert y_tiled.shape == (N, cout, H, W)
-    assert np.abs(y_tiled - y_direct).max() < 2e-6
+    assert np.abs(y_tiled - y_direct).max() < 1e-5       # fp32, different summation order
     xp = OO.zero_pad2d(OO.periodic_pad2d(x.astype(np.float64), ((0, 0), (pad, pad))), ((pad, pad), (0, 0)))
     ref = np.stack([OO.conv2d_valid(xp[:, :, r:r + d * (k - 1) + 1], kern[r].astype(np.float64), None, (d, d))[:, :, 0]
                     for r in range(H)], axis=2) + bias.astype(np.float64).T[None, :, :, None]
