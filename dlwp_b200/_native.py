@@ -153,7 +153,7 @@ def lib():
             raise ImportError(
                 'libdlwp_b200.so is not built (%s). Run `python -m dlwp_b200.build` (needs nvcc); dlwp_b200 has no '
                 'CPU or PyTorch fallback for its CUDA kernels.' % LIB_PATH)
-        # DLWP_B200_LIB: an alternative build of the same ABI (A/B experiments: scripts/build_variants.sh)
+        # DLWP_B200_LIB: an alternative build of the same ABI (same-box A/B experiments, profiles/r02_variants_ab.txt)
         handle = ctypes.CDLL(os.environ.get('DLWP_B200_LIB') or LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if the ABI and the binding drift apart

@@ -248,19 +248,19 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
     const int Wps = Ws + 2 * wpad_s, Wpd = Wd + 2 * wpad_d;
     const long long Has = Hs + 2 * TC_HPAD, Had = Hd + 2 * TC_HPAD;
     if (KIND == 2) {
-        // UpSampling2D(2): one thread per SOURCE pixel and chunk -- one 16-byte load (two for the split) feeds the four
-        // destination pixels (the per-destination-pixel form re-read every source vector four times and reached 3.2 TB/s
-        // of DRAM traffic: profiles/r02_net_b_bf16_ncu_summary.txt)
+        // UpSampling2D(2): one thread per destination COLUMN and source row -- the source vector is loaded once for the two
+        // destination rows, and the stores of a warp stay contiguous (one thread per source pixel writing its 2 x 2 block
+        // halves the store efficiency: 2x slower on the fp16 split, profiles/r02_net_b_per_op.jsonl)
         const int ys0 = row0 >> 1, ys1 = (row0 + rows + 1) >> 1;
-        const long long totals = (long long)N * C8 * (ys1 - ys0) * Ws;
+        const long long totals = (long long)N * C8 * (ys1 - ys0) * Wd;
         for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < totals; idx += (long long)gridDim.x * blockDim.x) {
-            const int xs = (int)(idx % Ws);
-            long long t = idx / Ws;
+            const int x = (int)(idx % Wd);
+            long long t = idx / Wd;
             const int ys = ys0 + (int)(t % (ys1 - ys0));
             t /= (ys1 - ys0);
             const int c8 = (int)(t % C8);
             const int n = (int)(t / C8);
-            const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + PPC * c8) * Has + TC_HPAD + ys) * Wps + wpad_s + xs;
+            const uint4* sh = src + (((long long)n * src_planes_total + src_plane0 + PPC * c8) * Has + TC_HPAD + ys) * Wps + wpad_s + (x >> 1);
             const uint4 vh = __ldg(sh);
             uint4 vl = make_uint4(0, 0, 0, 0);
             if (!BF16) vl = __ldg(sh + Has * Wps);
@@ -268,16 +268,12 @@ __global__ void __launch_bounds__(256) p_ew_kernel(const uint4* __restrict__ src
             for (int dy = 0; dy < 2; ++dy) {
                 const int y = 2 * ys + dy;
                 if (y < row0 || y >= row0 + rows) continue;
-                uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + PPC * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + 2 * xs;
+                uint4* dh = dst + (((long long)n * dst_planes_total + dst_plane0 + PPC * c8) * Had + TC_HPAD + y) * Wpd + wpad_d + x;
                 uint4* dl = dh + Had * Wpd;
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const int x = 2 * xs + dx;
-                    dh[dx] = vh;
-                    if (!BF16) dl[dx] = vl;
-                    if (x < wpad_d) { dh[dx + Wd] = vh; if (!BF16) dl[dx + Wd] = vl; }
-                    if (x >= Wd - wpad_d) { dh[dx - Wd] = vh; if (!BF16) dl[dx - Wd] = vl; }
-                }
+                dh[0] = vh;
+                if (!BF16) dl[0] = vl;
+                if (x < wpad_d) { dh[Wd] = vh; if (!BF16) dl[Wd] = vl; }
+                if (x >= Wd - wpad_d) { dh[-Wd] = vh; if (!BF16) dl[-Wd] = vl; }
             }
         }
         return;
@@ -335,7 +331,7 @@ int tc_ew_launch(int kind, const __half* src, __half* dst, int N, int planes, in
     const int rows = ((row_begin == 0 && row_end == 0) ? Hd : row_end) - row0;
     long long total = (long long)N * C8 * rows * Wd;
     if (total <= 0) return 0;
-    if (kind == DLWP_OP_UPSAMPLE) total = (long long)N * C8 * (((row0 + rows + 1) >> 1) - (row0 >> 1)) * Ws;
+    if (kind == DLWP_OP_UPSAMPLE) total = (long long)N * C8 * (((row0 + rows + 1) >> 1) - (row0 >> 1)) * Wd;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);

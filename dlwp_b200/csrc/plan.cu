@@ -1384,6 +1384,10 @@ extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const f
         e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         DLWP_CUDA_TRY(e);
+        if (pl->band_graphs.size() >= 8) {  // bounded cache, like the single-domain graphs
+            cudaGraphExecDestroy(pl->band_graphs.begin()->second);
+            pl->band_graphs.erase(pl->band_graphs.begin());
+        }
         it = pl->band_graphs.emplace(key, exec).first;
     }
     DLWP_CUDA_TRY(cudaGraphLaunch(it->second, stream));

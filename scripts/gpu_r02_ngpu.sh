@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, N GPUs (default 4): lat-band with the peer-memory halo, Net A + Net B; multi_gpu_model test; DP training
+# round 2, N GPUs (default 4; scripts/gpu_r02_8gpu.sh is the 8-GPU subset): lat-band with the peer-memory halo, Net A + Net B; multi_gpu_model test; DP training
 N=${1:-4}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514"
