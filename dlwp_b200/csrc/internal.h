@@ -68,6 +68,7 @@ int halo_copy(const float* const src[2], float* const dst[2], const int rows[2],
 // ---- training kernels (train.cu); stride arrays are {n, c, h} element strides -------------------------------------------
 int conv2d_bwd_input(const DlwpConvDesc& d, const float* dy, const float* w, float* dx, cudaStream_t stream);
 int conv2d_bwd_weight(const DlwpConvDesc& d, const float* x, const float* dy, float* dw, float* db, cudaStream_t stream);
+int conv2d_bwd_input_fwd(const DlwpConvDesc& d, const float* dy, const float* w, float* dx, float* wt, cudaStream_t stream);
 int act_bwd(const float* y, float* g, int act, int N, int C, int H, int W, const long long* ys, const long long* gs,
             cudaStream_t stream);
 int maxpool_bwd(const float* x, const float* g, float* dx, int N, int C, int Hp, int Wp, const long long* xs,

@@ -137,6 +137,8 @@ struct DlwpPlan {
     std::vector<float*> gbuf;        // gradient w.r.t. every buffer (max_batch samples)
     std::vector<float*> out_store;   // plan-owned model outputs during training
     float *flat_g = nullptr, *flat_m = nullptr, *flat_v = nullptr, *stats = nullptr;
+    float *bwd_scratch = nullptr, *wt_scratch = nullptr;   // dX via the forward kernels: scratch gradient, flipped weights
+    std::vector<char> g_touched;                           // per buffer: something has accumulated into its gradient this step
     long long flat_elems = 0, adam_t = 0;
     std::vector<long long> gk_off, gb_off;
     float* loss_wmap = nullptr;      // optional (H, W) latitude weights of the loss
@@ -744,7 +746,7 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (g) cudaFree(g);
     for (float* g : pl->out_store)
         if (g) cudaFree(g);
-    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats, pl->loss_wmap})
+    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats, pl->loss_wmap, pl->bwd_scratch, pl->wt_scratch})
         if (g) cudaFree(g);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
@@ -1433,6 +1435,11 @@ static int train_setup(DlwpPlan* pl) {
     DLWP_CUDA_TRY(cudaMemset(pl->flat_m, 0, sizeof(float) * off));
     DLWP_CUDA_TRY(cudaMemset(pl->flat_v, 0, sizeof(float) * off));
     DLWP_CUDA_TRY(cudaMalloc(&pl->stats, sizeof(float) * 2 * pl->outputs.size()));
+    long long max_buf = 0, max_w = 0;
+    for (const Buffer& b : pl->buffers) max_buf = std::max(max_buf, b.sample_elems() * pl->max_batch);
+    for (const Weight& w : pl->weights) max_w = std::max(max_w, w.k_elems);
+    DLWP_CUDA_TRY(cudaMalloc(&pl->bwd_scratch, sizeof(float) * max_buf));
+    DLWP_CUDA_TRY(cudaMalloc(&pl->wt_scratch, sizeof(float) * std::max<long long>(max_w, 1)));
     pl->train_ready = true;
     return 0;
 }
@@ -1470,6 +1477,8 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
     }
     // ---- backward: ops in reverse order; gradients accumulate into channel windows of the per-buffer gradient ----
     if (backward) {
+        pl->g_touched.assign(pl->buffers.size(), 0);
+        for (int o : pl->outputs) pl->g_touched[o] = 1;     // the loss gradient is already there
         for (int i = (int)pl->ops.size() - 1; i >= 0; --i) {
             const DlwpOpDesc& op = pl->ops[i];
             const Buffer& s = pl->buffers[op.src];
@@ -1487,12 +1496,27 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
                     rc = act_bwd(yt, gt, op.act, N, op.Cout, t.d.H, t.d.W, ts, ts, stream);
                     if (!rc) rc = conv2d_bwd_weight(d, xs, gt, pl->flat_g + pl->gk_off[op.weight_id],
                                                     w.has_bias ? pl->flat_g + pl->gb_off[op.weight_id] : nullptr, stream);
-                    if (!rc && (op.src != pl->input_buf || input_grad)) rc = conv2d_bwd_input(d, gt, w.k, gs, stream);
+                    if (!rc && (op.src != pl->input_buf || input_grad)) {
+                        // dX through the forward kernels (conv2d_bwd_input_fwd): straight into the gradient window when
+                        // nothing has accumulated there yet (it was zeroed above), else via scratch + add
+                        const bool whole = op.src_c0 == 0 && op.src_c == s.d.C;
+                        float* dst = (!pl->g_touched[op.src] && whole) ? gs : pl->bwd_scratch;
+                        DlwpConvDesc dd = d;
+                        if (dst != gs) { dd.x_stride_n = (long long)op.src_c * s_hw; }
+                        int r2 = conv2d_bwd_input_fwd(dd, gt, w.k, dst, pl->wt_scratch, stream);
+                        if (r2 == -1) rc = conv2d_bwd_input(d, gt, w.k, gs, stream);
+                        else if (r2) rc = r2;
+                        else if (dst != gs) {
+                            const long long sc[3] = {(long long)op.src_c * s_hw, s_hw, s.d.W};
+                            rc = add_bwd(pl->bwd_scratch, gs, N, op.src_c, s.d.H, s.d.W, sc, ss, stream);
+                        }
+                    }
+                    pl->g_touched[op.src] = 1;
                     break;
                 }
-                case DLWP_OP_MAXPOOL: rc = maxpool_bwd(xs, gt, gs, N, op.src_c, t.d.H, t.d.W, ss, ts, ss, stream); break;
-                case DLWP_OP_UPSAMPLE: rc = upsample_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); break;
-                case DLWP_OP_COPY: rc = add_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); break;
+                case DLWP_OP_MAXPOOL: rc = maxpool_bwd(xs, gt, gs, N, op.src_c, t.d.H, t.d.W, ss, ts, ss, stream); pl->g_touched[op.src] = 1; break;
+                case DLWP_OP_UPSAMPLE: rc = upsample_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); pl->g_touched[op.src] = 1; break;
+                case DLWP_OP_COPY: rc = add_bwd(gt, gs, N, op.src_c, s.d.H, s.d.W, ts, ss, stream); pl->g_touched[op.src] = 1; break;
                 default: DLWP_REQUIRE(false, DLWP_ESHAPE, "op %d has no backward", i);
             }
             if (rc) return rc;

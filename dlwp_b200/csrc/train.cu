@@ -117,6 +117,145 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const BwdParams p)
     }
 }
 
+// ---- dW, tiled ----------------------------------------------------------------------------------------------------------
+// dW[i,j,c,o] = sum over pixels of X(c, y + d*i - pad_t, x + d*j - pad_l) * dY(o, y, x).  The kernel above re-reads all of dY
+// for every (tap, channel) and does one FMA per load; it took 71 % of a training step (profiles/r02_launches_train.txt).
+// Here a CTA owns 16 input channels x up to 64 filters for a share of the output-pixel tiles: per tile the (padded) X tile
+// and the dY tile are staged in shared memory once; thread (channel, filter group) keeps K*K*OT accumulators in registers
+// and slides a K x (d*(K-1)+1) register window along the row, so a pixel costs K + OT shared-memory loads for K*K*OT FMAs.
+// Partial sums go to the gradient with one atomicAdd per weight and CTA.
+constexpr int BWT_CC = 16, BWT_TH = 8, BWT_TW = 32;
+
+template <int K, int D, int OT>
+__global__ void __launch_bounds__(256) conv_bwd_weight_tiled_kernel(const BwdParams p, int OC, int tiles_x, int tiles_y) {
+    constexpr int WW = D * (K - 1) + 1, XH = BWT_TH + D * (K - 1), XW = BWT_TW + D * (K - 1), XWP = XW | 1;
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                                   // [BWT_CC][XH][XWP]
+    float* ds = sm + BWT_CC * XH * XWP;               // [OC][BWT_TH * BWT_TW]
+    const int ochunks = (p.Cout + OC - 1) / OC;
+    const int c0 = (blockIdx.x / ochunks) * BWT_CC, o0 = (blockIdx.x % ochunks) * OC;
+    const int cl = threadIdx.x % BWT_CC, og = threadIdx.x / BWT_CC;
+    float acc[K * K][OT];
+    float bsum[OT];      // dB: the channel-0 thread of every filter group of the FIRST channel chunk sums its dY values
+#pragma unroll
+    for (int q = 0; q < OT; ++q) bsum[q] = 0.f;
+    const bool do_bias = p.db != nullptr && c0 == 0 && cl == 0;
+#pragma unroll
+    for (int t = 0; t < K * K; ++t)
+#pragma unroll
+        for (int q = 0; q < OT; ++q) acc[t][q] = 0.f;
+    const long long ntiles = (long long)p.N * tiles_y * tiles_x;
+    for (long long tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+        const int tx = (int)(tile % tiles_x);
+        long long r = tile / tiles_x;
+        const int ty = (int)(r % tiles_y), n = (int)(r / tiles_y);
+        const int y0 = ty * BWT_TH, x0 = tx * BWT_TW;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < BWT_CC * XH * XW; idx += blockDim.x) {
+            const int xx = idx % XW;
+            int q = idx / XW;
+            const int yy = q % XH, c = q / XH;
+            int gy = y0 + yy - p.pad_t, gx = x0 + xx - p.pad_l;
+            bool ok = c0 + c < p.Cin;
+            if (p.mode_h == DLWP_PAD_PERIODIC) gy = wrap_index(gy, p.H);
+            else ok = ok && gy >= 0 && gy < p.H;
+            if (p.mode_w == DLWP_PAD_PERIODIC) gx = wrap_index(gx, p.W);
+            else ok = ok && gx >= 0 && gx < p.W;
+            xs[(c * XH + yy) * XWP + xx] =
+                ok ? __ldg(p.x + (long long)n * p.xs_n + (long long)(c0 + c) * p.xs_c + (long long)gy * p.xs_h + gx) : 0.f;
+        }
+        for (int idx = threadIdx.x; idx < OC * BWT_TH * BWT_TW; idx += blockDim.x) {
+            const int xx = idx % BWT_TW;
+            int q = idx / BWT_TW;
+            const int yy = q % BWT_TH, o = q / BWT_TH;
+            const bool ok = o0 + o < p.Cout && y0 + yy < p.Ho && x0 + xx < p.Wo;
+            ds[o * (BWT_TH * BWT_TW) + yy * BWT_TW + xx] =
+                ok ? __ldg(p.dy + (long long)n * p.ys_n + (long long)(o0 + o) * p.ys_c + (long long)(y0 + yy) * p.ys_h + x0 + xx) : 0.f;
+        }
+        __syncthreads();
+        if (og * OT < OC) {
+            const float* xc = xs + cl * XH * XWP;
+            const float* dq = ds + (og * OT) * (BWT_TH * BWT_TW);
+#pragma unroll 1
+            for (int yy = 0; yy < BWT_TH; ++yy) {
+                float win[K][WW];
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int t = 0; t + 1 < WW; ++t) win[i][t + 1] = xc[(yy + i * D) * XWP + t];
+#pragma unroll
+                for (int xx = 0; xx < BWT_TW; ++xx) {
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+#pragma unroll
+                        for (int t = 0; t + 1 < WW; ++t) win[i][t] = win[i][t + 1];
+                        win[i][WW - 1] = xc[(yy + i * D) * XWP + xx + WW - 1];
+                    }
+                    float g[OT];
+#pragma unroll
+                    for (int q = 0; q < OT; ++q) g[q] = dq[q * (BWT_TH * BWT_TW) + yy * BWT_TW + xx];
+                    if (do_bias) {
+#pragma unroll
+                        for (int q = 0; q < OT; ++q) bsum[q] += g[q];
+                    }
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+#pragma unroll
+                        for (int j = 0; j < K; ++j)
+#pragma unroll
+                            for (int q = 0; q < OT; ++q) acc[i * K + j][q] = fmaf(win[i][j * D], g[q], acc[i * K + j][q]);
+                }
+            }
+        }
+    }
+    if (og * OT < OC && c0 + cl < p.Cin) {
+#pragma unroll
+        for (int t = 0; t < K * K; ++t)
+#pragma unroll
+            for (int q = 0; q < OT; ++q) {
+                const int o = o0 + og * OT + q;
+                if (o < p.Cout) atomicAdd(p.dw + ((long long)t * p.Cin + c0 + cl) * p.Cout + o, acc[t][q]);
+            }
+    }
+    if (do_bias && og * OT < OC) {
+#pragma unroll
+        for (int q = 0; q < OT; ++q)
+            if (o0 + og * OT + q < p.Cout) atomicAdd(p.db + o0 + og * OT + q, bsum[q]);
+    }
+}
+
+template <int K, int D, int OT>
+static int launch_bwd_weight_tiled(const BwdParams& p, cudaStream_t stream) {
+    constexpr int XH = BWT_TH + D * (K - 1), XW = BWT_TW + D * (K - 1), XWP = XW | 1;
+    int OC = std::min(64, (p.Cout + OT - 1) / OT * OT);
+    OC = std::min(OC, 16 * OT);                       // 256 threads = 16 channels x 16 filter groups
+    const int threads = BWT_CC * (OC / OT);
+    const size_t smem = sizeof(float) * ((size_t)BWT_CC * XH * XWP + (size_t)OC * BWT_TH * BWT_TW);
+    static std::atomic<unsigned long long> done{0};
+    if (first_use_on_device(done))
+        cudaFuncSetAttribute(conv_bwd_weight_tiled_kernel<K, D, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    const int tiles_x = (p.Wo + BWT_TW - 1) / BWT_TW, tiles_y = (p.Ho + BWT_TH - 1) / BWT_TH;
+    const int gx = ((p.Cin + BWT_CC - 1) / BWT_CC) * ((p.Cout + OC - 1) / OC);
+    const long long ntiles = (long long)p.N * tiles_x * tiles_y;
+    const int gy = (int)std::max<long long>(1, std::min<long long>(ntiles, (148 * 4 + gx - 1) / gx));
+    conv_bwd_weight_tiled_kernel<K, D, OT><<<dim3(gx, gy), threads, smem, stream>>>(p, OC, tiles_x, tiles_y);
+    return after_launch("conv_bwd_weight_tiled_kernel");
+}
+
+// W'(i, j, o, c) = W(kh-1-i, kw-1-j, c, o): the weights of the forward conv that computes dX from dY
+__global__ void __launch_bounds__(256) flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int kh, int kw,
+                                                            int Cin, int Cout) {
+    const int total = kh * kw * Cin * Cout;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int c = idx % Cin;
+        int r = idx / Cin;
+        const int o = r % Cout;
+        r /= Cout;
+        const int j = r % kw, i = r / kw;
+        wt[idx] = w[(((long long)(kh - 1 - i) * kw + (kw - 1 - j)) * Cin + c) * Cout + o];
+    }
+}
+
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* dy, float* db, int N, int Cout, int Ho, int Wo,
                                                         long long ys_n, long long ys_c, long long ys_h) {
     const int o = blockIdx.x;
@@ -251,15 +390,47 @@ int conv2d_bwd_input(const DlwpConvDesc& d, const float* dy, const float* w, flo
     return after_launch("conv_bwd_input_kernel");
 }
 
+// dX through the FORWARD kernels: dX = conv(dY, W') with W' the flipped, channel-transposed weights and the paddings mirrored
+// (adjoint of PeriodicPadding2D = periodic, of ZeroPadding2D + 'valid' = zero padding of dY).  OVERWRITES dx (dense
+// (N, Cin, H, W) with the strides of d.x_stride_*); wt: scratch for kh*kw*Cin*Cout floats.  Returns -1 when the layer is not
+// a stride-1 'same' convolution (then the caller keeps conv2d_bwd_input).
+int conv2d_bwd_input_fwd(const DlwpConvDesc& d, const float* dy, const float* w, float* dx, float* wt, cudaStream_t stream) {
+    if (d.rowwise || d.pre_op) return -1;
+    if (d.pad_t + d.pad_b != d.dil_h * (d.kh - 1) || d.pad_l + d.pad_r != d.dil_w * (d.kw - 1)) return -1;
+    const int total = d.kh * d.kw * d.Cin * d.Cout;
+    flip_transpose_kernel<<<std::min((total + 255) / 256, 148 * 4), 256, 0, stream>>>(w, wt, d.kh, d.kw, d.Cin, d.Cout);
+    int rc = after_launch("flip_transpose_kernel");
+    if (rc) return rc;
+    DlwpConvDesc b = d;
+    b.Cin = d.Cout; b.Cout = d.Cin;
+    b.pad_t = d.pad_b; b.pad_b = d.pad_t; b.pad_l = d.pad_r; b.pad_r = d.pad_l;
+    b.act = DLWP_ACT_LINEAR;
+    b.impl = DLWP_IMPL_AUTO;
+    b.row_begin = b.row_end = 0;
+    b.x_stride_n = d.y_stride_n; b.x_stride_c = d.y_stride_c; b.x_stride_h = d.y_stride_h;
+    b.y_stride_n = d.x_stride_n; b.y_stride_c = d.x_stride_c; b.y_stride_h = d.x_stride_h;
+    return conv2d_fwd(b, dy, wt, nullptr, dx, stream);
+}
+
 int conv2d_bwd_weight(const DlwpConvDesc& d, const float* x, const float* dy, float* dw, float* db, cudaStream_t stream) {
     DLWP_REQUIRE(!d.rowwise && !d.pre_op, DLWP_ESHAPE, "backward is not implemented for row-connected / pre_op layers");
     BwdParams p = bwd_params(d);
     p.x = x; p.dy = dy; p.dw = dw; p.db = db;
-    const int nchunks = (d.Cout + BW_OCH - 1) / BW_OCH;
-    const int nb = d.kh * d.kw * d.Cin * nchunks;
-    p.nsplit = std::max(1, std::min(d.N, (148 * 4 + nb - 1) / nb));
-    conv_bwd_weight_kernel<<<dim3(nb, p.nsplit), 256, 0, stream>>>(p);
-    int rc = after_launch("conv_bwd_weight_kernel");
+    int rc = -1;
+    if (d.kh == d.kw && d.dil_h == d.dil_w) {          // the tiled kernel's instances: the example nets' layer shapes
+        if (d.kh == 3 && d.dil_h == 1) rc = launch_bwd_weight_tiled<3, 1, 4>(p, stream);
+        else if (d.kh == 3 && d.dil_h == 2) rc = launch_bwd_weight_tiled<3, 2, 4>(p, stream);
+        else if (d.kh == 5 && d.dil_h == 1) rc = launch_bwd_weight_tiled<5, 1, 2>(p, stream);
+    }
+    if (rc == -1) {
+        const int nchunks = (d.Cout + BW_OCH - 1) / BW_OCH;
+        const int nb = d.kh * d.kw * d.Cin * nchunks;
+        p.nsplit = std::max(1, std::min(d.N, (148 * 4 + nb - 1) / nb));
+        conv_bwd_weight_kernel<<<dim3(nb, p.nsplit), 256, 0, stream>>>(p);
+        rc = after_launch("conv_bwd_weight_kernel");
+    } else {
+        return rc;      // the tiled kernel sums dB itself
+    }
     if (rc || !db) return rc;
     bias_grad_kernel<<<dim3(d.Cout, std::min(d.N, 16)), 256, 0, stream>>>(dy, db, d.N, d.Cout, p.Ho, p.Wo, p.ys_n, p.ys_c,
                                                                           p.ys_h);

@@ -16,6 +16,7 @@ ap.add_argument('--batch', type=int, default=16)
 ap.add_argument('--steps', type=int, default=20)
 ap.add_argument('--math', default='tc')
 ap.add_argument('--per-op', action='store_true')
+ap.add_argument('--opt', action='append', default=[], help='DlwpPlanOptions field, e.g. --opt tc_taps_in_k=1')
 args = ap.parse_args()
 os.environ['DLWP_MATH'] = args.math
 
@@ -54,7 +55,8 @@ for layer in model.layers:  # glorot-uniform kernels, small biases (synthetic we
                            (0.02 * rng.standard_normal(co)).astype(np.float32)])
 
 N, K = args.batch, args.steps
-eng = CompiledNet(model, N, impl='tc' if args.math == 'tc' else None, force_ffma=args.math != 'tc')
+opts = {k: int(v) for k, v in (o.split('=') for o in args.opt)}
+eng = CompiledNet(model, N, impl='tc' if args.math == 'tc' else None, force_ffma=args.math != 'tc', options=opts)
 x0 = torch.from_numpy(np.random.RandomState(0).standard_normal((N,) + cs).astype(np.float32)).cuda()
 series = eng.rollout_device(x0, K, use_graph=True)   # warm-up + graph build
 torch.cuda.synchronize()
@@ -71,7 +73,7 @@ alg_bytes, flops = 62111600.0 * N, 4678041600.0 * N
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json'))) \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6538.0}
 line = {'workload': 'net_b_skip_unet_12x180x360_rollout (BASELINE.json configs[2])', 'math': args.math,
-        'tensor_cores': bool(eng.uses_tensor_cores()), 'batch': N, 'steps': K, 'ms_per_step': ms_step,
+        'tensor_cores': bool(eng.uses_tensor_cores()), 'options': opts, 'precision': os.environ.get('DLWP_PRECISION', 'fp32'), 'batch': N, 'steps': K, 'ms_per_step': ms_step,
         'forecast_steps_per_sec': N / (ms_step * 1e-3), 'algorithmic_gbs': alg_bytes / (ms_step * 1e-3) / 1e9,
         'hbm_frac': alg_bytes / (ms_step * 1e-3) / 1e9 / peaks['hbm_gbs'], 'useful_tflops': flops / (ms_step * 1e-3) / 1e12,
         'finite': bool(torch.isfinite(series[-1]).all().item())}
