@@ -328,6 +328,35 @@ class LatBandEngine(object):
                                                  self.net._stream()), 'dlwp_rollout_latband')
         return series
 
+    def predict_timeseries(self, predictors, time_steps, gather=True):
+        """The lat-band counterpart of `DLWPNeuralNet.predict_timeseries` (models.py:247-301) for time_dim == 1 models:
+        every rank passes the SAME numpy predictors (N, C, H, W); the state is rolled forward `time_steps` times with the
+        latitude split over the ranks.  gather=True: rank 0 returns the complete float32 series (steps, N, C, H, W)
+        assembled from all bands (one collective gather of the per-rank bands), the other ranks return None;
+        gather=False: every rank returns (its band of the series, (row_lo, row_hi))."""
+        import torch
+        time_steps = int(time_steps)
+        if time_steps < 1:
+            raise ValueError("time_steps must be an int > 0")
+        x0 = torch.from_numpy(np.ascontiguousarray(predictors, np.float32)).cuda()
+        series = self.rollout_device(x0, time_steps)
+        lo, hi = self.me.band
+        band = series[:, :, :, lo:hi, :].contiguous()
+        if not gather:
+            return band.cpu().numpy(), (lo, hi)
+        if self.world == 1:
+            return band.cpu().numpy()
+        import torch.distributed as dist
+        rows = [p.band[1] - p.band[0] for p in self.planners]
+        pad = max(rows)                                  # dist.gather wants equal shapes: pad the shorter bands
+        buf = torch.zeros(band.shape[:3] + (pad, band.shape[4]), dtype=torch.float32, device='cuda')
+        buf[:, :, :, :hi - lo] = band
+        parts = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(buf, parts, dst=0)
+        if self.rank != 0:
+            return None
+        return torch.cat([p[:, :, :, :r] for p, r in zip(parts, rows)], dim=3).cpu().numpy()
+
     def band_to_host(self, series):
         """This rank's band of the series as a pinned numpy array (steps, N, C, band_rows, W)."""
         import torch

@@ -32,6 +32,14 @@ for use_graph in (False, True):
     print('rank %d/%d band [%d,%d) graph=%d: band rows == single-domain rows: %s' % (rank, world, lo, hi, use_graph, same),
           flush=True)
     ok = ok and same
+# the reference-facing entry: numpy in, complete series on rank 0 (bands gathered with one collective)
+full = eng.predict_timeseries(x0, K)
+if rank == 0:
+    same = bool(np.array_equal(full, ref.cpu().numpy()))
+    print('rank 0: LatBandEngine.predict_timeseries (halo %s) == single-domain series: %s' % (eng.halo, same), flush=True)
+    ok = ok and same
+else:
+    assert full is None
 flag = torch.tensor([1 if ok else 0], device='cuda')
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

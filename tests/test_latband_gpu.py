@@ -155,3 +155,19 @@ def test_unet_peer_memory_halo_is_bit_identical_to_single_domain(precision):
     eng.close()
     got = _run_bands_p2p(dlwp.model, 2, x0, 4, True, options={'precision': precision})
     np.testing.assert_array_equal(got, ref)
+
+
+def test_latband_engine_predict_timeseries_single_rank():
+    """LatBandEngine.predict_timeseries (the reference-facing entry of the lat-band path) with one rank: equals the
+    single-domain predict_timeseries bit for bit; multi-rank runs are checked by bench.py / scripts/latband_check.py."""
+    from dlwp_b200.parallel import LatBandEngine
+    layers = OL.net_a_layers((6, 30, 60))
+    dlwp = build_product_sequential(layers)
+    oracle_sequential_like(dlwp, layers, seed=2, bias_scale=0.05)
+    x0 = np.random.RandomState(1).standard_normal((3, 6, 30, 60)).astype(np.float32)
+    eng = LatBandEngine(dlwp.model, 3, 0, 1)
+    got = eng.predict_timeseries(x0, 5)
+    np.testing.assert_array_equal(got, dlwp.predict_timeseries(x0, 5))
+    with pytest.raises(ValueError):
+        eng.predict_timeseries(x0, 0)
+    eng.close()
