@@ -8,6 +8,10 @@
 namespace dlwp {
 static const SwFolded kTable[] = {
     //                   KH KWE NC NCOLS KS D CBLK ACT              OUT FULL
+    SW_FOLDED_ENTRY_BF16(3, 1, 8, 32, 2, 2, 4, DLWP_ACT_TANH, 1, 1, "bf16 Net A conv1: 6->32 3x3 dil 2 tanh"),
+    SW_FOLDED_ENTRY_BF16(5, 5, 6, 32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1, "bf16 Net A conv2: 32->6 5x5 linear, fp32 series + P feedback"),
+    SW_FOLDED_ENTRY_X(5, 5, 6, 32, 2, 1, 1, DLWP_ACT_LINEAR, 3, 1,
+                      "bf16 Net A conv2: 32->6 5x5 linear, fp32 series + P feedback + latitude-band neighbours' halo rows", 1, 1),
     SW_FOLDED_ENTRY_BF16(3, 1, 8, 32, 3, 2, 4, DLWP_ACT_TANH, 1, 1, "bf16 Net B conv_2d_1: 12->32 3x3 dil 2 tanh"),
     SW_FOLDED_ENTRY_BF16(3, 1, 8, 64, 3, 1, 8, DLWP_ACT_TANH, 1, 1, "bf16 Net B conv_2d_2: 16->64 3x3 tanh"),
     SW_FOLDED_ENTRY_BF16(3, 1, 8, 128, 6, 1, 16, DLWP_ACT_TANH, 1, 1, "bf16 Net B conv_2d_3: 32->128 3x3 tanh"),

@@ -258,7 +258,12 @@ class LatBandEngine(object):
                                  up.halo[1] if up else 0, down.halo[0] if down else 0)
         self.halo = 'nccl'
         if self.native and world > 1 and halo in ('auto', 'p2p'):
-            self.halo = 'p2p' if self._connect_peers(dist, rank, world, strict=(halo == 'p2p')) else 'nccl'
+            ok = self._connect_peers(dist, rank, world, strict=(halo == 'p2p'))
+            if ok is None:       # the handles could not be mapped on some rank: a fresh plan, and the NCCL exchange
+                self.net.close()
+                self.net = CompiledNet(model, batch, impl=impl, row_windows=self.me.windows)
+                ok = False
+            self.halo = 'p2p' if ok else 'nccl'
         if self.native and world > 1 and self.halo == 'nccl':
             import torch
             lib = nat.lib()
@@ -299,8 +304,10 @@ class LatBandEngine(object):
         flag = torch.tensor([good], device='cuda')
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if not int(flag.item()):
-            raise RuntimeError('peer-memory halo: cudaIpcOpenMemHandle failed on some rank: ' +
-                               nat.lib().dlwp_last_error_string().decode())
+            if strict:
+                raise RuntimeError('peer-memory halo: cudaIpcOpenMemHandle failed on some rank: ' +
+                                   nat.lib().dlwp_last_error_string().decode())
+            return None
         return True
 
     def close(self, destroy_comm=False):
