@@ -99,6 +99,8 @@ SYMBOLS = {
     'dlwp_comm_destroy': (None, [ctypes.c_void_p]),
     'dlwp_rollout_latband': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i32, fptr, fptr, i32,
                                             ctypes.POINTER(BandInfo), i32, ctypes.c_void_p]),
+    'dlwp_rollout_latband_host': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, i32, fptr, fptr, i32,
+                                                 ctypes.POINTER(BandInfo), i32]),
     'dlwp_train_step': (ctypes.c_int, [ctypes.c_void_p, i32, fptr, ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(ctypes.c_float), i32, i32, ctypes.POINTER(ctypes.c_float),
                                        ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),

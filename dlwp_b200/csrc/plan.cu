@@ -90,7 +90,8 @@ struct DlwpPlan {
     float* d_x0 = nullptr;
     float* d_series = nullptr;
     long long d_x0_cap = 0, d_series_cap = 0;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> d2h_events;   // dlwp_rollout_latband_host: one per group of steps
     std::vector<cudaEvent_t> events;
     // tensor-core chain mode (every op a tc-capable conv): per-op schedule + which packed buffer each conv writes
     bool tc = false;
@@ -773,6 +774,8 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
     if (pl->s_compute) cudaStreamDestroy(pl->s_compute);
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
+    for (cudaEvent_t e : pl->d2h_events) cudaEventDestroy(e);
     delete pl;
 }
 
@@ -906,18 +909,9 @@ extern "C" int dlwp_rollout(DlwpPlan* pl, int32_t N, const float* x0, float* ser
     return 0;
 }
 
-extern "C" int dlwp_rollout_host(DlwpPlan* pl, int32_t N, const float* x0_host, float* series_host,
-                                 int32_t iterations, int32_t d2h_group) {
-    DLWP_REQUIRE(pl && x0_host && series_host, DLWP_EINVAL, "null argument");
-    DLWP_REQUIRE(N > 0 && N <= pl->max_batch, DLWP_ESHAPE, "batch %d outside (0, %d]", N, pl->max_batch);
-    DLWP_REQUIRE(iterations > 0, DLWP_EINVAL, "iterations must be > 0");
-    int rc = check_rollout_shapes(pl);
-    if (rc) return rc;
-    const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
-    const int n_out = (int)pl->outputs.size();
-    const long long need = slot * n_out * iterations;
-    if (!pl->s_compute) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking));
-    if (!pl->s_copy) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+namespace dlwp {
+// device copies of the host-side x0 and series of dlwp_rollout_host / dlwp_rollout_latband_host (grown on demand)
+static int ensure_host_staging(DlwpPlan* pl, long long slot, long long need) {
     if (pl->d_x0_cap < slot) {
         if (pl->d_x0) cudaFree(pl->d_x0);
         pl->d_x0 = nullptr; pl->d_x0_cap = 0;
@@ -932,6 +926,24 @@ extern "C" int dlwp_rollout_host(DlwpPlan* pl, int32_t N, const float* x0_host, 
                      (long long)(sizeof(float) * need), cudaGetErrorString(e));
         pl->d_series_cap = need;
     }
+    return 0;
+}
+}  // namespace dlwp
+
+extern "C" int dlwp_rollout_host(DlwpPlan* pl, int32_t N, const float* x0_host, float* series_host,
+                                 int32_t iterations, int32_t d2h_group) {
+    DLWP_REQUIRE(pl && x0_host && series_host, DLWP_EINVAL, "null argument");
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch, DLWP_ESHAPE, "batch %d outside (0, %d]", N, pl->max_batch);
+    DLWP_REQUIRE(iterations > 0, DLWP_EINVAL, "iterations must be > 0");
+    int rc = check_rollout_shapes(pl);
+    if (rc) return rc;
+    const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
+    const int n_out = (int)pl->outputs.size();
+    const long long need = slot * n_out * iterations;
+    if (!pl->s_compute) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking));
+    if (!pl->s_copy) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+    rc = ensure_host_staging(pl, slot, need);
+    if (rc) return rc;
     if (d2h_group <= 0) d2h_group = std::max(1, iterations / 8);
     const int groups = (iterations + d2h_group - 1) / d2h_group;
     while ((int)pl->events.size() < groups) {
@@ -1135,8 +1147,11 @@ static bool latband_can_overlap(const DlwpPlan* pl, const DlwpBandInfo& b) {
     return true;
 }
 
+// Iterations [t0, t1) of a rollout of `iterations` steps (the whole loop for a device-resident rollout; groups of steps when
+// the D2H of finished states is pipelined behind the compute, dlwp_rollout_latband_host).
 static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float* series, int iterations,
-                         const DlwpBandInfo& b, cudaStream_t stream) {
+                         const DlwpBandInfo& b, cudaStream_t stream, int t0 = 0, int t1 = -1) {
+    if (t1 < 0) t1 = iterations;
     const long long slot = (long long)N * pl->buffers[pl->input_buf].sample_elems();
     const int n_out = (int)pl->outputs.size();
     if (pl->p2p && b.world > 1) {
@@ -1148,11 +1163,13 @@ static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float
         pl->p2p_up_end = up ? b.band_lo + b.send_up : 0;
         pl->p2p_down_begin = down ? b.band_hi - b.send_down : 1 << 30;
         int rc = 0;
-        halo_signal_kernel<<<1, 1, 0, stream>>>(up ? pl->peer_flags[0] : nullptr, down ? pl->peer_flags[1] : nullptr);
-        halo_wait_kernel<<<1, 1, 0, stream>>>(pl->flags, up ? 1 : 0, down ? 1 : 0);
-        if ((rc = after_launch("halo barrier"))) return rc;
+        if (t0 == 0) {
+            halo_signal_kernel<<<1, 1, 0, stream>>>(up ? pl->peer_flags[0] : nullptr, down ? pl->peer_flags[1] : nullptr);
+            halo_wait_kernel<<<1, 1, 0, stream>>>(pl->flags, up ? 1 : 0, down ? 1 : 0);
+            if ((rc = after_launch("halo barrier"))) return rc;
+        }
         pl->p2p_active = true;
-        for (int t = 0; t < iterations && !rc; ++t) {
+        for (int t = t0; t < t1 && !rc; ++t) {
             pl->cur_parity = t & 1;
             in.P = pl->P_in[t & 1];
             pl->p2p_send = t + 1 < iterations;
@@ -1191,7 +1208,7 @@ static int latband_range(DlwpPlan* pl, void* comm, int N, const float* x0, float
     const int int_lo = b.rank > 0 ? std::max(w0, b.band_lo + op0.pad_t) : w0;
     const int int_hi = b.rank + 1 < b.world ? std::min(w1, b.band_hi - span + op0.pad_t) : w1;
     bool halo_pending = false;
-    for (int t = 0; t < iterations; ++t) {
+    for (int t = t0; t < t1; ++t) {
         int rc = 0;
         if (overlap && halo_pending && int_lo < int_hi) {
             // iteration t with the exchange of iteration t - 1 still in flight on s_copy
@@ -1341,21 +1358,10 @@ extern "C" int dlwp_plan_halo_connect(DlwpPlan* pl, int32_t which, DlwpPlan* nei
     return 0;
 }
 
-extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const float* x0, float* series,
-                                    int32_t iterations, const DlwpBandInfo* band, int32_t use_graph,
-                                    dlwp_stream_t stream_) {
-    DLWP_REQUIRE(pl && x0 && series && band, DLWP_EINVAL, "null argument");
-    DLWP_REQUIRE(band->world == 1 || comm != nullptr || pl->p2p, DLWP_EINVAL,
-                 "a communicator (or dlwp_plan_halo_enable + peers) is required for world > 1");
-    if (pl->p2p && band->world > 1) {
-        DLWP_REQUIRE(band->rank == 0 || pl->peer_flags[0], DLWP_ESTATE, "upper neighbour not connected");
-        DLWP_REQUIRE(band->rank + 1 == band->world || pl->peer_flags[1], DLWP_ESTATE, "lower neighbour not connected");
-    }
-    DLWP_REQUIRE(N > 0 && N <= pl->max_batch && iterations > 0, DLWP_ESHAPE, "bad batch / iterations");
-    int rc = check_rollout_shapes(pl);
-    if (rc) return rc;
+namespace dlwp {
+static int ensure_halo_stage(DlwpPlan* pl, const DlwpBandInfo& b) {
     const Buffer& in = pl->buffers[pl->input_buf];
-    const int max_rows = std::max(std::max(band->send_up, band->send_down), std::max(band->recv_top, band->recv_bot));
+    const int max_rows = std::max(std::max(b.send_up, b.send_down), std::max(b.recv_top, b.recv_bot));
     const long long need = (long long)pl->max_batch * in.d.C * std::max(1, max_rows) * in.d.W;
     if (pl->halo_cap < need) {
         for (float*& h : pl->halo_stage) {
@@ -1365,6 +1371,29 @@ extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const f
         }
         pl->halo_cap = need;
     }
+    return 0;
+}
+
+static int check_latband_args(DlwpPlan* pl, void* comm, int N, int iterations, const DlwpBandInfo* band) {
+    DLWP_REQUIRE(band->world == 1 || comm != nullptr || pl->p2p, DLWP_EINVAL,
+                 "a communicator (or dlwp_plan_halo_enable + peers) is required for world > 1");
+    if (pl->p2p && band->world > 1) {
+        DLWP_REQUIRE(band->rank == 0 || pl->peer_flags[0], DLWP_ESTATE, "upper neighbour not connected");
+        DLWP_REQUIRE(band->rank + 1 == band->world || pl->peer_flags[1], DLWP_ESTATE, "lower neighbour not connected");
+    }
+    DLWP_REQUIRE(N > 0 && N <= pl->max_batch && iterations > 0, DLWP_ESHAPE, "bad batch / iterations");
+    return check_rollout_shapes(pl);
+}
+}  // namespace dlwp
+
+extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const float* x0, float* series,
+                                    int32_t iterations, const DlwpBandInfo* band, int32_t use_graph,
+                                    dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && x0 && series && band, DLWP_EINVAL, "null argument");
+    int rc = check_latband_args(pl, comm, N, iterations, band);
+    if (rc) return rc;
+    rc = ensure_halo_stage(pl, *band);
+    if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!use_graph) return latband_range(pl, comm, N, x0, series, iterations, *band, stream);
     GraphKey key{N, iterations, x0, series};
@@ -1394,6 +1423,52 @@ extern "C" int dlwp_rollout_latband(DlwpPlan* pl, void* comm, int32_t N, const f
     }
     DLWP_CUDA_TRY(cudaGraphLaunch(it->second, stream));
     g_launches.fetch_add((long long)pl->ops.size() * iterations);
+    return 0;
+}
+
+extern "C" int dlwp_rollout_latband_host(DlwpPlan* pl, void* comm, int32_t N, const float* x0_host, float* band_host,
+                                         int32_t iterations, const DlwpBandInfo* band, int32_t d2h_group) {
+    DLWP_REQUIRE(pl && x0_host && band_host && band, DLWP_EINVAL, "null argument");
+    int rc = check_latband_args(pl, comm, N, iterations, band);
+    if (rc) return rc;
+    rc = ensure_halo_stage(pl, *band);
+    if (rc) return rc;
+    const Buffer& in = pl->buffers[pl->input_buf];
+    const int H = in.d.H, W = in.d.W, rows = band->band_hi - band->band_lo;
+    DLWP_REQUIRE(band->band_lo >= 0 && band->band_hi <= H && rows > 0, DLWP_ESHAPE, "band [%d, %d) outside [0, %d)",
+                 band->band_lo, band->band_hi, H);
+    const long long slot = (long long)N * in.sample_elems();
+    const int n_out = (int)pl->outputs.size();
+    rc = ensure_host_staging(pl, slot, slot * n_out * iterations);
+    if (rc) return rc;
+    if (!pl->s_compute) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_compute, cudaStreamNonBlocking));
+    if (!pl->s_d2h) DLWP_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
+    if (d2h_group <= 0) d2h_group = std::max(1, iterations / 8);
+    const int groups = (iterations + d2h_group - 1) / d2h_group;
+    while ((int)pl->d2h_events.size() < groups) {
+        cudaEvent_t ev;
+        DLWP_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        pl->d2h_events.push_back(ev);
+    }
+    // The WHOLE x0 goes up: the exponent of its image comes from max|x0| over the full state, which must be the same on
+    // every rank (and the same as a single-domain rollout's, so that the bands stay bit-identical to it).
+    DLWP_CUDA_TRY(cudaMemcpyAsync(pl->d_x0, x0_host, sizeof(float) * slot, cudaMemcpyHostToDevice, pl->s_compute));
+    const long long planes = (long long)N * in.d.C;        // (sample, channel) planes per state
+    const size_t width = sizeof(float) * (size_t)rows * W;  // a band's rows of one plane are contiguous
+    for (int g = 0; g < groups; ++g) {
+        const int t0 = g * d2h_group, t1 = std::min(iterations, t0 + d2h_group);
+        rc = latband_range(pl, comm, N, pl->d_x0, pl->d_series, iterations, *band, pl->s_compute, t0, t1);
+        if (rc) return rc;
+        DLWP_CUDA_TRY(cudaEventRecord(pl->d2h_events[g], pl->s_compute));
+        DLWP_CUDA_TRY(cudaStreamWaitEvent(pl->s_d2h, pl->d2h_events[g], 0));
+        const long long states = (long long)(t1 - t0) * n_out;
+        DLWP_CUDA_TRY(cudaMemcpy2DAsync(band_host + (long long)t0 * n_out * planes * rows * W, width,
+                                        pl->d_series + (long long)t0 * n_out * slot + (long long)band->band_lo * W,
+                                        sizeof(float) * (size_t)H * W, width, (size_t)(states * planes),
+                                        cudaMemcpyDeviceToHost, pl->s_d2h));
+    }
+    DLWP_CUDA_TRY(cudaStreamSynchronize(pl->s_d2h));
+    DLWP_CUDA_TRY(cudaStreamSynchronize(pl->s_compute));
     return 0;
 }
 

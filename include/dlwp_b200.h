@@ -278,6 +278,14 @@ void dlwp_comm_destroy(void* comm);
 int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0, float* series, int32_t iterations,
                          const DlwpBandInfo* band, int32_t use_graph, dlwp_stream_t stream);
 
+/* The same with host buffers (what LatBandEngine.predict_timeseries calls; the band counterpart of dlwp_rollout_host and of
+ * the loops at DLWP/model/models.py:277-293): x0_host is the full (N,C,H,W) initial state, band_host receives THIS rank's
+ * band of every state, (iterations * n_outputs, N, C, band_hi - band_lo, W) contiguous.  The device series stays inside
+ * the plan; the band rows of finished groups of `d2h_group` steps (0 = iterations / 8) travel to the host as strided 2-D
+ * copies on a second stream while the next steps compute.  Blocks until band_host is complete. */
+int dlwp_rollout_latband_host(DlwpPlan* plan, void* comm, int32_t N, const float* x0_host, float* band_host,
+                              int32_t iterations, const DlwpBandInfo* band, int32_t d2h_group);
+
 /* Halo exchange over peer memory (NVLink) instead of NCCL: after dlwp_plan_halo_enable the input image is double-buffered
  * and the last conv of iteration t stores the rows its neighbours need straight into THEIR images from its epilogue; two
  * one-thread kernels per iteration count arrivals (no packing, no copy kernels, no collective).  Set-up, once per plan:
