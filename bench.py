@@ -418,8 +418,9 @@ def run_latband(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from dlwp_b200 import _native as nat
-    from dlwp_b200.parallel import LatBandEngine, halo_summary
+    from dlwp_b200.parallel import LatBandEngine, bind_host_near_gpu, halo_summary
     torch.cuda.set_device(local_rank)
+    bound_cpus = bind_host_near_gpu(local_rank)           # pinned host buffers on the GPU's own socket
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     K, W = args.steps, max(args.warmup, 3)
     B = args.batch * world if args.scaling == 'weak' else args.batch
@@ -466,18 +467,25 @@ def run_latband(args, rank, world, local_rank):
     vref = dlwp.model.engine(vb).rollout_device(vx, vk, use_graph=False)
     torch.cuda.synchronize()
     lo_, hi_ = veng.me.band
-    vflag = torch.tensor([1 if torch.equal(vs[:, :, :, lo_:hi_], vref[:, :, :, lo_:hi_]) else 0], device='cuda')
+    vhost = veng.rollout_host(vx.cpu().numpy(), vk)        # the host-buffer path must deliver the same band
+    same = torch.equal(vs[:, :, :, lo_:hi_], vref[:, :, :, lo_:hi_]) and \
+        np.array_equal(vhost, vref[:, :, :, lo_:hi_].cpu().numpy())
+    vflag = torch.tensor([1 if same else 0], device='cuda')
     dist.all_reduce(vflag, op=dist.ReduceOp.MIN)
     verified = bool(int(vflag.item()))
 
     # end to end: H2D of x0, rollout, D2H of this rank's band of every state (host concatenation along H is free)
     Ke = min(K, args.e2e_steps)
-    x0_pinned = torch.from_numpy(x0).pin_memory()
-    eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))   # warm the pinned pool
+    x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
+    del series                                            # the host path keeps its own device series inside the plan
+    torch.cuda.empty_cache()
+    band = eng.rollout_host(x0_pinned, Ke)                # warm-up: sizes the device series and the pinned host pool
+    del band
     barrier()
     t0 = time.perf_counter()
-    band = eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+    band = eng.rollout_host(x0_pinned, Ke)                # numpy in -> this rank's band of every state, numpy out
     dt = time.perf_counter() - t0
+    assert band.shape == (Ke, B, STATE[0], eng.me.band[1] - eng.me.band[0], STATE[2]) and np.isfinite(band[-1]).all()
     t = torch.tensor([dt], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
@@ -493,7 +501,7 @@ def run_latband(args, rank, world, local_rank):
                        'batch_per_gpu': B / world, 'global_batch_capped_by_memory': capped,
                        'state': list(STATE), 'parallelism': 'latband%d (91 latitude rows split over %d GPUs, halo 4 rows)'
                        % (world, world), 'bands': [list(p.band) for p in eng.planners],
-                       'bands_equal_single_domain_bitwise': verified,
+                       'bands_equal_single_domain_bitwise': verified, 'host_cpus_bound_near_gpu': bound_cpus,
                        'halo': {'rows_per_side': 4, 'bytes_per_neighbour_per_direction_per_step': per_dir,
                                 'exchange': eng.halo,
                                 'collective': HALO_TEXT[eng.halo],
@@ -502,7 +510,7 @@ def run_latband(args, rank, world, local_rank):
                        'l2': 'per-step working set >> L2 at this batch; no flush', 'e2e_steps': Ke},
             'e2e': {'value': B * Ke / dt, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': B * int(np.prod(STATE)) * 4 / Ke,
                     'd2h_bytes_per_step': B * STATE[0] * rows * STATE[2] * 4,
-                    'api': 'LatBandEngine.rollout_device + band_to_host (per-rank band)', 'steps': Ke, 'seconds': dt},
+                    'api': 'LatBandEngine.rollout_host(numpy) -> numpy (per-rank band; strided D2H pipelined behind the steps)', 'steps': Ke, 'seconds': dt},
             'gpu_launches': launches, 'clocks': clocks.summary(),
             'roofline': None, 'cpu_baseline': None,
         }
@@ -552,6 +560,8 @@ def run_net_b(args, rank, world, local_rank):
     from dlwp_b200 import _native as nat
     torch.cuda.set_device(local_rank)
     if world > 1:
+        from dlwp_b200.parallel import bind_host_near_gpu
+        bind_host_near_gpu(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     K, W = args.steps, max(args.warmup, 3)
     prec = args.precision
@@ -613,15 +623,20 @@ def run_net_b(args, rank, world, local_rank):
     # end to end
     Ke = min(K, args.e2e_steps)
     if latband:
-        x0_pinned = torch.from_numpy(x0).pin_memory()
-        eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+        x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
+        del series
+        torch.cuda.empty_cache()
+        band = eng.rollout_host(x0_pinned, Ke)
+        del band
         barrier()
         t0 = time.perf_counter()
-        eng.band_to_host(eng.rollout_device(x0_pinned.cuda(non_blocking=True), Ke, out=series[:Ke]))
+        band = eng.rollout_host(x0_pinned, Ke)
         dt = time.perf_counter() - t0
         rows = eng.me.band[1] - eng.me.band[0]
+        assert band.shape == (Ke, B, NET_B_STATE[0], rows, NET_B_STATE[2]) and np.isfinite(band[-1]).all()
+        del band
         d2h = B * NET_B_STATE[0] * rows * NET_B_STATE[2] * 4
-        api = 'LatBandEngine.rollout_device + band_to_host (per-rank band)'
+        api = 'LatBandEngine.rollout_host(numpy) -> numpy (per-rank band; strided D2H pipelined behind the steps)'
     else:
         x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
         dlwp.predict_timeseries(x0_pinned, Ke)

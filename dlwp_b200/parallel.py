@@ -208,6 +208,32 @@ def halo_summary(planner, N, C, W):
             'recv_bytes_per_iteration': int((top + bottom) * per_row)}
 
 
+def bind_host_near_gpu(device_index):
+    """
+    Restrict this process to the CPUs NVML reports as local to CUDA device `device_index` (one process per GPU: pinned
+    host buffers are then allocated on, and filled through, the socket the GPU hangs off -- on a two-socket box a D2H that
+    crosses the inter-socket link loses bandwidth to every other rank doing the same).  Returns the number of CPUs kept,
+    0 when nothing was changed (no NVML, no affinity support, or the mask would be empty).
+    """
+    import os
+    try:
+        import pynvml
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        local = set(64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1)
+        keep = sorted(local & os.sched_getaffinity(0))
+        if not keep or len(keep) == len(os.sched_getaffinity(0)):
+            return 0
+        os.sched_setaffinity(0, keep)
+        return len(keep)
+    except Exception:       # affinity is an optimisation: never a reason to fail
+        return 0
+
+
 def _nccl_library():
     """torch's bundled NCCL (the same shared object torch.distributed uses), loaded by the C library with dlopen."""
     import os
@@ -335,6 +361,28 @@ class LatBandEngine(object):
                                                  self.net._stream()), 'dlwp_rollout_latband')
         return series
 
+    def rollout_host(self, x0, iterations, out=None, d2h_group=0):
+        """
+        numpy in -> numpy out through dlwp_rollout_latband_host: x0 (N, C, H, W), identical on every rank; returns this
+        rank's band of every state, (iterations * n_out, N, C, band_rows, W), in pinned host memory (`out`: a pinned torch
+        tensor of that shape to reuse).  The band rows of finished steps travel D2H while the next steps compute.
+        """
+        import ctypes
+        import torch
+        if not self.native:
+            raise RuntimeError('rollout_host needs the native lat-band rollout')
+        x0 = np.ascontiguousarray(x0, np.float32)
+        lo, hi = self.me.band
+        shape = (int(iterations) * self.n_out,) + tuple(x0.shape[:2]) + (hi - lo, x0.shape[3])
+        buf = out if out is not None else torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        if tuple(buf.shape) != shape or buf.dtype != torch.float32 or not buf.is_contiguous():
+            raise ValueError('out must be a contiguous float32 tensor of shape %r' % (shape,))
+        self.net.sync_weights()
+        nat.check(nat.lib().dlwp_rollout_latband_host(self.net.plan, self.comm, x0.shape[0], x0.ctypes.data,
+                                                      buf.data_ptr(), int(iterations), ctypes.byref(self.info),
+                                                      int(d2h_group)), 'dlwp_rollout_latband_host')
+        return buf.numpy()
+
     def predict_timeseries(self, predictors, time_steps, gather=True):
         """The lat-band counterpart of `DLWPNeuralNet.predict_timeseries` (models.py:247-301) for time_dim == 1 models:
         every rank passes the SAME numpy predictors (N, C, H, W); the state is rolled forward `time_steps` times with the
@@ -345,14 +393,13 @@ class LatBandEngine(object):
         time_steps = int(time_steps)
         if time_steps < 1:
             raise ValueError("time_steps must be an int > 0")
+        lo, hi = self.me.band
+        if not gather or self.world == 1:   # host in, host out: the pipelined native path
+            band = self.rollout_host(predictors, time_steps)
+            return (band, (lo, hi)) if not gather else band
         x0 = torch.from_numpy(np.ascontiguousarray(predictors, np.float32)).cuda()
         series = self.rollout_device(x0, time_steps)
-        lo, hi = self.me.band
         band = series[:, :, :, lo:hi, :].contiguous()
-        if not gather:
-            return band.cpu().numpy(), (lo, hi)
-        if self.world == 1:
-            return band.cpu().numpy()
         import torch.distributed as dist
         rows = [p.band[1] - p.band[0] for p in self.planners]
         pad = max(rows)                                  # dist.gather wants equal shapes: pad the shorter bands

@@ -40,6 +40,11 @@ if rank == 0:
     ok = ok and same
 else:
     assert full is None
+# host buffers in, this rank's band out, strided D2H pipelined behind the steps (groups of 2 of the 6 steps)
+band = eng.rollout_host(x0, K, d2h_group=2)
+same = bool(np.array_equal(band, ref[:, :, :, lo:hi].cpu().numpy()))
+print('rank %d: LatBandEngine.rollout_host band == single-domain rows: %s' % (rank, same), flush=True)
+ok = ok and same
 flag = torch.tensor([1 if ok else 0], device='cuda')
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -157,6 +157,61 @@ def test_unet_peer_memory_halo_is_bit_identical_to_single_domain(precision):
     np.testing.assert_array_equal(got, ref)
 
 
+def test_latband_host_rollout_pipelined_band_copies():
+    """dlwp_rollout_latband_host (numpy in, this band's rows of every state out; groups of steps copied D2H while the next
+    ones compute): three bands in one process, one blocking call per band on its own thread, peer-memory halo -- the
+    concatenated bands equal the single-domain predict_timeseries bit for bit, twice in a row (counters carry over)."""
+    import ctypes
+    import threading
+    import torch
+    from dlwp_b200 import _native as nat
+    from dlwp_b200.engine import CompiledNet, Lowering
+    from dlwp_b200.parallel import make_planners
+    lib = nat.lib()
+    layers = OL.net_a_layers()
+    dlwp = build_product_sequential(layers)
+    oracle_sequential_like(dlwp, layers, seed=5, bias_scale=0.05)
+    x0 = np.random.RandomState(2).standard_normal((3, 6, 91, 180)).astype(np.float32)
+    iterations, world = 7, 3
+    ref = dlwp.predict_timeseries(x0, iterations)
+    low = Lowering(dlwp.model)
+    planners = make_planners(low.ops, low.buffers, 91, world)
+    nets = [CompiledNet(dlwp.model, 3, row_windows=p.windows) for p in planners]
+    for n in nets:
+        nat.check(lib.dlwp_plan_halo_enable(n.plan), 'dlwp_plan_halo_enable')
+        n.sync_weights()
+    for r in range(world):
+        if r > 0:
+            nat.check(lib.dlwp_plan_halo_connect(nets[r].plan, 0, nets[r - 1].plan))
+        if r + 1 < world:
+            nat.check(lib.dlwp_plan_halo_connect(nets[r].plan, 1, nets[r + 1].plan))
+    for rep in range(2):
+        bands = [torch.full((iterations, 3, 6, p.band[1] - p.band[0], 180), float('nan'), dtype=torch.float32,
+                            pin_memory=True) for p in planners]
+        codes = [None] * world
+
+        def work(r):
+            p = planners[r]
+            up = planners[r - 1] if r > 0 else None
+            down = planners[r + 1] if r + 1 < world else None
+            info = nat.BandInfo(r, world, p.band[0], p.band[1], p.halo[0], p.halo[1], up.halo[1] if up else 0,
+                                down.halo[0] if down else 0)
+            codes[r] = lib.dlwp_rollout_latband_host(nets[r].plan, None, 3, x0.ctypes.data, bands[r].data_ptr(),
+                                                     iterations, ctypes.byref(info), 2)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert codes == [0] * world, (codes, lib.dlwp_last_error_string())
+        assert lib.dlwp_debug_flags() == 0
+        got = np.concatenate([b.numpy() for b in bands], axis=3)
+        np.testing.assert_array_equal(got, ref)
+    for n in nets:
+        n.close()
+
+
 def test_latband_engine_predict_timeseries_single_rank():
     """LatBandEngine.predict_timeseries (the reference-facing entry of the lat-band path) with one rank: equals the
     single-domain predict_timeseries bit for bit; multi-rank runs are checked by bench.py / scripts/latband_check.py."""
