@@ -77,6 +77,8 @@ int upsample_bwd(const float* g, float* dx, int N, int C, int Hl, int Wl, const 
                  cudaStream_t stream);
 int add_bwd(const float* g, float* dx, int N, int C, int H, int W, const long long* gs, const long long* dxs,
             cudaStream_t stream);
+int acc_loss_grad(const float* yhat, const float* y, const float* mean, long long per, float* g, long long n, double* stats,
+                  float scale, int regularize, cudaStream_t stream);
 int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream,
              const float* wmap = nullptr, long long hw = 1);
 int regularize_grad(const float* w, float* g, long long n, float l1, float l2, float* stat, cudaStream_t stream);

@@ -143,6 +143,11 @@ struct DlwpPlan {
     long long flat_elems = 0, adam_t = 0;
     std::vector<long long> gk_off, gb_off;
     float* loss_wmap = nullptr;      // optional (H, W) latitude weights of the loss
+    // DLWP.custom.anomaly_correlation_loss instead of the MSE (dlwp_train_loss_kind)
+    int loss_kind = 0, acc_regularize = 1, acc_reverse = 1;
+    float* acc_mean = nullptr;       // optional climatology, one sample of an output
+    long long acc_mean_elems = 0;
+    double* acc_stats = nullptr;     // 5 sums per output
 };
 
 namespace dlwp {
@@ -747,7 +752,8 @@ extern "C" void dlwp_plan_destroy(DlwpPlan* pl) {
         if (g) cudaFree(g);
     for (float* g : pl->out_store)
         if (g) cudaFree(g);
-    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats, pl->loss_wmap, pl->bwd_scratch, pl->wt_scratch})
+    if (pl->acc_stats) cudaFree(pl->acc_stats);
+    for (float* g : {pl->flat_g, pl->flat_m, pl->flat_v, pl->stats, pl->loss_wmap, pl->bwd_scratch, pl->wt_scratch, pl->acc_mean})
         if (g) cudaFree(g);
     for (Buffer& b : pl->buffers)
         if (b.d.kind == DLWP_BUF_INTERNAL && b.ptr) cudaFree(b.ptr);
@@ -1546,8 +1552,18 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
         const long long nk = (long long)N * pl->buffers[pl->outputs[k]].sample_elems();
         const float lw = loss_weights ? loss_weights[k] : 1.f;
         const Buffer& ob = pl->buffers[pl->outputs[k]];
-        rc = mse_grad(pl->out_store[k], targets[k], backward ? pl->gbuf[pl->outputs[k]] : nullptr, nk, lw * 2.f / (float)nk,
-                      pl->stats + 2 * k, stream, pl->loss_wmap, (long long)ob.d.H * ob.d.W);
+        if (pl->loss_kind == 1) {
+            if (!pl->acc_stats) DLWP_CUDA_TRY(cudaMalloc(&pl->acc_stats, sizeof(double) * 5 * n_out));
+            if (k == 0) DLWP_CUDA_TRY(cudaMemsetAsync(pl->acc_stats, 0, sizeof(double) * 5 * n_out, stream));
+            DLWP_REQUIRE(!pl->acc_mean || pl->acc_mean_elems == ob.sample_elems(), DLWP_ESHAPE,
+                         "the ACC loss mean has %lld elements, output %d has %lld per sample", pl->acc_mean_elems, k,
+                         ob.sample_elems());
+            rc = acc_loss_grad(pl->out_store[k], targets[k], pl->acc_mean, ob.sample_elems(),
+                               backward ? pl->gbuf[pl->outputs[k]] : nullptr, nk, pl->acc_stats + 5 * k,
+                               pl->acc_reverse ? lw : -lw, pl->acc_regularize, stream);
+        } else
+            rc = mse_grad(pl->out_store[k], targets[k], backward ? pl->gbuf[pl->outputs[k]] : nullptr, nk, lw * 2.f / (float)nk,
+                          pl->stats + 2 * k, stream, pl->loss_wmap, (long long)ob.d.H * ob.d.W);
         if (rc) return rc;
     }
     // ---- backward: ops in reverse order; gradients accumulate into channel windows of the per-buffer gradient ----
@@ -1597,6 +1613,20 @@ extern "C" int dlwp_train_step(DlwpPlan* pl, int32_t N, const float* x, const fl
             if (rc) return rc;
         }
     }
+    if (pl->loss_kind == 1) {
+        std::vector<double> hs(5 * n_out);
+        DLWP_CUDA_TRY(cudaMemcpyAsync(hs.data(), pl->acc_stats, sizeof(double) * 5 * n_out, cudaMemcpyDeviceToHost, stream));
+        DLWP_CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int k = 0; k < n_out; ++k) {
+            const double nk = (double)N * pl->buffers[pl->outputs[k]].sample_elems();
+            const double* v = hs.data() + 5 * k;
+            const double a = v[0] / sqrt(v[1] * v[2]);
+            const double m = pl->acc_regularize == 1 ? v[3] / nk : (pl->acc_regularize == 2 ? v[4] / nk : 0.0);
+            losses[k] = (float)(pl->acc_reverse ? m - a : a - m);
+            if (maes) maes[k] = (float)(v[4] / nk);
+        }
+        return 0;
+    }
     std::vector<float> h(2 * n_out);
     DLWP_CUDA_TRY(cudaMemcpyAsync(h.data(), pl->stats, sizeof(float) * 2 * n_out, cudaMemcpyDeviceToHost, stream));
     DLWP_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1618,6 +1648,29 @@ extern "C" int dlwp_train_loss_weights(DlwpPlan* pl, const float* wmap_host, int
                  ob.d.H * ob.d.W);
     DLWP_CUDA_TRY(cudaMalloc(&pl->loss_wmap, sizeof(float) * elems));
     DLWP_CUDA_TRY(cudaMemcpy(pl->loss_wmap, wmap_host, sizeof(float) * elems, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int dlwp_train_loss_kind(DlwpPlan* pl, int32_t kind, int32_t regularize, int32_t reverse, const float* mean_host,
+                                    int64_t mean_elems) {
+    DLWP_REQUIRE(pl != nullptr, DLWP_EINVAL, "null plan");
+    DLWP_REQUIRE(kind == 0 || kind == 1, DLWP_EINVAL, "loss kind %d (0 = MSE, 1 = anomaly correlation)", kind);
+    DLWP_REQUIRE(regularize >= 0 && regularize <= 2, DLWP_EINVAL, "regularize %d (0 none, 1 mse, 2 mae)", regularize);
+    DLWP_REQUIRE(regularize == 0 || reverse, DLWP_EINVAL, "a regularized ACC loss is always reversed (custom.py:1053-1055)");
+    if (pl->acc_mean) cudaFree(pl->acc_mean);
+    pl->acc_mean = nullptr;
+    pl->acc_mean_elems = 0;
+    pl->loss_kind = kind;
+    pl->acc_regularize = regularize;
+    pl->acc_reverse = reverse ? 1 : 0;
+    if (kind == 1 && mean_host) {
+        const Buffer& ob = pl->buffers[pl->outputs[0]];
+        DLWP_REQUIRE(mean_elems == (int64_t)ob.sample_elems(), DLWP_ESHAPE, "the mean must have C*H*W = %lld elements",
+                     ob.sample_elems());
+        DLWP_CUDA_TRY(cudaMalloc(&pl->acc_mean, sizeof(float) * mean_elems));
+        DLWP_CUDA_TRY(cudaMemcpy(pl->acc_mean, mean_host, sizeof(float) * mean_elems, cudaMemcpyHostToDevice));
+        pl->acc_mean_elems = mean_elems;
+    }
     return 0;
 }
 

@@ -353,6 +353,53 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const float* yhat, const 
     }
 }
 
+// DLWP.custom.anomaly_correlation_loss (custom.py:1036-1088).  Over the WHOLE batch tensor of one output, with the optional
+// climatology mu (one sample's worth, broadcast over the batch):
+//   a = sum (p-mu)(y-mu) / sqrt(sum (p-mu)^2 * sum (y-mu)^2),   loss = s * (m - a),
+// m = mean (p-y)^2 ('mse'), mean |p-y| ('mae') or 0 (regularize_mean=None), s = +1 (reverse) / -1.  Two passes: the five
+// sums (double atomics: a is a ratio of sums of ~1e7 terms), then
+//   dloss/dp_i = s * ( dm/dp_i - [ (y_i-mu_i) / sqrt(Spp Syy) - a (p_i-mu_i) / Spp ] ).
+// stats: Spy, Spp, Syy, sum (p-y)^2, sum |p-y|
+__global__ void __launch_bounds__(256) acc_stats_kernel(const float* yhat, const float* y, const float* mean, long long per,
+                                                        long long n, double* stats) {
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float mu = mean ? mean[i % per] : 0.f;
+        const float p = yhat[i] - mu, t = y[i] - mu, d = yhat[i] - y[i];
+        v[0] += p * t; v[1] += p * p; v[2] += t * t; v[3] += d * d; v[4] += fabsf(d);
+    }
+    __shared__ float red[5][8];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double a = 0.0;
+        for (int wq = 0; wq < 8; ++wq) a += (double)red[threadIdx.x][wq];
+        atomicAdd(stats + threadIdx.x, a);
+    }
+}
+
+__global__ void __launch_bounds__(256) acc_grad_kernel(const float* yhat, const float* y, const float* mean, long long per,
+                                                       float* g, long long n, const double* stats, float scale,
+                                                       int regularize) {
+    const double spp = stats[1], syy = stats[2];
+    const float inv = (float)(1.0 / sqrt(spp * syy));
+    const float a_over_spp = (float)(stats[0] / sqrt(spp * syy) / spp);
+    const float inv_n = 1.f / (float)n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float mu = mean ? mean[i % per] : 0.f;
+        const float p = yhat[i] - mu, t = y[i] - mu, d = yhat[i] - y[i];
+        float dm = 0.f;
+        if (regularize == 1) dm = 2.f * d * inv_n;
+        else if (regularize == 2) dm = (d > 0.f ? inv_n : (d < 0.f ? -inv_n : 0.f));
+        g[i] += scale * (dm - (t * inv - a_over_spp * p));
+    }
+}
+
 // Keras Adam (no amsgrad): lr_t = lr * sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; w -= lr_t m/(sqrt v + eps)
 __global__ void __launch_bounds__(256) adam_kernel(float* w, const float* g, float* m, float* v, long long n, float lr_t,
                                                    float b1, float b2, float eps) {
@@ -472,6 +519,15 @@ int add_bwd(const float* g, float* dx, int N, int C, int H, int W, const long lo
     ew_bwd_kernel<BW_ADD><<<blocks_for((long long)N * C * H * W), 256, 0, stream>>>(p);
     return after_launch("add_bwd");
 }
+int acc_loss_grad(const float* yhat, const float* y, const float* mean, long long per, float* g, long long n, double* stats,
+                  float scale, int regularize, cudaStream_t stream) {
+    acc_stats_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, mean, per, n, stats);
+    int rc = after_launch("acc_stats_kernel");
+    if (rc || !g) return rc;
+    acc_grad_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, mean, per, g, n, stats, scale, regularize);
+    return after_launch("acc_grad_kernel");
+}
+
 int mse_grad(const float* yhat, const float* y, float* g, long long n, float scale, float* stats, cudaStream_t stream,
              const float* wmap, long long hw) {
     mse_grad_kernel<<<blocks_for(n), 256, 0, stream>>>(yhat, y, g, n, scale, stats, wmap, hw);

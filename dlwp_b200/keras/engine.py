@@ -316,6 +316,9 @@ class Model(object):
         self.loss_weights = loss_weights
         self._compile_kwargs = dict(optimizer=optimizer, loss=loss, metrics=metrics, loss_weights=loss_weights,
                                     **kwargs)
+        stale = self.__dict__.pop('_train_engine', None)   # a new loss / optimizer: the training plan (its loss kind, Adam
+        if stale is not None:                              # moments and step count) starts afresh, as in Keras
+            stale.close()
 
     def engine(self, batch=None, device=None):
         """The compiled GPU plan (built lazily; rebuilt when a larger batch chunk is needed).  `device`: CUDA device index

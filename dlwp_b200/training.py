@@ -21,6 +21,29 @@ def _loss_is_mse(loss):
     return getattr(loss, 'base_loss', None) is mean_squared_error and hasattr(loss, 'weights')
 
 
+_ACC_REGULARIZE = {None: 0, 'mse': 1, 'mae': 2}
+
+
+def _loss_is_acc(loss):
+    """DLWP.custom.anomaly_correlation_loss(...) / DLWP.custom.acc_loss (custom.py:1036-1093)."""
+    if loss == 'acc_loss':
+        return True
+    return all(hasattr(loss, a) for a in ('mean', 'regularize_mean', 'reverse')) and getattr(loss, '__name__', '') == 'acc_loss'
+
+
+def _set_acc_loss(eng, loss):
+    from . import _native as nat
+    if loss == 'acc_loss':
+        from .custom import acc_loss as loss
+    if loss.regularize_mean not in _ACC_REGULARIZE:
+        raise NotImplementedError("anomaly_correlation_loss(regularize_mean=%r): the device loss has None, 'mse' and 'mae'"
+                                  % (loss.regularize_mean,))
+    mean = None if loss.mean is None else np.ascontiguousarray(loss.mean, np.float32)
+    nat.check(nat.lib().dlwp_train_loss_kind(eng.plan, 1, _ACC_REGULARIZE[loss.regularize_mean], 1 if loss.reverse else 0,
+                                             None if mean is None else mean.ctypes.data, 0 if mean is None else mean.size),
+              'dlwp_train_loss_kind')
+
+
 def _loss_weight_map(model, eng):
     """(H, W) weight map of a latitude-weighted loss, or None."""
     loss = model.loss[0] if isinstance(model.loss, (list, tuple)) else model.loss
@@ -51,6 +74,9 @@ def _engine(model, batch):
         if wmap is not None:
             from . import _native as nat
             nat.check(nat.lib().dlwp_train_loss_weights(eng.plan, wmap.ctypes.data, wmap.size), 'dlwp_train_loss_weights')
+        first = model.loss[0] if isinstance(model.loss, (list, tuple)) else model.loss
+        if _loss_is_acc(first):
+            _set_acc_loss(eng, first)
         model._train_engine = eng
     return eng
 
@@ -67,8 +93,10 @@ def _check_compiled(model):
         raise RuntimeError('You must compile your model before using it.')
     loss = model.loss
     losses = loss if isinstance(loss, (list, tuple)) else [loss]
-    if not all(_loss_is_mse(l) for l in losses):
-        raise NotImplementedError('dlwp_b200 trains with loss="mse" (latitude-weighted / ACC losses: SURVEY.md 8f)')
+    if not (all(_loss_is_mse(l) for l in losses) or (all(_loss_is_acc(l) for l in losses) and
+                                                     all(l is losses[0] or l == losses[0] for l in losses))):
+        raise NotImplementedError('dlwp_b200 trains with loss="mse", DLWP.custom.latitude_weighted_loss(mean_squared_error) '
+                                  'or one DLWP.custom.anomaly_correlation_loss for all outputs')
 
 
 def _dist():

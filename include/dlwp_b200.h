@@ -311,6 +311,13 @@ int dlwp_train_step(DlwpPlan* plan, int32_t N, const float* x, const float* cons
 /* Optional (H, W) weight map of DLWP.custom.latitude_weighted_loss (custom.py:956-991): both tensors are multiplied by it
  * before the MSE. HOST pointer; NULL removes it. */
 int dlwp_train_loss_weights(DlwpPlan* plan, const float* wmap_host, int64_t elems);
+/* DLWP.custom.anomaly_correlation_loss (custom.py:1036-1088) instead of the MSE (kind 1; 0 restores the MSE): per output,
+ * over the whole batch tensor, a = <p-mu, y-mu> / sqrt(|p-mu|^2 |y-mu|^2) and loss = m - a (reverse != 0) or a - m, with
+ * m = the MSE (regularize 1), the MAE (2) or nothing (0; regularized losses are always reversed).  mean_host: optional
+ * climatology mu, one sample of an output (C*H*W floats, HOST), NULL = 0.  dlwp_train_step then reports this loss in
+ * losses[k].  Not combined with the latitude weight map. */
+int dlwp_train_loss_kind(DlwpPlan* plan, int32_t kind, int32_t regularize, int32_t reverse, const float* mean_host,
+                         int64_t mean_elems);
 /* The flat gradient buffer (device) for a data-parallel all-reduce between dlwp_train_step and dlwp_train_adam, and the
  * gradient w.r.t. the input (valid when input_grad was set). */
 int dlwp_train_buffers(DlwpPlan* plan, float** flat_grad, int64_t* elems, float** input_grad);

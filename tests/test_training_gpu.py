@@ -14,9 +14,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _autograd(net, conv_layers, x_np, targets, loss_weights):
+def _autograd(net, conv_layers, x_np, targets, loss_weights, loss_fn=None):
     """Loss and gradients from torch autograd (float64) on the oracle net; grads returned in Keras layouts."""
     import torch
+    if loss_fn is None:
+        def loss_fn(o, t):
+            return ((o - t) ** 2).mean()
     params = []
     for layer in conv_layers:
         w = torch.tensor(np.transpose(layer.kernel, (3, 2, 0, 1)).astype(np.float64), requires_grad=True)
@@ -27,7 +30,7 @@ def _autograd(net, conv_layers, x_np, targets, loss_weights):
     x = torch.tensor(x_np.astype(np.float64), requires_grad=True)
     outs = net.forward(x)
     outs = outs if isinstance(outs, list) else [outs]
-    losses = [((o - torch.tensor(t.astype(np.float64))) ** 2).mean() for o, t in zip(outs, targets)]
+    losses = [loss_fn(o, torch.tensor(t.astype(np.float64))) for o, t in zip(outs, targets)]
     total = sum(w * l for w, l in zip(loss_weights, losses))
     total.backward()
     grads = []
@@ -170,6 +173,54 @@ def test_latitude_weighted_mse_matches_reference_definition():
         layer._tparam, layer._tw = None, None
     for g, r in zip(eng.weight_grads(), want):
         assert _rel(g, r) < TOL
+
+
+@pytest.mark.parametrize('regularize,with_mean', [('mse', False), ('mae', True), (None, False)])
+def test_anomaly_correlation_loss_matches_reference_definition(regularize, with_mean):
+    """DLWP.custom.anomaly_correlation_loss (custom.py:1036-1088) as the training loss: value and gradients vs torch autograd
+    (float64) of the reference's formula, two outputs with loss weights; then through compile / train_on_batch."""
+    import torch
+    from dlwp_b200 import training
+    from dlwp_b200.custom import anomaly_correlation_loss
+    from dlwp_b200.engine import CompiledNet
+    cs = (12, 16, 24)
+    dlwp, onet = build_functional_pair(cs, skip=True, integration_steps=2, seed=6, bias_scale=0.05)
+    rng = np.random.RandomState(2)
+    x = rng.standard_normal((3,) + cs).astype(np.float32)
+    ys = [rng.standard_normal((3,) + cs).astype(np.float32) for _ in range(2)]
+    mean = (0.3 * rng.standard_normal((1,) + cs)).astype(np.float32) if with_mean else None
+    loss = anomaly_correlation_loss(mean=mean, regularize_mean=regularize)
+    mu = 0.0 if mean is None else torch.tensor(mean.astype(np.float64))
+
+    def ref_loss(p, t):
+        a = ((p - mu) * (t - mu)).mean() / torch.sqrt(((p - mu) ** 2).mean() * ((t - mu) ** 2).mean())
+        m = ((p - t) ** 2).mean() if regularize == 'mse' else ((p - t).abs().mean() if regularize == 'mae' else 0.0)
+        return m - a
+
+    lw = [0.4, 0.6]
+    eng = CompiledNet(dlwp.model, 3, force_ffma=True)
+    training._set_acc_loss(eng, loss)
+    losses, maes = eng.train_step(torch.from_numpy(x).cuda(), [torch.from_numpy(v).cuda() for v in ys], lw, True, True)
+    ref_l, ref_g, ref_dx = _autograd(onet, onet.conv_layers, x, ys, lw, loss_fn=ref_loss)
+    for k in range(2):
+        assert abs(losses[k] - ref_l[k]) < 1e-5
+    # the library's value is also what the host-side loss object computes on the predictions
+    pred = dlwp.model.predict(x)
+    for k in range(2):
+        assert abs(losses[k] - float(loss(ys[k], pred[k]))) < 1e-5
+    for g, r in zip(eng.weight_grads(), ref_g):
+        assert g.shape == r.shape and _rel(g, r) < TOL
+    assert _rel(eng.input_grad_tensor(3).cpu().numpy(), ref_dx) < TOL
+    eng.close()
+    # through the Keras-style entry points
+    dlwp.model.compile(loss=loss, optimizer='adam', loss_weights=lw)
+    first = dlwp.model.train_on_batch(x, ys)
+    first = first[0] if isinstance(first, (list, tuple)) else first
+    assert abs(first - (lw[0] * ref_l[0] + lw[1] * ref_l[1])) < 1e-5
+    for _ in range(5):
+        last = dlwp.model.train_on_batch(x, ys)
+    last = last[0] if isinstance(last, (list, tuple)) else last
+    assert last < first
 
 
 def test_l2_regularizer_enters_gradient_and_loss_and_trained_model_saves(tmp_path):
