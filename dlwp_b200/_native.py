@@ -105,6 +105,7 @@ SYMBOLS = {
                                        ctypes.POINTER(ctypes.c_float), i32, i32, ctypes.POINTER(ctypes.c_float),
                                        ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
     'dlwp_train_loss_weights': (ctypes.c_int, [ctypes.c_void_p, fptr, i64]),
+    'dlwp_train_allreduce': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'dlwp_train_loss_kind': (ctypes.c_int, [ctypes.c_void_p, i32, i32, i32, fptr, i64]),
     'dlwp_train_buffers': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64),
                                           ctypes.POINTER(ctypes.c_void_p)]),

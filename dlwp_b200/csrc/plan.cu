@@ -1018,6 +1018,7 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -1033,6 +1034,7 @@ static int nccl_load(const char* path) {
     g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
     g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     DLWP_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Send &&
                      g_nccl.Recv,
@@ -1671,6 +1673,15 @@ extern "C" int dlwp_train_loss_kind(DlwpPlan* pl, int32_t kind, int32_t regulari
         DLWP_CUDA_TRY(cudaMemcpy(pl->acc_mean, mean_host, sizeof(float) * mean_elems, cudaMemcpyHostToDevice));
         pl->acc_mean_elems = mean_elems;
     }
+    return 0;
+}
+
+extern "C" int dlwp_train_allreduce(DlwpPlan* pl, void* comm, dlwp_stream_t stream_) {
+    DLWP_REQUIRE(pl && pl->train_ready, DLWP_ESTATE, "run dlwp_train_step first");
+    DLWP_REQUIRE(comm != nullptr, DLWP_EINVAL, "null communicator");
+    DLWP_REQUIRE(g_nccl.AllReduce != nullptr, DLWP_EARCH, "the loaded NCCL library has no ncclAllReduce");
+    // ncclFloat32 = 7, ncclAvg = 4 (NCCL >= 2.10): the mean over the ranks, in place, ordered on `stream` after the backward
+    DLWP_NCCL_TRY(g_nccl.AllReduce(pl->flat_g, pl->flat_g, (size_t)pl->flat_elems, 7, 4, comm, (cudaStream_t)stream_));
     return 0;
 }
 

@@ -247,6 +247,24 @@ def _nccl_library():
     return 'libnccl.so.2'
 
 
+def create_native_comm(dist, rank, world):
+    """The library's own NCCL communicator over the ranks of an initialised torch.distributed group (collective: every rank
+    calls it).  torch.distributed only carries the 128-byte NCCL id from rank 0 to the others."""
+    import ctypes
+    import torch
+    lib = nat.lib()
+    path = _nccl_library().encode()
+    ident = (ctypes.c_char * 128)()
+    if rank == 0:
+        nat.check(lib.dlwp_comm_unique_id(path, ident), 'dlwp_comm_unique_id')
+    t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device='cuda')
+    dist.broadcast(t, 0)
+    ident = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+    comm = ctypes.c_void_p()
+    nat.check(lib.dlwp_comm_create(path, rank, world, ident, ctypes.byref(comm)), 'dlwp_comm_create')
+    return comm
+
+
 class LatBandEngine(object):
     """
     GPU implementation: a row-windowed DlwpPlan per rank; the rollout loop INCLUDING the halo exchange runs inside the C
@@ -291,16 +309,7 @@ class LatBandEngine(object):
                 ok = False
             self.halo = 'p2p' if ok else 'nccl'
         if self.native and world > 1 and self.halo == 'nccl':
-            import torch
-            lib = nat.lib()
-            path = _nccl_library().encode()
-            ident = (ctypes.c_char * 128)()
-            if rank == 0:
-                nat.check(lib.dlwp_comm_unique_id(path, ident), 'dlwp_comm_unique_id')
-            t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device='cuda')
-            dist.broadcast(t, 0)
-            ident = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
-            nat.check(lib.dlwp_comm_create(path, rank, world, ident, ctypes.byref(self.comm)), 'dlwp_comm_create')
+            self.comm = create_native_comm(dist, rank, world)
 
     def _connect_peers(self, dist, rank, world, strict=False):
         """Enable the peer-memory halo on this rank's plan and map the neighbours' images (CUDA IPC handles swapped with one

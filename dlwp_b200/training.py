@@ -109,6 +109,27 @@ def _dist():
     return None
 
 
+_native_comm = {}
+
+
+def _allreduce_gradients(eng, dist):
+    """Mean of the flat gradient buffer over the data-parallel ranks.  NCCL process groups: one ncclAllReduce inside the
+    library on its own communicator (created once per process, dlwp_train_allreduce), on the stream of the backward;
+    other back ends: torch.distributed on a tensor view of the buffer."""
+    if dist.get_backend() == 'nccl':
+        from . import _native as nat
+        from .parallel import create_native_comm
+        key = (dist.get_rank(), dist.get_world_size())
+        if key not in _native_comm:
+            _native_comm.clear()
+            _native_comm[key] = create_native_comm(dist, *key)
+        nat.check(nat.lib().dlwp_train_allreduce(eng.plan, _native_comm[key], eng._stream()), 'dlwp_train_allreduce')
+        return
+    g = eng.grad_tensor()
+    dist.all_reduce(g)
+    g.div_(dist.get_world_size())
+
+
 def _step(model, x, y, train):
     import torch
     _check_compiled(model)
@@ -126,9 +147,7 @@ def _step(model, x, y, train):
         opt = model.optimizer
         dist = _dist()
         if dist is not None:
-            g = eng.grad_tensor()
-            dist.all_reduce(g)
-            g.div_(dist.get_world_size())
+            _allreduce_gradients(eng, dist)
         if opt.__class__.__name__ != 'Adam':
             raise NotImplementedError('dlwp_b200 implements the Adam update (the optimizer of every DLWP example)')
         if getattr(opt, 'amsgrad', False):

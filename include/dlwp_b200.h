@@ -321,6 +321,10 @@ int dlwp_train_loss_kind(DlwpPlan* plan, int32_t kind, int32_t regularize, int32
 /* The flat gradient buffer (device) for a data-parallel all-reduce between dlwp_train_step and dlwp_train_adam, and the
  * gradient w.r.t. the input (valid when input_grad was set). */
 int dlwp_train_buffers(DlwpPlan* plan, float** flat_grad, int64_t* elems, float** input_grad);
+/* Data-parallel training (one process per GPU; the reference's multi-GPU mode is keras multi_gpu_model, models.py:104-109):
+ * averages the flat gradient buffer over the ranks of `comm` (dlwp_comm_create) in place with one ncclAllReduce(ncclAvg),
+ * enqueued on `stream` -- between dlwp_train_step and dlwp_train_regularize / dlwp_train_adam. */
+int dlwp_train_allreduce(DlwpPlan* plan, void* comm, dlwp_stream_t stream);
 int dlwp_train_weight_offsets(DlwpPlan* plan, int32_t weight_id, int64_t* kernel_off, int64_t* bias_off);
 /* keras.regularizers.L1L2 (kernel_regularizer= / bias_regularizer=, examples/train.py:155): adds l1 * sign(w) + 2 * l2 * w
  * to the weight's slots of the flat gradient buffer (after dlwp_train_step and the all-reduce, before dlwp_train_adam) and

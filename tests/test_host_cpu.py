@@ -241,6 +241,31 @@ def test_model_pickles_after_training_state_was_attached_and_with_latitude_loss(
     assert np.isfinite(acc(a, b)).all() and acc.__name__ == 'acc_loss'
 
 
+def test_training_loss_recognition():
+    """Which compiled losses the device training path takes (training._check_compiled): 'mse', a latitude-weighted MSE, one
+    anomaly-correlation loss for all outputs (custom.py:1036-1093); anything else is refused before any GPU work."""
+    from dlwp_b200 import training
+    from dlwp_b200.custom import acc_loss, anomaly_correlation_loss, latitude_weighted_loss
+    from dlwp_b200.keras.losses import mean_absolute_error, mean_squared_error
+
+    class M(object):
+        _compile_kwargs = {}
+
+    def ok(loss):
+        m = M()
+        m.loss = loss
+        training._check_compiled(m)
+
+    for good in ('mse', mean_squared_error, latitude_weighted_loss(mean_squared_error, np.linspace(-90, 90, 7), (2, 7, 9)),
+                 acc_loss, 'acc_loss', anomaly_correlation_loss(regularize_mean=None), [acc_loss, acc_loss]):
+        ok(good)
+    assert training._loss_is_acc(anomaly_correlation_loss(mean=np.zeros((1, 2, 3, 4)), regularize_mean='mae'))
+    assert not training._loss_is_acc('mse') and not training._loss_is_mse(acc_loss)
+    for bad in ('mae', mean_absolute_error, [acc_loss, 'mse'], [acc_loss, anomaly_correlation_loss(regularize_mean='mae')]):
+        with pytest.raises(NotImplementedError):
+            ok(bad)
+
+
 def test_recurrent_front_block_builds_and_lowers(nat):
     """examples/train.py:144-157: PeriodicPadding3D + ZeroPadding3D + ConvLSTM2D + Reshape in front of the conv stack.
     Per time step: input conv (pads fused), recurrent conv ('same', zero padded; absent at t = 0), one gate op."""
