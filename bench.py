@@ -490,6 +490,7 @@ def run_latband(args, rank, world, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     rows = eng.me.band[1] - eng.me.band[0]
+    up_rows = eng.uploaded_rows()                         # per rank: the band plus the halo rows it reads
     if rank == 0:
         halo = halo_summary(eng.planners[min(1, world - 1)], B, STATE[0], STATE[2])
         per_dir = halo['bytes_per_row'] * 4
@@ -508,7 +509,7 @@ def run_latband(args, rank, world, local_rank):
                                 'link_time_us_at_770GBs': per_dir / 770e9 * 1e6,
                                 'fraction_of_step_time': per_dir / 770e9 / (ms / K * 1e-3)},
                        'l2': 'per-step working set >> L2 at this batch; no flush', 'e2e_steps': Ke},
-            'e2e': {'value': B * Ke / dt, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': B * int(np.prod(STATE)) * 4 / Ke,
+            'e2e': {'value': B * Ke / dt, 'unit': 'forecast-steps/s', 'h2d_bytes_per_step': B * STATE[0] * (up_rows[1] - up_rows[0]) * STATE[2] * 4 / Ke,
                     'd2h_bytes_per_step': B * STATE[0] * rows * STATE[2] * 4,
                     'api': 'LatBandEngine.rollout_host(numpy) -> numpy (per-rank band; strided D2H pipelined behind the steps)', 'steps': Ke, 'seconds': dt},
             'gpu_launches': launches, 'clocks': clocks.summary(),
@@ -636,6 +637,7 @@ def run_net_b(args, rank, world, local_rank):
         assert band.shape == (Ke, B, NET_B_STATE[0], rows, NET_B_STATE[2]) and np.isfinite(band[-1]).all()
         del band
         d2h = B * NET_B_STATE[0] * rows * NET_B_STATE[2] * 4
+        h2d = B * NET_B_STATE[0] * (eng.uploaded_rows()[1] - eng.uploaded_rows()[0]) * NET_B_STATE[2] * 4
         api = 'LatBandEngine.rollout_host(numpy) -> numpy (per-rank band; strided D2H pipelined behind the steps)'
     else:
         x0_pinned = torch.from_numpy(x0).pin_memory().numpy()
@@ -647,7 +649,7 @@ def run_net_b(args, rank, world, local_rank):
         dt = time.perf_counter() - t0
         assert y.shape == (Ke, B) + NET_B_STATE and np.isfinite(y[-1]).all()
         del y
-        d2h = B * int(np.prod(NET_B_STATE)) * 4
+        d2h = h2d = B * int(np.prod(NET_B_STATE)) * 4
         api = 'DLWPFunctional.predict_timeseries(numpy)->numpy'
     if world > 1:
         t = torch.tensor([dt], device='cuda')
@@ -707,7 +709,7 @@ def run_net_b(args, rank, world, local_rank):
             'scaling': args.scaling if latband else 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if s_act == 2 else 'f32', 'data': 'synthetic', 'config': config,
             'e2e': {'value': n_forecasts * Ke / dt, 'unit': 'forecast-steps/s',
-                    'h2d_bytes_per_step': B * int(np.prod(NET_B_STATE)) * 4 / Ke, 'd2h_bytes_per_step': d2h, 'api': api,
+                    'h2d_bytes_per_step': h2d / Ke, 'd2h_bytes_per_step': d2h, 'api': api,
                     'steps': Ke, 'seconds': dt},
             'gpu_launches': launches, 'clocks': clocks.summary(), 'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line))

@@ -217,6 +217,7 @@ int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wp
         }
         int rc = after_launch("amax_kernel");
         if (rc) return rc;
+        if (ps.after_amax && (rc = ps.after_amax(ps.after_amax_ctx, ps.amax, stream))) return rc;
     }
     const long long total = (long long)N * ((C + 7) / 8) * (row1 - row0) * (W + 2 * wpad);
     if (total <= 0) return 0;

@@ -132,6 +132,10 @@ struct TcPackScale {
     int fresh = 1;
     int amax_row0 = 0, amax_row1 = 0;  // fresh: rows whose max|x| defines the exponent (0,0 = all H rows)
     int bf16 = 0;                      // 1: one bf16 plane per chunk, no exponent (e / amax unused)
+    // fresh: called (host side) between the max|x| measurement and the packing kernel -- a latitude-band rank that holds
+    // only its own rows of x0 reduces the word over the ranks here, so that every rank derives the same exponent
+    int (*after_amax)(void* ctx, float* amax, cudaStream_t stream) = nullptr;
+    void* after_amax_ctx = nullptr;
 };
 int tc_pack_state(const float* x, __half* xp, int N, int C, int H, int W, int wpad, long long xs_n, long long xs_c,
                   long long xs_h, cudaStream_t stream, int row0, int row1, const TcPackScale& ps);

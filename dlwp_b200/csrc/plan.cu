@@ -92,6 +92,7 @@ struct DlwpPlan {
     long long d_x0_cap = 0, d_series_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> d2h_events;   // dlwp_rollout_latband_host: one per group of steps
+    void* x0_amax_comm = nullptr;          // set while x0 holds only this rank's rows: max|x0| is reduced over these ranks
     std::vector<cudaEvent_t> events;
     // tensor-core chain mode (every op a tc-capable conv): per-op schedule + which packed buffer each conv writes
     bool tc = false;
@@ -461,6 +462,8 @@ static int run_one_tc(DlwpPlan* pl, int i, int N, cudaStream_t stream, int t, bo
                      planes_out, stream, win, sc, pl->tc_opt, peers);
 }
 
+static int amax_allreduce(void* comm, float* amax, cudaStream_t stream);   // (NCCL: defined with the lat-band exchange)
+
 // One application of the chain at iteration t.  input_is_packed: the feedback conv of iteration t - 1 already wrote the
 // input image (rollout).  feedback_write: let the feedback conv write the next input image (off for a plain forward).
 static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool input_is_packed, bool feedback_write,
@@ -477,7 +480,11 @@ static int run_ops_tc(DlwpPlan* pl, int N, cudaStream_t stream, int t, bool inpu
         // The exponent comes from max|x| over the whole state when every row is known to be valid (x0 of a rollout: the
         // same value on every rank of a latitude-band run), else over the rows this plan reads (a band's series slot
         // holds garbage outside band + halo).
-        if (!input_rows_all_valid) { ps.amax_row0 = pl->tc_in_row0; ps.amax_row1 = pl->tc_in_row1; }
+        if (!input_rows_all_valid || pl->x0_amax_comm) { ps.amax_row0 = pl->tc_in_row0; ps.amax_row1 = pl->tc_in_row1; }
+        if (pl->x0_amax_comm && t == 0) {   // x0 holds this band's rows only: the ranks agree on max|x0| before packing
+            ps.after_amax = amax_allreduce;
+            ps.after_amax_ctx = pl->x0_amax_comm;
+        }
         int rc = tc_pack_state(in.ptr, in.P, N, in.d.C, in.d.H, in.d.W, in.wpad, in.sample_elems(),
                                (long long)in.d.H * in.d.W, in.d.W, stream, pl->tc_in_row0, pl->tc_in_row1, ps);
         if (rc) return rc;
@@ -922,6 +929,7 @@ static int ensure_host_staging(DlwpPlan* pl, long long slot, long long need) {
         if (pl->d_x0) cudaFree(pl->d_x0);
         pl->d_x0 = nullptr; pl->d_x0_cap = 0;
         DLWP_CUDA_TRY(cudaMalloc(&pl->d_x0, sizeof(float) * slot));
+        DLWP_CUDA_TRY(cudaMemset(pl->d_x0, 0, sizeof(float) * slot));   // (a band uploads only its rows; the rest stays finite)
         pl->d_x0_cap = slot;
     }
     if (pl->d_series_cap < need) {
@@ -1051,6 +1059,12 @@ static int nccl_load(const char* path) {
             return 1000 + _r;                                                                          \
         }                                                                                              \
     } while (0)
+
+static int amax_allreduce(void* comm, float* amax, cudaStream_t stream) {
+    DLWP_REQUIRE(g_nccl.AllReduce != nullptr, DLWP_EARCH, "the loaded NCCL library has no ncclAllReduce");
+    DLWP_NCCL_TRY(g_nccl.AllReduce(amax, amax, 1, 7 /* ncclFloat32 */, 2 /* ncclMax */, comm, stream));
+    return 0;
+}
 
 // One grouped SendRecv of the halo rows of `slot` (N, C, H, W): my top/bottom band rows out, the neighbours' rows in.
 // Three launches per iteration: ONE kernel packs the rows for both neighbours, one NCCL group moves them, ONE kernel
@@ -1458,14 +1472,28 @@ extern "C" int dlwp_rollout_latband_host(DlwpPlan* pl, void* comm, int32_t N, co
         DLWP_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         pl->d2h_events.push_back(ev);
     }
-    // The WHOLE x0 goes up: the exponent of its image comes from max|x0| over the full state, which must be the same on
-    // every rank (and the same as a single-domain rollout's, so that the bands stay bit-identical to it).
-    DLWP_CUDA_TRY(cudaMemcpyAsync(pl->d_x0, x0_host, sizeof(float) * slot, cudaMemcpyHostToDevice, pl->s_compute));
     const long long planes = (long long)N * in.d.C;        // (sample, channel) planes per state
+    // Only the rows this rank reads (band + halo) go up.  The exponent of the x0 image comes from max|x0| over the FULL state
+    // (every rank must scale alike, and like a single-domain rollout, for the bands to stay bit-identical to it): each rank
+    // measures its rows and one 4-byte ncclAllReduce(max) on `comm` makes it global.  Without a communicator (peer-memory
+    // halo set up by hand) the whole x0 is uploaded instead; bf16 images and the fp32 kernels have no exponent.
+    int up_lo = std::max(0, band->band_lo - band->recv_top), up_hi = std::min(H, band->band_hi + band->recv_bot);
+    if (pl->tc && pl->tc_in_row1 > 0) { up_lo = std::min(up_lo, pl->tc_in_row0); up_hi = std::max(up_hi, pl->tc_in_row1); }
+    const bool needs_amax = pl->tc && !pl->tc_opt.bf16;
+    const bool partial = band->world > 1 && (up_lo > 0 || up_hi < H) && (!needs_amax || comm != nullptr);
+    if (partial) {
+        const size_t up_width = sizeof(float) * (size_t)(up_hi - up_lo) * W, pitch = sizeof(float) * (size_t)H * W;
+        DLWP_CUDA_TRY(cudaMemcpy2DAsync(pl->d_x0 + (long long)up_lo * W, pitch, x0_host + (long long)up_lo * W, pitch,
+                                        up_width, (size_t)planes, cudaMemcpyHostToDevice, pl->s_compute));
+    } else {
+        DLWP_CUDA_TRY(cudaMemcpyAsync(pl->d_x0, x0_host, sizeof(float) * slot, cudaMemcpyHostToDevice, pl->s_compute));
+    }
+    pl->x0_amax_comm = (partial && needs_amax) ? comm : nullptr;
     const size_t width = sizeof(float) * (size_t)rows * W;  // a band's rows of one plane are contiguous
     for (int g = 0; g < groups; ++g) {
         const int t0 = g * d2h_group, t1 = std::min(iterations, t0 + d2h_group);
         rc = latband_range(pl, comm, N, pl->d_x0, pl->d_series, iterations, *band, pl->s_compute, t0, t1);
+        pl->x0_amax_comm = nullptr;     // (only iteration 0 packs x0)
         if (rc) return rc;
         DLWP_CUDA_TRY(cudaEventRecord(pl->d2h_events[g], pl->s_compute));
         DLWP_CUDA_TRY(cudaStreamWaitEvent(pl->s_d2h, pl->d2h_events[g], 0));

@@ -293,6 +293,7 @@ class LatBandEngine(object):
         self.driver = LatBandRollout(H, rank, world, self.planners,
                                      lambda src, outs: self.net.forward_into(src, outs), dist=dist)
         self.rank, self.world, self.H = rank, world, H
+        self._dist = dist
         self.n_out = self.net.n_outputs
         self.native = bool(native)
         self.comm = ctypes.c_void_p()
@@ -387,10 +388,21 @@ class LatBandEngine(object):
         if tuple(buf.shape) != shape or buf.dtype != torch.float32 or not buf.is_contiguous():
             raise ValueError('out must be a contiguous float32 tensor of shape %r' % (shape,))
         self.net.sync_weights()
+        if self.world > 1 and not self.comm:
+            # (peer-memory halo: the library's communicator was not needed so far -- here it carries the 4-byte max|x0|
+            # reduction that lets every rank upload only its own rows of x0; collective, every rank gets here together)
+            self.comm = create_native_comm(self._dist, self.rank, self.world)
         nat.check(nat.lib().dlwp_rollout_latband_host(self.net.plan, self.comm, x0.shape[0], x0.ctypes.data,
                                                       buf.data_ptr(), int(iterations), ctypes.byref(self.info),
                                                       int(d2h_group)), 'dlwp_rollout_latband_host')
         return buf.numpy()
+
+    def uploaded_rows(self):
+        """Rows of x0 that `rollout_host` copies to this rank's device: the band plus the halo rows it reads."""
+        lo, hi = self.me.band
+        if self.world == 1:
+            return 0, self.H
+        return max(0, lo - self.me.halo[0]), min(self.H, hi + self.me.halo[1])
 
     def predict_timeseries(self, predictors, time_steps, gather=True):
         """The lat-band counterpart of `DLWPNeuralNet.predict_timeseries` (models.py:247-301) for time_dim == 1 models:

@@ -279,8 +279,10 @@ int dlwp_rollout_latband(DlwpPlan* plan, void* comm, int32_t N, const float* x0,
                          const DlwpBandInfo* band, int32_t use_graph, dlwp_stream_t stream);
 
 /* The same with host buffers (what LatBandEngine.predict_timeseries calls; the band counterpart of dlwp_rollout_host and of
- * the loops at DLWP/model/models.py:277-293): x0_host is the full (N,C,H,W) initial state, band_host receives THIS rank's
- * band of every state, (iterations * n_outputs, N, C, band_hi - band_lo, W) contiguous.  The device series stays inside
+ * the loops at DLWP/model/models.py:277-293): x0_host is the full (N,C,H,W) initial state -- only the rows this rank reads
+ * (band + halo) are copied to the device when `comm` is given (tensor-core plans then agree on max|x0|, which fixes the
+ * exponent of the x0 image, with one 4-byte ncclAllReduce; comm == NULL: the whole x0 goes up) -- and band_host receives
+ * THIS rank's band of every state, (iterations * n_outputs, N, C, band_hi - band_lo, W) contiguous.  The device series stays inside
  * the plan; the band rows of finished groups of `d2h_group` steps (0 = iterations / 8) travel to the host as strided 2-D
  * copies on a second stream while the next steps compute.  Blocks until band_host is complete. */
 int dlwp_rollout_latband_host(DlwpPlan* plan, void* comm, int32_t N, const float* x0_host, float* band_host,
