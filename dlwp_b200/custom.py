@@ -157,11 +157,13 @@ def latitude_weighted_loss(loss_function=mean_squared_error, lats=None, output_s
     return _LatLoss(loss_function, weights)
 
 
-def anomaly_correlation(y_true, y_pred, mean=0., regularize_mean='mse', reverse=True):
-    """DLWP/custom.py:994-1033 on numpy arrays (climatological mean assumed 0, as in the reference)."""
+def _acc_terms(y_true, y_pred, mean, regularize_mean):
+    """(a, m) of DLWP/custom.py:1060-1075: the correlation of the anomalies (climatology `mean` subtracted, None = 0) and the
+    regularizer, which the reference computes on the RAW tensors."""
     if regularize_mean is not None:
         assert regularize_mean in ['global', 'spatial', 'mse', 'mae']
-    a = np.mean(y_pred * y_true) / np.sqrt(np.mean(np.square(y_pred)) * np.mean(np.square(y_true)))
+    pa, ta = (y_pred, y_true) if mean is None else (y_pred - mean, y_true - mean)
+    a = np.mean(pa * ta) / np.sqrt(np.mean(np.square(pa)) * np.mean(np.square(ta)))
     m = None
     if regularize_mean == 'global':
         m = np.abs((np.mean(y_true) - np.mean(y_pred)) / np.mean(y_true))
@@ -172,23 +174,29 @@ def anomaly_correlation(y_true, y_pred, mean=0., regularize_mean='mse', reverse=
         m = mean_squared_error(y_true, y_pred)
     elif regularize_mean == 'mae':
         m = mean_absolute_error(y_true, y_pred)
+    return a, m
+
+
+def anomaly_correlation(y_true, y_pred, mean=0., regularize_mean='mse', reverse=True):
+    """DLWP/custom.py:994-1033 on numpy arrays (climatological mean assumed 0: `mean` is ignored, as in the reference)."""
+    a, m = _acc_terms(y_true, y_pred, None, regularize_mean)
     if reverse:
         return m - a if regularize_mean is not None else -a
     return a - m if regularize_mean else a
 
 
 class _AccLoss(object):
-    """The `acc_loss` closure of DLWP/custom.py:1080-1086 as a picklable callable."""
+    """The `acc_loss` closure of DLWP/custom.py:1057-1086 as a picklable callable."""
     __name__ = 'acc_loss'
 
     def __init__(self, mean, regularize_mean, reverse):
         self.mean, self.regularize_mean, self.reverse = mean, regularize_mean, reverse
 
     def __call__(self, y_true, y_pred):
-        if self.mean is not None:
-            return anomaly_correlation(y_true - self.mean, y_pred - self.mean, regularize_mean=self.regularize_mean,
-                                       reverse=self.reverse)
-        return anomaly_correlation(y_true, y_pred, regularize_mean=self.regularize_mean, reverse=self.reverse)
+        a, m = _acc_terms(y_true, y_pred, self.mean, self.regularize_mean)
+        if self.reverse:
+            return m - a if self.regularize_mean is not None else -a
+        return a - m if self.regularize_mean else a
 
 
 def anomaly_correlation_loss(mean=None, regularize_mean='mse', reverse=True):

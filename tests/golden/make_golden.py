@@ -85,13 +85,18 @@ def install_stubs():
              stack=lambda xs, axis=0: np.stack(xs, axis=axis),
              ones=np.ones, zeros=np.zeros,
              normalize_data_format=lambda v: 'channels_last' if v is None else v,
-             conv2d=_np_conv2d)
+             conv2d=_np_conv2d,
+             # the reductions / pointwise ops the loss functions of custom.py:994-1088 use
+             mean=lambda x, axis=None: np.mean(x, axis=tuple(axis) if isinstance(axis, list) else axis),
+             sqrt=np.sqrt, square=np.square, abs=np.abs, variable=lambda v, name=None: np.asarray(v))
     _mod('keras', backend=K)
     _mod('keras.callbacks', Callback=_Any, EarlyStopping=_Any)
     _mod('keras.layers', Lambda=_Any, Layer=_Any)
     _mod('keras.layers.convolutional', ZeroPadding2D=_StubZeroPadding2D, ZeroPadding3D=_StubZeroPadding3D)
     _mod('keras.layers.local', LocallyConnected2D=_Any)
-    _mod('keras.losses', mean_absolute_error=None, mean_squared_error=None)
+    # keras.losses (Keras 2.2 losses.py): the mean over the LAST axis
+    _mod('keras.losses', mean_absolute_error=lambda y_true, y_pred: np.mean(np.abs(y_pred - y_true), axis=-1),
+         mean_squared_error=lambda y_true, y_pred: np.mean(np.square(y_pred - y_true), axis=-1))
     _mod('keras.utils', conv_utils=None, multi_gpu_model=None)
     _mod('keras.engine')
     _mod('keras.engine.base_layer', InputSpec=_Any)
@@ -224,6 +229,23 @@ def gen_insolation():
     sol2 = ns['insolation'](dates[:3], lat2.copy(), lon2.copy(), S=2.)
     np.savez_compressed(os.path.join(HERE, 'insolation.npz'), dates=dates.values.astype('datetime64[s]').astype(np.int64),
                         lat=lat, lon=lon, sol=sol, sol2=sol2)
+
+
+def gen_acc_loss(custom):
+    """DLWP/custom.py:1036-1088 anomaly_correlation_loss, every regularize_mean, with and without a climatology, and
+    custom.py:994-1033 anomaly_correlation -- executed from the reference module on float64 arrays."""
+    rng = np.random.RandomState(21)
+    y_true = rng.standard_normal((3, 4, 6, 8)) + 0.5
+    y_pred = y_true + 0.4 * rng.standard_normal((3, 4, 6, 8))
+    mean = 0.3 * rng.standard_normal((1, 4, 6, 8))
+    out = {'y_true': y_true, 'y_pred': y_pred, 'mean': mean}
+    for reg in (None, 'mse', 'mae', 'global', 'spatial'):
+        for use_mean in (False, True):
+            fn = custom.anomaly_correlation_loss(mean=mean if use_mean else None, regularize_mean=reg)
+            out['loss_%s_%d' % (reg, use_mean)] = np.asarray(fn(y_true, y_pred), np.float64)
+        out['metric_%s' % reg] = np.asarray(custom.anomaly_correlation(y_true, y_pred, regularize_mean=reg), np.float64)
+    out['loss_none_forward'] = np.asarray(custom.anomaly_correlation_loss(regularize_mean=None, reverse=False)(y_true, y_pred))
+    np.savez_compressed(os.path.join(HERE, 'acc_loss.npz'), **out)
 
 
 def gen_row_conv(custom):
@@ -370,7 +392,8 @@ def main():
     gens = [('padding2d', lambda: gen_periodic_padding(custom)), ('row_conv', lambda: gen_row_conv(custom)),
             ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
-            ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation)]
+            ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation),
+            ('acc_loss', lambda: gen_acc_loss(custom))]
     for name, fn in gens:
         if not only or name in only:
             fn()

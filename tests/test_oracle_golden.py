@@ -232,6 +232,25 @@ def test_conv_lstm_first_step_and_gate_algebra():
     np.testing.assert_allclose(y0, OO.hard_sigmoid(z2[-1][:, 6:]) * np.tanh(cst), atol=1e-14)
 
 
+def test_anomaly_correlation_loss_matches_reference_function(golden_dir):
+    """DLWP/custom.py:994-1088 executed from the reference module on a numpy backend (make_golden.py:gen_acc_loss): the
+    product's host-side loss objects reproduce it for every regularize_mean, with and without a climatology.  The device
+    loss of the training path is checked against these objects in tests/test_training_gpu.py."""
+    from dlwp_b200.custom import anomaly_correlation, anomaly_correlation_loss
+    g = _load(golden_dir, 'acc_loss.npz')
+    yt, yp, mean = g['y_true'], g['y_pred'], g['mean']
+    for reg in (None, 'mse', 'mae', 'global', 'spatial'):
+        for use_mean in (False, True):
+            fn = anomaly_correlation_loss(mean=mean if use_mean else None, regularize_mean=reg)
+            want = g['loss_%s_%d' % (reg, use_mean)]
+            got = np.asarray(fn(yt, yp))
+            assert got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(anomaly_correlation(yt, yp, regularize_mean=reg), g['metric_%s' % reg], rtol=1e-12)
+    fwd = anomaly_correlation_loss(regularize_mean=None, reverse=False)
+    np.testing.assert_allclose(fwd(yt, yp), g['loss_none_forward'], rtol=1e-12)
+
+
 def test_insolation_matches_reference_function(golden_dir):
     """DLWP/util.py:300-352 run from the reference's source text (tests/golden/make_golden.py:gen_insolation)."""
     from oracle import estimator as OE
