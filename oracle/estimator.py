@@ -2,8 +2,13 @@
 Restatement of `TimeSeriesEstimator.predict` (DLWP/model/extensions.py:136-303) and `insolation`
 (DLWP/util.py:300-352) on plain numpy arrays.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-The reference drives the loop through xarray (`reindex`, `.loc`), which is not available here or on the GPU box, so this
-restatement is UNPINNED: it follows the cited lines with index arithmetic in place of label lookups --
+The reference drives the loop through xarray (`reindex`, `.loc`), which is not available here or on the GPU box.  Pinning:
+`insolation` against the reference function run from its source text (tests/golden/insolation.npz); the loop against the
+reference's OWN `TimeSeriesEstimator.predict`, executed by tests/golden/make_golden.py:gen_estimator on a numpy stand-in for
+the few xarray calls it makes (tests/golden/fake_xarray.py: `reindex` = exact label lookup with NaN fill, `.loc` = label ->
+position, views for scalar labels) -- tests/golden/estimator.npz, six cases (tests/test_oracle_golden.py).  The stand-in is
+ours, so the pin is on the reference's loop logic, not on xarray itself.  This file follows the cited lines with index
+arithmetic in place of label lookups --
 
 * `p_da.reindex(sample=r_da.sample)` (extensions.py:226): r_da.sample = p_da.sample + (es + interval - 1)·dt on an evenly
   spaced sample axis, i.e. new p[i] = old p[i + shift], NaN where i + shift runs past the data;

@@ -248,6 +248,82 @@ def gen_acc_loss(custom):
     np.savez_compressed(os.path.join(HERE, 'acc_loss.npz'), **out)
 
 
+def gen_estimator(models, util):
+    """The reference's OWN `TimeSeriesEstimator.__init__` / `.predict` (DLWP/model/extensions.py:21-303) executed on a
+    numpy stand-in for xarray (tests/golden/fake_xarray.py: reindex = exact label lookup with NaN fill, .loc = label ->
+    position) with a SeriesDataGenerator-shaped stub and a model whose `predict` is a fixed numpy map.  Cases: equal
+    input / output time steps; fewer output than input steps with insolation and an output varlev subset; more output than
+    input steps with prefer_first_times on and off; impute with interval 2; keep_time_dim."""
+    import fake_xarray
+    sys.modules['xarray'] = fake_xarray
+    ext = load_ref('DLWP.model.extensions', 'DLWP/model/extensions.py')
+    gens = sys.modules['DLWP.model.generators']
+    rng = np.random.RandomState(33)
+    names = np.array(['z/500', 't/850', 'u/300'])
+    nt, H, W = 14, 5, 8
+    data = rng.standard_normal((nt, 3, H, W)).astype(np.float32)
+    times = np.datetime64('2003-03-01T00:00', 'ns') + np.arange(nt) * np.timedelta64(6 * 3600 * 10 ** 9, 'ns')
+    lat, lon = np.linspace(80., -80., H), np.arange(0., 360., 45.)
+
+    class Gen(gens.SeriesDataGenerator):
+        def __init__(self, in_sel, out_sel, t_in, t_out, interval, sol):
+            self.ds = fake_xarray.Dataset({'sample': times, 'varlev': names, 'lat': lat, 'lon': lon})
+            self._input_sel = {'varlev': list(in_sel)} if in_sel is not None else {}
+            self._output_sel = {'varlev': list(out_sel)} if out_sel is not None else {}
+            self._input_time_steps, self._output_time_steps, self._interval = t_in, t_out, interval
+            self._add_insolation = sol
+            self._n_sample = nt - t_in - t_out - interval + 2
+            iin = [list(names).index(v) for v in (in_sel if in_sel is not None else names)]
+            iout = [list(names).index(v) for v in (out_sel if out_sel is not None else names)]
+            S = self._n_sample
+            pp = np.stack([data[n:n + S][:, iin] for n in range(t_in)], axis=1)
+            if sol:
+                dt = times[1] - times[0]
+                so = np.stack([util.insolation(times[:S] + n * dt, lat.copy(), lon.copy()) for n in range(t_in)], axis=1)
+                pp = np.concatenate([pp, so[:, :, None]], axis=2)
+            off = t_in + interval - 1
+            tt = np.stack([data[off + n:off + n + S][:, iout] for n in range(t_out)], axis=1)
+            self.convolution_shape = (pp.shape[1] * pp.shape[2], H, W)
+            self._p, self._t = pp.reshape((S, -1, H, W)), tt.reshape((S, -1, H, W))
+
+        def generate(self, samples, scale_and_impute=True):
+            return self._p.copy(), self._t.copy()
+
+    class Net(models.DLWPNeuralNet):
+        def __init__(self, w, time_dim):
+            self.w, self.time_dim = w, time_dim
+
+        def predict(self, x, **kwargs):
+            return np.tanh(np.einsum('nchw,co->nohw', np.asarray(x, np.float32), self.w)).astype(np.float32)
+
+    out = {'lat': lat, 'lon': lon, 'times': times.astype('datetime64[s]').astype(np.int64), 'names': names}
+    cases = []
+    specs = [('equal', None, None, 2, 2, 1, False, 5, {}),
+             ('fewer_out_sol', ['z/500', 't/850', 'u/300'], ['z/500', 'u/300'], 2, 1, 1, True, 4, {}),
+             ('more_out_first', None, None, 1, 2, 1, False, 3, {}),
+             ('more_out_last', None, None, 1, 2, 1, False, 3, {'prefer_first_times': False}),
+             ('impute_interval2', ['z/500', 't/850', 'u/300'], ['t/850'], 2, 1, 2, True, 3, {'impute': True}),
+             ('equal_keep_time', None, None, 2, 2, 1, False, 5, {'keep_time_dim': True})]
+    for key, in_sel, out_sel, t_in, t_out, interval, sol, steps, kw in specs:
+        gen = Gen(in_sel, out_sel, t_in, t_out, interval, sol)
+        v_in, v_out = gen._p.shape[1], gen._t.shape[1]
+        w = (0.5 * rng.standard_normal((v_in, v_out))).astype(np.float32)
+        est = ext.TimeSeriesEstimator(Net(w, t_in), gen)
+        res = est.predict(steps, **kw)
+        out[key + '/p'], out[key + '/t'], out[key + '/w'] = gen._p, gen._t, w
+        out[key + '/result'] = np.asarray(res.values, np.float32)
+        out[key + '/dims'] = np.array(res.dims)
+        out[key + '/f_hour'] = np.asarray(res.coords['f_hour']).astype('timedelta64[s]').astype(np.int64)
+        out[key + '/time'] = np.asarray(res.coords['time']).astype('datetime64[s]').astype(np.int64)
+        out[key + '/varlev'] = np.asarray(res.coords['varlev'])
+        out[key + '/spec'] = np.array([t_in, t_out, interval, int(sol), steps, int(kw.get('impute', False)),
+                                       int(kw.get('prefer_first_times', True)), int(kw.get('keep_time_dim', False))])
+        out[key + '/in_varlev'] = np.array(list(est._input_sel['varlev']))
+        cases.append(key)
+    out['cases'] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, 'estimator.npz'), **out)
+
+
 def gen_row_conv(custom):
     rng = np.random.RandomState(11)
     x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
@@ -384,7 +460,7 @@ def gen_torchnn(models_torch):
 
 def main():
     install_stubs()
-    load_ref('DLWP.util', 'DLWP/util.py')
+    util = load_ref('DLWP.util', 'DLWP/util.py')
     custom = load_ref('DLWP.custom', 'DLWP/custom.py')
     models = load_ref('DLWP.model.models', 'DLWP/model/models.py')
     models_torch = load_ref('DLWP.model.models_torch', 'DLWP/model/models_torch.py')
@@ -393,7 +469,7 @@ def main():
             ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
             ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation),
-            ('acc_loss', lambda: gen_acc_loss(custom))]
+            ('acc_loss', lambda: gen_acc_loss(custom)), ('estimator', lambda: gen_estimator(models, util))]
     for name, fn in gens:
         if not only or name in only:
             fn()

@@ -251,6 +251,67 @@ def test_anomaly_correlation_loss_matches_reference_function(golden_dir):
     np.testing.assert_allclose(fwd(yt, yp), g['loss_none_forward'], rtol=1e-12)
 
 
+def _estimator_cases(golden_dir):
+    g = _load(golden_dir, 'estimator.npz')
+    for key in [str(c) for c in g['cases']]:
+        t_in, t_out, interval, sol, steps, impute, first, keep_time = [int(v) for v in g[key + '/spec']]
+        yield g, key, t_in, t_out, interval, bool(sol), steps, bool(impute), bool(first), bool(keep_time)
+
+
+def test_estimator_loop_matches_reference_loop(golden_dir):
+    """oracle/estimator.py vs the reference's own TimeSeriesEstimator.predict (extensions.py:136-303) executed on a numpy
+    stand-in for xarray (make_golden.py:gen_estimator): forecast values including the NaN pattern of samples that run out
+    of data, for equal / fewer / more output time steps, insolation, impute, interval 2, keep_time_dim."""
+    from oracle import estimator as OE
+    for g, key, t_in, t_out, interval, sol, steps, impute, first, keep_time in _estimator_cases(golden_dir):
+        w = g[key + '/w']
+        fn = lambda x: np.tanh(np.einsum('nchw,co->nohw', np.asarray(x, np.float32), w)).astype(np.float32)
+        times = g['times'].astype('datetime64[s]')
+        S = g[key + '/p'].shape[0]
+        res, es, keep = OE.estimator_predict(fn, g[key + '/p'], steps, t_in, t_out, list(g[key + '/in_varlev']),
+                                             list(g[key + '/varlev']), times[:S], times[1] - times[0], g['lat'], g['lon'],
+                                             interval, sol, impute, first)
+        got = OE.estimator_series(res, steps, es, keep, keep_time, first)
+        want = g[key + '/result']
+        assert got.shape == want.shape, key
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want), err_msg=key)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6, equal_nan=True, err_msg=key)
+
+
+def test_product_estimator_host_loop_matches_reference_loop(golden_dir):
+    """dlwp_b200.model.TimeSeriesEstimator (host loop; the device loop is checked against it in tests/test_estimator_gpu.py)
+    vs the same golden: values, dimension names, f_hour / time / varlev coordinates."""
+    from dlwp_b200.model import DLWPNeuralNet, TimeSeriesEstimator
+    for g, key, t_in, t_out, interval, sol, steps, impute, first, keep_time in _estimator_cases(golden_dir):
+        w = g[key + '/w']
+        times = g['times'].astype('datetime64[s]')
+        in_vl = [v for v in g[key + '/in_varlev'] if v != 'SOL']
+
+        class Gen(object):
+            _input_sel, _output_sel = {'varlev': in_vl}, {'varlev': list(g[key + '/varlev'])}
+            _input_time_steps, _output_time_steps, _interval, _add_insolation = t_in, t_out, interval, sol
+            _n_sample = g[key + '/p'].shape[0]
+            sample_times, lat, lon = times[:g[key + '/p'].shape[0]], g['lat'], g['lon']
+            convolution_shape = g[key + '/p'].shape[1:]
+
+            def generate(self, samples, scale_and_impute=True):
+                return g[key + '/p'].copy(), g[key + '/t'].copy()
+
+        dlwp = DLWPNeuralNet(is_convolutional=True, time_dim=t_in, scaler_type=None, scale_targets=False)
+        dlwp.predict = lambda x, **kw: np.tanh(np.einsum('nchw,co->nohw', np.asarray(x, np.float32), w)).astype(np.float32)
+        est = TimeSeriesEstimator(dlwp, Gen())
+        est._device_ok = lambda: False
+        out = est.predict(steps, impute=impute, keep_time_dim=keep_time, prefer_first_times=first)
+        want = g[key + '/result']
+        got = np.asarray(out.values)
+        assert got.shape == want.shape and tuple(out.dims) == tuple(g[key + '/dims']), key
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6, equal_nan=True, err_msg=key)
+        coords = out.coords if isinstance(out.coords, dict) else {k: v.values for k, v in out.coords.items()}
+        np.testing.assert_array_equal(np.asarray(coords['f_hour']).astype('timedelta64[s]').astype(np.int64), g[key + '/f_hour'])
+        np.testing.assert_array_equal(np.asarray(coords['time']).astype('datetime64[s]').astype(np.int64), g[key + '/time'])
+        assert list(coords['varlev']) == list(g[key + '/varlev'])
+
+
 def test_insolation_matches_reference_function(golden_dir):
     """DLWP/util.py:300-352 run from the reference's source text (tests/golden/make_golden.py:gen_insolation)."""
     from oracle import estimator as OE
