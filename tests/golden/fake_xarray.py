@@ -13,7 +13,7 @@ Semantics implemented (xarray's documented behaviour for these calls):
   result is a view; array of labels: fancy indexing, a copy); `da.loc[{...}] = value` writes the selected block, a DataArray
   value being assigned by position after a check that the shapes agree.
 * `da.reindex(sample=new, method=None)`: rows are looked up by exact label; labels absent from the old index give NaN rows.
-* `da.isel(dim=slice)`.
+* `da.isel(dim=slice)`, `da.sel(dim=labels)` (= `.loc`), `da.load()` (no-op), `Dataset` with coordinate and data variables.
 """
 
 import numpy as np
@@ -80,6 +80,8 @@ class DataArray(object):
             dims = ['dim_%d' % i for i in range(self.values.ndim)]
         self.dims = tuple(dims)
         coords = [] if coords is None else coords
+        if isinstance(coords, dict):                      # xr.DataArray(data, coords={'sample': ..., ...}, dims=[...])
+            coords = [coords[d] for d in self.dims]
         if self.values.ndim and len(coords) != self.values.ndim:
             raise ValueError('one coordinate per dimension expected')
         self.coords = {}
@@ -176,6 +178,12 @@ class DataArray(object):
         coords = [new if d == dim else self.coords[d] for d in self.dims]
         return DataArray(out, coords=coords, dims=self.dims)
 
+    def sel(self, **indexers):
+        return self.loc[indexers] if indexers else self
+
+    def load(self):
+        return self
+
     def isel(self, **indexers):
         key = tuple(indexers.get(d, slice(None)) for d in self.dims)
         return self[key]
@@ -184,10 +192,16 @@ class DataArray(object):
 class Dataset(object):
     """Just the attributes of `generator.ds` the estimator reads: dims, variables, coords, item / attribute access."""
 
-    def __init__(self, coords):
+    def __init__(self, coords, **data_vars):
         self.coords = {k: DataArray(v, coords=[v], dims=[k]) for k, v in coords.items()}
         self.dims = {k: len(v) for k, v in coords.items()}
         self.variables = dict(self.coords)
+        for name, da in data_vars.items():                # e.g. predictors=DataArray(...)
+            self.variables[name] = da
+            self.__dict__[name] = da
+
+    def load(self):
+        return self
 
     def __getitem__(self, name):
         return self.coords[name]

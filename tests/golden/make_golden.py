@@ -97,7 +97,7 @@ def install_stubs():
     # keras.losses (Keras 2.2 losses.py): the mean over the LAST axis
     _mod('keras.losses', mean_absolute_error=lambda y_true, y_pred: np.mean(np.abs(y_pred - y_true), axis=-1),
          mean_squared_error=lambda y_true, y_pred: np.mean(np.square(y_pred - y_true), axis=-1))
-    _mod('keras.utils', conv_utils=None, multi_gpu_model=None)
+    _mod('keras.utils', conv_utils=None, multi_gpu_model=None, Sequence=object)
     _mod('keras.engine')
     _mod('keras.engine.base_layer', InputSpec=_Any)
     _mod('keras.models')
@@ -324,6 +324,56 @@ def gen_estimator(models, util):
     np.savez_compressed(os.path.join(HERE, 'estimator.npz'), **out)
 
 
+def gen_series_generator():
+    """The reference's OWN `SeriesDataGenerator` (DLWP/model/generators.py:323-640: __init__, generate, __getitem__, __len__,
+    the shape properties) on the xarray stand-in: predictors / targets of every sample and of one batch, with a variable
+    selection, insolation, a target sequence and interval 2.  (`np.int`, which the reference still uses, is aliased to int:
+    it left numpy in 1.24.)"""
+    import fake_xarray
+    sys.modules['xarray'] = fake_xarray
+    if not hasattr(np, 'int'):
+        np.int = int
+    gmod = load_ref('DLWP.model.generators_impl', 'DLWP/model/generators.py')
+    rng = np.random.RandomState(44)
+    names = np.array(['z/500', 't/850', 'u/300', 'v/300'])
+    nt, H, W = 15, 4, 6
+    data = rng.standard_normal((nt, 4, H, W)).astype(np.float32)
+    times = np.datetime64('2004-12-30T00:00', 'ns') + np.arange(nt) * np.timedelta64(6 * 3600 * 10 ** 9, 'ns')
+    lat, lon = np.linspace(75., -75., H), np.arange(0., 360., 60.)
+    pred = fake_xarray.DataArray(data, coords=[times, names, lat, lon], dims=['sample', 'varlev', 'lat', 'lon'])
+    ds = fake_xarray.Dataset({'sample': times, 'varlev': names, 'lat': lat, 'lon': lon}, predictors=pred)
+
+    class M(object):
+        is_convolutional, is_recurrent, impute = True, False, False
+
+        def scaler_transform(self, p, t):                 # scaler_type=None model: models.py scaler_transform is the identity
+            return p, t
+
+    out = {'data': data, 'times': times.astype('datetime64[s]').astype(np.int64), 'lat': lat, 'lon': lon, 'names': names}
+    cases = []
+    specs = [('plain', None, None, 1, 1, None, 1, False, 4),
+             ('subset_sol', ['z/500', 'u/300', 't/850'], ['t/850', 'z/500'], 2, 1, None, 1, True, 4),
+             ('sequence_interval2', ['z/500', 't/850', 'u/300', 'v/300'], ['u/300'], 2, 2, 3, 2, True, 3)]
+    for key, in_sel, out_sel, t_in, t_out, seq, interval, sol, batch in specs:
+        gen = gmod.SeriesDataGenerator(M(), ds, input_sel={'varlev': in_sel} if in_sel else None,
+                                       output_sel={'varlev': out_sel} if out_sel else None, input_time_steps=t_in,
+                                       output_time_steps=t_out, sequence=seq, interval=interval, add_insolation=sol,
+                                       batch_size=batch, shuffle=False, remove_nan=False)
+        p, t = gen.generate([], scale_and_impute=False)
+        xb, yb = gen[1]                                   # second batch (scaler: identity model below)
+        out[key + '/p'] = p
+        out[key + '/xb'] = xb
+        for k, (tt, yy) in enumerate(zip(t if seq else [t], yb if seq else [yb])):
+            out[key + '/t%d' % k], out[key + '/yb%d' % k] = tt, yy
+        out[key + '/spec'] = np.array([t_in, t_out, seq or 0, interval, int(sol), batch, gen._n_sample, len(gen)])
+        out[key + '/shapes'] = np.array(list(gen.convolution_shape) + list(gen.output_convolution_shape))
+        out[key + '/in_sel'] = np.array(in_sel if in_sel else list(names))
+        out[key + '/out_sel'] = np.array(out_sel if out_sel else list(names))
+        cases.append(key)
+    out['cases'] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, 'series_generator.npz'), **out)
+
+
 def gen_row_conv(custom):
     rng = np.random.RandomState(11)
     x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
@@ -469,7 +519,8 @@ def main():
             ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
             ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation),
-            ('acc_loss', lambda: gen_acc_loss(custom)), ('estimator', lambda: gen_estimator(models, util))]
+            ('acc_loss', lambda: gen_acc_loss(custom)), ('estimator', lambda: gen_estimator(models, util)),
+            ('series_generator', gen_series_generator)]
     for name, fn in gens:
         if not only or name in only:
             fn()

@@ -123,3 +123,27 @@ def test_device_series_generator_matches_host_assembly_and_trains():
     loss = h.history['loss']
     assert len(loss) == 3 and np.isfinite(loss).all() and loss[-1] < loss[0]
     assert isinstance(gen1[0][0], torch.Tensor)
+
+
+def test_device_series_generator_matches_reference_generator():
+    """dlwp_gather_series / DeviceSeriesGenerator vs the reference's own SeriesDataGenerator.__getitem__ and generate
+    (generators.py:529-640, executed by tests/golden/make_golden.py:gen_series_generator): batch count, the second batch
+    (predictors with the insolation channel, every target of the sequence) and all samples."""
+    import os
+    from dlwp_b200.model import DeviceSeriesGenerator
+    from tests.test_oracle_golden import series_generator_cases
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    for g, key, series, (t_in, t_out, seq, interval, sol, batch, n_sample, n_batches) in series_generator_cases(golden):
+        gen = DeviceSeriesGenerator(series, batch_size=batch, sequence=seq or None, shuffle=False)
+        assert gen._n_sample == n_sample and len(gen) == n_batches, key
+        X, ys = gen[1]
+        ys = ys if seq else [ys]
+        np.testing.assert_allclose(X.cpu().numpy(), g[key + '/xb'], rtol=0, atol=1e-6, err_msg=key)
+        for k, y in enumerate(ys):
+            np.testing.assert_array_equal(y.cpu().numpy(), g[key + '/yb%d' % k], err_msg=key)
+        full = DeviceSeriesGenerator(series, batch_size=n_sample, sequence=seq or None, shuffle=False)
+        X, ys = full[0]
+        ys = ys if seq else [ys]
+        np.testing.assert_allclose(X.cpu().numpy(), g[key + '/p'], rtol=0, atol=1e-6, err_msg=key)
+        for k, y in enumerate(ys):
+            np.testing.assert_array_equal(y.cpu().numpy(), g[key + '/t%d' % k], err_msg=key)

@@ -312,6 +312,31 @@ def test_product_estimator_host_loop_matches_reference_loop(golden_dir):
         assert list(coords['varlev']) == list(g[key + '/varlev'])
 
 
+def series_generator_cases(golden_dir):
+    """(golden, key, ArraySeriesGenerator, spec) for every case of tests/golden/series_generator.npz."""
+    from dlwp_b200.model import ArraySeriesGenerator
+    g = _load(golden_dir, 'series_generator.npz')
+    for key in [str(c) for c in g['cases']]:
+        t_in, t_out, seq, interval, sol, batch, n_sample, n_batches = [int(v) for v in g[key + '/spec']]
+        series = ArraySeriesGenerator(g['data'], g['times'].astype('datetime64[s]'), g['lat'], g['lon'], list(g['names']),
+                                      list(g[key + '/in_sel']), list(g[key + '/out_sel']), t_in, t_out, interval, bool(sol))
+        yield g, key, series, (t_in, t_out, seq, interval, sol, batch, n_sample, n_batches)
+
+
+def test_array_series_generator_matches_reference_generator(golden_dir):
+    """The reference's own SeriesDataGenerator (generators.py:323-640) run on the xarray stand-in
+    (make_golden.py:gen_series_generator) vs the in-memory ArraySeriesGenerator: predictors incl. the insolation channel
+    (float32 insolation: 1e-6), first target array, shapes and sample count (sequence = None geometry)."""
+    for g, key, series, (t_in, t_out, seq, interval, sol, batch, n_sample, n_batches) in series_generator_cases(golden_dir):
+        assert tuple(series.convolution_shape) == tuple(g[key + '/shapes'][:3])
+        assert tuple(series.output_convolution_shape) == tuple(g[key + '/shapes'][3:])
+        p, t = series.generate([])
+        if not seq:
+            assert series._n_sample == n_sample
+        np.testing.assert_allclose(p[:n_sample], g[key + '/p'], rtol=0, atol=1e-6, err_msg=key)
+        np.testing.assert_array_equal(t[:n_sample], g[key + '/t0'], err_msg=key)
+
+
 def test_insolation_matches_reference_function(golden_dir):
     """DLWP/util.py:300-352 run from the reference's source text (tests/golden/make_golden.py:gen_insolation)."""
     from oracle import estimator as OE
