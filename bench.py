@@ -11,7 +11,11 @@ section 3).  One "step" = one rollout step over the whole batch; value = B * K /
 
 * `value`      device-resident rollout (x0 and the series in HBM), one CUDA-graph launch of K steps, CUDA events.
 * `e2e`        the reference-facing call DLWPNeuralNet.predict_timeseries(numpy) -> numpy: H2D of x0, rollout, D2H of
-               every step's state, wall clock around the call.
+               every step's state, wall clock around the call.  N > 1 (latitude bands): LatBandEngine.rollout_host --
+               every rank uploads the rows of x0 it reads and receives its band of every state (dlwp_rollout_latband_host).
+* N > 1        the north-star partition: latitude bands, halo rows over NVLink peer memory (--halo nccl: grouped SendRecv),
+               --scaling weak (default: B forecasts per GPU) | strong; --parallel batch = independent forecasts per GPU.
+* --workload net_b [--precision bf16]: the skip U-Net on 12x180x360 (BASELINE.json configs[2], configs[3] with --gpus N).
 * `roofline`   the dominant kernel (conv 32->6 5x5) timed alone with CUDA events: SURVEY.md 8(d) algorithmic bytes / time
                against the measured HBM copy peak (MEASURED_PEAKS.json).
 * `cpu_baseline` / `--impl reference`: the reference's rollout loop restated in oracle/ around a torch-CPU fp32 forward
