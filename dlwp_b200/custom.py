@@ -288,3 +288,19 @@ class EarlyStoppingMin(EarlyStopping):
         if epoch < self.min_epochs:
             return
         super(EarlyStoppingMin, self).on_epoch_end(epoch, logs)
+
+
+# ==================================================================================================================== #
+# PyTorch classes (custom.py:1098-1107)
+# ==================================================================================================================== #
+
+class TorchReshape(object):
+    """`x.view(*shape)` as a layer of a DLWPTorchNN (the torch twin resolves unknown layer names here)."""
+
+    def __init__(self, shape):
+        if not isinstance(shape, tuple):
+            raise ValueError("'shape' must be a tuple of integers")
+        self.shape = shape
+
+    def __call__(self, x):
+        return x.view(*self.shape)

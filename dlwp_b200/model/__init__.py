@@ -5,11 +5,11 @@ from .generators import (ArrayDataGenerator, ArraySeriesGenerator, DataGenerator
                          SeriesDataGenerator, SmartDataGenerator)
 from .extensions import TimeSeriesEstimator  # noqa: F401,E402
 from .models import DLWPFunctional, DLWPNeuralNet  # noqa: F401,E402
+from .models_torch import DLWPTorchNN  # noqa: F401,E402
 
 _OUT_OF_SCOPE = {
     'Preprocessor': 'DLWP/model/preprocessing.py (offline data preparation, needs netCDF4/xarray)',
     'verify': 'DLWP/model/verify.py (post-processing metrics, needs xarray/pandas)',
-    'DLWPTorchNN': 'DLWP/model/models_torch.py (PyTorch twin of DLWPNeuralNet)',
 }
 
 

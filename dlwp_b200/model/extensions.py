@@ -22,6 +22,7 @@ import numpy as np
 from .. import _native as nat
 from ..util import insolation
 from .models import DLWPFunctional, DLWPNeuralNet
+from .models_torch import DLWPTorchNN
 
 
 class LabeledArray(object):
@@ -46,7 +47,7 @@ def _wrap(values, dims, coords):
 class TimeSeriesEstimator(object):
     def __init__(self, model, generator):
         """extensions.py:28-135.  `model`: DLWPNeuralNet / DLWPFunctional; `generator`: see the module docstring."""
-        if not isinstance(model, (DLWPNeuralNet, DLWPFunctional)):
+        if not isinstance(model, (DLWPNeuralNet, DLWPFunctional, DLWPTorchNN)):
             raise TypeError("'model' must be a valid instance of a DLWP model class")
         for attr in ('generate', 'convolution_shape', '_n_sample', 'sample_times', 'lat', 'lon'):
             if not hasattr(generator, attr):

@@ -70,6 +70,26 @@ class OZeroPadding2D(OPeriodicPadding2D):
         return ops.zero_pad2d(x, self.padding, self.data_format)
 
 
+class OFillPadding2D(OPeriodicPadding2D):
+    """DLWP/custom.py:309-402 (numpy only)."""
+
+    def __call__(self, x):
+        return ops.fill_pad2d(np.asarray(x), self.padding, self.data_format)
+
+
+class OTFPadding2D(OPeriodicPadding2D):
+    """DLWP/custom.py:527-599 (numpy only)."""
+
+    def __init__(self, padding=(1, 1), data_format=None, mode='CONSTANT', constant_values=0, **kwargs):
+        super(OTFPadding2D, self).__init__(padding, data_format)
+        if mode.upper() == 'CONSTANT' and constant_values != 0:
+            raise NotImplementedError('constant_values != 0')
+        self.mode = mode
+
+    def __call__(self, x):
+        return ops.tf_pad2d(np.asarray(x), self.padding, self.mode, self.data_format)
+
+
 class OConv2D(OLayer):
     """Keras Conv2D, 'valid', cross-correlation, kernel (kh,kw,Cin,Cout) -- SURVEY.md Appendix A.2."""
 
@@ -306,6 +326,8 @@ def concatenate(xs, axis=1):
 LAYER_REGISTRY = {
     'PeriodicPadding2D': OPeriodicPadding2D,
     'ZeroPadding2D': OZeroPadding2D,
+    'FillPadding2D': OFillPadding2D,
+    'TFPadding2D': OTFPadding2D,
     'Conv2D': OConv2D,
     'RowConnected2D': ORowConnected2D,
     'MaxPooling2D': OMaxPooling2D,
