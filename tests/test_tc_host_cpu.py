@@ -170,6 +170,45 @@ def test_sliding_window_units_cover_every_output_pixel_once(nat, case):
     assert worst <= per_cta + (per_cta // (hi - lo) + 2) * d * (k - 1)
 
 
+def test_sliding_window_cover_randomised_geometries(nat):
+    """Seeded sweep of the same invariant over ragged shapes the fixed cases do not hit: widths around the 128-pixel strip and
+    its pairing threshold, 1..200 rows, latitude-band windows of 2..8 ranks, 1..148 CTAs, odd batches."""
+    rng = np.random.RandomState(123)
+    tried = 0
+    while tried < 80:
+        k, d = [(3, 1), (3, 2), (5, 1)][rng.randint(3)]
+        cin = int(rng.choice([6, 8, 12, 16, 24, 32, 64]))
+        cout = int(rng.choice([6, 8, 12, 16, 32, 64]))
+        W = int(rng.choice([8, 36, 44, 60, 90, 124, 127, 128, 129, 180, 200, 256, 257, 360]))
+        H = int(rng.randint(1, 201)) if rng.rand() < 0.7 else int(rng.choice([91, 180, 181]))
+        N = int(rng.choice([1, 2, 3, 7, 16, 33, 64]))
+        sms = int(rng.choice([1, 2, 7, 64, 147, 148]))
+        desc = _desc(nat, cin, H, W, cout, k, d, N=N)
+        rc, L = _plan(nat, desc)
+        if rc != 0 or L['mode'] != 1:
+            continue                                       # geometry the sliding-window kernel does not take
+        r0 = r1 = 0
+        if H >= 16 and rng.rand() < 0.5:                   # a latitude band
+            parts = int(rng.randint(2, 9))
+            which = int(rng.randint(parts))
+            r0, r1 = which * H // parts, (which + 1) * H // parts
+            if r1 - r0 < 1:
+                continue
+        desc.row_begin, desc.row_end = r0, r1
+        cover = np.zeros((N, H, W), np.int32)
+        info = (ctypes.c_int32 * 4)()
+        rc = nat.lib().dlwp_debug_sw_cover(ctypes.byref(desc), sms, cover.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                           cover.size, info, 4)
+        case = (N, cin, H, W, cout, k, d, r0, r1, sms)
+        assert rc == 0, case
+        lo, hi = (0, H) if (r0, r1) == (0, 0) else (r0, r1)
+        assert (cover[:, lo:hi] == 1).all(), case
+        assert not cover[:, :lo].any() and not cover[:, hi:].any(), case
+        ctas, segments, worst, staged = list(info)
+        assert 1 <= ctas <= sms, case
+        tried += 1
+
+
 def _split16(x):
     """fp32 -> (hi, lo) fp16 pair with x ~= hi + lo (what pack_state_kernel and the epilogues store)."""
     hi = x.astype(np.float16)
