@@ -320,6 +320,34 @@ def gen_estimator(models, util):
                                        int(kw.get('prefer_first_times', True)), int(kw.get('keep_time_dim', False))])
         out[key + '/in_varlev'] = np.array(list(est._input_sel['varlev']))
         cases.append(key)
+    # a DLWPFunctional that predicts a sequence (_n_steps = 2): the estimator hands the whole forecast to the model's own
+    # predict_timeseries (extensions.py:204-208)
+    class Chain(object):
+        n_outputs = 2
+
+        def __init__(self, w):
+            self.w = w
+
+        def forward(self, x):
+            a = np.tanh(np.einsum('nchw,co->nohw', x, self.w))
+            return [a, np.tanh(np.einsum('nchw,co->nohw', a, self.w))]
+
+    gen = Gen(None, None, 1, 1, 1, False)
+    w = (0.5 * rng.standard_normal((3, 3))).astype(np.float32)
+    fun = models.DLWPFunctional(is_convolutional=True, is_recurrent=False, time_dim=1)
+    fun.model = _FakeKerasModel(Chain(w.astype(np.float64)))
+    fun._n_steps = 2
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        est = ext.TimeSeriesEstimator(fun, gen)
+    res = est.predict(5)
+    key = 'functional_sequence'
+    out[key + '/p'], out[key + '/t'], out[key + '/w'] = gen._p, gen._t, w
+    out[key + '/result'] = np.asarray(res.values, np.float32)
+    out[key + '/dims'] = np.array(res.dims)
+    out[key + '/f_hour'] = np.asarray(res.coords['f_hour']).astype('timedelta64[s]').astype(np.int64)
+    out[key + '/time'] = np.asarray(res.coords['time']).astype('datetime64[s]').astype(np.int64)
     out['cases'] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, 'estimator.npz'), **out)
 

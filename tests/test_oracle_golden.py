@@ -312,6 +312,43 @@ def test_product_estimator_host_loop_matches_reference_loop(golden_dir):
         assert list(coords['varlev']) == list(g[key + '/varlev'])
 
 
+def test_product_estimator_functional_sequence_matches_reference(golden_dir):
+    """extensions.py:204-208: a DLWPFunctional that predicts a sequence (_n_steps = 2) -- the estimator defers to the model's
+    own predict_timeseries; values and coordinates vs the reference's estimator + the reference's DLWPFunctional."""
+    from dlwp_b200.model import DLWPFunctional, TimeSeriesEstimator
+    g = _load(golden_dir, 'estimator.npz')
+    key = 'functional_sequence'
+    w = g[key + '/w'].astype(np.float64)
+    times = g['times'].astype('datetime64[s]')
+    S = g[key + '/p'].shape[0]
+
+    class Model(object):
+        outputs = [None, None]
+
+        def predict(self, x, **kwargs):
+            a = np.tanh(np.einsum('nchw,co->nohw', np.asarray(x, np.float64), w))
+            return [a.astype(np.float32), np.tanh(np.einsum('nchw,co->nohw', a, w)).astype(np.float32)]
+
+    class Gen(object):
+        _input_sel, _output_sel = {'varlev': list(g['names'])}, {'varlev': list(g['names'])}
+        _input_time_steps, _output_time_steps, _interval, _add_insolation = 1, 1, 1, False
+        _n_sample, sample_times, lat, lon = S, times[:S], g['lat'], g['lon']
+        convolution_shape = g[key + '/p'].shape[1:]
+
+        def generate(self, samples, scale_and_impute=True):
+            return g[key + '/p'].copy(), g[key + '/t'].copy()
+
+    fun = DLWPFunctional(is_convolutional=True, is_recurrent=False, time_dim=1)
+    fun.model, fun._n_steps = Model(), 2
+    out = TimeSeriesEstimator(fun, Gen()).predict(5)
+    got, want = np.asarray(out.values), g[key + '/result']
+    assert got.shape == want.shape and tuple(out.dims) == tuple(g[key + '/dims'])
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6, equal_nan=True)
+    coords = out.coords if isinstance(out.coords, dict) else {k: v.values for k, v in out.coords.items()}
+    np.testing.assert_array_equal(np.asarray(coords['f_hour']).astype('timedelta64[s]').astype(np.int64), g[key + '/f_hour'])
+    np.testing.assert_array_equal(np.asarray(coords['time']).astype('datetime64[s]').astype(np.int64), g[key + '/time'])
+
+
 def series_generator_cases(golden_dir):
     """(golden, key, ArraySeriesGenerator, spec) for every case of tests/golden/series_generator.npz."""
     from dlwp_b200.model import ArraySeriesGenerator
