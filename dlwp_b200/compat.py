@@ -33,5 +33,15 @@ def install(force=False):
         'keras.regularizers': keras.regularizers, 'keras.losses': keras.losses, 'keras.backend': keras.backend,
         'keras.utils': keras.utils, 'keras.optimizers': keras.optimizers,
     }
+    # every other submodule under its reference name too (`DLWP.model.extensions`, `DLWP.model.models_torch`, `keras.engine`,
+    # ...): without the alias the import system would find the file through the aliased package's __path__ and execute it
+    # a SECOND time under the new name -- duplicate classes that fail isinstance checks (and relative imports that resolve
+    # against `DLWP` instead of `dlwp_b200`)
+    import importlib
+    import pkgutil
+    for package, alias in ((model, 'DLWP.model'), (keras, 'keras')):
+        for info in pkgutil.walk_packages(package.__path__, package.__name__ + '.'):
+            sub = importlib.import_module(info.name)
+            mods.setdefault(alias + info.name[len(package.__name__):], sub)
     sys.modules.update(mods)
     return dlwp_b200

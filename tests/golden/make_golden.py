@@ -402,6 +402,30 @@ def gen_series_generator():
     np.savez_compressed(os.path.join(HERE, 'series_generator.npz'), **out)
 
 
+def gen_wrapper_pickles(models):
+    """What `DLWP.util.save_model` writes as `<name>.pkl` (util.py:143-149): the reference's wrapper objects with `.model`
+    and `.base_model` set to None, pickled by the reference's own classes -- one DLWPNeuralNet with fitted sklearn scalers,
+    one DLWPFunctional that predicts a sequence."""
+    import pickle
+    from copy import copy
+    rng = np.random.RandomState(8)
+    nn = models.DLWPNeuralNet(is_convolutional=False, is_recurrent=False, time_dim=2, scaler_type='StandardScaler',
+                              scale_targets=True, apply_same_y_scaling=False, impute_missing=False)
+    X, y = rng.standard_normal((20, 6)), 3.0 * rng.standard_normal((20, 4)) + 1.0
+    nn.scaler_fit(X, y)
+    nn._is_init_fit = True
+    fun = models.DLWPFunctional(is_convolutional=True, is_recurrent=False, time_dim=3)
+    fun._n_steps, fun.gpus = 4, 2
+    blobs = {}
+    for key, obj in (('neuralnet', nn), ('functional', fun)):
+        c = copy(obj)
+        c.model = None
+        c.base_model = None
+        blobs[key] = np.frombuffer(pickle.dumps(c, protocol=pickle.HIGHEST_PROTOCOL), np.uint8)
+    Xs, ys = nn.scaler_transform(X, y)
+    np.savez_compressed(os.path.join(HERE, 'wrapper_pickles.npz'), X=X, y=y, Xs=Xs, ys=ys, **blobs)
+
+
 def gen_row_conv(custom):
     rng = np.random.RandomState(11)
     x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
@@ -548,7 +572,7 @@ def main():
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
             ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation),
             ('acc_loss', lambda: gen_acc_loss(custom)), ('estimator', lambda: gen_estimator(models, util)),
-            ('series_generator', gen_series_generator)]
+            ('series_generator', gen_series_generator), ('wrapper_pickles', lambda: gen_wrapper_pickles(models))]
     for name, fn in gens:
         if not only or name in only:
             fn()

@@ -241,6 +241,38 @@ def test_model_pickles_after_training_state_was_attached_and_with_latitude_loss(
     assert np.isfinite(acc(a, b)).all() and acc.__name__ == 'acc_loss'
 
 
+def test_reference_pickled_wrappers_load_as_product_classes():
+    """`<name>.pkl` of DLWP.util.save_model (util.py:143-149) as written by the REFERENCE's classes
+    (tests/golden/make_golden.py:gen_wrapper_pickles): under compat.install() it unpickles into the product's classes with
+    every attribute (fitted sklearn scalers included), and every submodule alias is the SAME module object as its
+    dlwp_b200 original (no duplicate classes)."""
+    import os
+    import pickle
+    import sys
+    import dlwp_b200.compat
+    import dlwp_b200.keras.engine
+    import dlwp_b200.model
+    dlwp_b200.compat.install()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'wrapper_pickles.npz'))
+    nn = pickle.loads(bytes(g['neuralnet']))
+    assert type(nn) is dlwp_b200.model.DLWPNeuralNet
+    assert (nn.time_dim, nn.scaler_type, nn.scale_targets, nn.apply_same_y_scaling, nn.is_convolutional) == \
+        (2, 'StandardScaler', True, False, False)
+    assert nn.model is None and nn.base_model is None and nn._is_init_fit
+    Xs, ys = nn.scaler_transform(g['X'], g['y'])
+    np.testing.assert_allclose(Xs, g['Xs'], rtol=1e-12)
+    np.testing.assert_allclose(ys, g['ys'], rtol=1e-12)
+    fun = pickle.loads(bytes(g['functional']))
+    assert type(fun) is dlwp_b200.model.DLWPFunctional and (fun.time_dim, fun._n_steps, fun.gpus) == (3, 4, 2)
+    for alias, mod in (('DLWP.model.extensions', 'dlwp_b200.model.extensions'),
+                       ('DLWP.model.models_torch', 'dlwp_b200.model.models_torch'),
+                       ('DLWP.model.generators', 'dlwp_b200.model.generators'), ('keras.engine', 'dlwp_b200.keras.engine'),
+                       ('keras.saving', 'dlwp_b200.keras.saving')):
+        assert sys.modules[alias] is sys.modules[mod], alias
+    from DLWP.model.extensions import TimeSeriesEstimator
+    assert TimeSeriesEstimator is dlwp_b200.model.TimeSeriesEstimator
+
+
 def test_training_loss_recognition():
     """Which compiled losses the device training path takes (training._check_compiled): 'mse', a latitude-weighted MSE, one
     anomaly-correlation loss for all outputs (custom.py:1036-1093); anything else is refused before any GPU work."""
