@@ -110,7 +110,7 @@ def _gather_uneven(gathered, band, rank, world):
 def test_latband_rollout_with_halo_exchange_matches_single_domain(world):
     cs, n, steps = (6, 23, 16), 2, 4
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context('spawn').Manager()     # (never fork a process that already runs helper threads)
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, cs, n, steps, ret), nprocs=world, join=True)
     assert ret['err'] < 1e-6, ret['err']                 # float32 storage of float64 results between iterations
