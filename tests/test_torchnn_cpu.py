@@ -121,14 +121,15 @@ def test_build_model_validation_matches_the_reference_messages():
         good.predict_timeseries(np.zeros((1, 6, 8, 8), np.float32), 0)
 
 
-def test_torch_adam_equals_keras_adam_with_the_mapped_epsilon():
+@pytest.mark.parametrize('eps', [1e-8, 1e-3])
+def test_torch_adam_equals_keras_adam_with_the_mapped_epsilon(eps):
     """torch.optim.Adam vs the Keras 2.2 update dlwp_train_adam implements (training.py / train.cu adam_kernel), with the
     per-step epsilon `DLWPTorchNN._torch_adam_step_constants` hands to it: identical trajectories."""
     import torch
     rng = np.random.RandomState(5)
     w0 = rng.standard_normal(7)
     grads = [rng.standard_normal(7) * s for s in (1.0, 1e-3, 1e-6, 2.0, 1e-8, 0.5)]
-    lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-8
+    lr, b1, b2 = 1e-2, 0.9, 0.999
     p = torch.tensor(w0, dtype=torch.float64, requires_grad=True)
     opt = torch.optim.Adam([p], lr=lr, betas=(b1, b2), eps=eps)
     w, m, v = w0.copy(), np.zeros(7), np.zeros(7)
