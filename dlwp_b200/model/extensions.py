@@ -58,8 +58,8 @@ class TimeSeriesEstimator(object):
         self._interval = int(getattr(generator, '_interval', 1))
         times = np.asarray(generator.sample_times).astype('datetime64[s]')
         self._dt = times[1] - times[0]
-        self._input_sel = {'varlev': np.array(list(generator._input_sel['varlev']))}
-        self._output_sel = {'varlev': np.array(list(generator._output_sel['varlev']))}
+        self._input_sel = {'varlev': np.array(self._varlev_of(generator, generator._input_sel))}
+        self._output_sel = {'varlev': np.array(self._varlev_of(generator, generator._output_sel))}
         self._outputs_in_inputs = {
             'varlev': np.array([v for v in self._output_sel['varlev'] if v in self._input_sel['varlev']])}
         if self._add_insolation:
@@ -68,6 +68,17 @@ class TimeSeriesEstimator(object):
         self._output_time_steps = int(getattr(generator, '_output_time_steps', model.time_dim))
 
     # -- helpers ---------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _varlev_of(generator, sel):
+        """extensions.py:54-75: the generator's own selection, or -- when it was left empty -- every varlev of its dataset."""
+        if sel and 'varlev' in sel:
+            return [str(v) for v in sel['varlev']]
+        ds = getattr(generator, 'ds', None)
+        if sel or ds is None or 'varlev' not in ds.dims:
+            raise NotImplementedError('TimeSeriesEstimator needs a flat varlev dimension (variable / level selections are '
+                                      'not mapped here)')
+        return [str(v) for v in np.asarray(ds.coords['varlev'].values)]
+
     def _device_ok(self):
         m = self.model
         if getattr(m, 'impute', False) or getattr(m, 'scaler_type', None) is not None:

@@ -1,9 +1,17 @@
 """
-Names of `DLWP.model.generators` (reference DLWP/model/generators.py).  The reference's generators read xarray
-Datasets from netCDF -- disk-bound host code outside the rollout hot path and xarray is not
-available offline.  The classes exist so `isinstance` checks in `fit_generator` (models.py:224) and imports keep working;
-`ArrayDataGenerator` is the in-memory stand-in used by tests and benchmarks: the same Sequence protocol
-(`__len__`, `__getitem__`, `on_epoch_end`, `convolution_shape`) over numpy arrays.
+`DLWP.model.generators` (reference DLWP/model/generators.py).
+
+* `SeriesDataGenerator` -- the generator of the reference's example scripts (generators.py:323-640) -- works on any dataset
+  object that answers the handful of xarray calls it needs (`ds.predictors`, `ds.dims`, `.isel(time_step=-1)`,
+  `.sel(**selection)`, `.values`, the `sample` / `lat` / `lon` coordinates): a real `xarray.Dataset` where xarray is
+  installed (it is not in this image nor on the GPU box) or the numpy stand-in the golden generator uses.  Batches are
+  assembled in memory exactly like the reference's `generate`; `as_array_series()` / `to_device()` hand the same data to the
+  GPU-resident assembly (`DeviceSeriesGenerator`, `dlwp_gather_series`).  Pinned against the reference's own class run on
+  the stand-in (tests/golden/series_generator.npz).
+* `DataGenerator` / `SmartDataGenerator` (the latter deprecated in the reference itself) read netCDF-backed predictor /
+  target pairs -- disk-bound host code outside the rollout path; the names exist for `isinstance`
+  checks and imports and raise on construction.
+* `ArrayDataGenerator` / `ArraySeriesGenerator`: in-memory stand-ins over numpy arrays (tests, benchmarks, TimeSeriesEstimator).
 """
 
 import numpy as np
@@ -13,16 +21,210 @@ from ..keras.utils import Sequence
 
 class DataGenerator(Sequence):
     def __init__(self, *args, **kwargs):
-        raise NotImplementedError('DLWP.model.DataGenerator needs xarray/netCDF4 (not available offline); use '
-                                  'dlwp_b200.model.ArrayDataGenerator for in-memory arrays')
+        raise NotImplementedError('DLWP.model.%s reads netCDF-backed predictor/target pairs (outside the rollout path); use '
+                                  'SeriesDataGenerator, or dlwp_b200.model.ArrayDataGenerator for in-memory arrays'
+                                  % type(self).__name__)
 
 
 class SmartDataGenerator(DataGenerator):
     pass
 
 
-class SeriesDataGenerator(DataGenerator):
-    pass
+def _drop_nan_samples(p, t):
+    """DLWP/util.py:238-268 with the defaults: samples (rows) with a NaN in the predictors or the targets are removed."""
+    bad = np.isnan(p.reshape(p.shape[0], -1)).any(axis=1) | np.isnan(t.reshape(t.shape[0], -1)).any(axis=1)
+    return (p[~bad], t[~bad]) if bad.any() else (p, t)
+
+
+class SeriesDataGenerator(Sequence):
+    """
+    generators.py:323-640: samples are windows of ONE continuous series -- `input_time_steps` consecutive fields as
+    predictors, the `output_time_steps` fields that follow `interval - 1` skipped steps as targets (`sequence` such target
+    arrays in a row for models that predict a sequence), an optional insolation channel per input time step.  Same
+    constructor arguments, attributes (`_n_sample`, `_input_sel`, `_add_insolation`, ...), shape properties and Sequence
+    protocol as the reference; `load` is accepted and ignored (the selected variables are held as numpy arrays).
+    """
+
+    def __init__(self, model, ds, input_sel=None, output_sel=None, input_time_steps=1, output_time_steps=1, sequence=None,
+                 interval=1, add_insolation=False, batch_size=32, shuffle=False, remove_nan=True, load='required'):
+        self.model = model
+        if not hasattr(ds, 'predictors'):
+            raise ValueError("dataset must have 'predictors' variable")
+        for name, value in (('input_time_steps', input_time_steps), ('output_time_steps', output_time_steps),
+                            ('batch_size', batch_size), ('interval', interval)):
+            assert int(value) > 0, name
+        if sequence is not None:
+            assert int(sequence) > 0
+        if load and load not in ('full', 'required', 'minimal') and not isinstance(load, bool):
+            raise ValueError("'load' must be one of 'full', 'required', or 'minimal'")
+        self.ds = ds
+        self._batch_size, self._shuffle, self._remove_nan = batch_size, shuffle, remove_nan
+        self._is_convolutional = model.is_convolutional
+        self._keep_time_axis = model.is_recurrent
+        self._impute_missing = model.impute
+        self._sequence = sequence
+        self._input_time_steps, self._output_time_steps, self._interval = input_time_steps, output_time_steps, interval
+        self._n_sample = ds.dims['sample'] - input_time_steps - output_time_steps * (sequence or 1) + 2 - interval
+        # ('time_step' datasets: the sample coordinate dates the LAST time step, generators.py:391-394)
+        self.da = ds.predictors.isel(time_step=-1) if 'time_step' in ds.dims else ds.predictors
+        self._input_sel, self._output_sel = input_sel or {}, output_sel or {}
+        self.input_da = self.da.sel(**self._input_sel)
+        self.output_da = self.da.sel(**self._output_sel)
+        self._in = np.asarray(self.input_da.values)
+        self._out = np.asarray(self.output_da.values)
+        self._add_insolation = int(add_insolation)
+        self._sol = None
+        if add_insolation:
+            from ..util import insolation
+            self._sol = insolation(np.asarray(self.da.sample.values), np.asarray(self.da.lat.values, np.float64),
+                                   np.asarray(self.da.lon.values, np.float64))
+        self._indices = []
+        self.on_epoch_end()
+
+    # -- metadata the TimeSeriesEstimator of this package reads ------------------------------------------------------------------
+    @property
+    def sample_times(self):
+        return np.asarray(self.ds.sample.values).astype('datetime64[s]')[:self._n_sample]
+
+    @property
+    def lat(self):
+        return np.asarray(self.ds.lat.values, np.float64)
+
+    @property
+    def lon(self):
+        return np.asarray(self.ds.lon.values, np.float64)
+
+    # -- shapes (generators.py:425-522) ----------------------------------------------------------------------------------------
+    def _shapes(self, steps, field_shape, sol):
+        """(original, features, dense, convolution) shapes of `steps` stacked fields of shape `field_shape`."""
+        full = (steps,) + tuple(field_shape)
+        grid = full[-2:]
+        n = int(np.prod(full)) + int(np.prod(grid)) * steps * sol
+        dense = (steps, n // steps) if self._keep_time_axis else (n,)
+        if self._keep_time_axis:
+            conv = (steps, int(np.prod(full[1:-2])) + sol) + grid
+        else:
+            conv = (int(np.prod(full[:-2])) + steps * sol,) + grid
+        return full, n, dense, conv
+
+    @property
+    def shape(self):
+        return self._shapes(self._input_time_steps, self._in.shape[1:], 0)[0]
+
+    @property
+    def n_features(self):
+        return self._shapes(self._input_time_steps, self._in.shape[1:], self._add_insolation)[1]
+
+    @property
+    def dense_shape(self):
+        return self._shapes(self._input_time_steps, self._in.shape[1:], self._add_insolation)[2]
+
+    @property
+    def convolution_shape(self):
+        return self._shapes(self._input_time_steps, self._in.shape[1:], self._add_insolation)[3]
+
+    @property
+    def output_shape(self):
+        return self._shapes(self._output_time_steps, self._out.shape[1:], 0)[0]
+
+    @property
+    def output_n_features(self):
+        return self._shapes(self._output_time_steps, self._out.shape[1:], 0)[1]
+
+    @property
+    def output_dense_shape(self):
+        return self._shapes(self._output_time_steps, self._out.shape[1:], 0)[2]
+
+    @property
+    def output_convolution_shape(self):
+        return self._shapes(self._output_time_steps, self._out.shape[1:], 0)[3]
+
+    def _as_2d(self, which):
+        keep, self._keep_time_axis = self._keep_time_axis, False
+        try:
+            return tuple(getattr(self, which))
+        finally:
+            self._keep_time_axis = keep
+
+    @property
+    def shape_2d(self):
+        return self._as_2d('convolution_shape')
+
+    @property
+    def output_shape_2d(self):
+        return self._as_2d('output_convolution_shape')
+
+    # -- batches (generators.py:524-640) -----------------------------------------------------------------------------------------
+    def on_epoch_end(self):
+        self._indices = np.arange(self._n_sample)
+        if self._shuffle:
+            np.random.shuffle(self._indices)
+
+    @staticmethod
+    def _windows(series, samples, first, steps):
+        """(len(samples), steps, ...): `steps` consecutive fields starting `first` after each sample index."""
+        return np.stack([series[samples + first + n] for n in range(steps)], axis=1)
+
+    def _finish(self, p, t, scale_and_impute):
+        if self._remove_nan:
+            p, t = _drop_nan_samples(p, t)
+        if scale_and_impute:
+            if self._impute_missing:
+                p, t = self.model.imputer_transform(p, t)
+            p, t = self.model.scaler_transform(p, t)
+        if self._is_convolutional:
+            p = p.reshape((p.shape[0],) + tuple(self.convolution_shape))
+            t = t.reshape((t.shape[0],) + tuple(self.output_convolution_shape))
+        elif self._keep_time_axis:
+            p = p.reshape((p.shape[0],) + tuple(self.dense_shape))
+            t = t.reshape((t.shape[0],) + tuple(self.output_dense_shape))
+        return p, t
+
+    def generate(self, samples, scale_and_impute=True):
+        samples = np.arange(self._n_sample) if len(samples) == 0 else np.array(samples, dtype=np.int64)
+        ti, to = self._input_time_steps, self._output_time_steps
+        p = self._windows(self._in, samples, 0, ti)
+        if self._sol is not None:                      # the insolation channel goes last within every input time step
+            sol = self._windows(self._sol, samples, 0, ti)
+            p = np.concatenate([p.reshape((len(samples), ti, -1) + sol.shape[-2:]), sol[:, :, None]], axis=2)
+        p = p.reshape((len(samples), -1))
+        first = ti + self._interval - 1
+        if self._sequence is None:
+            t = self._windows(self._out, samples, first, to).reshape((len(samples), -1))
+            return self._finish(p, t, scale_and_impute)
+        targets = []
+        for s in range(self._sequence):                # (like the reference, the predictors pass through _finish every time)
+            t = self._windows(self._out, samples, first + to * s, to).reshape((len(samples), -1))
+            p, t = self._finish(p.reshape((p.shape[0], -1)), t, scale_and_impute)
+            targets.append(t)
+        return p, targets
+
+    def __len__(self):
+        return int(np.ceil(self._n_sample / self._batch_size))
+
+    def __getitem__(self, index):
+        if int(index) < 0:
+            index = len(self) + index
+        if index > len(self):
+            raise IndexError
+        return self.generate(self._indices[index * self._batch_size:(index + 1) * self._batch_size])
+
+    # -- hand-over to the GPU-resident assembly --------------------------------------------------------------------------------
+    def as_array_series(self):
+        """The same series as an `ArraySeriesGenerator` ('varlev' datasets: fields of shape (varlev, lat, lon))."""
+        if 'varlev' not in self.ds.dims or self._in.ndim != 4 or set(self._input_sel) - {'varlev'} or \
+                set(self._output_sel) - {'varlev'}:
+            raise NotImplementedError('only datasets with a flat varlev dimension map onto ArraySeriesGenerator')
+        names = [str(v) for v in np.asarray(self.da.varlev.values)]
+        return ArraySeriesGenerator(np.asarray(self.da.values, np.float32), np.asarray(self.da.sample.values), self.lat,
+                                    self.lon, names, [str(v) for v in self._input_sel.get('varlev', names)],
+                                    [str(v) for v in self._output_sel.get('varlev', names)], self._input_time_steps,
+                                    self._output_time_steps, self._interval, bool(self._add_insolation))
+
+    def to_device(self, seed=0):
+        """`DeviceSeriesGenerator` over the same series: batches gathered on the GPU, CUDA tensors for fit_generator."""
+        return DeviceSeriesGenerator(self.as_array_series(), batch_size=self._batch_size, sequence=self._sequence,
+                                     shuffle=self._shuffle, seed=seed)
 
 
 class ArrayDataGenerator(Sequence):

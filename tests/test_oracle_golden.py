@@ -374,6 +374,53 @@ def test_array_series_generator_matches_reference_generator(golden_dir):
         np.testing.assert_array_equal(t[:n_sample], g[key + '/t0'], err_msg=key)
 
 
+def test_product_series_data_generator_matches_reference_generator(golden_dir):
+    """dlwp_b200.model.SeriesDataGenerator on the xarray stand-in vs the reference's own class on the same dataset
+    (generators.py:323-640 -> series_generator.npz): sample count, batch count, every shape property, all samples, one batch,
+    every target of a sequence; `as_array_series()` hands the same series to the GPU assembly; and the TimeSeriesEstimator
+    accepts it as its generator."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import fake_xarray
+    from dlwp_b200.model import DLWPNeuralNet, SeriesDataGenerator, TimeSeriesEstimator
+    g = _load(golden_dir, 'series_generator.npz')
+    times = g['times'].astype('datetime64[s]').astype('datetime64[ns]')
+    pred = fake_xarray.DataArray(g['data'], coords=[times, g['names'], g['lat'], g['lon']],
+                                 dims=['sample', 'varlev', 'lat', 'lon'])
+    ds = fake_xarray.Dataset({'sample': times, 'varlev': g['names'], 'lat': g['lat'], 'lon': g['lon']}, predictors=pred)
+    model = DLWPNeuralNet(is_convolutional=True, is_recurrent=False, time_dim=1, scaler_type=None, scale_targets=False)
+    for key in [str(c) for c in g['cases']]:
+        t_in, t_out, seq, interval, sol, batch, n_sample, n_batches = [int(v) for v in g[key + '/spec']]
+        plain = key == 'plain'
+        gen = SeriesDataGenerator(model, ds, input_sel=None if plain else {'varlev': list(g[key + '/in_sel'])},
+                                  output_sel=None if plain else {'varlev': list(g[key + '/out_sel'])},
+                                  input_time_steps=t_in, output_time_steps=t_out, sequence=seq or None, interval=interval,
+                                  add_insolation=bool(sol), batch_size=batch, shuffle=False, remove_nan=False)
+        assert (gen._n_sample, len(gen)) == (n_sample, n_batches), key
+        assert tuple(gen.convolution_shape) + tuple(gen.output_convolution_shape) == tuple(g[key + '/shapes']), key
+        p, t = gen.generate([], scale_and_impute=False)
+        xb, yb = gen[1]
+        np.testing.assert_allclose(p, g[key + '/p'], rtol=0, atol=1e-6, err_msg=key)
+        np.testing.assert_allclose(xb, g[key + '/xb'], rtol=0, atol=1e-6, err_msg=key)
+        for k, (tt, yy) in enumerate(zip(t if seq else [t], yb if seq else [yb])):
+            np.testing.assert_array_equal(tt, g[key + '/t%d' % k], err_msg=key)
+            np.testing.assert_array_equal(yy, g[key + '/yb%d' % k], err_msg=key)
+        arr = gen.as_array_series()
+        np.testing.assert_allclose(arr.generate([])[0][:n_sample], g[key + '/p'], rtol=0, atol=1e-6, err_msg=key)
+        if not seq:
+            est = TimeSeriesEstimator(model, gen)
+            assert list(est._output_sel['varlev']) == [str(v) for v in g[key + '/out_sel']]
+            assert est._input_time_steps == t_in and len(est.generator.sample_times) == n_sample
+    # recurrent models keep the time axis (generators.py:451-461)
+    rec = DLWPNeuralNet(is_convolutional=True, is_recurrent=True, time_dim=2, scaler_type=None, scale_targets=False)
+    gen = SeriesDataGenerator(rec, ds, input_time_steps=2, output_time_steps=2, add_insolation=True, batch_size=5)
+    assert gen.convolution_shape == (2, 5, 4, 6) and gen.output_convolution_shape == (2, 4, 4, 6)
+    assert gen.shape_2d == (10, 4, 6) and gen.output_shape_2d == (8, 4, 6) and gen.shape == (2, 4, 4, 6)
+    assert gen.n_features == 2 * 5 * 24 and gen.dense_shape == (2, 5 * 24) and gen[0][0].shape == (5, 2, 5, 4, 6)
+    with pytest.raises(ValueError):
+        SeriesDataGenerator(rec, object())
+
+
 def test_insolation_matches_reference_function(golden_dir):
     """DLWP/util.py:300-352 run from the reference's source text (tests/golden/make_golden.py:gen_insolation)."""
     from oracle import estimator as OE
