@@ -402,3 +402,12 @@ def test_time_series_estimator_host_loop_and_coordinates():
     assert list(coords['f_hour']) == [np.timedelta64(6 * k, 'h') for k in (1, 2, 3, 4)]
     assert coords['time'][0] == times[1]                                       # the last input time of sample 0
     assert list(coords['varlev']) == ['z/500', 't/850']
+
+
+def test_host_cpu_binding_is_a_no_op_without_a_gpu():
+    """parallel.bind_host_near_gpu is an optimisation for one-process-per-GPU runs: without CUDA / NVML it changes nothing."""
+    import os
+    from dlwp_b200.parallel import bind_host_near_gpu
+    before = os.sched_getaffinity(0)
+    assert bind_host_near_gpu(0) == 0
+    assert os.sched_getaffinity(0) == before
