@@ -68,6 +68,17 @@ class _StubZeroPadding3D(_StubZeroPadding2D):
         super(_StubZeroPadding3D, self).__init__((padding,) * 3 if isinstance(padding, int) else padding, data_format)
 
 
+class _Assignable(np.ndarray):
+    """K.zeros(...) with an eager `.assign` (see install_stubs)."""
+
+    def __new__(cls, shape):
+        return np.zeros(shape).view(cls)
+
+    def assign(self, value):
+        self[...] = value
+        return self
+
+
 class _Any(object):
     def __init__(self, *a, **k):
         pass
@@ -83,12 +94,18 @@ def install_stubs():
              backend=lambda: 'numpy',
              concatenate=lambda xs, axis=-1: np.concatenate(xs, axis=axis),
              stack=lambda xs, axis=0: np.stack(xs, axis=axis),
-             ones=np.ones, zeros=np.zeros,
              normalize_data_format=lambda v: 'channels_last' if v is None else v,
              conv2d=_np_conv2d,
              # the reductions / pointwise ops the loss functions of custom.py:994-1088 use
              mean=lambda x, axis=None: np.mean(x, axis=tuple(axis) if isinstance(axis, list) else axis),
-             sqrt=np.sqrt, square=np.square, abs=np.abs, variable=lambda v, name=None: np.asarray(v))
+             sqrt=np.sqrt, square=np.square, abs=np.abs, variable=lambda v, name=None: np.asarray(v),
+             # latitude_weighted_loss (custom.py:956-991); `zeros` returns an array whose `assign` stores eagerly (TF2 / the
+             # documented intent -- under graph-mode TF1 the assign op of custom.py:973 is never run)
+             cos=np.cos, sin=np.sin, pow=np.power, cast_to_floatx=lambda v: np.asarray(v, np.float32),
+             expand_dims=lambda x, axis=-1: np.expand_dims(x, axis),
+             repeat_elements=lambda x, rep, axis: np.repeat(x, rep, axis=axis))
+    K.zeros = lambda shape, **kw: _Assignable(shape)
+    K.ones = np.ones
     _mod('keras', backend=K)
     _mod('keras.callbacks', Callback=_Any, EarlyStopping=_Any)
     _mod('keras.layers', Lambda=_Any, Layer=_Any)
@@ -426,6 +443,22 @@ def gen_wrapper_pickles(models):
     np.savez_compressed(os.path.join(HERE, 'wrapper_pickles.npz'), X=X, y=y, Xs=Xs, ys=ys, **blobs)
 
 
+def gen_lat_loss(custom):
+    """latitude_weighted_loss (custom.py:956-991) with both weightings on a (C, H, W) output, and without latitudes."""
+    rng = np.random.RandomState(17)
+    lats = np.linspace(87.5, -87.5, 8)
+    shape = (3, 8, 10)
+    y_true = rng.standard_normal((4,) + shape).astype(np.float32)
+    y_pred = (y_true + 0.3 * rng.standard_normal((4,) + shape)).astype(np.float32)
+    out = {'lats': lats, 'y_true': y_true, 'y_pred': y_pred}
+    mse = sys.modules['keras.losses'].mean_squared_error
+    for weighting in ('cosine', 'midlatitude'):
+        fn = custom.latitude_weighted_loss(mse, lats, shape, axis=-2, weighting=weighting)
+        out['loss_' + weighting] = np.asarray(fn(y_true, y_pred), np.float64)
+    out['loss_none'] = np.asarray(custom.latitude_weighted_loss(mse, None, shape)(y_true, y_pred), np.float64)
+    np.savez_compressed(os.path.join(HERE, 'lat_loss.npz'), **out)
+
+
 def gen_row_conv(custom):
     rng = np.random.RandomState(11)
     x = rng.standard_normal((2, 4, 9, 12)).astype(np.float64)
@@ -571,7 +604,7 @@ def main():
             ('neuralnet', lambda: gen_rollout_neuralnet(models)), ('functional', lambda: gen_rollout_functional(models)),
             ('torchnn', lambda: gen_torchnn(models_torch)), ('padding3d', lambda: gen_padding_3d_and_fill(custom)),
             ('recurrent', lambda: gen_rollout_recurrent(models)), ('insolation', gen_insolation),
-            ('acc_loss', lambda: gen_acc_loss(custom)), ('estimator', lambda: gen_estimator(models, util)),
+            ('acc_loss', lambda: gen_acc_loss(custom)), ('lat_loss', lambda: gen_lat_loss(custom)), ('estimator', lambda: gen_estimator(models, util)),
             ('series_generator', gen_series_generator), ('wrapper_pickles', lambda: gen_wrapper_pickles(models))]
     for name, fn in gens:
         if not only or name in only:

@@ -232,6 +232,21 @@ def test_conv_lstm_first_step_and_gate_algebra():
     np.testing.assert_allclose(y0, OO.hard_sigmoid(z2[-1][:, 6:]) * np.tanh(cst), atol=1e-14)
 
 
+def test_latitude_weighted_loss_matches_reference_function(golden_dir):
+    """custom.py:956-991 executed from the reference module with an eagerly assigning `K.zeros` (the documented intent; see
+    DESIGN.md section 7 on graph-mode TF1): cosine and mid-latitude weights broadcast over (H, W), and the no-latitude case.
+    The (H, W) weight map the training kernel uses (`training._loss_weight_map`) comes from the same object."""
+    from dlwp_b200.custom import latitude_weighted_loss
+    from dlwp_b200.keras.losses import mean_squared_error
+    g = _load(golden_dir, 'lat_loss.npz')
+    for weighting in ('cosine', 'midlatitude'):
+        fn = latitude_weighted_loss(mean_squared_error, g['lats'], (3, 8, 10), axis=-2, weighting=weighting)
+        np.testing.assert_allclose(fn(g['y_true'], g['y_pred']), g['loss_' + weighting], rtol=0, atol=2e-7)
+        assert np.asarray(fn.weights).shape == (8, 10)
+    fn = latitude_weighted_loss(mean_squared_error, None, (3, 8, 10))
+    np.testing.assert_allclose(fn(g['y_true'], g['y_pred']), g['loss_none'], rtol=0, atol=2e-7)
+
+
 def test_anomaly_correlation_loss_matches_reference_function(golden_dir):
     """DLWP/custom.py:994-1088 executed from the reference module on a numpy backend (make_golden.py:gen_acc_loss): the
     product's host-side loss objects reproduce it for every regularize_mean, with and without a climatology.  The device
