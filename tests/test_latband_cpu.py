@@ -106,6 +106,73 @@ def _gather_uneven(gathered, band, rank, world):
         gathered[r].copy_(t) if r != rank else gathered[r].copy_(band)
 
 
+def _simulate_row_validity(low, planner, nat):
+    """Execute the plan symbolically for one rank: valid[buffer][channel, row] starts true on the input rows the planner asks
+    for (`need_in`) and becomes true where an op writes; every destination row an op computes must find ALL the source rows
+    its definition reads (pad / dilation / pool / upsample maps written out per row, not the planner's interval arithmetic)
+    valid or outside [0, H) (latitude padding).  Returns valid[] at the end."""
+    bufs = low.buffers
+    valid = [np.zeros((b['C'], b['H']), bool) for b in bufs]
+    in_buf = [i for i, b in enumerate(bufs) if b['kind'] == nat.BUF_INPUT][0]
+    valid[in_buf][:, planner.need_in[0]:planner.need_in[1]] = True
+    for op, win in zip(low.ops, planner.windows):
+        if win is None:
+            continue
+        src, dst = valid[op['src']], valid[op['dst']]
+        Hs = bufs[op['src']]['H']
+        ch = slice(op['src_c0'], op['src_c0'] + op['src_c'])
+        kind = op['kind']
+
+        def rows_read(y):
+            if kind == nat.OP_CONV:
+                rows = [y - op['pad_t'] + op['dil_h'] * i for i in range(op['kh'])]     # rows of the (pre-op'ed) source
+                Hp = Hs // 2 if op['pre_op'] == 1 else (Hs * 2 if op['pre_op'] == 2 else Hs)
+                rows = [r for r in rows if 0 <= r < Hp]                                  # others are zero padding
+                if op['pre_op'] == 1:
+                    return [q for r in rows for q in (2 * r, 2 * r + 1)]
+                if op['pre_op'] == 2:
+                    return [r // 2 for r in rows]
+                return rows
+            if kind == nat.OP_PAD:
+                return [r for r in [y - op['pad_t']] if 0 <= r < Hs]
+            if kind == nat.OP_MAXPOOL:
+                return [2 * y, 2 * y + 1]
+            if kind == nat.OP_UPSAMPLE:
+                return [y // 2]
+            return [y]
+
+        for y in range(win[0], win[1]):
+            for r in rows_read(y):
+                assert src[ch, r].all(), (op, win, y, r)
+        out_c = op['Cout'] if kind == nat.OP_CONV else op['src_c']
+        dst[op['dst_c0']:op['dst_c0'] + out_c, win[0]:win[1]] = True
+    return valid
+
+
+@pytest.mark.parametrize('world', [1, 2, 3, 4, 5, 8])
+def test_band_windows_cover_every_row_their_consumers_read(world):
+    """Net A (91 rows) and the skip U-Net (two 2x poolings, upsamplings, skip concatenations; one and two unrolled
+    applications): for every rank the row windows suffice, the outputs hold the whole band, and the bands tile [0, H)."""
+    from dlwp_b200 import _native as nat
+    from dlwp_b200.engine import Lowering
+    from dlwp_b200.parallel import make_planners
+    from tests.helpers import build_functional_pair
+    cases = [(_net_a((6, 91, 180))[0], 91)]
+    for steps in (1, 2):
+        dlwp, _ = build_functional_pair((12, 180, 36), skip=True, integration_steps=steps)
+        cases.append((Lowering(dlwp.model), 180))
+    for low, H in cases:
+        planners = make_planners(low.ops, low.buffers, H, world)
+        assert [p.band for p in planners][0][0] == 0 and planners[-1].band[1] == H
+        assert all(a.band[1] == b.band[0] for a, b in zip(planners, planners[1:]))
+        for p in planners:
+            valid = _simulate_row_validity(low, p, nat)
+            for i, b in enumerate(low.buffers):
+                if b['kind'] == nat.BUF_OUTPUT:
+                    assert valid[i][:, p.band[0]:p.band[1]].all()
+            assert p.halo[0] >= 0 and p.halo[1] >= 0
+
+
 @pytest.mark.parametrize('world', [2, 3])
 def test_latband_rollout_with_halo_exchange_matches_single_domain(world):
     cs, n, steps = (6, 23, 16), 2, 4
